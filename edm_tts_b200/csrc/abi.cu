@@ -1,0 +1,764 @@
+// C ABI of libedm_s2a.so: stateless operators + the S2A decoder context. See include/edm_s2a.h for the contract.
+// Host code here only validates arguments, builds TMA descriptors and enqueues kernels on the caller's stream.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/edm_s2a.h"
+#include "attention.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "rvq.cuh"
+
+using namespace edm;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define EDM_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess) return fail(EDM_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__));    \
+  } while (0)
+#define EDM_LAUNCH_CHECK(name)                                                                       \
+  do {                                                                                               \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                              \
+    cudaError_t e__ = cudaGetLastError();                                                            \
+    if (e__ != cudaSuccess) return fail(EDM_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+int check_arch() {
+  static int cached = 1;  // 1 = unknown
+  if (cached != 1) return cached;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cached = fail(EDM_ERR_CUDA, "no CUDA device");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return cached = fail(EDM_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return cached = fail(EDM_ERR_ARCH, "device sm_%d%d is not sm_100: this library has no fallback path", prop.major, prop.minor);
+  return cached = 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------- TMA descriptors
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, cols] with row pitch ld (elements); box = 64 columns (128 B, swizzle-128B) x box_rows
+int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (enc == nullptr) return fail(EDM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0) return fail(EDM_ERR_INVALID, "TMA operand must be 16-byte aligned (ptr %p, ld %llu)", ptr, (unsigned long long)ld);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EDM_ERR_CUDA, "cuTensorMapEncodeTiled(2d rows=%llu cols=%llu ld=%llu) failed: %d", (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, (int)r);
+  return 0;
+}
+// bf16 [B, N, cols]: box = 64 cols x 128 rows x 1 batch; rows past N are zero-filled instead of reading the next sequence
+int make_tmap_3d(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t N, uint64_t cols) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (enc == nullptr) return fail(EDM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {cols, N, B};
+  cuuint64_t strides[2] = {cols * 2, N * cols * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EDM_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- launch helpers
+template <int EPI>
+int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / kGemmBN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_bf16_tn_kernel<EPI><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ma, mb, p);
+  EDM_LAUNCH_CHECK("gemm_bf16_tn");
+  return 0;
+}
+int launch_gemm(int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+  if (p.M <= 0 || p.N % kGemmBN != 0 || p.K % kGemmBK != 0 || p.K <= 0) return fail(EDM_ERR_INVALID, "gemm shape M=%d N=%d K=%d unsupported (N %% 256, K %% 64)", p.M, p.N, p.K);
+  switch (epi) {
+    case EPI_BF16: return launch_gemm_t<EPI_BF16>(ma, mb, p, st);
+    case EPI_SWISH_BF16: return launch_gemm_t<EPI_SWISH_BF16>(ma, mb, p, st);
+    case EPI_QKV_ROPE: return launch_gemm_t<EPI_QKV_ROPE>(ma, mb, p, st);
+    case EPI_RESID_F32: return launch_gemm_t<EPI_RESID_F32>(ma, mb, p, st);
+    case EPI_F32: return launch_gemm_t<EPI_F32>(ma, mb, p, st);
+  }
+  return fail(EDM_ERR_INVALID, "unknown epilogue %d", epi);
+}
+
+int launch_attention(const CUtensorMap& mqkv, int B, int N, int H, void* out, uint32_t lbo, uint32_t sbo, uint32_t kstep, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    EDM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    attr_set = true;
+  }
+  AttnParams p;
+  p.B = B; p.N = N; p.H = H;
+  p.q_col0 = 0; p.k_col0 = H * 64; p.v_col0 = 2 * H * 64;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = static_cast<long long>(H) * 64;
+  p.scale_log2e = 0.125f * 1.4426950408889634f;
+  p.v_lbo = lbo; p.v_sbo = sbo; p.v_kstep = kstep;
+  dim3 grid((N + 127) / 128, H, B);
+  attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, st>>>(mqkv, p);
+  EDM_LAUNCH_CHECK("attention_fwd");
+  return 0;
+}
+
+int launch_ln(const LnParams& p, cudaStream_t st) {
+  if (p.rows <= 0) return 0;
+  layernorm_kernel<<<(p.rows + 7) / 8, 256, 0, st>>>(p);
+  EDM_LAUNCH_CHECK("layernorm");
+  return 0;
+}
+
+int launch_sample(const SampleParams& p, cudaStream_t st) {
+  if (p.rows <= 0) return 0;
+  sample_kernel<<<(p.rows + 7) / 8, 256, 0, st>>>(p);
+  EDM_LAUNCH_CHECK("sample");
+  return 0;
+}
+
+__global__ void fill_u8_kernel(uint8_t* p, long long n, uint8_t v) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void assemble_codes_kernel(const int* coarse, int n_coarse, const int* fine, int n_fine, long long* out, int B, int T) {
+  const int Q = n_coarse + n_fine;
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * Q * T) return;
+  const int t = static_cast<int>(i % T);
+  const int q = static_cast<int>((i / T) % Q);
+  const int b = static_cast<int>(i / (static_cast<long long>(T) * Q));
+  out[i] = q < n_coarse ? coarse[(static_cast<long long>(b) * 4 + q) * T + t] : fine[(static_cast<long long>(b) * n_fine + (q - n_coarse)) * T + t];
+}
+
+}  // namespace
+
+// ================================================================================================ stateless ops
+extern "C" int edm_abi_version(void) { return EDM_ABI_VERSION; }
+extern "C" const char* edm_last_error(void) { return g_err; }
+extern "C" unsigned long long edm_launch_count(void) { return g_launches.load(); }
+
+extern "C" int edm_gemm_bf16(const void* a, long long lda, const void* b, long long ldb, int M, int N, int K, int epilogue,
+                             const float* bias, void* out, long long ldo, float scale, const float* rope_cos,
+                             const float* rope_sin, int seq_len, int rope_cols, void* stream) {
+  if (int rc = check_arch()) return rc;
+  CUtensorMap ma, mb;
+  if (int rc = make_tmap_2d(&ma, a, M, K, lda, kGemmBM)) return rc;
+  if (int rc = make_tmap_2d(&mb, b, N, K, ldb, kGemmBN)) return rc;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.a_k_offset = 0; p.b_row_offset = 0;
+  p.bias = bias; p.out = out; p.ldo = ldo; p.scale = scale;
+  p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.seq_len = seq_len > 0 ? seq_len : 1; p.rope_cols = rope_cols;
+  if (epilogue == EPI_QKV_ROPE && (rope_cos == nullptr || rope_sin == nullptr)) return fail(EDM_ERR_INVALID, "rope tables required");
+  return launch_gemm(epilogue, ma, mb, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int edm_attention_dbg(const void* qkv, int B, int N, int H, void* out, unsigned v_lbo, unsigned v_sbo,
+                                 unsigned v_kstep, void* stream) {
+  if (int rc = check_arch()) return rc;
+  if (B <= 0 || N <= 0 || H <= 0) return fail(EDM_ERR_INVALID, "attention shape");
+  CUtensorMap m;
+  if (int rc = make_tmap_3d(&m, qkv, B, N, 3ull * H * 64)) return rc;
+  return launch_attention(m, B, N, H, out, v_lbo, v_sbo, v_kstep, static_cast<cudaStream_t>(stream));
+}
+extern "C" int edm_attention(const void* qkv, int B, int N, int H, void* out, void* stream) {
+  return edm_attention_dbg(qkv, B, N, H, out, 1024, 1024, 2048, stream);
+}
+
+extern "C" int edm_layernorm(const void* in, int in_is_bf16, int rows, const float* w1, const float* b1, const float* w2,
+                             const float* b2, float* y_out, void* z_out, int seq_len, int z_skip, float eps, void* stream) {
+  if (int rc = check_arch()) return rc;
+  LnParams p;
+  p.in = in; p.in_is_bf16 = in_is_bf16; p.rows = rows; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2;
+  p.y_out = y_out; p.z_out = static_cast<__nv_bfloat16*>(z_out); p.seq_len = seq_len > 0 ? seq_len : 1; p.z_skip = z_skip; p.eps = eps;
+  return launch_ln(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int edm_conv_module(const void* in, void* out, const float* dw_w, const float* dw_b, const float* cln_w, int B, int N, void* stream) {
+  if (int rc = check_arch()) return rc;
+  ConvModParams p;
+  p.in = static_cast<const __nv_bfloat16*>(in); p.out = static_cast<__nv_bfloat16*>(out);
+  p.dw_w = dw_w; p.dw_b = dw_b; p.cln_w = cln_w; p.B = B; p.N = N;
+  dim3 grid((N + kConvTT - 1) / kConvTT, B);
+  conv_module_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  EDM_LAUNCH_CHECK("conv_module");
+  return 0;
+}
+
+extern "C" int edm_sample(const float* logits, long long ld, int rows, const float* noise, int use_philox, unsigned long long seed,
+                          unsigned step, const int* forced_ids, int* ids, float* logp, int T, int Q, int out_q_stride, int out_q0, void* stream) {
+  if (int rc = check_arch()) return rc;
+  SampleParams p;
+  p.logits = logits; p.ld = ld; p.rows = rows; p.noise = noise; p.use_philox = use_philox; p.seed = seed; p.step = step;
+  p.forced_ids = forced_ids; p.ids = ids; p.ids_raw = nullptr; p.logp = logp; p.T = T; p.Q = Q; p.out_q_stride = out_q_stride; p.out_q0 = out_q0;
+  return launch_sample(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int edm_remask(const float* logp, const float* gumbel, const uint8_t* mask_old, uint8_t* mask_new, const uint8_t* forced_mask,
+                          int B, int T, float ratio, float temp_ratio, unsigned long long seed, unsigned step, void* stream) {
+  if (int rc = check_arch()) return rc;
+  if (T > kRemaskMaxT) return fail(EDM_ERR_INVALID, "remask supports T <= %d", kRemaskMaxT);
+  RemaskParams p;
+  p.logp = logp; p.gumbel = gumbel; p.mask_old = mask_old; p.mask_new = mask_new; p.forced_mask = forced_mask;
+  p.T = T; p.ratio = ratio; p.temp_ratio = temp_ratio; p.seed = seed; p.step = step;
+  remask_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  EDM_LAUNCH_CHECK("remask");
+  return 0;
+}
+
+extern "C" int edm_rvq_encode(const void* z, int z_is_bf16, int B, int T, int n_levels, const float* w_in, const float* b_in,
+                              const float* cb_norm, const float* cb_n2, const float* g, long long* codes, const long long* forced,
+                              float* latents, void* stream) {
+  if (int rc = check_arch()) return rc;
+  if (n_levels < 1 || n_levels > kRvqLevels || B <= 0 || T <= 0) return fail(EDM_ERR_INVALID, "rvq shape B=%d T=%d levels=%d", B, T, n_levels);
+  static bool attr_set = false;
+  if (!attr_set) {
+    EDM_CUDA(cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRvqSmemBytes));
+    attr_set = true;
+  }
+  RvqParams p;
+  p.z = z; p.z_is_bf16 = z_is_bf16; p.B = B; p.T = T; p.n_levels = n_levels; p.w_in = w_in; p.b_in = b_in;
+  p.cb_norm = cb_norm; p.cb_n2 = cb_n2; p.g = g; p.codes = codes; p.forced = forced; p.latents = latents;
+  dim3 grid((T + kRvqFrames - 1) / kRvqFrames, B);
+  rvq_encode_kernel<<<grid, 256, kRvqSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+  EDM_LAUNCH_CHECK("rvq_encode");
+  return 0;
+}
+
+extern "C" int edm_codes_to_features(const long long* codes, const float* proj, float* out, int B, int L, int T, int unreduced, void* stream) {
+  if (int rc = check_arch()) return rc;
+  if (L < 1 || L > kRvqLevels) return fail(EDM_ERR_INVALID, "codes_to_features levels=%d", L);
+  CodesToFeatParams p;
+  p.codes = codes; p.proj = proj; p.out = out; p.B = B; p.L = L; p.T = T; p.unreduced = unreduced;
+  dim3 grid((T + 31) / 32, B);
+  codes_to_features_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  EDM_LAUNCH_CHECK("codes_to_features");
+  return 0;
+}
+
+// ================================================================================================ S2A context
+namespace {
+
+const char* const kBlockFields[] = {
+    "ff1_ln_w", "ff1_ln_b", "ff1_w1", "ff1_b1", "ff1_w2", "ff1_b2",                       //
+    "attn_ln_w", "attn_ln_b", "wqkv", "wo", "bo",                                        //
+    "conv_ln_w", "conv_ln_b", "pw1_w", "pw1_b", "dw_w", "dw_b", "cln_w", "pw2_w", "pw2_b",  //
+    "ff2_ln_w", "ff2_ln_b", "ff2_w1", "ff2_b1", "ff2_w2", "ff2_b2",                       //
+    "post_ln_w", "post_ln_b"};
+enum BlockField {
+  F_FF1_LN_W, F_FF1_LN_B, F_FF1_W1, F_FF1_B1, F_FF1_W2, F_FF1_B2,
+  F_ATTN_LN_W, F_ATTN_LN_B, F_WQKV, F_WO, F_BO,
+  F_CONV_LN_W, F_CONV_LN_B, F_PW1_W, F_PW1_B, F_DW_W, F_DW_B, F_CLN_W, F_PW2_W, F_PW2_B,
+  F_FF2_LN_W, F_FF2_LN_B, F_FF2_W1, F_FF2_B1, F_FF2_W2, F_FF2_B2,
+  F_POST_LN_W, F_POST_LN_B, F_BLOCK_COUNT
+};
+const char* const kGlobalFields[] = {"sem_emb", "mask_token", "feat_table", "feat_const", "fp_ln_w", "fp_ln_b",
+                                     "inj_table", "inj_const", "inj_ln_w", "inj_ln_b", "tl_ln_w", "tl_ln_b",
+                                     "head_w", "head_b", "fine_w", "fine_b", "rope_cos", "rope_sin"};
+enum GlobalField {
+  G_SEM_EMB, G_MASK_TOKEN, G_FEAT_TABLE, G_FEAT_CONST, G_FP_LN_W, G_FP_LN_B,
+  G_INJ_TABLE, G_INJ_CONST, G_INJ_LN_W, G_INJ_LN_B, G_TL_LN_W, G_TL_LN_B,
+  G_HEAD_W, G_HEAD_B, G_FINE_W, G_FINE_B, G_ROPE_COS, G_ROPE_SIN, G_COUNT
+};
+
+struct BlockMaps {
+  CUtensorMap ff1_w1, ff1_w2, wqkv, wo, pw1, pw2, ff2_w1, ff2_w2;
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct edm_s2a_ctx {
+  edm_s2a_config cfg;
+  std::vector<const void*> w;  // depth * F_BLOCK_COUNT + G_COUNT
+  std::vector<BlockMaps> bmaps;
+  CUtensorMap head_map, fine_map;
+  int n_fine;
+
+  // bound shapes
+  bool bound = false;
+  int B = 0, T = 0, P = 0, N = 0, M = 0, Mt = 0;
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+  // workspace views
+  float *x_in, *x, *coarse_out[4], *logits, *coarse_logits, *fine_logits, *logp;
+  __nv_bfloat16 *z, *h, *qkv, *g, *zt, *fine_h, *fine_z;
+  int *ids, *ids_raw, *pred_codes, *pred_raw, *fine_codes, *sem_tokens, *sem_prompt, *ac_prompt;
+  uint8_t *mask_a, *mask_b;
+  int ac_levels = 0;
+  bool mask_in_a = true;  // which buffer holds the current mask
+  CUtensorMap m_z, m_h, m_g, m_zt, m_fine_z, m_qkv;
+
+  const void* bw(int layer, int f) const { return w[static_cast<size_t>(layer) * F_BLOCK_COUNT + f]; }
+  const float* bwf(int layer, int f) const { return static_cast<const float*>(bw(layer, f)); }
+  const void* gw(int f) const { return w[static_cast<size_t>(cfg.depth) * F_BLOCK_COUNT + f]; }
+  const float* gwf(int f) const { return static_cast<const float*>(gw(f)); }
+  uint8_t* mask_cur() { return mask_in_a ? mask_a : mask_b; }
+  uint8_t* mask_next() { return mask_in_a ? mask_b : mask_a; }
+};
+
+namespace {
+
+int validate_cfg(const edm_s2a_config* c) {
+  if (c == nullptr) return fail(EDM_ERR_INVALID, "null config");
+  if (c->hidden != 1024 || c->heads != 16 || c->ff_mult != 4 || c->conv_kernel != 5 || c->num_codes != 1024)
+    return fail(EDM_ERR_INVALID, "kernels are specialised for hidden=1024 heads=16 ff_mult=4 conv_kernel=5 codes=1024 (got %d %d %d %d %d)", c->hidden,
+                c->heads, c->ff_mult, c->conv_kernel, c->num_codes);
+  if (c->depth < 1 || c->depth > 64 || c->n_injection < 1 || c->n_injection > 4 || c->num_quantizers <= c->n_injection || c->num_quantizers > 12)
+    return fail(EDM_ERR_INVALID, "unsupported depth / injection / quantizer counts");
+  for (int i = 0; i < c->n_injection; ++i) {
+    if (c->injection_layers[i] < 0 || c->injection_layers[i] >= c->depth) return fail(EDM_ERR_INVALID, "injection layer out of range");
+    if (i > 0 && c->injection_layers[i] <= c->injection_layers[i - 1]) return fail(EDM_ERR_INVALID, "injection layers must increase");
+  }
+  return 0;
+}
+
+int injection_index(const edm_s2a_config& c, int layer) {
+  for (int i = 0; i < c.n_injection; ++i)
+    if (c.injection_layers[i] == layer) return i;
+  return -1;
+}
+
+GemmParams gp(int M, int N, int K, const float* bias, void* out, long long ldo, float scale = 1.0f) {
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.a_k_offset = 0; p.b_row_offset = 0; p.bias = bias; p.out = out; p.ldo = ldo; p.scale = scale;
+  p.rope_cos = nullptr; p.rope_sin = nullptr; p.seq_len = 1; p.rope_cols = 0;
+  return p;
+}
+
+// One conformer block on the bound workspace. In: x (fp32 residual stream) and z = LN_ff1(x) (bf16). Out: x holds the
+// pre-post_norm sum; the caller applies post_norm (it differs per call site).
+int run_block_body(edm_s2a_ctx* c, int l, cudaStream_t st) {
+  const int M = c->M;
+  const float eps = 1e-5f;
+  // ff1: x += 0.5 * W2 swish(W1 z + b1) + b2
+  if (int rc = launch_gemm(EPI_SWISH_BF16, c->m_z, c->bmaps[l].ff1_w1, gp(M, 4096, 1024, c->bwf(l, F_FF1_B1), c->h, 4096), st)) return rc;
+  if (int rc = launch_gemm(EPI_RESID_F32, c->m_h, c->bmaps[l].ff1_w2, gp(M, 1024, 4096, c->bwf(l, F_FF1_B2), c->x, 1024, 0.5f), st)) return rc;
+  // attention
+  LnParams ln;
+  ln.in = c->x; ln.in_is_bf16 = 0; ln.rows = M; ln.w1 = c->bwf(l, F_ATTN_LN_W); ln.b1 = c->bwf(l, F_ATTN_LN_B); ln.w2 = nullptr; ln.b2 = nullptr;
+  ln.y_out = nullptr; ln.z_out = c->z; ln.seq_len = 1; ln.z_skip = 0; ln.eps = eps;
+  if (int rc = launch_ln(ln, st)) return rc;
+  {
+    GemmParams p = gp(M, 3072, 1024, nullptr, c->qkv, 3072);
+    p.rope_cos = c->gwf(G_ROPE_COS); p.rope_sin = c->gwf(G_ROPE_SIN); p.seq_len = c->N; p.rope_cols = 2048;
+    if (int rc = launch_gemm(EPI_QKV_ROPE, c->m_z, c->bmaps[l].wqkv, p, st)) return rc;
+  }
+  if (int rc = launch_attention(c->m_qkv, c->B, c->N, 16, c->z, 1024, 1024, 2048, st)) return rc;
+  if (int rc = launch_gemm(EPI_RESID_F32, c->m_z, c->bmaps[l].wo, gp(M, 1024, 1024, c->bwf(l, F_BO), c->x, 1024, 1.0f), st)) return rc;
+  // conv module
+  ln.w1 = c->bwf(l, F_CONV_LN_W); ln.b1 = c->bwf(l, F_CONV_LN_B);
+  if (int rc = launch_ln(ln, st)) return rc;
+  if (int rc = launch_gemm(EPI_BF16, c->m_z, c->bmaps[l].pw1, gp(M, 4096, 1024, c->bwf(l, F_PW1_B), c->h, 4096), st)) return rc;
+  {
+    ConvModParams p;
+    p.in = c->h; p.out = c->g; p.dw_w = c->bwf(l, F_DW_W); p.dw_b = c->bwf(l, F_DW_B); p.cln_w = c->bwf(l, F_CLN_W); p.B = c->B; p.N = c->N;
+    dim3 grid((c->N + kConvTT - 1) / kConvTT, c->B);
+    conv_module_kernel<<<grid, 256, 0, st>>>(p);
+    EDM_LAUNCH_CHECK("conv_module");
+  }
+  if (int rc = launch_gemm(EPI_RESID_F32, c->m_g, c->bmaps[l].pw2, gp(M, 1024, 2048, c->bwf(l, F_PW2_B), c->x, 1024, 1.0f), st)) return rc;
+  // ff2
+  ln.w1 = c->bwf(l, F_FF2_LN_W); ln.b1 = c->bwf(l, F_FF2_LN_B);
+  if (int rc = launch_ln(ln, st)) return rc;
+  if (int rc = launch_gemm(EPI_SWISH_BF16, c->m_z, c->bmaps[l].ff2_w1, gp(M, 4096, 1024, c->bwf(l, F_FF2_B1), c->h, 4096), st)) return rc;
+  if (int rc = launch_gemm(EPI_RESID_F32, c->m_h, c->bmaps[l].ff2_w2, gp(M, 1024, 4096, c->bwf(l, F_FF2_B2), c->x, 1024, 0.5f), st)) return rc;
+  return 0;
+}
+
+// pass prologue: x = copy of the encoder input, z = LN_ff1[0](x)
+int pass_prologue(edm_s2a_ctx* c, const float* x_src, cudaStream_t st) {
+  LnParams ln;
+  ln.in = x_src; ln.in_is_bf16 = 0; ln.rows = c->M; ln.w1 = nullptr; ln.b1 = nullptr;
+  ln.w2 = c->bwf(0, F_FF1_LN_W); ln.b2 = c->bwf(0, F_FF1_LN_B);
+  ln.y_out = c->x; ln.z_out = c->z; ln.seq_len = 1; ln.z_skip = 0; ln.eps = 1e-5f;
+  return launch_ln(ln, st);
+}
+
+}  // namespace
+
+extern "C" int edm_s2a_num_weights(const edm_s2a_config* cfg) {
+  if (validate_cfg(cfg)) return EDM_ERR_INVALID;
+  return cfg->depth * F_BLOCK_COUNT + G_COUNT;
+}
+
+extern "C" const char* edm_s2a_weight_name(const edm_s2a_config* cfg, int index) {
+  thread_local char buf[64];
+  if (validate_cfg(cfg)) return nullptr;
+  const int nb = cfg->depth * F_BLOCK_COUNT;
+  if (index < 0 || index >= nb + G_COUNT) return nullptr;
+  if (index < nb)
+    snprintf(buf, sizeof(buf), "blocks.%d.%s", index / F_BLOCK_COUNT, kBlockFields[index % F_BLOCK_COUNT]);
+  else
+    snprintf(buf, sizeof(buf), "%s", kGlobalFields[index - nb]);
+  return buf;
+}
+
+extern "C" edm_s2a_ctx* edm_s2a_create(const edm_s2a_config* cfg, const void* const* weights, int n_weights) {
+  if (check_arch()) return nullptr;
+  if (validate_cfg(cfg)) return nullptr;
+  const int expect = cfg->depth * F_BLOCK_COUNT + G_COUNT;
+  if (weights == nullptr || n_weights != expect) {
+    fail(EDM_ERR_INVALID, "expected %d weight pointers, got %d", expect, n_weights);
+    return nullptr;
+  }
+  for (int i = 0; i < expect; ++i)
+    if (weights[i] == nullptr) {
+      fail(EDM_ERR_INVALID, "weight %s is null", edm_s2a_weight_name(cfg, i));
+      return nullptr;
+    }
+  edm_s2a_ctx* c = new edm_s2a_ctx();
+  c->cfg = *cfg;
+  c->w.assign(weights, weights + expect);
+  c->n_fine = cfg->num_quantizers - cfg->n_injection;
+  c->bmaps.resize(cfg->depth);
+  int rc = 0;
+  for (int l = 0; l < cfg->depth && rc == 0; ++l) {
+    BlockMaps& m = c->bmaps[l];
+    rc = rc ? rc : make_tmap_2d(&m.ff1_w1, c->bw(l, F_FF1_W1), 4096, 1024, 1024, kGemmBN);
+    rc = rc ? rc : make_tmap_2d(&m.ff1_w2, c->bw(l, F_FF1_W2), 1024, 4096, 4096, kGemmBN);
+    rc = rc ? rc : make_tmap_2d(&m.wqkv, c->bw(l, F_WQKV), 3072, 1024, 1024, kGemmBN);
+    rc = rc ? rc : make_tmap_2d(&m.wo, c->bw(l, F_WO), 1024, 1024, 1024, kGemmBN);
+    rc = rc ? rc : make_tmap_2d(&m.pw1, c->bw(l, F_PW1_W), 4096, 1024, 1024, kGemmBN);
+    rc = rc ? rc : make_tmap_2d(&m.pw2, c->bw(l, F_PW2_W), 1024, 2048, 2048, kGemmBN);
+    rc = rc ? rc : make_tmap_2d(&m.ff2_w1, c->bw(l, F_FF2_W1), 4096, 1024, 1024, kGemmBN);
+    rc = rc ? rc : make_tmap_2d(&m.ff2_w2, c->bw(l, F_FF2_W2), 1024, 4096, 4096, kGemmBN);
+  }
+  rc = rc ? rc : make_tmap_2d(&c->head_map, c->gw(G_HEAD_W), static_cast<uint64_t>(cfg->num_quantizers) * 1024, 1024, 1024, kGemmBN);
+  rc = rc ? rc : make_tmap_2d(&c->fine_map, c->gw(G_FINE_W), static_cast<uint64_t>(c->n_fine) * 1024, 1024, 1024, kGemmBN);
+  if (rc) {
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+extern "C" void edm_s2a_destroy(edm_s2a_ctx* ctx) { delete ctx; }
+
+namespace {
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 1024);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+size_t carve(edm_s2a_ctx* c, uint8_t* base, int B, int T, int P, bool assign) {
+  const size_t N = static_cast<size_t>(P) + T, M = static_cast<size_t>(B) * N, Mt = static_cast<size_t>(B) * T;
+  const int nf = c->n_fine;
+  Carver k{base};
+  float* x_in = k.take<float>(M * 1024);
+  float* x = k.take<float>(M * 1024);
+  float* co[4];
+  for (int i = 0; i < 4; ++i) co[i] = k.take<float>(M * 1024);
+  __nv_bfloat16* z = k.take<__nv_bfloat16>(M * 1024);
+  __nv_bfloat16* h = k.take<__nv_bfloat16>(M * 4096);
+  __nv_bfloat16* qkv = k.take<__nv_bfloat16>(M * 3072);
+  __nv_bfloat16* g = k.take<__nv_bfloat16>(M * 2048);
+  __nv_bfloat16* zt = k.take<__nv_bfloat16>(Mt * 1024);
+  float* logits = k.take<float>(Mt * 1024);
+  float* coarse_logits = k.take<float>(4 * Mt * 1024);
+  __nv_bfloat16* fine_h = k.take<__nv_bfloat16>(Mt * nf * 1024);
+  __nv_bfloat16* fine_z = k.take<__nv_bfloat16>(Mt * nf * 1024);
+  float* fine_logits = k.take<float>(Mt * nf * 1024);
+  float* logp = k.take<float>(Mt);
+  int* ids = k.take<int>(Mt);
+  int* ids_raw = k.take<int>(Mt);
+  int* pred = k.take<int>(Mt * 4);
+  int* pred_raw = k.take<int>(Mt * 4);
+  int* fine_codes = k.take<int>(Mt * nf);
+  int* sem_tokens = k.take<int>(Mt);
+  int* sem_prompt = k.take<int>(static_cast<size_t>(B) * (P > 0 ? P : 1));
+  int* ac_prompt = k.take<int>(static_cast<size_t>(B) * 12 * (P > 0 ? P : 1));
+  uint8_t* mask_a = k.take<uint8_t>(Mt);
+  uint8_t* mask_b = k.take<uint8_t>(Mt);
+  if (assign) {
+    c->x_in = x_in; c->x = x;
+    for (int i = 0; i < 4; ++i) c->coarse_out[i] = co[i];
+    c->z = z; c->h = h; c->qkv = qkv; c->g = g; c->zt = zt; c->logits = logits; c->coarse_logits = coarse_logits;
+    c->fine_h = fine_h; c->fine_z = fine_z; c->fine_logits = fine_logits; c->logp = logp; c->ids = ids; c->ids_raw = ids_raw;
+    c->pred_codes = pred; c->pred_raw = pred_raw; c->fine_codes = fine_codes; c->sem_tokens = sem_tokens; c->sem_prompt = sem_prompt;
+    c->ac_prompt = ac_prompt; c->mask_a = mask_a; c->mask_b = mask_b;
+  }
+  return align_up(k.off, 1024);
+}
+}  // namespace
+
+extern "C" size_t edm_s2a_workspace_bytes(const edm_s2a_ctx* ctx, int B, int T, int P) {
+  if (ctx == nullptr || B <= 0 || T <= 0 || P < 0) return 0;
+  return carve(const_cast<edm_s2a_ctx*>(ctx), nullptr, B, T, P, false);
+}
+
+extern "C" int edm_s2a_bind(edm_s2a_ctx* c, void* workspace, size_t bytes, int B, int T, int P) {
+  if (c == nullptr || workspace == nullptr || B <= 0 || T <= 0 || P < 0) return fail(EDM_ERR_INVALID, "bind arguments");
+  if (T > kRemaskMaxT) return fail(EDM_ERR_INVALID, "T=%d exceeds %d", T, kRemaskMaxT);
+  if (P + T > c->cfg.max_positions) return fail(EDM_ERR_INVALID, "P+T=%d exceeds rotary table (%d)", P + T, c->cfg.max_positions);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return fail(EDM_ERR_INVALID, "workspace must be 1024-byte aligned");
+  const size_t need = carve(c, nullptr, B, T, P, false);
+  if (bytes < need) return fail(EDM_ERR_INVALID, "workspace too small: %zu < %zu", bytes, need);
+  carve(c, static_cast<uint8_t*>(workspace), B, T, P, true);
+  c->ws = static_cast<uint8_t*>(workspace); c->ws_bytes = bytes;
+  c->B = B; c->T = T; c->P = P; c->N = P + T; c->M = B * (P + T); c->Mt = B * T;
+  int rc = 0;
+  rc = rc ? rc : make_tmap_2d(&c->m_z, c->z, c->M, 1024, 1024, kGemmBM);
+  rc = rc ? rc : make_tmap_2d(&c->m_h, c->h, c->M, 4096, 4096, kGemmBM);
+  rc = rc ? rc : make_tmap_2d(&c->m_g, c->g, c->M, 2048, 2048, kGemmBM);
+  rc = rc ? rc : make_tmap_2d(&c->m_zt, c->zt, c->Mt, 1024, 1024, kGemmBM);
+  rc = rc ? rc : make_tmap_2d(&c->m_fine_z, c->fine_z, c->Mt, static_cast<uint64_t>(c->n_fine) * 1024, static_cast<uint64_t>(c->n_fine) * 1024, kGemmBM);
+  rc = rc ? rc : make_tmap_3d(&c->m_qkv, c->qkv, B, c->N, 3072);
+  if (rc) return rc;
+  c->bound = true;
+  return 0;
+}
+
+extern "C" void* edm_s2a_buffer(edm_s2a_ctx* c, const char* name, size_t* bytes) {
+  if (c == nullptr || !c->bound || name == nullptr) return nullptr;
+  const size_t M = c->M, Mt = c->Mt;
+  struct { const char* n; void* p; size_t b; } tab[] = {
+      {"x_in", c->x_in, M * 1024 * 4}, {"x", c->x, M * 1024 * 4}, {"z", c->z, M * 1024 * 2}, {"h", c->h, M * 4096 * 2},
+      {"qkv", c->qkv, M * 3072 * 2}, {"g", c->g, M * 2048 * 2}, {"zt", c->zt, Mt * 1024 * 2},
+      {"coarse_out0", c->coarse_out[0], M * 1024 * 4}, {"coarse_out1", c->coarse_out[1], M * 1024 * 4},
+      {"coarse_out2", c->coarse_out[2], M * 1024 * 4}, {"coarse_out3", c->coarse_out[3], M * 1024 * 4},
+      {"logits", c->logits, Mt * 1024 * 4}, {"coarse_logits", c->coarse_logits, 4 * Mt * 1024 * 4},
+      {"fine_logits", c->fine_logits, Mt * c->n_fine * 1024 * 4}, {"logp", c->logp, Mt * 4}, {"ids", c->ids, Mt * 4},
+      {"ids_raw", c->ids_raw, Mt * 4}, {"pred_codes", c->pred_codes, Mt * 16}, {"pred_raw", c->pred_raw, Mt * 16},
+      {"fine_codes", c->fine_codes, Mt * c->n_fine * 4}, {"mask", c->mask_cur(), Mt}};
+  for (auto& e : tab)
+    if (strcmp(e.n, name) == 0) {
+      if (bytes) *bytes = e.b;
+      return e.p;
+    }
+  return nullptr;
+}
+
+extern "C" int edm_s2a_build_input(edm_s2a_ctx* c, const int* sem_tokens, const int* sem_prompt, const int* ac_prompt, int ac_levels, void* stream) {
+  if (c == nullptr || !c->bound) return fail(EDM_ERR_STATE, "context not bound");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (sem_tokens == nullptr) return fail(EDM_ERR_INVALID, "semantic tokens required");
+  if (c->P > 0) {
+    if (sem_prompt == nullptr || ac_prompt == nullptr) return fail(EDM_ERR_INVALID, "bound with P=%d but no prompt given", c->P);
+    if (ac_levels < c->cfg.n_injection || ac_levels > 12) return fail(EDM_ERR_INVALID, "acoustic prompt needs >= %d levels (got %d)", c->cfg.n_injection, ac_levels);
+    EDM_CUDA(cudaMemcpyAsync(c->sem_prompt, sem_prompt, sizeof(int) * c->B * c->P, cudaMemcpyDeviceToDevice, st));
+    EDM_CUDA(cudaMemcpyAsync(c->ac_prompt, ac_prompt, sizeof(int) * c->B * ac_levels * c->P, cudaMemcpyDeviceToDevice, st));
+  }
+  c->ac_levels = ac_levels;
+  EDM_CUDA(cudaMemcpyAsync(c->sem_tokens, sem_tokens, sizeof(int) * c->Mt, cudaMemcpyDeviceToDevice, st));
+  BuildInputParams p;
+  p.x = c->x_in; p.sem_tokens = c->sem_tokens; p.sem_prompt = c->P > 0 ? c->sem_prompt : nullptr; p.ac_prompt = c->P > 0 ? c->ac_prompt : nullptr;
+  p.ac_prompt_levels = ac_levels; p.sem_emb = c->gwf(G_SEM_EMB); p.mask_token = c->gwf(G_MASK_TOKEN); p.feat_table = c->gwf(G_FEAT_TABLE);
+  p.feat_const = c->gwf(G_FEAT_CONST); p.fp_ln_w = c->gwf(G_FP_LN_W); p.fp_ln_b = c->gwf(G_FP_LN_B); p.B = c->B; p.T = c->T; p.P = c->P; p.eps = 1e-5f;
+  build_input_kernel<<<(c->M + 7) / 8, 256, 0, st>>>(p);
+  EDM_LAUNCH_CHECK("build_input");
+  c->mask_in_a = true;
+  fill_u8_kernel<<<(c->Mt + 255) / 256, 256, 0, st>>>(c->mask_a, c->Mt, 1);
+  EDM_LAUNCH_CHECK("fill_mask");
+  return 0;
+}
+
+extern "C" int edm_s2a_first_level(edm_s2a_ctx* c, const float* x_in, void* stream) {
+  if (c == nullptr || !c->bound) return fail(EDM_ERR_STATE, "context not bound");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = pass_prologue(c, x_in ? x_in : c->x_in, st)) return rc;
+  const int last = c->cfg.injection_layers[0];
+  for (int l = 0; l <= last; ++l) {
+    if (int rc = run_block_body(c, l, st)) return rc;
+    LnParams ln;
+    ln.in = c->x; ln.in_is_bf16 = 0; ln.rows = c->M; ln.w1 = c->bwf(l, F_POST_LN_W); ln.b1 = c->bwf(l, F_POST_LN_B); ln.eps = 1e-5f;
+    if (l < last) {
+      ln.w2 = c->bwf(l + 1, F_FF1_LN_W); ln.b2 = c->bwf(l + 1, F_FF1_LN_B);
+      ln.y_out = c->x; ln.z_out = c->z; ln.seq_len = 1; ln.z_skip = 0;
+    } else {
+      ln.w2 = c->gwf(G_TL_LN_W); ln.b2 = c->gwf(G_TL_LN_B);
+      ln.y_out = nullptr; ln.z_out = c->zt; ln.seq_len = c->N; ln.z_skip = c->P;
+    }
+    if (int rc = launch_ln(ln, st)) return rc;
+  }
+  GemmParams p = gp(c->Mt, 1024, 1024, c->gwf(G_HEAD_B), c->logits, 1024);
+  return launch_gemm(EPI_F32, c->m_zt, c->head_map, p, st);
+}
+
+extern "C" int edm_s2a_step(edm_s2a_ctx* c, int step, int steps, float temperature, unsigned long long seed, const float* cat_noise,
+                            const float* remask_noise, const int* forced_ids, const uint8_t* forced_mask, void* stream) {
+  if (c == nullptr || !c->bound) return fail(EDM_ERR_STATE, "context not bound");
+  if (steps < 2 || step < 0 || step >= steps) return fail(EDM_ERR_INVALID, "step %d of %d", step, steps);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool last = step == steps - 1;
+  SampleParams sp;
+  sp.logits = c->logits; sp.ld = 1024; sp.rows = c->Mt; sp.noise = last ? nullptr : cat_noise; sp.use_philox = last ? 0 : 1; sp.seed = seed;
+  sp.step = static_cast<unsigned>(step); sp.forced_ids = forced_ids; sp.ids = c->ids; sp.ids_raw = c->ids_raw; sp.logp = last ? nullptr : c->logp;
+  sp.T = c->T; sp.Q = 1; sp.out_q_stride = 1; sp.out_q0 = 0;
+  if (int rc = launch_sample(sp, st)) return rc;
+  uint8_t* m_old = c->mask_cur();
+  uint8_t* m_new = nullptr;
+  if (!last) {
+    // python: mask_ratio is a double; torch multiplies float32 tensors by float32(ratio)
+    const double ratio_d = std::cos(M_PI / 2.0 * (static_cast<double>(step + 1) / static_cast<double>(steps)));
+    RemaskParams rp;
+    rp.logp = c->logp; rp.gumbel = remask_noise; rp.mask_old = m_old; rp.mask_new = c->mask_next(); rp.forced_mask = forced_mask;
+    rp.T = c->T; rp.ratio = static_cast<float>(ratio_d); rp.temp_ratio = static_cast<float>(static_cast<double>(temperature) * ratio_d);
+    rp.seed = seed; rp.step = static_cast<unsigned>(step);
+    remask_kernel<<<c->B, 256, 0, st>>>(rp);
+    EDM_LAUNCH_CHECK("remask");
+    m_new = c->mask_next();
+  }
+  UpdateInputParams up;
+  up.x = c->x_in; up.sem_tokens = c->sem_tokens; up.ids = c->ids; up.mask_old = m_old; up.mask_new = m_new; up.sem_emb = c->gwf(G_SEM_EMB);
+  up.mask_token = c->gwf(G_MASK_TOKEN); up.feat_table = c->gwf(G_FEAT_TABLE); up.feat_const = c->gwf(G_FEAT_CONST);
+  up.fp_ln_w = c->gwf(G_FP_LN_W); up.fp_ln_b = c->gwf(G_FP_LN_B); up.B = c->B; up.T = c->T; up.P = c->P; up.eps = 1e-5f;
+  update_input_kernel<<<(c->Mt + 7) / 8, 256, 0, st>>>(up);
+  EDM_LAUNCH_CHECK("update_input");
+  if (!last) c->mask_in_a = !c->mask_in_a;
+  return 0;
+}
+
+extern "C" int edm_s2a_full_pass(edm_s2a_ctx* c, const float* x_in, const int* forced_coarse, long long* codes_out, void* stream) {
+  if (c == nullptr || !c->bound) return fail(EDM_ERR_STATE, "context not bound");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const edm_s2a_config& cfg = c->cfg;
+  if (int rc = pass_prologue(c, x_in ? x_in : c->x_in, st)) return rc;
+  for (int l = 0; l < cfg.depth; ++l) {
+    if (int rc = run_block_body(c, l, st)) return rc;
+    const int k = injection_index(cfg, l);
+    const bool is_last = l == cfg.depth - 1;
+    LnParams ln;
+    ln.in = c->x; ln.in_is_bf16 = 0; ln.rows = c->M; ln.w1 = c->bwf(l, F_POST_LN_W); ln.b1 = c->bwf(l, F_POST_LN_B); ln.eps = 1e-5f;
+    if (k < 0) {
+      if (!is_last) {
+        ln.w2 = c->bwf(l + 1, F_FF1_LN_W); ln.b2 = c->bwf(l + 1, F_FF1_LN_B); ln.y_out = c->x; ln.z_out = c->z; ln.seq_len = 1; ln.z_skip = 0;
+      } else {
+        ln.w2 = nullptr; ln.b2 = nullptr; ln.y_out = nullptr; ln.z_out = c->zt; ln.seq_len = c->N; ln.z_skip = c->P;  // bf16 copy of the target rows
+      }
+      if (int rc = launch_ln(ln, st)) return rc;
+      continue;
+    }
+    // injection layer k: keep the block output, predict level k on the target rows, inject
+    ln.w2 = c->gwf(G_TL_LN_W); ln.b2 = c->gwf(G_TL_LN_B); ln.y_out = c->coarse_out[k]; ln.z_out = c->zt; ln.seq_len = c->N; ln.z_skip = c->P;
+    if (int rc = launch_ln(ln, st)) return rc;
+    float* lk = c->coarse_logits + static_cast<size_t>(k) * c->Mt * 1024;
+    {
+      GemmParams p = gp(c->Mt, 1024, 1024, c->gwf(G_HEAD_B) + k * 1024, lk, 1024);
+      p.b_row_offset = k * 1024;
+      if (int rc = launch_gemm(EPI_F32, c->m_zt, c->head_map, p, st)) return rc;
+    }
+    SampleParams sp;
+    sp.logits = lk; sp.ld = 1024; sp.rows = c->Mt; sp.noise = nullptr; sp.use_philox = 0; sp.seed = 0; sp.step = 0; sp.forced_ids = forced_coarse;
+    sp.ids = c->pred_codes; sp.ids_raw = c->pred_raw; sp.logp = nullptr; sp.T = c->T; sp.Q = 1; sp.out_q_stride = 4; sp.out_q0 = k;
+    if (int rc = launch_sample(sp, st)) return rc;
+    InjectParams ip;
+    ip.x = c->x; ip.cur_out = c->coarse_out[k]; ip.prev_out = (k > 0 && cfg.residual) ? c->coarse_out[k - 1] : nullptr;
+    ip.pred_codes = c->pred_codes; ip.ac_prompt = c->P > 0 ? c->ac_prompt : nullptr; ip.ac_prompt_levels = c->ac_levels;
+    for (int i = 0; i < 4; ++i) ip.tables[i] = c->gwf(G_INJ_TABLE) + (static_cast<size_t>(k) * 4 + i) * 1024 * 1024;
+    ip.inj_const = c->gwf(G_INJ_CONST) + k * 1024; ip.ln_w = c->gwf(G_INJ_LN_W) + k * 1024; ip.ln_b = c->gwf(G_INJ_LN_B) + k * 1024;
+    ip.level = k; ip.B = c->B; ip.T = c->T; ip.P = c->P; ip.eps = 1e-5f;
+    inject_kernel<<<(c->M + 7) / 8, 256, 0, st>>>(ip);
+    EDM_LAUNCH_CHECK("inject");
+    LnParams nx;
+    nx.in = c->x; nx.in_is_bf16 = 0; nx.rows = c->M; nx.w1 = nullptr; nx.b1 = nullptr; nx.eps = 1e-5f; nx.y_out = nullptr;
+    if (!is_last) {
+      nx.w2 = c->bwf(l + 1, F_FF1_LN_W); nx.b2 = c->bwf(l + 1, F_FF1_LN_B); nx.z_out = c->z; nx.seq_len = 1; nx.z_skip = 0;
+    } else {
+      nx.w2 = nullptr; nx.b2 = nullptr; nx.z_out = c->zt; nx.seq_len = c->N; nx.z_skip = c->P;
+    }
+    if (int rc = launch_ln(nx, st)) return rc;
+  }
+  // fine levels: fine_head (wrapper :38-41) -> per-(token, level) LayerNorm -> per-codebook heads (:43-54)
+  const int nf = c->n_fine;
+  if (int rc = launch_gemm(EPI_BF16, c->m_zt, c->fine_map, gp(c->Mt, nf * 1024, 1024, c->gwf(G_FINE_B), c->fine_h, static_cast<long long>(nf) * 1024), st)) return rc;
+  {
+    LnParams ln;
+    ln.in = c->fine_h; ln.in_is_bf16 = 1; ln.rows = c->Mt * nf; ln.w1 = c->gwf(G_TL_LN_W); ln.b1 = c->gwf(G_TL_LN_B); ln.w2 = nullptr; ln.b2 = nullptr;
+    ln.y_out = nullptr; ln.z_out = c->fine_z; ln.seq_len = 1; ln.z_skip = 0; ln.eps = 1e-5f;
+    if (int rc = launch_ln(ln, st)) return rc;
+  }
+  for (int q = 0; q < nf; ++q) {
+    const int lvl = cfg.n_injection + q;
+    GemmParams p = gp(c->Mt, 1024, 1024, c->gwf(G_HEAD_B) + lvl * 1024, c->fine_logits + q * 1024, static_cast<long long>(nf) * 1024);
+    p.a_k_offset = q * 1024; p.b_row_offset = lvl * 1024;
+    if (int rc = launch_gemm(EPI_F32, c->m_fine_z, c->head_map, p, st)) return rc;
+  }
+  {
+    SampleParams sp;
+    sp.logits = c->fine_logits; sp.ld = 1024; sp.rows = c->Mt * nf; sp.noise = nullptr; sp.use_philox = 0; sp.seed = 0; sp.step = 0; sp.forced_ids = nullptr;
+    sp.ids = c->fine_codes; sp.ids_raw = nullptr; sp.logp = nullptr; sp.T = c->T; sp.Q = nf; sp.out_q_stride = nf; sp.out_q0 = 0;
+    if (int rc = launch_sample(sp, st)) return rc;
+  }
+  if (codes_out != nullptr) {
+    const long long total = static_cast<long long>(c->B) * cfg.num_quantizers * c->T;
+    assemble_codes_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(c->pred_raw, cfg.n_injection, c->fine_codes, nf, codes_out, c->B, c->T);
+    EDM_LAUNCH_CHECK("assemble_codes");
+  }
+  return 0;
+}
+
+extern "C" int edm_s2a_decode(edm_s2a_ctx* c, const int* sem_tokens, const int* sem_prompt, const int* ac_prompt, int ac_levels, int steps,
+                              float temperature, unsigned long long seed, const float* cat_noise, const float* remask_noise,
+                              const int* forced_ids, const uint8_t* forced_masks, const int* forced_coarse, long long* codes_out, void* stream) {
+  if (c == nullptr || !c->bound) return fail(EDM_ERR_STATE, "context not bound");
+  if (steps < 1) return fail(EDM_ERR_INVALID, "steps must be >= 1");
+  if (int rc = edm_s2a_build_input(c, sem_tokens, sem_prompt, ac_prompt, ac_levels, stream)) return rc;
+  if (steps > 1) {
+    const size_t Mt = c->Mt;
+    for (int s = 0; s < steps; ++s) {
+      if (int rc = edm_s2a_first_level(c, nullptr, stream)) return rc;
+      const bool last = s == steps - 1;
+      if (int rc = edm_s2a_step(c, s, steps, temperature, seed, (cat_noise && !last) ? cat_noise + s * Mt * 1024 : nullptr,
+                                (remask_noise && !last) ? remask_noise + s * Mt : nullptr, forced_ids ? forced_ids + s * Mt : nullptr,
+                                (forced_masks && !last) ? forced_masks + s * Mt : nullptr, stream))
+        return rc;
+    }
+  }
+  return edm_s2a_full_pass(c, nullptr, forced_coarse, codes_out, stream);
+}

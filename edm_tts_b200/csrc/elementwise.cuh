@@ -1,0 +1,576 @@
+// Bandwidth-bound kernels of the S2A decode path: LayerNorm (+ fused second LayerNorm / bf16 cast / row compaction),
+// the conformer conv module's GLU -> depthwise conv -> Swish -> ChanLayerNorm chain, encoder-input construction,
+// code->feature injection, sampling / arg-max over 1024 logits, and confidence re-masking.
+// All rows are 1024 channels wide (hidden size); one warp owns one row, each lane 8 x 128-bit (fp32) accesses.
+#pragma once
+#include "ptx.cuh"
+
+namespace edm {
+
+constexpr int kD = 1024;        // hidden size
+constexpr int kConvC = 2048;    // conv-module inner channels
+constexpr int kV = 1024;        // codebook size (logit width)
+
+// lane l of a warp owns columns {i*128 + 4*l .. +3 : i = 0..7}
+__device__ __forceinline__ void row_load_f32(const float* row, int lane, float (&v)[32]) {
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 t = r4[i * 32 + lane];
+    v[4 * i + 0] = t.x;
+    v[4 * i + 1] = t.y;
+    v[4 * i + 2] = t.z;
+    v[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void row_load_f32_ldg(const float* row, int lane, float (&v)[32]) {
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 t = __ldg(r4 + i * 32 + lane);
+    v[4 * i + 0] = t.x;
+    v[4 * i + 1] = t.y;
+    v[4 * i + 2] = t.z;
+    v[4 * i + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void row_add_f32_ldg(const float* row, int lane, float (&v)[32]) {
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 t = __ldg(r4 + i * 32 + lane);
+    v[4 * i + 0] += t.x;
+    v[4 * i + 1] += t.y;
+    v[4 * i + 2] += t.z;
+    v[4 * i + 3] += t.w;
+  }
+}
+__device__ __forceinline__ void row_load_bf16(const __nv_bfloat16* row, int lane, float (&v)[32]) {
+  const uint2* r2 = reinterpret_cast<const uint2*>(row);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint2 t = r2[i * 32 + lane];
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+    v[4 * i + 0] = __low2float(a);
+    v[4 * i + 1] = __high2float(a);
+    v[4 * i + 2] = __low2float(b);
+    v[4 * i + 3] = __high2float(b);
+  }
+}
+__device__ __forceinline__ void row_store_f32(float* row, int lane, const float (&v)[32]) {
+  float4* r4 = reinterpret_cast<float4*>(row);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r4[i * 32 + lane] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void row_store_bf16(__nv_bfloat16* row, int lane, const float (&v)[32]) {
+  uint2* r2 = reinterpret_cast<uint2*>(row);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r2[i * 32 + lane] = make_uint2(pack_bf16x2(v[4 * i], v[4 * i + 1]), pack_bf16x2(v[4 * i + 2], v[4 * i + 3]));
+}
+
+// nn.LayerNorm over 1024 channels, eps 1e-5, fp32 statistics (two-pass, in registers).
+__device__ __forceinline__ void row_layernorm(float (&v)[32], const float* w, const float* b, int lane, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / kD);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / kD) + eps);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 ww = __ldg(w4 + i * 32 + lane), bb = __ldg(b4 + i * 32 + lane);
+    v[4 * i + 0] = (v[4 * i + 0] - mean) * rstd * ww.x + bb.x;
+    v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * ww.y + bb.y;
+    v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * ww.z + bb.z;
+    v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * ww.w + bb.w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// y = LN1(in) (skipped when w1 == nullptr); optional fp32 store of y; z = LN2(y) when w2 != nullptr else y;
+// optional bf16 store of z, optionally compacted to the target rows of each sequence (drops the prompt prefix).
+struct LnParams {
+  const void* in;
+  int in_is_bf16;
+  int rows;
+  const float *w1, *b1, *w2, *b2;
+  float* y_out;           // nullable
+  __nv_bfloat16* z_out;   // nullable
+  int seq_len, z_skip;    // z row for input row (b*seq_len + n) is b*(seq_len - z_skip) + (n - z_skip); rows n < z_skip dropped
+  float eps;
+};
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= p.rows) return;
+  float v[32];
+  if (p.in_is_bf16)
+    row_load_bf16(static_cast<const __nv_bfloat16*>(p.in) + static_cast<long long>(row) * kD, lane, v);
+  else
+    row_load_f32(static_cast<const float*>(p.in) + static_cast<long long>(row) * kD, lane, v);
+  if (p.w1 != nullptr) row_layernorm(v, p.w1, p.b1, lane, p.eps);
+  if (p.y_out != nullptr) row_store_f32(p.y_out + static_cast<long long>(row) * kD, lane, v);
+  if (p.z_out != nullptr) {
+    long long zrow = row;
+    if (p.z_skip > 0) {
+      const int b = row / p.seq_len, n = row % p.seq_len;
+      if (n < p.z_skip) return;
+      zrow = static_cast<long long>(b) * (p.seq_len - p.z_skip) + (n - p.z_skip);
+    }
+    if (p.w2 != nullptr) row_layernorm(v, p.w2, p.b2, lane, p.eps);
+    row_store_bf16(p.z_out + zrow * kD, lane, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ conv module core
+// Reference: conformer.py:59-66 (GLU), :69-77 + :23-25 (depthwise conv, k = 5, zero pad (2,2) inside each sequence),
+// :54-56 (Swish), :90-99 (ChanLayerNorm: mean / biased var over the 2048 channels of a token, scale only,
+// eps = 1e-4 because the activations are bf16 under autocast). Every intermediate the reference materialises in
+// bf16 is rounded to bf16 here as well.
+// in  : [B*N, 4096] bf16 (pointwise-conv output: first 2048 = value, last 2048 = gate)
+// out : [B*N, 2048] bf16
+struct ConvModParams {
+  const __nv_bfloat16* in;
+  __nv_bfloat16* out;
+  const float* dw_w;    // [2048, 5]
+  const float* dw_b;    // [2048]
+  const float* cln_w;   // [2048]
+  int B, N;
+};
+constexpr int kConvTT = 16;  // output tokens per CTA
+
+__global__ void __launch_bounds__(256) conv_module_kernel(const ConvModParams p) {
+  __shared__ float s_sum[kConvTT][8];
+  __shared__ float s_sq[kConvTT][8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c0 = tid * 8;
+  const int t0 = blockIdx.x * kConvTT;
+  const int b = blockIdx.y;
+  const __nv_bfloat16* base = p.in + static_cast<long long>(b) * p.N * (2 * kConvC);
+
+  float wt[8][5], bias[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) wt[c][j] = __ldg(p.dw_w + (c0 + c) * 5 + j);
+    bias[c] = __ldg(p.dw_b + c0 + c);
+  }
+
+  float win[5][8];
+#pragma unroll
+  for (int j = 0; j < 5; ++j)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) win[j][c] = 0.f;
+  uint4 keep[kConvTT];
+
+#pragma unroll
+  for (int r = 0; r < kConvTT + 4; ++r) {
+    const int t = t0 - 2 + r;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) win[j][c] = win[j + 1][c];
+    if (t >= 0 && t < p.N) {
+      const uint4 av = *reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * (2 * kConvC) + c0);
+      const uint4 gv = *reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * (2 * kConvC) + kConvC + c0);
+      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&av);
+      const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float a_lo = __low2float(a2[c]), a_hi = __high2float(a2[c]);
+        const float g_lo = __low2float(g2[c]), g_hi = __high2float(g2[c]);
+        win[4][2 * c + 0] = bf16_round(a_lo * bf16_round(1.0f / (1.0f + __expf(-g_lo))));
+        win[4][2 * c + 1] = bf16_round(a_hi * bf16_round(1.0f / (1.0f + __expf(-g_hi))));
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) win[4][c] = 0.f;
+    }
+    if (r >= 4) {
+      const int o = r - 4;  // output token t0 + o, window = tokens t0+o-2 .. t0+o+2
+      float sv[8];
+      float s = 0.f, q = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) acc = fmaf(wt[c][j], win[j][c], acc);
+        const float y = bf16_round(acc + bias[c]);
+        const float sw = bf16_round(y * bf16_round(1.0f / (1.0f + __expf(-y))));
+        sv[c] = sw;
+        s += sw;
+        q += sw * sw;
+      }
+      keep[o] = make_uint4(pack_bf16x2(sv[0], sv[1]), pack_bf16x2(sv[2], sv[3]), pack_bf16x2(sv[4], sv[5]), pack_bf16x2(sv[6], sv[7]));
+      s = warp_sum(s);
+      q = warp_sum(q);
+      if (lane == 0) {
+        s_sum[o][warp] = s;
+        s_sq[o][warp] = q;
+      }
+    }
+  }
+  __syncthreads();
+
+  float cw[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) cw[c] = __ldg(p.cln_w + c0 + c);
+#pragma unroll
+  for (int o = 0; o < kConvTT; ++o) {
+    const int t = t0 + o;
+    if (t >= p.N) break;
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      s += s_sum[o][w];
+      q += s_sq[o][w];
+    }
+    const float mean = s * (1.0f / kConvC);
+    const float var = fmaxf(q * (1.0f / kConvC) - mean * mean, 0.f);
+    const float mean_b = bf16_round(mean);
+    const float rstd_b = bf16_round(rsqrtf(fmaxf(bf16_round(var), 1e-4f)));
+    const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&keep[o]);
+    float y[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float lo = __low2float(k2[c]), hi = __high2float(k2[c]);
+      y[2 * c + 0] = bf16_round(bf16_round(lo - mean_b) * rstd_b) * cw[2 * c + 0];
+      y[2 * c + 1] = bf16_round(bf16_round(hi - mean_b) * rstd_b) * cw[2 * c + 1];
+    }
+    *reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * p.N + t) * kConvC + c0) =
+        make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ encoder input
+// Reference: modeling_injection_conformer.py:139-168. Target rows: semantic embedding + mask token. Prompt rows:
+// semantic embedding + LayerNorm(Linear(level-0 DAC feature)), where Linear o codes_to_features collapses to a table
+// lookup (feat_table[code] = W_fp (W_out0 codebook0[code]) , feat_const = W_fp b_out0 + b_fp), exact algebra.
+struct BuildInputParams {
+  float* x;                        // [B, N, 1024]
+  const int* sem_tokens;           // [B, T]
+  const int* sem_prompt;           // [B, P] or nullptr
+  const int* ac_prompt;            // [B, Qp, P] (level 0 used here) or nullptr
+  int ac_prompt_levels;            // Qp
+  const float* sem_emb;            // [num_semantic, 1024]
+  const float* mask_token;         // [1024]
+  const float* feat_table;         // [1024 codes, 1024]
+  const float* feat_const;         // [1024]
+  const float *fp_ln_w, *fp_ln_b;  // acoustic_feat_proj.1
+  int B, T, P;
+  float eps;
+};
+
+__global__ void __launch_bounds__(256) build_input_kernel(const BuildInputParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.P + p.T;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (row >= static_cast<long long>(p.B) * N) return;
+  const int b = static_cast<int>(row / N), n = static_cast<int>(row % N);
+  float v[32];
+  if (n < p.P) {
+    const int code = p.ac_prompt[(static_cast<long long>(b) * p.ac_prompt_levels + 0) * p.P + n];
+    row_load_f32_ldg(p.feat_table + static_cast<long long>(code) * kD, lane, v);
+    row_add_f32_ldg(p.feat_const, lane, v);
+    row_layernorm(v, p.fp_ln_w, p.fp_ln_b, lane, p.eps);
+    row_add_f32_ldg(p.sem_emb + static_cast<long long>(p.sem_prompt[static_cast<long long>(b) * p.P + n]) * kD, lane, v);
+  } else {
+    row_load_f32_ldg(p.sem_emb + static_cast<long long>(p.sem_tokens[static_cast<long long>(b) * p.T + (n - p.P)]) * kD, lane, v);
+    row_add_f32_ldg(p.mask_token, lane, v);
+  }
+  row_store_f32(p.x + row * kD, lane, v);
+}
+
+// Per-step update of the target rows (modeling_injection_conformer.py:184-197, :214-218):
+//   still masked after re-masking -> sem + mask_token;  masked before, kept now -> sem + LN(feat_table[id] + const);
+//   already unmasked earlier -> untouched.
+struct UpdateInputParams {
+  float* x;
+  const int* sem_tokens;   // [B, T]
+  const int* ids;          // [B, T] sampled level-0 codes
+  const uint8_t* mask_old; // [B, T]
+  const uint8_t* mask_new; // [B, T] or nullptr (final step: nothing is re-masked)
+  const float* sem_emb;
+  const float* mask_token;
+  const float* feat_table;
+  const float* feat_const;
+  const float *fp_ln_w, *fp_ln_b;
+  int B, T, P;
+  float eps;
+};
+
+__global__ void __launch_bounds__(256) update_input_kernel(const UpdateInputParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (r >= static_cast<long long>(p.B) * p.T) return;
+  const int b = static_cast<int>(r / p.T), t = static_cast<int>(r % p.T);
+  const bool was = p.mask_old[r] != 0;
+  const bool now = p.mask_new != nullptr && p.mask_new[r] != 0;
+  if (!was && !now) return;
+  float v[32];
+  if (now) {
+    row_load_f32_ldg(p.mask_token, lane, v);
+  } else {
+    row_load_f32_ldg(p.feat_table + static_cast<long long>(p.ids[r]) * kD, lane, v);
+    row_add_f32_ldg(p.feat_const, lane, v);
+    row_layernorm(v, p.fp_ln_w, p.fp_ln_b, lane, p.eps);
+  }
+  row_add_f32_ldg(p.sem_emb + static_cast<long long>(p.sem_tokens[r]) * kD, lane, v);
+  row_store_f32(p.x + (static_cast<long long>(b) * (p.P + p.T) + p.P + t) * kD, lane, v);
+}
+
+// ------------------------------------------------------------------------------------------------ coarse injection
+// Reference: injection_conformer_wrapper.py:107-129. At injection layer k (level k):
+//   inj = LN_k(Linear_k(sum_{i<=k} W_out_i codebook_i[code_i] + b_out_i)) = LN_k(sum_i inj_table[k][i][code_i] + inj_const[k])
+//   x   = block_out + inj + (k > 0 ? previous coarse block_out : 0)
+// code_i comes from the arg-max of this pass for target rows and from the acoustic prompt for prompt rows.
+struct InjectParams {
+  float* x;                 // out: [B, N, 1024]
+  const float* cur_out;     // block output at this injection layer (coarse_out[k])
+  const float* prev_out;    // coarse_out[k-1] or nullptr
+  const int* pred_codes;    // [B, 4, T]
+  const int* ac_prompt;     // [B, Qp, P] or nullptr
+  int ac_prompt_levels;
+  const float* tables[4];   // inj_table[k][i] : [1024 codes, 1024]
+  const float* inj_const;   // [1024]
+  const float *ln_w, *ln_b; // project_injection[k].1
+  int level;                // k
+  int B, T, P;
+  float eps;
+};
+
+__global__ void __launch_bounds__(256) inject_kernel(const InjectParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.P + p.T;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (row >= static_cast<long long>(p.B) * N) return;
+  const int b = static_cast<int>(row / N), n = static_cast<int>(row % N);
+  float v[32];
+  row_load_f32_ldg(p.inj_const, lane, v);
+  for (int i = 0; i <= p.level; ++i) {
+    int code;
+    if (n < p.P)
+      code = p.ac_prompt[(static_cast<long long>(b) * p.ac_prompt_levels + i) * p.P + n];
+    else
+      code = p.pred_codes[(static_cast<long long>(b) * 4 + i) * p.T + (n - p.P)];
+    row_add_f32_ldg(p.tables[i] + static_cast<long long>(code) * kD, lane, v);
+  }
+  row_layernorm(v, p.ln_w, p.ln_b, lane, p.eps);
+  float o[32];
+  row_load_f32(p.cur_out + row * kD, lane, o);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] += o[i];
+  if (p.prev_out != nullptr) {
+    row_load_f32(p.prev_out + row * kD, lane, o);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += o[i];
+  }
+  row_store_f32(p.x + row * kD, lane, v);
+}
+
+// ------------------------------------------------------------------------------------------------ sampling
+// Philox4x32-10, counter = (row, column group, step, 0), key = seed.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float gumbel_from_bits(uint32_t bits) {
+  const float u = (static_cast<float>(bits >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1)
+  return -__logf(-__logf(u));
+}
+
+// One warp per row of 1024 logits. id = argmax(logit + gumbel) (first index wins ties); logp = log softmax(logits)[id].
+// Reference: Categorical(logits).sample() (modeling_injection_conformer.py:192) == argmax(log p + Gumbel); arg-max
+// decoding (:185, :228, injection_conformer_wrapper.py:121) is the same kernel with no noise.
+struct SampleParams {
+  const float* logits;      // [rows, 1024] with row stride ld
+  long long ld;
+  int rows;
+  const float* noise;       // [rows, 1024] Gumbel noise (parity runs) or nullptr
+  int use_philox;           // noise == nullptr && use_philox: in-kernel Gumbel noise
+  unsigned long long seed;
+  unsigned int step;
+  const int* forced_ids;    // teacher forcing (parity runs) or nullptr
+  int* ids;                 // out (forced id when teacher forcing), element (row) lands at out_base(row)
+  int* ids_raw;             // out, the model's own choice (nullable)
+  float* logp;              // out [rows] or nullptr
+  // output index mapping: row r = (b, t, q) with r = (b*T + t)*Q + q  ->  ids[(b*out_q_stride + out_q0 + q)*T + t]
+  int T, Q, out_q_stride, out_q0;
+};
+
+__global__ void __launch_bounds__(256) sample_kernel(const SampleParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
+  if (row >= p.rows) return;
+  float v[32];
+  row_load_f32(p.logits + row * p.ld, lane, v);
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
+  mx = warp_max(mx);
+  float se = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) se += __expf(v[i] - mx);
+  se = warp_sum(se);
+
+  float best = -INFINITY;
+  int best_idx = 0x7fffffff;
+  if (p.noise != nullptr) {
+    float g[32];
+    row_load_f32(p.noise + row * kV, lane, g);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float s = v[i] + g[i];
+      const int idx = (i >> 2) * 128 + lane * 4 + (i & 3);
+      if (s > best) {
+        best = s;
+        best_idx = idx;
+      }
+    }
+  } else if (p.use_philox) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 bits = philox4x32_10(make_uint4(static_cast<uint32_t>(row), static_cast<uint32_t>(i * 32 + lane), p.step,
+                                                  static_cast<uint32_t>(row >> 32)),
+                                       make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32)));
+      const uint32_t bb[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float s = v[4 * i + j] + gumbel_from_bits(bb[j]);
+        const int idx = i * 128 + lane * 4 + j;
+        if (s > best) {
+          best = s;
+          best_idx = idx;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int idx = (i >> 2) * 128 + lane * 4 + (i & 3);
+      if (v[i] > best) {
+        best = v[i];
+        best_idx = idx;
+      }
+    }
+  }
+  // lane-local scan order is increasing in idx, so strict '>' keeps the first maximum; same rule across lanes
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+    if (ob > best || (ob == best && oi < best_idx)) {
+      best = ob;
+      best_idx = oi;
+    }
+  }
+  const long long bt = row / p.Q;
+  const int q = static_cast<int>(row % p.Q);
+  const int b = static_cast<int>(bt / p.T), t = static_cast<int>(bt % p.T);
+  const long long oidx = (static_cast<long long>(b) * p.out_q_stride + p.out_q0 + q) * p.T + t;
+  int id = best_idx;
+  if (p.forced_ids != nullptr) id = p.forced_ids[oidx];
+  if (lane == 0) {
+    p.ids[oidx] = id;
+    if (p.ids_raw != nullptr) p.ids_raw[oidx] = best_idx;
+  }
+  if (p.logp != nullptr) {
+    // the owner lane of column `id` publishes its logit
+    const int owner = (id & 127) >> 2;
+    const int slot = ((id >> 7) << 2) | (id & 3);
+    float val = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i == slot) val = v[i];
+    val = __shfl_sync(0xffffffffu, val, owner);
+    if (lane == 0) p.logp[row] = (val - mx) - __logf(se);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ re-masking
+// Reference: modeling_injection_conformer.py:199-219 + edm_tts/utils/utils.py:49-60.
+//   mask_len = max(1, min(#masked - 1, floor(float32(T) * float32(ratio))))
+//   conf     = masked ? logp + float32(temperature * ratio) * gumbel : +inf
+//   cut      = sort(conf)[mask_len];  new_mask = conf < cut
+// One CTA per sequence; the k-th order statistic is found by rank counting in shared memory (T <= 4096).
+struct RemaskParams {
+  const float* logp;        // [B, T]
+  const float* gumbel;      // [B, T] or nullptr (then Philox)
+  const uint8_t* mask_old;  // [B, T]
+  uint8_t* mask_new;        // [B, T]
+  const uint8_t* forced_mask;  // teacher forcing: copied to mask_new when given
+  int T;
+  float ratio;       // float32(cos(pi/2 (t+1)/S))
+  float temp_ratio;  // float32(temperature * ratio)
+  unsigned long long seed;
+  unsigned int step;
+};
+constexpr int kRemaskMaxT = 4096;
+
+__global__ void __launch_bounds__(256) remask_kernel(const RemaskParams p) {
+  __shared__ float conf[kRemaskMaxT];
+  __shared__ int s_count;
+  __shared__ float s_cut;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const long long base = static_cast<long long>(b) * p.T;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  int local = 0;
+  for (int t = tid; t < p.T; t += 256) {
+    const bool m = p.mask_old[base + t] != 0;
+    float c = INFINITY;
+    if (m) {
+      float g;
+      if (p.gumbel != nullptr) {
+        g = p.gumbel[base + t];
+      } else {
+        const uint4 bits = philox4x32_10(make_uint4(static_cast<uint32_t>(base + t), 0x52454d41u, p.step, 0u),
+                                         make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32)));
+        g = gumbel_from_bits(bits.x);
+      }
+      c = __fadd_rn(p.logp[base + t], __fmul_rn(p.temp_ratio, g));
+      ++local;
+    }
+    conf[t] = c;
+  }
+  atomicAdd(&s_count, local);
+  __syncthreads();
+  if (p.forced_mask != nullptr) {
+    for (int t = tid; t < p.T; t += 256) p.mask_new[base + t] = p.forced_mask[base + t];
+    return;
+  }
+  float ml = floorf(__fmul_rn(static_cast<float>(p.T), p.ratio));
+  ml = fmaxf(1.0f, fminf(static_cast<float>(s_count - 1), ml));
+  const int k = static_cast<int>(ml);
+  for (int t = tid; t < p.T; t += 256) {
+    const float c = conf[t];
+    int less = 0, leq = 0;
+    for (int u = 0; u < p.T; ++u) {
+      const float o = conf[u];
+      less += (o < c);
+      leq += (o <= c);
+    }
+    if (less <= k && k < leq) s_cut = c;  // every thread that qualifies writes the same value
+  }
+  __syncthreads();
+  const float cut = s_cut;
+  for (int t = tid; t < p.T; t += 256) p.mask_new[base + t] = conf[t] < cut ? 1 : 0;
+}
+
+}  // namespace edm

@@ -1,0 +1,156 @@
+/* edm_s2a.h — C ABI of the B200-native S2A decode path (libedm_s2a.so).
+ *
+ * The reference (naba89/EDM-TTS) has no FFI boundary: its hot path is a chain of torch.nn.Module calls. Each entry
+ * point below names the reference code it replaces (path:line relative to the reference repo). Conventions:
+ *   - every pointer is a CUDA device pointer unless the name ends in _host; `stream` is a cudaStream_t passed as void*;
+ *   - calls only enqueue work on `stream` (no device synchronisation, no allocation after edm_s2a_bind);
+ *   - return value 0 = ok, negative = error; edm_last_error() gives a thread-local message;
+ *   - bf16 buffers are raw 16-bit storage; "f32" is IEEE float; token / code ids are int32 unless stated;
+ *   - the library refuses to run on anything but compute capability 10.x (no fallback path exists).
+ */
+#ifndef EDM_S2A_H_
+#define EDM_S2A_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDM_ABI_VERSION 1
+
+enum edm_status {
+  EDM_OK = 0,
+  EDM_ERR_INVALID = -1,    /* bad argument / unsupported shape */
+  EDM_ERR_CUDA = -2,       /* CUDA runtime / driver error */
+  EDM_ERR_ARCH = -3,       /* device is not sm_100 */
+  EDM_ERR_STATE = -4       /* call order violated (e.g. decode before bind) */
+};
+
+/* GEMM epilogues (edm_gemm_bf16) */
+enum edm_epilogue {
+  EDM_EPI_BF16 = 0,        /* out_bf16 = acc + bias */
+  EDM_EPI_SWISH_BF16 = 1,  /* conformer.py:54-56,152-154  Linear -> Swish */
+  EDM_EPI_QKV_ROPE = 2,    /* conformer.py:132-138       to_q/to_kv + rotary embedding on q,k */
+  EDM_EPI_RESID_F32 = 3,   /* conformer.py:222-233       x += scale * (Linear(...)) on the fp32 residual stream */
+  EDM_EPI_F32 = 4          /* injection_conformer_wrapper.py:56-63   logits head */
+};
+
+int edm_abi_version(void);
+const char* edm_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Stateless operators (unit-parity surface)
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* out[M,N] = epilogue(A[M,K] (bf16, row pitch lda) x B[N,K]^T (bf16, row pitch ldb)), tcgen05 + TMA.
+ * Replaces nn.Linear / 1x1 nn.Conv1d calls: conformer.py:124-126,152-154,170,175; wrapper :38-63. N % 256 == 0, K % 64 == 0. */
+int edm_gemm_bf16(const void* a, long long lda, const void* b, long long ldb, int M, int N, int K, int epilogue,
+                  const float* bias, void* out, long long ldo, float scale, const float* rope_cos,
+                  const float* rope_sin, int seq_len, int rope_cols, void* stream);
+
+/* softmax(q k^T / 8) v for H heads of 64; qkv is the fused projection [B*N, 3*H*64] (q | k | v), out [B*N, H*64] bf16.
+ * Replaces Attend.flash_attn, attend.py:63-115 (non-causal, no mask, dropout 0). */
+int edm_attention(const void* qkv, int B, int N, int H, void* out, void* stream);
+/* bring-up variant exposing the MN-major V descriptor fields (bytes) */
+int edm_attention_dbg(const void* qkv, int B, int N, int H, void* out, unsigned v_lbo, unsigned v_sbo, unsigned v_kstep,
+                      void* stream);
+
+/* y = LN(in; w1,b1) [optional fp32 store], z = LN(y; w2,b2) or y [optional bf16 store, rows n < z_skip of every
+ * seq_len-long sequence dropped]. 1024 channels. Replaces nn.LayerNorm at conformer.py:106,168,216 and wrapper :44. */
+int edm_layernorm(const void* in, int in_is_bf16, int rows, const float* w1, const float* b1, const float* w2,
+                  const float* b2, float* y_out, void* z_out, int seq_len, int z_skip, float eps, void* stream);
+
+/* GLU -> depthwise conv (k=5, zero pad 2|2 per sequence) -> Swish -> ChanLayerNorm; in [B*N,4096] bf16 -> out [B*N,2048]
+ * bf16. Replaces conformer.py:171-174 (GLU :59-66, DepthWiseConv1d :69-77, Swish :54-56, ChanLayerNorm :90-99). */
+int edm_conv_module(const void* in, void* out, const float* dw_w, const float* dw_b, const float* cln_w, int B, int N,
+                    void* stream);
+
+/* Per-row arg-max / Gumbel-max sampling over 1024 logits + log-softmax of the chosen id.
+ * rows = B*T*Q; ids land at ids[(b*out_q_stride + out_q0 + q)*T + t]. noise: [rows,1024] Gumbel or NULL;
+ * use_philox: in-kernel noise when noise == NULL. Replaces modeling_injection_conformer.py:185,192,203-207,228. */
+int edm_sample(const float* logits, long long ld, int rows, const float* noise, int use_philox,
+               unsigned long long seed, unsigned step, const int* forced_ids, int* ids, float* logp, int T, int Q,
+               int out_q_stride, int out_q0, void* stream);
+
+/* Confidence re-masking of one step (modeling_injection_conformer.py:199-213 + utils/utils.py:49-60). */
+int edm_remask(const float* logp, const float* gumbel, const uint8_t* mask_old, uint8_t* mask_new,
+               const uint8_t* forced_mask, int B, int T, float ratio, float temp_ratio, unsigned long long seed,
+               unsigned step, void* stream);
+
+/* DAC residual VQ: z [B,1024,T] (fp32 or bf16) -> codes int64 [B,n_levels,T]. Replaces
+ * ResidualVectorQuantize.forward, dac/vector_quantizer.py:146-210 (codes only; eval mode). Tables are built by the
+ * host side (edm_tts_b200/dac_rvq.py) from the reference state dict. */
+int edm_rvq_encode(const void* z, int z_is_bf16, int B, int T, int n_levels, const float* w_in, const float* b_in,
+                   const float* cb_norm, const float* cb_n2, const float* g, long long* codes,
+                   const long long* forced, float* latents, void* stream);
+
+/* codes int64 [B,L,T] -> features fp32 [B,1024,T] (or [B,L,1024,T] when unreduced); proj = [12,1024,1024] projected
+ * codebooks incl. bias. Replaces from_codes / from_codes_unreduced, dac/vector_quantizer.py:212-252. */
+int edm_codes_to_features(const long long* codes, const float* proj, float* out, int B, int L, int T, int unreduced,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * S2A decoder context: InjectionConformerModel.infer_special, modeling_injection_conformer.py:130-230, and
+ * InjectionConformerWrapper.forward_first_level / forward, injection_conformer_wrapper.py:65-150.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct edm_s2a_ctx edm_s2a_ctx;
+
+typedef struct edm_s2a_config {
+  int hidden;             /* 1024 */
+  int heads;              /* 16 (head dim 64) */
+  int depth;              /* <= 16 */
+  int ff_mult;            /* 4 */
+  int conv_kernel;        /* 5 */
+  int num_quantizers;     /* 12 */
+  int num_codes;          /* 1024 */
+  int num_semantic;       /* rows of the semantic embedding */
+  int n_injection;        /* <= 4 */
+  int injection_layers[4];
+  int residual;           /* config.residual */
+  int max_positions;      /* rows of the rotary tables */
+} edm_s2a_config;
+
+/* Weight table: names are fixed by the library; the host passes one device pointer per name, in order. */
+int edm_s2a_num_weights(const edm_s2a_config* cfg);
+const char* edm_s2a_weight_name(const edm_s2a_config* cfg, int index);
+
+edm_s2a_ctx* edm_s2a_create(const edm_s2a_config* cfg, const void* const* weights, int n_weights);
+void edm_s2a_destroy(edm_s2a_ctx* ctx);
+
+size_t edm_s2a_workspace_bytes(const edm_s2a_ctx* ctx, int B, int T, int P);
+/* workspace must be 1024-byte aligned; shapes stay bound until the next bind */
+int edm_s2a_bind(edm_s2a_ctx* ctx, void* workspace, size_t bytes, int B, int T, int P);
+
+/* named views into the bound workspace (for parity tests / the Python mirror): returns device pointer or NULL */
+void* edm_s2a_buffer(edm_s2a_ctx* ctx, const char* name, size_t* bytes);
+
+/* modeling_injection_conformer.py:139-168: build encoder input + mask state (all target rows masked). */
+int edm_s2a_build_input(edm_s2a_ctx* ctx, const int* sem_tokens, const int* sem_prompt, const int* ac_prompt,
+                        int ac_prompt_levels, void* stream);
+/* wrapper :65-90: blocks 0..first injection layer + head 0 on the target rows -> buffer "logits" [B*T,1024] fp32.
+ * x_in (fp32 [B,N,1024]) replaces the context's encoder input when not NULL. */
+int edm_s2a_first_level(edm_s2a_ctx* ctx, const float* x_in, void* stream);
+/* modeling_injection_conformer.py:184-219 for step `step` of `steps`: sample/argmax, feature re-embed, re-mask. */
+int edm_s2a_step(edm_s2a_ctx* ctx, int step, int steps, float temperature, unsigned long long seed,
+                 const float* cat_noise, const float* remask_noise, const int* forced_ids, const uint8_t* forced_mask,
+                 void* stream);
+/* wrapper :92-150 + modeling :228: full pass -> codes int64 [B,12,T]. forced_coarse int32 [B,4,T] teacher-forces the
+ * tokens injected at the coarse levels (the emitted codes are still the model's own arg-max). keep_logits != 0 keeps
+ * per-level logits in buffers "coarse_logits" / "fine_logits". x_in as above. */
+int edm_s2a_full_pass(edm_s2a_ctx* ctx, const float* x_in, const int* forced_coarse, long long* codes_out,
+                      void* stream);
+/* whole infer_special: build_input, `steps` first-level passes (skipped when steps == 1), full pass. Noise / forcing
+ * arrays are laid out [step][...] and may be NULL (Philox noise from `seed`). */
+int edm_s2a_decode(edm_s2a_ctx* ctx, const int* sem_tokens, const int* sem_prompt, const int* ac_prompt,
+                   int ac_prompt_levels, int steps, float temperature, unsigned long long seed, const float* cat_noise,
+                   const float* remask_noise, const int* forced_ids, const uint8_t* forced_masks,
+                   const int* forced_coarse, long long* codes_out, void* stream);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+unsigned long long edm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDM_S2A_H_ */

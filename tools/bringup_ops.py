@@ -1,0 +1,303 @@
+"""GPU bring-up for the stateless operators: each sub-test compares one kernel with a plain torch computation and prints
+max errors (and a timing for the large shapes). Run one sub-test per process so a trap in one kernel cannot poison the
+others:  for t in gemm attn ln conv sample remask rvq; do timeout 300 python tools/bringup_ops.py $t; done
+"""
+import math
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from edm_tts_b200 import _lib as L  # noqa: E402
+
+dev = "cuda"
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def rb(x):
+    return x.to(torch.bfloat16).float()
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def rope_tables(npos):
+    inv = 1.0 / (10000 ** (torch.arange(0, 64, 2, device=dev).float() / 64))
+    t = torch.arange(npos, device=dev).float()
+    f = torch.einsum("i,j->ij", t, inv)
+    return f.cos().contiguous(), f.sin().contiguous()
+
+
+def gemm_call(a, b, epi, bias=None, out=None, scale=1.0, cos=None, sin=None, seq_len=1, rope_cols=0):
+    M, K = a.shape
+    N = b.shape[0]
+    L.check(L.lib().edm_gemm_bf16(L.ptr(a), K, L.ptr(b), K, M, N, K, epi, L.ptr(bias), L.ptr(out), out.shape[1], scale,
+                                  L.ptr(cos), L.ptr(sin), seq_len, rope_cols, L.stream_ptr()), "gemm")
+
+
+def test_gemm():
+    torch.manual_seed(0)
+    for (M, N, K) in [(128, 256, 64), (128, 256, 256), (300, 512, 1024), (1000, 1024, 4096)]:
+        a = bf(torch.randn(M, K, device=dev))
+        b = bf(torch.randn(N, K, device=dev) / math.sqrt(K))
+        bias = torch.randn(N, device=dev)
+        acc = a.float() @ b.float().T
+        # F32
+        out = torch.empty(M, N, device=dev)
+        gemm_call(a, b, L.EPI_F32, bias, out)
+        torch.cuda.synchronize()
+        err = (out - (acc + bias)).abs().max().item()
+        print(f"gemm F32   M={M} N={N} K={K} max_abs_err={err:.3e}", flush=True)
+        # BF16
+        outb = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+        gemm_call(a, b, L.EPI_BF16, bias, outb)
+        err = (outb.float() - rb(acc + bias)).abs().max().item()
+        print(f"gemm BF16  max_abs_err={err:.3e}", flush=True)
+        # SWISH
+        gemm_call(a, b, L.EPI_SWISH_BF16, bias, outb)
+        h = rb(acc + bias)
+        ref = rb(h * rb(torch.sigmoid(h)))
+        err = (outb.float() - ref).abs().max().item()
+        print(f"gemm SWISH max_abs_err={err:.3e}", flush=True)
+        # RESID
+        x0 = torch.randn(M, N, device=dev)
+        x = x0.clone()
+        gemm_call(a, b, L.EPI_RESID_F32, bias, x, scale=0.5)
+        ref = x0 + 0.5 * rb(acc + bias)
+        err = (x - ref).abs().max().item()
+        print(f"gemm RESID max_abs_err={err:.3e}", flush=True)
+        # ROPE (needs N multiple of 256; treat first half of the columns as rotary)
+        seq = 77
+        cos, sin = rope_tables(seq)
+        rope_cols = N // 2 if (N // 2) % 256 == 0 else N
+        gemm_call(a, b, L.EPI_QKV_ROPE, None, outb, cos=cos, sin=sin, seq_len=seq, rope_cols=rope_cols)
+        t = rb(acc).view(M, N // 64, 64)
+        pos = torch.arange(M, device=dev) % seq
+        c = torch.cat([cos[pos], cos[pos]], -1)[:, None, :]
+        s = torch.cat([sin[pos], sin[pos]], -1)[:, None, :]
+        rot = torch.cat([-t[..., 32:], t[..., :32]], -1)
+        r = (t * c + rot * s)
+        ref = torch.where((torch.arange(N, device=dev) < rope_cols).view(1, N // 64, 64), r, t).reshape(M, N)
+        err = (outb.float() - rb(ref)).abs().max().item()
+        print(f"gemm ROPE  max_abs_err={err:.3e} (rope_cols={rope_cols})", flush=True)
+    # timing at the bench shapes
+    for (M, N, K, epi) in [(32000, 4096, 1024, L.EPI_SWISH_BF16), (32000, 1024, 4096, L.EPI_RESID_F32), (32000, 3072, 1024, L.EPI_BF16),
+                           (32000, 1024, 1024, L.EPI_RESID_F32), (32000, 1024, 2048, L.EPI_RESID_F32)]:
+        a = bf(torch.randn(M, K, device=dev))
+        b = bf(torch.randn(N, K, device=dev) / math.sqrt(K))
+        bias = torch.randn(N, device=dev)
+        out = torch.zeros(M, N, device=dev, dtype=torch.float32 if epi == L.EPI_RESID_F32 else torch.bfloat16)
+        ms = timeit(lambda: gemm_call(a, b, epi, bias, out, scale=0.5))
+        ms_ref = timeit(lambda: torch.matmul(a, b.T))
+        print(f"gemm time M={M} N={N} K={K} epi={epi}: {ms:.3f} ms = {2 * M * N * K / ms / 1e9:.1f} TFLOP/s  (torch.matmul {ms_ref:.3f} ms = {2 * M * N * K / ms_ref / 1e9:.1f})", flush=True)
+
+
+def attn_ref(qkv, B, N, H):
+    q, k, v = qkv.float().view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    return torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * N, H * 64)
+
+
+def test_attn():
+    torch.manual_seed(0)
+    variants = [(1024, 1024, 2048), (16, 1024, 2048), (1024, 1024, 256), (2048, 1024, 2048), (1024, 2048, 2048)]
+    for (B, N, H) in [(1, 128, 1), (2, 150, 16), (2, 500, 16), (1, 1650, 16)]:
+        qkv = bf(torch.randn(B * N, 3 * H * 64, device=dev))
+        ref = attn_ref(qkv, B, N, H)
+        for v in variants:
+            out = torch.zeros(B * N, H * 64, device=dev, dtype=torch.bfloat16)
+            L.check(L.lib().edm_attention_dbg(L.ptr(qkv), B, N, H, L.ptr(out), v[0], v[1], v[2], L.stream_ptr()), "attn")
+            torch.cuda.synchronize()
+            err = (out.float() - ref).abs().max().item()
+            print(f"attn B={B} N={N} H={H} variant={v}: max_abs_err={err:.3e} nan={torch.isnan(out.float()).any().item()}", flush=True)
+            if err < 2e-2:
+                break
+    B, N, H = 64, 500, 16
+    qkv = bf(torch.randn(B * N, 3 * H * 64, device=dev))
+    out = torch.zeros(B * N, H * 64, device=dev, dtype=torch.bfloat16)
+    ms = timeit(lambda: L.check(L.lib().edm_attention(L.ptr(qkv), B, N, H, L.ptr(out), L.stream_ptr())))
+    q, k, v = qkv.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ms_ref = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
+    fl = 4 * B * H * N * N * 64
+    print(f"attn time B={B} N={N}: {ms:.3f} ms = {fl / ms / 1e9:.1f} TFLOP/s (torch sdpa {ms_ref:.3f} ms)", flush=True)
+
+
+def test_ln():
+    torch.manual_seed(0)
+    rows = 1003
+    x = torch.randn(rows, 1024, device=dev) * 2 + 0.3
+    w1, b1, w2, b2 = [torch.randn(1024, device=dev) for _ in range(4)]
+    y = torch.empty_like(x)
+    z = torch.empty(rows, 1024, device=dev, dtype=torch.bfloat16)
+    L.check(L.lib().edm_layernorm(L.ptr(x), 0, rows, L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(y), L.ptr(z), 1, 0, 1e-5, L.stream_ptr()))
+    yr = torch.nn.functional.layer_norm(x, (1024,), w1, b1)
+    zr = torch.nn.functional.layer_norm(yr, (1024,), w2, b2)
+    print(f"ln y err={(y - yr).abs().max().item():.3e} z err={(z.float() - zr).abs().max().item():.3e} (|z| max {zr.abs().max().item():.2f})", flush=True)
+    # compaction + bf16 input
+    B, N, P = 3, 50, 7
+    xb = bf(torch.randn(B * N, 1024, device=dev))
+    zt = torch.empty(B * (N - P), 1024, device=dev, dtype=torch.bfloat16)
+    L.check(L.lib().edm_layernorm(L.ptr(xb), 1, B * N, L.ptr(w1), L.ptr(b1), None, None, None, L.ptr(zt), N, P, 1e-5, L.stream_ptr()))
+    ref = torch.nn.functional.layer_norm(xb.float(), (1024,), w1, b1).view(B, N, 1024)[:, P:].reshape(-1, 1024)
+    print(f"ln compaction err={(zt.float() - ref).abs().max().item():.3e}", flush=True)
+    rows = 32000
+    x = torch.randn(rows, 1024, device=dev)
+    z = torch.empty(rows, 1024, device=dev, dtype=torch.bfloat16)
+    ms = timeit(lambda: L.lib().edm_layernorm(L.ptr(x), 0, rows, L.ptr(w1), L.ptr(b1), None, None, None, L.ptr(z), 1, 0, 1e-5, L.stream_ptr()))
+    print(f"ln time rows={rows}: {ms * 1e3:.1f} us = {rows * 6144 / ms / 1e6:.0f} GB/s", flush=True)
+
+
+def conv_ref(h, dw_w, dw_b, cln_w, B, N):
+    """bf16-autocast-like restatement of GLU -> dwconv -> swish -> chanLN"""
+    x = h.float().view(B, N, 4096)
+    a, g = x[..., :2048], x[..., 2048:]
+    glu = rb(a * rb(torch.sigmoid(g)))  # [B,N,2048]
+    xp = torch.nn.functional.pad(glu.transpose(1, 2), (2, 2))
+    y = torch.nn.functional.conv1d(xp, dw_w.view(2048, 1, 5), dw_b, groups=2048)  # [B,2048,N] fp32
+    y = rb(y)
+    s = rb(y * rb(torch.sigmoid(y)))
+    var = rb(s.var(dim=1, unbiased=False, keepdim=True))
+    mean = rb(s.mean(dim=1, keepdim=True))
+    o = rb(rb(s - mean) * rb(var.clamp(min=1e-4).rsqrt())) * cln_w.view(1, 2048, 1)
+    return rb(o).transpose(1, 2).reshape(B * N, 2048)
+
+
+def test_conv():
+    torch.manual_seed(0)
+    for (B, N) in [(2, 37), (3, 150), (2, 500)]:
+        h = bf(torch.randn(B * N, 4096, device=dev))
+        dw_w = rb(torch.randn(2048, 5, device=dev) * 0.4)
+        dw_b = torch.randn(2048, device=dev) * 0.1
+        cln_w = torch.randn(2048, device=dev)
+        out = torch.empty(B * N, 2048, device=dev, dtype=torch.bfloat16)
+        L.check(L.lib().edm_conv_module(L.ptr(h), L.ptr(out), L.ptr(dw_w), L.ptr(dw_b), L.ptr(cln_w), B, N, L.stream_ptr()))
+        ref = conv_ref(h, dw_w, dw_b, cln_w, B, N)
+        d = (out.float() - ref).abs()
+        print(f"conv B={B} N={N}: max_abs_err={d.max().item():.3e} mean={d.mean().item():.3e} frac>0.05={(d > 0.05).float().mean().item():.2e}", flush=True)
+    B, N = 64, 500
+    h = bf(torch.randn(B * N, 4096, device=dev))
+    out = torch.empty(B * N, 2048, device=dev, dtype=torch.bfloat16)
+    ms = timeit(lambda: L.lib().edm_conv_module(L.ptr(h), L.ptr(out), L.ptr(dw_w), L.ptr(dw_b), L.ptr(cln_w), B, N, L.stream_ptr()))
+    print(f"conv time B={B} N={N}: {ms * 1e3:.1f} us = {B * N * 12288 / ms / 1e6:.0f} GB/s", flush=True)
+
+
+def test_sample():
+    torch.manual_seed(0)
+    B, T, Q = 3, 50, 1
+    rows = B * T * Q
+    logits = torch.randn(rows, 1024, device=dev) * 3
+    g = -torch.log(-torch.log(torch.rand(rows, 1024, device=dev).clamp(1e-7, 1 - 1e-7)))
+    ids = torch.empty(B, T, device=dev, dtype=torch.int32)
+    logp = torch.empty(rows, device=dev)
+    L.check(L.lib().edm_sample(L.ptr(logits), 1024, rows, L.ptr(g), 0, 0, 0, None, L.ptr(ids), L.ptr(logp), T, 1, 1, 0, L.stream_ptr()))
+    ref_ids = (logits + g).argmax(-1)
+    ref_lp = torch.log_softmax(logits, -1).gather(-1, ref_ids[:, None])[:, 0]
+    print(f"sample noise: id mismatches={(ids.view(-1).long() != ref_ids).sum().item()} logp err={(logp - ref_lp).abs().max().item():.3e}", flush=True)
+    L.check(L.lib().edm_sample(L.ptr(logits), 1024, rows, None, 0, 0, 0, None, L.ptr(ids), L.ptr(logp), T, 1, 1, 0, L.stream_ptr()))
+    print(f"argmax: mismatches={(ids.view(-1).long() != logits.argmax(-1)).sum().item()}", flush=True)
+    # multi-level layout [B*T, Q, 1024] -> ids [B, Q, T]
+    Q = 8
+    logits = torch.randn(B * T * Q, 1024, device=dev)
+    ids = torch.empty(B, Q, T, device=dev, dtype=torch.int32)
+    L.check(L.lib().edm_sample(L.ptr(logits), 1024, B * T * Q, None, 0, 0, 0, None, L.ptr(ids), None, T, Q, Q, 0, L.stream_ptr()))
+    ref = logits.view(B, T, Q, 1024).argmax(-1).permute(0, 2, 1)
+    print(f"argmax multi-level: mismatches={(ids.long() != ref).sum().item()}", flush=True)
+    # philox statistics: empirical distribution of samples vs softmax
+    rows = 4096
+    base = torch.randn(1, 1024, device=dev) * 2
+    logits = base.expand(rows, 1024).contiguous()
+    ids = torch.empty(rows, device=dev, dtype=torch.int32)
+    L.check(L.lib().edm_sample(L.ptr(logits), 1024, rows, None, 1, 1234, 0, None, L.ptr(ids), None, rows, 1, 1, 0, L.stream_ptr()))
+    p = torch.softmax(base[0], -1)
+    top = p.argmax().item()
+    print(f"philox: empirical P(top)={(ids == top).float().mean().item():.4f} expected={p[top].item():.4f}", flush=True)
+
+
+def test_remask():
+    torch.manual_seed(0)
+    B, T = 5, 500
+    logp = -torch.rand(B, T, device=dev) * 5
+    g = -torch.log(-torch.log(torch.rand(B, T, device=dev).clamp(1e-7, 1 - 1e-7)))
+    mask_old = (torch.rand(B, T, device=dev) < 0.7)
+    steps, step, temp = 8, 2, 1.0
+    ratio = math.cos(math.pi / 2.0 * ((step + 1) / steps))
+    mo = mask_old.to(torch.uint8).contiguous()
+    mn = torch.empty_like(mo)
+    L.check(L.lib().edm_remask(L.ptr(logp), L.ptr(g), L.ptr(mo), L.ptr(mn), None, B, T, float(torch.tensor(ratio, dtype=torch.float32)),
+                               float(torch.tensor(temp * ratio, dtype=torch.float32)), 0, step, L.stream_ptr()))
+    init = torch.full((B,), T, device=dev, dtype=torch.long)
+    mask_len = torch.floor(init * ratio)
+    mask_len = torch.maximum(torch.ones_like(mask_len), torch.minimum(mask_old.sum(-1) - 1, mask_len))
+    sel = torch.where(mask_old, logp.exp(), torch.inf)
+    conf = torch.log(sel) + (temp * ratio) * g
+    srt, _ = torch.sort(conf, dim=-1)
+    cut = torch.take_along_dim(srt, mask_len.long().unsqueeze(-1), dim=-1)
+    ref = conf < cut
+    print(f"remask mismatches={(mn.bool() != ref).sum().item()} masked={mn.sum(-1).tolist()} ref={ref.sum(-1).tolist()}", flush=True)
+
+
+def test_rvq():
+    torch.manual_seed(0)
+    B, T, Lv = 2, 333, 12
+    z = torch.randn(B, 1024, T, device=dev)
+    w_in = torch.randn(Lv, 8, 1024, device=dev) / 32
+    b_in = torch.randn(Lv, 8, device=dev) * 0.1
+    cb = torch.randn(Lv, 1024, 8, device=dev)
+    w_out = torch.randn(Lv, 1024, 8, device=dev) * 0.2
+    b_out = torch.randn(Lv, 1024, device=dev) * 0.05
+    # reference loop (vector_quantizer.py semantics)
+    res = z.clone()
+    ref_codes = []
+    for i in range(Lv):
+        e = torch.einsum("dc,bct->bdt", w_in[i], res) + b_in[i][None, :, None]
+        enc = torch.nn.functional.normalize(e.permute(0, 2, 1).reshape(-1, 8))
+        cbn = torch.nn.functional.normalize(cb[i])
+        dist = enc.pow(2).sum(1, keepdim=True) - 2 * enc @ cbn.t() + cbn.pow(2).sum(1, keepdim=True).t()
+        idx = (-dist).max(1)[1].view(B, T)
+        ref_codes.append(idx)
+        zq = torch.einsum("cd,btd->bct", w_out[i], cb[i][idx]) + b_out[i][None, :, None]
+        res = res - zq
+    ref_codes = torch.stack(ref_codes, 1)
+    cbn = torch.nn.functional.normalize(cb, dim=-1).contiguous()
+    n2 = cbn.pow(2).sum(-1).contiguous()
+    proj = torch.einsum("lcd,lkd->lkc", w_out, cb) + b_out[:, None, :]  # [L, codes, 1024]
+    g = torch.einsum("idc,jkc->ijkd", w_in, proj).contiguous()  # [i, j, codes, 8]
+    codes = torch.empty(B, Lv, T, device=dev, dtype=torch.int64)
+    L.check(L.lib().edm_rvq_encode(L.ptr(z), 0, B, T, Lv, L.ptr(w_in.view(96, 1024).contiguous()), L.ptr(b_in.view(96).contiguous()), L.ptr(cbn),
+                                   L.ptr(n2), L.ptr(g), L.ptr(codes), None, None, L.stream_ptr()))
+    mism = (codes != ref_codes)
+    print(f"rvq free-running mismatches per level: {mism.sum((0, 2)).tolist()} of {B * T}", flush=True)
+    L.check(L.lib().edm_rvq_encode(L.ptr(z), 0, B, T, Lv, L.ptr(w_in.view(96, 1024).contiguous()), L.ptr(b_in.view(96).contiguous()), L.ptr(cbn),
+                                   L.ptr(n2), L.ptr(g), L.ptr(codes), L.ptr(ref_codes.contiguous()), None, L.stream_ptr()))
+    print(f"rvq teacher-forced mismatches per level: {(codes != ref_codes).sum((0, 2)).tolist()}", flush=True)
+    feats = torch.empty(B, 1024, T, device=dev)
+    L.check(L.lib().edm_codes_to_features(L.ptr(ref_codes.contiguous()), L.ptr(proj.contiguous()), L.ptr(feats), B, Lv, T, 0, L.stream_ptr()))
+    ref_f = sum(torch.einsum("cd,btd->bct", w_out[i], cb[i][ref_codes[:, i]]) + b_out[i][None, :, None] for i in range(Lv))
+    print(f"codes_to_features err={(feats - ref_f).abs().max().item():.3e}", flush=True)
+    B, T = 32, 3000
+    z = torch.randn(B, 1024, T, device=dev)
+    codes = torch.empty(B, Lv, T, device=dev, dtype=torch.int64)
+    ms = timeit(lambda: L.lib().edm_rvq_encode(L.ptr(z), 0, B, T, Lv, L.ptr(w_in.view(96, 1024).contiguous()), L.ptr(b_in.view(96).contiguous()),
+                                               L.ptr(cbn), L.ptr(n2), L.ptr(g), L.ptr(codes), None, None, L.stream_ptr()), iters=5, warm=2)
+    print(f"rvq time B={B} T={T}: {ms:.3f} ms = {B * T / ms / 1e3:.2f} Mframes/s, {B * T * 4192 / ms / 1e6:.0f} GB/s", flush=True)
+
+
+if __name__ == "__main__":
+    t0 = time.time()
+    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvq": test_rvq}[sys.argv[1]]()
+    torch.cuda.synchronize()
+    print(f"[{sys.argv[1]}] done in {time.time() - t0:.1f}s", flush=True)
