@@ -1,0 +1,179 @@
+"""Generate golden vectors from the UNMODIFIED reference (build container only: needs /root/reference).
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+The reference is imported from /root/reference (never copied). Harness-side patches, none of which touch reference files:
+  * DAC.from_pretrained -> construct DAC(DACConfig(...)) (the reference's own from_pretrained breaks under transformers 5.x
+    because DAC.__init__ never calls post_init());
+  * torch.multinomial and Gumbel.sample read pre-generated noise so the run is bit-deterministic;
+  * random_topk_mask / forward_first_level / encoder.forward are wrapped to record their outputs.
+Weights are the deterministic ones of oracle/weights.py loaded into the reference modules, inputs oracle.weights.make_inputs.
+Outputs: tests/golden/s2a_*.pt, tests/golden/rvq_*.pt (small tensors only).
+"""
+import os
+import sys
+import tempfile
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
+sys.dont_write_bytecode = True
+
+from oracle.weights import OracleConfig, make_inputs, make_quantizer_state_dict, make_state_dict  # noqa: E402
+
+from edm_tts.models.dac import DAC  # noqa: E402
+from edm_tts.models.dac.configuration import DACConfig  # noqa: E402
+from edm_tts.models.dac.vector_quantizer import ResidualVectorQuantize  # noqa: E402
+from edm_tts.models.injection_conformer import modeling_injection_conformer as mic  # noqa: E402
+from edm_tts.models.injection_conformer.configuration import InjectionConformerConfig  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+CONFIGS = {
+    # name: (OracleConfig, DACConfig kwargs)
+    "small": (OracleConfig(hidden=128, heads=2, depth=6, injection_layers=(1, 2, 3, 4), num_semantic=50, n_codebooks=12,
+                           codebook_size=64, codebook_dim=8, latent_dim=128),
+              dict(encoder_dim=8, decoder_dim=32, codebook_size=64)),
+    "full": (OracleConfig(), dict()),
+}
+
+
+def build_reference(cfg: OracleConfig, dac_kwargs, seed):
+    dac_cfg = DACConfig(**dac_kwargs)
+    DAC.from_pretrained = classmethod(lambda cls, path, *a, **k: cls(dac_cfg))  # shim, see module docstring
+    rc = InjectionConformerConfig(hidden_size=cfg.hidden, num_semantic_tokens=cfg.num_semantic, acoustic_model_path="unused",
+                                  encoder_num_heads=cfg.heads, encoder_num_layers=cfg.depth, encoder_ff_mult=cfg.ff_mult,
+                                  encoder_conv_kernel_size=cfg.conv_kernel, injection_layers=list(cfg.injection_layers),
+                                  residual=cfg.residual, use_injection=cfg.use_injection)
+    model = mic.InjectionConformerModel(rc).eval()
+    sd = make_state_dict(cfg, seed)
+    res = model.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    bad = [k for k in res.missing_keys if not (k.startswith("acoustic_model.encoder.") or k.startswith("acoustic_model.decoder."))]
+    assert not bad, f"hot-path keys not covered by oracle.weights: {bad[:5]}"
+    return model, sd
+
+
+class NoiseFeed:
+    """Replaces the reference's two RNG consumers with reads from pre-generated tensors and records decisions."""
+
+    def __init__(self, cat_gumbel, remask_gumbel):
+        self.cat, self.rem = cat_gumbel, remask_gumbel
+        self.i_cat = self.i_rem = 0
+        self.ids, self.masks, self.first_logits = [], [], []
+
+    def multinomial(self, probs, num_samples, replacement=False, *, generator=None):
+        g = self.cat[self.i_cat]
+        self.i_cat += 1
+        return (torch.log(probs) + g).argmax(dim=-1, keepdim=True)
+
+    def gumbel_sample(self, dist_self, sample_shape=torch.Size()):
+        g = self.rem[self.i_rem]
+        self.i_rem += 1
+        return g.unsqueeze(-1)
+
+
+def run_reference(model, inp, steps, temperature, autocast=False):
+    feed = NoiseFeed(inp["cat_gumbel"], inp["remask_gumbel"])
+    orig_multinomial, orig_gumbel = torch.multinomial, torch.distributions.gumbel.Gumbel.sample
+    orig_topk, orig_ffl, orig_fwd = mic.random_topk_mask, model.encoder.forward_first_level, model.encoder.forward
+    rec = {}
+
+    def topk(*a, **k):
+        m = orig_topk(*a, **k)
+        feed.masks.append(m.clone())
+        return m
+
+    def ffl(*a, **k):
+        out = orig_ffl(*a, **k)
+        feed.first_logits.append(out[:, 0].float().clone())
+        return out
+
+    def fwd(*a, **k):
+        out = orig_fwd(*a, **k)
+        rec["all_logits"] = out.float().clone()
+        return out
+
+    torch.multinomial = feed.multinomial
+    torch.distributions.gumbel.Gumbel.sample = feed.gumbel_sample
+    mic.random_topk_mask = topk
+    model.encoder.forward_first_level = ffl
+    model.encoder.forward = fwd
+    try:
+        with torch.inference_mode(), torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
+            codes = model.infer_special(inp["semantic_tokens"], inp["acoustic_prompt_tokens"], inp["semantic_prompt_tokens"],
+                                        steps=steps, temperature=temperature)
+    finally:
+        torch.multinomial = orig_multinomial
+        torch.distributions.gumbel.Gumbel.sample = orig_gumbel
+        mic.random_topk_mask = orig_topk
+        model.encoder.forward_first_level = orig_ffl
+        model.encoder.forward = orig_fwd
+    rec.update(codes=codes, step_masks=feed.masks, first_logits=feed.first_logits)
+    return rec
+
+
+def subsample_rows(t, n=6):
+    """Keep n evenly spaced target rows of a [B, T, V] tensor."""
+    idx = torch.linspace(0, t.shape[1] - 1, n).long()
+    return t[:, idx].clone(), idx
+
+
+def make_s2a(name, cfg_name, B, T, P, steps, seed=0, temperature=1.0, with_autocast=False):
+    cfg, dac_kwargs = CONFIGS[cfg_name]
+    torch.manual_seed(0)
+    model, _ = build_reference(cfg, dac_kwargs, seed)
+    inp = make_inputs(B, T, P, steps, cfg, seed=1234 + T + 7 * P + steps)
+    rec = run_reference(model, inp, steps, temperature)
+    gold = dict(cfg_name=cfg_name, B=B, T=T, P=P, steps=steps, weight_seed=seed, input_seed=1234 + T + 7 * P + steps, temperature=temperature,
+                codes=rec["codes"].to(torch.int16), step_masks=[m.clone() for m in rec["step_masks"]],
+                step_argmax=[l.argmax(-1).to(torch.int16) for l in rec["first_logits"]])
+    rows = [subsample_rows(l) for l in rec["first_logits"]]
+    gold["step_logit_rows"] = [r[0] for r in rows]
+    gold["row_idx"] = rows[0][1] if rows else None
+    al = rec["all_logits"]  # [B, Q, T, V]
+    idx = torch.linspace(0, T - 1, 4).long()
+    gold["final_logit_rows"] = al[:, :, idx].clone()
+    gold["final_row_idx"] = idx
+    top2 = al.topk(2, dim=-1)[0]
+    gold["final_margin"] = (top2[..., 0] - top2[..., 1]).to(torch.float16)   # reference's own top-1 margin per decision
+    if with_autocast:
+        rec_bf = run_reference(model, inp, steps, temperature, autocast=True)
+        gold["bf16_step0_logit_rows"] = rec_bf["first_logits"][0][:, rows[0][1]].clone() if rows else None
+        gold["bf16_codes"] = rec_bf["codes"].to(torch.int16)
+    torch.save(gold, os.path.join(OUT, f"s2a_{name}.pt"))
+    print(f"s2a_{name}: codes {tuple(rec['codes'].shape)} steps={steps} saved", flush=True)
+
+
+def make_rvq(name, cfg_name, B, T, seed=0):
+    cfg, dac_kwargs = CONFIGS[cfg_name]
+    q = ResidualVectorQuantize(input_dim=cfg.latent_dim, n_codebooks=cfg.n_codebooks, codebook_size=cfg.codebook_size,
+                               codebook_dim=cfg.codebook_dim, quantizer_dropout=0.5).eval()
+    q.load_state_dict(make_quantizer_state_dict(cfg, seed), strict=True)
+    g = torch.Generator().manual_seed(99 + T)
+    z = torch.randn(B, cfg.latent_dim, T, generator=g)
+    with torch.inference_mode():
+        out = q(z)
+        feats = q.from_codes(out["codes"])[0]
+        unred = q.from_codes_unreduced(out["codes"][:, :4])
+    gold = dict(cfg_name=cfg_name, B=B, T=T, weight_seed=seed, z_seed=99 + T, codes=out["codes"].to(torch.int16),
+                latents_head=out["latents"][:, :, :8].clone(), zq_head=out["z"][:, :16, :8].clone(),
+                feats_head=feats[:, :16, :8].clone(), unred_head=unred[:, :, :16, :8].clone(),
+                zq_sum=out["z"].double().sum().item(), feats_sum=feats.double().sum().item())
+    torch.save(gold, os.path.join(OUT, f"rvq_{name}.pt"))
+    print(f"rvq_{name}: codes {tuple(out['codes'].shape)} saved", flush=True)
+
+
+if __name__ == "__main__":
+    with tempfile.TemporaryDirectory():
+        make_rvq("small", "small", 2, 50)
+        make_rvq("full", "full", 2, 75)
+        make_s2a("small_s1", "small", 2, 40, 0, 1)
+        make_s2a("small_s4", "small", 2, 40, 0, 4)
+        make_s2a("small_s8_prompt", "small", 2, 40, 16, 8, with_autocast=True)
+        make_s2a("full_s1", "full", 1, 60, 0, 1)
+        make_s2a("full_s8", "full", 2, 150, 0, 8, with_autocast=True)
+        make_s2a("full_s4_prompt", "full", 1, 100, 50, 4)
