@@ -1,0 +1,276 @@
+"""S2A decode throughput on B200: decoded codec frames/s for BASELINE.json's config 2 (B=64 x 10 s = 500 frames, full
+8-step first-level schedule + full pass, bf16 tensor cores) per GPU, weak-scaled over N GPUs (one process per GPU, no
+collective on the decode path; the codes are all-gathered once per step over NCCL).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0). See DESIGN.md "Measurement" for the definition of every field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, T_FRAMES, P_PROMPT, DECODE_STEPS = 64, 500, 0, 8
+WORKLOAD = "S2A decode: batch 64 x 10 s (500 frames) per GPU, 8 first-level steps + full pass, no prompt (BASELINE config 2)"
+METRIC, UNIT = "s2a_decoded_codec_frames_per_s", "frames/s"
+
+
+def flops_per_frame(S, T):
+    """algorithmic FLOPs per target frame with no prompt."""
+    return (S * (276.82e6 + 20480.0 * T) if S > 1 else 0.0) + 922.75e6 + 65536.0 * T
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+            }
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:  # NVML missing: report that instead of fabricating clocks
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def result(self):
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p.get("bf16_tflops_sustained", 1406.7), p.get("hbm_gbs", 6460.2), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+def cpu_oracle_fps(B, T, steps, repeats, threads):
+    """Times the oracle (CPU restatement of the reference, fp32) on the host cores."""
+    import torch
+
+    from oracle import s2a as os2a
+    from oracle.weights import OracleConfig, make_inputs, make_state_dict
+
+    torch.set_num_threads(threads)
+    cfg = OracleConfig()
+    sd = make_state_dict(cfg, 0)
+    inp = make_inputs(B, T, 0, steps, cfg, seed=1234)
+    times = []
+    with torch.inference_mode():
+        for i in range(repeats + 1):
+            t0 = time.perf_counter()
+            os2a.infer_special(sd, cfg, inp["semantic_tokens"], None, None, steps=steps, cat_gumbel=inp["cat_gumbel"],
+                               remask_gumbel=inp["remask_gumbel"], mode="fp32")
+            times.append(time.perf_counter() - t0)
+    best = min(times[1:]) if repeats > 0 else times[0]
+    return B * T / best, times
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host CPU (oracle port; the Python reference itself cannot
+    travel to the GPU box), all host threads, one bounded sample per step: 1 utterance x 500 frames x 8 steps."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import s2a as os2a
+    from oracle.weights import OracleConfig, make_inputs, make_state_dict
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = OracleConfig()
+    sd = make_state_dict(cfg, 0)
+    inp = make_inputs(1, T_FRAMES, 0, DECODE_STEPS, cfg, seed=1234)
+
+    def step():
+        with torch.inference_mode():
+            os2a.infer_special(sd, cfg, inp["semantic_tokens"], None, None, steps=DECODE_STEPS, cat_gumbel=inp["cat_gumbel"],
+                               remask_gumbel=inp["remask_gumbel"], mode="fp32")
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    fps = args.steps * T_FRAMES / dt
+    sample = f"1 utterance x {T_FRAMES} frames x {DECODE_STEPS} steps per step (1/64 of the GPU arm's batch), fp32, torch CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as ge
+    ge.build()
+    from edm_tts_b200 import InjectionConformerModel, _lib
+    from edm_tts_b200.config import InjectionConformerConfig
+    from oracle.weights import OracleConfig, make_state_dict
+
+    lib = _lib.lib()
+    cfg = OracleConfig()
+    sd = make_state_dict(cfg, 0)          # random-init weights of the reference architecture (no checkpoints offline)
+    model = InjectionConformerModel(InjectionConformerConfig(), sd, device=dev)
+    del sd
+    B, T = B_PER_GPU, T_FRAMES
+    g = torch.Generator().manual_seed(1234 + rank)
+    sem_host = torch.randint(0, cfg.num_semantic, (B, T), generator=g).pin_memory()
+    codes_host = torch.empty(B, cfg.n_codebooks, T, dtype=torch.int64).pin_memory()
+    sem_dev = sem_host.to(dev)
+    gathered = [torch.empty(B, cfg.n_codebooks, T, device=dev, dtype=torch.int64) for _ in range(world)] if world > 1 else None
+
+    def step_resident():
+        codes = model.infer_special(sem_dev, None, None, steps=DECODE_STEPS, temperature=1.0, seed=rank)
+        if world > 1:
+            dist.all_gather(gathered, codes)
+        return codes
+
+    def step_e2e():
+        sd_ = sem_host.to(dev, non_blocking=True)
+        codes = model.infer_special(sd_, None, None, steps=DECODE_STEPS, temperature=1.0, seed=rank)
+        if world > 1:
+            dist.all_gather(gathered, codes)
+        codes_host.copy_(codes, non_blocking=True)
+        return codes
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, k, profile=False):
+        sync_all()
+        if profile:
+            lib.edm_prof_enable(1)
+        l0 = lib.edm_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        launches = lib.edm_launch_count() - l0
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), launches
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total, launches = timed(step_resident, args.steps, profile=True)
+    sampler.stop_flag = True
+    sampler.join()
+    pm, pw, pc = (C.c_double * 5)(), (C.c_double * 5)(), (C.c_int * 5)()
+    _lib.check(lib.edm_prof_collect(pm, pw, pc), "prof_collect")
+    lib.edm_prof_enable(0)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    frames = world * B * T * args.steps
+    value = frames / (ms_total * 1e-3)
+    e2e = frames / (ms_e2e * 1e-3)
+    tf_peak, hbm_peak, peak_kind = peaks()
+    gemm_tflops = pw[0] / (pm[0] * 1e-3) / 1e12 if pm[0] > 0 else 0.0
+    kernels = {
+        "gemm_tcgen05": {"launches": pc[0], "ms": pm[0], "tflops": gemm_tflops},
+        "attention_tcgen05": {"launches": pc[1], "ms": pm[1], "tflops": pw[1] / (pm[1] * 1e-3) / 1e12 if pm[1] > 0 else 0.0},
+        "layernorm": {"launches": pc[2], "ms": pm[2], "gbs": pw[2] / (pm[2] * 1e-3) / 1e9 if pm[2] > 0 else 0.0, "frac_hbm": pw[2] / (pm[2] * 1e-3) / 1e9 / hbm_peak if pm[2] > 0 else 0.0},
+        "conv_module": {"launches": pc[3], "ms": pm[3], "gbs": pw[3] / (pm[3] * 1e-3) / 1e9 if pm[3] > 0 else 0.0, "frac_hbm": pw[3] / (pm[3] * 1e-3) / 1e9 / hbm_peak if pm[3] > 0 else 0.0},
+    }
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "frames": T, "prompt_frames": P_PROMPT, "decode_steps": DECODE_STEPS,
+                   "weights": "random-init, reference architecture (configs/injection_conformer/base_config)",
+                   "sampling_noise": "in-kernel Philox", "l2": "working set 3.5 GB per step >> 126 MB L2 (no flush needed)",
+                   "parallelism": f"batch-sharded x{world}, all_gather of codes per step" if world > 1 else "single GPU"},
+        "clocks": sampler.result(),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": sem_host.numel() * 8 * world, "d2h_bytes_per_step": codes_host.numel() * 8 * world,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches) * world,
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (all conformer / head GEMMs of the timed region)",
+                     "achieved": gemm_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tf_peak, "traffic": None,
+                     "peak_kind": f"{peak_kind} bf16 sustained", "gemm_share_of_step": pm[0] / ms_total},
+        "kernels": kernels,
+        "model_flops_utilisation": {"algorithmic_tflops": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12,
+                                    "frac_of_peak": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12 / tf_peak},
+    }
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        fps, times = cpu_oracle_fps(1, 150, DECODE_STEPS, repeats=3, threads=threads)
+        out["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": f"oracle (fp32 torch CPU restatement of the reference) on 1 utterance x 150 frames x {DECODE_STEPS} steps "
+                                         f"(BASELINE config 1), best of 3 after 1 warm-up; runs {[round(t, 2) for t in times]} s"}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

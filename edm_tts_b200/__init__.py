@@ -1,0 +1,16 @@
+"""edm_tts_b200: B200-native S2A masked iterative decoding + DAC RVQ search behind the reference's Python API.
+
+(The directory is named edm_tts_b200 because "edm-tts_b200" is not an importable Python identifier.)
+"""
+from .config import DACConfig, InjectionConformerConfig  # noqa: F401
+
+
+def __getattr__(name):
+    # torch / CUDA are only touched when the model classes are actually requested
+    if name == "InjectionConformerModel":
+        from .s2a import InjectionConformerModel
+        return InjectionConformerModel
+    if name == "ResidualVectorQuantize":
+        from .dac_rvq import ResidualVectorQuantize
+        return ResidualVectorQuantize
+    raise AttributeError(name)

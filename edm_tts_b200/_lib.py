@@ -34,6 +34,8 @@ _SIGNATURES = {
     "edm_abi_version": (_i, []),
     "edm_last_error": (C.c_char_p, []),
     "edm_launch_count": (_ull, []),
+    "edm_prof_enable": (None, [_i]),
+    "edm_prof_collect": (_i, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "edm_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _f, _vp, _vp, _i, _i, _vp]),
     "edm_attention": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "edm_attention_dbg": (_i, [_vp, _i, _i, _i, _vp, _u, _u, _u, _vp]),

@@ -41,6 +41,50 @@ int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(EDM_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(e__)); \
   } while (0)
 
+// ---------------------------------------------------------------------------------------------- per-kernel timing
+// bench.py brackets every launch of a kernel class with CUDA events on the launching stream (edm_prof_enable) so the
+// roofline numbers come from the timed region itself, not from a profiler run.
+enum ProfKind { PK_GEMM = 0, PK_ATTN, PK_LN, PK_CONV, PK_OTHER, PK_COUNT };
+struct ProfEntry {
+  cudaEvent_t a, b;
+  int kind;
+  double work;
+};
+bool g_prof_on = false;
+std::vector<ProfEntry> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t prof_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+struct ProfScope {
+  bool on;
+  ProfEntry e;
+  cudaStream_t st;
+  ProfScope(int kind, double work, cudaStream_t s) : on(g_prof_on), st(s) {
+    if (on) {
+      e.kind = kind;
+      e.work = work;
+      e.a = prof_event();
+      e.b = prof_event();
+      cudaEventRecord(e.a, st);
+    }
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(e.b, st);
+      g_prof.push_back(e);
+    }
+  }
+};
+
 int check_arch() {
   static int cached = 1;  // 1 = unknown
   if (cached != 1) return cached;
@@ -115,6 +159,7 @@ int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
   }
   const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / kGemmBN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  ProfScope prof(PK_GEMM, 2.0 * p.M * p.N * p.K, st);
   gemm_bf16_tn_kernel<EPI><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ma, mb, p);
   EDM_LAUNCH_CHECK("gemm_bf16_tn");
   return 0;
@@ -145,6 +190,7 @@ int launch_attention(const CUtensorMap& mqkv, int B, int N, int H, void* out, ui
   p.scale_log2e = 0.125f * 1.4426950408889634f;
   p.v_lbo = lbo; p.v_sbo = sbo; p.v_kstep = kstep;
   dim3 grid((N + 127) / 128, H, B);
+  ProfScope prof(PK_ATTN, 4.0 * B * H * static_cast<double>(N) * N * 64, st);
   attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, st>>>(mqkv, p);
   EDM_LAUNCH_CHECK("attention_fwd");
   return 0;
@@ -152,6 +198,9 @@ int launch_attention(const CUtensorMap& mqkv, int B, int N, int H, void* out, ui
 
 int launch_ln(const LnParams& p, cudaStream_t st) {
   if (p.rows <= 0) return 0;
+  // algorithmic bytes: one read of the row + each requested output
+  ProfScope prof(PK_LN, static_cast<double>(p.rows) * kD * ((p.in_is_bf16 ? 2 : 4) + (p.y_out ? 4 : 0)) +
+                            (p.z_out ? static_cast<double>(p.rows) * (p.z_skip > 0 ? static_cast<double>(p.seq_len - p.z_skip) / p.seq_len : 1.0) * kD * 2 : 0.0), st);
   layernorm_kernel<<<(p.rows + 7) / 8, 256, 0, st>>>(p);
   EDM_LAUNCH_CHECK("layernorm");
   return 0;
@@ -184,6 +233,33 @@ __global__ void assemble_codes_kernel(const int* coarse, int n_coarse, const int
 extern "C" int edm_abi_version(void) { return EDM_ABI_VERSION; }
 extern "C" const char* edm_last_error(void) { return g_err; }
 extern "C" unsigned long long edm_launch_count(void) { return g_launches.load(); }
+
+extern "C" void edm_prof_enable(int on) {
+  for (auto& e : g_prof) {
+    g_event_pool.push_back(e.a);
+    g_event_pool.push_back(e.b);
+  }
+  g_prof.clear();
+  g_prof_on = on != 0;
+}
+// ms / work / count arrays of length 5: gemm (flops), attention (flops), layernorm (bytes), conv module (bytes), other.
+// Synchronises on the recorded events, so call it after the timed region.
+extern "C" int edm_prof_collect(double* ms, double* work, int* count) {
+  for (int k = 0; k < PK_COUNT; ++k) {
+    ms[k] = 0.0;
+    work[k] = 0.0;
+    count[k] = 0;
+  }
+  for (auto& e : g_prof) {
+    EDM_CUDA(cudaEventSynchronize(e.b));
+    float t = 0.f;
+    EDM_CUDA(cudaEventElapsedTime(&t, e.a, e.b));
+    ms[e.kind] += t;
+    work[e.kind] += e.work;
+    count[e.kind] += 1;
+  }
+  return 0;
+}
 
 extern "C" int edm_gemm_bf16(const void* a, long long lda, const void* b, long long ldb, int M, int N, int K, int epilogue,
                              const float* bias, void* out, long long ldo, float scale, const float* rope_cos,
@@ -402,6 +478,7 @@ int run_block_body(edm_s2a_ctx* c, int l, cudaStream_t st) {
     ConvModParams p;
     p.in = c->h; p.out = c->g; p.dw_w = c->bwf(l, F_DW_W); p.dw_b = c->bwf(l, F_DW_B); p.cln_w = c->bwf(l, F_CLN_W); p.B = c->B; p.N = c->N;
     dim3 grid((c->N + kConvTT - 1) / kConvTT, c->B);
+    ProfScope prof(PK_CONV, static_cast<double>(c->B) * c->N * 12288.0, st);
     conv_module_kernel<<<grid, 256, 0, st>>>(p);
     EDM_LAUNCH_CHECK("conv_module");
   }

@@ -1,0 +1,306 @@
+"""Host-side mirror of the reference's S2A model API on top of the C ABI (libedm_s2a.so).
+
+Mirrors edm_tts/models/injection_conformer/modeling_injection_conformer.py:25-230 (InjectionConformerModel) and
+injection_conformer_wrapper.py:9-150 (InjectionConformerWrapper): same constructor inputs (config + state dict / HF
+directory), same method names and argument meaning, same error behaviour (assert on length mismatch, ValueError for
+malformed prompts). Python only moves pointers; all arithmetic runs in the CUDA kernels. No CPU fallback exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib as L
+from .config import InjectionConformerConfig
+from .weights import pack_rvq_weights, pack_s2a_weights
+
+MAX_CHUNK = 64  # sequences decoded per bound workspace (larger batches are processed in chunks; utterances are independent)
+
+
+class _Encoder:
+    """InjectionConformerWrapper mirror: forward_first_level / forward / apply_single_to_logits."""
+
+    def __init__(self, model: "InjectionConformerModel"):
+        self._m = model
+
+    @staticmethod
+    def _prompt_len(x, mask_time_indices):
+        if mask_time_indices is None:
+            return 0
+        first = mask_time_indices[0].to(torch.int64).argmax().item() if mask_time_indices[0].any() else x.shape[1]
+        expect = torch.zeros_like(mask_time_indices)
+        expect[:, first:] = True
+        if not torch.equal(expect, mask_time_indices):
+            raise ValueError("mask_time_indices must select a common suffix [:, P:] of every sequence (as infer_special builds it)")
+        return int(first)
+
+    def forward_first_level(self, x, mask=None, mask_time_indices=None):
+        """injection_conformer_wrapper.py:65-90 -> logits [b, 1, t, codes] (fp32)."""
+        assert mask is None, "the S2A decode path never passes a padding mask"
+        m = self._m
+        B, N, _ = x.shape
+        P = self._prompt_len(x, mask_time_indices)
+        m._bind(B, N - P, P)
+        L.check(L.lib().edm_s2a_first_level(m._ctx, L.ptr(x.float().contiguous()), L.stream_ptr()), "first_level")
+        return m._view("logits", (B, 1, N - P, m.num_codevectors), torch.float32).clone()
+
+    def forward(self, x, mask=None, injections=None, acoustic_model=None, mask_time_indices=None, *, prompt_codes=None,
+                forced_coarse=None):
+        """injection_conformer_wrapper.py:92-150 in eval mode -> logits [b, q, t, codes] (fp32).
+        Prompt injections are taken as the acoustic prompt *codes* (prompt_codes [b, >=4, P]); the feature tensors the
+        reference passes in `injections` are a function of those codes and are rebuilt from the folded tables."""
+        assert mask is None, "the S2A decode path never passes a padding mask"
+        m = self._m
+        B, N, _ = x.shape
+        P = self._prompt_len(x, mask_time_indices)
+        if P > 0 and prompt_codes is None:
+            raise ValueError("with a prompt prefix pass prompt_codes=<acoustic prompt tokens>; feature-valued injections are not accepted")
+        m._bind(B, N - P, P)
+        if P > 0:
+            m._load_prompt_codes(prompt_codes)
+        codes = torch.empty(B, m.num_quantizers, N - P, device=x.device, dtype=torch.int64)
+        fc = None if forced_coarse is None else forced_coarse.to(torch.int32).contiguous()
+        L.check(L.lib().edm_s2a_full_pass(m._ctx, L.ptr(x.float().contiguous()), L.ptr(fc), L.ptr(codes), L.stream_ptr()), "full_pass")
+        n_inj = len(m.injection_layers)
+        coarse = m._view("coarse_logits", (4, B, N - P, m.num_codevectors), torch.float32)[:n_inj].permute(1, 0, 2, 3)
+        fine = m._view("fine_logits", (B, N - P, m.num_quantizers - n_inj, m.num_codevectors), torch.float32).permute(0, 2, 1, 3)
+        return torch.cat([coarse, fine], dim=1)
+
+    __call__ = forward
+
+    def apply_single_to_logits(self, inp, idx):
+        """injection_conformer_wrapper.py:56-63: LayerNorm + per-codebook head idx -> [b, 1, n, codes]."""
+        m = self._m
+        B, n, d = inp.shape
+        z = torch.empty(B * n, d, device=inp.device, dtype=torch.bfloat16)
+        w = m._w
+        L.check(L.lib().edm_layernorm(L.ptr(inp.float().contiguous()), 0, B * n, L.ptr(w["tl_ln_w"]), L.ptr(w["tl_ln_b"]), None, None, None,
+                                      L.ptr(z), 1, 0, 1e-5, L.stream_ptr()), "layernorm")
+        out = torch.empty(B * n, m.num_codevectors, device=inp.device, dtype=torch.float32)
+        head = w["head_w"][idx * m.num_codevectors:(idx + 1) * m.num_codevectors]
+        bias = w["head_b"][idx * m.num_codevectors:(idx + 1) * m.num_codevectors]
+        L.check(L.lib().edm_gemm_bf16(L.ptr(z), d, L.ptr(head), d, B * n, m.num_codevectors, d, L.EPI_F32, L.ptr(bias), L.ptr(out),
+                                      m.num_codevectors, 1.0, None, None, 1, 0, L.stream_ptr()), "gemm")
+        return out.view(B, 1, n, m.num_codevectors)
+
+
+class _AcousticModel:
+    """The slice of the DAC API the S2A path touches (dac/modeling_dac.py:173-182): code -> feature lookups."""
+
+    def __init__(self, rvq_tables, latent_dim, n_codebooks, codebook_size):
+        self._t = rvq_tables
+        self.latent_dim, self.n_codebooks, self.codebook_size = latent_dim, n_codebooks, codebook_size
+
+    def _c2f(self, codes, unreduced):
+        codes = codes.to(torch.int64).contiguous()
+        B, Lv, T = codes.shape
+        if Lv > self._t["n_levels"]:
+            raise ValueError(f"codes have {Lv} levels, quantizer has {self._t['n_levels']}")
+        shape = (B, Lv, self.latent_dim, T) if unreduced else (B, self.latent_dim, T)
+        out = torch.empty(shape, device=codes.device, dtype=torch.float32)
+        L.check(L.lib().edm_codes_to_features(L.ptr(codes), L.ptr(self._t["proj"]), L.ptr(out), B, Lv, T, int(unreduced), L.stream_ptr()),
+                "codes_to_features")
+        return out
+
+    def codes_to_features(self, codes):
+        return self._c2f(codes, False)
+
+    def codes_to_features_unreduced(self, codes):
+        return self._c2f(codes, True)
+
+
+class InjectionConformerModel:
+    """Drop-in for the reference InjectionConformerModel on the decode path (inference only)."""
+
+    def __init__(self, config, state_dict: dict, device="cuda", dac_config=None, max_positions: int = 4096):
+        if not torch.cuda.is_available():
+            raise L.EdmError("edm_tts_b200 needs a CUDA device (sm_100); there is no CPU fallback")
+        self.config = InjectionConformerConfig.from_any(config, dac_config)
+        cfg = self.config
+        self.device = torch.device(device)
+        self.injection_layers = list(cfg.injection_layers)
+        self.num_quantizers = cfg.dac.n_codebooks
+        self.num_codevectors = cfg.dac.codebook_size
+        self.acoustic_size = cfg.dac.latent_dim
+        self.loss_all = cfg.loss_all
+        lib = L.lib()
+        c = L.S2AConfig()
+        c.hidden, c.heads, c.depth, c.ff_mult, c.conv_kernel = cfg.hidden_size, cfg.heads, cfg.depth, cfg.ff_mult, cfg.conv_kernel_size
+        c.num_quantizers, c.num_codes, c.num_semantic = self.num_quantizers, self.num_codevectors, cfg.num_semantic_tokens
+        c.n_injection = len(self.injection_layers)
+        for i, l in enumerate(self.injection_layers[:4]):
+            c.injection_layers[i] = l
+        c.residual, c.max_positions = int(cfg.residual), max_positions
+        self._cfg_c = c
+        n = lib.edm_s2a_num_weights(C.byref(c))
+        if n <= 0:
+            raise ValueError("unsupported S2A configuration: " + lib.edm_last_error().decode())
+        if not cfg.use_injection:
+            raise ValueError("use_injection=False is not supported by the B200 decode path")
+        with torch.cuda.device(self.device):
+            self._w = pack_s2a_weights(state_dict, cfg, self.device, max_positions)
+            self._rvq = pack_rvq_weights(state_dict, self.num_quantizers, "acoustic_model.quantizer.", self.device)
+            names = [lib.edm_s2a_weight_name(C.byref(c), i).decode() for i in range(n)]
+            ptrs = (C.c_void_p * n)(*[self._w[name].data_ptr() for name in names])
+            self._ctx = lib.edm_s2a_create(C.byref(c), ptrs, n)
+        if not self._ctx:
+            raise L.EdmError("edm_s2a_create failed: " + lib.edm_last_error().decode())
+        self._bound = None
+        self._ws = None
+        self.encoder = _Encoder(self)
+        self.acoustic_model = _AcousticModel(self._rvq, self.acoustic_size, self.num_quantizers, self.num_codevectors)
+        self.semantic_embedding = self._w["sem_emb"]
+        self.mask_token = self._w["mask_token"].view(1, 1, -1)
+        self.training = False
+
+    # ------------------------------------------------------------------ construction helpers
+    @classmethod
+    def from_pretrained(cls, path: str, device="cuda", **kw):
+        """HF directory (config.json + model.safetensors), as written by the reference's save_pretrained."""
+        from safetensors.torch import load_file
+
+        cfg = InjectionConformerConfig.from_pretrained(path)
+        return cls(cfg, load_file(os.path.join(path, "model.safetensors")), device=device, **kw)
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ctx", None):
+                L.lib().edm_s2a_destroy(self._ctx)
+                self._ctx = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ workspace plumbing
+    def _bind(self, B, T, P):
+        key = (B, T, P)
+        if self._bound == key:
+            return
+        lib = L.lib()
+        need = lib.edm_s2a_workspace_bytes(self._ctx, B, T, P)
+        if need == 0:
+            raise ValueError(f"invalid decode shape B={B} T={T} P={P}")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        L.check(lib.edm_s2a_bind(self._ctx, self._ws.data_ptr(), self._ws.numel(), B, T, P), "bind")
+        self._bound = key
+
+    def _view(self, name, shape, dtype):
+        nbytes = C.c_size_t(0)
+        p = L.lib().edm_s2a_buffer(self._ctx, name.encode(), C.byref(nbytes))
+        if not p:
+            raise L.EdmError(f"no workspace buffer {name}")
+        off = p - self._ws.data_ptr()
+        numel = 1
+        for s in shape:
+            numel *= s
+        esz = torch.empty(0, dtype=dtype).element_size()
+        assert numel * esz <= nbytes.value, (name, shape, nbytes.value)
+        return self._ws[off:off + numel * esz].view(dtype).view(*shape)
+
+    def _load_prompt_codes(self, prompt_codes):
+        B, T, P = self._bound
+        pc = prompt_codes.to(self.device, torch.int32).contiguous()
+        dummy_sem = torch.zeros(B, T, device=self.device, dtype=torch.int32)
+        dummy_sp = torch.zeros(B, P, device=self.device, dtype=torch.int32)
+        L.check(L.lib().edm_s2a_build_input(self._ctx, L.ptr(dummy_sem), L.ptr(dummy_sp), L.ptr(pc), pc.shape[1], L.stream_ptr()), "build_input")
+
+    # ------------------------------------------------------------------ the decode API
+    @torch.no_grad()
+    def infer_special(self, semantic_tokens, acoustic_prompt_tokens=None, semantic_prompt_tokens=None, steps=1, temperature=1.0, *,
+                      seed=0, cat_gumbel=None, remask_gumbel=None, forced_ids=None, forced_masks=None, forced_coarse=None):
+        """modeling_injection_conformer.py:130-230. Returns LongTensor [b, num_quantizers, t].
+        Keyword-only extras are for parity runs: injected Gumbel noise (cat_gumbel [S-1, b*t, codes], remask_gumbel
+        [S-1, b, t]) and teacher forcing (forced_ids [S, b, t], forced_masks [S-1, b, t], forced_coarse [b, 4, t])."""
+        dev = self.device
+        st = semantic_tokens.to(dev)
+        B, T = st.shape
+        has_prompt = acoustic_prompt_tokens is not None and semantic_prompt_tokens is not None
+        P = 0
+        if has_prompt:
+            ap, sp = acoustic_prompt_tokens.to(dev), semantic_prompt_tokens.to(dev)
+            if ap.dim() != 3 or sp.dim() != 2 or ap.shape[0] != B or sp.shape[0] != B or ap.shape[-1] != sp.shape[-1]:
+                raise ValueError("prompt tokens must be acoustic [b, q, p] and semantic [b, p] with matching b and p")
+            if ap.shape[1] < len(self.injection_layers):
+                raise IndexError("acoustic prompt needs at least one level per injection layer")  # reference: list index out of range
+            P = ap.shape[-1]
+        out = torch.empty(B, self.num_quantizers, T, device=dev, dtype=torch.int64)
+        lib = L.lib()
+        for b0 in range(0, B, MAX_CHUNK):
+            b1 = min(B, b0 + MAX_CHUNK)
+            nb = b1 - b0
+            self._bind(nb, T, P)
+            sl = slice(b0, b1)
+            sem = st[sl].to(torch.int32).contiguous()
+            spc = sp[sl].to(torch.int32).contiguous() if has_prompt else None
+            apc = ap[sl].to(torch.int32).contiguous() if has_prompt else None
+            cg = None if cat_gumbel is None else cat_gumbel.to(dev).view(-1, B, T, self.num_codevectors)[:, sl].contiguous().float()
+            rg = None if remask_gumbel is None else remask_gumbel.to(dev)[:, sl].contiguous().float()
+            fi = None if forced_ids is None else forced_ids.to(dev)[:, sl].to(torch.int32).contiguous()
+            fm = None if forced_masks is None else forced_masks.to(dev)[:, sl].to(torch.uint8).contiguous()
+            fc = None if forced_coarse is None else forced_coarse.to(dev)[sl].to(torch.int32).contiguous()
+            codes = torch.empty(nb, self.num_quantizers, T, device=dev, dtype=torch.int64)
+            L.check(lib.edm_s2a_decode(self._ctx, L.ptr(sem), L.ptr(spc), L.ptr(apc), apc.shape[1] if has_prompt else 0, int(steps),
+                                       float(temperature), int(seed) + b0, L.ptr(cg), L.ptr(rg), L.ptr(fi), L.ptr(fm), L.ptr(fc), L.ptr(codes),
+                                       L.stream_ptr()), "decode")
+            out[sl] = codes
+        return out
+
+    generate = infer_special
+
+    @torch.no_grad()
+    def decode_trace(self, semantic_tokens, acoustic_prompt_tokens=None, semantic_prompt_tokens=None, steps=1, temperature=1.0, *,
+                     seed=0, cat_gumbel=None, remask_gumbel=None, forced_ids=None, forced_masks=None, forced_coarse=None):
+        """infer_special run stage by stage through the same C entry points edm_s2a_decode composes, returning every
+        intermediate (per-step first-level logits / own ids / masks, per-level final logits). Parity tests only."""
+        dev, lib = self.device, L.lib()
+        st = semantic_tokens.to(dev).to(torch.int32).contiguous()
+        B, T = st.shape
+        assert B <= MAX_CHUNK
+        has_prompt = acoustic_prompt_tokens is not None and semantic_prompt_tokens is not None
+        ap = acoustic_prompt_tokens.to(dev).to(torch.int32).contiguous() if has_prompt else None
+        sp = semantic_prompt_tokens.to(dev).to(torch.int32).contiguous() if has_prompt else None
+        P = ap.shape[-1] if has_prompt else 0
+        self._bind(B, T, P)
+        s_ = L.stream_ptr()
+        L.check(lib.edm_s2a_build_input(self._ctx, L.ptr(st), L.ptr(sp), L.ptr(ap), ap.shape[1] if has_prompt else 0, s_), "build_input")
+        tr = dict(step_logits=[], step_ids=[], step_masks=[], x0=self._view("x_in", (B, P + T, self.config.hidden_size), torch.float32).clone())
+        V = self.num_codevectors
+        if steps > 1:
+            for s in range(steps):
+                last = s == steps - 1
+                L.check(lib.edm_s2a_first_level(self._ctx, None, s_), "first_level")
+                tr["step_logits"].append(self._view("logits", (B, T, V), torch.float32).clone())
+                cg = None if (cat_gumbel is None or last) else cat_gumbel[s].to(dev).float().contiguous()
+                rg = None if (remask_gumbel is None or last) else remask_gumbel[s].to(dev).float().contiguous()
+                fi = None if forced_ids is None else forced_ids[s].to(dev).to(torch.int32).contiguous()
+                fm = None if (forced_masks is None or last) else forced_masks[s].to(dev).to(torch.uint8).contiguous()
+                L.check(lib.edm_s2a_step(self._ctx, s, int(steps), float(temperature), int(seed), L.ptr(cg), L.ptr(rg), L.ptr(fi), L.ptr(fm), s_), "step")
+                tr["step_ids"].append(self._view("ids_raw", (B, T), torch.int32).clone().long())
+                if not last:
+                    tr["step_masks"].append(self._view("mask", (B, T), torch.uint8).clone().bool())
+        tr["x_final"] = self._view("x_in", (B, P + T, self.config.hidden_size), torch.float32).clone()
+        codes = torch.empty(B, self.num_quantizers, T, device=dev, dtype=torch.int64)
+        fc = None if forced_coarse is None else forced_coarse.to(dev).to(torch.int32).contiguous()
+        L.check(lib.edm_s2a_full_pass(self._ctx, None, L.ptr(fc), L.ptr(codes), s_), "full_pass")
+        n_inj = len(self.injection_layers)
+        coarse = self._view("coarse_logits", (4, B, T, V), torch.float32)[:n_inj].permute(1, 0, 2, 3)
+        fine = self._view("fine_logits", (B, T, self.num_quantizers - n_inj, V), torch.float32).permute(0, 2, 1, 3)
+        tr["all_logits"] = torch.cat([coarse, fine], dim=1).clone()
+        tr["codes"] = codes
+        return tr
+
+    def forward(self, acoustic_tokens, semantic_tokens):
+        """Training forward (modeling_injection_conformer.py:76-128) is outside the accelerated decode path."""
+        assert acoustic_tokens.shape[-1] == semantic_tokens.shape[-1], "Acoustic and semantic tokens must have same length"
+        raise NotImplementedError("training forward is not part of the B200 decode path (SURVEY.md section 8: out of scope)")
+
+    __call__ = forward

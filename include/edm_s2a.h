@@ -149,6 +149,11 @@ int edm_s2a_decode(edm_s2a_ctx* ctx, const int* sem_tokens, const int* sem_promp
                    const int* forced_coarse, long long* codes_out, void* stream);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 unsigned long long edm_launch_count(void);
+/* Measurement hooks (bench.py): while enabled, every GEMM / attention / LayerNorm / conv-module launch is bracketed by
+ * CUDA events on its stream. edm_prof_collect fills 5-element arrays (gemm, attention, layernorm, conv module, other):
+ * summed milliseconds, summed algorithmic work (FLOPs for the first two, bytes for the rest) and launch counts. */
+void edm_prof_enable(int on);
+int edm_prof_collect(double* ms, double* work, int* count);
 
 #ifdef __cplusplus
 }

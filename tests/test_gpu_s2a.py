@@ -1,0 +1,121 @@
+"""GPU parity of the S2A decode path (through the C ABI) against the oracle and the reference's golden vectors.
+
+Tolerances (bf16 tensor-core GEMMs with fp32 accumulation vs the fp32 oracle; logits are ~unit variance):
+  first-level / final logits: max |diff| < 0.15, mean |diff| < 0.02; every arg-max disagreement must be a near-tie, i.e. the
+  oracle's own margin between its choice and ours is < 0.12 (SURVEY.md section 8c protocol, teacher-forced upstream).
+Index / mask work that does not depend on bf16 logits (encoder input, re-masking given forced ids, code assembly) is exact.
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+MAX_TOL, MEAN_TOL = 0.15, 0.02
+
+
+def _check_reports(reports):
+    for r in reports:
+        print(f"{r['what']:32s} max={r['max']:.4f} mean={r['mean']:.5f} agree={r['agree']:.4f} mismatch={r['n_mismatch']}/{r['n']} "
+              f"not_near_tie={r['n_not_near_tie']} worst_margin={r['worst_margin']:.4f}")
+    for r in reports:
+        assert r["max"] < MAX_TOL and r["mean"] < MEAN_TOL, r
+        assert r["n_not_near_tie"] == 0, r
+        assert r["agree"] > 0.9, r
+
+
+@pytest.mark.parametrize("B,T,P,steps", [(2, 150, 0, 8), (1, 60, 0, 1), (1, 100, 50, 4), (3, 77, 33, 2)])
+def test_teacher_forced_parity_vs_oracle(B, T, P, steps):
+    from tests.parity_utils import full_model, teacher_forced_parity
+
+    cfg, sd, model = full_model()
+    inp, ref, ours, reports = teacher_forced_parity(cfg, sd, model, B, T, P, steps, input_seed=1234 + T + 7 * P + steps)
+    # encoder input: gathers + LayerNorm only -> tight
+    torch.testing.assert_close(ours["x0"], ref["x0"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(ours["x_final"], ref["x_final"], rtol=1e-4, atol=2e-4)
+    _check_reports(reports)
+    # the model's own sampled ids under the same injected noise agree except at near-ties
+    for s in range(len(ref["step_ids"])):
+        agree = (ours["step_ids"][s] == ref["step_ids"][s]).float().mean().item()
+        assert agree > 0.9, (s, agree)
+
+
+@pytest.mark.parametrize("name", ["full_s1", "full_s8", "full_s4_prompt"])
+def test_against_reference_golden(name, golden_dir):
+    """Free-running CUDA decode vs the codes the unmodified reference produced (fp32, CPU). Without teacher forcing a
+    single near-tie flip cascades, so the bar is per-level agreement, not equality; the first level of a 1-step decode has no
+    cascade and must agree except at near-ties (reference margin from the golden file)."""
+    from oracle.weights import make_inputs
+    from tests.parity_utils import full_model
+
+    g = torch.load(os.path.join(golden_dir, f"s2a_{name}.pt"))
+    cfg, sd, model = full_model(g["weight_seed"])
+    inp = make_inputs(g["B"], g["T"], g["P"], g["steps"], cfg, seed=g["input_seed"])
+    codes = model.infer_special(inp["semantic_tokens"], inp["acoustic_prompt_tokens"], inp["semantic_prompt_tokens"], steps=g["steps"],
+                                temperature=g["temperature"], cat_gumbel=inp["cat_gumbel"] if g["steps"] > 1 else None,
+                                remask_gumbel=inp["remask_gumbel"] if g["steps"] > 1 else None)
+    ref = g["codes"].long().to(codes.device)
+    assert codes.shape == ref.shape and codes.dtype == torch.int64
+    agree = (codes == ref).float().mean(dim=(0, 2))
+    print(name, "per-level agreement with the reference:", [round(a, 3) for a in agree.tolist()])
+    if g["steps"] == 1:
+        mism = codes[:, 0] != ref[:, 0]
+        margin = g["final_margin"][:, 0].float().to(codes.device)
+        assert (margin[mism] < 0.12).all(), margin[mism]
+        assert agree[0] > 0.93
+    # multi-step free-running decodes diverge chaotically after the first flipped sample (random-init network); the strict
+    # multi-step check is the teacher-forced test above, this one only guards against gross errors
+    assert agree.mean() > (0.5 if g["steps"] == 1 else 0.15)
+
+
+def test_batch_chunking_and_determinism(monkeypatch):
+    """B > MAX_CHUNK is decoded in chunks; rows must not depend on which chunk / batch they were decoded in (this is
+    what makes N-GPU batch sharding bit-identical to 1 GPU)."""
+    from oracle.weights import make_inputs
+    from tests.parity_utils import full_model
+
+    cfg, sd, model = full_model()
+    inp = make_inputs(5, 64, 0, 3, cfg, seed=7)
+    kw = dict(steps=3, cat_gumbel=inp["cat_gumbel"], remask_gumbel=inp["remask_gumbel"])
+    all_codes = model.infer_special(inp["semantic_tokens"], None, None, **kw)
+    again = model.infer_special(inp["semantic_tokens"], None, None, **kw)
+    assert torch.equal(all_codes, again)
+    sub = slice(2, 4)
+    V = cfg.codebook_size
+    part = model.infer_special(inp["semantic_tokens"][sub], None, None, steps=3,
+                               cat_gumbel=inp["cat_gumbel"].view(2, 5, 64, V)[:, sub].reshape(2, -1, V),
+                               remask_gumbel=inp["remask_gumbel"][:, sub])
+    assert torch.equal(part, all_codes[sub])
+    import edm_tts_b200.s2a as s2a_mod
+
+    monkeypatch.setattr(s2a_mod, "MAX_CHUNK", 2)
+    chunked = model.infer_special(inp["semantic_tokens"], None, None, **kw)
+    assert torch.equal(chunked, all_codes)
+
+
+def test_philox_path_runs_and_is_seeded():
+    from oracle.weights import make_inputs
+    from tests.parity_utils import full_model
+
+    cfg, sd, model = full_model()
+    inp = make_inputs(2, 50, 0, 1, cfg, seed=3)
+    a = model.infer_special(inp["semantic_tokens"], None, None, steps=4, seed=11)
+    b = model.infer_special(inp["semantic_tokens"], None, None, steps=4, seed=11)
+    c = model.infer_special(inp["semantic_tokens"], None, None, steps=4, seed=12)
+    assert torch.equal(a, b)
+    assert not torch.equal(a, c)
+    assert a.min() >= 0 and a.max() < cfg.codebook_size
+
+
+def test_api_errors():
+    from tests.parity_utils import full_model
+
+    cfg, sd, model = full_model()
+    sem = torch.zeros(1, 10, dtype=torch.long)
+    with pytest.raises(ValueError):
+        model.infer_special(sem, torch.zeros(1, 12, 5, dtype=torch.long), torch.zeros(1, 6, dtype=torch.long))
+    with pytest.raises(IndexError):
+        model.infer_special(sem, torch.zeros(1, 2, 5, dtype=torch.long), torch.zeros(1, 5, dtype=torch.long))
+    with pytest.raises(AssertionError):
+        model.forward(torch.zeros(1, 12, 9, dtype=torch.long), sem)
