@@ -206,6 +206,19 @@ int launch_ln(const LnParams& p, cudaStream_t st) {
   return 0;
 }
 
+int launch_conv(const ConvModParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    EDM_CUDA(cudaFuncSetAttribute(conv_module_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
+    attr_set = true;
+  }
+  dim3 grid((p.N + kConvTT - 1) / kConvTT, p.B);
+  ProfScope prof(PK_CONV, static_cast<double>(p.B) * p.N * 12288.0, st);
+  conv_module_kernel<<<grid, 256, kConvSmemBytes, st>>>(p);
+  EDM_LAUNCH_CHECK("conv_module");
+  return 0;
+}
+
 int launch_sample(const SampleParams& p, cudaStream_t st) {
   if (p.rows <= 0) return 0;
   sample_kernel<<<(p.rows + 7) / 8, 256, 0, st>>>(p);
@@ -302,10 +315,7 @@ extern "C" int edm_conv_module(const void* in, void* out, const float* dw_w, con
   ConvModParams p;
   p.in = static_cast<const __nv_bfloat16*>(in); p.out = static_cast<__nv_bfloat16*>(out);
   p.dw_w = dw_w; p.dw_b = dw_b; p.cln_w = cln_w; p.B = B; p.N = N;
-  dim3 grid((N + kConvTT - 1) / kConvTT, B);
-  conv_module_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  EDM_LAUNCH_CHECK("conv_module");
-  return 0;
+  return launch_conv(p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int edm_sample(const float* logits, long long ld, int rows, const float* noise, int use_philox, unsigned long long seed,
@@ -477,10 +487,7 @@ int run_block_body(edm_s2a_ctx* c, int l, cudaStream_t st) {
   {
     ConvModParams p;
     p.in = c->h; p.out = c->g; p.dw_w = c->bwf(l, F_DW_W); p.dw_b = c->bwf(l, F_DW_B); p.cln_w = c->bwf(l, F_CLN_W); p.B = c->B; p.N = c->N;
-    dim3 grid((c->N + kConvTT - 1) / kConvTT, c->B);
-    ProfScope prof(PK_CONV, static_cast<double>(c->B) * c->N * 12288.0, st);
-    conv_module_kernel<<<grid, 256, 0, st>>>(p);
-    EDM_LAUNCH_CHECK("conv_module");
+    if (int rc = launch_conv(p, st)) return rc;
   }
   if (int rc = launch_gemm(EPI_RESID_F32, c->m_g, c->bmaps[l].pw2, gp(M, 1024, 2048, c->bwf(l, F_PW2_B), c->x, 1024, 1.0f), st)) return rc;
   // ff2

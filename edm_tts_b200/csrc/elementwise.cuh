@@ -146,16 +146,18 @@ struct ConvModParams {
   const float* cln_w;   // [2048]
   int B, N;
 };
-constexpr int kConvTT = 16;  // output tokens per CTA
+constexpr int kConvTT = 24;  // output tokens per CTA (4 halo rows are re-read and re-gated: 17 % overhead)
+constexpr uint32_t kConvSmemBytes = kConvTT * 256 * 16;  // per-thread spill of the Swish outputs (bf16 x 8 per token)
 
-__global__ void __launch_bounds__(256) conv_module_kernel(const ConvModParams p) {
+__global__ void __launch_bounds__(256, 2) conv_module_kernel(const ConvModParams p) {
+  extern __shared__ uint4 s_keep[];  // [kConvTT][256]
   __shared__ float s_sum[kConvTT][8];
   __shared__ float s_sq[kConvTT][8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c0 = tid * 8;
   const int t0 = blockIdx.x * kConvTT;
   const int b = blockIdx.y;
-  const __nv_bfloat16* base = p.in + static_cast<long long>(b) * p.N * (2 * kConvC);
+  const __nv_bfloat16* base = p.in + static_cast<long long>(b) * p.N * (2 * kConvC) + c0;
 
   float wt[8][5], bias[8];
 #pragma unroll
@@ -170,47 +172,70 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModParams p)
   for (int j = 0; j < 5; ++j)
 #pragma unroll
     for (int c = 0; c < 8; ++c) win[j][c] = 0.f;
-  uint4 keep[kConvTT];
+
+  // two rows of loads in flight ahead of the arithmetic
+  uint4 pa[2], pg[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int t = t0 - 2 + r;
+    if (t >= 0 && t < p.N) {
+      pa[r] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * (2 * kConvC));
+      pg[r] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * (2 * kConvC) + kConvC);
+    } else {
+      pa[r] = make_uint4(0, 0, 0, 0);
+      pg[r] = make_uint4(0, 0, 0, 0);
+    }
+  }
 
 #pragma unroll
   for (int r = 0; r < kConvTT + 4; ++r) {
-    const int t = t0 - 2 + r;
+    const uint4 av = pa[r & 1], gv = pg[r & 1];
+    {
+      const int tn = t0 + r;  // row r + 2
+      if (r + 2 < kConvTT + 4 && tn >= 0 && tn < p.N) {
+        pa[r & 1] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(tn) * (2 * kConvC));
+        pg[r & 1] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(tn) * (2 * kConvC) + kConvC);
+      } else {
+        pa[r & 1] = make_uint4(0, 0, 0, 0);
+        pg[r & 1] = make_uint4(0, 0, 0, 0);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int c = 0; c < 8; ++c) win[j][c] = win[j + 1][c];
-    if (t >= 0 && t < p.N) {
-      const uint4 av = *reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * (2 * kConvC) + c0);
-      const uint4 gv = *reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * (2 * kConvC) + kConvC + c0);
-      const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&av);
-      const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
+    {
+      // GLU: value * bf16(sigmoid(gate)), rounded to bf16 (zero rows stay zero: 0 * 0.5 = 0)
+      const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float a_lo = __low2float(a2[c]), a_hi = __high2float(a2[c]);
-        const float g_lo = __low2float(g2[c]), g_hi = __high2float(g2[c]);
-        win[4][2 * c + 0] = bf16_round(a_lo * bf16_round(1.0f / (1.0f + __expf(-g_lo))));
-        win[4][2 * c + 1] = bf16_round(a_hi * bf16_round(1.0f / (1.0f + __expf(-g_hi))));
+        const uint32_t sg = pack_bf16x2(sigmoid_tanh(bf16lo(gw[c])), sigmoid_tanh(bf16hi(gw[c])));
+        const uint32_t gl = bf16x2_mul(aw[c], sg);
+        win[4][2 * c + 0] = bf16lo(gl);
+        win[4][2 * c + 1] = bf16hi(gl);
       }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 8; ++c) win[4][c] = 0.f;
     }
     if (r >= 4) {
       const int o = r - 4;  // output token t0 + o, window = tokens t0+o-2 .. t0+o+2
-      float sv[8];
+      uint32_t sp[4];
       float s = 0.f, q = 0.f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float acc = 0.f;
+      for (int c = 0; c < 4; ++c) {
+        float acc0 = bias[2 * c], acc1 = bias[2 * c + 1];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) acc = fmaf(wt[c][j], win[j][c], acc);
-        const float y = bf16_round(acc + bias[c]);
-        const float sw = bf16_round(y * bf16_round(1.0f / (1.0f + __expf(-y))));
-        sv[c] = sw;
-        s += sw;
-        q += sw * sw;
+        for (int j = 0; j < 5; ++j) {
+          acc0 = fmaf(wt[2 * c][j], win[j][2 * c], acc0);
+          acc1 = fmaf(wt[2 * c + 1][j], win[j][2 * c + 1], acc1);
+        }
+        const uint32_t y2 = pack_bf16x2(acc0, acc1);
+        const uint32_t sg = pack_bf16x2(sigmoid_tanh(bf16lo(y2)), sigmoid_tanh(bf16hi(y2)));
+        sp[c] = bf16x2_mul(y2, sg);
+        const float v0 = bf16lo(sp[c]), v1 = bf16hi(sp[c]);
+        s += v0 + v1;
+        q = fmaf(v0, v0, q);
+        q = fmaf(v1, v1, q);
       }
-      keep[o] = make_uint4(pack_bf16x2(sv[0], sv[1]), pack_bf16x2(sv[2], sv[3]), pack_bf16x2(sv[4], sv[5]), pack_bf16x2(sv[6], sv[7]));
+      s_keep[o * 256 + tid] = make_uint4(sp[0], sp[1], sp[2], sp[3]);
       s = warp_sum(s);
       q = warp_sum(q);
       if (lane == 0) {
@@ -224,7 +249,7 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModParams p)
   float cw[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) cw[c] = __ldg(p.cln_w + c0 + c);
-#pragma unroll
+#pragma unroll 4
   for (int o = 0; o < kConvTT; ++o) {
     const int t = t0 + o;
     if (t >= p.N) break;
@@ -236,18 +261,18 @@ __global__ void __launch_bounds__(256) conv_module_kernel(const ConvModParams p)
     }
     const float mean = s * (1.0f / kConvC);
     const float var = fmaxf(q * (1.0f / kConvC) - mean * mean, 0.f);
-    const float mean_b = bf16_round(mean);
-    const float rstd_b = bf16_round(rsqrtf(fmaxf(bf16_round(var), 1e-4f)));
-    const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&keep[o]);
-    float y[8];
+    const uint32_t mean2 = pack_bf16x2(mean, mean);
+    const float rs = rsqrtf(fmaxf(bf16_round(var), 1e-4f));
+    const uint32_t rstd2 = pack_bf16x2(rs, rs);
+    const uint4 k = s_keep[o * 256 + tid];
+    const uint32_t kw[4] = {k.x, k.y, k.z, k.w};
+    uint32_t ow[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const float lo = __low2float(k2[c]), hi = __high2float(k2[c]);
-      y[2 * c + 0] = bf16_round(bf16_round(lo - mean_b) * rstd_b) * cw[2 * c + 0];
-      y[2 * c + 1] = bf16_round(bf16_round(hi - mean_b) * rstd_b) * cw[2 * c + 1];
+      const uint32_t n2 = bf16x2_mul(bf16x2_sub(kw[c], mean2), rstd2);
+      ow[c] = pack_bf16x2(bf16lo(n2) * cw[2 * c], bf16hi(n2) * cw[2 * c + 1]);
     }
-    *reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * p.N + t) * kConvC + c0) =
-        make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+    *reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * p.N + t) * kConvC + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
   }
 }
 

@@ -3,8 +3,10 @@
 //
 //   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B swizzle, kStages-deep mbarrier ring)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (128 x 256 x 16 per instruction, fp32 accum in TMEM)
-//   warps 2..5  : epilogue (tcgen05.ld -> registers -> fused op -> global), overlapped with the next tile's mainloop
-//                 through two TMEM accumulator buffers (2 x 256 columns = all 512 columns).
+//   warps 2..9  : epilogue (tcgen05.ld -> registers -> fused op -> global), overlapped with the next tile's mainloop
+//                 through two TMEM accumulator buffers (2 x 256 columns = all 512 columns). Warp w reads TMEM lane
+//                 quadrant w % 4 and column half (w - 2) / 4; the next chunk's tcgen05.ld is in flight while the
+//                 current one is processed.
 //
 // Fused epilogues cover every GEMM of the conformer block (reference: edm_tts/models/conformer/conformer.py:149-181,
 // 113-146) and the logits heads (injection_conformer_wrapper.py:38-63); rounding points follow bf16 autocast:
@@ -40,7 +42,8 @@ constexpr int kGemmBM = 128;
 constexpr int kGemmBN = 256;
 constexpr int kGemmBK = 64;
 constexpr int kGemmStages = 4;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmEpiWarps = 8;  // two per TMEM lane quadrant, each owning half of the tile's columns
+constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
 constexpr uint32_t kGemmABytes = kGemmBM * kGemmBK * 2;
 constexpr uint32_t kGemmBBytes = kGemmBN * kGemmBK * 2;
 constexpr uint32_t kGemmStageBytes = kGemmABytes + kGemmBBytes;
@@ -83,10 +86,12 @@ __device__ __forceinline__ void gemm_epilogue_32(const GemmParams& p, int row, i
   } else {
     if constexpr (EPI == EPI_SWISH_BF16) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float h = bf16_round(v[i]);
-        float s = bf16_round(sigmoidf_fast(h));
-        v[i] = h * s;
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t h2 = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        const uint32_t s2 = pack_bf16x2(sigmoid_tanh(bf16lo(h2)), sigmoid_tanh(bf16hi(h2)));
+        const uint32_t o2 = bf16x2_mul(h2, s2);
+        v[2 * i] = bf16lo(o2);
+        v[2 * i + 1] = bf16hi(o2);
       }
     }
     uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col);
@@ -170,7 +175,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 128);
+      mbar_init(&tmem_empty_bar[b], 32 * kGemmEpiWarps);
     }
     fence_mbar_init();
   }
@@ -234,7 +239,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   } else {
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;   // which 128 of the tile's 256 columns
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -242,23 +248,30 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const int row = m_blk * kGemmBM + quad * 32 + lane;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kGemmBN;
+      const int col0 = n_blk * kGemmBN + half * 128;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kGemmBN + half * 128;
       if constexpr (EPI == EPI_QKV_ROPE) {
-#pragma unroll 1
-        for (int c = 0; c < kGemmBN / 64; ++c) {
-          uint32_t lo[32], hi[32];
-          tmem_ld_32x32(taddr + c * 64, lo);
-          tmem_ld_32x32(taddr + c * 64 + 32, hi);
-          tmem_ld_wait();
-          if (row < p.M) gemm_epilogue_rope64(p, row, n_blk * kGemmBN + c * 64, lo, hi);
+        uint32_t lo[2][32], hi[2][32];
+        tmem_ld_32x32(taddr, lo[0]);
+        tmem_ld_32x32(taddr + 32, hi[0]);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld_wait_dep(lo[c]);
+          tmem_ld_wait_dep(hi[c]);
+          if (c == 0) {
+            tmem_ld_32x32(taddr + 64, lo[1]);
+            tmem_ld_32x32(taddr + 96, hi[1]);
+          }
+          if (row < p.M) gemm_epilogue_rope64(p, row, col0 + c * 64, lo[c], hi[c]);
         }
       } else {
-#pragma unroll 1
-        for (int c = 0; c < kGemmBN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c * 32, r);
-          tmem_ld_wait();
-          if (row < p.M) gemm_epilogue_32<EPI>(p, row, n_blk * kGemmBN + c * 32, r);
+        uint32_t r[2][32];
+        tmem_ld_32x32(taddr, r[0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld_wait_dep(r[c & 1]);
+          if (c + 1 < 4) tmem_ld_32x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+          if (row < p.M) gemm_epilogue_32<EPI>(p, row, col0 + c * 32, r[c & 1]);
         }
       }
       tc_fence_before();
