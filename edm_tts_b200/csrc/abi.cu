@@ -189,7 +189,7 @@ int launch_attention(const CUtensorMap& mqkv, int B, int N, int H, void* out, ui
   p.ldo = static_cast<long long>(H) * 64;
   p.scale_log2e = 0.125f * 1.4426950408889634f;
   p.v_lbo = lbo; p.v_sbo = sbo; p.v_kstep = kstep;
-  dim3 grid((N + 127) / 128, H, B);
+  dim3 grid((N + 255) / 256, H, B);
   ProfScope prof(PK_ATTN, 4.0 * B * H * static_cast<double>(N) * N * 64, st);
   attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, st>>>(mqkv, p);
   EDM_LAUNCH_CHECK("attention_fwd");
@@ -322,7 +322,7 @@ extern "C" int edm_sample(const float* logits, long long ld, int rows, const flo
                           unsigned step, const int* forced_ids, int* ids, float* logp, int T, int Q, int out_q_stride, int out_q0, void* stream) {
   if (int rc = check_arch()) return rc;
   SampleParams p;
-  p.logits = logits; p.ld = ld; p.rows = rows; p.noise = noise; p.use_philox = use_philox; p.seed = seed; p.step = step;
+  p.logits = logits; p.ld = ld; p.rows = rows; p.noise = noise; p.use_philox = use_philox; p.seed = seed; p.step = step; p.row0 = 0;
   p.forced_ids = forced_ids; p.ids = ids; p.ids_raw = nullptr; p.logp = logp; p.T = T; p.Q = Q; p.out_q_stride = out_q_stride; p.out_q0 = out_q0;
   return launch_sample(p, static_cast<cudaStream_t>(stream));
 }
@@ -333,7 +333,7 @@ extern "C" int edm_remask(const float* logp, const float* gumbel, const uint8_t*
   if (T > kRemaskMaxT) return fail(EDM_ERR_INVALID, "remask supports T <= %d", kRemaskMaxT);
   RemaskParams p;
   p.logp = logp; p.gumbel = gumbel; p.mask_old = mask_old; p.mask_new = mask_new; p.forced_mask = forced_mask;
-  p.T = T; p.ratio = ratio; p.temp_ratio = temp_ratio; p.seed = seed; p.step = step;
+  p.T = T; p.ratio = ratio; p.temp_ratio = temp_ratio; p.seed = seed; p.step = step; p.row0 = 0;
   remask_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   EDM_LAUNCH_CHECK("remask");
   return 0;
@@ -420,6 +420,7 @@ struct edm_s2a_ctx {
   int *ids, *ids_raw, *pred_codes, *pred_raw, *fine_codes, *sem_tokens, *sem_prompt, *ac_prompt;
   uint8_t *mask_a, *mask_b;
   int ac_levels = 0;
+  long long batch_offset = 0;  // global index of this context's first sequence (Philox counters)
   bool mask_in_a = true;  // which buffer holds the current mask
   CUtensorMap m_z, m_h, m_g, m_zt, m_fine_z, m_qkv;
 
@@ -714,6 +715,12 @@ extern "C" int edm_s2a_first_level(edm_s2a_ctx* c, const float* x_in, void* stre
   return launch_gemm(EPI_F32, c->m_zt, c->head_map, p, st);
 }
 
+extern "C" int edm_s2a_set_batch_offset(edm_s2a_ctx* c, long long batch_offset) {
+  if (c == nullptr || batch_offset < 0) return fail(EDM_ERR_INVALID, "batch offset");
+  c->batch_offset = batch_offset;
+  return 0;
+}
+
 extern "C" int edm_s2a_step(edm_s2a_ctx* c, int step, int steps, float temperature, unsigned long long seed, const float* cat_noise,
                             const float* remask_noise, const int* forced_ids, const uint8_t* forced_mask, void* stream) {
   if (c == nullptr || !c->bound) return fail(EDM_ERR_STATE, "context not bound");
@@ -722,7 +729,7 @@ extern "C" int edm_s2a_step(edm_s2a_ctx* c, int step, int steps, float temperatu
   const bool last = step == steps - 1;
   SampleParams sp;
   sp.logits = c->logits; sp.ld = 1024; sp.rows = c->Mt; sp.noise = last ? nullptr : cat_noise; sp.use_philox = last ? 0 : 1; sp.seed = seed;
-  sp.step = static_cast<unsigned>(step); sp.forced_ids = forced_ids; sp.ids = c->ids; sp.ids_raw = c->ids_raw; sp.logp = last ? nullptr : c->logp;
+  sp.step = static_cast<unsigned>(step); sp.row0 = c->batch_offset * c->T; sp.forced_ids = forced_ids; sp.ids = c->ids; sp.ids_raw = c->ids_raw; sp.logp = last ? nullptr : c->logp;
   sp.T = c->T; sp.Q = 1; sp.out_q_stride = 1; sp.out_q0 = 0;
   if (int rc = launch_sample(sp, st)) return rc;
   uint8_t* m_old = c->mask_cur();
@@ -733,7 +740,7 @@ extern "C" int edm_s2a_step(edm_s2a_ctx* c, int step, int steps, float temperatu
     RemaskParams rp;
     rp.logp = c->logp; rp.gumbel = remask_noise; rp.mask_old = m_old; rp.mask_new = c->mask_next(); rp.forced_mask = forced_mask;
     rp.T = c->T; rp.ratio = static_cast<float>(ratio_d); rp.temp_ratio = static_cast<float>(static_cast<double>(temperature) * ratio_d);
-    rp.seed = seed; rp.step = static_cast<unsigned>(step);
+    rp.seed = seed; rp.step = static_cast<unsigned>(step); rp.row0 = c->batch_offset * c->T;
     remask_kernel<<<c->B, 256, 0, st>>>(rp);
     EDM_LAUNCH_CHECK("remask");
     m_new = c->mask_next();
@@ -778,7 +785,7 @@ extern "C" int edm_s2a_full_pass(edm_s2a_ctx* c, const float* x_in, const int* f
       if (int rc = launch_gemm(EPI_F32, c->m_zt, c->head_map, p, st)) return rc;
     }
     SampleParams sp;
-    sp.logits = lk; sp.ld = 1024; sp.rows = c->Mt; sp.noise = nullptr; sp.use_philox = 0; sp.seed = 0; sp.step = 0; sp.forced_ids = forced_coarse;
+    sp.logits = lk; sp.ld = 1024; sp.rows = c->Mt; sp.noise = nullptr; sp.use_philox = 0; sp.seed = 0; sp.step = 0; sp.row0 = 0; sp.forced_ids = forced_coarse;
     sp.ids = c->pred_codes; sp.ids_raw = c->pred_raw; sp.logp = nullptr; sp.T = c->T; sp.Q = 1; sp.out_q_stride = 4; sp.out_q0 = k;
     if (int rc = launch_sample(sp, st)) return rc;
     InjectParams ip;
@@ -815,7 +822,7 @@ extern "C" int edm_s2a_full_pass(edm_s2a_ctx* c, const float* x_in, const int* f
   }
   {
     SampleParams sp;
-    sp.logits = c->fine_logits; sp.ld = 1024; sp.rows = c->Mt * nf; sp.noise = nullptr; sp.use_philox = 0; sp.seed = 0; sp.step = 0; sp.forced_ids = nullptr;
+    sp.logits = c->fine_logits; sp.ld = 1024; sp.rows = c->Mt * nf; sp.noise = nullptr; sp.use_philox = 0; sp.seed = 0; sp.step = 0; sp.row0 = 0; sp.forced_ids = nullptr;
     sp.ids = c->fine_codes; sp.ids_raw = nullptr; sp.logp = nullptr; sp.T = c->T; sp.Q = nf; sp.out_q_stride = nf; sp.out_q0 = 0;
     if (int rc = launch_sample(sp, st)) return rc;
   }

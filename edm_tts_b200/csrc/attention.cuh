@@ -1,17 +1,18 @@
 // Non-causal multi-head attention for the conformer block (reference: edm_tts/models/conformer/attend.py:63-115 via
 // conformer.py:128-146): softmax(q k^T / sqrt(64)) v, H heads of 64, no mask, one sequence = one batch element.
 //
-// One CTA = 128 query rows of one (batch, head). Both contractions run on tcgen05 with fp32 accumulators in TMEM:
-//   S = Q K^T : A = Q  [128 x 64]  K-major smem,  B = K tile [128 x 64] K-major smem   -> TMEM cols [0,128)
-//   O = P V   : A = P  [128 x 128] K-major smem (written by the softmax warps as bf16),
-//               B = V tile [128 kv x 64] which TMA delivers with the head dim contiguous = MN-major B operand
-//                                                                                        -> TMEM cols [128,192)
-//   warps 0..3 : softmax, one query row per thread (TMEM lane == row, so no shuffles): two passes over S in
-//                32-column tcgen05.ld chunks (row max, then exp2 + bf16 P into 128B-swizzled smem); the running
-//                output lives in registers and is rescaled there, each P V product is read back from TMEM and added.
-//   warp 4     : TMA producer (Q once, then a 2-deep K/V ring)
-//   warp 5     : TMEM allocator + single-thread MMA issuer
-// 112 KB smem + 256 TMEM columns per CTA -> two CTAs per SM overlap each other's softmax and MMA phases.
+// One CTA = 256 query rows (two 128-row tiles, "ping" and "pong") of one (batch, head). Both contractions run on
+// tcgen05 with fp32 accumulators in TMEM (all 512 columns: S0 | S1 | O0 | O1):
+//   S_w = Q_w K^T : A = Q_w [128 x 64] K-major smem,  B = K tile [128 x 64] K-major smem        -> 128 TMEM columns
+//   O_w += P_w V  : A = P_w [128 x 128] K-major smem (bf16, written by the softmax warps),
+//                   B = V tile [128 kv x 64]: TMA delivers it with the head dim contiguous = MN-major B  -> 64 columns
+//   warps 0..3 / 4..7 : softmax warpgroup of tile 0 / 1, one query row per thread (TMEM lane == row, no shuffles).
+//                       The whole S row (128 fp32) is pulled into registers once; P goes to 128B-swizzled smem.
+//                       O stays in TMEM and is rescaled there only when the running max moves by more than 2^8
+//                       (warp-uniform decision), so after the first tile the rescale path is practically never taken.
+//   warp 8            : TMA producer (both Q tiles once, then a 3-deep K/V ring shared by the two query tiles)
+//   warp 9            : TMEM allocator + single-thread MMA issuer. Issue order S0 S1 | PV0 S0' | PV1 S1' | ... keeps the
+//                       tensor pipe busy on one tile while the other tile's warpgroup is in its exp2 phase.
 #pragma once
 #include "ptx.cuh"
 
@@ -27,29 +28,44 @@ struct AttnParams {
   uint32_t v_lbo, v_sbo, v_kstep;
 };
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;
+constexpr int kAttnKvStages = 3;
 constexpr uint32_t kAttnTile = 128 * 64 * 2;  // 16 KB: one [128 x 64] bf16 tile
-constexpr uint32_t kAttnSmemBytes = kAttnTile /*Q*/ + 2 * kAttnTile /*K*/ + 2 * kAttnTile /*V*/ + 2 * kAttnTile /*P*/ + 256;
+constexpr uint32_t kAttnSmemBytes = 2 * kAttnTile /*Q0,Q1*/ + 2 * kAttnKvStages * kAttnTile /*K,V ring*/ + 4 * kAttnTile /*P0,P1*/ + 256;
+constexpr float kAttnRescaleThreshold = 8.0f;  // log2 units
 
-__global__ void __launch_bounds__(kAttnThreads, 2)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0],"
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16,"
+      " %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kAttnTile;
-  uint8_t* sV = sK + 2 * kAttnTile;
-  uint8_t* sP = sV + 2 * kAttnTile;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kAttnTile);
+  uint8_t* sQ = smem;                                   // 2 tiles
+  uint8_t* sK = sQ + 2 * kAttnTile;                     // kAttnKvStages tiles
+  uint8_t* sV = sK + kAttnKvStages * kAttnTile;         // kAttnKvStages tiles
+  uint8_t* sP = sV + kAttnKvStages * kAttnTile;         // 2 x (2 half tiles)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kAttnTile);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kv_full = bars + 1;                   // [3]
+  uint64_t* kv_empty = bars + 1 + kAttnKvStages;  // [3]
+  uint64_t* s_full = bars + 1 + 2 * kAttnKvStages;  // [2]
+  uint64_t* p_full = s_full + 2;                    // [2]
+  uint64_t* o_full = p_full + 2;                    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qt2 = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int n_kv = (p.N + 127) / 128;
 
   if (threadIdx.x == 0) {
@@ -59,174 +75,209 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
     }
     tma_prefetch_desc(&tma_qkv);
     mbar_init(q_full, 1);
-    mbar_init(&kv_full[0], 1);
-    mbar_init(&kv_full[1], 1);
-    mbar_init(&kv_empty[0], 1);
-    mbar_init(&kv_empty[1], 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    for (int s = 0; s < kAttnKvStages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int w = 0; w < 2; ++w) {
+      mbar_init(&s_full[w], 1);
+      mbar_init(&p_full[w], 128);
+      mbar_init(&o_full[w], 1);
+    }
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<256>(tmem_slot);
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;        // 128 columns
-  const uint32_t tmem_O = tmem_base + 128;  // 64 columns
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, kAttnTile);
-      tma_load_3d(&tma_qkv, q_full, sQ, p.q_col0 + h * 64, qt * 128, b);
+      mbar_arrive_expect_tx(q_full, 2 * kAttnTile);
+      tma_load_3d(&tma_qkv, q_full, sQ, p.q_col0 + h * 64, qt2 * 256, b);
+      tma_load_3d(&tma_qkv, q_full, sQ + kAttnTile, p.q_col0 + h * 64, qt2 * 256 + 128, b);
       for (int j = 0; j < n_kv; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        const int s = j % kAttnKvStages;
+        mbar_wait(&kv_empty[s], ((j / kAttnKvStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[s], 2 * kAttnTile);
         tma_load_3d(&tma_qkv, &kv_full[s], sK + s * kAttnTile, p.k_col0 + h * 64, j * 128, b);
         tma_load_3d(&tma_qkv, &kv_full[s], sV + s * kAttnTile, p.v_col0 + h * 64, j * 128, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
-      const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ), 16, 1024);
-      mbar_wait(q_full, 0);
-      // S_0
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      {
-        const uint64_t kdesc = umma_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t qdesc[2] = {umma_desc_sw128(smem_u32(sQ), 16, 1024), umma_desc_sw128(smem_u32(sQ + kAttnTile), 16, 1024)};
+      auto issue_s = [&](int w, int stage) {
+        const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + stage * kAttnTile), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(s_full);
-      }
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j & 1;
-        // P_j is in smem, S_j and O_{j-1} have been drained from TMEM
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-        const uint64_t pdesc0 = umma_desc_sw128(smem_u32(sP), 16, 1024);
-        const uint64_t pdesc1 = umma_desc_sw128(smem_u32(sP + kAttnTile), 16, 1024);
-        const uint32_t v_addr = smem_u32(sV + s * kAttnTile);
+        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + w * 128, qdesc[w] + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[w]);
+      };
+      auto issue_pv = [&](int w, int stage, int j) {
+        const uint32_t p_addr = smem_u32(sP + w * 2 * kAttnTile);
+        const uint64_t pdesc0 = umma_desc_sw128(p_addr, 16, 1024);
+        const uint64_t pdesc1 = umma_desc_sw128(p_addr + kAttnTile, 16, 1024);
+        const uint32_t v_addr = smem_u32(sV + stage * kAttnTile);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint64_t adesc = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
           const uint64_t bdesc = umma_desc_sw128(v_addr + k * p.v_kstep, p.v_lbo, p.v_sbo);
-          umma_ss(tmem_O, adesc, bdesc, idesc_o, k != 0);
+          umma_ss(tmem_base + 256 + w * 64, adesc, bdesc, idesc_o, (j > 0 || k != 0) ? 1u : 0u);
         }
-        umma_commit(o_full);
-        umma_commit(&kv_empty[s]);
-        if (j + 1 < n_kv) {
-          const int s1 = (j + 1) & 1;
-          mbar_wait(&kv_full[s1], ((j + 1) >> 1) & 1);
+        umma_commit(&o_full[w]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % kAttnKvStages;
+        const int s1 = (j + 1) % kAttnKvStages;
+        const bool more = j + 1 < n_kv;
+        // tile 0: P0(j) is in smem and S0(j) has been drained (and O0 rescaled if needed)
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, s, j);
+        if (more) {
+          mbar_wait(&kv_full[s1], ((j + 1) / kAttnKvStages) & 1);
           tc_fence_after();
-          const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + s1 * kAttnTile), 16, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem_S, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(s_full);
+          issue_s(0, s1);
         }
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, s, j);
+        umma_commit(&kv_empty[s]);  // K_j / V_j no longer needed once everything issued so far has completed
+        if (more) issue_s(1, s1);
       }
     }
   } else {
-    // ---- softmax: thread <-> query row
-    const int row_in_tile = warp * 32 + lane;
-    const int q_row = qt * 128 + row_in_tile;
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o_acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+    // ---- softmax warpgroups: w = 0 (warps 0..3) / 1 (warps 4..7); thread <-> query row
+    const int w = warp >> 2;
+    const int row_in_tile = (warp & 3) * 32 + lane;
+    const int q_row = qt2 * 256 + w * 128 + row_in_tile;
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tmem_S = tmem_base + w * 128 + lane_off;
+    const uint32_t tmem_O = tmem_base + 256 + w * 64 + lane_off;
     const float sl2 = p.scale_log2e;
-    uint8_t* p_row = sP + row_in_tile * 128;
+    uint8_t* p_row = sP + w * 2 * kAttnTile + row_in_tile * 128;
     const int sw = row_in_tile & 7;
+    float m_ref = -INFINITY;  // reference max in scaled log2 units
+    float l_run = 0.f;
 
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(&s_full[w], j & 1);
       tc_fence_after();
-      const int kv_valid = p.N - j * 128;  // columns >= kv_valid are padding
-      float mx = m_run;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_S + lane_off + c * 32, r);
-        tmem_ld_wait();
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      tmem_ld_32x32(tmem_S, s0);
+      tmem_ld_32x32(tmem_S + 32, s1);
+      tmem_ld_32x32(tmem_S + 64, s2);
+      tmem_ld_32x32(tmem_S + 96, s3);
+      tmem_ld_wait_dep(s0);
+      tmem_ld_wait_dep(s1);
+      tmem_ld_wait_dep(s2);
+      tmem_ld_wait_dep(s3);
+      const int kv_valid = p.N - j * 128;
+      if (kv_valid < 128) {  // only the last tile of a ragged sequence: padded key columns -> -inf
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(r[i]);
-          if (c * 32 + i < kv_valid) mx = fmaxf(mx, s);
+          if (i >= kv_valid) s0[i] = 0xff800000u;
+          if (32 + i >= kv_valid) s1[i] = 0xff800000u;
+          if (64 + i >= kv_valid) s2[i] = 0xff800000u;
+          if (96 + i >= kv_valid) s3[i] = 0xff800000u;
         }
       }
-      const float alpha = (m_run == -INFINITY) ? 0.f : exp2f((m_run - mx) * sl2);
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
+        mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
+        mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
+      }
+      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+      // lazy rescale: keep the old reference unless the max moved by more than 2^8 (p stays <= 256, exact enough in fp32/bf16)
+      const bool need = m_new - m_ref > kAttnRescaleThreshold;  // true at j == 0 (m_ref = -inf)
+      float alpha = 1.0f;
+      if (need) {
+        alpha = exp2f(m_ref - m_new);  // 0 at j == 0
+        m_ref = m_new;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        // O_w *= alpha in TMEM; PV(j-1) must have completed, PV(j) is not issued before our p_full arrive
+        mbar_wait(&o_full[w], (j - 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_O + lane_off + c * 32, r);
-          tmem_ld_wait();
+          uint32_t o[32];
+          tmem_ld_32x32(tmem_O + c * 32, o);
+          tmem_ld_wait_dep(o);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = (o_acc[c * 32 + i] + __uint_as_float(r[i])) * alpha;
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32(tmem_O + c * 32, o);
         }
+        tmem_st_wait();
       }
       l_run *= alpha;
-      const float mb = mx * sl2;
-      float lsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_S + lane_off + c * 32, r);
-        tmem_ld_wait();
-        uint32_t w[16];
+      float ls0 = 0.f, ls1 = 0.f;
+      auto emit = [&](uint32_t (&s)[32], int c) {
+        uint32_t wv[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float p0 = (c * 32 + 2 * i < kv_valid) ? exp2f(fmaf(__uint_as_float(r[2 * i]), sl2, -mb)) : 0.f;
-          float p1 = (c * 32 + 2 * i + 1 < kv_valid) ? exp2f(fmaf(__uint_as_float(r[2 * i + 1]), sl2, -mb)) : 0.f;
-          lsum += p0 + p1;
-          w[i] = pack_bf16x2(p0, p1);
+          const float p0 = exp2f(fmaf(__uint_as_float(s[2 * i]), sl2, -m_ref));
+          const float p1 = exp2f(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -m_ref));
+          ls0 += p0;
+          ls1 += p1;
+          wv[i] = pack_bf16x2(p0, p1);
         }
         // 32 kv columns = 64 B = four 16 B chunks of this row; 128B swizzle: chunk index ^= (row & 7)
         uint8_t* half = p_row + (c >> 1) * kAttnTile;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int chunk = ((c & 1) * 4 + q) ^ sw;
-          *reinterpret_cast<uint4*>(half + chunk * 16) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+          *reinterpret_cast<uint4*>(half + chunk * 16) = make_uint4(wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
         }
-      }
-      l_run += lsum;
-      m_run = mx;
+      };
+      emit(s0, 0);
+      emit(s1, 1);
+      emit(s2, 2);
+      emit(s3, 3);
+      l_run += ls0 + ls1;
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[w]);
     }
-    // last P V product
-    mbar_wait(o_full, (n_kv - 1) & 1);
+    // epilogue: O_w / l
+    mbar_wait(&o_full[w], (n_kv - 1) & 1);
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_O + lane_off + c * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = (o_acc[c * 32 + i] + __uint_as_float(r[i])) * inv_l;
-    }
+    uint32_t o0[32], o1[32];
+    tmem_ld_32x32(tmem_O, o0);
+    tmem_ld_32x32(tmem_O + 32, o1);
+    tmem_ld_wait_dep(o0);
+    tmem_ld_wait_dep(o1);
     if (q_row < p.N) {
       uint4* o = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * p.N + q_row) * p.ldo + h * 64);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        o[i] = make_uint4(pack_bf16x2(o_acc[8 * i + 0], o_acc[8 * i + 1]), pack_bf16x2(o_acc[8 * i + 2], o_acc[8 * i + 3]),
-                          pack_bf16x2(o_acc[8 * i + 4], o_acc[8 * i + 5]), pack_bf16x2(o_acc[8 * i + 6], o_acc[8 * i + 7]));
+      for (int i = 0; i < 4; ++i) {
+        o[i] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * i + 0]) * inv_l, __uint_as_float(o0[8 * i + 1]) * inv_l),
+                          pack_bf16x2(__uint_as_float(o0[8 * i + 2]) * inv_l, __uint_as_float(o0[8 * i + 3]) * inv_l),
+                          pack_bf16x2(__uint_as_float(o0[8 * i + 4]) * inv_l, __uint_as_float(o0[8 * i + 5]) * inv_l),
+                          pack_bf16x2(__uint_as_float(o0[8 * i + 6]) * inv_l, __uint_as_float(o0[8 * i + 7]) * inv_l));
+        o[4 + i] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * i + 0]) * inv_l, __uint_as_float(o1[8 * i + 1]) * inv_l),
+                              pack_bf16x2(__uint_as_float(o1[8 * i + 2]) * inv_l, __uint_as_float(o1[8 * i + 3]) * inv_l),
+                              pack_bf16x2(__uint_as_float(o1[8 * i + 4]) * inv_l, __uint_as_float(o1[8 * i + 5]) * inv_l),
+                              pack_bf16x2(__uint_as_float(o1[8 * i + 6]) * inv_l, __uint_as_float(o1[8 * i + 7]) * inv_l));
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<256>(tmem_base);
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace edm

@@ -431,6 +431,7 @@ struct SampleParams {
   int use_philox;           // noise == nullptr && use_philox: in-kernel Gumbel noise
   unsigned long long seed;
   unsigned int step;
+  long long row0;           // global index of row 0 (keeps the Philox stream independent of batch chunking / sharding)
   const int* forced_ids;    // teacher forcing (parity runs) or nullptr
   int* ids;                 // out (forced id when teacher forcing), element (row) lands at out_base(row)
   int* ids_raw;             // out, the model's own choice (nullable)
@@ -471,8 +472,8 @@ __global__ void __launch_bounds__(256) sample_kernel(const SampleParams p) {
   } else if (p.use_philox) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const uint4 bits = philox4x32_10(make_uint4(static_cast<uint32_t>(row), static_cast<uint32_t>(i * 32 + lane), p.step,
-                                                  static_cast<uint32_t>(row >> 32)),
+      const uint4 bits = philox4x32_10(make_uint4(static_cast<uint32_t>(p.row0 + row), static_cast<uint32_t>(i * 32 + lane), p.step,
+                                                  static_cast<uint32_t>((p.row0 + row) >> 32)),
                                        make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32)));
       const uint32_t bb[4] = {bits.x, bits.y, bits.z, bits.w};
 #pragma unroll
@@ -545,6 +546,7 @@ struct RemaskParams {
   float temp_ratio;  // float32(temperature * ratio)
   unsigned long long seed;
   unsigned int step;
+  long long row0;    // global index of element (0, 0)
 };
 constexpr int kRemaskMaxT = 4096;
 
@@ -565,7 +567,7 @@ __global__ void __launch_bounds__(256) remask_kernel(const RemaskParams p) {
       if (p.gumbel != nullptr) {
         g = p.gumbel[base + t];
       } else {
-        const uint4 bits = philox4x32_10(make_uint4(static_cast<uint32_t>(base + t), 0x52454d41u, p.step, 0u),
+        const uint4 bits = philox4x32_10(make_uint4(static_cast<uint32_t>(p.row0 + base + t), 0x52454d41u, p.step, static_cast<uint32_t>((p.row0 + base + t) >> 32)),
                                          make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32)));
         g = gumbel_from_bits(bits.x);
       }

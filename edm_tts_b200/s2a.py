@@ -216,9 +216,10 @@ class InjectionConformerModel:
     # ------------------------------------------------------------------ the decode API
     @torch.no_grad()
     def infer_special(self, semantic_tokens, acoustic_prompt_tokens=None, semantic_prompt_tokens=None, steps=1, temperature=1.0, *,
-                      seed=0, cat_gumbel=None, remask_gumbel=None, forced_ids=None, forced_masks=None, forced_coarse=None):
+                      seed=0, batch_offset=0, cat_gumbel=None, remask_gumbel=None, forced_ids=None, forced_masks=None, forced_coarse=None):
         """modeling_injection_conformer.py:130-230. Returns LongTensor [b, num_quantizers, t].
-        Keyword-only extras are for parity runs: injected Gumbel noise (cat_gumbel [S-1, b*t, codes], remask_gumbel
+        seed / batch_offset drive the in-kernel Philox noise: row r of the call draws from counter (batch_offset + r), so a
+        batch decoded in chunks or shards gives the same tokens as in one piece. Other keyword-only extras are for parity runs: injected Gumbel noise (cat_gumbel [S-1, b*t, codes], remask_gumbel
         [S-1, b, t]) and teacher forcing (forced_ids [S, b, t], forced_masks [S-1, b, t], forced_coarse [b, 4, t])."""
         dev = self.device
         st = semantic_tokens.to(dev)
@@ -248,8 +249,9 @@ class InjectionConformerModel:
             fm = None if forced_masks is None else forced_masks.to(dev)[:, sl].to(torch.uint8).contiguous()
             fc = None if forced_coarse is None else forced_coarse.to(dev)[sl].to(torch.int32).contiguous()
             codes = torch.empty(nb, self.num_quantizers, T, device=dev, dtype=torch.int64)
+            L.check(lib.edm_s2a_set_batch_offset(self._ctx, int(batch_offset) + b0), "set_batch_offset")
             L.check(lib.edm_s2a_decode(self._ctx, L.ptr(sem), L.ptr(spc), L.ptr(apc), apc.shape[1] if has_prompt else 0, int(steps),
-                                       float(temperature), int(seed) + b0, L.ptr(cg), L.ptr(rg), L.ptr(fi), L.ptr(fm), L.ptr(fc), L.ptr(codes),
+                                       float(temperature), int(seed), L.ptr(cg), L.ptr(rg), L.ptr(fi), L.ptr(fm), L.ptr(fc), L.ptr(codes),
                                        L.stream_ptr()), "decode")
             out[sl] = codes
         return out

@@ -126,6 +126,10 @@ int edm_s2a_bind(edm_s2a_ctx* ctx, void* workspace, size_t bytes, int B, int T, 
 /* named views into the bound workspace (for parity tests / the Python mirror): returns device pointer or NULL */
 void* edm_s2a_buffer(edm_s2a_ctx* ctx, const char* name, size_t* bytes);
 
+/* Global index of this context's first sequence inside the caller's whole batch. The in-kernel Philox counters are
+ * offset by it so the sampled tokens do not depend on how the batch is chunked or sharded over GPUs. */
+int edm_s2a_set_batch_offset(edm_s2a_ctx* ctx, long long batch_offset);
+
 /* modeling_injection_conformer.py:139-168: build encoder input + mask state (all target rows masked). */
 int edm_s2a_build_input(edm_s2a_ctx* ctx, const int* sem_tokens, const int* sem_prompt, const int* ac_prompt,
                         int ac_prompt_levels, void* stream);
