@@ -11,8 +11,11 @@
 //                       O stays in TMEM and is rescaled there only when the running max moves by more than 2^8
 //                       (warp-uniform decision), so after the first tile the rescale path is practically never taken.
 //   warp 8            : TMA producer (both Q tiles once, then a 3-deep K/V ring shared by the two query tiles)
-//   warp 9            : TMEM allocator + single-thread MMA issuer. Issue order S0 S1 | PV0 S0' | PV1 S1' | ... keeps the
-//                       tensor pipe busy on one tile while the other tile's warpgroup is in its exp2 phase.
+//   warp 9            : TMEM allocator + single-thread MMA issuer. S_w(j+1) is issued as soon as the warpgroup has pulled
+//                       S_w(j) into registers (s_free), i.e. before P_w(j) V(j), so the next scores are ready when the
+//                       exp2 phase of the current tile ends.
+//   warps 10..11      : idle; they exist so the producer/MMA warpgroup can hand its registers to the softmax warpgroups
+//                       (setmaxnreg 40 / 224): a 128-wide fp32 score row per thread does not fit in 168 registers.
 #pragma once
 #include "ptx.cuh"
 
@@ -28,7 +31,7 @@ struct AttnParams {
   uint32_t v_lbo, v_sbo, v_kstep;
 };
 
-constexpr int kAttnThreads = 320;
+constexpr int kAttnThreads = 384;
 constexpr int kAttnKvStages = 3;
 constexpr uint32_t kAttnTile = 128 * 64 * 2;  // 16 KB: one [128 x 64] bf16 tile
 constexpr uint32_t kAttnSmemBytes = 2 * kAttnTile /*Q0,Q1*/ + 2 * kAttnKvStages * kAttnTile /*K,V ring*/ + 4 * kAttnTile /*P0,P1*/ + 256;
@@ -46,6 +49,11 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
@@ -61,7 +69,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
   uint64_t* s_full = bars + 1 + 2 * kAttnKvStages;  // [2]
   uint64_t* p_full = s_full + 2;                    // [2]
   uint64_t* o_full = p_full + 2;                    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_free = o_full + 2;                    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -83,6 +92,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
       mbar_init(&s_full[w], 1);
       mbar_init(&p_full[w], 128);
       mbar_init(&o_full[w], 1);
+      mbar_init(&s_free[w], 128);
     }
     fence_mbar_init();
   }
@@ -91,7 +101,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 8) {
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, 2 * kAttnTile);
@@ -137,24 +148,29 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
       for (int j = 0; j < n_kv; ++j) {
         const int s = j % kAttnKvStages;
         const int s1 = (j + 1) % kAttnKvStages;
-        const bool more = j + 1 < n_kv;
-        // tile 0: P0(j) is in smem and S0(j) has been drained (and O0 rescaled if needed)
+        if (j + 1 < n_kv) {
+          // next scores as soon as each warpgroup has drained S_w(j) into registers
+          mbar_wait(&kv_full[s1], ((j + 1) / kAttnKvStages) & 1);
+          mbar_wait(&s_free[0], j & 1);
+          tc_fence_after();
+          issue_s(0, s1);
+          mbar_wait(&s_free[1], j & 1);
+          tc_fence_after();
+          issue_s(1, s1);
+        }
+        // P_w(j) is in smem (and O_w rescaled if needed)
         mbar_wait(&p_full[0], j & 1);
         tc_fence_after();
         issue_pv(0, s, j);
-        if (more) {
-          mbar_wait(&kv_full[s1], ((j + 1) / kAttnKvStages) & 1);
-          tc_fence_after();
-          issue_s(0, s1);
-        }
         mbar_wait(&p_full[1], j & 1);
         tc_fence_after();
         issue_pv(1, s, j);
         umma_commit(&kv_empty[s]);  // K_j / V_j no longer needed once everything issued so far has completed
-        if (more) issue_s(1, s1);
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ---- softmax warpgroups: w = 0 (warps 0..3) / 1 (warps 4..7); thread <-> query row
     const int w = warp >> 2;
     const int row_in_tile = (warp & 3) * 32 + lane;
@@ -180,6 +196,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
       tmem_ld_wait_dep(s1);
       tmem_ld_wait_dep(s2);
       tmem_ld_wait_dep(s3);
+      tc_fence_before();
+      mbar_arrive(&s_free[w]);  // S_w may be overwritten by the next Q K^T
       const int kv_valid = p.N - j * 128;
       if (kv_valid < 128) {  // only the last tile of a ragged sequence: padded key columns -> -inf
 #pragma unroll
@@ -203,13 +221,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
       const bool need = m_new - m_ref > kAttnRescaleThreshold;  // true at j == 0 (m_ref = -inf)
       float alpha = 1.0f;
       if (need) {
-        alpha = exp2f(m_ref - m_new);  // 0 at j == 0
+        alpha = ex2_approx(m_ref - m_new);  // 0 at j == 0
         m_ref = m_new;
       }
-      if (j > 0 && __any_sync(0xffffffffu, need)) {
-        // O_w *= alpha in TMEM; PV(j-1) must have completed, PV(j) is not issued before our p_full arrive
+      if (j > 0) {
+        // P_w V(j-1) must have completed before P_w is overwritten or O_w rescaled (it normally has, long ago)
         mbar_wait(&o_full[w], (j - 1) & 1);
         tc_fence_after();
+      }
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        // O_w *= alpha in TMEM; PV(j) is not issued before our p_full arrive
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t o[32];
@@ -227,8 +248,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
         uint32_t wv[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = exp2f(fmaf(__uint_as_float(s[2 * i]), sl2, -m_ref));
-          const float p1 = exp2f(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -m_ref));
+          const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), sl2, -m_ref));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -m_ref));
           ls0 += p0;
           ls1 += p1;
           wv[i] = pack_bf16x2(p0, p1);
