@@ -165,7 +165,7 @@ int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
   return 0;
 }
 int launch_gemm(int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
-  if (p.M <= 0 || p.N % kGemmBN != 0 || p.K % kGemmBK != 0 || p.K <= 0) return fail(EDM_ERR_INVALID, "gemm shape M=%d N=%d K=%d unsupported (N %% 256, K %% 64)", p.M, p.N, p.K);
+  if (p.M <= 0 || p.N % kGemmBN != 0 || p.N > kGemmMaxN || p.K % kGemmBK != 0 || p.K <= 0) return fail(EDM_ERR_INVALID, "gemm shape M=%d N=%d K=%d unsupported (N %% 256, N <= 8192, K %% 64)", p.M, p.N, p.K);
   switch (epi) {
     case EPI_BF16: return launch_gemm_t<EPI_BF16>(ma, mb, p, st);
     case EPI_SWISH_BF16: return launch_gemm_t<EPI_SWISH_BF16>(ma, mb, p, st);

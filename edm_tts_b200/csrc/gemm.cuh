@@ -1,12 +1,13 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a: C[M,N] = A[M,K] * B[N,K]^T (both operands K-major, which is
 // how activations [tokens, channels] and nn.Linear weights [out, in] already sit in HBM).
 //
-//   warp 0      : TMA producer  (cp.async.bulk.tensor, 128B swizzle, kStages-deep mbarrier ring)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (128 x 256 x 16 per instruction, fp32 accum in TMEM)
-//   warps 2..9  : epilogue (tcgen05.ld -> registers -> fused op -> global), overlapped with the next tile's mainloop
-//                 through two TMEM accumulator buffers (2 x 256 columns = all 512 columns). Warp w reads TMEM lane
-//                 quadrant w % 4 and column half (w - 2) / 4; the next chunk's tcgen05.ld is in flight while the
-//                 current one is processed.
+//   warp 0       : TMA producer  (cp.async.bulk.tensor, 128B swizzle, kStages-deep mbarrier ring)
+//   warp 1       : TMEM allocator + single-thread tcgen05.mma issuer (128 x 256 x 16 per instruction, fp32 accum in TMEM)
+//   warps 2..17  : epilogue. Warp w owns TMEM lane quadrant w % 4 and 64 of the tile's 256 columns: it pulls its
+//                  128 x 64 slice into registers with two tcgen05.ld, releases the accumulator buffer at once
+//                  (so the MMA warp never waits for epilogue arithmetic), then applies the fused op and stores.
+//                  Two TMEM accumulator buffers (2 x 256 columns = all 512) overlap epilogue and next mainloop.
+//   The bias vector is staged in shared memory once per CTA (broadcast LDS instead of a dependent global load).
 //
 // Fused epilogues cover every GEMM of the conformer block (reference: edm_tts/models/conformer/conformer.py:149-181,
 // 113-146) and the logits heads (injection_conformer_wrapper.py:38-63); rounding points follow bf16 autocast:
@@ -42,68 +43,48 @@ constexpr int kGemmBM = 128;
 constexpr int kGemmBN = 256;
 constexpr int kGemmBK = 64;
 constexpr int kGemmStages = 4;
-constexpr int kGemmEpiWarps = 8;  // two per TMEM lane quadrant, each owning half of the tile's columns
+constexpr int kGemmEpiWarps = 16;  // four per TMEM lane quadrant, each owning 64 of the tile's 256 columns
 constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
+constexpr int kGemmMaxN = 8192;    // bias staging capacity
 constexpr uint32_t kGemmABytes = kGemmBM * kGemmBK * 2;
 constexpr uint32_t kGemmBBytes = kGemmBN * kGemmBK * 2;
 constexpr uint32_t kGemmStageBytes = kGemmABytes + kGemmBBytes;
-constexpr uint32_t kGemmSmemBytes = kGemmStages * kGemmStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr uint32_t kGemmSmemBytes = kGemmStages * kGemmStageBytes + kGemmMaxN * 4 /*bias*/ + 1024 /*align slack*/ + 256 /*barriers*/;
 
-__device__ __forceinline__ float sigmoidf_fast(float v) { return 1.0f / (1.0f + __expf(-v)); }
-
+// 32 consecutive columns of one row. v: accumulators (+ bias already added by the caller).
 template <int EPI>
-__device__ __forceinline__ void gemm_epilogue_32(const GemmParams& p, int row, int col, const uint32_t (&r)[32]) {
-  // r: 32 consecutive fp32 accumulators of `row`, columns [col, col + 32)
-  float v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-  if (p.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 b = __ldg(b4 + i);
-      v[4 * i + 0] += b.x;
-      v[4 * i + 1] += b.y;
-      v[4 * i + 2] += b.z;
-      v[4 * i + 3] += b.w;
-    }
-  }
+__device__ __forceinline__ void gemm_store_32(const GemmParams& p, int row, int col, float (&v)[32]) {
   if constexpr (EPI == EPI_F32) {
     float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col);
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   } else if constexpr (EPI == EPI_RESID_F32) {
-    float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col);
+    // x += scale * bf16(v): fire-and-forget vector reductions resolved in L2. Every element has exactly one writer per
+    // GEMM, so the result is the same single rounded add a load/add/store would give, without pulling x through the SM.
+    float* o = static_cast<float*>(p.out) + static_cast<long long>(row) * p.ldo + col;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float4 x = o[i];
-      x.x += p.scale * bf16_round(v[4 * i + 0]);
-      x.y += p.scale * bf16_round(v[4 * i + 1]);
-      x.z += p.scale * bf16_round(v[4 * i + 2]);
-      x.w += p.scale * bf16_round(v[4 * i + 3]);
-      o[i] = x;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * i), "f"(p.scale * bf16_round(v[4 * i + 0])),
+                   "f"(p.scale * bf16_round(v[4 * i + 1])), "f"(p.scale * bf16_round(v[4 * i + 2])),
+                   "f"(p.scale * bf16_round(v[4 * i + 3]))
+                   : "memory");
     }
   } else {
+    uint32_t w[16];
     if constexpr (EPI == EPI_SWISH_BF16) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const uint32_t h2 = pack_bf16x2(v[2 * i], v[2 * i + 1]);
         const uint32_t s2 = pack_bf16x2(sigmoid_tanh(bf16lo(h2)), sigmoid_tanh(bf16hi(h2)));
-        const uint32_t o2 = bf16x2_mul(h2, s2);
-        v[2 * i] = bf16lo(o2);
-        v[2 * i + 1] = bf16hi(o2);
+        w[i] = bf16x2_mul(h2, s2);
       }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
     }
     uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 w;
-      w.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-      w.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      w.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-      w.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-      o[i] = w;
-    }
+    for (int i = 0; i < 4; ++i) o[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
   }
 }
 
@@ -111,40 +92,47 @@ __device__ __forceinline__ void gemm_epilogue_32(const GemmParams& p, int row, i
 // applied to the bf16 projection output in fp32 and rounded to bf16 when SDPA consumes it.
 __device__ __forceinline__ void gemm_epilogue_rope64(const GemmParams& p, int row, int col, const uint32_t (&lo)[32],
                                                      const uint32_t (&hi)[32]) {
-  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col;
-  uint32_t w[32];
+  uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col);
+  // the projection output is bf16 in the reference: round first (also halves the live registers)
+  uint32_t l2[16], h2[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    l2[i] = pack_bf16x2(__uint_as_float(lo[2 * i]), __uint_as_float(lo[2 * i + 1]));
+    h2[i] = pack_bf16x2(__uint_as_float(hi[2 * i]), __uint_as_float(hi[2 * i + 1]));
+  }
   if (col < p.rope_cols) {
     const int pos = row % p.seq_len;
     const float4* c4 = reinterpret_cast<const float4*>(p.rope_cos + static_cast<long long>(pos) * 32);
     const float4* s4 = reinterpret_cast<const float4*>(p.rope_sin + static_cast<long long>(pos) * 32);
-    float o_lo[32], o_hi[32];
+    float4 cs[8], sn[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float4 c = __ldg(c4 + i), s = __ldg(s4 + i);
-      const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {s.x, s.y, s.z, s.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float x1 = bf16_round(__uint_as_float(lo[4 * i + j]));
-        float x2 = bf16_round(__uint_as_float(hi[4 * i + j]));
-        o_lo[4 * i + j] = __fadd_rn(__fmul_rn(x1, cc[j]), __fmul_rn(-x2, ss[j]));
-        o_hi[4 * i + j] = __fadd_rn(__fmul_rn(x2, cc[j]), __fmul_rn(x1, ss[j]));
-      }
+      cs[i] = __ldg(c4 + i);
+      sn[i] = __ldg(s4 + i);
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      w[i] = pack_bf16x2(o_lo[2 * i], o_lo[2 * i + 1]);
-      w[16 + i] = pack_bf16x2(o_hi[2 * i], o_hi[2 * i + 1]);
+    for (int g = 0; g < 4; ++g) {  // 8 columns of each half per group
+      uint32_t ol[4], oh[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = 4 * g + q;  // packed pair index: columns 2i, 2i+1
+        const float4 c = cs[i >> 1], s = sn[i >> 1];
+        const float c0 = (i & 1) ? c.z : c.x, c1 = (i & 1) ? c.w : c.y;
+        const float s0 = (i & 1) ? s.z : s.x, s1 = (i & 1) ? s.w : s.y;
+        const float x1a = bf16lo(l2[i]), x1b = bf16hi(l2[i]), x2a = bf16lo(h2[i]), x2b = bf16hi(h2[i]);
+        ol[q] = pack_bf16x2(__fadd_rn(__fmul_rn(x1a, c0), __fmul_rn(-x2a, s0)), __fadd_rn(__fmul_rn(x1b, c1), __fmul_rn(-x2b, s1)));
+        oh[q] = pack_bf16x2(__fadd_rn(__fmul_rn(x2a, c0), __fmul_rn(x1a, s0)), __fadd_rn(__fmul_rn(x2b, c1), __fmul_rn(x1b, s1)));
+      }
+      o[g] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+      o[4 + g] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      w[i] = pack_bf16x2(__uint_as_float(lo[2 * i]), __uint_as_float(lo[2 * i + 1]));
-      w[16 + i] = pack_bf16x2(__uint_as_float(hi[2 * i]), __uint_as_float(hi[2 * i + 1]));
+    for (int g = 0; g < 4; ++g) {
+      o[g] = make_uint4(l2[4 * g], l2[4 * g + 1], l2[4 * g + 2], l2[4 * g + 3]);
+      o[4 + g] = make_uint4(h2[4 * g], h2[4 * g + 1], h2[4 * g + 2], h2[4 * g + 3]);
     }
   }
-  uint4* o = reinterpret_cast<uint4*>(out);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
 }
 
 template <int EPI>
@@ -152,7 +140,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
+  float* s_bias = reinterpret_cast<float*>(smem + kGemmStages * kGemmStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes + kGemmMaxN * 4);
   uint64_t* empty_bar = full_bar + kGemmStages;
   uint64_t* tmem_full_bar = empty_bar + kGemmStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -180,6 +169,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_base_slot);
+  if (p.bias != nullptr) {
+    for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = __ldg(p.bias + i);
+  } else {
+    for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -239,45 +233,52 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   } else {
-    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
-    const int half = (warp - 2) >> 2;   // which 128 of the tile's 256 columns
+    const int quad = warp & 3;         // TMEM lane quadrant this warp may read
+    const int sub = (warp - 2) >> 2;   // which 64 of the tile's 256 columns
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t / num_n, n_blk = t % num_n;
+      const int row = m_blk * kGemmBM + quad * 32 + lane;
+      const int col0 = n_blk * kGemmBN + sub * 64;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kGemmBN + sub * 64;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * kGemmBM + quad * 32 + lane;
-      const int col0 = n_blk * kGemmBN + half * 128;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kGemmBN + half * 128;
-      if constexpr (EPI == EPI_QKV_ROPE) {
-        uint32_t lo[2][32], hi[2][32];
-        tmem_ld_32x32(taddr, lo[0]);
-        tmem_ld_32x32(taddr + 32, hi[0]);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          tmem_ld_wait_dep(lo[c]);
-          tmem_ld_wait_dep(hi[c]);
-          if (c == 0) {
-            tmem_ld_32x32(taddr + 64, lo[1]);
-            tmem_ld_32x32(taddr + 96, hi[1]);
-          }
-          if (row < p.M) gemm_epilogue_rope64(p, row, col0 + c * 64, lo[c], hi[c]);
-        }
-      } else {
-        uint32_t r[2][32];
-        tmem_ld_32x32(taddr, r[0]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld_wait_dep(r[c & 1]);
-          if (c + 1 < 4) tmem_ld_32x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
-          if (row < p.M) gemm_epilogue_32<EPI>(p, row, col0 + c * 32, r[c & 1]);
-        }
-      }
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(taddr, r0);
+      tmem_ld_32x32(taddr + 32, r1);
+      tmem_ld_wait_dep(r0);
+      tmem_ld_wait_dep(r1);
+      // the slice is in registers: hand the accumulator buffer back before doing any arithmetic
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      if (row >= p.M) continue;
+      if constexpr (EPI == EPI_QKV_ROPE) {
+        gemm_epilogue_rope64(p, row, col0, r0, r1);
+      } else {
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + col0);
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = b4[i];
+          v[4 * i + 0] = __uint_as_float(r0[4 * i + 0]) + b.x;
+          v[4 * i + 1] = __uint_as_float(r0[4 * i + 1]) + b.y;
+          v[4 * i + 2] = __uint_as_float(r0[4 * i + 2]) + b.z;
+          v[4 * i + 3] = __uint_as_float(r0[4 * i + 3]) + b.w;
+        }
+        gemm_store_32<EPI>(p, row, col0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = b4[8 + i];
+          v[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
+          v[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
+          v[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
+          v[4 * i + 3] = __uint_as_float(r1[4 * i + 3]) + b.w;
+        }
+        gemm_store_32<EPI>(p, row, col0 + 32, v);
+      }
     }
   }
 
