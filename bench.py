@@ -254,7 +254,7 @@ def main():
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": sem_host.numel() * 8 * world, "d2h_bytes_per_step": codes_host.numel() * 8 * world,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches) * world,
-        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel (all conformer / head GEMMs of the timed region)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_pair_kernel (tcgen05 cta_group::2; all conformer / head GEMMs of the timed region)",
                      "achieved": gemm_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tf_peak, "traffic": None,
                      "peak_kind": f"{peak_kind} bf16 sustained", "gemm_share_of_step": pm[0] / ms_total},
         "kernels": kernels,

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -150,16 +151,36 @@ int make_tmap_3d(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t N, uint64
 }
 
 // ---------------------------------------------------------------------------------------------- launch helpers
+bool gemm_use_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EDM_GEMM_PAIR");  // bring-up switch: 0 = single-CTA 128x256 tiles, 1 = CTA-pair 256x256 tiles
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// rows of a B-operand TMA box: a CTA of a pair loads half of the 256-row weight tile
+uint32_t gemm_b_box_rows() { return gemm_use_pairs() ? kGemmBN / 2 : kGemmBN; }
+
 template <int EPI>
 int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     attr_set = true;
+  }
+  ProfScope prof(PK_GEMM, 2.0 * p.M * p.N * p.K, st);
+  if (gemm_use_pairs()) {
+    const int tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (p.N / kGemmBN);
+    const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+    gemm_bf16_tn_pair_kernel<EPI><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, p);
+    EDM_LAUNCH_CHECK("gemm_bf16_tn_pair");
+    return 0;
   }
   const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / kGemmBN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  ProfScope prof(PK_GEMM, 2.0 * p.M * p.N * p.K, st);
   gemm_bf16_tn_kernel<EPI><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ma, mb, p);
   EDM_LAUNCH_CHECK("gemm_bf16_tn");
   return 0;
@@ -280,7 +301,7 @@ extern "C" int edm_gemm_bf16(const void* a, long long lda, const void* b, long l
   if (int rc = check_arch()) return rc;
   CUtensorMap ma, mb;
   if (int rc = make_tmap_2d(&ma, a, M, K, lda, kGemmBM)) return rc;
-  if (int rc = make_tmap_2d(&mb, b, N, K, ldb, kGemmBN)) return rc;
+  if (int rc = make_tmap_2d(&mb, b, N, K, ldb, gemm_b_box_rows())) return rc;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.a_k_offset = 0; p.b_row_offset = 0;
   p.bias = bias; p.out = out; p.ldo = ldo; p.scale = scale;
@@ -548,17 +569,17 @@ extern "C" edm_s2a_ctx* edm_s2a_create(const edm_s2a_config* cfg, const void* co
   int rc = 0;
   for (int l = 0; l < cfg->depth && rc == 0; ++l) {
     BlockMaps& m = c->bmaps[l];
-    rc = rc ? rc : make_tmap_2d(&m.ff1_w1, c->bw(l, F_FF1_W1), 4096, 1024, 1024, kGemmBN);
-    rc = rc ? rc : make_tmap_2d(&m.ff1_w2, c->bw(l, F_FF1_W2), 1024, 4096, 4096, kGemmBN);
-    rc = rc ? rc : make_tmap_2d(&m.wqkv, c->bw(l, F_WQKV), 3072, 1024, 1024, kGemmBN);
-    rc = rc ? rc : make_tmap_2d(&m.wo, c->bw(l, F_WO), 1024, 1024, 1024, kGemmBN);
-    rc = rc ? rc : make_tmap_2d(&m.pw1, c->bw(l, F_PW1_W), 4096, 1024, 1024, kGemmBN);
-    rc = rc ? rc : make_tmap_2d(&m.pw2, c->bw(l, F_PW2_W), 1024, 2048, 2048, kGemmBN);
-    rc = rc ? rc : make_tmap_2d(&m.ff2_w1, c->bw(l, F_FF2_W1), 4096, 1024, 1024, kGemmBN);
-    rc = rc ? rc : make_tmap_2d(&m.ff2_w2, c->bw(l, F_FF2_W2), 1024, 4096, 4096, kGemmBN);
+    rc = rc ? rc : make_tmap_2d(&m.ff1_w1, c->bw(l, F_FF1_W1), 4096, 1024, 1024, gemm_b_box_rows());
+    rc = rc ? rc : make_tmap_2d(&m.ff1_w2, c->bw(l, F_FF1_W2), 1024, 4096, 4096, gemm_b_box_rows());
+    rc = rc ? rc : make_tmap_2d(&m.wqkv, c->bw(l, F_WQKV), 3072, 1024, 1024, gemm_b_box_rows());
+    rc = rc ? rc : make_tmap_2d(&m.wo, c->bw(l, F_WO), 1024, 1024, 1024, gemm_b_box_rows());
+    rc = rc ? rc : make_tmap_2d(&m.pw1, c->bw(l, F_PW1_W), 4096, 1024, 1024, gemm_b_box_rows());
+    rc = rc ? rc : make_tmap_2d(&m.pw2, c->bw(l, F_PW2_W), 1024, 2048, 2048, gemm_b_box_rows());
+    rc = rc ? rc : make_tmap_2d(&m.ff2_w1, c->bw(l, F_FF2_W1), 4096, 1024, 1024, gemm_b_box_rows());
+    rc = rc ? rc : make_tmap_2d(&m.ff2_w2, c->bw(l, F_FF2_W2), 1024, 4096, 4096, gemm_b_box_rows());
   }
-  rc = rc ? rc : make_tmap_2d(&c->head_map, c->gw(G_HEAD_W), static_cast<uint64_t>(cfg->num_quantizers) * 1024, 1024, 1024, kGemmBN);
-  rc = rc ? rc : make_tmap_2d(&c->fine_map, c->gw(G_FINE_W), static_cast<uint64_t>(c->n_fine) * 1024, 1024, 1024, kGemmBN);
+  rc = rc ? rc : make_tmap_2d(&c->head_map, c->gw(G_HEAD_W), static_cast<uint64_t>(cfg->num_quantizers) * 1024, 1024, 1024, gemm_b_box_rows());
+  rc = rc ? rc : make_tmap_2d(&c->fine_map, c->gw(G_FINE_W), static_cast<uint64_t>(c->n_fine) * 1024, 1024, 1024, gemm_b_box_rows());
   if (rc) {
     delete c;
     return nullptr;

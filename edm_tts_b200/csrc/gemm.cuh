@@ -287,4 +287,164 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair variant
+// Same roles, but two CTAs of a cluster (two SMs of one TPC) share each 256 x 256 output tile through
+// tcgen05.mma.cta_group::2: CTA r loads rows r*128.. of A and rows r*128.. of the B tile (half the B bytes per SM, a third
+// less L2->SM operand traffic per FLOP than 128 x 256 tiles), CTA 0's MMA thread issues M = 256 instructions that read
+// both CTAs' shared memory and write each CTA's own TMEM half, completion is multicast to both CTAs' barriers.
+// 32 KB per stage instead of 48 KB -> a 6-deep ring in the same shared memory.
+constexpr int kPairStages = 6;
+constexpr uint32_t kPairStageBytes = 2 * kGemmABytes;  // A (128 x 64) + half of B (128 x 64)
+constexpr uint32_t kPairSmemBytes = kPairStages * kPairStageBytes + kGemmMaxN * 4 + 1024 + 256;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* s_bias = reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes + kGemmMaxN * 4);
+  uint64_t* empty_bar = full_bar + kPairStages;
+  uint64_t* tmem_full_bar = empty_bar + kPairStages;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  const int num_m = (p.M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+  const int num_n = p.N / kGemmBN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = p.K / kGemmBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < kPairStages; ++s) {
+      mbar_init(&full_bar[s], 1);   // CTA 0's expect_tx arrive; the bytes of both CTAs land here
+      mbar_init(&empty_bar[s], 1);  // one multicast commit per use
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 2 * 32 * kGemmEpiWarps);  // epilogue threads of both CTAs arrive on CTA 0's barrier
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair<512>(tmem_base_slot);
+  if (p.bias != nullptr) {
+    for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = __ldg(p.bias + i);
+  } else {
+    for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = 0.f;
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers initialised and TMEM allocated before any cross-CTA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int m_blk = t / num_n, n_blk = t % num_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kPairStageBytes;
+          uint8_t* sb = sa + kGemmABytes;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
+          tma_load_2d_pair(&tma_a, &full_bar[stage], sa, p.a_k_offset + kb * kGemmBK, m_blk * 2 * kGemmBM + rank * kGemmBM);
+          tma_load_2d_pair(&tma_b, &full_bar[stage], sb, kb * kGemmBK, p.b_row_offset + n_blk * kGemmBN + rank * (kGemmBN / 2));
+          if (++stage == kPairStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kGemmBM, kGemmBN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kGemmBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kPairStageBytes);
+          const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sa + kGemmABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kGemmBK / 16; ++k) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[stage]);
+          if (++stage == kPairStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_pair(&tmem_full_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int m_blk = t / num_n, n_blk = t % num_n;
+      const int row = m_blk * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM + quad * 32 + lane;
+      const int col0 = n_blk * kGemmBN + sub * 64;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kGemmBN + sub * 64;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(taddr, r0);
+      tmem_ld_32x32(taddr + 32, r1);
+      tmem_ld_wait_dep(r0);
+      tmem_ld_wait_dep(r1);
+      tc_fence_before();
+      mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+      if (row >= p.M) continue;
+      if constexpr (EPI == EPI_QKV_ROPE) {
+        gemm_epilogue_rope64(p, row, col0, r0, r1);
+      } else {
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + col0);
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = b4[i];
+          v[4 * i + 0] = __uint_as_float(r0[4 * i + 0]) + b.x;
+          v[4 * i + 1] = __uint_as_float(r0[4 * i + 1]) + b.y;
+          v[4 * i + 2] = __uint_as_float(r0[4 * i + 2]) + b.z;
+          v[4 * i + 3] = __uint_as_float(r0[4 * i + 3]) + b.w;
+        }
+        gemm_store_32<EPI>(p, row, col0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = b4[8 + i];
+          v[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
+          v[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
+          v[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
+          v[4 * i + 3] = __uint_as_float(r1[4 * i + 3]) + b.w;
+        }
+        gemm_store_32<EPI>(p, row, col0 + 32, v);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be reading our shared memory / signalling our barriers
+  if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
+}
+
 }  // namespace edm
