@@ -161,7 +161,7 @@ def main():
     ge.build()
     from edm_tts_b200 import InjectionConformerModel, _lib
     from edm_tts_b200.config import InjectionConformerConfig
-    from oracle.weights import OracleConfig, make_state_dict
+    from edm_tts_b200.synthetic import OracleConfig, make_state_dict
 
     lib = _lib.lib()
     cfg = OracleConfig()

@@ -1,0 +1,134 @@
+"""Deterministic synthetic weights and inputs under the reference's state-dict key names.
+
+Used by bench.py (random-init weights of the reference architecture; there are no checkpoints offline) and, re-exported
+through oracle/weights.py, by the parity tests and the golden-vector generator, so that all of them see bit-identical
+tensors. Every tensor is drawn from its own torch.Generator seeded by crc32(key) ^ seed on the CPU, so the build
+container (where the reference is importable) and the GPU box (where it is not) regenerate the same weights without
+shipping 2 GB. Pure data generation: no model arithmetic lives here.
+"""
+from __future__ import annotations
+
+import math
+import zlib
+from dataclasses import dataclass, field
+
+import torch
+
+
+@dataclass
+class OracleConfig:
+    """Dims of the S2A model + DAC quantizer. Defaults = configs/injection_conformer/base_config + configs/dac/base_config."""
+    hidden: int = 1024
+    heads: int = 16
+    depth: int = 16
+    ff_mult: int = 4
+    conv_expansion: int = 2
+    conv_kernel: int = 5
+    injection_layers: tuple = (4, 7, 10, 13)
+    num_semantic: int = 1024
+    n_codebooks: int = 12
+    codebook_size: int = 1024
+    codebook_dim: int = 8
+    latent_dim: int = 1024
+    residual: bool = True
+    use_injection: bool = True
+
+    @property
+    def dim_head(self) -> int:
+        return self.hidden // self.heads
+
+
+def _gen(key: str, seed: int) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed((zlib.crc32(key.encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF)
+    return g
+
+
+def _randn(key, seed, *shape, std=1.0):
+    return torch.randn(*shape, generator=_gen(key, seed), dtype=torch.float32) * std
+
+
+def make_state_dict(cfg: OracleConfig, seed: int = 0) -> dict:
+    """All parameters the hot path touches, keyed as in InjectionConformerModel.state_dict()."""
+    d, sd = cfg.hidden, {}
+
+    def linear(prefix, out_f, in_f, bias=True, gain=1.0):
+        sd[prefix + ".weight"] = _randn(prefix + ".weight", seed, out_f, in_f, std=gain / math.sqrt(in_f))
+        if bias:
+            sd[prefix + ".bias"] = _randn(prefix + ".bias", seed, out_f, std=0.05)
+
+    def lnorm(prefix, n):
+        sd[prefix + ".weight"] = 1.0 + _randn(prefix + ".weight", seed, n, std=0.1)
+        sd[prefix + ".bias"] = _randn(prefix + ".bias", seed, n, std=0.05)
+
+    sd["mask_token"] = _randn("mask_token", seed, 1, 1, d)
+    sd["semantic_embedding.weight"] = _randn("semantic_embedding.weight", seed, cfg.num_semantic, d)
+    linear("acoustic_feat_proj.0", d, cfg.latent_dim)
+    lnorm("acoustic_feat_proj.1", d)
+    inner = d * cfg.conv_expansion
+    for i in range(cfg.depth):
+        p = f"encoder.layers.{i}."
+        for ff in ("ff1", "ff2"):
+            linear(p + ff + ".fn.fn.net.0", d * cfg.ff_mult, d)
+            linear(p + ff + ".fn.fn.net.3", d, d * cfg.ff_mult)
+            lnorm(p + ff + ".fn.norm", d)
+        linear(p + "attn.fn.to_q", d, d, bias=False)
+        linear(p + "attn.fn.to_kv", 2 * d, d, bias=False)
+        linear(p + "attn.fn.to_out", d, d)
+        lnorm(p + "attn.norm", d)
+        lnorm(p + "conv.net.0", d)
+        sd[p + "conv.net.2.weight"] = _randn(p + "conv.net.2.weight", seed, inner * 2, d, 1, std=1 / math.sqrt(d))
+        sd[p + "conv.net.2.bias"] = _randn(p + "conv.net.2.bias", seed, inner * 2, std=0.05)
+        sd[p + "conv.net.4.conv.weight"] = _randn(p + "conv.net.4.conv.weight", seed, inner, 1, cfg.conv_kernel, std=0.5)
+        sd[p + "conv.net.4.conv.bias"] = _randn(p + "conv.net.4.conv.bias", seed, inner, std=0.05)
+        sd[p + "conv.net.6.weight"] = 1.0 + _randn(p + "conv.net.6.weight", seed, 1, inner, 1, std=0.1)
+        sd[p + "conv.net.7.weight"] = _randn(p + "conv.net.7.weight", seed, d, inner, 1, std=1 / math.sqrt(inner))
+        sd[p + "conv.net.7.bias"] = _randn(p + "conv.net.7.bias", seed, d, std=0.05)
+        lnorm(p + "post_norm", d)
+    for k in range(len(cfg.injection_layers)):
+        linear(f"encoder.project_injection.{k}.0", d, cfg.latent_dim)
+        lnorm(f"encoder.project_injection.{k}.1", d)
+    n_fine = cfg.n_codebooks - len(cfg.injection_layers)
+    linear("encoder.fine_head.0", d * n_fine, d)
+    lnorm("encoder.to_logits.0", d)
+    sd["encoder.to_logits.1.weight"] = _randn("encoder.to_logits.1.weight", seed, cfg.n_codebooks, d, cfg.codebook_size, std=1 / math.sqrt(d))
+    sd["encoder.to_logits.1.bias"] = _randn("encoder.to_logits.1.bias", seed, 1, 1, cfg.n_codebooks, cfg.codebook_size, std=0.05)
+    sd.update(make_quantizer_state_dict(cfg, seed, prefix="acoustic_model.quantizer."))
+    return sd
+
+
+def make_quantizer_state_dict(cfg: OracleConfig, seed: int = 0, prefix: str = "") -> dict:
+    """DAC ResidualVectorQuantize parameters (weight-normed 1x1 convs keep their original0/original1 split)."""
+    sd = {}
+    for i in range(cfg.n_codebooks):
+        q = f"{prefix}quantizers.{i}."
+        sd[q + "codebook.weight"] = _randn(q + "codebook.weight", seed, cfg.codebook_size, cfg.codebook_dim)
+        v_in = _randn(q + "in_proj.v", seed, cfg.codebook_dim, cfg.latent_dim, 1, std=1 / math.sqrt(cfg.latent_dim))
+        sd[q + "in_proj.parametrizations.weight.original1"] = v_in
+        sd[q + "in_proj.parametrizations.weight.original0"] = v_in.flatten(1).norm(dim=1).view(-1, 1, 1) * (1.0 + _randn(q + "in_proj.g", seed, cfg.codebook_dim, 1, 1, std=0.1))
+        sd[q + "in_proj.bias"] = _randn(q + "in_proj.bias", seed, cfg.codebook_dim, std=0.05)
+        # later levels quantise a shrinking residual, as in a trained codec
+        v_out = _randn(q + "out_proj.v", seed, cfg.latent_dim, cfg.codebook_dim, 1, std=0.35 * (0.8 ** i))
+        sd[q + "out_proj.parametrizations.weight.original1"] = v_out
+        sd[q + "out_proj.parametrizations.weight.original0"] = v_out.flatten(1).norm(dim=1).view(-1, 1, 1) * (1.0 + _randn(q + "out_proj.g", seed, cfg.latent_dim, 1, 1, std=0.1))
+        sd[q + "out_proj.bias"] = _randn(q + "out_proj.bias", seed, cfg.latent_dim, std=0.02)
+    return sd
+
+
+def make_inputs(B: int, T: int, P: int, steps: int, cfg: OracleConfig, seed: int = 1234) -> dict:
+    """Synthetic tokens + injected sampling noise, all from one CPU generator."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    out = {"semantic_tokens": torch.randint(0, cfg.num_semantic, (B, T), generator=g)}
+    if P > 0:
+        out["acoustic_prompt_tokens"] = torch.randint(0, cfg.codebook_size, (B, cfg.n_codebooks, P), generator=g)
+        out["semantic_prompt_tokens"] = torch.randint(0, cfg.num_semantic, (B, P), generator=g)
+    else:
+        out["acoustic_prompt_tokens"] = None
+        out["semantic_prompt_tokens"] = None
+    n = max(steps - 1, 0)
+    u = torch.rand(n, B * T, cfg.codebook_size, generator=g).clamp_(1e-10, 1 - 1e-7)
+    out["cat_gumbel"] = -torch.log(-torch.log(u))          # Gumbel(0,1): Categorical.sample == argmax(logits + g)
+    u = torch.rand(n, B, T, generator=g).clamp_(1e-10, 1 - 1e-7)
+    out["remask_gumbel"] = -torch.log(-torch.log(u))       # noise of random_topk_mask
+    return out
