@@ -90,8 +90,10 @@ __device__ __forceinline__ void gemm_store_32(const GemmParams& p, int row, int 
 
 // One 64-wide head: lo = columns [col, col+32), hi = [col+32, col+64). Reference: conformer.py:45-51 (rotate_half),
 // applied to the bf16 projection output in fp32 and rounded to bf16 when SDPA consumes it.
+// tab_row: this row's cos|sin (16 float4, chunk index XOR-swizzled by swz) staged in shared memory, or nullptr to read
+// the global tables directly.
 __device__ __forceinline__ void gemm_epilogue_rope64(const GemmParams& p, int row, int col, const uint32_t (&lo)[32],
-                                                     const uint32_t (&hi)[32]) {
+                                                     const uint32_t (&hi)[32], const float4* tab_row = nullptr, int swz = 0) {
   uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col);
   // the projection output is bf16 in the reference: round first (also halves the live registers)
   uint32_t l2[16], h2[16];
@@ -104,21 +106,27 @@ __device__ __forceinline__ void gemm_epilogue_rope64(const GemmParams& p, int ro
     const int pos = row % p.seq_len;
     const float4* c4 = reinterpret_cast<const float4*>(p.rope_cos + static_cast<long long>(pos) * 32);
     const float4* s4 = reinterpret_cast<const float4*>(p.rope_sin + static_cast<long long>(pos) * 32);
-    float4 cs[8], sn[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      cs[i] = __ldg(c4 + i);
-      sn[i] = __ldg(s4 + i);
-    }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {  // 8 columns of each half per group
+    for (int g = 0; g < 4; ++g) {  // 8 columns of each half per group: cos/sin chunks 2g, 2g+1
+      float4 cs[2], sn[2];
+      if (tab_row != nullptr) {
+        cs[0] = tab_row[(2 * g) ^ swz];
+        cs[1] = tab_row[(2 * g + 1) ^ swz];
+        sn[0] = tab_row[8 + ((2 * g) ^ swz)];
+        sn[1] = tab_row[8 + ((2 * g + 1) ^ swz)];
+      } else {
+        cs[0] = __ldg(c4 + 2 * g);
+        cs[1] = __ldg(c4 + 2 * g + 1);
+        sn[0] = __ldg(s4 + 2 * g);
+        sn[1] = __ldg(s4 + 2 * g + 1);
+      }
       uint32_t ol[4], oh[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int i = 4 * g + q;  // packed pair index: columns 2i, 2i+1
-        const float4 c = cs[i >> 1], s = sn[i >> 1];
-        const float c0 = (i & 1) ? c.z : c.x, c1 = (i & 1) ? c.w : c.y;
-        const float s0 = (i & 1) ? s.z : s.x, s1 = (i & 1) ? s.w : s.y;
+        const float4 c = cs[q >> 1], s = sn[q >> 1];
+        const float c0 = (q & 1) ? c.z : c.x, c1 = (q & 1) ? c.w : c.y;
+        const float s0 = (q & 1) ? s.z : s.x, s1 = (q & 1) ? s.w : s.y;
         const float x1a = bf16lo(l2[i]), x1b = bf16hi(l2[i]), x2a = bf16lo(h2[i]), x2b = bf16hi(h2[i]);
         ol[q] = pack_bf16x2(__fadd_rn(__fmul_rn(x1a, c0), __fmul_rn(-x2a, s0)), __fadd_rn(__fmul_rn(x1b, c1), __fmul_rn(-x2b, s1)));
         oh[q] = pack_bf16x2(__fadd_rn(__fmul_rn(x2a, c0), __fmul_rn(x1a, s0)), __fadd_rn(__fmul_rn(x2b, c1), __fmul_rn(x1b, s1)));
@@ -403,6 +411,27 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       const int row = m_blk * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM + quad * 32 + lane;
       const int col0 = n_blk * kGemmBN + sub * 64;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kGemmBN + sub * 64;
+      bool rope_tile = false;
+      if constexpr (EPI == EPI_QKV_ROPE) {
+        // The rotary cos|sin rows of this CTA's 128 token rows go to shared memory (the bias area is free: no bias here)
+        // while the tile's mainloop is still running: one coalesced 32 KB read per tile instead of 4 x 128 rows x 256 B
+        // of dependent 16-byte loads. Chunk index is XOR-swizzled with (row & 7) so row-per-lane reads are conflict-free.
+        rope_tile = n_blk * kGemmBN < p.rope_cols;
+        if (rope_tile) {
+          float4* tab = reinterpret_cast<float4*>(s_bias);
+          const int et = threadIdx.x - 64;
+          asm volatile("bar.sync 1, 512;" ::: "memory");  // previous tile's readers are done
+#pragma unroll
+          for (int i = et; i < 128 * 16; i += 32 * kGemmEpiWarps) {
+            const int r = i >> 4, c = i & 15;
+            const int grow = m_blk * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM + r;
+            const int pos = (grow < p.M ? grow : 0) % p.seq_len;
+            const float* src = (c < 8 ? p.rope_cos : p.rope_sin) + static_cast<long long>(pos) * 32 + (c & 7) * 4;
+            tab[r * 16 + (c ^ (r & 7))] = __ldg(reinterpret_cast<const float4*>(src));
+          }
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+        }
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       uint32_t r0[32], r1[32];
@@ -416,7 +445,8 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       if (acc == 0) acc_phase ^= 1;
       if (row >= p.M) continue;
       if constexpr (EPI == EPI_QKV_ROPE) {
-        gemm_epilogue_rope64(p, row, col0, r0, r1);
+        const int tr = quad * 32 + lane;
+        gemm_epilogue_rope64(p, row, col0, r0, r1, rope_tile ? reinterpret_cast<const float4*>(s_bias) + tr * 16 : nullptr, tr & 7);
       } else {
         const float4* b4 = reinterpret_cast<const float4*>(s_bias + col0);
         float v[32];
