@@ -90,10 +90,10 @@ __device__ __forceinline__ void gemm_store_32(const GemmParams& p, int row, int 
 
 // One 64-wide head: lo = columns [col, col+32), hi = [col+32, col+64). Reference: conformer.py:45-51 (rotate_half),
 // applied to the bf16 projection output in fp32 and rounded to bf16 when SDPA consumes it.
-// tab_row: this row's cos|sin (16 float4, chunk index XOR-swizzled by swz) staged in shared memory, or nullptr to read
-// the global tables directly.
+// tab_row: shared-space address of this row's cos|sin (16 float4, chunk index XOR-swizzled by swz), or 0 to read the
+// global tables directly.
 __device__ __forceinline__ void gemm_epilogue_rope64(const GemmParams& p, int row, int col, const uint32_t (&lo)[32],
-                                                     const uint32_t (&hi)[32], const float4* tab_row = nullptr, int swz = 0) {
+                                                     const uint32_t (&hi)[32], uint32_t tab_row = 0, int swz = 0) {
   uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col);
   // the projection output is bf16 in the reference: round first (also halves the live registers)
   uint32_t l2[16], h2[16];
@@ -109,11 +109,11 @@ __device__ __forceinline__ void gemm_epilogue_rope64(const GemmParams& p, int ro
 #pragma unroll
     for (int g = 0; g < 4; ++g) {  // 8 columns of each half per group: cos/sin chunks 2g, 2g+1
       float4 cs[2], sn[2];
-      if (tab_row != nullptr) {
-        cs[0] = tab_row[(2 * g) ^ swz];
-        cs[1] = tab_row[(2 * g + 1) ^ swz];
-        sn[0] = tab_row[8 + ((2 * g) ^ swz)];
-        sn[1] = tab_row[8 + ((2 * g + 1) ^ swz)];
+      if (tab_row != 0) {
+        cs[0] = lds128(tab_row + 16 * ((2 * g) ^ swz));
+        cs[1] = lds128(tab_row + 16 * ((2 * g + 1) ^ swz));
+        sn[0] = lds128(tab_row + 16 * (8 + ((2 * g) ^ swz)));
+        sn[1] = lds128(tab_row + 16 * (8 + ((2 * g + 1) ^ swz)));
       } else {
         cs[0] = __ldg(c4 + 2 * g);
         cs[1] = __ldg(c4 + 2 * g + 1);
@@ -172,7 +172,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 32 * kGemmEpiWarps);
+      mbar_init(&tmem_empty_bar[b], kGemmEpiWarps);  // one elected lane per epilogue warp
     }
     fence_mbar_init();
   }
@@ -259,18 +259,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       tmem_ld_wait_dep(r1);
       // the slice is in registers: hand the accumulator buffer back before doing any arithmetic
       tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
       if (row >= p.M) continue;
       if constexpr (EPI == EPI_QKV_ROPE) {
         gemm_epilogue_rope64(p, row, col0, r0, r1);
       } else {
-        const float4* b4 = reinterpret_cast<const float4*>(s_bias + col0);
+        const uint32_t b4 = smem_u32(s_bias + col0);
         float v[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 b = b4[i];
+          const float4 b = lds128(b4 + 16 * i);
           v[4 * i + 0] = __uint_as_float(r0[4 * i + 0]) + b.x;
           v[4 * i + 1] = __uint_as_float(r0[4 * i + 1]) + b.y;
           v[4 * i + 2] = __uint_as_float(r0[4 * i + 2]) + b.z;
@@ -279,7 +280,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         gemm_store_32<EPI>(p, row, col0, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 b = b4[8 + i];
+          const float4 b = lds128(b4 + 16 * (8 + i));
           v[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
           v[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
           v[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
@@ -336,7 +337,7 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 2 * 32 * kGemmEpiWarps);  // epilogue threads of both CTAs arrive on CTA 0's barrier
+      mbar_init(&tmem_empty_bar[b], 2 * kGemmEpiWarps);  // one lane per epilogue warp of both CTAs arrives on CTA 0's barrier
     }
     fence_mbar_init();
   }
@@ -440,19 +441,20 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       tmem_ld_wait_dep(r0);
       tmem_ld_wait_dep(r1);
       tc_fence_before();
-      mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
       if (row >= p.M) continue;
       if constexpr (EPI == EPI_QKV_ROPE) {
         const int tr = quad * 32 + lane;
-        gemm_epilogue_rope64(p, row, col0, r0, r1, rope_tile ? reinterpret_cast<const float4*>(s_bias) + tr * 16 : nullptr, tr & 7);
+        gemm_epilogue_rope64(p, row, col0, r0, r1, rope_tile ? smem_u32(s_bias) + tr * 256 : 0u, tr & 7);
       } else {
-        const float4* b4 = reinterpret_cast<const float4*>(s_bias + col0);
+        const uint32_t b4 = smem_u32(s_bias + col0);
         float v[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 b = b4[i];
+          const float4 b = lds128(b4 + 16 * i);
           v[4 * i + 0] = __uint_as_float(r0[4 * i + 0]) + b.x;
           v[4 * i + 1] = __uint_as_float(r0[4 * i + 1]) + b.y;
           v[4 * i + 2] = __uint_as_float(r0[4 * i + 2]) + b.z;
@@ -461,7 +463,7 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         gemm_store_32<EPI>(p, row, col0, v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 b = b4[8 + i];
+          const float4 b = lds128(b4 + 16 * (8 + i));
           v[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
           v[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
           v[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;

@@ -70,6 +70,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {  // explicit shared-space load (generic pointers compile to LD.E)
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {  // generic-proxy smem writes -> visible to TMA / UMMA
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -186,7 +192,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       "{\n\t"
       ".reg .b32 remote;\n\t"
       "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remote];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
