@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libedm_s2a.so")
 
-EPI_BF16, EPI_SWISH_BF16, EPI_QKV_ROPE, EPI_RESID_F32, EPI_F32 = range(5)
+EPI_BF16, EPI_SWISH_BF16, EPI_QKV_ROPE, EPI_RESID_F32, EPI_F32, EPI_GLU_BF16 = range(6)
 
 
 class S2AConfig(C.Structure):
@@ -40,7 +40,7 @@ _SIGNATURES = {
     "edm_attention": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "edm_attention_dbg": (_i, [_vp, _i, _i, _i, _vp, _u, _u, _u, _vp]),
     "edm_layernorm": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
-    "edm_conv_module": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "edm_conv_module": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "edm_sample": (_i, [_vp, _ll, _i, _vp, _i, _ull, _u, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "edm_remask": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _ull, _u, _vp]),
     "edm_rvq_encode": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -193,6 +193,7 @@ int launch_gemm(int epi, const CUtensorMap& ma, const CUtensorMap& mb, const Gem
     case EPI_QKV_ROPE: return launch_gemm_t<EPI_QKV_ROPE>(ma, mb, p, st);
     case EPI_RESID_F32: return launch_gemm_t<EPI_RESID_F32>(ma, mb, p, st);
     case EPI_F32: return launch_gemm_t<EPI_F32>(ma, mb, p, st);
+    case EPI_GLU_BF16: return launch_gemm_t<EPI_GLU_BF16>(ma, mb, p, st);
   }
   return fail(EDM_ERR_INVALID, "unknown epilogue %d", epi);
 }
@@ -227,15 +228,20 @@ int launch_ln(const LnParams& p, cudaStream_t st) {
   return 0;
 }
 
-int launch_conv(const ConvModParams& p, cudaStream_t st) {
+// glu_input: the kernel reads [B*N, 4096] and applies the GLU itself; otherwise the input is the already gated [B*N, 2048]
+int launch_conv(const ConvModParams& p, bool glu_input, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    EDM_CUDA(cudaFuncSetAttribute(conv_module_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
+    EDM_CUDA(cudaFuncSetAttribute(conv_module_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
+    EDM_CUDA(cudaFuncSetAttribute(conv_module_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
     attr_set = true;
   }
   dim3 grid((p.N + kConvTT - 1) / kConvTT, p.B);
-  ProfScope prof(PK_CONV, static_cast<double>(p.B) * p.N * 12288.0, st);
-  conv_module_kernel<<<grid, 256, kConvSmemBytes, st>>>(p);
+  ProfScope prof(PK_CONV, static_cast<double>(p.B) * p.N * (glu_input ? 12288.0 : 8192.0), st);
+  if (glu_input)
+    conv_module_kernel<true><<<grid, 256, kConvSmemBytes, st>>>(p);
+  else
+    conv_module_kernel<false><<<grid, 256, kConvSmemBytes, st>>>(p);
   EDM_LAUNCH_CHECK("conv_module");
   return 0;
 }
@@ -331,12 +337,12 @@ extern "C" int edm_layernorm(const void* in, int in_is_bf16, int rows, const flo
   return launch_ln(p, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int edm_conv_module(const void* in, void* out, const float* dw_w, const float* dw_b, const float* cln_w, int B, int N, void* stream) {
+extern "C" int edm_conv_module(const void* in, int glu_input, void* out, const float* dw_w, const float* dw_b, const float* cln_w, int B, int N, void* stream) {
   if (int rc = check_arch()) return rc;
   ConvModParams p;
   p.in = static_cast<const __nv_bfloat16*>(in); p.out = static_cast<__nv_bfloat16*>(out);
   p.dw_w = dw_w; p.dw_b = dw_b; p.cln_w = cln_w; p.B = B; p.N = N;
-  return launch_conv(p, static_cast<cudaStream_t>(stream));
+  return launch_conv(p, glu_input != 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int edm_sample(const float* logits, long long ld, int rows, const float* noise, int use_philox, unsigned long long seed,
@@ -505,11 +511,12 @@ int run_block_body(edm_s2a_ctx* c, int l, cudaStream_t st) {
   // conv module
   ln.w1 = c->bwf(l, F_CONV_LN_W); ln.b1 = c->bwf(l, F_CONV_LN_B);
   if (int rc = launch_ln(ln, st)) return rc;
-  if (int rc = launch_gemm(EPI_BF16, c->m_z, c->bmaps[l].pw1, gp(M, 4096, 1024, c->bwf(l, F_PW1_B), c->h, 4096), st)) return rc;
+  // pointwise conv 1 + GLU in one pass: the packed weight interleaves 32 value rows with their 32 gate rows
+  if (int rc = launch_gemm(EPI_GLU_BF16, c->m_z, c->bmaps[l].pw1, gp(M, 4096, 1024, c->bwf(l, F_PW1_B), c->h, 2048), st)) return rc;
   {
     ConvModParams p;
     p.in = c->h; p.out = c->g; p.dw_w = c->bwf(l, F_DW_W); p.dw_b = c->bwf(l, F_DW_B); p.cln_w = c->bwf(l, F_CLN_W); p.B = c->B; p.N = c->N;
-    if (int rc = launch_conv(p, st)) return rc;
+    if (int rc = launch_conv(p, false, st)) return rc;
   }
   if (int rc = launch_gemm(EPI_RESID_F32, c->m_g, c->bmaps[l].pw2, gp(M, 1024, 2048, c->bwf(l, F_PW2_B), c->x, 1024, 1.0f), st)) return rc;
   // ff2

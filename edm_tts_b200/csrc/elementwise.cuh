@@ -149,6 +149,9 @@ struct ConvModParams {
 constexpr int kConvTT = 24;  // output tokens per CTA (4 halo rows are re-read and re-gated: 17 % overhead)
 constexpr uint32_t kConvSmemBytes = kConvTT * 256 * 16;  // per-thread spill of the Swish outputs (bf16 x 8 per token)
 
+// kGlu = true : in is [B*N, 4096] (value | gate), the GLU runs here.
+// kGlu = false: in is [B*N, 2048], already gated by the pointwise-conv GEMM epilogue (EPI_GLU_BF16).
+template <bool kGlu>
 __global__ void __launch_bounds__(256, 2) conv_module_kernel(const ConvModParams p) {
   extern __shared__ uint4 s_keep[];  // [kConvTT][256]
   __shared__ float s_sum[kConvTT][8];
@@ -157,7 +160,8 @@ __global__ void __launch_bounds__(256, 2) conv_module_kernel(const ConvModParams
   const int c0 = tid * 8;
   const int t0 = blockIdx.x * kConvTT;
   const int b = blockIdx.y;
-  const __nv_bfloat16* base = p.in + static_cast<long long>(b) * p.N * (2 * kConvC) + c0;
+  constexpr int kInW = kGlu ? 2 * kConvC : kConvC;  // input row width
+  const __nv_bfloat16* base = p.in + static_cast<long long>(b) * p.N * kInW + c0;
 
   float wt[8][5], bias[8];
 #pragma unroll
@@ -174,13 +178,13 @@ __global__ void __launch_bounds__(256, 2) conv_module_kernel(const ConvModParams
     for (int c = 0; c < 8; ++c) win[j][c] = 0.f;
 
   // two rows of loads in flight ahead of the arithmetic
-  uint4 pa[2], pg[2];
+  uint4 pa[2], pg[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int t = t0 - 2 + r;
     if (t >= 0 && t < p.N) {
-      pa[r] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * (2 * kConvC));
-      pg[r] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * (2 * kConvC) + kConvC);
+      pa[r] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * kInW);
+      if constexpr (kGlu) pg[r] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * kInW + kConvC);
     } else {
       pa[r] = make_uint4(0, 0, 0, 0);
       pg[r] = make_uint4(0, 0, 0, 0);
@@ -193,8 +197,8 @@ __global__ void __launch_bounds__(256, 2) conv_module_kernel(const ConvModParams
     {
       const int tn = t0 + r;  // row r + 2
       if (r + 2 < kConvTT + 4 && tn >= 0 && tn < p.N) {
-        pa[r & 1] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(tn) * (2 * kConvC));
-        pg[r & 1] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(tn) * (2 * kConvC) + kConvC);
+        pa[r & 1] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(tn) * kInW);
+        if constexpr (kGlu) pg[r & 1] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(tn) * kInW + kConvC);
       } else {
         pa[r & 1] = make_uint4(0, 0, 0, 0);
         pg[r & 1] = make_uint4(0, 0, 0, 0);
@@ -209,8 +213,11 @@ __global__ void __launch_bounds__(256, 2) conv_module_kernel(const ConvModParams
       const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const uint32_t sg = pack_bf16x2(sigmoid_tanh(bf16lo(gw[c])), sigmoid_tanh(bf16hi(gw[c])));
-        const uint32_t gl = bf16x2_mul(aw[c], sg);
+        uint32_t gl = aw[c];
+        if constexpr (kGlu) {
+          const uint32_t sg = pack_bf16x2(sigmoid_tanh(bf16lo(gw[c])), sigmoid_tanh(bf16hi(gw[c])));
+          gl = bf16x2_mul(aw[c], sg);
+        }
         win[4][2 * c + 0] = bf16lo(gl);
         win[4][2 * c + 1] = bf16hi(gl);
       }

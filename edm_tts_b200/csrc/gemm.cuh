@@ -23,6 +23,8 @@ enum EpiKind : int {
   EPI_QKV_ROPE = 2,    // cols < rope_cols: rotary embedding on bf16(acc) per 64-wide head; others bf16(acc)
   EPI_RESID_F32 = 3,   // x_f32[r, c] += scale * bf16(acc + bias)                                (residual branches)
   EPI_F32 = 4,         // out_f32 = acc + bias                                                   (logits heads)
+  EPI_GLU_BF16 = 5,    // per 64 columns: first 32 = value, last 32 = gate (weights interleaved at pack time);
+                       // out_bf16[., N/2] = bf16(bf16(value) * bf16(sigmoid(bf16(gate))))       (conv module pointwise-1 + GLU)
 };
 
 struct GemmParams {
@@ -90,6 +92,22 @@ __device__ __forceinline__ void gemm_store_32(const GemmParams& p, int row, int 
 
 // One 64-wide head: lo = columns [col, col+32), hi = [col+32, col+64). Reference: conformer.py:45-51 (rotate_half),
 // applied to the bf16 projection output in fp32 and rounded to bf16 when SDPA consumes it.
+// GLU over one 64-column group: a = 32 value accumulators (+bias), g = their 32 gates (+bias). Reference: Conv1d output is
+// bf16, GLU = out * gate.sigmoid() in bf16 (conformer/conformer.py:59-66,170-171). Writes 32 bf16 at column col_out.
+__device__ __forceinline__ void gemm_store_glu(const GemmParams& p, int row, int col_out, const float (&a)[32], const float (&g)[32]) {
+  uint32_t w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t a2 = pack_bf16x2(a[2 * i], a[2 * i + 1]);
+    const uint32_t g2 = pack_bf16x2(g[2 * i], g[2 * i + 1]);
+    const uint32_t s2 = pack_bf16x2(sigmoid_tanh(bf16lo(g2)), sigmoid_tanh(bf16hi(g2)));
+    w[i] = bf16x2_mul(a2, s2);
+  }
+  uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col_out);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+
 // tab_row: shared-space address of this row's cos|sin (16 float4, chunk index XOR-swizzled by swz), or 0 to read the
 // global tables directly.
 __device__ __forceinline__ void gemm_epilogue_rope64(const GemmParams& p, int row, int col, const uint32_t (&lo)[32],
@@ -277,16 +295,29 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
           v[4 * i + 2] = __uint_as_float(r0[4 * i + 2]) + b.z;
           v[4 * i + 3] = __uint_as_float(r0[4 * i + 3]) + b.w;
         }
-        gemm_store_32<EPI>(p, row, col0, v);
+        if constexpr (EPI == EPI_GLU_BF16) {
+          float g[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = lds128(b4 + 16 * (8 + i));
-          v[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
-          v[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
-          v[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
-          v[4 * i + 3] = __uint_as_float(r1[4 * i + 3]) + b.w;
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = lds128(b4 + 16 * (8 + i));
+            g[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
+            g[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
+            g[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
+            g[4 * i + 3] = __uint_as_float(r1[4 * i + 3]) + b.w;
+          }
+          gemm_store_glu(p, row, col0 >> 1, v, g);
+        } else {
+          gemm_store_32<EPI>(p, row, col0, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = lds128(b4 + 16 * (8 + i));
+            v[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
+            v[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
+            v[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
+            v[4 * i + 3] = __uint_as_float(r1[4 * i + 3]) + b.w;
+          }
+          gemm_store_32<EPI>(p, row, col0 + 32, v);
         }
-        gemm_store_32<EPI>(p, row, col0 + 32, v);
       }
     }
   }
@@ -460,16 +491,29 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           v[4 * i + 2] = __uint_as_float(r0[4 * i + 2]) + b.z;
           v[4 * i + 3] = __uint_as_float(r0[4 * i + 3]) + b.w;
         }
-        gemm_store_32<EPI>(p, row, col0, v);
+        if constexpr (EPI == EPI_GLU_BF16) {
+          float g[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = lds128(b4 + 16 * (8 + i));
-          v[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
-          v[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
-          v[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
-          v[4 * i + 3] = __uint_as_float(r1[4 * i + 3]) + b.w;
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = lds128(b4 + 16 * (8 + i));
+            g[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
+            g[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
+            g[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
+            g[4 * i + 3] = __uint_as_float(r1[4 * i + 3]) + b.w;
+          }
+          gemm_store_glu(p, row, col0 >> 1, v, g);
+        } else {
+          gemm_store_32<EPI>(p, row, col0, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = lds128(b4 + 16 * (8 + i));
+            v[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
+            v[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
+            v[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
+            v[4 * i + 3] = __uint_as_float(r1[4 * i + 3]) + b.w;
+          }
+          gemm_store_32<EPI>(p, row, col0 + 32, v);
         }
-        gemm_store_32<EPI>(p, row, col0 + 32, v);
       }
     }
   }

@@ -34,6 +34,13 @@ def quantizer_tensors(sd: dict, n_codebooks: int, prefix: str, device, dtype=tor
     return torch.stack(w_in), torch.stack(b_in), torch.stack(w_out), torch.stack(b_out), torch.stack(cb)
 
 
+def glu_interleave(n_out: int) -> torch.Tensor:
+    """Row order [v0..v31, g0..g31, v32..v63, g32..g63, ...] for a [2C] -> (value C | gate C) projection."""
+    c = n_out // 2
+    v = torch.arange(c).view(-1, 32)
+    return torch.cat([v, v + c], dim=1).reshape(-1)
+
+
 def rope_tables(max_positions: int, dim_head: int, device):
     """cos / sin of RotaryEmbedding.forward (conformer/conformer.py:28-42); only the first half is stored (freqs = cat(f, f))."""
     inv_freq = 1.0 / (10000 ** (torch.arange(0, dim_head, 2, device=device).float() / dim_head))
@@ -65,8 +72,11 @@ def pack_s2a_weights(sd: dict, cfg: InjectionConformerConfig, device, max_positi
         out[o + "bo"] = f32(sd[p + "attn.fn.to_out.bias"])
         out[o + "conv_ln_w"] = f32(sd[p + "conv.net.0.weight"])
         out[o + "conv_ln_b"] = f32(sd[p + "conv.net.0.bias"])
-        out[o + "pw1_w"] = bf16(sd[p + "conv.net.2.weight"][:, :, 0])
-        out[o + "pw1_b"] = f32(sd[p + "conv.net.2.bias"])
+        # pointwise conv 1 feeds a GLU (value = first half of the channels, gate = second half): interleave 32 value rows
+        # with their 32 gate rows so the GEMM epilogue, which owns 64 consecutive columns per thread, can gate in place
+        perm = glu_interleave(sd[p + "conv.net.2.weight"].shape[0])
+        out[o + "pw1_w"] = bf16(sd[p + "conv.net.2.weight"][:, :, 0][perm])
+        out[o + "pw1_b"] = f32(sd[p + "conv.net.2.bias"][perm])
         # autocast runs the depthwise conv with bf16 weights
         out[o + "dw_w"] = f32(sd[p + "conv.net.4.conv.weight"][:, 0, :].to(torch.bfloat16).float())
         out[o + "dw_b"] = f32(sd[p + "conv.net.4.conv.bias"])

@@ -34,7 +34,8 @@ enum edm_epilogue {
   EDM_EPI_SWISH_BF16 = 1,  /* conformer.py:54-56,152-154  Linear -> Swish */
   EDM_EPI_QKV_ROPE = 2,    /* conformer.py:132-138       to_q/to_kv + rotary embedding on q,k */
   EDM_EPI_RESID_F32 = 3,   /* conformer.py:222-233       x += scale * (Linear(...)) on the fp32 residual stream */
-  EDM_EPI_F32 = 4          /* injection_conformer_wrapper.py:56-63   logits head */
+  EDM_EPI_F32 = 4,         /* injection_conformer_wrapper.py:56-63   logits head */
+  EDM_EPI_GLU_BF16 = 5     /* conformer.py:59-66,170-171  pointwise conv + GLU; weight rows interleaved 32 value | 32 gate */
 };
 
 int edm_abi_version(void);
@@ -62,10 +63,12 @@ int edm_attention_dbg(const void* qkv, int B, int N, int H, void* out, unsigned 
 int edm_layernorm(const void* in, int in_is_bf16, int rows, const float* w1, const float* b1, const float* w2,
                   const float* b2, float* y_out, void* z_out, int seq_len, int z_skip, float eps, void* stream);
 
-/* GLU -> depthwise conv (k=5, zero pad 2|2 per sequence) -> Swish -> ChanLayerNorm; in [B*N,4096] bf16 -> out [B*N,2048]
- * bf16. Replaces conformer.py:171-174 (GLU :59-66, DepthWiseConv1d :69-77, Swish :54-56, ChanLayerNorm :90-99). */
-int edm_conv_module(const void* in, void* out, const float* dw_w, const float* dw_b, const float* cln_w, int B, int N,
-                    void* stream);
+/* GLU -> depthwise conv (k=5, zero pad 2|2 per sequence) -> Swish -> ChanLayerNorm -> out [B*N,2048] bf16.
+ * glu_input != 0: in is [B*N,4096] bf16 (value | gate) and the GLU runs here; glu_input == 0: in is [B*N,2048] bf16 already
+ * gated by the pointwise-conv GEMM (EDM_EPI_GLU_BF16), which is what the decoder context uses.
+ * Replaces conformer.py:171-174 (GLU :59-66, DepthWiseConv1d :69-77, Swish :54-56, ChanLayerNorm :90-99). */
+int edm_conv_module(const void* in, int glu_input, void* out, const float* dw_w, const float* dw_b, const float* cln_w,
+                    int B, int N, void* stream);
 
 /* Per-row arg-max / Gumbel-max sampling over 1024 logits + log-softmax of the chosen id.
  * rows = B*T*Q; ids land at ids[(b*out_q_stride + out_q0 + q)*T + t]. noise: [rows,1024] Gumbel or NULL;

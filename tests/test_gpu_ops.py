@@ -54,6 +54,10 @@ def test_gemm_epilogues(L, M, N, K):
     gemm(L, a, b, L.EPI_SWISH_BF16, bias, outb)
     h = rb(acc + bias)
     assert_bf16_close(outb, rb(h * rb(torch.sigmoid(h))), h, ulps=3)
+    outg = torch.empty(M, N // 2, device=dev, dtype=torch.bfloat16)
+    gemm(L, a, b, L.EPI_GLU_BF16, bias, outg)
+    hb = rb(acc + bias).view(M, N // 64, 2, 32)
+    assert_bf16_close(outg, rb(hb[:, :, 0] * rb(torch.sigmoid(hb[:, :, 1]))).reshape(M, N // 2), hb[:, :, 0].reshape(M, N // 2), ulps=3)
     x0 = torch.randn(M, N, device=dev)
     x = x0.clone()
     gemm(L, a, b, L.EPI_RESID_F32, bias, x, scale=0.5)
@@ -132,10 +136,17 @@ def test_conv_module(L, B, N):
     dw_b = torch.randn(2048, device=dev) * 0.1
     cln_w = torch.randn(2048, device=dev)
     out = torch.empty(B * N, 2048, device=dev, dtype=torch.bfloat16)
-    L.check(L.lib().edm_conv_module(L.ptr(h), L.ptr(out), L.ptr(dw_w), L.ptr(dw_b), L.ptr(cln_w), B, N, L.stream_ptr()))
+    L.check(L.lib().edm_conv_module(L.ptr(h), 1, L.ptr(out), L.ptr(dw_w), L.ptr(dw_b), L.ptr(cln_w), B, N, L.stream_ptr()))
     d = (out.float() - _conv_ref(h, dw_w, dw_b, cln_w, B, N)).abs()
     # a bf16 rounding flip in an intermediate moves the result by at most a few ulps; the bulk is exact
     assert d.max().item() < 0.07 and d.mean().item() < 1e-4, (d.max().item(), d.mean().item())
+    # same module with the GLU already applied upstream (what the GEMM epilogue EPI_GLU_BF16 feeds it)
+    x = h.float().view(B * N, 4096)
+    gated = bf(rb(x[:, :2048] * rb(torch.sigmoid(x[:, 2048:]))))
+    out2 = torch.empty_like(out)
+    L.check(L.lib().edm_conv_module(L.ptr(gated), 0, L.ptr(out2), L.ptr(dw_w), L.ptr(dw_b), L.ptr(cln_w), B, N, L.stream_ptr()))
+    d2 = (out2.float() - _conv_ref(h, dw_w, dw_b, cln_w, B, N)).abs()
+    assert d2.max().item() < 0.07 and d2.mean().item() < 1e-4, (d2.max().item(), d2.mean().item())
 
 
 def test_sample_and_remask(L):

@@ -74,6 +74,13 @@ def test_gemm():
         ref = rb(h * rb(torch.sigmoid(h)))
         err = (outb.float() - ref).abs().max().item()
         print(f"gemm SWISH max_abs_err={err:.3e}", flush=True)
+        # GLU (columns interleaved 32 value | 32 gate)
+        outg = torch.empty(M, N // 2, device=dev, dtype=torch.bfloat16)
+        gemm_call(a, b, L.EPI_GLU_BF16, bias, outg)
+        hb = rb(acc + bias).view(M, N // 64, 2, 32)
+        refg = rb(hb[:, :, 0] * rb(torch.sigmoid(hb[:, :, 1]))).reshape(M, N // 2)
+        err = (outg.float() - refg).abs().max().item()
+        print(f"gemm GLU   max_abs_err={err:.3e}", flush=True)
         # RESID
         x0 = torch.randn(M, N, device=dev)
         x = x0.clone()
@@ -96,12 +103,12 @@ def test_gemm():
         err = (outb.float() - rb(ref)).abs().max().item()
         print(f"gemm ROPE  max_abs_err={err:.3e} (rope_cols={rope_cols})", flush=True)
     # timing at the bench shapes
-    for (M, N, K, epi) in [(32000, 4096, 1024, L.EPI_SWISH_BF16), (32000, 1024, 4096, L.EPI_RESID_F32), (32000, 3072, 1024, L.EPI_BF16),
+    for (M, N, K, epi) in [(32000, 4096, 1024, L.EPI_GLU_BF16), (32000, 4096, 1024, L.EPI_SWISH_BF16), (32000, 1024, 4096, L.EPI_RESID_F32), (32000, 3072, 1024, L.EPI_BF16),
                            (32000, 1024, 1024, L.EPI_RESID_F32), (32000, 1024, 2048, L.EPI_RESID_F32)]:
         a = bf(torch.randn(M, K, device=dev))
         b = bf(torch.randn(N, K, device=dev) / math.sqrt(K))
         bias = torch.randn(N, device=dev)
-        out = torch.zeros(M, N, device=dev, dtype=torch.float32 if epi == L.EPI_RESID_F32 else torch.bfloat16)
+        out = torch.zeros(M, N // 2 if epi == L.EPI_GLU_BF16 else N, device=dev, dtype=torch.float32 if epi == L.EPI_RESID_F32 else torch.bfloat16)
         ms = timeit(lambda: gemm_call(a, b, epi, bias, out, scale=0.5))
         ms_ref = timeit(lambda: torch.matmul(a, b.T))
         print(f"gemm time M={M} N={N} K={K} epi={epi}: {ms:.3f} ms = {2 * M * N * K / ms / 1e9:.1f} TFLOP/s  (torch.matmul {ms_ref:.3f} ms = {2 * M * N * K / ms_ref / 1e9:.1f})", flush=True)
@@ -184,15 +191,18 @@ def test_conv():
         dw_b = torch.randn(2048, device=dev) * 0.1
         cln_w = torch.randn(2048, device=dev)
         out = torch.empty(B * N, 2048, device=dev, dtype=torch.bfloat16)
-        L.check(L.lib().edm_conv_module(L.ptr(h), L.ptr(out), L.ptr(dw_w), L.ptr(dw_b), L.ptr(cln_w), B, N, L.stream_ptr()))
+        L.check(L.lib().edm_conv_module(L.ptr(h), 1, L.ptr(out), L.ptr(dw_w), L.ptr(dw_b), L.ptr(cln_w), B, N, L.stream_ptr()))
         ref = conv_ref(h, dw_w, dw_b, cln_w, B, N)
         d = (out.float() - ref).abs()
         print(f"conv B={B} N={N}: max_abs_err={d.max().item():.3e} mean={d.mean().item():.3e} frac>0.05={(d > 0.05).float().mean().item():.2e}", flush=True)
     B, N = 64, 500
     h = bf(torch.randn(B * N, 4096, device=dev))
     out = torch.empty(B * N, 2048, device=dev, dtype=torch.bfloat16)
-    ms = timeit(lambda: L.lib().edm_conv_module(L.ptr(h), L.ptr(out), L.ptr(dw_w), L.ptr(dw_b), L.ptr(cln_w), B, N, L.stream_ptr()))
+    ms = timeit(lambda: L.lib().edm_conv_module(L.ptr(h), 1, L.ptr(out), L.ptr(dw_w), L.ptr(dw_b), L.ptr(cln_w), B, N, L.stream_ptr()))
     print(f"conv time B={B} N={N}: {ms * 1e3:.1f} us = {B * N * 12288 / ms / 1e6:.0f} GB/s", flush=True)
+    hg = bf(torch.randn(B * N, 2048, device=dev))
+    ms = timeit(lambda: L.lib().edm_conv_module(L.ptr(hg), 0, L.ptr(out), L.ptr(dw_w), L.ptr(dw_b), L.ptr(cln_w), B, N, L.stream_ptr()))
+    print(f"conv (pre-gated input) time B={B} N={N}: {ms * 1e3:.1f} us = {B * N * 8192 / ms / 1e6:.0f} GB/s", flush=True)
 
 
 def test_sample():
