@@ -238,6 +238,23 @@ def main():
         "layernorm": {"launches": pc[2], "ms": pm[2], "gbs": pw[2] / (pm[2] * 1e-3) / 1e9 if pm[2] > 0 else 0.0, "frac_hbm": pw[2] / (pm[2] * 1e-3) / 1e9 / hbm_peak if pm[2] > 0 else 0.0},
         "conv_module": {"launches": pc[3], "ms": pm[3], "gbs": pw[3] / (pm[3] * 1e-3) / 1e9 if pm[3] > 0 else 0.0, "frac_hbm": pw[3] / (pm[3] * 1e-3) / 1e9 / hbm_peak if pm[3] > 0 else 0.0},
     }
+    # secondary kernel (BASELINE config 4): DAC RVQ encode of a dump_tokens batch, z [32, 1024, 3000] fp32 resident in HBM
+    from edm_tts_b200 import ResidualVectorQuantize
+    from edm_tts_b200.synthetic import make_quantizer_state_dict
+
+    rvq = ResidualVectorQuantize(make_quantizer_state_dict(cfg, 0), device=dev)
+    zb = torch.randn(32, 1024, 3000, device=dev)
+    for _ in range(3):
+        rvq.encode(zb)
+    torch.cuda.synchronize()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(10):
+        rvq.encode(zb)
+    r1.record()
+    torch.cuda.synchronize()
+    rvq_ms = r0.elapsed_time(r1) / 10
+    del zb
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -258,6 +275,10 @@ def main():
                      "achieved": gemm_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tf_peak, "traffic": None,
                      "peak_kind": f"{peak_kind} bf16 sustained", "gemm_share_of_step": pm[0] / ms_total},
         "kernels": kernels,
+        "secondary": {"metric": "dac_rvq_encode_frames_per_s", "value": 32 * 3000 / (rvq_ms * 1e-3), "unit": "frames/s", "ms": rvq_ms,
+                      "workload": "DAC RVQ encode, z [32, 1024, 3000] fp32 (dump_tokens batch, BASELINE config 4), 12 codebooks, per GPU",
+                      "hbm_gbs": 32 * 3000 * (4096 + 96) / (rvq_ms * 1e-3) / 1e9, "frac_hbm": 32 * 3000 * (4096 + 96) / (rvq_ms * 1e-3) / 1e9 / hbm_peak,
+                      "note": "3xTF32 mma.sync contractions + exhaustive 1024-code search; bound by the legacy tensor path / compare ALU work, not HBM"},
         "model_flops_utilisation": {"algorithmic_tflops": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12,
                                     "frac_of_peak": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12 / tf_peak},
     }

@@ -366,7 +366,7 @@ extern "C" int edm_remask(const float* logp, const float* gumbel, const uint8_t*
   return 0;
 }
 
-extern "C" int edm_rvq_encode(const void* z, int z_is_bf16, int B, int T, int n_levels, const float* w_in, const float* b_in,
+extern "C" int edm_rvq_encode(const void* z, int z_is_bf16, int B, int T, int n_levels, const float* w_in_t, const float* b_in,
                               const float* cb_norm, const float* cb_n2, const float* g, long long* codes, const long long* forced,
                               float* latents, void* stream) {
   if (int rc = check_arch()) return rc;
@@ -377,7 +377,7 @@ extern "C" int edm_rvq_encode(const void* z, int z_is_bf16, int B, int T, int n_
     attr_set = true;
   }
   RvqParams p;
-  p.z = z; p.z_is_bf16 = z_is_bf16; p.B = B; p.T = T; p.n_levels = n_levels; p.w_in = w_in; p.b_in = b_in;
+  p.z = z; p.z_is_bf16 = z_is_bf16; p.B = B; p.T = T; p.n_levels = n_levels; p.w_in_t = w_in_t; p.b_in = b_in;
   p.cb_norm = cb_norm; p.cb_n2 = cb_n2; p.g = g; p.codes = codes; p.forced = forced; p.latents = latents;
   dim3 grid((T + kRvqFrames - 1) / kRvqFrames, B);
   rvq_encode_kernel<<<grid, 256, kRvqSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);

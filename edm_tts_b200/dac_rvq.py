@@ -40,7 +40,7 @@ class ResidualVectorQuantize:
         codes = torch.empty(B, self.n_codebooks, T, device=self.device, dtype=torch.int64)
         lat = torch.empty(B, 96, T, device=self.device, dtype=torch.float32) if return_latents else None
         fc = None if forced_codes is None else forced_codes.to(self.device, torch.int64).contiguous()
-        L.check(L.lib().edm_rvq_encode(L.ptr(z), int(z.dtype == torch.bfloat16), B, T, self.n_codebooks, L.ptr(t["w_in"]), L.ptr(t["b_in"]),
+        L.check(L.lib().edm_rvq_encode(L.ptr(z), int(z.dtype == torch.bfloat16), B, T, self.n_codebooks, L.ptr(t["w_in_t"]), L.ptr(t["b_in"]),
                                        L.ptr(t["cb_norm"]), L.ptr(t["cb_n2"]), L.ptr(t["g"]), L.ptr(codes), L.ptr(fc), L.ptr(lat),
                                        L.stream_ptr()), "rvq_encode")
         return (codes, lat[:, : self.n_codebooks * self.codebook_dim]) if return_latents else codes

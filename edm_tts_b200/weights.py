@@ -136,7 +136,7 @@ def pack_rvq_weights(sd: dict, n_codebooks: int, prefix: str, device) -> dict:
     g_full = torch.zeros(12, 12, cb.shape[1], cbd, device=device, dtype=torch.float32)
     g_full[:L, :L] = g.float()
     return {
-        "w_in": padl(w_in.float()).reshape(12 * cbd, latent).contiguous(),
+        "w_in_t": padl(w_in.float()).reshape(12 * cbd, latent).t().contiguous(),   # [latent, 96]: rows are contiguous per channel
         "b_in": padl(b_in.float()).reshape(-1).contiguous(),
         "cb_norm": padl(cbn).contiguous(),
         "cb_n2": padl(cbn.pow(2).sum(-1)).contiguous(),

@@ -84,8 +84,9 @@ int edm_remask(const float* logp, const float* gumbel, const uint8_t* mask_old, 
 
 /* DAC residual VQ: z [B,1024,T] (fp32 or bf16) -> codes int64 [B,n_levels,T]. Replaces
  * ResidualVectorQuantize.forward, dac/vector_quantizer.py:146-210 (codes only; eval mode). Tables are built by the
- * host side (edm_tts_b200/dac_rvq.py) from the reference state dict. */
-int edm_rvq_encode(const void* z, int z_is_bf16, int B, int T, int n_levels, const float* w_in, const float* b_in,
+ * host side (edm_tts_b200/weights.py:pack_rvq_weights) from the reference state dict: w_in_t [1024,96] stacked folded
+ * in_proj weights (transposed), b_in [96], cb_norm [12,1024,8], cb_n2 [12,1024], g [12,12,1024,8]. */
+int edm_rvq_encode(const void* z, int z_is_bf16, int B, int T, int n_levels, const float* w_in_t, const float* b_in,
                    const float* cb_norm, const float* cb_n2, const float* g, long long* codes,
                    const long long* forced, float* latents, void* stream);
 

@@ -33,7 +33,8 @@ def test_rvq_codes_vs_oracle(B, T):
     print(f"B={B} T={T}: {int(mism.sum())} / {mism.numel()} index mismatches; oracle margins there: {margins.tolist()[:8]}")
     assert (margins < 2e-5).all(), "index mismatch that is not a near-tie"
     assert mism.float().mean().item() < 1e-3
-    torch.testing.assert_close(lat, ref["latents"], rtol=1e-4, atol=2e-5)
+    # 3xTF32 tensor-core projection vs fp32 cuDNN conv: ~2^-20 relative per product, latents are O(1)
+    torch.testing.assert_close(lat, ref["latents"], rtol=1e-4, atol=1e-4)
     # free-running equals teacher-forced wherever no upstream level flipped
     free = q.encode(z)
     clean = ~(mism.cumsum(1) > 0)

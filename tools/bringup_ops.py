@@ -287,11 +287,12 @@ def test_rvq():
     proj = torch.einsum("lcd,lkd->lkc", w_out, cb) + b_out[:, None, :]  # [L, codes, 1024]
     g = torch.einsum("idc,jkc->ijkd", w_in, proj).contiguous()  # [i, j, codes, 8]
     codes = torch.empty(B, Lv, T, device=dev, dtype=torch.int64)
-    L.check(L.lib().edm_rvq_encode(L.ptr(z), 0, B, T, Lv, L.ptr(w_in.view(96, 1024).contiguous()), L.ptr(b_in.view(96).contiguous()), L.ptr(cbn),
+    w_t, b_flat = w_in.view(96, 1024).t().contiguous(), b_in.view(96).contiguous()
+    L.check(L.lib().edm_rvq_encode(L.ptr(z), 0, B, T, Lv, L.ptr(w_t), L.ptr(b_flat), L.ptr(cbn),
                                    L.ptr(n2), L.ptr(g), L.ptr(codes), None, None, L.stream_ptr()))
     mism = (codes != ref_codes)
     print(f"rvq free-running mismatches per level: {mism.sum((0, 2)).tolist()} of {B * T}", flush=True)
-    L.check(L.lib().edm_rvq_encode(L.ptr(z), 0, B, T, Lv, L.ptr(w_in.view(96, 1024).contiguous()), L.ptr(b_in.view(96).contiguous()), L.ptr(cbn),
+    L.check(L.lib().edm_rvq_encode(L.ptr(z), 0, B, T, Lv, L.ptr(w_t), L.ptr(b_flat), L.ptr(cbn),
                                    L.ptr(n2), L.ptr(g), L.ptr(codes), L.ptr(ref_codes.contiguous()), None, L.stream_ptr()))
     print(f"rvq teacher-forced mismatches per level: {(codes != ref_codes).sum((0, 2)).tolist()}", flush=True)
     feats = torch.empty(B, 1024, T, device=dev)
@@ -301,7 +302,7 @@ def test_rvq():
     B, T = 32, 3000
     z = torch.randn(B, 1024, T, device=dev)
     codes = torch.empty(B, Lv, T, device=dev, dtype=torch.int64)
-    ms = timeit(lambda: L.lib().edm_rvq_encode(L.ptr(z), 0, B, T, Lv, L.ptr(w_in.view(96, 1024).contiguous()), L.ptr(b_in.view(96).contiguous()),
+    ms = timeit(lambda: L.lib().edm_rvq_encode(L.ptr(z), 0, B, T, Lv, L.ptr(w_t), L.ptr(b_flat),
                                                L.ptr(cbn), L.ptr(n2), L.ptr(g), L.ptr(codes), None, None, L.stream_ptr()), iters=5, warm=2)
     print(f"rvq time B={B} T={T}: {ms:.3f} ms = {B * T / ms / 1e3:.2f} Mframes/s, {B * T * 4192 / ms / 1e6:.0f} GB/s", flush=True)
 
