@@ -239,9 +239,9 @@ int launch_conv(const ConvModParams& p, bool glu_input, cudaStream_t st) {
   dim3 grid((p.N + kConvTT - 1) / kConvTT, p.B);
   ProfScope prof(PK_CONV, static_cast<double>(p.B) * p.N * (glu_input ? 12288.0 : 8192.0), st);
   if (glu_input)
-    conv_module_kernel<true><<<grid, 256, kConvSmemBytes, st>>>(p);
+    conv_module_kernel<true><<<grid, kConvThreads, kConvSmemBytes, st>>>(p);
   else
-    conv_module_kernel<false><<<grid, 256, kConvSmemBytes, st>>>(p);
+    conv_module_kernel<false><<<grid, kConvThreads, kConvSmemBytes, st>>>(p);
   EDM_LAUNCH_CHECK("conv_module");
   return 0;
 }

@@ -146,73 +146,73 @@ struct ConvModParams {
   const float* cln_w;   // [2048]
   int B, N;
 };
-constexpr int kConvTT = 24;  // output tokens per CTA (4 halo rows are re-read and re-gated: 17 % overhead)
-constexpr uint32_t kConvSmemBytes = kConvTT * 256 * 16;  // per-thread spill of the Swish outputs (bf16 x 8 per token)
+constexpr int kConvTT = 20;        // output tokens per CTA (4 halo rows are re-read: 20 % more loads, served by L2)
+constexpr int kConvThreads = 512;  // 4 channels per thread
+constexpr uint32_t kConvSmemBytes = kConvTT * kConvThreads * 8;  // Swish outputs of the tile (bf16 x 4 per thread and token)
 
 // kGlu = true : in is [B*N, 4096] (value | gate), the GLU runs here.
 // kGlu = false: in is [B*N, 2048], already gated by the pointwise-conv GEMM epilogue (EPI_GLU_BF16).
+// Three phases per CTA (20 tokens x 2048 channels): (1) every thread streams its 4 channels through the 5-tap window and
+// parks the Swish outputs in shared memory, (2) one warp per token reduces mean / variance over the 2048 channels,
+// (3) every thread normalises its channels. 16 warps per CTA, two CTAs per SM.
 template <bool kGlu>
-__global__ void __launch_bounds__(256, 2) conv_module_kernel(const ConvModParams p) {
-  extern __shared__ uint4 s_keep[];  // [kConvTT][256]
-  __shared__ float s_sum[kConvTT][8];
-  __shared__ float s_sq[kConvTT][8];
+__global__ void __launch_bounds__(kConvThreads, 2) conv_module_kernel(const ConvModParams p) {
+  extern __shared__ uint2 s_keep[];  // [kConvTT][512]
+  __shared__ uint32_t s_mean2[kConvTT];
+  __shared__ uint32_t s_rstd2[kConvTT];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int c0 = tid * 8;
+  const int c0 = tid * 4;
   const int t0 = blockIdx.x * kConvTT;
   const int b = blockIdx.y;
   constexpr int kInW = kGlu ? 2 * kConvC : kConvC;  // input row width
   const __nv_bfloat16* base = p.in + static_cast<long long>(b) * p.N * kInW + c0;
 
-  float wt[8][5], bias[8];
+  float wt[4][5], bias[4];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < 4; ++c) {
 #pragma unroll
     for (int j = 0; j < 5; ++j) wt[c][j] = __ldg(p.dw_w + (c0 + c) * 5 + j);
     bias[c] = __ldg(p.dw_b + c0 + c);
   }
 
-  float win[5][8];
+  float win[5][4];
 #pragma unroll
   for (int j = 0; j < 5; ++j)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) win[j][c] = 0.f;
+    for (int c = 0; c < 4; ++c) win[j][c] = 0.f;
 
   // two rows of loads in flight ahead of the arithmetic
-  uint4 pa[2], pg[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+  uint2 pa[2], pg[2] = {make_uint2(0, 0), make_uint2(0, 0)};
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int t = t0 - 2 + r;
+    pa[r] = make_uint2(0, 0);
     if (t >= 0 && t < p.N) {
-      pa[r] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * kInW);
-      if constexpr (kGlu) pg[r] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * kInW + kConvC);
-    } else {
-      pa[r] = make_uint4(0, 0, 0, 0);
-      pg[r] = make_uint4(0, 0, 0, 0);
+      pa[r] = *reinterpret_cast<const uint2*>(base + static_cast<long long>(t) * kInW);
+      if constexpr (kGlu) pg[r] = *reinterpret_cast<const uint2*>(base + static_cast<long long>(t) * kInW + kConvC);
     }
   }
 
 #pragma unroll
   for (int r = 0; r < kConvTT + 4; ++r) {
-    const uint4 av = pa[r & 1], gv = pg[r & 1];
+    const uint2 av = pa[r & 1], gv = pg[r & 1];
     {
       const int tn = t0 + r;  // row r + 2
+      pa[r & 1] = make_uint2(0, 0);
       if (r + 2 < kConvTT + 4 && tn >= 0 && tn < p.N) {
-        pa[r & 1] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(tn) * kInW);
-        if constexpr (kGlu) pg[r & 1] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(tn) * kInW + kConvC);
-      } else {
-        pa[r & 1] = make_uint4(0, 0, 0, 0);
-        pg[r & 1] = make_uint4(0, 0, 0, 0);
+        pa[r & 1] = *reinterpret_cast<const uint2*>(base + static_cast<long long>(tn) * kInW);
+        if constexpr (kGlu) pg[r & 1] = *reinterpret_cast<const uint2*>(base + static_cast<long long>(tn) * kInW + kConvC);
       }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) win[j][c] = win[j + 1][c];
+      for (int c = 0; c < 4; ++c) win[j][c] = win[j + 1][c];
     {
       // GLU: value * bf16(sigmoid(gate)), rounded to bf16 (zero rows stay zero: 0 * 0.5 = 0)
-      const uint32_t aw[4] = {av.x, av.y, av.z, av.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+      const uint32_t aw[2] = {av.x, av.y}, gw[2] = {gv.x, gv.y};
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t gl = aw[c];
         if constexpr (kGlu) {
           const uint32_t sg = pack_bf16x2(sigmoid_tanh(bf16lo(gw[c])), sigmoid_tanh(bf16hi(gw[c])));
@@ -224,10 +224,9 @@ __global__ void __launch_bounds__(256, 2) conv_module_kernel(const ConvModParams
     }
     if (r >= 4) {
       const int o = r - 4;  // output token t0 + o, window = tokens t0+o-2 .. t0+o+2
-      uint32_t sp[4];
-      float s = 0.f, q = 0.f;
+      uint32_t sp[2];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float acc0 = bias[2 * c], acc1 = bias[2 * c + 1];
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
@@ -237,49 +236,53 @@ __global__ void __launch_bounds__(256, 2) conv_module_kernel(const ConvModParams
         const uint32_t y2 = pack_bf16x2(acc0, acc1);
         const uint32_t sg = pack_bf16x2(sigmoid_tanh(bf16lo(y2)), sigmoid_tanh(bf16hi(y2)));
         sp[c] = bf16x2_mul(y2, sg);
-        const float v0 = bf16lo(sp[c]), v1 = bf16hi(sp[c]);
-        s += v0 + v1;
-        q = fmaf(v0, v0, q);
-        q = fmaf(v1, v1, q);
       }
-      s_keep[o * 256 + tid] = make_uint4(sp[0], sp[1], sp[2], sp[3]);
-      s = warp_sum(s);
-      q = warp_sum(q);
-      if (lane == 0) {
-        s_sum[o][warp] = s;
-        s_sq[o][warp] = q;
-      }
+      s_keep[o * kConvThreads + tid] = make_uint2(sp[0], sp[1]);
     }
   }
   __syncthreads();
 
-  float cw[8];
+  // per-token statistics over the 2048 channels (ChanLayerNorm: biased variance, bf16 mean / var / rstd)
+  for (int o = warp; o < kConvTT; o += kConvThreads / 32) {
+    const uint4* row = reinterpret_cast<const uint4*>(s_keep + o * kConvThreads);
+    float s = 0.f, q = 0.f;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) cw[c] = __ldg(p.cln_w + c0 + c);
+    for (int i = 0; i < 8; ++i) {
+      const uint4 v = row[i * 32 + lane];
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float lo = bf16lo(w4[k]), hi = bf16hi(w4[k]);
+        s += lo + hi;
+        q = fmaf(lo, lo, q);
+        q = fmaf(hi, hi, q);
+      }
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0) {
+      const float mean = s * (1.0f / kConvC);
+      const float var = fmaxf(q * (1.0f / kConvC) - mean * mean, 0.f);
+      const float rs = rsqrtf(fmaxf(bf16_round(var), 1e-4f));
+      s_mean2[o] = pack_bf16x2(mean, mean);
+      s_rstd2[o] = pack_bf16x2(rs, rs);
+    }
+  }
+  __syncthreads();
+
+  float cw[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) cw[c] = __ldg(p.cln_w + c0 + c);
 #pragma unroll 4
   for (int o = 0; o < kConvTT; ++o) {
     const int t = t0 + o;
     if (t >= p.N) break;
-    float s = 0.f, q = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      s += s_sum[o][w];
-      q += s_sq[o][w];
-    }
-    const float mean = s * (1.0f / kConvC);
-    const float var = fmaxf(q * (1.0f / kConvC) - mean * mean, 0.f);
-    const uint32_t mean2 = pack_bf16x2(mean, mean);
-    const float rs = rsqrtf(fmaxf(bf16_round(var), 1e-4f));
-    const uint32_t rstd2 = pack_bf16x2(rs, rs);
-    const uint4 k = s_keep[o * 256 + tid];
-    const uint32_t kw[4] = {k.x, k.y, k.z, k.w};
-    uint32_t ow[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint32_t n2 = bf16x2_mul(bf16x2_sub(kw[c], mean2), rstd2);
-      ow[c] = pack_bf16x2(bf16lo(n2) * cw[2 * c], bf16hi(n2) * cw[2 * c + 1]);
-    }
-    *reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * p.N + t) * kConvC + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    const uint32_t mean2 = s_mean2[o], rstd2 = s_rstd2[o];
+    const uint2 k = s_keep[o * kConvThreads + tid];
+    const uint32_t n0 = bf16x2_mul(bf16x2_sub(k.x, mean2), rstd2);
+    const uint32_t n1 = bf16x2_mul(bf16x2_sub(k.y, mean2), rstd2);
+    *reinterpret_cast<uint2*>(p.out + (static_cast<long long>(b) * p.N + t) * kConvC + c0) =
+        make_uint2(pack_bf16x2(bf16lo(n0) * cw[0], bf16hi(n0) * cw[1]), pack_bf16x2(bf16lo(n1) * cw[2], bf16hi(n1) * cw[3]));
   }
 }
 
