@@ -166,6 +166,9 @@ def test_ln():
     z = torch.empty(rows, 1024, device=dev, dtype=torch.bfloat16)
     ms = timeit(lambda: L.lib().edm_layernorm(L.ptr(x), 0, rows, L.ptr(w1), L.ptr(b1), None, None, None, L.ptr(z), 1, 0, 1e-5, L.stream_ptr()))
     print(f"ln time rows={rows}: {ms * 1e3:.1f} us = {rows * 6144 / ms / 1e6:.0f} GB/s", flush=True)
+    y = torch.empty(rows, 1024, device=dev)
+    ms = timeit(lambda: L.lib().edm_layernorm(L.ptr(x), 0, rows, L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), L.ptr(y), L.ptr(z), 1, 0, 1e-5, L.stream_ptr()))
+    print(f"ln double (fp32 y + bf16 z) time rows={rows}: {ms * 1e3:.1f} us = {rows * 10240 / ms / 1e6:.0f} GB/s", flush=True)
 
 
 def conv_ref(h, dw_w, dw_b, cln_w, B, N):
