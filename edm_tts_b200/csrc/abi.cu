@@ -211,7 +211,8 @@ int launch_attention(const CUtensorMap& mqkv, int B, int N, int H, void* out, ui
   p.ldo = static_cast<long long>(H) * 64;
   p.scale_log2e = 0.125f * 1.4426950408889634f;
   p.v_lbo = lbo; p.v_sbo = sbo; p.v_kstep = kstep;
-  dim3 grid((N + 255) / 256, H, B);
+  const int items = ((N + 255) / 256) * H * B;
+  dim3 grid(items < num_sms() ? items : num_sms());
   ProfScope prof(PK_ATTN, 4.0 * B * H * static_cast<double>(N) * N * 64, st);
   attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, st>>>(mqkv, p);
   EDM_LAUNCH_CHECK("attention_fwd");

@@ -1,7 +1,9 @@
 // Non-causal multi-head attention for the conformer block (reference: edm_tts/models/conformer/attend.py:63-115 via
 // conformer.py:128-146): softmax(q k^T / sqrt(64)) v, H heads of 64, no mask, one sequence = one batch element.
 //
-// One CTA = 256 query rows (two 128-row tiles, "ping" and "pong") of one (batch, head). Both contractions run on
+// Persistent CTAs (one per SM) loop over work items; one item = 256 query rows (two 128-row tiles, "ping" and "pong")
+// of one (batch, head). The TMA producer runs one item ahead (Q is double-buffered, the K/V ring is continuous across
+// items), so the next item's first scores are issued while the current item's last tile is in its exp2 phase. Both contractions run on
 // tcgen05 with fp32 accumulators in TMEM (all 512 columns: S0 | S1 | O0 | O1):
 //   S_w = Q_w K^T : A = Q_w [128 x 64] K-major smem,  B = K tile [128 x 64] K-major smem        -> 128 TMEM columns
 //   O_w += P_w V  : A = P_w [128 x 128] K-major smem (bf16, written by the softmax warps),
@@ -15,7 +17,7 @@
 //                       S_w(j) into registers (s_free), i.e. before P_w(j) V(j), so the next scores are ready when the
 //                       exp2 phase of the current tile ends.
 //   warps 10..11      : idle; they exist so the producer/MMA warpgroup can hand its registers to the softmax warpgroups
-//                       (setmaxnreg 40 / 224): a 128-wide fp32 score row per thread does not fit in 168 registers.
+//                       (setmaxnreg 88 / 208): a 128-wide fp32 score row per thread does not fit in 168 registers.
 #pragma once
 #include "ptx.cuh"
 
@@ -34,7 +36,7 @@ struct AttnParams {
 constexpr int kAttnThreads = 384;
 constexpr int kAttnKvStages = 3;
 constexpr uint32_t kAttnTile = 128 * 64 * 2;  // 16 KB: one [128 x 64] bf16 tile
-constexpr uint32_t kAttnSmemBytes = 2 * kAttnTile /*Q0,Q1*/ + 2 * kAttnKvStages * kAttnTile /*K,V ring*/ + 4 * kAttnTile /*P0,P1*/ + 256;
+constexpr uint32_t kAttnSmemBytes = 4 * kAttnTile /*Q0,Q1 x 2 slots*/ + 2 * kAttnKvStages * kAttnTile /*K,V ring*/ + 4 * kAttnTile /*P0,P1*/ + 256;
 constexpr float kAttnRescaleThreshold = 8.0f;  // log2 units
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -58,24 +60,29 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;                                   // 2 tiles
-  uint8_t* sK = sQ + 2 * kAttnTile;                     // kAttnKvStages tiles
+  uint8_t* sQ = smem;                                   // 2 slots x 2 tiles
+  uint8_t* sK = sQ + 4 * kAttnTile;                     // kAttnKvStages tiles
   uint8_t* sV = sK + kAttnKvStages * kAttnTile;         // kAttnKvStages tiles
   uint8_t* sP = sV + kAttnKvStages * kAttnTile;         // 2 x (2 half tiles)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kAttnTile);
-  uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;                   // [3]
-  uint64_t* kv_empty = bars + 1 + kAttnKvStages;  // [3]
-  uint64_t* s_full = bars + 1 + 2 * kAttnKvStages;  // [2]
-  uint64_t* p_full = s_full + 2;                    // [2]
-  uint64_t* o_full = p_full + 2;                    // [2]
-  uint64_t* s_free = o_full + 2;                    // [2]
+  uint64_t* q_full = bars + 0;                          // [2]
+  uint64_t* q_empty = bars + 2;                         // [2]
+  uint64_t* kv_full = bars + 4;                         // [3]
+  uint64_t* kv_empty = kv_full + kAttnKvStages;         // [3]
+  uint64_t* s_full = kv_empty + kAttnKvStages;          // [2]
+  uint64_t* p_full = s_full + 2;                        // [2]
+  uint64_t* o_full = p_full + 2;                        // [2]
+  uint64_t* s_free = o_full + 2;                        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int qt2 = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int n_kv = (p.N + 127) / 128;
+  const int n_q2 = (p.N + 255) / 256;
+  const int total_items = n_q2 * p.H * p.B;
+  // persistent: this CTA handles work items blockIdx.x, blockIdx.x + gridDim.x, ... ; item -> (query-tile pair, head, batch)
+  const int my_items = (total_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int total_g = my_items * n_kv;  // kv iterations of this CTA, numbered g = item_index * n_kv + j
 
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
@@ -83,7 +90,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
       __trap();
     }
     tma_prefetch_desc(&tma_qkv);
-    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+    }
     for (int s = 0; s < kAttnKvStages; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
@@ -101,197 +111,217 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
   if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  if (warp == 8) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * kAttnTile);
-      tma_load_3d(&tma_qkv, q_full, sQ, p.q_col0 + h * 64, qt2 * 256, b);
-      tma_load_3d(&tma_qkv, q_full, sQ + kAttnTile, p.q_col0 + h * 64, qt2 * 256 + 128, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j % kAttnKvStages;
-        mbar_wait(&kv_empty[s], ((j / kAttnKvStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * kAttnTile);
-        tma_load_3d(&tma_qkv, &kv_full[s], sK + s * kAttnTile, p.k_col0 + h * 64, j * 128, b);
-        tma_load_3d(&tma_qkv, &kv_full[s], sV + s * kAttnTile, p.v_col0 + h * 64, j * 128, b);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if (warp == 8) {
+      if (lane == 0) {
+        for (int i = 0; i < my_items; ++i) {
+          const int it = blockIdx.x + i * gridDim.x;
+          const int qt2 = it % n_q2, h = (it / n_q2) % p.H, b = it / (n_q2 * p.H);
+          const int qs = i & 1;
+          mbar_wait(&q_empty[qs], ((i >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[qs], 2 * kAttnTile);
+          tma_load_3d(&tma_qkv, &q_full[qs], sQ + qs * 2 * kAttnTile, p.q_col0 + h * 64, qt2 * 256, b);
+          tma_load_3d(&tma_qkv, &q_full[qs], sQ + qs * 2 * kAttnTile + kAttnTile, p.q_col0 + h * 64, qt2 * 256 + 128, b);
+          for (int j = 0; j < n_kv; ++j) {
+            const int g = i * n_kv + j;
+            const int s = g % kAttnKvStages;
+            mbar_wait(&kv_empty[s], ((g / kAttnKvStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(&kv_full[s], 2 * kAttnTile);
+            tma_load_3d(&tma_qkv, &kv_full[s], sK + s * kAttnTile, p.k_col0 + h * 64, j * 128, b);
+            tma_load_3d(&tma_qkv, &kv_full[s], sV + s * kAttnTile, p.v_col0 + h * 64, j * 128, b);
+          }
+        }
+      }
+    } else if (warp == 9) {
+      if (lane == 0 && total_g > 0) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
+        // scores of kv iteration g for tile w (both tiles are issued back to back by the callers)
+        auto issue_s = [&](int w, int g) {
+          const int i = g / n_kv;
+          const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + (i & 1) * 2 * kAttnTile + w * kAttnTile), 16, 1024);
+          const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + (g % kAttnKvStages) * kAttnTile), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + w * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[w]);
+        };
+        auto issue_pv = [&](int w, int g) {
+          const uint32_t p_addr = smem_u32(sP + w * 2 * kAttnTile);
+          const uint64_t pdesc0 = umma_desc_sw128(p_addr, 16, 1024);
+          const uint64_t pdesc1 = umma_desc_sw128(p_addr + kAttnTile, 16, 1024);
+          const uint32_t v_addr = smem_u32(sV + (g % kAttnKvStages) * kAttnTile);
+          const bool first = (g % n_kv) == 0;  // first kv tile of an item overwrites O
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t adesc = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
+            const uint64_t bdesc = umma_desc_sw128(v_addr + k * p.v_kstep, p.v_lbo, p.v_sbo);
+            umma_ss(tmem_base + 256 + w * 64, adesc, bdesc, idesc_o, (!first || k != 0) ? 1u : 0u);
+          }
+          umma_commit(&o_full[w]);
+        };
+        mbar_wait(&q_full[0], 0);
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        issue_s(0, 0);
+        issue_s(1, 0);
+        if (n_kv == 1) umma_commit(&q_empty[0]);
+        for (int g = 0; g < total_g; ++g) {
+          if (g + 1 < total_g) {
+            // next scores as soon as each warpgroup has drained S_w(g) into registers
+            const int g1 = g + 1;
+            const int i1 = g1 / n_kv, j1 = g1 % n_kv;
+            if (j1 == 0) mbar_wait(&q_full[i1 & 1], (i1 >> 1) & 1);
+            mbar_wait(&kv_full[g1 % kAttnKvStages], (g1 / kAttnKvStages) & 1);
+            mbar_wait(&s_free[0], g & 1);
+            tc_fence_after();
+            issue_s(0, g1);
+            mbar_wait(&s_free[1], g & 1);
+            tc_fence_after();
+            issue_s(1, g1);
+            if (j1 == n_kv - 1) umma_commit(&q_empty[i1 & 1]);  // Q slot reusable once the item's last scores are done
+          }
+          // P_w(g) is in smem (and O_w rescaled if needed)
+          mbar_wait(&p_full[0], g & 1);
+          tc_fence_after();
+          issue_pv(0, g);
+          mbar_wait(&p_full[1], g & 1);
+          tc_fence_after();
+          issue_pv(1, g);
+          umma_commit(&kv_empty[g % kAttnKvStages]);  // K / V stage free once everything issued so far has completed
+        }
       }
     }
-  } else if (warp == 9) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
-      const uint64_t qdesc[2] = {umma_desc_sw128(smem_u32(sQ), 16, 1024), umma_desc_sw128(smem_u32(sQ + kAttnTile), 16, 1024)};
-      auto issue_s = [&](int w, int stage) {
-        const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + stage * kAttnTile), 16, 1024);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + w * 128, qdesc[w] + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[w]);
-      };
-      auto issue_pv = [&](int w, int stage, int j) {
-        const uint32_t p_addr = smem_u32(sP + w * 2 * kAttnTile);
-        const uint64_t pdesc0 = umma_desc_sw128(p_addr, 16, 1024);
-        const uint64_t pdesc1 = umma_desc_sw128(p_addr + kAttnTile, 16, 1024);
-        const uint32_t v_addr = smem_u32(sV + stage * kAttnTile);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t adesc = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
-          const uint64_t bdesc = umma_desc_sw128(v_addr + k * p.v_kstep, p.v_lbo, p.v_sbo);
-          umma_ss(tmem_base + 256 + w * 64, adesc, bdesc, idesc_o, (j > 0 || k != 0) ? 1u : 0u);
-        }
-        umma_commit(&o_full[w]);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j % kAttnKvStages;
-        const int s1 = (j + 1) % kAttnKvStages;
-        if (j + 1 < n_kv) {
-          // next scores as soon as each warpgroup has drained S_w(j) into registers
-          mbar_wait(&kv_full[s1], ((j + 1) / kAttnKvStages) & 1);
-          mbar_wait(&s_free[0], j & 1);
-          tc_fence_after();
-          issue_s(0, s1);
-          mbar_wait(&s_free[1], j & 1);
-          tc_fence_after();
-          issue_s(1, s1);
-        }
-        // P_w(j) is in smem (and O_w rescaled if needed)
-        mbar_wait(&p_full[0], j & 1);
-        tc_fence_after();
-        issue_pv(0, s, j);
-        mbar_wait(&p_full[1], j & 1);
-        tc_fence_after();
-        issue_pv(1, s, j);
-        umma_commit(&kv_empty[s]);  // K_j / V_j no longer needed once everything issued so far has completed
-      }
-    }
-  }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     // ---- softmax warpgroups: w = 0 (warps 0..3) / 1 (warps 4..7); thread <-> query row
     const int w = warp >> 2;
     const int row_in_tile = (warp & 3) * 32 + lane;
-    const int q_row = qt2 * 256 + w * 128 + row_in_tile;
     const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t tmem_S = tmem_base + w * 128 + lane_off;
     const uint32_t tmem_O = tmem_base + 256 + w * 64 + lane_off;
     const float sl2 = p.scale_log2e;
     uint8_t* p_row = sP + w * 2 * kAttnTile + row_in_tile * 128;
     const int sw = row_in_tile & 7;
-    float m_ref = -INFINITY;  // reference max in scaled log2 units
-    float l_run = 0.f;
 
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[w], j & 1);
-      tc_fence_after();
-      uint32_t s0[32], s1[32], s2[32], s3[32];
-      tmem_ld_32x32(tmem_S, s0);
-      tmem_ld_32x32(tmem_S + 32, s1);
-      tmem_ld_32x32(tmem_S + 64, s2);
-      tmem_ld_32x32(tmem_S + 96, s3);
-      tmem_ld_wait_dep(s0);
-      tmem_ld_wait_dep(s1);
-      tmem_ld_wait_dep(s2);
-      tmem_ld_wait_dep(s3);
-      tc_fence_before();
-      mbar_arrive(&s_free[w]);  // S_w may be overwritten by the next Q K^T
-      const int kv_valid = p.N - j * 128;
-      if (kv_valid < 128) {  // only the last tile of a ragged sequence: padded key columns -> -inf
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i >= kv_valid) s0[i] = 0xff800000u;
-          if (32 + i >= kv_valid) s1[i] = 0xff800000u;
-          if (64 + i >= kv_valid) s2[i] = 0xff800000u;
-          if (96 + i >= kv_valid) s3[i] = 0xff800000u;
-        }
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        mx0 = fmaxf(mx0, __uint_as_float(s0[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(s1[i]));
-        mx2 = fmaxf(mx2, __uint_as_float(s2[i]));
-        mx3 = fmaxf(mx3, __uint_as_float(s3[i]));
-      }
-      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
-      // lazy rescale: keep the old reference unless the max moved by more than 2^8 (p stays <= 256, exact enough in fp32/bf16)
-      const bool need = m_new - m_ref > kAttnRescaleThreshold;  // true at j == 0 (m_ref = -inf)
-      float alpha = 1.0f;
-      if (need) {
-        alpha = ex2_approx(m_ref - m_new);  // 0 at j == 0
-        m_ref = m_new;
-      }
-      if (j > 0) {
-        // P_w V(j-1) must have completed before P_w is overwritten or O_w rescaled (it normally has, long ago)
-        mbar_wait(&o_full[w], (j - 1) & 1);
+    for (int i = 0; i < my_items; ++i) {
+      const int it = blockIdx.x + i * gridDim.x;
+      const int qt2 = it % n_q2, h = (it / n_q2) % p.H, b = it / (n_q2 * p.H);
+      const int q_row = qt2 * 256 + w * 128 + row_in_tile;
+      float m_ref = -INFINITY;  // reference max in scaled log2 units
+      float l_run = 0.f;
+
+      for (int j = 0; j < n_kv; ++j) {
+        const int g = i * n_kv + j;
+        mbar_wait(&s_full[w], g & 1);
         tc_fence_after();
+        uint32_t s0[32], s1[32], s2[32], s3[32];
+        tmem_ld_32x32(tmem_S, s0);
+        tmem_ld_32x32(tmem_S + 32, s1);
+        tmem_ld_32x32(tmem_S + 64, s2);
+        tmem_ld_32x32(tmem_S + 96, s3);
+        tmem_ld_wait_dep(s0);
+        tmem_ld_wait_dep(s1);
+        tmem_ld_wait_dep(s2);
+        tmem_ld_wait_dep(s3);
+        tc_fence_before();
+        mbar_arrive(&s_free[w]);  // S_w may be overwritten by the next Q K^T
+        const int kv_valid = p.N - j * 128;
+        if (kv_valid < 128) {  // only the last tile of a ragged sequence: padded key columns -> -inf
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (c >= kv_valid) s0[c] = 0xff800000u;
+            if (32 + c >= kv_valid) s1[c] = 0xff800000u;
+            if (64 + c >= kv_valid) s2[c] = 0xff800000u;
+            if (96 + c >= kv_valid) s3[c] = 0xff800000u;
+          }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          mx0 = fmaxf(mx0, __uint_as_float(s0[c]));
+          mx1 = fmaxf(mx1, __uint_as_float(s1[c]));
+          mx2 = fmaxf(mx2, __uint_as_float(s2[c]));
+          mx3 = fmaxf(mx3, __uint_as_float(s3[c]));
+        }
+        const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+        // lazy rescale: keep the old reference unless the max moved by more than 2^8 (p stays <= 256, exact enough in fp32/bf16)
+        const bool need = m_new - m_ref > kAttnRescaleThreshold;  // true at j == 0 (m_ref = -inf)
+        float alpha = 1.0f;
+        if (need) {
+          alpha = ex2_approx(m_ref - m_new);  // 0 at j == 0
+          m_ref = m_new;
+        }
+        if (j > 0) {
+          // P_w V(g-1) must have completed before P_w is overwritten or O_w rescaled (it normally has, long ago)
+          mbar_wait(&o_full[w], (g - 1) & 1);
+          tc_fence_after();
+        }
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          // O_w *= alpha in TMEM; PV(g) is not issued before our p_full arrive
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(tmem_O + c * 32, o);
+            tmem_ld_wait_dep(o);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st_32x32(tmem_O + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+        l_run *= alpha;
+        float ls0 = 0.f, ls1 = 0.f;
+        auto emit = [&](uint32_t (&s)[32], int c) {
+          uint32_t wv[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * e]), sl2, -m_ref));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * e + 1]), sl2, -m_ref));
+            ls0 += p0;
+            ls1 += p1;
+            wv[e] = pack_bf16x2(p0, p1);
+          }
+          // 32 kv columns = 64 B = four 16 B chunks of this row; 128B swizzle: chunk index ^= (row & 7)
+          uint8_t* half = p_row + (c >> 1) * kAttnTile;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = ((c & 1) * 4 + q) ^ sw;
+            *reinterpret_cast<uint4*>(half + chunk * 16) = make_uint4(wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
+          }
+        };
+        emit(s0, 0);
+        emit(s1, 1);
+        emit(s2, 2);
+        emit(s3, 3);
+        l_run += ls0 + ls1;
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(&p_full[w]);
       }
-      if (j > 0 && __any_sync(0xffffffffu, need)) {
-        // O_w *= alpha in TMEM; PV(j) is not issued before our p_full arrive
+      // item epilogue: O_w / l
+      mbar_wait(&o_full[w], (i * n_kv + n_kv - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / l_run;
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(tmem_O, o0);
+      tmem_ld_32x32(tmem_O + 32, o1);
+      tmem_ld_wait_dep(o0);
+      tmem_ld_wait_dep(o1);
+      if (q_row < p.N) {
+        uint4* o = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * p.N + q_row) * p.ldo + h * 64);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t o[32];
-          tmem_ld_32x32(tmem_O + c * 32, o);
-          tmem_ld_wait_dep(o);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32(tmem_O + c * 32, o);
+        for (int e = 0; e < 4; ++e) {
+          o[e] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * e + 0]) * inv_l, __uint_as_float(o0[8 * e + 1]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o0[8 * e + 2]) * inv_l, __uint_as_float(o0[8 * e + 3]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o0[8 * e + 4]) * inv_l, __uint_as_float(o0[8 * e + 5]) * inv_l),
+                            pack_bf16x2(__uint_as_float(o0[8 * e + 6]) * inv_l, __uint_as_float(o0[8 * e + 7]) * inv_l));
+          o[4 + e] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * e + 0]) * inv_l, __uint_as_float(o1[8 * e + 1]) * inv_l),
+                                pack_bf16x2(__uint_as_float(o1[8 * e + 2]) * inv_l, __uint_as_float(o1[8 * e + 3]) * inv_l),
+                                pack_bf16x2(__uint_as_float(o1[8 * e + 4]) * inv_l, __uint_as_float(o1[8 * e + 5]) * inv_l),
+                                pack_bf16x2(__uint_as_float(o1[8 * e + 6]) * inv_l, __uint_as_float(o1[8 * e + 7]) * inv_l));
         }
-        tmem_st_wait();
-      }
-      l_run *= alpha;
-      float ls0 = 0.f, ls1 = 0.f;
-      auto emit = [&](uint32_t (&s)[32], int c) {
-        uint32_t wv[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), sl2, -m_ref));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -m_ref));
-          ls0 += p0;
-          ls1 += p1;
-          wv[i] = pack_bf16x2(p0, p1);
-        }
-        // 32 kv columns = 64 B = four 16 B chunks of this row; 128B swizzle: chunk index ^= (row & 7)
-        uint8_t* half = p_row + (c >> 1) * kAttnTile;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = ((c & 1) * 4 + q) ^ sw;
-          *reinterpret_cast<uint4*>(half + chunk * 16) = make_uint4(wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
-        }
-      };
-      emit(s0, 0);
-      emit(s1, 1);
-      emit(s2, 2);
-      emit(s3, 3);
-      l_run += ls0 + ls1;
-      tc_fence_before();
-      fence_proxy_async_smem();
-      mbar_arrive(&p_full[w]);
-    }
-    // epilogue: O_w / l
-    mbar_wait(&o_full[w], (n_kv - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l_run;
-    uint32_t o0[32], o1[32];
-    tmem_ld_32x32(tmem_O, o0);
-    tmem_ld_32x32(tmem_O + 32, o1);
-    tmem_ld_wait_dep(o0);
-    tmem_ld_wait_dep(o1);
-    if (q_row < p.N) {
-      uint4* o = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * p.N + q_row) * p.ldo + h * 64);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        o[i] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * i + 0]) * inv_l, __uint_as_float(o0[8 * i + 1]) * inv_l),
-                          pack_bf16x2(__uint_as_float(o0[8 * i + 2]) * inv_l, __uint_as_float(o0[8 * i + 3]) * inv_l),
-                          pack_bf16x2(__uint_as_float(o0[8 * i + 4]) * inv_l, __uint_as_float(o0[8 * i + 5]) * inv_l),
-                          pack_bf16x2(__uint_as_float(o0[8 * i + 6]) * inv_l, __uint_as_float(o0[8 * i + 7]) * inv_l));
-        o[4 + i] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * i + 0]) * inv_l, __uint_as_float(o1[8 * i + 1]) * inv_l),
-                              pack_bf16x2(__uint_as_float(o1[8 * i + 2]) * inv_l, __uint_as_float(o1[8 * i + 3]) * inv_l),
-                              pack_bf16x2(__uint_as_float(o1[8 * i + 4]) * inv_l, __uint_as_float(o1[8 * i + 5]) * inv_l),
-                              pack_bf16x2(__uint_as_float(o1[8 * i + 6]) * inv_l, __uint_as_float(o1[8 * i + 7]) * inv_l));
       }
     }
   }
