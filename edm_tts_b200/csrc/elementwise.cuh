@@ -147,7 +147,7 @@ struct ConvModParams {
   const float* cln_w;   // [2048]
   int B, N;
 };
-constexpr int kConvTT = 20;        // output tokens per CTA (4 halo rows are re-read: 20 % more loads, served by L2)
+constexpr int kConvTT = 20;        // output tokens per CTA (4 halo rows are re-read: 20 % more loads, served by L2); 25 measured slower (wave quantisation)
 constexpr int kConvThreads = 512;  // 4 channels per thread
 constexpr uint32_t kConvSmemBytes = kConvTT * kConvThreads * 8;  // Swish outputs of the tile (bf16 x 4 per thread and token)
 
