@@ -217,7 +217,10 @@ def main():
         step_resident()
     sampler = ClockSampler(local)
     sampler.start()
-    ms_total, launches = timed(step_resident, args.steps, profile=True)
+    ms_total, launches = timed(step_resident, args.steps)          # the headline: no per-kernel instrumentation inside
+    # same K steps again with every GEMM / attention / LayerNorm / conv launch bracketed by CUDA events (roofline numbers);
+    # the event records add a few % of gaps between kernels, so this pass is reported separately as instrumented_ms_per_step
+    ms_prof, _ = timed(step_resident, args.steps, profile=True)
     sampler.stop_flag = True
     sampler.join()
     pm, pw, pc = (C.c_double * 5)(), (C.c_double * 5)(), (C.c_int * 5)()
@@ -273,7 +276,7 @@ def main():
         "gpu_launches": int(launches) * world,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_pair_kernel (tcgen05 cta_group::2; all conformer / head GEMMs of the timed region)",
                      "achieved": gemm_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tf_peak, "traffic": None,
-                     "peak_kind": f"{peak_kind} bf16 sustained", "gemm_share_of_step": pm[0] / ms_total},
+                     "peak_kind": f"{peak_kind} bf16 sustained", "gemm_share_of_step": pm[0] / ms_prof, "instrumented_ms_per_step": ms_prof / args.steps},
         "kernels": kernels,
         "secondary": {"metric": "dac_rvq_encode_frames_per_s", "value": 32 * 3000 / (rvq_ms * 1e-3), "unit": "frames/s", "ms": rvq_ms,
                       "workload": "DAC RVQ encode, z [32, 1024, 3000] fp32 (dump_tokens batch, BASELINE config 4), 12 codebooks, per GPU",

@@ -22,10 +22,11 @@ def _check_reports(reports):
     for r in reports:
         assert r["max"] < MAX_TOL and r["mean"] < MEAN_TOL, r
         assert r["n_not_near_tie"] == 0, r
-        assert r["agree"] > 0.9, r
+        assert r["agree"] > 0.9 or r["n"] < 30, r
 
 
-@pytest.mark.parametrize("B,T,P,steps", [(2, 150, 0, 8), (1, 60, 0, 1), (1, 100, 50, 4), (3, 77, 33, 2)])
+@pytest.mark.parametrize("B,T,P,steps", [(2, 150, 0, 8), (1, 60, 0, 1), (1, 100, 50, 4), (3, 77, 33, 2),
+                                         (1, 1, 0, 1), (2, 3, 2, 2), (1, 600, 0, 3), (1, 1500, 150, 2)])
 def test_teacher_forced_parity_vs_oracle(B, T, P, steps):
     from tests.parity_utils import full_model, teacher_forced_parity
 
@@ -38,7 +39,7 @@ def test_teacher_forced_parity_vs_oracle(B, T, P, steps):
     # the model's own sampled ids under the same injected noise agree except at near-ties
     for s in range(len(ref["step_ids"])):
         agree = (ours["step_ids"][s] == ref["step_ids"][s]).float().mean().item()
-        assert agree > 0.9, (s, agree)
+        assert agree > 0.9 or ref["step_ids"][s].numel() < 30, (s, agree)
 
 
 @pytest.mark.parametrize("name", ["full_s1", "full_s8", "full_s4_prompt"])
