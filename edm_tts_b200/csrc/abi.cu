@@ -14,6 +14,7 @@
 #include "elementwise.cuh"
 #include "gemm.cuh"
 #include "rvq.cuh"
+#include "rvq_tc.cuh"
 
 using namespace edm;
 
@@ -147,6 +148,22 @@ int make_tmap_3d(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t N, uint64
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(EDM_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+  return 0;
+}
+
+// fp32 row-major [rows, cols] with row pitch ld (elements); box = 32 columns (128 B, swizzle-128B) x box_rows
+int make_tmap_f32_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (enc == nullptr) return fail(EDM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 4) % 16 != 0) return fail(EDM_ERR_INVALID, "TMA operand must be 16-byte aligned (ptr %p, ld %llu)", ptr, (unsigned long long)ld);
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EDM_ERR_CUDA, "cuTensorMapEncodeTiled(f32 rows=%llu cols=%llu ld=%llu) failed: %d", (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, (int)r);
   return 0;
 }
 
@@ -383,6 +400,47 @@ extern "C" int edm_rvq_encode(const void* z, int z_is_bf16, int B, int T, int n_
   dim3 grid((T + kRvqFrames - 1) / kRvqFrames, B);
   rvq_encode_kernel<<<grid, 256, kRvqSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
   EDM_LAUNCH_CHECK("rvq_encode");
+  return 0;
+}
+
+// bring-up knob (tools/bringup_ops.py rvqtc): descriptor strides of the MN-major tf32 A operand
+unsigned g_rvq_a_lbo = kRpZBytes / 4, g_rvq_a_sbo = 512;
+int g_rvq_skip_project = 0;  // 1: e_ws is taken as given (tests the search kernel alone)
+extern "C" void edm_rvq_tc_debug(unsigned lbo, unsigned sbo, int skip_project) {
+  g_rvq_a_lbo = lbo;
+  g_rvq_a_sbo = sbo;
+  g_rvq_skip_project = skip_project;
+}
+
+extern "C" int edm_rvq_encode_tc(const float* z, int B, int T, int n_levels, const float* w_hi, const float* w_lo, const float* b_in,
+                                 const float* cb_packed, const float* g, float* e_ws, long long* codes, const long long* forced,
+                                 float* latents, void* stream) {
+  if (int rc = check_arch()) return rc;
+  if (n_levels < 1 || n_levels > kRvqLevels || B <= 0 || T <= 0) return fail(EDM_ERR_INVALID, "rvq shape B=%d T=%d levels=%d", B, T, n_levels);
+  if (T % 4 != 0) return fail(EDM_ERR_INVALID, "rvq_encode_tc needs T %% 4 == 0 (16-byte rows for TMA), got T=%d: pad the time axis", T);
+  static bool attr_set = false;
+  if (!attr_set) {
+    EDM_CUDA(cudaFuncSetAttribute(rvq_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmemBytes));
+    EDM_CUDA(cudaFuncSetAttribute(rvq_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemBytes));
+    attr_set = true;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap mz, mwh, mwl, mcb;
+  if (int rc = make_tmap_f32_2d(&mz, z, static_cast<uint64_t>(B) * kRtLatent, T, T, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (int rc = make_tmap_f32_2d(&mwh, w_hi, kRtE, kRtLatent, kRtLatent, kRtE)) return rc;
+  if (int rc = make_tmap_f32_2d(&mwl, w_lo, kRtE, kRtLatent, kRtLatent, kRtE)) return rc;
+  if (int rc = make_tmap_f32_2d(&mcb, cb_packed, 12 * 1024, 32, 32, kRsChunk)) return rc;
+  const int tiles = ((T + kRtFrames - 1) / kRtFrames) * B;
+  RvqProjParams pp;
+  pp.B = B; pp.T = T; pp.b_in = b_in; pp.e_out = e_ws; pp.a_lbo = g_rvq_a_lbo; pp.a_sbo = g_rvq_a_sbo;
+  if (!g_rvq_skip_project) {
+    rvq_project_kernel<<<tiles < num_sms() ? tiles : num_sms(), kRpThreads, kRpSmemBytes, st>>>(mz, mwh, mwl, pp);
+    EDM_LAUNCH_CHECK("rvq_project");
+  }
+  RvqSearchParams sp;
+  sp.B = B; sp.T = T; sp.n_levels = n_levels; sp.e = e_ws; sp.g = g; sp.codes = codes; sp.forced = forced; sp.latents = latents;
+  rvq_search_kernel<<<tiles < 2 * num_sms() ? tiles : 2 * num_sms(), kRsThreads, kRsSmemBytes, st>>>(mcb, sp);
+  EDM_LAUNCH_CHECK("rvq_search");
   return 0;
 }
 

@@ -151,6 +151,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= 2ull << 61;  // SWIZZLE_128B
   return d;
 }
+// MN-major tf32 operands only exist in the "128B swizzle, 32-byte atom" layout (descriptor layout type 1; TMA swizzle
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 32 contiguous MN elements (128 B) per K index, 32 B chunks XOR-swizzled with
+// (K row & 3), 4 K-rows per 512 B atom. LBO = stride between 32-element MN atoms, SBO = stride between 4-row K groups.
+__device__ __forceinline__ uint64_t umma_desc_sw128_base32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  d |= 1ull << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
 // Instruction descriptor: bf16 x bf16 -> fp32 accumulate.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
   return (1u << 4)                                  // D = f32
@@ -174,6 +186,36 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
 // mbarrier arrives once all previously issued MMAs of this thread have completed (implies fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------- UMMA kind::tf32 (fp32 operands in smem, low 13 mantissa bits ignored)
+// Instruction descriptor: tf32 x tf32 -> fp32 accumulate. K = 8 per instruction.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4)                                  // D = f32
+         | (2u << 7) | (2u << 10)                   // A, B = tf32
+         | (static_cast<uint32_t>(a_mn_major) << 15)  //
+         | (static_cast<uint32_t>(b_mn_major) << 16)  //
+         | (static_cast<uint32_t>(n >> 3) << 17)      //
+         | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_ss_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// fp32 -> tf32 (round to nearest, ties away): the result is an fp32 bit pattern with the low 13 mantissa bits clear
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // ---------------------------------------------------------------- CTA pairs (cta_group::2): two SMs share one MMA tile

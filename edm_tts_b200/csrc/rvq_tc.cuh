@@ -1,0 +1,432 @@
+// DAC ResidualVectorQuantize nearest-code search on the 5th-generation tensor cores (tcgen05, kind::tf32, TMEM accumulators).
+// Reference: edm_tts/models/dac/vector_quantizer.py:146-210 (residual loop), :33-67 + :75-91 (per-level search).
+//
+// Same algebra as rvq.cuh (z is read once, the level loop runs on 8-d latents with the G cross tables), split in two kernels:
+//
+//   rvq_project_kernel : E[frame, 96] = z[b, :, t] . W_in^T + b_in for all 12 levels at once. z [B, 1024, T] is consumed as an
+//                        MN-major (frames contiguous) tf32 A operand straight from TMA boxes (128B swizzle with 32 B atoms), so the
+//                        channel-major layout of the reference needs no transpose. fp32-level accuracy comes from the 3xTF32
+//                        split: four "split" warps rewrite every staged z tile as hi = tf32(z) and lo = tf32(z - hi) in place
+//                        (elementwise, so they never need to know the swizzle), the weights are pre-split at pack time, and the
+//                        MMA thread accumulates hi*hi + lo*hi + hi*lo into one TMEM accumulator.
+//   rvq_search_kernel  : 128 frames per CTA, thread <-> frame. Per level: subtract the G rows of the codes chosen so far,
+//                        L2-normalise, write the 3xTF32-split latent row as a K-major A operand (128B swizzle) to shared memory;
+//                        the MMA thread multiplies it with the packed codebook [c_hi | c_hi | c_lo | -|c|^2/2] streamed in
+//                        128-code chunks by TMA (K = 32 per code), scores land in TMEM (2 x 128 columns, double-buffered) and
+//                        each thread scans its own row with tcgen05.ld for the first maximum. Two CTAs per SM overlap one
+//                        tile's level-boundary latency with the other's scan.
+//
+//   score(code) = e^ . c^ - |c^|^2 / 2  = -(dist - |e^|^2) / 2   with dist = |e^|^2 - 2 e^ . c^ + |c^|^2 (the reference formula),
+//   so arg-max score (first maximum) = the reference's argmax(-dist).
+#pragma once
+#include "ptx.cuh"
+
+namespace edm {
+
+constexpr int kRtFrames = 128;  // frames per tile = UMMA M
+constexpr int kRtE = 96;        // 12 levels x 8 dims
+constexpr int kRtLatent = 1024;
+
+// ------------------------------------------------------------------------------------------------ projection
+constexpr int kRpKc = 32;                                            // latent channels per pipeline stage
+constexpr int kRpStages = 3;
+constexpr uint32_t kRpZBytes = kRtFrames * kRpKc * 4;                // 16 KB: 4 TMA boxes of (32 frames x 32 channels)
+constexpr uint32_t kRpWBytes = kRtE * kRpKc * 4;                     // 12 KB: 96 outputs x 32 channels (K-major)
+constexpr uint32_t kRpStageBytes = 2 * kRpZBytes + 2 * kRpWBytes;    // z_hi | z_lo | w_hi | w_lo = 56 KB
+constexpr uint32_t kRpSmemBytes = kRpStages * kRpStageBytes + 1024 + 256;
+constexpr int kRpThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 split, warps 6-9 epilogue
+
+struct RvqProjParams {
+  int B, T;
+  const float* b_in;  // [96]
+  float* e_out;       // [B*T, 96] projected latents (before any residual correction)
+  uint32_t a_lbo, a_sbo;  // MN-major A descriptor strides (bytes): 32-frame atoms kRpZBytes/4 apart, 4-channel K-groups 512 apart
+};
+
+__global__ void __launch_bounds__(kRpThreads, 1)
+rvq_project_kernel(const __grid_constant__ CUtensorMap tma_z, const __grid_constant__ CUtensorMap tma_whi,
+                   const __grid_constant__ CUtensorMap tma_wlo, const RvqProjParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kRpStages * kRpStageBytes);
+  uint64_t* split_bar = full_bar + kRpStages;
+  uint64_t* empty_bar = split_bar + kRpStages;
+  uint64_t* tfull_bar = empty_bar + kRpStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_b = (p.T + kRtFrames - 1) / kRtFrames;
+  const int num_tiles = tiles_per_b * p.B;
+  constexpr int kNumKc = kRtLatent / kRpKc;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_z);
+    tma_prefetch_desc(&tma_whi);
+    tma_prefetch_desc(&tma_wlo);
+    for (int s = 0; s < kRpStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&split_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRtFrames;
+        for (int kc = 0; kc < kNumKc; ++kc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * kRpStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], kRpZBytes + 2 * kRpWBytes);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)  // frames beyond T are zero-filled by TMA
+            tma_load_2d(&tma_z, &full_bar[stage], st + i * (kRpZBytes / 4), t0 + 32 * i, b * kRtLatent + kc * kRpKc);
+          tma_load_2d(&tma_whi, &full_bar[stage], st + 2 * kRpZBytes, kc * kRpKc, 0);
+          tma_load_2d(&tma_wlo, &full_bar[stage], st + 2 * kRpZBytes + kRpWBytes, kc * kRpKc, 0);
+          if (++stage == kRpStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kRtFrames, kRtE, /*a_mn_major=*/1, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 128;
+        for (int kc = 0; kc < kNumKc; ++kc) {
+          mbar_wait(&full_bar[stage], phase);   // weights (TMA) landed
+          mbar_wait(&split_bar[stage], phase);  // z tile rewritten as hi / lo by the split warps
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * kRpStageBytes);
+#pragma unroll
+          for (int k = 0; k < kRpKc / 8; ++k) {
+            // A (MN-major, 128B swizzle with 32 B atoms): 8 channels = two 512 B K-groups inside each 32-frame box; the four
+            // boxes (32-frame atoms along M) are kRpZBytes / 4 apart. B (K-major): +32 B per 8-element K step inside the 128 B
+            // swizzle row.
+            const uint64_t a_hi = umma_desc_sw128_base32(st + k * 1024, p.a_lbo, p.a_sbo);
+            const uint64_t a_lo = umma_desc_sw128_base32(st + kRpZBytes + k * 1024, p.a_lbo, p.a_sbo);
+            const uint64_t b_hi = umma_desc_sw128(st + 2 * kRpZBytes, 16, 1024) + 2 * k;
+            const uint64_t b_lo = umma_desc_sw128(st + 2 * kRpZBytes + kRpWBytes, 16, 1024) + 2 * k;
+            umma_ss_tf32(d_tmem, a_lo, b_hi, idesc, (kc | k) != 0 ? 1u : 0u);
+            umma_ss_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_ss_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kRpStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp < 6) {
+    // split warps: z tile (as TMA wrote it) -> hi = tf32(z) in place, lo = tf32(z - hi) at the same offset of the lo tile
+    const int st_tid = threadIdx.x - 64;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kc = 0; kc < kNumKc; ++kc) {
+        mbar_wait(&full_bar[stage], phase);
+        const uint32_t zh = smem_u32(smem + stage * kRpStageBytes) + st_tid * 16;
+#pragma unroll
+        for (int i = 0; i < static_cast<int>(kRpZBytes) / (128 * 16); ++i) {
+          const float4 v = lds128(zh + i * 2048);
+          float4 h, l;
+          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+          sts128(zh + i * 2048, h);
+          sts128(zh + kRpZBytes + i * 2048, l);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&split_bar[stage]);
+        if (++stage == kRpStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // epilogue warps: thread <-> frame (TMEM lane), 96 accumulator columns + bias -> E[frame, 96]
+    const int quad = warp & 3;
+    const int f = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_b, t = (tile % tiles_per_b) * kRtFrames + f;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 128;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      uint32_t r0[32], r1[32], r2[32];
+      tmem_ld_32x32(taddr, r0);
+      tmem_ld_32x32(taddr + 32, r1);
+      tmem_ld_32x32(taddr + 64, r2);
+      tmem_ld_wait_dep(r0);
+      tmem_ld_wait_dep(r1);
+      tmem_ld_wait_dep(r2);
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+      if (t < p.T) {
+        float4* o = reinterpret_cast<float4*>(p.e_out + (static_cast<long long>(b) * p.T + t) * kRtE);
+        const float4* b4 = reinterpret_cast<const float4*>(p.b_in);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bb = __ldg(b4 + i);
+          o[i] = make_float4(__uint_as_float(r0[4 * i]) + bb.x, __uint_as_float(r0[4 * i + 1]) + bb.y,
+                             __uint_as_float(r0[4 * i + 2]) + bb.z, __uint_as_float(r0[4 * i + 3]) + bb.w);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bb = __ldg(b4 + 8 + i);
+          o[8 + i] = make_float4(__uint_as_float(r1[4 * i]) + bb.x, __uint_as_float(r1[4 * i + 1]) + bb.y,
+                                 __uint_as_float(r1[4 * i + 2]) + bb.z, __uint_as_float(r1[4 * i + 3]) + bb.w);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bb = __ldg(b4 + 16 + i);
+          o[16 + i] = make_float4(__uint_as_float(r2[4 * i]) + bb.x, __uint_as_float(r2[4 * i + 1]) + bb.y,
+                                  __uint_as_float(r2[4 * i + 2]) + bb.z, __uint_as_float(r2[4 * i + 3]) + bb.w);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ level search
+constexpr int kRsChunk = 128;                                  // codes per MMA (UMMA N) and per TMA box
+constexpr int kRsChunks = 1024 / kRsChunk;
+constexpr int kRsRing = 4;
+constexpr uint32_t kRsTileBytes = 128 * 128;                   // 128 rows x 32 fp32 (A tile and every codebook chunk)
+constexpr uint32_t kRsSmemBytes = kRsTileBytes * (1 + kRsRing) + 12 * 128 * 4 + 1024 + 256;
+constexpr int kRsThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 search
+
+struct RvqSearchParams {
+  int B, T, n_levels;
+  const float* e;           // [B*T, 96] from rvq_project_kernel
+  const float* g;           // [12, 12, 1024, 8]  G[i][j][code] (j < i used)
+  long long* codes;         // out [B, n_levels, T]
+  const long long* forced;  // teacher forcing [B, n_levels, T] or nullptr
+  float* latents;           // out [B, 96, T] residual-corrected latents before normalisation, or nullptr
+};
+
+// 32 scores of one frame (codes kBase .. kBase+31 of the current chunk): running first maximum, chunk-local index
+template <int kBase>
+__device__ __forceinline__ void rvq_scan32(const uint32_t (&r)[32], float& best, int& cidx) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float v = __uint_as_float(r[i]);
+    if (v > best) {  // strict: the first maximum wins, codes are visited in increasing order
+      best = v;
+      cidx = kBase + i;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kRsThreads, 2)
+rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;
+  uint8_t* sRing = smem + kRsTileBytes;
+  int* s_chosen = reinterpret_cast<int*>(sRing + kRsRing * kRsTileBytes);  // [12][128]
+  uint64_t* ring_full = reinterpret_cast<uint64_t*>(s_chosen + 12 * 128);
+  uint64_t* ring_empty = ring_full + kRsRing;
+  uint64_t* tfull_bar = ring_empty + kRsRing;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* a_ready = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_b = (p.T + kRtFrames - 1) / kRtFrames;
+  const int num_tiles = tiles_per_b * p.B;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_cb);
+    for (int s = 0; s < kRsRing; ++s) {
+      mbar_init(&ring_full[s], 1);
+      mbar_init(&ring_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 128);
+    }
+    mbar_init(a_ready, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        for (int l = 0; l < p.n_levels; ++l)
+          for (int ch = 0; ch < kRsChunks; ++ch, ++g) {
+            const uint32_t s = g % kRsRing;
+            mbar_wait(&ring_empty[s], ((g / kRsRing) & 1) ^ 1);
+            mbar_arrive_expect_tx(&ring_full[s], kRsTileBytes);
+            tma_load_2d(&tma_cb, &ring_full[s], sRing + s * kRsTileBytes, 0, l * 1024 + ch * kRsChunk);
+          }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(kRtFrames, kRsChunk, 0, 0);
+      const uint64_t adesc = umma_desc_sw128(smem_u32(sA), 16, 1024);
+      uint32_t g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        for (int l = 0; l < p.n_levels; ++l, ++it) {
+          mbar_wait(a_ready, it & 1);  // the 128 latent rows of this level are in shared memory
+          for (int ch = 0; ch < kRsChunks; ++ch, ++g) {
+            const uint32_t s = g % kRsRing, buf = g & 1;
+            mbar_wait(&ring_full[s], (g / kRsRing) & 1);
+            mbar_wait(&tempty_bar[buf], ((g >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint64_t bdesc = umma_desc_sw128(smem_u32(sRing + s * kRsTileBytes), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_ss_tf32(tmem_base + buf * kRsChunk, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0 ? 1u : 0u);
+            umma_commit(&ring_empty[s]);
+            umma_commit(&tfull_bar[buf]);
+          }
+        }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int f = quad * 32 + lane;
+    const uint32_t a_row = smem_u32(sA) + f * 128;
+    const int sw = f & 7;
+    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    uint32_t g = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_b, t = (tile % tiles_per_b) * kRtFrames + f;
+      const bool live = t < p.T;
+      const float4* erow = reinterpret_cast<const float4*>(p.e + (static_cast<long long>(b) * p.T + (live ? t : 0)) * kRtE);
+      float cur[8];
+      {
+        const float4 a = live ? __ldg(erow) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 c = live ? __ldg(erow + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        cur[0] = a.x; cur[1] = a.y; cur[2] = a.z; cur[3] = a.w; cur[4] = c.x; cur[5] = c.y; cur[6] = c.z; cur[7] = c.w;
+      }
+      for (int l = 0; l < p.n_levels; ++l) {
+        if (p.latents != nullptr && live) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) p.latents[(static_cast<long long>(b) * kRtE + l * 8 + k) * p.T + t] = cur[k];
+        }
+        // F.normalize: x / max(|x|_2, 1e-12)
+        float n2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) n2 = fmaf(cur[k], cur[k], n2);
+        const float den = fmaxf(sqrtf(n2), 1e-12f);
+        float hi[8], lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float en = __fdiv_rn(cur[k], den);
+          hi[k] = tf32_rna(en);
+          lo[k] = tf32_rna(en - hi[k]);
+        }
+        // A row (K = 32): [e_hi | e_lo | e_hi | 1 1 0 0 0 0 0 0] against B rows [c_hi | c_hi | c_lo | x_hi x_lo 0 ...]
+        sts128(a_row + ((0 ^ sw) << 4), make_float4(hi[0], hi[1], hi[2], hi[3]));
+        sts128(a_row + ((1 ^ sw) << 4), make_float4(hi[4], hi[5], hi[6], hi[7]));
+        sts128(a_row + ((2 ^ sw) << 4), make_float4(lo[0], lo[1], lo[2], lo[3]));
+        sts128(a_row + ((3 ^ sw) << 4), make_float4(lo[4], lo[5], lo[6], lo[7]));
+        sts128(a_row + ((4 ^ sw) << 4), make_float4(hi[0], hi[1], hi[2], hi[3]));
+        sts128(a_row + ((5 ^ sw) << 4), make_float4(hi[4], hi[5], hi[6], hi[7]));
+        sts128(a_row + ((6 ^ sw) << 4), make_float4(1.f, 1.f, 0.f, 0.f));
+        sts128(a_row + ((7 ^ sw) << 4), make_float4(0.f, 0.f, 0.f, 0.f));
+        fence_proxy_async_smem();
+        mbar_arrive(a_ready);
+
+        // next level's latent, minus everything that does not depend on this level's decision (loads overlap the scan)
+        float nxt[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) nxt[k] = 0.f;
+        if (l + 1 < p.n_levels) {
+          if (live) {
+            const float4 a = __ldg(erow + 2 * (l + 1)), c = __ldg(erow + 2 * (l + 1) + 1);
+            nxt[0] = a.x; nxt[1] = a.y; nxt[2] = a.z; nxt[3] = a.w; nxt[4] = c.x; nxt[5] = c.y; nxt[6] = c.z; nxt[7] = c.w;
+          }
+          for (int j = 0; j < l; ++j) {
+            const int cj = s_chosen[j * 128 + f];
+            const float4* gp = reinterpret_cast<const float4*>(p.g + ((static_cast<long long>(l + 1) * 12 + j) * 1024 + cj) * 8);
+            const float4 a = __ldg(gp), c = __ldg(gp + 1);
+            nxt[0] -= a.x; nxt[1] -= a.y; nxt[2] -= a.z; nxt[3] -= a.w; nxt[4] -= c.x; nxt[5] -= c.y; nxt[6] -= c.z; nxt[7] -= c.w;
+          }
+        }
+
+        float best = -INFINITY;
+        int bidx = 0;
+        for (int ch = 0; ch < kRsChunks; ++ch, ++g) {
+          const uint32_t buf = g & 1;
+          const uint32_t taddr = tmem_row + buf * kRsChunk;
+          mbar_wait(&tfull_bar[buf], (g >> 1) & 1);
+          tc_fence_after();
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(taddr, r0);
+          tmem_ld_32x32(taddr + 32, r1);
+          tmem_ld_wait_dep(r0);
+          tmem_ld_wait_dep(r1);
+          int cidx = -1;
+          rvq_scan32<0>(r0, best, cidx);
+          rvq_scan32<32>(r1, best, cidx);
+          tmem_ld_32x32(taddr + 64, r0);
+          tmem_ld_32x32(taddr + 96, r1);
+          tmem_ld_wait_dep(r0);
+          tmem_ld_wait_dep(r1);
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[buf]);  // the accumulator buffer may be overwritten by chunk g + 2
+          rvq_scan32<64>(r0, best, cidx);
+          rvq_scan32<96>(r1, best, cidx);
+          if (cidx >= 0) bidx = ch * kRsChunk + cidx;
+        }
+
+        const long long oidx = (static_cast<long long>(b) * p.n_levels + l) * p.T + t;
+        if (live) p.codes[oidx] = bidx;
+        const int chosen = (p.forced != nullptr && live) ? static_cast<int>(p.forced[oidx]) : bidx;
+        s_chosen[l * 128 + f] = chosen;
+        if (l + 1 < p.n_levels) {
+          const float4* gp = reinterpret_cast<const float4*>(p.g + ((static_cast<long long>(l + 1) * 12 + l) * 1024 + chosen) * 8);
+          const float4 a = __ldg(gp), c = __ldg(gp + 1);
+          cur[0] = nxt[0] - a.x; cur[1] = nxt[1] - a.y; cur[2] = nxt[2] - a.z; cur[3] = nxt[3] - a.w;
+          cur[4] = nxt[4] - c.x; cur[5] = nxt[5] - c.y; cur[6] = nxt[6] - c.z; cur[7] = nxt[7] - c.w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
+}  // namespace edm

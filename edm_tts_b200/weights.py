@@ -121,6 +121,12 @@ def pack_s2a_weights(sd: dict, cfg: InjectionConformerConfig, device, max_positi
     return out
 
 
+def tf32_round(t: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest tf32 value (10 explicit mantissa bits, ties away from zero, like cvt.rna.tf32.f32), kept as fp32."""
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def pack_rvq_weights(sd: dict, n_codebooks: int, prefix: str, device) -> dict:
     """Tables of the fused RVQ search (csrc/rvq.cuh): stacked in_proj, normalised codebooks, G[i][j] cross tables, and the
     projected codebooks (incl. bias) for codes -> features."""
@@ -135,7 +141,20 @@ def pack_rvq_weights(sd: dict, n_codebooks: int, prefix: str, device) -> dict:
         return torch.cat([t, torch.zeros(pad, *t.shape[1:], device=t.device, dtype=t.dtype)]) if pad else t
     g_full = torch.zeros(12, 12, cb.shape[1], cbd, device=device, dtype=torch.float32)
     g_full[:L, :L] = g.float()
+    # tcgen05 path (csrc/rvq_tc.cuh): 3xTF32 operand splits. hi = tf32(v) (round to nearest, ties away), lo = tf32(v - hi).
+    w_all = padl(w_in.float()).reshape(12 * cbd, latent).contiguous()               # [96, latent]: K-major B operand
+    w_hi = tf32_round(w_all)
+    w_lo = tf32_round(w_all - w_hi)
+    cbn_p, x = padl(cbn), -0.5 * padl(cbn.pow(2).sum(-1))
+    c_hi = tf32_round(cbn_p)
+    c_lo = tf32_round(cbn_p - c_hi)
+    x_hi = tf32_round(x)
+    x_lo = tf32_round(x - x_hi)
+    cb_packed = torch.zeros(12, cb.shape[1], 32, device=device, dtype=torch.float32)
+    cb_packed[..., 0:8], cb_packed[..., 8:16], cb_packed[..., 16:24] = c_hi, c_hi, c_lo  # against [e_hi | e_lo | e_hi | 1 1 0..]
+    cb_packed[..., 24], cb_packed[..., 25] = x_hi, x_lo
     return {
+        "w_hi": w_hi.contiguous(), "w_lo": w_lo.contiguous(), "cb_packed": cb_packed.contiguous(),
         "w_in_t": padl(w_in.float()).reshape(12 * cbd, latent).t().contiguous(),   # [latent, 96]: rows are contiguous per channel
         "b_in": padl(b_in.float()).reshape(-1).contiguous(),
         "cb_norm": padl(cbn).contiguous(),

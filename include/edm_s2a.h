@@ -90,6 +90,19 @@ int edm_rvq_encode(const void* z, int z_is_bf16, int B, int T, int n_levels, con
                    const float* cb_norm, const float* cb_n2, const float* g, long long* codes,
                    const long long* forced, float* latents, void* stream);
 
+/* Same search on the tcgen05 tensor cores (csrc/rvq_tc.cuh): a 3xTF32 projection GEMM z -> e_ws [B*T,96] followed by the
+ * 12-level search with TMEM-resident score tiles. z fp32 [B,1024,T] with T % 4 == 0 (TMA needs 16-byte rows; the host
+ * side pads / converts other inputs). Tables (pack_rvq_weights): w_hi / w_lo [96,1024] tf32-split stacked in_proj weights,
+ * b_in [96], cb_packed [12,1024,32] = [c^_hi | c^_hi | c^_lo | -|c^|^2/2 hi, lo, 0...], g [12,12,1024,8]. e_ws is caller
+ * scratch of B*T*96 floats. Replaces ResidualVectorQuantize.forward, dac/vector_quantizer.py:146-210. */
+int edm_rvq_encode_tc(const float* z, int B, int T, int n_levels, const float* w_hi, const float* w_lo, const float* b_in,
+                      const float* cb_packed, const float* g, float* e_ws, long long* codes, const long long* forced,
+                      float* latents, void* stream);
+
+/* Bring-up only: override the shared-memory descriptor strides of the projection's MN-major A operand; skip_project = 1
+ * makes edm_rvq_encode_tc search the latents already in e_ws. */
+void edm_rvq_tc_debug(unsigned lbo, unsigned sbo, int skip_project);
+
 /* codes int64 [B,L,T] -> features fp32 [B,1024,T] (or [B,L,1024,T] when unreduced); proj = [12,1024,1024] projected
  * codebooks incl. bias. Replaces from_codes / from_codes_unreduced, dac/vector_quantizer.py:212-252. */
 int edm_codes_to_features(const long long* codes, const float* proj, float* out, int B, int L, int T, int unreduced,

@@ -310,8 +310,99 @@ def test_rvq():
     print(f"rvq time B={B} T={T}: {ms:.3f} ms = {B * T / ms / 1e3:.2f} Mframes/s, {B * T * 4192 / ms / 1e6:.0f} GB/s", flush=True)
 
 
+def test_rvqtc():
+    """tcgen05 RVQ (csrc/rvq_tc.cuh): projection vs an fp64 einsum, teacher-forced and free-running codes vs the fp32 torch loop."""
+    from edm_tts_b200.weights import tf32_round
+    torch.manual_seed(0)
+    Lv = 12
+    w_in = torch.randn(Lv, 8, 1024, device=dev) / 32
+    b_in = torch.randn(Lv, 8, device=dev) * 0.1
+    cb = torch.randn(Lv, 1024, 8, device=dev)
+    w_out = torch.randn(Lv, 1024, 8, device=dev) * 0.2
+    b_out = torch.randn(Lv, 1024, device=dev) * 0.05
+    cbn = torch.nn.functional.normalize(cb, dim=-1).contiguous()
+    proj = torch.einsum("lcd,lkd->lkc", w_out, cb) + b_out[:, None, :]
+    g = torch.einsum("idc,jkc->ijkd", w_in, proj).contiguous()
+    w_all = w_in.view(96, 1024).contiguous()
+    w_hi = tf32_round(w_all)
+    w_lo = tf32_round(w_all - w_hi)
+    x = -0.5 * cbn.pow(2).sum(-1)
+    c_hi = tf32_round(cbn)
+    c_lo = tf32_round(cbn - c_hi)
+    x_hi = tf32_round(x)
+    cbp = torch.zeros(Lv, 1024, 32, device=dev)
+    cbp[..., 0:8], cbp[..., 8:16], cbp[..., 16:24] = c_hi, c_hi, c_lo
+    cbp[..., 24], cbp[..., 25] = x_hi, tf32_round(x - x_hi)
+    b_flat = b_in.view(96).contiguous()
+
+    def run(z, forced=None, want_lat=False, e_given=None):
+        B, _, T = z.shape
+        codes = torch.empty(B, Lv, T, device=dev, dtype=torch.int64)
+        e_ws = torch.full((B * T, 96), float("nan"), device=dev) if e_given is None else e_given.float().contiguous()
+        lat = torch.empty(B, 96, T, device=dev) if want_lat else None
+        L.check(L.lib().edm_rvq_encode_tc(L.ptr(z), B, T, Lv, L.ptr(w_hi), L.ptr(w_lo), L.ptr(b_flat), L.ptr(cbp), L.ptr(g), L.ptr(e_ws),
+                                          L.ptr(codes), L.ptr(forced), L.ptr(lat), L.stream_ptr()), "rvq_tc")
+        torch.cuda.synchronize()
+        return codes, e_ws, lat
+
+    combos = [(4096, 512)] if len(sys.argv) < 4 else [(int(a), int(b)) for a, b in zip(sys.argv[2::2], sys.argv[3::2])]
+    for (B, T) in [(1, 128), (2, 332), (2, 3000)]:
+        z = torch.randn(B, 1024, T, device=dev)
+        e_ref = (torch.einsum("nc,bct->btn", w_all.double(), z.double()) + b_flat.double()).reshape(B * T, 96)
+        for lbo, sbo in combos:
+            L.lib().edm_rvq_tc_debug(lbo, sbo, 0)
+            codes, e_ws, _ = run(z)
+            err = (e_ws.double() - e_ref).abs().max().item()
+            print(f"rvqtc B={B} T={T} lbo={lbo} sbo={sbo}: projection max err {err:.3e} (|e| max {e_ref.abs().max().item():.2f})", flush=True)
+            if err > 1e-3 and T == 128:
+                d = (e_ws.double() - e_ref).abs()
+                print("   bias", b_flat[:4].tolist(), "out", e_ws[0, :4].tolist(), "ref", e_ref[0, :4].tolist())
+                ones = run(torch.ones_like(z))[1]
+                print("   z=1: out", ones[0, :4].tolist(), ones[77, :4].tolist(), "expected", (w_all.double().sum(1) + b_flat.double())[:4].tolist())
+                print("   err by 32-frame block:", [f"{d[i * 32:(i + 1) * 32].max().item():.2e}" for i in range(4)])
+                print("   err by frame (first 40):", [f"{v:.1e}" for v in d[:40].max(1)[0].tolist()])
+                print("   err by output column group:", [f"{d[:, i * 8:(i + 1) * 8].max().item():.2e}" for i in range(12)])
+                # which reference entry does each output equal? (permutation detection on row 0..3, col 0..3)
+                for r in (0, 1, 5, 33):
+                    for c in (0, 1, 9):
+                        hit = ((e_ref - e_ws[r, c].double()).abs() < 1e-4).nonzero()
+                        print(f"   out[{r},{c}]={e_ws[r, c].item():+.5f} matches ref at {hit[:4].tolist()}")
+        # fp32 torch loop (vector_quantizer.py semantics) with margins
+        res = z.clone()
+        ref_codes, margins = [], []
+        for i in range(Lv):
+            e = torch.einsum("dc,bct->bdt", w_in[i], res) + b_in[i][None, :, None]
+            enc = torch.nn.functional.normalize(e.permute(0, 2, 1).reshape(-1, 8))
+            dist = enc.pow(2).sum(1, keepdim=True) - 2 * enc @ cbn[i].t() + cbn[i].pow(2).sum(1, keepdim=True).t()
+            top2 = (-dist).topk(2, dim=1)[0]
+            margins.append((top2[:, 0] - top2[:, 1]).view(B, T))
+            idx = (-dist).max(1)[1].view(B, T)
+            ref_codes.append(idx)
+            res = res - (torch.einsum("cd,btd->bct", w_out[i], cb[i][idx]) + b_out[i][None, :, None])
+        ref_codes, margins = torch.stack(ref_codes, 1).contiguous(), torch.stack(margins, 1)
+        L.lib().edm_rvq_tc_debug(4096, 512, 1)   # search kernel alone on exact latents
+        forced, _, lat = run(z, ref_codes, True, e_given=e_ref)
+        mism = forced != ref_codes
+        print(f"  [search only, exact latents] teacher-forced mismatches per level {mism.sum((0, 2)).tolist()} of {B * T}; max oracle margin at a mismatch "
+              f"{margins[mism].max().item() if mism.any() else 0.0:.2e}", flush=True)
+        L.lib().edm_rvq_tc_debug(combos[-1][0], combos[-1][1], 0)
+        forced, _, lat = run(z, ref_codes, True)
+        mism = forced != ref_codes
+        print(f"  teacher-forced mismatches per level {mism.sum((0, 2)).tolist()} of {B * T}; max oracle margin at a mismatch "
+              f"{margins[mism].max().item() if mism.any() else 0.0:.2e}", flush=True)
+        free = run(z)[0]
+        print(f"  free-running mismatches per level {(free != ref_codes).sum((0, 2)).tolist()}", flush=True)
+    B, T = 32, 3000
+    z = torch.randn(B, 1024, T, device=dev)
+    codes = torch.empty(B, Lv, T, device=dev, dtype=torch.int64)
+    e_ws = torch.empty(B * T, 96, device=dev)
+    ms = timeit(lambda: L.lib().edm_rvq_encode_tc(L.ptr(z), B, T, Lv, L.ptr(w_hi), L.ptr(w_lo), L.ptr(b_flat), L.ptr(cbp), L.ptr(g), L.ptr(e_ws),
+                                                  L.ptr(codes), None, None, L.stream_ptr()), iters=10, warm=3)
+    print(f"rvqtc time B={B} T={T}: {ms:.3f} ms = {B * T / ms / 1e3:.2f} Mframes/s, {B * T * 4192 / ms / 1e6:.0f} GB/s", flush=True)
+
+
 if __name__ == "__main__":
     t0 = time.time()
-    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvq": test_rvq}[sys.argv[1]]()
+    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvq": test_rvq, "rvqtc": test_rvqtc}[sys.argv[1]]()
     torch.cuda.synchronize()
     print(f"[{sys.argv[1]}] done in {time.time() - t0:.1f}s", flush=True)
