@@ -406,10 +406,12 @@ extern "C" int edm_rvq_encode(const void* z, int z_is_bf16, int B, int T, int n_
 // bring-up knob (tools/bringup_ops.py rvqtc): descriptor strides of the MN-major tf32 A operand
 unsigned g_rvq_a_lbo = kRpZBytes / 4, g_rvq_a_sbo = 512;
 int g_rvq_skip_project = 0;  // 1: e_ws is taken as given (tests the search kernel alone)
-extern "C" void edm_rvq_tc_debug(unsigned lbo, unsigned sbo, int skip_project) {
+int g_rvq_scan_probe = 0;    // 1: search kernel without the compare work (timing floor of TMA + MMA + TMEM reads)
+extern "C" void edm_rvq_tc_debug(unsigned lbo, unsigned sbo, int skip_project, int scan_probe) {
   g_rvq_a_lbo = lbo;
   g_rvq_a_sbo = sbo;
   g_rvq_skip_project = skip_project;
+  g_rvq_scan_probe = scan_probe;
 }
 
 extern "C" int edm_rvq_encode_tc(const float* z, int B, int T, int n_levels, const float* w_hi, const float* w_lo, const float* b_in,
@@ -421,7 +423,8 @@ extern "C" int edm_rvq_encode_tc(const float* z, int B, int T, int n_levels, con
   static bool attr_set = false;
   if (!attr_set) {
     EDM_CUDA(cudaFuncSetAttribute(rvq_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmemBytes));
-    EDM_CUDA(cudaFuncSetAttribute(rvq_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemBytes));
+    EDM_CUDA(cudaFuncSetAttribute(rvq_search_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemBytes));
+    EDM_CUDA(cudaFuncSetAttribute(rvq_search_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemBytes));
     attr_set = true;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -439,7 +442,12 @@ extern "C" int edm_rvq_encode_tc(const float* z, int B, int T, int n_levels, con
   }
   RvqSearchParams sp;
   sp.B = B; sp.T = T; sp.n_levels = n_levels; sp.e = e_ws; sp.g = g; sp.codes = codes; sp.forced = forced; sp.latents = latents;
-  rvq_search_kernel<<<tiles < 2 * num_sms() ? tiles : 2 * num_sms(), kRsThreads, kRsSmemBytes, st>>>(mcb, sp);
+  sp.one = 1.0f; sp.onei = 1;
+  const int sgrid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
+  if (g_rvq_scan_probe)
+    rvq_search_kernel<1><<<sgrid, kRsThreads, kRsSmemBytes, st>>>(mcb, sp);
+  else
+    rvq_search_kernel<0><<<sgrid, kRsThreads, kRsSmemBytes, st>>>(mcb, sp);
   EDM_LAUNCH_CHECK("rvq_search");
   return 0;
 }

@@ -226,7 +226,7 @@ constexpr int kRsChunk = 128;                                  // codes per MMA 
 constexpr int kRsChunks = 1024 / kRsChunk;
 constexpr int kRsRing = 4;
 constexpr uint32_t kRsTileBytes = 128 * 128;                   // 128 rows x 32 fp32 (A tile and every codebook chunk)
-constexpr uint32_t kRsSmemBytes = kRsTileBytes * (1 + kRsRing) + 12 * 128 * 4 + 1024 + 256;
+constexpr uint32_t kRsSmemBytes = kRsTileBytes * (1 + kRsRing) + (12 + 8) * 128 * 4 + 1024 + 256;
 constexpr int kRsThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 search
 
 struct RvqSearchParams {
@@ -236,21 +236,47 @@ struct RvqSearchParams {
   long long* codes;         // out [B, n_levels, T]
   const long long* forced;  // teacher forcing [B, n_levels, T] or nullptr
   float* latents;           // out [B, 96, T] residual-corrected latents before normalisation, or nullptr
+  float one;                // 1.0f and 1, passed at run time so the saves of rvq_scan_group4 stay FMUL / IMAD (FMA pipe)
+  int onei;
 };
 
-// 32 scores of one frame (codes kBase .. kBase+31 of the current chunk): running first maximum, chunk-local index
-template <int kBase>
-__device__ __forceinline__ void rvq_scan32(const uint32_t (&r)[32], float& best, int& cidx) {
+// Running first maximum of one frame's scores. The scan is ALU-pipe bound (FSETP / FMNMX / SEL all issue there at half
+// rate), so it works on groups of four: two FMNMX for the group maximum, one FSETP against the running best, one FMNMX to
+// update it, and the "remember this group" side (group id + its four raw scores) as predicated FMUL / IMAD by a run-time 1,
+// which issue on the otherwise idle FMA pipe. The winner inside the remembered group is resolved once per level.
+struct RvqBest {
+  float best;
+  int gid;        // group (code / 4) holding the running maximum
+  float s[4];     // its four scores
+};
+template <int kGroup0>
+__device__ __forceinline__ void rvq_scan32(const uint32_t (&r)[32], RvqBest& st, int group_base, float one, int onei) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float v = __uint_as_float(r[i]);
-    if (v > best) {  // strict: the first maximum wins, codes are visited in increasing order
-      best = v;
-      cidx = kBase + i;
-    }
+  for (int g = 0; g < 8; ++g) {
+    const float v0 = __uint_as_float(r[4 * g]), v1 = __uint_as_float(r[4 * g + 1]), v2 = __uint_as_float(r[4 * g + 2]),
+                v3 = __uint_as_float(r[4 * g + 3]);
+    const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+    asm(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.gt.f32 q, %6, %0;\n\t"           // strict: an equal later group never replaces an earlier one
+        "max.f32 %0, %0, %6;\n\t"
+        "@q mul.f32 %1, %7, %11;\n\t"
+        "@q mul.f32 %2, %8, %11;\n\t"
+        "@q mul.f32 %3, %9, %11;\n\t"
+        "@q mul.f32 %4, %10, %11;\n\t"
+        "@q mad.lo.s32 %5, %12, %13, %14;\n\t"
+        "}\n"
+        : "+f"(st.best), "+f"(st.s[0]), "+f"(st.s[1]), "+f"(st.s[2]), "+f"(st.s[3]), "+r"(st.gid)
+        : "f"(m), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(one), "r"(onei), "r"(kGroup0 + g), "r"(group_base));
   }
 }
+// bring-up probe: consumes the loaded registers with one op per 32 scores (measures the TMEM-read / MMA floor of the kernel)
+__device__ __forceinline__ void rvq_scan32_probe(const uint32_t (&r)[32], RvqBest& st) {
+  st.best = fmaxf(st.best, __uint_as_float(r[0] ^ r[31]));
+}
 
+template <int kScan>  // 0 = full scan, 1 = bring-up probe (loads only)
 __global__ void __launch_bounds__(kRsThreads, 2)
 rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -258,7 +284,8 @@ rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchPar
   uint8_t* sA = smem;
   uint8_t* sRing = smem + kRsTileBytes;
   int* s_chosen = reinterpret_cast<int*>(sRing + kRsRing * kRsTileBytes);  // [12][128]
-  uint64_t* ring_full = reinterpret_cast<uint64_t*>(s_chosen + 12 * 128);
+  float* s_nxt = reinterpret_cast<float*>(s_chosen + 12 * 128);            // [8][128] next level's partial latent (parked during the scan)
+  uint64_t* ring_full = reinterpret_cast<uint64_t*>(s_nxt + 8 * 128);
   uint64_t* ring_empty = ring_full + kRsRing;
   uint64_t* tfull_bar = ring_empty + kRsRing;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -367,11 +394,12 @@ rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchPar
         fence_proxy_async_smem();
         mbar_arrive(a_ready);
 
-        // next level's latent, minus everything that does not depend on this level's decision (loads overlap the scan)
-        float nxt[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) nxt[k] = 0.f;
+        // next level's latent, minus everything that does not depend on this level's decision (loads overlap the scan);
+        // parked in shared memory so the scan keeps its registers for four TMEM loads in flight
         if (l + 1 < p.n_levels) {
+          float nxt[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) nxt[k] = 0.f;
           if (live) {
             const float4 a = __ldg(erow + 2 * (l + 1)), c = __ldg(erow + 2 * (l + 1) + 1);
             nxt[0] = a.x; nxt[1] = a.y; nxt[2] = a.z; nxt[3] = a.w; nxt[4] = c.x; nxt[5] = c.y; nxt[6] = c.z; nxt[7] = c.w;
@@ -382,13 +410,18 @@ rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchPar
             const float4 a = __ldg(gp), c = __ldg(gp + 1);
             nxt[0] -= a.x; nxt[1] -= a.y; nxt[2] -= a.z; nxt[3] -= a.w; nxt[4] -= c.x; nxt[5] -= c.y; nxt[6] -= c.z; nxt[7] -= c.w;
           }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s_nxt[k * 128 + f] = nxt[k];
         }
 
-        float best = -INFINITY;
-        int bidx = 0;
+        RvqBest st;
+        st.best = -INFINITY;
+        st.gid = 0;
+        st.s[0] = st.s[1] = st.s[2] = st.s[3] = 0.f;
         for (int ch = 0; ch < kRsChunks; ++ch, ++g) {
           const uint32_t buf = g & 1;
           const uint32_t taddr = tmem_row + buf * kRsChunk;
+          const int group_base = ch * (kRsChunk / 4);
           mbar_wait(&tfull_bar[buf], (g >> 1) & 1);
           tc_fence_after();
           uint32_t r0[32], r1[32];
@@ -396,19 +429,29 @@ rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchPar
           tmem_ld_32x32(taddr + 32, r1);
           tmem_ld_wait_dep(r0);
           tmem_ld_wait_dep(r1);
-          int cidx = -1;
-          rvq_scan32<0>(r0, best, cidx);
-          rvq_scan32<32>(r1, best, cidx);
+          if constexpr (kScan == 0) {
+            rvq_scan32<0>(r0, st, group_base, p.one, p.onei);
+            rvq_scan32<8>(r1, st, group_base, p.one, p.onei);
+          } else {
+            rvq_scan32_probe(r0, st);
+            rvq_scan32_probe(r1, st);
+          }
           tmem_ld_32x32(taddr + 64, r0);
           tmem_ld_32x32(taddr + 96, r1);
           tmem_ld_wait_dep(r0);
           tmem_ld_wait_dep(r1);
           tc_fence_before();
           mbar_arrive(&tempty_bar[buf]);  // the accumulator buffer may be overwritten by chunk g + 2
-          rvq_scan32<64>(r0, best, cidx);
-          rvq_scan32<96>(r1, best, cidx);
-          if (cidx >= 0) bidx = ch * kRsChunk + cidx;
+          if constexpr (kScan == 0) {
+            rvq_scan32<16>(r0, st, group_base, p.one, p.onei);
+            rvq_scan32<24>(r1, st, group_base, p.one, p.onei);
+          } else {
+            rvq_scan32_probe(r0, st);
+            rvq_scan32_probe(r1, st);
+          }
         }
+        // first position of the maximum inside the remembered group
+        const int bidx = st.gid * 4 + (st.s[0] == st.best ? 0 : st.s[1] == st.best ? 1 : st.s[2] == st.best ? 2 : 3);
 
         const long long oidx = (static_cast<long long>(b) * p.n_levels + l) * p.T + t;
         if (live) p.codes[oidx] = bidx;
@@ -417,8 +460,9 @@ rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchPar
         if (l + 1 < p.n_levels) {
           const float4* gp = reinterpret_cast<const float4*>(p.g + ((static_cast<long long>(l + 1) * 12 + l) * 1024 + chosen) * 8);
           const float4 a = __ldg(gp), c = __ldg(gp + 1);
-          cur[0] = nxt[0] - a.x; cur[1] = nxt[1] - a.y; cur[2] = nxt[2] - a.z; cur[3] = nxt[3] - a.w;
-          cur[4] = nxt[4] - c.x; cur[5] = nxt[5] - c.y; cur[6] = nxt[6] - c.z; cur[7] = nxt[7] - c.w;
+          cur[0] = s_nxt[0 * 128 + f] - a.x; cur[1] = s_nxt[1 * 128 + f] - a.y; cur[2] = s_nxt[2 * 128 + f] - a.z;
+          cur[3] = s_nxt[3 * 128 + f] - a.w; cur[4] = s_nxt[4 * 128 + f] - c.x; cur[5] = s_nxt[5 * 128 + f] - c.y;
+          cur[6] = s_nxt[6 * 128 + f] - c.z; cur[7] = s_nxt[7 * 128 + f] - c.w;
         }
       }
     }

@@ -100,8 +100,9 @@ int edm_rvq_encode_tc(const float* z, int B, int T, int n_levels, const float* w
                       float* latents, void* stream);
 
 /* Bring-up only: override the shared-memory descriptor strides of the projection's MN-major A operand; skip_project = 1
- * makes edm_rvq_encode_tc search the latents already in e_ws. */
-void edm_rvq_tc_debug(unsigned lbo, unsigned sbo, int skip_project);
+ * makes edm_rvq_encode_tc search the latents already in e_ws; scan_probe = 1 runs the search without its compare work
+ * (timing floor; the codes are meaningless). */
+void edm_rvq_tc_debug(unsigned lbo, unsigned sbo, int skip_project, int scan_probe);
 
 /* codes int64 [B,L,T] -> features fp32 [B,1024,T] (or [B,L,1024,T] when unreduced); proj = [12,1024,1024] projected
  * codebooks incl. bias. Replaces from_codes / from_codes_unreduced, dac/vector_quantizer.py:212-252. */

@@ -350,7 +350,7 @@ def test_rvqtc():
         z = torch.randn(B, 1024, T, device=dev)
         e_ref = (torch.einsum("nc,bct->btn", w_all.double(), z.double()) + b_flat.double()).reshape(B * T, 96)
         for lbo, sbo in combos:
-            L.lib().edm_rvq_tc_debug(lbo, sbo, 0)
+            L.lib().edm_rvq_tc_debug(lbo, sbo, 0, 0)
             codes, e_ws, _ = run(z)
             err = (e_ws.double() - e_ref).abs().max().item()
             print(f"rvqtc B={B} T={T} lbo={lbo} sbo={sbo}: projection max err {err:.3e} (|e| max {e_ref.abs().max().item():.2f})", flush=True)
@@ -380,12 +380,12 @@ def test_rvqtc():
             ref_codes.append(idx)
             res = res - (torch.einsum("cd,btd->bct", w_out[i], cb[i][idx]) + b_out[i][None, :, None])
         ref_codes, margins = torch.stack(ref_codes, 1).contiguous(), torch.stack(margins, 1)
-        L.lib().edm_rvq_tc_debug(4096, 512, 1)   # search kernel alone on exact latents
+        L.lib().edm_rvq_tc_debug(4096, 512, 1, 0)   # search kernel alone on exact latents
         forced, _, lat = run(z, ref_codes, True, e_given=e_ref)
         mism = forced != ref_codes
         print(f"  [search only, exact latents] teacher-forced mismatches per level {mism.sum((0, 2)).tolist()} of {B * T}; max oracle margin at a mismatch "
               f"{margins[mism].max().item() if mism.any() else 0.0:.2e}", flush=True)
-        L.lib().edm_rvq_tc_debug(combos[-1][0], combos[-1][1], 0)
+        L.lib().edm_rvq_tc_debug(combos[-1][0], combos[-1][1], 0, 0)
         forced, _, lat = run(z, ref_codes, True)
         mism = forced != ref_codes
         print(f"  teacher-forced mismatches per level {mism.sum((0, 2)).tolist()} of {B * T}; max oracle margin at a mismatch "
@@ -401,8 +401,29 @@ def test_rvqtc():
     print(f"rvqtc time B={B} T={T}: {ms:.3f} ms = {B * T / ms / 1e3:.2f} Mframes/s, {B * T * 4192 / ms / 1e6:.0f} GB/s", flush=True)
 
 
+def test_rvqtime():
+    """Timing of the two tcgen05 RVQ kernels at BASELINE config 4 (z [32,1024,3000] fp32) through the public wrapper."""
+    from edm_tts_b200 import ResidualVectorQuantize
+    from edm_tts_b200.synthetic import OracleConfig, make_quantizer_state_dict
+    q = ResidualVectorQuantize(make_quantizer_state_dict(OracleConfig(), 0))
+    for (B, T) in [(32, 3000), (4, 3000), (1, 500)]:
+        z = torch.randn(B, 1024, T, device=dev)
+        L.lib().edm_rvq_tc_debug(4096, 512, 0, 0)
+        ms = timeit(lambda: q.encode(z), iters=10, warm=3)
+        L.lib().edm_rvq_tc_debug(4096, 512, 1, 0)
+        ms_s = timeit(lambda: q.encode(z), iters=10, warm=3)
+        L.lib().edm_rvq_tc_debug(4096, 512, 1, 1)
+        ms_p = timeit(lambda: q.encode(z), iters=10, warm=3)
+        L.lib().edm_rvq_tc_debug(4096, 512, 0, 0)
+        print(f"rvq tcgen05 B={B} T={T}: total {ms:.3f} ms (search alone {ms_s:.3f} ms [no-compare floor {ms_p:.3f}], projection ~{ms - ms_s:.3f} ms) = {B * T / ms / 1e3:.1f} Mframes/s, "
+              f"{B * T * 4192 / ms / 1e6:.0f} GB/s algorithmic", flush=True)
+    z = torch.randn(32, 1024, 3000, device=dev)
+    ms_old = timeit(lambda: q.encode(z, impl="mma_sync"), iters=5, warm=2)
+    print(f"rvq mma.sync kernel B=32 T=3000: {ms_old:.3f} ms", flush=True)
+
+
 if __name__ == "__main__":
     t0 = time.time()
-    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvq": test_rvq, "rvqtc": test_rvqtc}[sys.argv[1]]()
+    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvq": test_rvq, "rvqtc": test_rvqtc, "rvqtime": test_rvqtime}[sys.argv[1]]()
     torch.cuda.synchronize()
     print(f"[{sys.argv[1]}] done in {time.time() - t0:.1f}s", flush=True)
