@@ -404,7 +404,7 @@ extern "C" int edm_rvq_encode(const void* z, int z_is_bf16, int B, int T, int n_
 }
 
 // bring-up knob (tools/bringup_ops.py rvqtc): descriptor strides of the MN-major tf32 A operand
-unsigned g_rvq_a_lbo = kRpZBytes / 4, g_rvq_a_sbo = 512;
+unsigned g_rvq_a_lbo = 4096, g_rvq_a_sbo = 512;
 int g_rvq_skip_project = 0;  // 1: e_ws is taken as given (tests the search kernel alone)
 int g_rvq_scan_probe = 0;    // 1: search kernel without the compare work (timing floor of TMA + MMA + TMEM reads)
 extern "C" void edm_rvq_tc_debug(unsigned lbo, unsigned sbo, int skip_project, int scan_probe) {
@@ -435,9 +435,10 @@ extern "C" int edm_rvq_encode_tc(const float* z, int B, int T, int n_levels, con
   if (int rc = make_tmap_f32_2d(&mcb, cb_packed, 12 * 1024, 32, 32, kRsChunk)) return rc;
   const int tiles = ((T + kRtFrames - 1) / kRtFrames) * B;
   RvqProjParams pp;
-  pp.B = B; pp.T = T; pp.b_in = b_in; pp.e_out = e_ws; pp.a_lbo = g_rvq_a_lbo; pp.a_sbo = g_rvq_a_sbo;
-  if (!g_rvq_skip_project) {
-    rvq_project_kernel<<<tiles < num_sms() ? tiles : num_sms(), kRpThreads, kRpSmemBytes, st>>>(mz, mwh, mwl, pp);
+  pp.B = B; pp.T = T; pp.b_in = b_in; pp.e_out = e_ws; pp.a_lbo = g_rvq_a_lbo; pp.a_sbo = g_rvq_a_sbo; pp.dbg = g_rvq_skip_project >> 4;
+  if (!(g_rvq_skip_project & 1)) {
+      const int ptiles = ((T + kRpFrames - 1) / kRpFrames) * B;
+    rvq_project_kernel<<<ptiles < num_sms() ? ptiles : num_sms(), kRpThreads, kRpSmemBytes, st>>>(mz, mwh, mwl, pp);
     EDM_LAUNCH_CHECK("rvq_project");
   }
   RvqSearchParams sp;

@@ -28,19 +28,27 @@ constexpr int kRtE = 96;        // 12 levels x 8 dims
 constexpr int kRtLatent = 1024;
 
 // ------------------------------------------------------------------------------------------------ projection
-constexpr int kRpKc = 32;                                            // latent channels per pipeline stage
-constexpr int kRpStages = 3;
-constexpr uint32_t kRpZBytes = kRtFrames * kRpKc * 4;                // 16 KB: 4 TMA boxes of (32 frames x 32 channels)
+// Two rings: one for the raw z tiles (the only HBM stream: 3 x 32 KB in flight per SM keeps the memory system busy
+// across the ~1 us load latency) and a shallow one for what is needed only between "split" and "MMA": the lo tile and the
+// (L2-resident) hi / lo weight chunks.
+// A CTA tile is 256 frames (two 128-row accumulators): every weight chunk fetched from L2 feeds two MMAs, which halves the
+// L2 -> SM weight traffic (with 128-frame tiles it was 1.5x the z stream and the L2 fabric, not HBM, set the pace).
+constexpr int kRpFrames = 256;
+constexpr int kRpKc = 32;                                            // latent channels per pipeline step
+constexpr int kRpZStages = 3;
+constexpr int kRpLwStages = 2;
+constexpr uint32_t kRpZBytes = kRpFrames * kRpKc * 4;                // 32 KB: 8 TMA boxes of (32 frames x 32 channels)
 constexpr uint32_t kRpWBytes = kRtE * kRpKc * 4;                     // 12 KB: 96 outputs x 32 channels (K-major)
-constexpr uint32_t kRpStageBytes = 2 * kRpZBytes + 2 * kRpWBytes;    // z_hi | z_lo | w_hi | w_lo = 56 KB
-constexpr uint32_t kRpSmemBytes = kRpStages * kRpStageBytes + 1024 + 256;
-constexpr int kRpThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 split, warps 6-9 epilogue
+constexpr uint32_t kRpLwBytes = kRpZBytes + 2 * kRpWBytes;           // z_lo | w_hi | w_lo = 56 KB
+constexpr uint32_t kRpSmemBytes = kRpZStages * kRpZBytes + kRpLwStages * kRpLwBytes + 1024 + 256;
+constexpr int kRpThreads = 352;  // warp 0 z TMA, warp 1 MMA, warps 2-5 split, warps 6-9 epilogue, warp 10 weight TMA
 
 struct RvqProjParams {
   int B, T;
   const float* b_in;  // [96]
   float* e_out;       // [B*T, 96] projected latents (before any residual correction)
-  uint32_t a_lbo, a_sbo;  // MN-major A descriptor strides (bytes): 32-frame atoms kRpZBytes/4 apart, 4-channel K-groups 512 apart
+  uint32_t a_lbo, a_sbo;  // MN-major A descriptor strides (bytes): 32-frame atoms (TMA boxes) 4096 apart, 4-channel K-groups 512 apart
+  int dbg;                // bring-up timing probes: bit 0 = split warps skip their arithmetic, bit 1 = no MMAs are issued
 };
 
 __global__ void __launch_bounds__(kRpThreads, 1)
@@ -48,26 +56,36 @@ rvq_project_kernel(const __grid_constant__ CUtensorMap tma_z, const __grid_const
                    const __grid_constant__ CUtensorMap tma_wlo, const RvqProjParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kRpStages * kRpStageBytes);
-  uint64_t* split_bar = full_bar + kRpStages;
-  uint64_t* empty_bar = split_bar + kRpStages;
-  uint64_t* tfull_bar = empty_bar + kRpStages;
+  uint8_t* sZ = smem;                                   // kRpZStages x 16 KB (becomes the hi tile in place)
+  uint8_t* sLw = smem + kRpZStages * kRpZBytes;         // kRpLwStages x (lo tile | w_hi | w_lo)
+  uint64_t* z_full = reinterpret_cast<uint64_t*>(sLw + kRpLwStages * kRpLwBytes);
+  uint64_t* z_empty = z_full + kRpZStages;
+  uint64_t* w_full = z_empty + kRpZStages;
+  uint64_t* split_bar = w_full + kRpLwStages;
+  uint64_t* lw_empty = split_bar + kRpLwStages;
+  uint64_t* tfull_bar = lw_empty + kRpLwStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_per_b = (p.T + kRtFrames - 1) / kRtFrames;
+  const int tiles_per_b = (p.T + kRpFrames - 1) / kRpFrames;
   const int num_tiles = tiles_per_b * p.B;
   constexpr int kNumKc = kRtLatent / kRpKc;
+  const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const uint32_t total_steps = static_cast<uint32_t>(my_tiles) * kNumKc;  // pipeline steps of this CTA, numbered it
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_z);
     tma_prefetch_desc(&tma_whi);
     tma_prefetch_desc(&tma_wlo);
-    for (int s = 0; s < kRpStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < kRpZStages; ++s) {
+      mbar_init(&z_full[s], 1);
+      mbar_init(&z_empty[s], 1);
+    }
+    for (int s = 0; s < kRpLwStages; ++s) {
+      mbar_init(&w_full[s], 1);
       mbar_init(&split_bar[s], 128);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&lw_empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
@@ -75,7 +93,7 @@ rvq_project_kernel(const __grid_constant__ CUtensorMap tma_z, const __grid_const
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -83,134 +101,133 @@ rvq_project_kernel(const __grid_constant__ CUtensorMap tma_z, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRtFrames;
-        for (int kc = 0; kc < kNumKc; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = smem + stage * kRpStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], kRpZBytes + 2 * kRpWBytes);
+      for (uint32_t it = 0; it < total_steps; ++it) {
+        const int tile = blockIdx.x + (it / kNumKc) * gridDim.x, kc = it % kNumKc;
+        const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRpFrames;
+        const uint32_t zs = it % kRpZStages;
+        mbar_wait(&z_empty[zs], ((it / kRpZStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&z_full[zs], kRpZBytes);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)  // frames beyond T are zero-filled by TMA
-            tma_load_2d(&tma_z, &full_bar[stage], st + i * (kRpZBytes / 4), t0 + 32 * i, b * kRtLatent + kc * kRpKc);
-          tma_load_2d(&tma_whi, &full_bar[stage], st + 2 * kRpZBytes, kc * kRpKc, 0);
-          tma_load_2d(&tma_wlo, &full_bar[stage], st + 2 * kRpZBytes + kRpWBytes, kc * kRpKc, 0);
-          if (++stage == kRpStages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
+        for (int i = 0; i < kRpFrames / 32; ++i)  // frames beyond T are zero-filled by TMA
+          tma_load_2d(&tma_z, &z_full[zs], sZ + zs * kRpZBytes + i * 4096, t0 + 32 * i, b * kRtLatent + kc * kRpKc);
+      }
+    }
+  } else if (warp == 10) {
+    if (lane == 0) {
+      for (uint32_t it = 0; it < total_steps; ++it) {
+        const int kc = it % kNumKc;
+        const uint32_t ls = it % kRpLwStages;
+        mbar_wait(&lw_empty[ls], ((it / kRpLwStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(&w_full[ls], 2 * kRpWBytes);
+        tma_load_2d(&tma_whi, &w_full[ls], sLw + ls * kRpLwBytes + kRpZBytes, kc * kRpKc, 0);
+        tma_load_2d(&tma_wlo, &w_full[ls], sLw + ls * kRpLwBytes + kRpZBytes + kRpWBytes, kc * kRpKc, 0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(kRtFrames, kRtE, /*a_mn_major=*/1, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 128;
-        for (int kc = 0; kc < kNumKc; ++kc) {
-          mbar_wait(&full_bar[stage], phase);   // weights (TMA) landed
-          mbar_wait(&split_bar[stage], phase);  // z tile rewritten as hi / lo by the split warps
+      for (uint32_t it = 0; it < total_steps; ++it) {
+        const uint32_t tl = it / kNumKc, kc = it % kNumKc;
+        const uint32_t acc = tl & 1;
+        const uint32_t zs = it % kRpZStages, ls = it % kRpLwStages;
+        if (kc == 0) {
+          mbar_wait(&tempty_bar[acc], ((tl >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + stage * kRpStageBytes);
+        }
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        mbar_wait(&w_full[ls], (it / kRpLwStages) & 1);     // weights (TMA) landed
+        mbar_wait(&split_bar[ls], (it / kRpLwStages) & 1);  // z tile rewritten as hi (in place) / lo by the split warps
+        tc_fence_after();
+        const uint32_t zh = smem_u32(sZ + zs * kRpZBytes);
+        const uint32_t lw = smem_u32(sLw + ls * kRpLwBytes);
 #pragma unroll
-          for (int k = 0; k < kRpKc / 8; ++k) {
-            // A (MN-major, 128B swizzle with 32 B atoms): 8 channels = two 512 B K-groups inside each 32-frame box; the four
-            // boxes (32-frame atoms along M) are kRpZBytes / 4 apart. B (K-major): +32 B per 8-element K step inside the 128 B
-            // swizzle row.
-            const uint64_t a_hi = umma_desc_sw128_base32(st + k * 1024, p.a_lbo, p.a_sbo);
-            const uint64_t a_lo = umma_desc_sw128_base32(st + kRpZBytes + k * 1024, p.a_lbo, p.a_sbo);
-            const uint64_t b_hi = umma_desc_sw128(st + 2 * kRpZBytes, 16, 1024) + 2 * k;
-            const uint64_t b_lo = umma_desc_sw128(st + 2 * kRpZBytes + kRpWBytes, 16, 1024) + 2 * k;
-            umma_ss_tf32(d_tmem, a_lo, b_hi, idesc, (kc | k) != 0 ? 1u : 0u);
-            umma_ss_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-            umma_ss_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
-          }
-          umma_commit(&empty_bar[stage]);
-          if (++stage == kRpStages) {
-            stage = 0;
-            phase ^= 1;
+        for (int k = 0; k < ((p.dbg & 2) ? 0 : kRpKc / 8); ++k) {
+          // A (MN-major, 128B swizzle with 32 B atoms): 8 channels = two 512 B K-groups inside each 32-frame box (4 KB); the
+          // four boxes of one 128-frame accumulator are 4 KB apart. B (K-major): +32 B per 8-element K step inside the 128 B
+          // swizzle row.
+          const uint64_t b_hi = umma_desc_sw128(lw + kRpZBytes, 16, 1024) + 2 * k;
+          const uint64_t b_lo = umma_desc_sw128(lw + kRpZBytes + kRpWBytes, 16, 1024) + 2 * k;
+#pragma unroll
+          for (int m = 0; m < kRpFrames / 128; ++m) {
+            const uint64_t a_hi = umma_desc_sw128_base32(zh + m * 16384 + k * 1024, p.a_lbo, p.a_sbo);
+            const uint64_t a_lo = umma_desc_sw128_base32(lw + m * 16384 + k * 1024, p.a_lbo, p.a_sbo);
+            umma_ss_tf32(d_tmem + m * 128, a_lo, b_hi, idesc, (kc | k) != 0 ? 1u : 0u);
+            umma_ss_tf32(d_tmem + m * 128, a_hi, b_lo, idesc, 1u);
+            umma_ss_tf32(d_tmem + m * 128, a_hi, b_hi, idesc, 1u);
           }
         }
-        umma_commit(&tfull_bar[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        umma_commit(&z_empty[zs]);
+        umma_commit(&lw_empty[ls]);
+        if (kc == kNumKc - 1) umma_commit(&tfull_bar[acc]);
       }
     }
   } else if (warp < 6) {
     // split warps: z tile (as TMA wrote it) -> hi = tf32(z) in place, lo = tf32(z - hi) at the same offset of the lo tile
     const int st_tid = threadIdx.x - 64;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      for (int kc = 0; kc < kNumKc; ++kc) {
-        mbar_wait(&full_bar[stage], phase);
-        const uint32_t zh = smem_u32(smem + stage * kRpStageBytes) + st_tid * 16;
+    for (uint32_t it = 0; it < total_steps; ++it) {
+      const uint32_t zs = it % kRpZStages, ls = it % kRpLwStages;
+      mbar_wait(&z_full[zs], (it / kRpZStages) & 1);
+      mbar_wait(&lw_empty[ls], ((it / kRpLwStages) & 1) ^ 1);
+      const uint32_t zh = smem_u32(sZ + zs * kRpZBytes) + st_tid * 16;
+      const uint32_t zl = smem_u32(sLw + ls * kRpLwBytes) + st_tid * 16;
 #pragma unroll
-        for (int i = 0; i < static_cast<int>(kRpZBytes) / (128 * 16); ++i) {
-          const float4 v = lds128(zh + i * 2048);
-          float4 h, l;
-          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-          sts128(zh + i * 2048, h);
-          sts128(zh + kRpZBytes + i * 2048, l);
-        }
-        fence_proxy_async_smem();
-        mbar_arrive(&split_bar[stage]);
-        if (++stage == kRpStages) {
-          stage = 0;
-          phase ^= 1;
-        }
+      for (int i = 0; i < ((p.dbg & 1) ? 0 : static_cast<int>(kRpZBytes) / (128 * 16)); ++i) {
+        const float4 v = lds128(zh + i * 2048);
+        float4 h, l;
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+        sts128(zh + i * 2048, h);
+        sts128(zl + i * 2048, l);
       }
+      fence_proxy_async_smem();
+      mbar_arrive(&split_bar[ls]);
     }
-  } else {
-    // epilogue warps: thread <-> frame (TMEM lane), 96 accumulator columns + bias -> E[frame, 96]
+  } else if (warp < 10) {
+    // epilogue warps: thread <-> TMEM lane = frame of each 128-row accumulator, 96 columns + bias -> E[frame, 96]
     const int quad = warp & 3;
     const int f = quad * 32 + lane;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int b = tile / tiles_per_b, t = (tile % tiles_per_b) * kRtFrames + f;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 128;
-      mbar_wait(&tfull_bar[acc], acc_phase);
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int tile = blockIdx.x + tl * gridDim.x;
+      const int acc = tl & 1;
+      const int b = tile / tiles_per_b;
+      mbar_wait(&tfull_bar[acc], (tl >> 1) & 1);
       tc_fence_after();
-      uint32_t r0[32], r1[32], r2[32];
-      tmem_ld_32x32(taddr, r0);
-      tmem_ld_32x32(taddr + 32, r1);
-      tmem_ld_32x32(taddr + 64, r2);
-      tmem_ld_wait_dep(r0);
-      tmem_ld_wait_dep(r1);
-      tmem_ld_wait_dep(r2);
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-      if (t < p.T) {
-        float4* o = reinterpret_cast<float4*>(p.e_out + (static_cast<long long>(b) * p.T + t) * kRtE);
-        const float4* b4 = reinterpret_cast<const float4*>(p.b_in);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bb = __ldg(b4 + i);
-          o[i] = make_float4(__uint_as_float(r0[4 * i]) + bb.x, __uint_as_float(r0[4 * i + 1]) + bb.y,
-                             __uint_as_float(r0[4 * i + 2]) + bb.z, __uint_as_float(r0[4 * i + 3]) + bb.w);
+      for (int m = 0; m < kRpFrames / 128; ++m) {
+        const int t = (tile % tiles_per_b) * kRpFrames + m * 128 + f;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + m * 128;
+        uint32_t r0[32], r1[32], r2[32];
+        tmem_ld_32x32(taddr, r0);
+        tmem_ld_32x32(taddr + 32, r1);
+        tmem_ld_32x32(taddr + 64, r2);
+        tmem_ld_wait_dep(r0);
+        tmem_ld_wait_dep(r1);
+        tmem_ld_wait_dep(r2);
+        if (m == kRpFrames / 128 - 1) {
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[acc]);
         }
+        if (t < p.T) {
+          float4* o = reinterpret_cast<float4*>(p.e_out + (static_cast<long long>(b) * p.T + t) * kRtE);
+          const float4* b4 = reinterpret_cast<const float4*>(p.b_in);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bb = __ldg(b4 + 8 + i);
-          o[8 + i] = make_float4(__uint_as_float(r1[4 * i]) + bb.x, __uint_as_float(r1[4 * i + 1]) + bb.y,
-                                 __uint_as_float(r1[4 * i + 2]) + bb.z, __uint_as_float(r1[4 * i + 3]) + bb.w);
-        }
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = __ldg(b4 + i);
+            o[i] = make_float4(__uint_as_float(r0[4 * i]) + bb.x, __uint_as_float(r0[4 * i + 1]) + bb.y,
+                               __uint_as_float(r0[4 * i + 2]) + bb.z, __uint_as_float(r0[4 * i + 3]) + bb.w);
+          }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bb = __ldg(b4 + 16 + i);
-          o[16 + i] = make_float4(__uint_as_float(r2[4 * i]) + bb.x, __uint_as_float(r2[4 * i + 1]) + bb.y,
-                                  __uint_as_float(r2[4 * i + 2]) + bb.z, __uint_as_float(r2[4 * i + 3]) + bb.w);
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = __ldg(b4 + 8 + i);
+            o[8 + i] = make_float4(__uint_as_float(r1[4 * i]) + bb.x, __uint_as_float(r1[4 * i + 1]) + bb.y,
+                                   __uint_as_float(r1[4 * i + 2]) + bb.z, __uint_as_float(r1[4 * i + 3]) + bb.w);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = __ldg(b4 + 16 + i);
+            o[16 + i] = make_float4(__uint_as_float(r2[4 * i]) + bb.x, __uint_as_float(r2[4 * i + 1]) + bb.y,
+                                    __uint_as_float(r2[4 * i + 2]) + bb.z, __uint_as_float(r2[4 * i + 3]) + bb.w);
+          }
         }
       }
     }
@@ -218,7 +235,7 @@ rvq_project_kernel(const __grid_constant__ CUtensorMap tma_z, const __grid_const
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<256>(tmem_base);
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ level search

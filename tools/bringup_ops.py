@@ -417,7 +417,16 @@ def test_rvqtime():
         L.lib().edm_rvq_tc_debug(4096, 512, 0, 0)
         print(f"rvq tcgen05 B={B} T={T}: total {ms:.3f} ms (search alone {ms_s:.3f} ms [no-compare floor {ms_p:.3f}], projection ~{ms - ms_s:.3f} ms) = {B * T / ms / 1e3:.1f} Mframes/s, "
               f"{B * T * 4192 / ms / 1e6:.0f} GB/s algorithmic", flush=True)
+    for (B, T) in [(32, 3000), (375, 256), (94, 1024), (12, 8192)]:
+        z = torch.randn(B, 1024, T, device=dev)
+        L.lib().edm_rvq_tc_debug(4096, 512, 1, 1)
+        ms_s = timeit(lambda: q.encode(z), iters=10, warm=3)
+        for name, dbg in (("full", 0), ("no split math", 1), ("no MMA", 2), ("TMA stream only", 3)):
+            L.lib().edm_rvq_tc_debug(4096, 512, dbg << 4, 1)
+            ms_d = timeit(lambda: q.encode(z), iters=10, warm=3)
+            print(f"   projection probe B={B} T={T} [{name}]: {ms_d - ms_s:.3f} ms = {B * T * 4096 / (ms_d - ms_s) / 1e6:.0f} GB/s", flush=True)
     z = torch.randn(32, 1024, 3000, device=dev)
+    L.lib().edm_rvq_tc_debug(4096, 512, 0, 0)
     ms_old = timeit(lambda: q.encode(z, impl="mma_sync"), iters=5, warm=2)
     print(f"rvq mma.sync kernel B=32 T=3000: {ms_old:.3f} ms", flush=True)
 
