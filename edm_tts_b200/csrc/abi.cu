@@ -12,6 +12,7 @@
 #include "../../include/edm_s2a.h"
 #include "attention.cuh"
 #include "elementwise.cuh"
+#include "conv_stream.cuh"
 #include "gemm.cuh"
 #include "rvq.cuh"
 #include "rvq_tc.cuh"
@@ -247,19 +248,46 @@ int launch_ln(const LnParams& p, cudaStream_t st) {
 }
 
 // glu_input: the kernel reads [B*N, 4096] and applies the GLU itself; otherwise the input is the already gated [B*N, 2048]
+// (the decoder's path: the GLU runs in the pointwise-conv GEMM epilogue) and the streaming kernel of conv_stream.cuh is used.
 int launch_conv(const ConvModParams& p, bool glu_input, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     EDM_CUDA(cudaFuncSetAttribute(conv_module_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
     EDM_CUDA(cudaFuncSetAttribute(conv_module_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
+    EDM_CUDA(cudaFuncSetAttribute(conv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCsSmemBytes));
     attr_set = true;
   }
-  dim3 grid((p.N + kConvTT - 1) / kConvTT, p.B);
+  if (p.B <= 0 || p.N <= 0) return 0;
   ProfScope prof(PK_CONV, static_cast<double>(p.B) * p.N * (glu_input ? 12288.0 : 8192.0), st);
-  if (glu_input)
-    conv_module_kernel<true><<<grid, kConvThreads, kConvSmemBytes, st>>>(p);
-  else
-    conv_module_kernel<false><<<grid, kConvThreads, kConvSmemBytes, st>>>(p);
+  static const bool legacy = getenv("EDM_CONV_LEGACY") != nullptr;  // bring-up switch: tiled kernel on the gated input as well
+  if (glu_input || legacy) {
+    dim3 grid((p.N + kConvTT - 1) / kConvTT, p.B);
+    if (glu_input)
+      conv_module_kernel<true><<<grid, kConvThreads, kConvSmemBytes, st>>>(p);
+    else
+      conv_module_kernel<false><<<grid, kConvThreads, kConvSmemBytes, st>>>(p);
+  } else {
+    // split every sequence into runs so that the persistent CTAs are evenly loaded and few halo rows are re-read
+    // (run lengths are multiples of the 16-token statistics group, so only a sequence's last run has a partial group)
+    const int sms = num_sms();
+    int best_len = (p.N + 15) / 16 * 16;
+    double best = -1.0;
+    for (int len = 16; len <= (p.N + 15) / 16 * 16; len += 16) {
+      const long long units = static_cast<long long>(p.B) * ((p.N + len - 1) / len);
+      const long long rounds = (units + sms - 1) / sms;
+      const double eff = static_cast<double>(p.B) * p.N / (static_cast<double>(rounds * sms) * len) * len / (len + 4.0);
+      if (eff > best + 1e-9) {
+        best = eff;
+        best_len = len;
+      }
+    }
+    ConvStreamParams q;
+    q.in = p.in; q.out = p.out; q.dw_w = p.dw_w; q.dw_b = p.dw_b; q.cln_w = p.cln_w; q.B = p.B; q.N = p.N;
+    q.run_len = best_len;
+    q.runs_per_seq = (p.N + q.run_len - 1) / q.run_len;
+    const long long units = static_cast<long long>(p.B) * q.runs_per_seq;
+    conv_stream_kernel<<<static_cast<unsigned>(units < sms ? units : sms), kCsThreads, kCsSmemBytes, st>>>(q);
+  }
   EDM_LAUNCH_CHECK("conv_module");
   return 0;
 }

@@ -188,7 +188,7 @@ def conv_ref(h, dw_w, dw_b, cln_w, B, N):
 
 def test_conv():
     torch.manual_seed(0)
-    for (B, N) in [(2, 37), (3, 150), (2, 500)]:
+    for (B, N) in [(2, 37), (3, 150), (2, 500), (1, 1), (5, 3), (64, 500), (7, 1650)]:
         h = bf(torch.randn(B * N, 4096, device=dev))
         dw_w = rb(torch.randn(2048, 5, device=dev) * 0.4)
         dw_b = torch.randn(2048, device=dev) * 0.1
@@ -198,6 +198,15 @@ def test_conv():
         ref = conv_ref(h, dw_w, dw_b, cln_w, B, N)
         d = (out.float() - ref).abs()
         print(f"conv B={B} N={N}: max_abs_err={d.max().item():.3e} mean={d.mean().item():.3e} frac>0.05={(d > 0.05).float().mean().item():.2e}", flush=True)
+        # decoder path: GLU already applied (as the GEMM epilogue does) -> streaming kernel
+        x = h.float().view(B * N, 4096)
+        gated = bf(x[:, :2048] * rb(torch.sigmoid(x[:, 2048:])))
+        out2 = torch.full_like(out, float("nan"))
+        L.check(L.lib().edm_conv_module(L.ptr(gated), 0, L.ptr(out2), L.ptr(dw_w), L.ptr(dw_b), L.ptr(cln_w), B, N, L.stream_ptr()))
+        d2 = (out2.float() - ref).abs()
+        same = (out2 == out).float().mean().item()
+        print(f"conv (gated, streaming) B={B} N={N}: max_abs_err={d2.max().item():.3e} mean={d2.mean().item():.3e} frac>0.05={(d2 > 0.05).float().mean().item():.2e} "
+              f"bit-identical to the tiled kernel: {same:.6f} nan={torch.isnan(out2.float()).sum().item()}", flush=True)
     B, N = 64, 500
     h = bf(torch.randn(B * N, 4096, device=dev))
     out = torch.empty(B * N, 2048, device=dev, dtype=torch.bfloat16)
