@@ -73,6 +73,18 @@ def peaks():
     return 1400.0, 6650.0, "fallback"
 
 
+def ncu_traffic():
+    """DRAM bytes per GEMM launch from the committed ncu --set full capture of this same command (tools/gpu_ncu_bench.sh ->
+    tools/ncu_traffic.py -> profiles/ncu_traffic_r01.json); None when the file is missing."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        t = json.load(f)
+    e = t.get("gemm_bf16_tn_pair_kernel (all captured epilogues)")
+    return (e["traffic_bytes_per_launch"], "profiles/ncu_traffic_r01.json") if e else (None, None)
+
+
 def cpu_oracle_fps(B, T, steps, repeats, threads):
     """Times the oracle (CPU restatement of the reference, fp32) on the host cores."""
     import torch
@@ -234,6 +246,13 @@ def main():
     value = frames / (ms_total * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
     tf_peak, hbm_peak, peak_kind = peaks()
+    traffic, traffic_src = ncu_traffic()
+    # algorithmic bytes of the 8 GEMMs of one conformer block at M = B*T rows (operands read once, outputs written once,
+    # the fp32 residual stream read + written by the three residual GEMMs): DESIGN.md section 4
+    M = B * T
+    blk_bytes = (M * 1024 * 2 + 4096 * 1024 * 2 + M * 4096 * 2) * 2 + (M * 4096 * 2 + 1024 * 4096 * 2 + M * 1024 * 8) * 2 \
+        + (M * 1024 * 2 + 3072 * 1024 * 2 + M * 3072 * 2) + (M * 1024 * 2 + 1024 * 1024 * 2 + M * 1024 * 8) \
+        + (M * 1024 * 2 + 4096 * 1024 * 2 + M * 2048 * 2) + (M * 2048 * 2 + 1024 * 2048 * 2 + M * 1024 * 8)
     gemm_tflops = pw[0] / (pm[0] * 1e-3) / 1e12 if pm[0] > 0 else 0.0
     kernels = {
         "gemm_tcgen05": {"launches": pc[0], "ms": pm[0], "tflops": gemm_tflops},
@@ -275,13 +294,17 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches) * world,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_pair_kernel (tcgen05 cta_group::2; all conformer / head GEMMs of the timed region)",
-                     "achieved": gemm_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tf_peak, "traffic": None,
+                     "achieved": gemm_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tf_peak, "traffic": traffic,
+                     "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean of the 8 GEMMs of one block)",
+                     "traffic_source": traffic_src, "algorithmic_bytes_per_launch": blk_bytes / 8,
                      "peak_kind": f"{peak_kind} bf16 sustained", "gemm_share_of_step": pm[0] / ms_prof, "instrumented_ms_per_step": ms_prof / args.steps},
         "kernels": kernels,
         "secondary": {"metric": "dac_rvq_encode_frames_per_s", "value": 32 * 3000 / (rvq_ms * 1e-3), "unit": "frames/s", "ms": rvq_ms,
                       "workload": "DAC RVQ encode, z [32, 1024, 3000] fp32 (dump_tokens batch, BASELINE config 4), 12 codebooks, per GPU",
                       "hbm_gbs": 32 * 3000 * (4096 + 96) / (rvq_ms * 1e-3) / 1e9, "frac_hbm": 32 * 3000 * (4096 + 96) / (rvq_ms * 1e-3) / 1e9 / hbm_peak,
-                      "note": "3xTF32 mma.sync contractions + exhaustive 1024-code search; bound by the legacy tensor path / compare ALU work, not HBM"},
+                      "note": "tcgen05 kind::tf32: 3xTF32 projection GEMM (z read once through MN-major TMA boxes) + 12-level search with the "
+                              "[128 frames x 1024 codes] score tiles in TMEM; the search is bound by the per-score compare work (ALU pipe) and "
+                              "TMEM reads, the projection by the L2->SM fabric, not by HBM"},
         "model_flops_utilisation": {"algorithmic_tflops": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12,
                                     "frac_of_peak": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12 / tf_peak},
     }

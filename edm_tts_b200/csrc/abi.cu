@@ -181,19 +181,39 @@ bool gemm_use_pairs() {
 // rows of a B-operand TMA box: a CTA of a pair loads half of the 256-row weight tile
 uint32_t gemm_b_box_rows() { return gemm_use_pairs() ? kGemmBN / 2 : kGemmBN; }
 
+bool gemm_resid_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EDM_RESID_TMA");  // bring-up switch: 0 = residual add as red.global.add.v4.f32 from registers
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+
 template <int EPI>
 int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    if (EPI == EPI_RESID_F32)
+      EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI_RESID_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     attr_set = true;
   }
   ProfScope prof(PK_GEMM, 2.0 * p.M * p.N * p.K, st);
   if (gemm_use_pairs()) {
     const int tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (p.N / kGemmBN);
     const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-    gemm_bf16_tn_pair_kernel<EPI><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, p);
+    // short-K residual GEMMs are epilogue-bound: their add leaves as TMA reduce boxes (0.113 -> 0.081 ms at K = 1024); at
+    // K = 4096 the mainloop hides the register-issued reductions and the 6-stage ring is worth more (0.202 vs 0.208 ms)
+    if (EPI == EPI_RESID_F32 && gemm_resid_tma() && p.K <= 2048 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 4) % 16 == 0) {
+      CUtensorMap mc;
+      if (int rc = make_tmap_f32_2d(&mc, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+      gemm_bf16_tn_pair_kernel<EPI_RESID_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
+    } else {
+      gemm_bf16_tn_pair_kernel<EPI><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, ma, p);
+    }
     EDM_LAUNCH_CHECK("gemm_bf16_tn_pair");
     return 0;
   }

@@ -167,7 +167,9 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stream_kernel(const ConvSt
 #pragma unroll
     for (int j = 0; j < 5; ++j) win[j][0] = win[j][1] = 0ull;
 
-    // one input row: token tr (zero outside the sequence) -> window slot 4
+    auto chunk_wait = [&](uint32_t chunk) { cs_wait(bar0 + (chunk % (kCsRing / kCsChunk)) * 8, (chunk / (kCsRing / kCsChunk)) & 1); };
+    // one input row: token tr (zero outside the sequence) -> window slot 4. checked = false: the row exists and its chunk
+    // has already been waited for (full groups wait for their 16 rows up front, which keeps their unrolled body branch-free)
     auto pull_row = [&](int tr, auto checked) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stream_kernel(const ConvSt
         win[j][1] = win[j + 1][1];
       }
       if (!decltype(checked)::value || (tr >= run.t_lo && tr < run.t_hi)) {
-        if ((q & (kCsChunk - 1)) == 0) cs_wait(bar0 + ((q / kCsChunk) % (kCsRing / kCsChunk)) * 8, (q / kCsRing) & 1);
+        if (decltype(checked)::value && (q & (kCsChunk - 1)) == 0) chunk_wait(q / kCsChunk);
         uint2 v;
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(row0 + (q % kCsRing) * kCsRowBytes));
         win[4][0] = f2_from_bf16x2(v.x);
@@ -194,6 +196,9 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stream_kernel(const ConvSt
     auto group = [&](int tg, auto full) {
       constexpr bool kFull = decltype(full)::value;
       uint32_t u[kCsGroup][2];
+      if (kFull) {  // rows q .. q+15 were requested a group ago: in steady state these waits fall through
+        for (uint32_t c = q / kCsChunk; c <= (q + kCsGroup - 1) / kCsChunk; ++c) chunk_wait(c);
+      }
       // ---- phase 1: conv + Swish; park (sum, sumsq) of this thread's 4 channels per token
 #pragma unroll
       for (int o = 0; o < kCsGroup; ++o) {

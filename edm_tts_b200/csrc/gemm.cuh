@@ -25,6 +25,8 @@ enum EpiKind : int {
   EPI_F32 = 4,         // out_f32 = acc + bias                                                   (logits heads)
   EPI_GLU_BF16 = 5,    // per 64 columns: first 32 = value, last 32 = gate (weights interleaved at pack time);
                        // out_bf16[., N/2] = bf16(bf16(value) * bf16(sigmoid(bf16(gate))))       (conv module pointwise-1 + GLU)
+  EPI_RESID_TMA = 6,   // EPI_RESID_F32 with the add carried out as TMA reduce-add boxes (pair kernel only; chosen by the
+                       // launcher, not part of the ABI): 128 B rows reach L2 as whole lines instead of 16 B reductions
 };
 
 struct GemmParams {
@@ -337,9 +339,16 @@ constexpr int kPairStages = 6;
 constexpr uint32_t kPairStageBytes = 2 * kGemmABytes;  // A (128 x 64) + half of B (128 x 64)
 constexpr uint32_t kPairSmemBytes = kPairStages * kPairStageBytes + kGemmMaxN * 4 + 1024 + 256;
 
+// EPI_RESID_TMA trades two of the six ring stages for a 4 KB staging box per epilogue warp (same shared-memory total).
+constexpr int kPairStagesTma = 4;
+constexpr uint32_t kPairStagingBytes = 32 * 32 * 4;  // 32 rows x 32 fp32 columns
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                         const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
+  constexpr int kSt = (EPI == EPI_RESID_TMA) ? kPairStagesTma : kPairStages;
+  static_assert(kPairStagesTma * kPairStageBytes + kGemmEpiWarps * kPairStagingBytes == kPairStages * kPairStageBytes, "smem budget");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   float* s_bias = reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes);
@@ -362,7 +371,7 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    for (int s = 0; s < kPairStages; ++s) {
+    for (int s = 0; s < kSt; ++s) {
       mbar_init(&full_bar[s], 1);   // CTA 0's expect_tx arrive; the bytes of both CTAs land here
       mbar_init(&empty_bar[s], 1);  // one multicast commit per use
     }
@@ -396,7 +405,7 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kPairStageBytes);
           tma_load_2d_pair(&tma_a, &full_bar[stage], sa, p.a_k_offset + kb * kGemmBK, m_blk * 2 * kGemmBM + rank * kGemmBM);
           tma_load_2d_pair(&tma_b, &full_bar[stage], sb, kb * kGemmBK, p.b_row_offset + n_blk * kGemmBN + rank * (kGemmBN / 2));
-          if (++stage == kPairStages) {
+          if (++stage == kSt) {
             stage = 0;
             phase ^= 1;
           }
@@ -423,7 +432,7 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
 #pragma unroll
           for (int k = 0; k < kGemmBK / 16; ++k) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit_pair(&empty_bar[stage]);
-          if (++stage == kPairStages) {
+          if (++stage == kSt) {
             stage = 0;
             phase ^= 1;
           }
@@ -476,6 +485,35 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      if constexpr (EPI == EPI_RESID_TMA) {
+        // x[rows, cols] += scale * bf16(acc + bias): the warp's 32 x 64 slice leaves as two 32 x 32 fp32 boxes through its
+        // 4 KB staging buffer (128B-swizzled rows); rows beyond M are clipped by the tensor map
+        uint8_t* stg = smem + kSt * kPairStageBytes + (warp - 2) * kPairStagingBytes;
+        const uint32_t stg_row = smem_u32(stg) + lane * 128;
+        const int sw = lane & 7;
+        const int row0 = m_blk * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM + quad * 32;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t b4 = smem_u32(s_bias + col0 + 32 * h);
+          if (lane == 0) bulk_wait_group_read0();  // the previous box has been read out of the staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = lds128(b4 + 16 * i);
+            const uint32_t* r = h == 0 ? r0 : r1;
+            sts128(stg_row + ((i ^ sw) << 4),
+                   make_float4(p.scale * bf16_round(__uint_as_float(r[4 * i + 0]) + b.x), p.scale * bf16_round(__uint_as_float(r[4 * i + 1]) + b.y),
+                               p.scale * bf16_round(__uint_as_float(r[4 * i + 2]) + b.z), p.scale * bf16_round(__uint_as_float(r[4 * i + 3]) + b.w)));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tma_c, stg, col0 + 32 * h, row0);
+            bulk_commit_group();
+          }
+        }
+        continue;
+      }
       if (row >= p.M) continue;
       if constexpr (EPI == EPI_QKV_ROPE) {
         const int tr = quad * 32 + lane;
@@ -518,6 +556,9 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     }
   }
 
+  if constexpr (EPI == EPI_RESID_TMA) {
+    if (warp >= 2 && lane == 0) bulk_wait_group0();  // staging buffers must outlive the reductions that read them
+  }
   tc_fence_before();
   cluster_sync_all();  // the peer may still be reading our shared memory / signalling our barriers
   if (warp == 1) tmem_dealloc_pair<512>(tmem_base);

@@ -440,8 +440,53 @@ def test_rvqtime():
     print(f"rvq mma.sync kernel B=32 T=3000: {ms_old:.3f} ms", flush=True)
 
 
+def test_gemmsus():
+    """Sustained (power-capped) throughput of single GEMM shapes run back to back for ~2 s each, ours vs torch.matmul (cuBLAS),
+    with the SM clock sampled through NVML: separates 'kernel efficiency per clock' from 'energy per FLOP at the 1 kW cap'."""
+    import pynvml as nv
+    nv.nvmlInit()
+    h = nv.nvmlDeviceGetHandleByIndex(0)
+    torch.manual_seed(0)
+    M = 32000
+    shapes = [(4096, 1024, L.EPI_SWISH_BF16), (1024, 4096, L.EPI_RESID_F32), (4096, 1024, L.EPI_GLU_BF16), (3072, 1024, L.EPI_BF16)]
+    only = sys.argv[2] if len(sys.argv) > 2 else "both"
+    for (N, K, epi) in shapes:
+        a = bf(torch.randn(M, K, device=dev))
+        b = bf(torch.randn(N, K, device=dev) / math.sqrt(K))
+        bias = torch.randn(N, device=dev)
+        out = torch.zeros(M, N // 2 if epi == L.EPI_GLU_BF16 else N, device=dev, dtype=torch.float32 if epi == L.EPI_RESID_F32 else torch.bfloat16)
+        fns = {"ours": lambda: gemm_call(a, b, epi, bias, out, scale=0.5), "cublas": lambda: torch.matmul(a, b.T)}
+        for name, fn in fns.items():
+            if only not in ("both", name):
+                continue
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            clocks, power = [], []
+            t_end = time.time() + 2.0
+            iters_done, e_mid, n_mid = 0, None, 0
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            while time.time() < t_end:
+                if e_mid is None and time.time() > t_end - 1.0:   # time only the second half (clocks have settled)
+                    e0.record()
+                    e_mid, n_mid = True, iters_done
+                for _ in range(50):
+                    fn()
+                iters_done += 50
+                torch.cuda.synchronize()
+                clocks.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / max(1, iters_done - n_mid)
+            tail = clocks[len(clocks) // 2:]
+            print(f"sustained {name:6s} N={N} K={K} epi={epi}: {2 * M * N * K / ms / 1e9:7.1f} TFLOP/s, {ms * 1e3:.1f} us, SM clock ~{sorted(tail)[len(tail) // 2]} MHz, "
+                  f"power ~{sorted(power)[len(power) // 2]:.0f} W", flush=True)
+
+
 if __name__ == "__main__":
     t0 = time.time()
-    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvq": test_rvq, "rvqtc": test_rvqtc, "rvqtime": test_rvqtime}[sys.argv[1]]()
+    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvq": test_rvq, "rvqtc": test_rvqtc, "rvqtime": test_rvqtime, "gemmsus": test_gemmsus}[sys.argv[1]]()
     torch.cuda.synchronize()
     print(f"[{sys.argv[1]}] done in {time.time() - t0:.1f}s", flush=True)
