@@ -16,6 +16,14 @@ from . import _lib as L
 from .config import InjectionConformerConfig
 from .weights import pack_rvq_weights, pack_s2a_weights
 
+class InjectionConformerOutput(dict):
+    """modeling_injection_conformer.py:18-22 (a transformers ModelOutput there): attribute and key access."""
+
+    def __init__(self, loss=None, output_acoustic_codes=None, target_acoustic_codes=None):
+        super().__init__(loss=loss, output_acoustic_codes=output_acoustic_codes, target_acoustic_codes=target_acoustic_codes)
+        self.__dict__ = self
+
+
 MAX_CHUNK = 64  # sequences decoded per bound workspace (larger batches are processed in chunks; utterances are independent)
 
 
@@ -43,7 +51,8 @@ class _Encoder:
         B, N, _ = x.shape
         P = self._prompt_len(x, mask_time_indices)
         m._bind(B, N - P, P)
-        L.check(L.lib().edm_s2a_first_level(m._ctx, L.ptr(x.float().contiguous()), L.stream_ptr()), "first_level")
+        xf = x.float().contiguous()
+        L.check(L.lib().edm_s2a_first_level(m._ctx, L.ptr(xf), L.stream_ptr()), "first_level")
         return m._view("logits", (B, 1, N - P, m.num_codevectors), torch.float32).clone()
 
     def forward(self, x, mask=None, injections=None, acoustic_model=None, mask_time_indices=None, *, prompt_codes=None,
@@ -62,7 +71,8 @@ class _Encoder:
             m._load_prompt_codes(prompt_codes)
         codes = torch.empty(B, m.num_quantizers, N - P, device=x.device, dtype=torch.int64)
         fc = None if forced_coarse is None else forced_coarse.to(torch.int32).contiguous()
-        L.check(L.lib().edm_s2a_full_pass(m._ctx, L.ptr(x.float().contiguous()), L.ptr(fc), L.ptr(codes), L.stream_ptr()), "full_pass")
+        xf = x.float().contiguous()
+        L.check(L.lib().edm_s2a_full_pass(m._ctx, L.ptr(xf), L.ptr(fc), L.ptr(codes), L.stream_ptr()), "full_pass")
         n_inj = len(m.injection_layers)
         coarse = m._view("coarse_logits", (4, B, N - P, m.num_codevectors), torch.float32)[:n_inj].permute(1, 0, 2, 3)
         fine = m._view("fine_logits", (B, N - P, m.num_quantizers - n_inj, m.num_codevectors), torch.float32).permute(0, 2, 1, 3)
@@ -76,7 +86,8 @@ class _Encoder:
         B, n, d = inp.shape
         z = torch.empty(B * n, d, device=inp.device, dtype=torch.bfloat16)
         w = m._w
-        L.check(L.lib().edm_layernorm(L.ptr(inp.float().contiguous()), 0, B * n, L.ptr(w["tl_ln_w"]), L.ptr(w["tl_ln_b"]), None, None, None,
+        xf = inp.float().contiguous()
+        L.check(L.lib().edm_layernorm(L.ptr(xf), 0, B * n, L.ptr(w["tl_ln_w"]), L.ptr(w["tl_ln_b"]), None, None, None,
                                       L.ptr(z), 1, 0, 1e-5, L.stream_ptr()), "layernorm")
         out = torch.empty(B * n, m.num_codevectors, device=inp.device, dtype=torch.float32)
         head = w["head_w"][idx * m.num_codevectors:(idx + 1) * m.num_codevectors]
@@ -300,9 +311,68 @@ class InjectionConformerModel:
         tr["codes"] = codes
         return tr
 
-    def forward(self, acoustic_tokens, semantic_tokens):
-        """Training forward (modeling_injection_conformer.py:76-128) is outside the accelerated decode path."""
+    def cosine_schedule_mask(self, feature_length, batch_size):
+        """modeling_injection_conformer.py:62-74: one masking probability cos(u), u ~ U(0, pi/2), per sequence."""
+        import math
+
+        u = torch.empty(batch_size, device=self.device).uniform_(0, math.pi / 2)
+        p = torch.cos(u).unsqueeze(1).expand(batch_size, feature_length)
+        return torch.bernoulli(p).bool()
+
+    @torch.no_grad()
+    def forward(self, acoustic_tokens, semantic_tokens, *, mask_time_indices=None):
+        """InjectionConformerModel.forward (modeling_injection_conformer.py:76-128) in eval mode: masked encoder input,
+        ground-truth coarse injections, 12-level logits, mean cross-entropy over the masked positions (all positions with
+        loss_all) and the arg-max codes at the same positions. No dropout, no autograd: this is the validation-loss path,
+        composed from the decoder's own kernels; `mask_time_indices` replaces the cosine_schedule_mask draw (parity tests)."""
         assert acoustic_tokens.shape[-1] == semantic_tokens.shape[-1], "Acoustic and semantic tokens must have same length"
-        raise NotImplementedError("training forward is not part of the B200 decode path (SURVEY.md section 8: out of scope)")
+        dev, lib = self.device, L.lib()
+        ac = acoustic_tokens.to(dev)
+        st = semantic_tokens.to(dev)
+        B, Q, T = ac.shape
+        if Q != self.num_quantizers:
+            raise ValueError(f"acoustic_tokens must carry {self.num_quantizers} levels, got {Q}")
+        mask = (self.cosine_schedule_mask(T, B) if mask_time_indices is None else mask_time_indices.to(dev)).bool()
+        n_inj, V = len(self.injection_layers), self.num_codevectors
+        logp = torch.empty(B, Q, T, device=dev, dtype=torch.float32)          # log p(target) per (b, q, t)
+        out_codes = torch.empty(B, Q, T, device=dev, dtype=torch.int64)
+        s_ = L.stream_ptr()
+        for b0 in range(0, B, MAX_CHUNK):
+            b1 = min(B, b0 + MAX_CHUNK)
+            nb, sl = b1 - b0, slice(b0, b1)
+            self._bind(nb, T, 0)
+            sem = st[sl].to(torch.int32).contiguous()
+            tgt = ac[sl].to(torch.int32).contiguous()
+            L.check(lib.edm_s2a_build_input(self._ctx, L.ptr(sem), None, None, 0, s_), "build_input")
+            # one schedule step with everything teacher-forced: every (still fully masked) row receives the level-0 ground-truth
+            # features, then the rows of `mask` go back to the mask token = the reference's torch.where(mask, sem + mask_token, sem + feat).
+            # (every temporary is bound to a name until its call is enqueued: the caching allocator may hand a freed block to
+            # the next temporary, whose fill kernel would run before ours)
+            tgt0, m8 = tgt[:, 0].contiguous(), mask[sl].to(torch.uint8).contiguous()
+            L.check(lib.edm_s2a_step(self._ctx, 0, 2, 1.0, 0, None, None, L.ptr(tgt0), L.ptr(m8), s_), "step")
+            codes = torch.empty(nb, Q, T, device=dev, dtype=torch.int64)
+            tgt_c = tgt[:, :n_inj].contiguous()
+            L.check(lib.edm_s2a_full_pass(self._ctx, None, L.ptr(tgt_c), L.ptr(codes), s_), "full_pass")
+            out_codes[sl] = codes
+            # log-softmax of the target id at every position (the sampling kernel with the targets teacher-forced)
+            coarse = self._view("coarse_logits", (4, nb * T, V), torch.float32)
+            keep = []
+            for k in range(n_inj):
+                lp = torch.empty(nb * T, device=dev, dtype=torch.float32)
+                tk, ik = tgt[:, k].contiguous(), torch.empty(nb, T, device=dev, dtype=torch.int32)
+                keep += [tk, ik]
+                L.check(lib.edm_sample(L.ptr(coarse[k]), V, nb * T, None, 0, 0, 0, L.ptr(tk), L.ptr(ik), L.ptr(lp), T, 1, 1, 0, s_), "sample")
+                logp[sl, k] = lp.view(nb, T)
+            nf = Q - n_inj
+            fine = self._view("fine_logits", (nb * T * nf, V), torch.float32)
+            lp = torch.empty(nb * T * nf, device=dev, dtype=torch.float32)
+            tf, ids_f = tgt[:, n_inj:].contiguous(), torch.empty(nb, nf, T, device=dev, dtype=torch.int32)
+            L.check(lib.edm_sample(L.ptr(fine), V, nb * T * nf, None, 0, 0, 0, L.ptr(tf), L.ptr(ids_f), L.ptr(lp), T, nf, nf, 0, s_), "sample")
+            logp[sl, n_inj:] = lp.view(nb, T, nf).permute(0, 2, 1)
+            del keep
+        sel = torch.ones_like(mask) if self.loss_all else mask
+        sel3 = sel[:, None, :].expand(B, Q, T)
+        loss = -(logp.masked_select(sel3).mean())
+        return InjectionConformerOutput(loss=loss, output_acoustic_codes=out_codes.masked_select(sel3), target_acoustic_codes=ac.clone())
 
     __call__ = forward

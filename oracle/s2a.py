@@ -296,3 +296,25 @@ def infer_special(sd, cfg: OracleConfig, semantic_tokens, acoustic_prompt_tokens
     if trace is not None:
         trace["all_logits"] = all_logits
     return all_logits.argmax(dim=-1)
+
+
+def training_forward(sd, cfg: OracleConfig, acoustic_tokens, semantic_tokens, mask_time_indices, mode="fp32", loss_all=False):
+    """InjectionConformerModel.forward in eval mode, modeling_injection_conformer.py:76-128, with the cosine_schedule_mask draw
+    (:62-74) injected. Eval mode of the wrapper (injection_conformer_wrapper.py:113-131): the coarse logits are predicted, but
+    the features injected at every row are the ground-truth ones (`injections[injection_idx]`).
+    Returns loss, output codes (flat over the selected (b, q, t) positions, as the reference returns them) and all logits."""
+    assert acoustic_tokens.shape[-1] == semantic_tokens.shape[-1], "Acoustic and semantic tokens must have same length"
+    sem = F.embedding(semantic_tokens, sd["semantic_embedding.weight"])
+    B, T, _ = sem.shape
+    ac = feat_proj(sd, cfg, acoustic_tokens[:, 0], mode)                                     # :92-94
+    m = mask_time_indices.bool()
+    x = torch.where(m[:, :, None], sem + sd["mask_token"].expand(B, T, -1), sem + ac)        # :100-102
+    logits = forward_full(sd, cfg, x, mode=mode, forced_coarse=acoustic_tokens[:, : len(cfg.injection_layers)])   # [B, Q, T, V]
+    V = logits.shape[-1]
+    if not loss_all:
+        sel = logits.masked_select(m[:, None, :, None]).view(-1, V)                          # :114-116
+        tgt = acoustic_tokens.masked_select(m[:, None, :]).view(-1)
+    else:
+        sel, tgt = logits.reshape(-1, V), acoustic_tokens.reshape(-1)
+    loss = F.cross_entropy(sel.float(), tgt, reduction="mean")                               # :122
+    return dict(loss=loss, output_acoustic_codes=sel.argmax(dim=-1), target_acoustic_codes=acoustic_tokens, logits=logits)

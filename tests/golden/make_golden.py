@@ -167,6 +167,38 @@ def make_rvq(name, cfg_name, B, T, seed=0):
     print(f"rvq_{name}: codes {tuple(out['codes'].shape)} saved", flush=True)
 
 
+def make_train_forward(name, cfg_name, B, T, seed=0):
+    """InjectionConformerModel.forward (eval mode: no dropout, ground-truth injections) with cosine_schedule_mask replaced by a
+    fixed Bernoulli(0.6) mask: loss, arg-max codes and a few logit rows."""
+    cfg, dac_kwargs = CONFIGS[cfg_name]
+    torch.manual_seed(0)
+    model, _ = build_reference(cfg, dac_kwargs, seed)
+    g = torch.Generator().manual_seed(4321 + T)
+    sem = torch.randint(0, cfg.num_semantic, (B, T), generator=g)
+    ac = torch.randint(0, cfg.codebook_size, (B, cfg.n_codebooks, T), generator=g)
+    mask = torch.rand(B, T, generator=g) < 0.6
+    rec = {}
+    orig_fwd = model.encoder.forward
+
+    def fwd(*a, **k):
+        out = orig_fwd(*a, **k)
+        rec["all_logits"] = out.float().clone()
+        return out
+
+    model.encoder.forward = fwd
+    model.cosine_schedule_mask = lambda feature_length, batch_size: mask
+    with torch.inference_mode():
+        out = model(ac, sem)
+    idx = torch.linspace(0, T - 1, 4).long()
+    al = rec["all_logits"]
+    top2 = al.topk(2, dim=-1)[0]
+    gold = dict(cfg_name=cfg_name, B=B, T=T, weight_seed=seed, semantic_tokens=sem.to(torch.int16), acoustic_tokens=ac.to(torch.int16), mask=mask,
+                loss=out.loss.item(), output_codes=out.output_acoustic_codes.to(torch.int16), logit_rows=al[:, :, idx].clone(), row_idx=idx,
+                margin=(top2[..., 0] - top2[..., 1]).to(torch.float16))
+    torch.save(gold, os.path.join(OUT, f"train_fwd_{name}.pt"))
+    print(f"train_fwd_{name}: loss {out.loss.item():.6f} codes {tuple(out.output_acoustic_codes.shape)} saved", flush=True)
+
+
 if __name__ == "__main__":
     with tempfile.TemporaryDirectory():
         make_rvq("small", "small", 2, 50)
@@ -177,3 +209,5 @@ if __name__ == "__main__":
         make_s2a("full_s1", "full", 1, 60, 0, 1)
         make_s2a("full_s8", "full", 2, 150, 0, 8, with_autocast=True)
         make_s2a("full_s4_prompt", "full", 1, 100, 50, 4)
+        make_train_forward("small", "small", 2, 40)
+        make_train_forward("full", "full", 1, 60)

@@ -120,3 +120,40 @@ def test_api_errors():
         model.infer_special(sem, torch.zeros(1, 2, 5, dtype=torch.long), torch.zeros(1, 5, dtype=torch.long))
     with pytest.raises(AssertionError):
         model.forward(torch.zeros(1, 12, 9, dtype=torch.long), sem)
+
+
+@pytest.mark.parametrize("B,T,loss_all", [(2, 150, False), (3, 77, True), (1, 1, False)])
+def test_eval_forward_loss_vs_oracle(B, T, loss_all):
+    """InjectionConformerModel.forward (eval mode): loss and arg-max codes against the oracle restatement with the same mask."""
+    from oracle import s2a as os2a
+    from tests.parity_utils import compare_logits, full_model
+
+    cfg, sd, model = full_model()
+    g = torch.Generator().manual_seed(77 + T)
+    sem = torch.randint(0, cfg.num_semantic, (B, T), generator=g)
+    ac = torch.randint(0, cfg.codebook_size, (B, cfg.n_codebooks, T), generator=g)
+    mask = torch.rand(B, T, generator=g) < 0.6
+    mask[:, 0] = True                                            # keep at least one masked position per sequence
+    with torch.inference_mode():
+        ref = os2a.training_forward(sd, cfg, ac.cuda(), sem.cuda(), mask.cuda(), loss_all=loss_all)
+    old = model.loss_all
+    model.loss_all = loss_all
+    try:
+        out = model(ac, sem, mask_time_indices=mask)
+    finally:
+        model.loss_all = old
+    torch.cuda.synchronize()
+    print(f"loss ours {out.loss.item():.5f} oracle {ref['loss'].item():.5f}")
+    assert abs(out.loss.item() - ref["loss"].item()) < 2e-2
+    assert torch.equal(out["target_acoustic_codes"].cpu(), ac)
+    assert out.output_acoustic_codes.shape == ref["output_acoustic_codes"].shape
+    # arg-max codes agree except at near-ties of the oracle's own logits
+    sel = (torch.ones_like(mask) if loss_all else mask).cuda()[:, None, :].expand(B, cfg.n_codebooks, T)
+    ref_logits = ref["logits"].masked_select(sel[..., None]).view(-1, cfg.codebook_size)
+    ours_codes, ref_codes = out.output_acoustic_codes, ref["output_acoustic_codes"]
+    mism = ours_codes != ref_codes
+    margin = ref_logits.gather(1, ref_codes[:, None])[:, 0] - ref_logits.gather(1, ours_codes[:, None])[:, 0]
+    assert (margin[mism] < 0.12).all(), margin[mism].max().item()
+    assert mism.float().mean().item() < 0.1 or mism.numel() < 30
+    with pytest.raises(AssertionError):
+        model(ac[..., :-1], sem) if T > 1 else model(ac, sem[..., :0])

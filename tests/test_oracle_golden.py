@@ -83,3 +83,16 @@ def test_rvq_oracle_matches_reference(name, golden_dir):
     torch.testing.assert_close(feats[:, :16, :8], g["feats_head"], rtol=1e-5, atol=1e-5)
     unred = os2a.codes_to_features_unreduced(full_sd, cfg, codes[:, :4])
     torch.testing.assert_close(unred[:, :, :16, :8], g["unred_head"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["small", "full"])
+def test_training_forward_oracle_matches_reference(name, golden_dir):
+    """InjectionConformerModel.forward in eval mode (loss + arg-max codes) with the mask draw injected."""
+    g = torch.load(os.path.join(golden_dir, f"train_fwd_{name}.pt"))
+    cfg = CONFIGS[g["cfg_name"]]
+    sd = state_dict(g["cfg_name"], g["weight_seed"])
+    with torch.inference_mode():
+        out = os2a.training_forward(sd, cfg, g["acoustic_tokens"].long(), g["semantic_tokens"].long(), g["mask"])
+    assert abs(out["loss"].item() - g["loss"]) < 1e-4, (out["loss"].item(), g["loss"])
+    assert torch.equal(out["output_acoustic_codes"].to(torch.int16), g["output_codes"])
+    torch.testing.assert_close(out["logits"][:, :, g["row_idx"]], g["logit_rows"], rtol=1e-4, atol=1e-4)
