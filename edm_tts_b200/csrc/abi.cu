@@ -462,22 +462,28 @@ extern "C" void edm_rvq_tc_debug(unsigned lbo, unsigned sbo, int skip_project, i
   g_rvq_scan_probe = scan_probe;
 }
 
-extern "C" int edm_rvq_encode_tc(const float* z, int B, int T, int n_levels, const float* w_hi, const float* w_lo, const float* b_in,
+extern "C" int edm_rvq_encode_tc(const void* z, int z_is_bf16, int B, int T, int n_levels, const float* w_hi, const float* w_lo, const float* b_in,
                                  const float* cb_packed, const float* g, float* e_ws, long long* codes, const long long* forced,
                                  float* latents, void* stream) {
   if (int rc = check_arch()) return rc;
   if (n_levels < 1 || n_levels > kRvqLevels || B <= 0 || T <= 0) return fail(EDM_ERR_INVALID, "rvq shape B=%d T=%d levels=%d", B, T, n_levels);
-  if (T % 4 != 0) return fail(EDM_ERR_INVALID, "rvq_encode_tc needs T %% 4 == 0 (16-byte rows for TMA), got T=%d: pad the time axis", T);
+  if (T % (z_is_bf16 ? 8 : 4) != 0)
+    return fail(EDM_ERR_INVALID, "rvq_encode_tc needs 16-byte rows for TMA (T %% %d == 0), got T=%d: pad the time axis", z_is_bf16 ? 8 : 4, T);
   static bool attr_set = false;
   if (!attr_set) {
-    EDM_CUDA(cudaFuncSetAttribute(rvq_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmemBytes));
+    EDM_CUDA(cudaFuncSetAttribute(rvq_project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmemBytes));
+    EDM_CUDA(cudaFuncSetAttribute(rvq_project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmemBytes));
     EDM_CUDA(cudaFuncSetAttribute(rvq_search_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemBytes));
     EDM_CUDA(cudaFuncSetAttribute(rvq_search_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemBytes));
     attr_set = true;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap mz, mwh, mwl, mcb;
-  if (int rc = make_tmap_f32_2d(&mz, z, static_cast<uint64_t>(B) * kRtLatent, T, T, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  if (z_is_bf16) {
+    if (int rc = make_tmap_2d(&mz, z, static_cast<uint64_t>(B) * kRtLatent, T, T, 32)) return rc;
+  } else {
+    if (int rc = make_tmap_f32_2d(&mz, z, static_cast<uint64_t>(B) * kRtLatent, T, T, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return rc;
+  }
   if (int rc = make_tmap_f32_2d(&mwh, w_hi, kRtE, kRtLatent, kRtLatent, kRtE)) return rc;
   if (int rc = make_tmap_f32_2d(&mwl, w_lo, kRtE, kRtLatent, kRtLatent, kRtE)) return rc;
   if (int rc = make_tmap_f32_2d(&mcb, cb_packed, 12 * 1024, 32, 32, kRsChunk)) return rc;
@@ -486,7 +492,10 @@ extern "C" int edm_rvq_encode_tc(const float* z, int B, int T, int n_levels, con
   pp.B = B; pp.T = T; pp.b_in = b_in; pp.e_out = e_ws; pp.a_lbo = g_rvq_a_lbo; pp.a_sbo = g_rvq_a_sbo; pp.dbg = g_rvq_skip_project >> 4;
   if (!(g_rvq_skip_project & 1)) {
       const int ptiles = ((T + kRpFrames - 1) / kRpFrames) * B;
-    rvq_project_kernel<<<ptiles < num_sms() ? ptiles : num_sms(), kRpThreads, kRpSmemBytes, st>>>(mz, mwh, mwl, pp);
+    if (z_is_bf16)
+      rvq_project_kernel<true><<<ptiles < num_sms() ? ptiles : num_sms(), kRpThreads, kRpSmemBytes, st>>>(mz, mwh, mwl, pp);
+    else
+      rvq_project_kernel<false><<<ptiles < num_sms() ? ptiles : num_sms(), kRpThreads, kRpSmemBytes, st>>>(mz, mwh, mwl, pp);
     EDM_LAUNCH_CHECK("rvq_project");
   }
   RvqSearchParams sp;

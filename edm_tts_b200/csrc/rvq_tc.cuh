@@ -35,7 +35,7 @@ constexpr int kRtLatent = 1024;
 // L2 -> SM weight traffic (with 128-frame tiles it was 1.5x the z stream and the L2 fabric, not HBM, set the pace).
 constexpr int kRpFrames = 256;
 constexpr int kRpKc = 32;                                            // latent channels per pipeline step
-constexpr int kRpZStages = 3;
+constexpr int kRpZStages = 3;        // fp32 z: 3 x 32 KB; bf16 z: 6 x 16 KB staging tiles (same 96 KB)
 constexpr int kRpLwStages = 2;
 constexpr uint32_t kRpZBytes = kRpFrames * kRpKc * 4;                // 32 KB: 8 TMA boxes of (32 frames x 32 channels)
 constexpr uint32_t kRpWBytes = kRtE * kRpKc * 4;                     // 12 KB: 96 outputs x 32 channels (K-major)
@@ -51,16 +51,22 @@ struct RvqProjParams {
   int dbg;                // bring-up timing probes: bit 0 = split warps skip their arithmetic, bit 1 = no MMAs are issued
 };
 
+// kBf16: z is bf16 (what the DAC encoder produces under autocast). Its tiles land as bf16 staging boxes (6 x 16 KB ring), the
+// split warps expand them into the fp32 hi tile of the (hi | weights) slot in the MN-major layout the MMA expects; bf16 values
+// are tf32-exact, so the lo tile and its MMA disappear and z costs half the HBM bytes.
+template <bool kBf16>
 __global__ void __launch_bounds__(kRpThreads, 1)
 rvq_project_kernel(const __grid_constant__ CUtensorMap tma_z, const __grid_constant__ CUtensorMap tma_whi,
                    const __grid_constant__ CUtensorMap tma_wlo, const RvqProjParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sZ = smem;                                   // kRpZStages x 16 KB (becomes the hi tile in place)
-  uint8_t* sLw = smem + kRpZStages * kRpZBytes;         // kRpLwStages x (lo tile | w_hi | w_lo)
+  constexpr int kZSt = kBf16 ? 2 * kRpZStages : kRpZStages;
+  constexpr uint32_t kZB = kBf16 ? kRpZBytes / 2 : kRpZBytes;   // bytes per z ring slot
+  uint8_t* sZ = smem;                                   // fp32: 3 x 32 KB (becomes the hi tile in place); bf16: 6 x 16 KB staging
+  uint8_t* sLw = smem + kRpZStages * kRpZBytes;         // kRpLwStages x (lo tile [bf16: hi tile] | w_hi | w_lo)
   uint64_t* z_full = reinterpret_cast<uint64_t*>(sLw + kRpLwStages * kRpLwBytes);
-  uint64_t* z_empty = z_full + kRpZStages;
-  uint64_t* w_full = z_empty + kRpZStages;
+  uint64_t* z_empty = z_full + 2 * kRpZStages;
+  uint64_t* w_full = z_empty + 2 * kRpZStages;
   uint64_t* split_bar = w_full + kRpLwStages;
   uint64_t* lw_empty = split_bar + kRpLwStages;
   uint64_t* tfull_bar = lw_empty + kRpLwStages;
@@ -78,9 +84,9 @@ rvq_project_kernel(const __grid_constant__ CUtensorMap tma_z, const __grid_const
     tma_prefetch_desc(&tma_z);
     tma_prefetch_desc(&tma_whi);
     tma_prefetch_desc(&tma_wlo);
-    for (int s = 0; s < kRpZStages; ++s) {
+    for (int s = 0; s < kZSt; ++s) {
       mbar_init(&z_full[s], 1);
-      mbar_init(&z_empty[s], 1);
+      mbar_init(&z_empty[s], kBf16 ? 128 : 1);  // released by the split warps (bf16 staging) or by the MMA commit (fp32, in place)
     }
     for (int s = 0; s < kRpLwStages; ++s) {
       mbar_init(&w_full[s], 1);
@@ -104,12 +110,18 @@ rvq_project_kernel(const __grid_constant__ CUtensorMap tma_z, const __grid_const
       for (uint32_t it = 0; it < total_steps; ++it) {
         const int tile = blockIdx.x + (it / kNumKc) * gridDim.x, kc = it % kNumKc;
         const int b = tile / tiles_per_b, t0 = (tile % tiles_per_b) * kRpFrames;
-        const uint32_t zs = it % kRpZStages;
-        mbar_wait(&z_empty[zs], ((it / kRpZStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&z_full[zs], kRpZBytes);
+        const uint32_t zs = it % kZSt;
+        mbar_wait(&z_empty[zs], ((it / kZSt) & 1) ^ 1);
+        mbar_arrive_expect_tx(&z_full[zs], kZB);
+        if constexpr (kBf16) {
 #pragma unroll
-        for (int i = 0; i < kRpFrames / 32; ++i)  // frames beyond T are zero-filled by TMA
-          tma_load_2d(&tma_z, &z_full[zs], sZ + zs * kRpZBytes + i * 4096, t0 + 32 * i, b * kRtLatent + kc * kRpKc);
+          for (int i = 0; i < kRpFrames / 64; ++i)  // bf16 boxes: 64 frames (128 B) x 32 channels
+            tma_load_2d(&tma_z, &z_full[zs], sZ + zs * kZB + i * 4096, t0 + 64 * i, b * kRtLatent + kc * kRpKc);
+        } else {
+#pragma unroll
+          for (int i = 0; i < kRpFrames / 32; ++i)  // frames beyond T are zero-filled by TMA
+            tma_load_2d(&tma_z, &z_full[zs], sZ + zs * kZB + i * 4096, t0 + 32 * i, b * kRtLatent + kc * kRpKc);
+        }
       }
     }
   } else if (warp == 10) {
@@ -129,7 +141,7 @@ rvq_project_kernel(const __grid_constant__ CUtensorMap tma_z, const __grid_const
       for (uint32_t it = 0; it < total_steps; ++it) {
         const uint32_t tl = it / kNumKc, kc = it % kNumKc;
         const uint32_t acc = tl & 1;
-        const uint32_t zs = it % kRpZStages, ls = it % kRpLwStages;
+        const uint32_t zs = it % kZSt, ls = it % kRpLwStages;
         if (kc == 0) {
           mbar_wait(&tempty_bar[acc], ((tl >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -138,8 +150,8 @@ rvq_project_kernel(const __grid_constant__ CUtensorMap tma_z, const __grid_const
         mbar_wait(&w_full[ls], (it / kRpLwStages) & 1);     // weights (TMA) landed
         mbar_wait(&split_bar[ls], (it / kRpLwStages) & 1);  // z tile rewritten as hi (in place) / lo by the split warps
         tc_fence_after();
-        const uint32_t zh = smem_u32(sZ + zs * kRpZBytes);
         const uint32_t lw = smem_u32(sLw + ls * kRpLwBytes);
+        const uint32_t zh = kBf16 ? lw : smem_u32(sZ + zs * kZB);   // fp32 hi tile: expanded into the slot (bf16) or in place
 #pragma unroll
         for (int k = 0; k < ((p.dbg & 2) ? 0 : kRpKc / 8); ++k) {
           // A (MN-major, 128B swizzle with 32 B atoms): 8 channels = two 512 B K-groups inside each 32-frame box (4 KB); the
@@ -150,37 +162,62 @@ rvq_project_kernel(const __grid_constant__ CUtensorMap tma_z, const __grid_const
 #pragma unroll
           for (int m = 0; m < kRpFrames / 128; ++m) {
             const uint64_t a_hi = umma_desc_sw128_base32(zh + m * 16384 + k * 1024, p.a_lbo, p.a_sbo);
-            const uint64_t a_lo = umma_desc_sw128_base32(lw + m * 16384 + k * 1024, p.a_lbo, p.a_sbo);
-            umma_ss_tf32(d_tmem + m * 128, a_lo, b_hi, idesc, (kc | k) != 0 ? 1u : 0u);
-            umma_ss_tf32(d_tmem + m * 128, a_hi, b_lo, idesc, 1u);
+            if constexpr (kBf16) {
+              umma_ss_tf32(d_tmem + m * 128, a_hi, b_lo, idesc, (kc | k) != 0 ? 1u : 0u);
+            } else {
+              const uint64_t a_lo = umma_desc_sw128_base32(lw + m * 16384 + k * 1024, p.a_lbo, p.a_sbo);
+              umma_ss_tf32(d_tmem + m * 128, a_lo, b_hi, idesc, (kc | k) != 0 ? 1u : 0u);
+              umma_ss_tf32(d_tmem + m * 128, a_hi, b_lo, idesc, 1u);
+            }
             umma_ss_tf32(d_tmem + m * 128, a_hi, b_hi, idesc, 1u);
           }
         }
-        umma_commit(&z_empty[zs]);
+        if constexpr (!kBf16) umma_commit(&z_empty[zs]);
         umma_commit(&lw_empty[ls]);
         if (kc == kNumKc - 1) umma_commit(&tfull_bar[acc]);
       }
     }
   } else if (warp < 6) {
-    // split warps: z tile (as TMA wrote it) -> hi = tf32(z) in place, lo = tf32(z - hi) at the same offset of the lo tile
+    // split warps. fp32 z: tile (as TMA wrote it) -> hi = tf32(z) in place, lo = tf32(z - hi) at the same offset of the lo tile.
+    // bf16 z: staging boxes [32 channels][64 frames] (128B swizzle: 16 B chunk k of row c sits at chunk k ^ (c & 7)) -> fp32 hi
+    // tile of the slot, 32-frame boxes with 32 B chunks XOR-ed by (c & 3) (the MN-major tf32 layout).
     const int st_tid = threadIdx.x - 64;
     for (uint32_t it = 0; it < total_steps; ++it) {
-      const uint32_t zs = it % kRpZStages, ls = it % kRpLwStages;
-      mbar_wait(&z_full[zs], (it / kRpZStages) & 1);
+      const uint32_t zs = it % kZSt, ls = it % kRpLwStages;
+      mbar_wait(&z_full[zs], (it / kZSt) & 1);
       mbar_wait(&lw_empty[ls], ((it / kRpLwStages) & 1) ^ 1);
-      const uint32_t zh = smem_u32(sZ + zs * kRpZBytes) + st_tid * 16;
-      const uint32_t zl = smem_u32(sLw + ls * kRpLwBytes) + st_tid * 16;
+      if constexpr (kBf16) {
+        const uint32_t src = smem_u32(sZ + zs * kZB), dst = smem_u32(sLw + ls * kRpLwBytes);
 #pragma unroll
-      for (int i = 0; i < ((p.dbg & 1) ? 0 : static_cast<int>(kRpZBytes) / (128 * 16)); ++i) {
-        const float4 v = lds128(zh + i * 2048);
-        float4 h, l;
-        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-        l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-        sts128(zh + i * 2048, h);
-        sts128(zl + i * 2048, l);
+        for (int i = 0; i < ((p.dbg & 1) ? 0 : static_cast<int>(kZB) / (128 * 16)); ++i) {
+          const int q = st_tid + 128 * i;          // physical 16 B chunk of the staging tile
+          const int box = q >> 8, c = (q & 255) >> 3, k = (q & 7) ^ (c & 7);   // frames 64 box + 8 k .. + 7 of channel row c
+          const float4 v = lds128(src + q * 16);   // 8 bf16
+          const uint32_t w[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+          const uint32_t o = dst + (2 * box + (k >> 2)) * 4096 + c * 128 + (((k & 3) ^ (c & 3)) << 5);
+          sts128(o, make_float4(__uint_as_float(w[0] << 16), __uint_as_float(w[0] & 0xffff0000u), __uint_as_float(w[1] << 16),
+                                __uint_as_float(w[1] & 0xffff0000u)));
+          sts128(o + 16, make_float4(__uint_as_float(w[2] << 16), __uint_as_float(w[2] & 0xffff0000u), __uint_as_float(w[3] << 16),
+                                     __uint_as_float(w[3] & 0xffff0000u)));
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&z_empty[zs]);   // the staging slot can be refilled
+        mbar_arrive(&split_bar[ls]);
+      } else {
+        const uint32_t zh = smem_u32(sZ + zs * kZB) + st_tid * 16;
+        const uint32_t zl = smem_u32(sLw + ls * kRpLwBytes) + st_tid * 16;
+#pragma unroll
+        for (int i = 0; i < ((p.dbg & 1) ? 0 : static_cast<int>(kRpZBytes) / (128 * 16)); ++i) {
+          const float4 v = lds128(zh + i * 2048);
+          float4 h, l;
+          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+          sts128(zh + i * 2048, h);
+          sts128(zl + i * 2048, l);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&split_bar[ls]);
       }
-      fence_proxy_async_smem();
-      mbar_arrive(&split_bar[ls]);
     }
   } else if (warp < 10) {
     // epilogue warps: thread <-> TMEM lane = frame of each 128-row accumulator, 96 columns + bias -> E[frame, 96]

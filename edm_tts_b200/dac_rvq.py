@@ -35,10 +35,13 @@ class ResidualVectorQuantize:
             raise ValueError(f"z must be [B, {self.input_dim}, T]")
         if impl == "mma_sync":
             return self._encode_mma_sync(z, forced_codes, return_latents)
-        # the tcgen05 path reads z through fp32 TMA boxes: rows (the time axis) must be 16-byte multiples
-        z = z.to(self.device, torch.float32)
+        # the tcgen05 path reads z through TMA boxes: rows (the time axis) must be 16-byte multiples
+        if z.dtype not in (torch.float32, torch.bfloat16):
+            z = z.float()
+        z = z.to(self.device)
         B, _, T = z.shape
-        Tp = (T + 3) // 4 * 4
+        al = 8 if z.dtype == torch.bfloat16 else 4
+        Tp = (T + al - 1) // al * al
         z = torch.nn.functional.pad(z, (0, Tp - T)) if Tp != T else z.contiguous()
         t = self._t
         codes = torch.empty(B, self.n_codebooks, Tp, device=self.device, dtype=torch.int64)
@@ -48,7 +51,7 @@ class ResidualVectorQuantize:
             fc = forced_codes.to(self.device, torch.int64)
             fc = torch.nn.functional.pad(fc, (0, Tp - T)) if Tp != T else fc.contiguous()
         e_ws = torch.empty(B * Tp, 96, device=self.device, dtype=torch.float32)
-        L.check(L.lib().edm_rvq_encode_tc(L.ptr(z), B, Tp, self.n_codebooks, L.ptr(t["w_hi"]), L.ptr(t["w_lo"]), L.ptr(t["b_in"]),
+        L.check(L.lib().edm_rvq_encode_tc(L.ptr(z), int(z.dtype == torch.bfloat16), B, Tp, self.n_codebooks, L.ptr(t["w_hi"]), L.ptr(t["w_lo"]), L.ptr(t["b_in"]),
                                           L.ptr(t["cb_packed"]), L.ptr(t["g"]), L.ptr(e_ws), L.ptr(codes), L.ptr(fc), L.ptr(lat),
                                           L.stream_ptr()), "rvq_encode_tc")
         if Tp != T:

@@ -91,11 +91,11 @@ int edm_rvq_encode(const void* z, int z_is_bf16, int B, int T, int n_levels, con
                    const long long* forced, float* latents, void* stream);
 
 /* Same search on the tcgen05 tensor cores (csrc/rvq_tc.cuh): a 3xTF32 projection GEMM z -> e_ws [B*T,96] followed by the
- * 12-level search with TMEM-resident score tiles. z fp32 [B,1024,T] with T % 4 == 0 (TMA needs 16-byte rows; the host
- * side pads / converts other inputs). Tables (pack_rvq_weights): w_hi / w_lo [96,1024] tf32-split stacked in_proj weights,
+ * 12-level search with TMEM-resident score tiles. z [B,1024,T] fp32 with T % 4 == 0 or bf16 with T % 8 == 0 (TMA needs
+ * 16-byte rows; the host side pads other lengths). bf16 z is expanded to tf32-exact fp32 tiles on chip (half the HBM bytes). Tables (pack_rvq_weights): w_hi / w_lo [96,1024] tf32-split stacked in_proj weights,
  * b_in [96], cb_packed [12,1024,32] = [c^_hi | c^_hi | c^_lo | -|c^|^2/2 hi, lo, 0...], g [12,12,1024,8]. e_ws is caller
  * scratch of B*T*96 floats. Replaces ResidualVectorQuantize.forward, dac/vector_quantizer.py:146-210. */
-int edm_rvq_encode_tc(const float* z, int B, int T, int n_levels, const float* w_hi, const float* w_lo, const float* b_in,
+int edm_rvq_encode_tc(const void* z, int z_is_bf16, int B, int T, int n_levels, const float* w_hi, const float* w_lo, const float* b_in,
                       const float* cb_packed, const float* g, float* e_ws, long long* codes, const long long* forced,
                       float* latents, void* stream);
 

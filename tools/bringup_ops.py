@@ -349,7 +349,7 @@ def test_rvqtc():
         codes = torch.empty(B, Lv, T, device=dev, dtype=torch.int64)
         e_ws = torch.full((B * T, 96), float("nan"), device=dev) if e_given is None else e_given.float().contiguous()
         lat = torch.empty(B, 96, T, device=dev) if want_lat else None
-        L.check(L.lib().edm_rvq_encode_tc(L.ptr(z), B, T, Lv, L.ptr(w_hi), L.ptr(w_lo), L.ptr(b_flat), L.ptr(cbp), L.ptr(g), L.ptr(e_ws),
+        L.check(L.lib().edm_rvq_encode_tc(L.ptr(z), 0, B, T, Lv, L.ptr(w_hi), L.ptr(w_lo), L.ptr(b_flat), L.ptr(cbp), L.ptr(g), L.ptr(e_ws),
                                           L.ptr(codes), L.ptr(forced), L.ptr(lat), L.stream_ptr()), "rvq_tc")
         torch.cuda.synchronize()
         return codes, e_ws, lat
@@ -405,7 +405,7 @@ def test_rvqtc():
     z = torch.randn(B, 1024, T, device=dev)
     codes = torch.empty(B, Lv, T, device=dev, dtype=torch.int64)
     e_ws = torch.empty(B * T, 96, device=dev)
-    ms = timeit(lambda: L.lib().edm_rvq_encode_tc(L.ptr(z), B, T, Lv, L.ptr(w_hi), L.ptr(w_lo), L.ptr(b_flat), L.ptr(cbp), L.ptr(g), L.ptr(e_ws),
+    ms = timeit(lambda: L.lib().edm_rvq_encode_tc(L.ptr(z), 0, B, T, Lv, L.ptr(w_hi), L.ptr(w_lo), L.ptr(b_flat), L.ptr(cbp), L.ptr(g), L.ptr(e_ws),
                                                   L.ptr(codes), None, None, L.stream_ptr()), iters=10, warm=3)
     print(f"rvqtc time B={B} T={T}: {ms:.3f} ms = {B * T / ms / 1e3:.2f} Mframes/s, {B * T * 4192 / ms / 1e6:.0f} GB/s", flush=True)
 
@@ -426,6 +426,11 @@ def test_rvqtime():
         L.lib().edm_rvq_tc_debug(4096, 512, 0, 0)
         print(f"rvq tcgen05 B={B} T={T}: total {ms:.3f} ms (search alone {ms_s:.3f} ms [no-compare floor {ms_p:.3f}], projection ~{ms - ms_s:.3f} ms) = {B * T / ms / 1e3:.1f} Mframes/s, "
               f"{B * T * 4192 / ms / 1e6:.0f} GB/s algorithmic", flush=True)
+    zb = torch.randn(32, 1024, 3000, device=dev).to(torch.bfloat16)
+    same = torch.equal(q.encode(zb), q.encode(zb.float()))
+    ms_b = timeit(lambda: q.encode(zb), iters=10, warm=3)
+    print(f"rvq tcgen05 bf16 z B=32 T=3000: {ms_b:.3f} ms = {32 * 3000 / ms_b / 1e3:.1f} Mframes/s, {32 * 3000 * 2144 / ms_b / 1e6:.0f} GB/s algorithmic; "
+          f"codes identical to the fp32 copy of the same z: {same}", flush=True)
     for (B, T) in [(32, 3000), (375, 256), (94, 1024), (12, 8192)]:
         z = torch.randn(B, 1024, T, device=dev)
         L.lib().edm_rvq_tc_debug(4096, 512, 1, 1)
