@@ -280,8 +280,8 @@ constexpr int kRsChunk = 128;                                  // codes per MMA 
 constexpr int kRsChunks = 1024 / kRsChunk;
 constexpr int kRsRing = 4;
 constexpr uint32_t kRsTileBytes = 128 * 128;                   // 128 rows x 32 fp32 (A tile and every codebook chunk)
-constexpr uint32_t kRsSmemBytes = kRsTileBytes * (1 + kRsRing) + (12 + 8) * 128 * 4 + 1024 + 256;
-constexpr int kRsThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 search
+constexpr uint32_t kRsSmemBytes = kRsTileBytes * (1 + kRsRing) + (12 + 8 + 2) * 128 * 4 + 1024 + 256;
+constexpr int kRsThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 search + level bookkeeping, warps 6-9 search only
 
 struct RvqSearchParams {
   int B, T, n_levels;
@@ -290,39 +290,46 @@ struct RvqSearchParams {
   long long* codes;         // out [B, n_levels, T]
   const long long* forced;  // teacher forcing [B, n_levels, T] or nullptr
   float* latents;           // out [B, 96, T] residual-corrected latents before normalisation, or nullptr
-  float one;                // 1.0f and 1, passed at run time so the saves of rvq_scan_group4 stay FMUL / IMAD (FMA pipe)
+  float one;                // 1.0f and 1, passed at run time so the saves of rvq_scan32 stay FMUL / IMAD (FMA pipe)
   int onei;
 };
 
 // Running first maximum of one frame's scores. The scan is ALU-pipe bound (FSETP / FMNMX / SEL all issue there at half
-// rate), so it works on groups of four: two FMNMX for the group maximum, one FSETP against the running best, one FMNMX to
-// update it, and the "remember this group" side (group id + its four raw scores) as predicated FMUL / IMAD by a run-time 1,
-// which issue on the otherwise idle FMA pipe. The winner inside the remembered group is resolved once per level.
+// rate), so it works on groups of eight: four FMNMX3 / FMNMX for the group maximum, one FSETP against the running best, one
+// FMNMX to update it (0.75 ALU instructions per score), and the "remember this group" side (group id + its eight raw scores)
+// as predicated FMUL / IMAD by a run-time 1, which issue on the otherwise idle FMA pipe. The winner inside the
+// remembered group is resolved once per level.
 struct RvqBest {
   float best;
-  int gid;        // group (code / 4) holding the running maximum
-  float s[4];     // its four scores
+  int gid;       // group (code / 8) holding the running maximum
+  float s[8];    // its eight scores
 };
 template <int kGroup0>
 __device__ __forceinline__ void rvq_scan32(const uint32_t (&r)[32], RvqBest& st, int group_base, float one, int onei) {
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    const float v0 = __uint_as_float(r[4 * g]), v1 = __uint_as_float(r[4 * g + 1]), v2 = __uint_as_float(r[4 * g + 2]),
-                v3 = __uint_as_float(r[4 * g + 3]);
-    const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
-    asm(
-        "{\n\t"
+  for (int g = 0; g < 4; ++g) {
+    const float v0 = __uint_as_float(r[8 * g]), v1 = __uint_as_float(r[8 * g + 1]), v2 = __uint_as_float(r[8 * g + 2]),
+                v3 = __uint_as_float(r[8 * g + 3]), v4 = __uint_as_float(r[8 * g + 4]), v5 = __uint_as_float(r[8 * g + 5]),
+                v6 = __uint_as_float(r[8 * g + 6]), v7 = __uint_as_float(r[8 * g + 7]);
+    const float m = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), fmaxf(fmaxf(v4, v5), fmaxf(v6, v7)));
+    asm("{\n\t"
         ".reg .pred q;\n\t"
-        "setp.gt.f32 q, %6, %0;\n\t"           // strict: an equal later group never replaces an earlier one
-        "max.f32 %0, %0, %6;\n\t"
-        "@q mul.f32 %1, %7, %11;\n\t"
-        "@q mul.f32 %2, %8, %11;\n\t"
-        "@q mul.f32 %3, %9, %11;\n\t"
-        "@q mul.f32 %4, %10, %11;\n\t"
-        "@q mad.lo.s32 %5, %12, %13, %14;\n\t"
+        "setp.gt.f32 q, %10, %0;\n\t"           // strict: an equal later group never replaces an earlier one
+        "max.f32 %0, %0, %10;\n\t"
+        "@q mul.f32 %1, %11, %19;\n\t"
+        "@q mul.f32 %2, %12, %19;\n\t"
+        "@q mul.f32 %3, %13, %19;\n\t"
+        "@q mul.f32 %4, %14, %19;\n\t"
+        "@q mul.f32 %5, %15, %19;\n\t"
+        "@q mul.f32 %6, %16, %19;\n\t"
+        "@q mul.f32 %7, %17, %19;\n\t"
+        "@q mul.f32 %8, %18, %19;\n\t"
+        "@q mad.lo.s32 %9, %20, %21, %22;\n\t"
         "}\n"
-        : "+f"(st.best), "+f"(st.s[0]), "+f"(st.s[1]), "+f"(st.s[2]), "+f"(st.s[3]), "+r"(st.gid)
-        : "f"(m), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(one), "r"(onei), "r"(kGroup0 + g), "r"(group_base));
+        : "+f"(st.best), "+f"(st.s[0]), "+f"(st.s[1]), "+f"(st.s[2]), "+f"(st.s[3]), "+f"(st.s[4]), "+f"(st.s[5]), "+f"(st.s[6]),
+          "+f"(st.s[7]), "+r"(st.gid)
+        : "f"(m), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5), "f"(v6), "f"(v7), "f"(one), "r"(onei), "r"(kGroup0 + g),
+          "r"(group_base));
   }
 }
 // bring-up probe: consumes the loaded registers with one op per 32 scores (measures the TMEM-read / MMA floor of the kernel)
@@ -339,7 +346,9 @@ rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchPar
   uint8_t* sRing = smem + kRsTileBytes;
   int* s_chosen = reinterpret_cast<int*>(sRing + kRsRing * kRsTileBytes);  // [12][128]
   float* s_nxt = reinterpret_cast<float*>(s_chosen + 12 * 128);            // [8][128] next level's partial latent (parked during the scan)
-  uint64_t* ring_full = reinterpret_cast<uint64_t*>(s_nxt + 8 * 128);
+  float* s_pbest = s_nxt + 8 * 128;                                        // [128] best score of the upper column half (warps 6-9)
+  int* s_pidx = reinterpret_cast<int*>(s_pbest + 128);                     // [128] and its code
+  uint64_t* ring_full = reinterpret_cast<uint64_t*>(s_pidx + 128);
   uint64_t* ring_empty = ring_full + kRsRing;
   uint64_t* tfull_bar = ring_empty + kRsRing;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -358,7 +367,7 @@ rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchPar
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 128);
+      mbar_init(&tempty_bar[b], 256);  // both column halves have pulled their part of the buffer
     }
     mbar_init(a_ready, 128);
     fence_mbar_init();
@@ -403,120 +412,154 @@ rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchPar
         }
     }
   } else {
+    // Two warps per TMEM lane quadrant: warps 2-5 scan columns [0, 64) of every 128-code chunk and do the per-level
+    // bookkeeping of their frame, warps 6-9 scan columns [64, 128) and hand (best, code) over through shared memory
+    // (named barrier 1 + quad, 64 threads). Four warps per SM sub-partition keep TMEM loads and compares overlapped.
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int f = quad * 32 + lane;
     const uint32_t a_row = smem_u32(sA) + f * 128;
     const int sw = f & 7;
-    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t tmem_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + half * 64;
     uint32_t g = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int b = tile / tiles_per_b, t = (tile % tiles_per_b) * kRtFrames + f;
-      const bool live = t < p.T;
-      const float4* erow = reinterpret_cast<const float4*>(p.e + (static_cast<long long>(b) * p.T + (live ? t : 0)) * kRtE);
-      float cur[8];
-      {
-        const float4 a = live ? __ldg(erow) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 c = live ? __ldg(erow + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-        cur[0] = a.x; cur[1] = a.y; cur[2] = a.z; cur[3] = a.w; cur[4] = c.x; cur[5] = c.y; cur[6] = c.z; cur[7] = c.w;
+    // scans this warp's 64 columns of the 8 chunks of one level -> first maximum (score, code)
+    auto scan_level = [&](float& best_out, int& idx_out) {
+      RvqBest st;
+      st.best = -INFINITY;
+      st.gid = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) st.s[i] = 0.f;
+      for (int ch = 0; ch < kRsChunks; ++ch, ++g) {
+        const uint32_t buf = g & 1;
+        const uint32_t taddr = tmem_row + buf * kRsChunk;
+        const int group_base = ch * (kRsChunk / 8) + half * 8;
+        mbar_wait(&tfull_bar[buf], (g >> 1) & 1);
+        tc_fence_after();
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(taddr, r0);
+        tmem_ld_32x32(taddr + 32, r1);
+        tmem_ld_wait_dep(r0);
+        tmem_ld_wait_dep(r1);
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[buf]);  // the accumulator buffer may be overwritten by chunk g + 2
+        if constexpr (kScan == 0) {
+          rvq_scan32<0>(r0, st, group_base, p.one, p.onei);
+          rvq_scan32<4>(r1, st, group_base, p.one, p.onei);
+        } else {
+          rvq_scan32_probe(r0, st);
+          rvq_scan32_probe(r1, st);
+        }
       }
-      for (int l = 0; l < p.n_levels; ++l) {
-        if (p.latents != nullptr && live) {
+      // first position of the maximum inside the remembered group
+      int pos = 7;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) p.latents[(static_cast<long long>(b) * kRtE + l * 8 + k) * p.T + t] = cur[k];
-        }
-        // F.normalize: x / max(|x|_2, 1e-12)
-        float n2 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) n2 = fmaf(cur[k], cur[k], n2);
-        const float den = fmaxf(sqrtf(n2), 1e-12f);
-        float hi[8], lo[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float en = __fdiv_rn(cur[k], den);
-          hi[k] = tf32_rna(en);
-          lo[k] = tf32_rna(en - hi[k]);
-        }
-        // A row (K = 32): [e_hi | e_lo | e_hi | 1 1 0 0 0 0 0 0] against B rows [c_hi | c_hi | c_lo | x_hi x_lo 0 ...]
-        sts128(a_row + ((0 ^ sw) << 4), make_float4(hi[0], hi[1], hi[2], hi[3]));
-        sts128(a_row + ((1 ^ sw) << 4), make_float4(hi[4], hi[5], hi[6], hi[7]));
-        sts128(a_row + ((2 ^ sw) << 4), make_float4(lo[0], lo[1], lo[2], lo[3]));
-        sts128(a_row + ((3 ^ sw) << 4), make_float4(lo[4], lo[5], lo[6], lo[7]));
-        sts128(a_row + ((4 ^ sw) << 4), make_float4(hi[0], hi[1], hi[2], hi[3]));
-        sts128(a_row + ((5 ^ sw) << 4), make_float4(hi[4], hi[5], hi[6], hi[7]));
-        sts128(a_row + ((6 ^ sw) << 4), make_float4(1.f, 1.f, 0.f, 0.f));
-        sts128(a_row + ((7 ^ sw) << 4), make_float4(0.f, 0.f, 0.f, 0.f));
-        fence_proxy_async_smem();
-        mbar_arrive(a_ready);
+      for (int i = 6; i >= 0; --i) pos = st.s[i] == st.best ? i : pos;
+      best_out = st.best;
+      idx_out = st.gid * 8 + pos;
+    };
 
-        // next level's latent, minus everything that does not depend on this level's decision (loads overlap the scan);
-        // parked in shared memory so the scan keeps its registers for four TMEM loads in flight
-        if (l + 1 < p.n_levels) {
-          float nxt[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) nxt[k] = 0.f;
-          if (live) {
-            const float4 a = __ldg(erow + 2 * (l + 1)), c = __ldg(erow + 2 * (l + 1) + 1);
-            nxt[0] = a.x; nxt[1] = a.y; nxt[2] = a.z; nxt[3] = a.w; nxt[4] = c.x; nxt[5] = c.y; nxt[6] = c.z; nxt[7] = c.w;
+    if (half == 1) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        for (int l = 0; l < p.n_levels; ++l) {
+          float best;
+          int bidx;
+          scan_level(best, bidx);
+          s_pbest[f] = best;
+          s_pidx[f] = bidx;
+          switch (quad) {  // immediate barrier ids keep the CTA at 5 named barriers
+            case 0: asm volatile("barrier.arrive 1, 64;" ::: "memory"); break;
+            case 1: asm volatile("barrier.arrive 2, 64;" ::: "memory"); break;
+            case 2: asm volatile("barrier.arrive 3, 64;" ::: "memory"); break;
+            default: asm volatile("barrier.arrive 4, 64;" ::: "memory"); break;
           }
-          for (int j = 0; j < l; ++j) {
-            const int cj = s_chosen[j * 128 + f];
-            const float4* gp = reinterpret_cast<const float4*>(p.g + ((static_cast<long long>(l + 1) * 12 + j) * 1024 + cj) * 8);
+        }
+    } else {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_b, t = (tile % tiles_per_b) * kRtFrames + f;
+        const bool live = t < p.T;
+        const float4* erow = reinterpret_cast<const float4*>(p.e + (static_cast<long long>(b) * p.T + (live ? t : 0)) * kRtE);
+        float cur[8];
+        {
+          const float4 a = live ? __ldg(erow) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 c = live ? __ldg(erow + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+          cur[0] = a.x; cur[1] = a.y; cur[2] = a.z; cur[3] = a.w; cur[4] = c.x; cur[5] = c.y; cur[6] = c.z; cur[7] = c.w;
+        }
+        for (int l = 0; l < p.n_levels; ++l) {
+          if (p.latents != nullptr && live) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) p.latents[(static_cast<long long>(b) * kRtE + l * 8 + k) * p.T + t] = cur[k];
+          }
+          // F.normalize: x / max(|x|_2, 1e-12)
+          float n2 = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) n2 = fmaf(cur[k], cur[k], n2);
+          const float den = fmaxf(sqrtf(n2), 1e-12f);
+          float hi[8], lo[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float en = __fdiv_rn(cur[k], den);
+            hi[k] = tf32_rna(en);
+            lo[k] = tf32_rna(en - hi[k]);
+          }
+          // A row (K = 32): [e_hi | e_lo | e_hi | 1 1 0 0 0 0 0 0] against B rows [c_hi | c_hi | c_lo | x_hi x_lo 0 ...]
+          sts128(a_row + ((0 ^ sw) << 4), make_float4(hi[0], hi[1], hi[2], hi[3]));
+          sts128(a_row + ((1 ^ sw) << 4), make_float4(hi[4], hi[5], hi[6], hi[7]));
+          sts128(a_row + ((2 ^ sw) << 4), make_float4(lo[0], lo[1], lo[2], lo[3]));
+          sts128(a_row + ((3 ^ sw) << 4), make_float4(lo[4], lo[5], lo[6], lo[7]));
+          sts128(a_row + ((4 ^ sw) << 4), make_float4(hi[0], hi[1], hi[2], hi[3]));
+          sts128(a_row + ((5 ^ sw) << 4), make_float4(hi[4], hi[5], hi[6], hi[7]));
+          sts128(a_row + ((6 ^ sw) << 4), make_float4(1.f, 1.f, 0.f, 0.f));
+          sts128(a_row + ((7 ^ sw) << 4), make_float4(0.f, 0.f, 0.f, 0.f));
+          fence_proxy_async_smem();
+          mbar_arrive(a_ready);
+
+          // next level's latent, minus everything that does not depend on this level's decision (loads overlap the scan);
+          // parked in shared memory so the scan keeps its registers for the TMEM loads in flight
+          if (l + 1 < p.n_levels) {
+            float nxt[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) nxt[k] = 0.f;
+            if (live) {
+              const float4 a = __ldg(erow + 2 * (l + 1)), c = __ldg(erow + 2 * (l + 1) + 1);
+              nxt[0] = a.x; nxt[1] = a.y; nxt[2] = a.z; nxt[3] = a.w; nxt[4] = c.x; nxt[5] = c.y; nxt[6] = c.z; nxt[7] = c.w;
+            }
+            for (int j = 0; j < l; ++j) {
+              const int cj = s_chosen[j * 128 + f];
+              const float4* gp = reinterpret_cast<const float4*>(p.g + ((static_cast<long long>(l + 1) * 12 + j) * 1024 + cj) * 8);
+              const float4 a = __ldg(gp), c = __ldg(gp + 1);
+              nxt[0] -= a.x; nxt[1] -= a.y; nxt[2] -= a.z; nxt[3] -= a.w; nxt[4] -= c.x; nxt[5] -= c.y; nxt[6] -= c.z; nxt[7] -= c.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s_nxt[k * 128 + f] = nxt[k];
+          }
+
+          float best;
+          int bidx;
+          scan_level(best, bidx);
+          // merge with the upper column half: larger score wins, equal scores go to the smaller code (first maximum)
+          switch (quad) {
+            case 0: asm volatile("barrier.sync 1, 64;" ::: "memory"); break;
+            case 1: asm volatile("barrier.sync 2, 64;" ::: "memory"); break;
+            case 2: asm volatile("barrier.sync 3, 64;" ::: "memory"); break;
+            default: asm volatile("barrier.sync 4, 64;" ::: "memory"); break;
+          }
+          {
+            const float ob = s_pbest[f];
+            const int oi = s_pidx[f];
+            if (ob > best || (ob == best && oi < bidx)) bidx = oi;
+          }
+
+          const long long oidx = (static_cast<long long>(b) * p.n_levels + l) * p.T + t;
+          if (live) p.codes[oidx] = bidx;
+          const int chosen = (p.forced != nullptr && live) ? static_cast<int>(p.forced[oidx]) : bidx;
+          s_chosen[l * 128 + f] = chosen;
+          if (l + 1 < p.n_levels) {
+            const float4* gp = reinterpret_cast<const float4*>(p.g + ((static_cast<long long>(l + 1) * 12 + l) * 1024 + chosen) * 8);
             const float4 a = __ldg(gp), c = __ldg(gp + 1);
-            nxt[0] -= a.x; nxt[1] -= a.y; nxt[2] -= a.z; nxt[3] -= a.w; nxt[4] -= c.x; nxt[5] -= c.y; nxt[6] -= c.z; nxt[7] -= c.w;
+            cur[0] = s_nxt[0 * 128 + f] - a.x; cur[1] = s_nxt[1 * 128 + f] - a.y; cur[2] = s_nxt[2 * 128 + f] - a.z;
+            cur[3] = s_nxt[3 * 128 + f] - a.w; cur[4] = s_nxt[4 * 128 + f] - c.x; cur[5] = s_nxt[5 * 128 + f] - c.y;
+            cur[6] = s_nxt[6 * 128 + f] - c.z; cur[7] = s_nxt[7 * 128 + f] - c.w;
           }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) s_nxt[k * 128 + f] = nxt[k];
-        }
-
-        RvqBest st;
-        st.best = -INFINITY;
-        st.gid = 0;
-        st.s[0] = st.s[1] = st.s[2] = st.s[3] = 0.f;
-        for (int ch = 0; ch < kRsChunks; ++ch, ++g) {
-          const uint32_t buf = g & 1;
-          const uint32_t taddr = tmem_row + buf * kRsChunk;
-          const int group_base = ch * (kRsChunk / 4);
-          mbar_wait(&tfull_bar[buf], (g >> 1) & 1);
-          tc_fence_after();
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32(taddr, r0);
-          tmem_ld_32x32(taddr + 32, r1);
-          tmem_ld_wait_dep(r0);
-          tmem_ld_wait_dep(r1);
-          if constexpr (kScan == 0) {
-            rvq_scan32<0>(r0, st, group_base, p.one, p.onei);
-            rvq_scan32<8>(r1, st, group_base, p.one, p.onei);
-          } else {
-            rvq_scan32_probe(r0, st);
-            rvq_scan32_probe(r1, st);
-          }
-          tmem_ld_32x32(taddr + 64, r0);
-          tmem_ld_32x32(taddr + 96, r1);
-          tmem_ld_wait_dep(r0);
-          tmem_ld_wait_dep(r1);
-          tc_fence_before();
-          mbar_arrive(&tempty_bar[buf]);  // the accumulator buffer may be overwritten by chunk g + 2
-          if constexpr (kScan == 0) {
-            rvq_scan32<16>(r0, st, group_base, p.one, p.onei);
-            rvq_scan32<24>(r1, st, group_base, p.one, p.onei);
-          } else {
-            rvq_scan32_probe(r0, st);
-            rvq_scan32_probe(r1, st);
-          }
-        }
-        // first position of the maximum inside the remembered group
-        const int bidx = st.gid * 4 + (st.s[0] == st.best ? 0 : st.s[1] == st.best ? 1 : st.s[2] == st.best ? 2 : 3);
-
-        const long long oidx = (static_cast<long long>(b) * p.n_levels + l) * p.T + t;
-        if (live) p.codes[oidx] = bidx;
-        const int chosen = (p.forced != nullptr && live) ? static_cast<int>(p.forced[oidx]) : bidx;
-        s_chosen[l * 128 + f] = chosen;
-        if (l + 1 < p.n_levels) {
-          const float4* gp = reinterpret_cast<const float4*>(p.g + ((static_cast<long long>(l + 1) * 12 + l) * 1024 + chosen) * 8);
-          const float4 a = __ldg(gp), c = __ldg(gp + 1);
-          cur[0] = s_nxt[0 * 128 + f] - a.x; cur[1] = s_nxt[1 * 128 + f] - a.y; cur[2] = s_nxt[2 * 128 + f] - a.z;
-          cur[3] = s_nxt[3 * 128 + f] - a.w; cur[4] = s_nxt[4 * 128 + f] - c.x; cur[5] = s_nxt[5 * 128 + f] - c.y;
-          cur[6] = s_nxt[6 * 128 + f] - c.z; cur[7] = s_nxt[7 * 128 + f] - c.w;
         }
       }
     }
