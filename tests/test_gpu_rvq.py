@@ -69,3 +69,28 @@ def test_rvq_bf16_input_and_errors():
     assert torch.equal(a, b)
     with pytest.raises(ValueError):
         q.encode(torch.randn(2, 512, 10))
+
+
+def test_rvq_full_size_config4_properties():
+    """BASELINE config 4 at full size (z [32, 1024, 3000]): batch-split invariance, bf16 == fp32 copy of the same values,
+    determinism, valid indices, and the first-level code equals a direct nearest-code search of the projected latents."""
+    cfg, sd, q = _setup()
+    z = torch.randn(32, 1024, 3000, device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    codes = q.encode(z)
+    assert codes.shape == (32, 12, 3000) and codes.min() >= 0 and codes.max() < 1024
+    assert torch.equal(codes, q.encode(z))
+    assert torch.equal(codes[5:9], q.encode(z[5:9].contiguous()))
+    assert torch.equal(codes[:, :, 1000:1512], q.encode(z[:, :, 1000:1512].contiguous()))     # frames are independent
+    zb = z.to(torch.bfloat16)
+    assert torch.equal(q.encode(zb), q.encode(zb.float()))
+    # level 0 against plain torch on the same folded tables: e0 = W_in_0 z + b; nearest normalised code
+    t = q._t
+    w0 = (t["w_hi"] + t["w_lo"])[:8]                                                             # [8, 1024]
+    e0 = torch.einsum("dc,bct->btd", w0.double(), z[:2].double()) + t["b_in"][:8].double()
+    en = torch.nn.functional.normalize(e0, dim=-1)
+    score = en @ t["cb_norm"][0].double().t() - 0.5 * t["cb_n2"][0].double()
+    ref0 = score.argmax(-1)
+    mism = ref0 != codes[:2, 0]
+    top2 = score.topk(2, dim=-1)[0]
+    assert ((top2[..., 0] - top2[..., 1])[mism] < 1e-5).all()
+    assert mism.float().mean().item() < 1e-3
