@@ -14,6 +14,7 @@
 #include "elementwise.cuh"
 #include "conv_stream.cuh"
 #include "gemm.cuh"
+#include "kmeans.cuh"
 #include "rvq.cuh"
 #include "rvq_tc.cuh"
 
@@ -518,6 +519,29 @@ extern "C" int edm_codes_to_features(const long long* codes, const float* proj, 
   dim3 grid((T + 31) / 32, B);
   codes_to_features_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   EDM_LAUNCH_CHECK("codes_to_features");
+  return 0;
+}
+
+extern "C" int edm_kmeans_assign(const float* x, long long n_frames, int dim, const float* c_hi, const float* c_lo, const float* half_neg_norm,
+                                 int n_centroids, long long* idx_out, float* score_out, void* stream) {
+  if (int rc = check_arch()) return rc;
+  if (n_frames <= 0) return 0;
+  if (dim <= 0 || dim % kKmKc != 0 || n_centroids <= 0 || n_centroids % kKmCodes != 0 || n_centroids > kKmMaxCentroids || n_frames > 0x7fffffffLL)
+    return fail(EDM_ERR_INVALID, "kmeans_assign shape frames=%lld dim=%d centroids=%d unsupported (dim %% 32, centroids %% 256, <= 4096)", n_frames, dim, n_centroids);
+  static bool attr_set = false;
+  if (!attr_set) {
+    EDM_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKmSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap mx, mh, ml;
+  if (int rc = make_tmap_f32_2d(&mx, x, static_cast<uint64_t>(n_frames), dim, dim, kKmFrames)) return rc;
+  if (int rc = make_tmap_f32_2d(&mh, c_hi, n_centroids, dim, dim, kKmCodes)) return rc;
+  if (int rc = make_tmap_f32_2d(&ml, c_lo, n_centroids, dim, dim, kKmCodes)) return rc;
+  KmeansParams p;
+  p.n_frames = static_cast<int>(n_frames); p.dim = dim; p.n_centroids = n_centroids; p.half_neg_norm = half_neg_norm; p.idx_out = idx_out; p.score_out = score_out;
+  const int tiles = (p.n_frames + kKmFrames - 1) / kKmFrames;
+  kmeans_assign_kernel<<<tiles < num_sms() ? tiles : num_sms(), kKmThreads, kKmSmemBytes, static_cast<cudaStream_t>(stream)>>>(mx, mh, ml, p);
+  EDM_LAUNCH_CHECK("kmeans_assign");
   return 0;
 }
 

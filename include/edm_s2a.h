@@ -109,6 +109,14 @@ void edm_rvq_tc_debug(unsigned lbo, unsigned sbo, int skip_project, int scan_pro
 int edm_codes_to_features(const long long* codes, const float* proj, float* out, int B, int L, int T, int unreduced,
                           void* stream);
 
+/* Nearest-centroid assignment (HuBERT k-means step of the semantic tokenizer): x [n_frames, dim] fp32 -> idx int64 [n_frames],
+ * idx = argmax_c (x . c - |c|^2 / 2) = argmin_c |x - c|_2, first maximum on ties. c_hi / c_lo [n_centroids, dim]: tf32 split of
+ * the centroids, half_neg_norm [n_centroids] = -|c|^2 / 2 (edm_tts_b200/kmeans.py packs them); dim % 32 == 0, n_centroids % 256
+ * == 0 and <= 4096. score_out (nullable) receives the winning score. Replaces `(-torch.cdist(embed, centers)).argmax(-1)`,
+ * edm_tts/models/audio_tokenizer/semantic_tokenizer_hubert/semantic_tokenizer_hubert.py:74-90. */
+int edm_kmeans_assign(const float* x, long long n_frames, int dim, const float* c_hi, const float* c_lo,
+                      const float* half_neg_norm, int n_centroids, long long* idx_out, float* score_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * S2A decoder context: InjectionConformerModel.infer_special, modeling_injection_conformer.py:130-230, and
  * InjectionConformerWrapper.forward_first_level / forward, injection_conformer_wrapper.py:65-150.
