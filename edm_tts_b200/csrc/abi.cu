@@ -192,6 +192,15 @@ bool gemm_resid_tma() {
 }
 
 
+bool gemm_out_tma() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EDM_OUT_TMA");  // bring-up switch: 0 = bf16 epilogues store from registers
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int EPI>
 int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
@@ -200,6 +209,10 @@ int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
     EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     if (EPI == EPI_RESID_F32)
       EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI_RESID_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    if (EPI == EPI_SWISH_BF16)
+      EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI_SWISH_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    if (EPI == EPI_QKV_ROPE)
+      EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI_ROPE_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     attr_set = true;
   }
   ProfScope prof(PK_GEMM, 2.0 * p.M * p.N * p.K, st);
@@ -212,6 +225,14 @@ int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
       CUtensorMap mc;
       if (int rc = make_tmap_f32_2d(&mc, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
       gemm_bf16_tn_pair_kernel<EPI_RESID_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
+    } else if ((EPI == EPI_SWISH_BF16 || EPI == EPI_QKV_ROPE) && gemm_out_tma() && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 2) % 16 == 0) {
+      // bf16 tiles leave as TMA store boxes (whole 128-byte lines) instead of 16-byte stores from registers
+      CUtensorMap mc;
+      if (int rc = make_tmap_2d(&mc, p.out, p.M, p.N, p.ldo, 32)) return rc;
+      if (EPI == EPI_SWISH_BF16)
+        gemm_bf16_tn_pair_kernel<EPI_SWISH_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
+      else
+        gemm_bf16_tn_pair_kernel<EPI_ROPE_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
     } else {
       gemm_bf16_tn_pair_kernel<EPI><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, ma, p);
     }

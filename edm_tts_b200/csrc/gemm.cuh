@@ -25,6 +25,8 @@ enum EpiKind : int {
   EPI_F32 = 4,         // out_f32 = acc + bias                                                   (logits heads)
   EPI_GLU_BF16 = 5,    // per 64 columns: first 32 = value, last 32 = gate (weights interleaved at pack time);
                        // out_bf16[., N/2] = bf16(bf16(value) * bf16(sigmoid(bf16(gate))))       (conv module pointwise-1 + GLU)
+  EPI_ROPE_TMA = 8,    // EPI_QKV_ROPE with TMA store boxes
+  EPI_SWISH_TMA = 7,   // EPI_SWISH_BF16 with the tile leaving as TMA store boxes (pair kernel only; launcher's choice)
   EPI_RESID_TMA = 6,   // EPI_RESID_F32 with the add carried out as TMA reduce-add boxes (pair kernel only; chosen by the
                        // launcher, not part of the ABI): 128 B rows reach L2 as whole lines instead of 16 B reductions
 };
@@ -112,9 +114,17 @@ __device__ __forceinline__ void gemm_store_glu(const GemmParams& p, int row, int
 
 // tab_row: shared-space address of this row's cos|sin (16 float4, chunk index XOR-swizzled by swz), or 0 to read the
 // global tables directly.
+// stg_row != 0: the 8 output chunks go to this row of a 128B-swizzled shared-memory staging box (chunk c at (c ^ swz) * 16)
+// instead of global memory.
 __device__ __forceinline__ void gemm_epilogue_rope64(const GemmParams& p, int row, int col, const uint32_t (&lo)[32],
-                                                     const uint32_t (&hi)[32], uint32_t tab_row = 0, int swz = 0) {
+                                                     const uint32_t (&hi)[32], uint32_t tab_row = 0, int swz = 0, uint32_t stg_row = 0) {
   uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(row) * p.ldo + col);
+  auto put = [&](int c, uint4 v) {
+    if (stg_row != 0)
+      sts128(stg_row + ((c ^ swz) << 4), make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)));
+    else
+      o[c] = v;
+  };
   // the projection output is bf16 in the reference: round first (also halves the live registers)
   uint32_t l2[16], h2[16];
 #pragma unroll
@@ -151,14 +161,14 @@ __device__ __forceinline__ void gemm_epilogue_rope64(const GemmParams& p, int ro
         ol[q] = pack_bf16x2(__fadd_rn(__fmul_rn(x1a, c0), __fmul_rn(-x2a, s0)), __fadd_rn(__fmul_rn(x1b, c1), __fmul_rn(-x2b, s1)));
         oh[q] = pack_bf16x2(__fadd_rn(__fmul_rn(x2a, c0), __fmul_rn(x1a, s0)), __fadd_rn(__fmul_rn(x2b, c1), __fmul_rn(x1b, s1)));
       }
-      o[g] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-      o[4 + g] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+      put(g, make_uint4(ol[0], ol[1], ol[2], ol[3]));
+      put(4 + g, make_uint4(oh[0], oh[1], oh[2], oh[3]));
     }
   } else {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      o[g] = make_uint4(l2[4 * g], l2[4 * g + 1], l2[4 * g + 2], l2[4 * g + 3]);
-      o[4 + g] = make_uint4(h2[4 * g], h2[4 * g + 1], h2[4 * g + 2], h2[4 * g + 3]);
+      put(g, make_uint4(l2[4 * g], l2[4 * g + 1], l2[4 * g + 2], l2[4 * g + 3]));
+      put(4 + g, make_uint4(h2[4 * g], h2[4 * g + 1], h2[4 * g + 2], h2[4 * g + 3]));
     }
   }
 }
@@ -347,7 +357,9 @@ template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                          const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
-  constexpr int kSt = (EPI == EPI_RESID_TMA) ? kPairStagesTma : kPairStages;
+  constexpr bool kTmaOut = EPI == EPI_RESID_TMA || EPI == EPI_SWISH_TMA || EPI == EPI_ROPE_TMA;
+  constexpr bool kRope = EPI == EPI_QKV_ROPE || EPI == EPI_ROPE_TMA;
+  constexpr int kSt = kTmaOut ? kPairStagesTma : kPairStages;
   static_assert(kPairStagesTma * kPairStageBytes + kGemmEpiWarps * kPairStagingBytes == kPairStages * kPairStageBytes, "smem budget");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -453,7 +465,7 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       const int col0 = n_blk * kGemmBN + sub * 64;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kGemmBN + sub * 64;
       bool rope_tile = false;
-      if constexpr (EPI == EPI_QKV_ROPE) {
+      if constexpr (kRope) {
         // The rotary cos|sin rows of this CTA's 128 token rows go to shared memory (the bias area is free: no bias here)
         // while the tile's mainloop is still running: one coalesced 32 KB read per tile instead of 4 x 128 rows x 256 B
         // of dependent 16-byte loads. Chunk index is XOR-swizzled with (row & 7) so row-per-lane reads are conflict-free.
@@ -485,6 +497,55 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      if constexpr (EPI == EPI_ROPE_TMA) {
+        uint8_t* stg = smem + kSt * kPairStageBytes + (warp - 2) * kPairStagingBytes;
+        const int tr = quad * 32 + lane;
+        if (lane == 0) bulk_wait_group_read0();
+        __syncwarp();
+        gemm_epilogue_rope64(p, row, col0, r0, r1, rope_tile ? smem_u32(s_bias) + tr * 256 : 0u, tr & 7, smem_u32(stg) + lane * 128);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tma_c, stg, col0, m_blk * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM + quad * 32);
+          bulk_commit_group();
+        }
+        continue;
+      }
+      if constexpr (EPI == EPI_SWISH_TMA) {
+        // bf16 output: the warp's 32 x 64 slice is one 32-row x 128-byte box in its staging buffer (128B-swizzled rows), stored
+        // by TMA as whole lines instead of 32 x 8 scattered 16-byte stores; rows beyond M are clipped by the tensor map
+        uint8_t* stg = smem + kSt * kPairStageBytes + (warp - 2) * kPairStagingBytes;
+        const uint32_t stg_row = smem_u32(stg) + lane * 128;
+        const int sw = lane & 7;
+        const int row0 = m_blk * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM + quad * 32;
+        const uint32_t b4 = smem_u32(s_bias + col0);
+        uint32_t w[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t* r = h == 0 ? r0 : r1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = lds128(b4 + 16 * (8 * h + i));
+            const uint32_t h01 = pack_bf16x2(__uint_as_float(r[4 * i + 0]) + b.x, __uint_as_float(r[4 * i + 1]) + b.y);
+            const uint32_t h23 = pack_bf16x2(__uint_as_float(r[4 * i + 2]) + b.z, __uint_as_float(r[4 * i + 3]) + b.w);
+            w[16 * h + 2 * i] = bf16x2_mul(h01, pack_bf16x2(sigmoid_tanh(bf16lo(h01)), sigmoid_tanh(bf16hi(h01))));
+            w[16 * h + 2 * i + 1] = bf16x2_mul(h23, pack_bf16x2(sigmoid_tanh(bf16lo(h23)), sigmoid_tanh(bf16hi(h23))));
+          }
+        }
+        if (lane == 0) bulk_wait_group_read0();  // the previous tile's box has been read out of the staging buffer
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          sts128(stg_row + ((c ^ sw) << 4), make_float4(__uint_as_float(w[4 * c]), __uint_as_float(w[4 * c + 1]), __uint_as_float(w[4 * c + 2]),
+                                                       __uint_as_float(w[4 * c + 3])));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tma_c, stg, col0, row0);
+          bulk_commit_group();
+        }
+        continue;
+      }
       if constexpr (EPI == EPI_RESID_TMA) {
         // x[rows, cols] += scale * bf16(acc + bias): the warp's 32 x 64 slice leaves as two 32 x 32 fp32 boxes through its
         // 4 KB staging buffer (128B-swizzled rows); rows beyond M are clipped by the tensor map
@@ -556,7 +617,7 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     }
   }
 
-  if constexpr (EPI == EPI_RESID_TMA) {
+  if constexpr (kTmaOut) {
     if (warp >= 2 && lane == 0) bulk_wait_group0();  // staging buffers must outlive the reductions that read them
   }
   tc_fence_before();
