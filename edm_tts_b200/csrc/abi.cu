@@ -192,6 +192,15 @@ bool gemm_resid_tma() {
 }
 
 
+int resid_tma_max_k() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EDM_RESID_TMA_MAXK");  // bring-up knob: largest K whose residual epilogue goes through TMA reduce
+    v = e != nullptr ? atoi(e) : 2048;
+  }
+  return v;
+}
+
 bool gemm_out_tma() {
   static int v = -1;
   if (v < 0) {
@@ -221,7 +230,7 @@ int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
     const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
     // short-K residual GEMMs are epilogue-bound: their add leaves as TMA reduce boxes (0.113 -> 0.081 ms at K = 1024); at
     // K = 4096 the mainloop hides the register-issued reductions and the 6-stage ring is worth more (0.202 vs 0.208 ms)
-    if (EPI == EPI_RESID_F32 && gemm_resid_tma() && p.K <= 2048 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 4) % 16 == 0) {
+    if (EPI == EPI_RESID_F32 && gemm_resid_tma() && p.K <= resid_tma_max_k() && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 4) % 16 == 0) {
       CUtensorMap mc;
       if (int rc = make_tmap_f32_2d(&mc, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
       gemm_bf16_tn_pair_kernel<EPI_RESID_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);

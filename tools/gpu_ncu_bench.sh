@@ -7,8 +7,8 @@ CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/plain_ncu_bench.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_ncu_bench.log; exit 1; }
 tail -c 600 gpurun_out/plain_ncu_bench.log
 # launches per decode step: 469 GEMMs, 56 attention, 238 LayerNorm, 56 conv-module; 3 warm-up steps precede the timed one
-declare -A PAT=( [gemm]="gemm_bf16_tn_pair_kernel" [attn]="attention_fwd_kernel" [ln]="layernorm_kernel" [conv]="conv_module_kernel" [rvq]="rvq_" )
-declare -A SKIP=( [gemm]=1430 [attn]=170 [ln]=720 [conv]=170 [rvq]=3 )
+declare -A PAT=( [gemm]="gemm_bf16_tn_pair_kernel" [attn]="attention_fwd_kernel" [ln]="layernorm_kernel" [conv]="conv_stream_kernel" [rvq]="rvq_" )
+declare -A SKIP=( [gemm]=1430 [attn]=170 [ln]=720 [conv]=170 [rvq]=8 )
 declare -A CNT=( [gemm]=8 [attn]=1 [ln]=4 [conv]=1 [rvq]=2 )
 for c in ${@:-gemm attn ln conv rvq}; do
   ncu --set full --clock-control none --import-source on -k regex:${PAT[$c]} -s ${SKIP[$c]} -c ${CNT[$c]} -o gpurun_out/bench_$c -f $CMD > gpurun_out/ncu_bench_$c.log 2>&1
