@@ -267,6 +267,9 @@ int launch_gemm(int epi, const CUtensorMap& ma, const CUtensorMap& mb, const Gem
   return fail(EDM_ERR_INVALID, "unknown epilogue %d", epi);
 }
 
+#ifdef EDM_ATTN_TRACE
+unsigned long long* g_attn_trace = nullptr;
+#endif
 int launch_attention(const CUtensorMap& mqkv, int B, int N, int H, void* out, uint32_t lbo, uint32_t sbo, uint32_t kstep, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -280,6 +283,9 @@ int launch_attention(const CUtensorMap& mqkv, int B, int N, int H, void* out, ui
   p.ldo = static_cast<long long>(H) * 64;
   p.scale_log2e = 0.125f * 1.4426950408889634f;
   p.v_lbo = lbo; p.v_sbo = sbo; p.v_kstep = kstep;
+#ifdef EDM_ATTN_TRACE
+  p.trace = g_attn_trace;
+#endif
   const int items = ((N + 255) / 256) * H * B;
   dim3 grid(items < num_sms() ? items : num_sms());
   ProfScope prof(PK_ATTN, 4.0 * B * H * static_cast<double>(N) * N * 64, st);
@@ -413,6 +419,9 @@ extern "C" int edm_gemm_bf16(const void* a, long long lda, const void* b, long l
   return launch_gemm(epilogue, ma, mb, p, static_cast<cudaStream_t>(stream));
 }
 
+#ifdef EDM_ATTN_TRACE
+extern "C" void edm_attn_set_trace(unsigned long long* p) { g_attn_trace = p; }
+#endif
 extern "C" int edm_attention_dbg(const void* qkv, int B, int N, int H, void* out, unsigned v_lbo, unsigned v_sbo,
                                  unsigned v_kstep, void* stream) {
   if (int rc = check_arch()) return rc;

@@ -13,7 +13,7 @@
 //                       O stays in TMEM and is rescaled there only when the running max moves by more than 2^8
 //                       (warp-uniform decision), so after the first tile the rescale path is practically never taken.
 //   warp 8            : TMA producer (both Q tiles once, then a 3-deep K/V ring shared by the two query tiles)
-//   warp 9            : TMEM allocator + single-thread MMA issuer. S_w(j+1) is issued as soon as the warpgroup has pulled
+//   warp 9            : TMEM allocator + MMA issuer (whole warp in warp-uniform code, one elected lane issues). S_w(j+1) is issued as soon as the warpgroup has pulled
 //                       S_w(j) into registers (s_free), i.e. before P_w(j) V(j), so the next scores are ready when the
 //                       exp2 phase of the current tile ends.
 //                       (One issuer per query tile, warp 10 taking tile 1, was measured slower: 0.171 vs 0.154 ms at B=64,
@@ -34,7 +34,15 @@ struct AttnParams {
   float scale_log2e;      // softmax scale * log2(e)
   // MN-major V descriptor knobs (bytes); defaults 1024 / 1024 / 2048, exposed so a bring-up run can sweep them.
   uint32_t v_lbo, v_sbo, v_kstep;
+#ifdef EDM_ATTN_TRACE
+  unsigned long long* trace;  // bring-up build only (tools/gpu_attn_trace.sh): clock64 stamps of CTA 0, [kv iteration][16 events]
+#endif
 };
+#ifdef EDM_ATTN_TRACE
+#define ATTN_TRACE(g, k) do { if (blockIdx.x == 0 && p.trace != nullptr && (g) < 96) p.trace[(g) * 16 + (k)] = clock64(); } while (0)
+#else
+#define ATTN_TRACE(g, k) do { } while (0)
+#endif
 
 constexpr int kAttnThreads = 384;
 constexpr int kAttnKvStages = 3;
@@ -138,7 +146,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
         }
       }
     } else if (warp == 9) {
-      if (lane == 0 && total_g > 0) {
+      if (total_g > 0) {  // whole warp, warp-uniform control flow; one elected lane issues (umma_*_warp)
         constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
         constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
         // scores of kv iteration g for tile w (both tiles are issued back to back by the callers)
@@ -147,8 +155,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
           const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + (i & 1) * 2 * kAttnTile + w * kAttnTile), 16, 1024);
           const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + (g % kAttnKvStages) * kAttnTile), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + w * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(&s_full[w]);
+          for (int k = 0; k < 4; ++k) umma_ss_warp(tmem_base + w * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+          umma_commit_warp(&s_full[w]);
         };
         auto issue_pv = [&](int w, int g) {
           const uint32_t p_addr = smem_u32(sP + w * 2 * kAttnTile);
@@ -160,39 +168,43 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
           for (int k = 0; k < 8; ++k) {
             const uint64_t adesc = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
             const uint64_t bdesc = umma_desc_sw128(v_addr + k * p.v_kstep, p.v_lbo, p.v_sbo);
-            umma_ss(tmem_base + 256 + w * 64, adesc, bdesc, idesc_o, (!first || k != 0) ? 1u : 0u);
+            umma_ss_warp(tmem_base + 256 + w * 64, adesc, bdesc, idesc_o, (!first || k != 0) ? 1u : 0u);
           }
-          umma_commit(&o_full[w]);
+          umma_commit_warp(&o_full[w]);
         };
-        mbar_wait(&q_full[0], 0);
-        mbar_wait(&kv_full[0], 0);
+        mbar_wait_spin(&q_full[0], 0);
+        mbar_wait_spin(&kv_full[0], 0);
         tc_fence_after();
         issue_s(0, 0);
         issue_s(1, 0);
-        if (n_kv == 1) umma_commit(&q_empty[0]);
+        if (n_kv == 1) umma_commit_warp(&q_empty[0]);
         for (int g = 0; g < total_g; ++g) {
           if (g + 1 < total_g) {
             // next scores as soon as each warpgroup has drained S_w(g) into registers
             const int g1 = g + 1;
             const int i1 = g1 / n_kv, j1 = g1 % n_kv;
-            if (j1 == 0) mbar_wait(&q_full[i1 & 1], (i1 >> 1) & 1);
-            mbar_wait(&kv_full[g1 % kAttnKvStages], (g1 / kAttnKvStages) & 1);
-            mbar_wait(&s_free[0], g & 1);
+            if (j1 == 0) mbar_wait_spin(&q_full[i1 & 1], (i1 >> 1) & 1);
+            mbar_wait_spin(&kv_full[g1 % kAttnKvStages], (g1 / kAttnKvStages) & 1);
+            mbar_wait_spin(&s_free[0], g & 1);
             tc_fence_after();
             issue_s(0, g1);
-            mbar_wait(&s_free[1], g & 1);
+            ATTN_TRACE(g1, 8);
+            mbar_wait_spin(&s_free[1], g & 1);
             tc_fence_after();
             issue_s(1, g1);
-            if (j1 == n_kv - 1) umma_commit(&q_empty[i1 & 1]);  // Q slot reusable once the item's last scores are done
+            ATTN_TRACE(g1, 9);
+            if (j1 == n_kv - 1) umma_commit_warp(&q_empty[i1 & 1]);  // Q slot reusable once the item's last scores are done
           }
           // P_w(g) is in smem (and O_w rescaled if needed)
-          mbar_wait(&p_full[0], g & 1);
+          mbar_wait_spin(&p_full[0], g & 1);
           tc_fence_after();
           issue_pv(0, g);
-          mbar_wait(&p_full[1], g & 1);
+          ATTN_TRACE(g, 10);
+          mbar_wait_spin(&p_full[1], g & 1);
           tc_fence_after();
           issue_pv(1, g);
-          umma_commit(&kv_empty[g % kAttnKvStages]);  // K / V stage free once everything issued so far has completed
+          ATTN_TRACE(g, 11);
+          umma_commit_warp(&kv_empty[g % kAttnKvStages]);  // K / V stage free once everything issued so far has completed
         }
       }
     }
@@ -208,6 +220,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
     uint8_t* p_row = sP + w * 2 * kAttnTile + row_in_tile * 128;
     const int sw = row_in_tile & 7;
 
+    if (w == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");  // warpgroup 0 takes the first softmax phase
     for (int i = 0; i < my_items; ++i) {
       const int it = blockIdx.x + i * gridDim.x;
       const int qt2 = it % n_q2, h = (it / n_q2) % p.H, b = it / (n_q2 * p.H);
@@ -219,6 +232,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
         const int g = i * n_kv + j;
         mbar_wait(&s_full[w], g & 1);
         tc_fence_after();
+        if ((warp & 3) == 0 && lane == 0) ATTN_TRACE(g, 4 * w + 0);
         uint32_t s0[32], s1[32], s2[32], s3[32];
         tmem_ld_32x32(tmem_S, s0);
         tmem_ld_32x32(tmem_S + 32, s1);
@@ -230,6 +244,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
         tmem_ld_wait_dep(s3);
         tc_fence_before();
         mbar_arrive(&s_free[w]);  // S_w may be overwritten by the next Q K^T
+        if ((warp & 3) == 0 && lane == 0) ATTN_TRACE(g, 4 * w + 1);
         const int kv_valid = p.N - j * 128;
         if (kv_valid < 128) {  // only the last tile of a ragged sequence: padded key columns -> -inf
 #pragma unroll
@@ -261,6 +276,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
           mbar_wait(&o_full[w], (g - 1) & 1);
           tc_fence_after();
         }
+        if ((warp & 3) == 0 && lane == 0) ATTN_TRACE(g, 4 * w + 2);
         if (j > 0 && __any_sync(0xffffffffu, need)) {
           // O_w *= alpha in TMEM; PV(g) is not issued before our p_full arrive
 #pragma unroll
@@ -294,14 +310,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
             *reinterpret_cast<uint4*>(half + chunk * 16) = make_uint4(wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
           }
         };
+        // Ping-pong the softmax phases of the two warpgroups (named barriers 2 + w, 256 threads: 128 waiting + 128 arriving): the
+        // phase is MUFU-bound (128 ex2 per thread), so two warpgroups inside it at once just take twice as long, while strict
+        // alternation lets one warpgroup's TMEM drain / row max / barrier waits run under the other's exp2 phase. Left alone the
+        // two drift into lock-step (measured: 3.6 k cycles per kv iteration, 2.5 k of them in a contended exp2 phase; 3.2 k
+        // with the hand-over). Narrower critical sections (ex2 only, or ex2 + sums) were measured slower.
+        if (w == 0) asm volatile("bar.sync 2, 256;" ::: "memory"); else asm volatile("bar.sync 3, 256;" ::: "memory");
         emit(s0, 0);
         emit(s1, 1);
         emit(s2, 2);
         emit(s3, 3);
+        if (w == 0) asm volatile("bar.arrive 3, 256;" ::: "memory"); else asm volatile("bar.arrive 2, 256;" ::: "memory");
         l_run += ls0 + ls1;
         tc_fence_before();
         fence_proxy_async_smem();
         mbar_arrive(&p_full[w]);
+        if ((warp & 3) == 0 && lane == 0) ATTN_TRACE(g, 4 * w + 3);
       }
       // item epilogue: O_w / l
       mbar_wait(&o_full[w], (i * n_kv + n_kv - 1) & 1);

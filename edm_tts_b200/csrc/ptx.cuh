@@ -70,6 +70,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+// Non-suspending wait: polls with mbarrier.test_wait. try_wait parks the thread in hardware and its wake-up after the phase
+// flips was measured at ~0.8-1.4 k cycles in the attention kernel's MMA-issuing thread, where that reaction time is on the
+// critical path; a single polling thread costs next to nothing.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+#if EDM_WATCHDOG
+  long long t0 = clock64();
+#endif
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+#if EDM_WATCHDOG
+    if (!ok && clock64() - t0 > 4000000000LL) __trap();
+#endif
+  } while (!ok);
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {  // explicit shared-space load (generic pointers compile to LD.E)
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
@@ -198,6 +222,30 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Whole-warp variants: every lane executes the (warp-uniform) descriptor arithmetic, one elected lane issues. Keeping the issuing
+// code out of an `if (lane == 0)` region lets the compiler hold the descriptors in uniform registers; inside a divergent region it
+// wraps every tcgen05.mma in an ELECT / R2UR / BRA.U.ANY sequence (~20 instructions with latency per MMA, which made the single
+// issuing thread the critical path of the attention kernel).
+__device__ __forceinline__ void umma_ss_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_warp(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar))
       : "memory");
 }
 // mbarrier arrives once all previously issued MMAs of this thread have completed (implies fence::before_thread_sync).
