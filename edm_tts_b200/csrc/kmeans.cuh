@@ -91,7 +91,7 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp, warp-uniform control flow; one elected lane issues (umma_*_warp, see ptx.cuh)
       constexpr uint32_t idesc = umma_idesc_tf32(kKmFrames, kKmCodes, 0, 0);
       for (uint32_t it = 0; it < total_steps; ++it) {
         const uint32_t chunk = it / n_kc;              // (tile, code chunk) counter of this CTA
@@ -110,12 +110,12 @@ kmeans_assign_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_con
         const uint32_t d_tmem = tmem_base + buf * kKmCodes;
 #pragma unroll
         for (int k = 0; k < kKmKc / 8; ++k) {
-          umma_ss_tf32(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
-          umma_ss_tf32(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-          umma_ss_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+          umma_ss_tf32_warp(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+          umma_ss_tf32_warp(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+          umma_ss_tf32_warp(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
         }
-        umma_commit(&empty_bar[s]);
-        if (kc == n_kc - 1) umma_commit(&tfull_bar[buf]);
+        umma_commit_warp(&empty_bar[s]);
+        if (kc == n_kc - 1) umma_commit_warp(&tfull_bar[buf]);
       }
     }
   } else if (warp < 6) {

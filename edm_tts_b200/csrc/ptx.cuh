@@ -273,6 +273,18 @@ __device__ __forceinline__ void umma_ss_tf32(uint32_t d_tmem, uint64_t a_desc, u
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// whole-warp variant (see umma_ss_warp): warp-uniform operands, one elected lane issues
+__device__ __forceinline__ void umma_ss_tf32_warp(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // fp32 -> tf32 (round to nearest, ties away): the result is an fp32 bit pattern with the low 13 mantissa bits clear
 __device__ __forceinline__ float tf32_rna(float v) {
   uint32_t r;

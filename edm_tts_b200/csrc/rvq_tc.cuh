@@ -136,7 +136,7 @@ rvq_project_kernel(const __grid_constant__ CUtensorMap tma_z, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp, warp-uniform control flow; one elected lane issues (umma_*_warp, see ptx.cuh)
       constexpr uint32_t idesc = umma_idesc_tf32(kRtFrames, kRtE, /*a_mn_major=*/1, 0);
       for (uint32_t it = 0; it < total_steps; ++it) {
         const uint32_t tl = it / kNumKc, kc = it % kNumKc;
@@ -163,18 +163,18 @@ rvq_project_kernel(const __grid_constant__ CUtensorMap tma_z, const __grid_const
           for (int m = 0; m < kRpFrames / 128; ++m) {
             const uint64_t a_hi = umma_desc_sw128_base32(zh + m * 16384 + k * 1024, p.a_lbo, p.a_sbo);
             if constexpr (kBf16) {
-              umma_ss_tf32(d_tmem + m * 128, a_hi, b_lo, idesc, (kc | k) != 0 ? 1u : 0u);
+              umma_ss_tf32_warp(d_tmem + m * 128, a_hi, b_lo, idesc, (kc | k) != 0 ? 1u : 0u);
             } else {
               const uint64_t a_lo = umma_desc_sw128_base32(lw + m * 16384 + k * 1024, p.a_lbo, p.a_sbo);
-              umma_ss_tf32(d_tmem + m * 128, a_lo, b_hi, idesc, (kc | k) != 0 ? 1u : 0u);
-              umma_ss_tf32(d_tmem + m * 128, a_hi, b_lo, idesc, 1u);
+              umma_ss_tf32_warp(d_tmem + m * 128, a_lo, b_hi, idesc, (kc | k) != 0 ? 1u : 0u);
+              umma_ss_tf32_warp(d_tmem + m * 128, a_hi, b_lo, idesc, 1u);
             }
-            umma_ss_tf32(d_tmem + m * 128, a_hi, b_hi, idesc, 1u);
+            umma_ss_tf32_warp(d_tmem + m * 128, a_hi, b_hi, idesc, 1u);
           }
         }
-        if constexpr (!kBf16) umma_commit(&z_empty[zs]);
-        umma_commit(&lw_empty[ls]);
-        if (kc == kNumKc - 1) umma_commit(&tfull_bar[acc]);
+        if constexpr (!kBf16) umma_commit_warp(&z_empty[zs]);
+        umma_commit_warp(&lw_empty[ls]);
+        if (kc == kNumKc - 1) umma_commit_warp(&tfull_bar[acc]);
       }
     }
   } else if (warp < 6) {
@@ -391,7 +391,7 @@ rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchPar
           }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // whole warp, warp-uniform control flow; one elected lane issues (umma_*_warp, see ptx.cuh)
       constexpr uint32_t idesc = umma_idesc_tf32(kRtFrames, kRsChunk, 0, 0);
       const uint64_t adesc = umma_desc_sw128(smem_u32(sA), 16, 1024);
       uint32_t g = 0, it = 0;
@@ -405,9 +405,9 @@ rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchPar
             tc_fence_after();
             const uint64_t bdesc = umma_desc_sw128(smem_u32(sRing + s * kRsTileBytes), 16, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss_tf32(tmem_base + buf * kRsChunk, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0 ? 1u : 0u);
-            umma_commit(&ring_empty[s]);
-            umma_commit(&tfull_bar[buf]);
+            for (int k = 0; k < 4; ++k) umma_ss_tf32_warp(tmem_base + buf * kRsChunk, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0 ? 1u : 0u);
+            umma_commit_warp(&ring_empty[s]);
+            umma_commit_warp(&tfull_bar[buf]);
           }
         }
     }
