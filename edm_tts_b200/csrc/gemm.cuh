@@ -425,7 +425,7 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {  // whole warp of CTA 0, warp-uniform control flow; one elected lane issues (umma_*_pair_warp, see ptx.cuh)
       constexpr uint32_t idesc = umma_idesc_bf16(2 * kGemmBM, kGemmBN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -442,14 +442,14 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
           const uint64_t bdesc = umma_desc_sw128(sa + kGemmABytes, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < kGemmBK / 16; ++k) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_pair(&empty_bar[stage]);
+          for (int k = 0; k < kGemmBK / 16; ++k) umma_ss_pair_warp(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_pair_warp(&empty_bar[stage]);
           if (++stage == kSt) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_pair(&tmem_full_bar[acc]);
+        umma_commit_pair_warp(&tmem_full_bar[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
