@@ -170,6 +170,20 @@ int make_tmap_f32_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
 }
 
 // ---------------------------------------------------------------------------------------------- launch helpers
+// Boustrophedon traversal: consecutive launches walk their rows / tiles in opposite directions, so a kernel starts with the part
+// of its input that its producer wrote last and that is still in the 126 MB L2 (the hand-offs of the decoder are 66-262 MB).
+int next_direction() {
+  static int enabled = -1;
+  static int dir = 0;
+  if (enabled < 0) {
+    const char* e = getenv("EDM_FLIP");  // bring-up switch: 0 = every kernel walks forward
+    enabled = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return 0;
+  dir ^= 1;
+  return dir;
+}
+
 bool gemm_use_pairs() {
   static int v = -1;
   if (v < 0) {
@@ -211,7 +225,9 @@ bool gemm_out_tma() {
 }
 
 template <int EPI>
-int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p_in, cudaStream_t st) {
+  GemmParams p = p_in;
+  p.reverse = next_direction();
   static bool attr_set = false;
   if (!attr_set) {
     EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
@@ -282,7 +298,7 @@ int launch_attention(const CUtensorMap& mqkv, int B, int N, int H, void* out, ui
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = static_cast<long long>(H) * 64;
   p.scale_log2e = 0.125f * 1.4426950408889634f;
-  p.v_lbo = lbo; p.v_sbo = sbo; p.v_kstep = kstep;
+  p.v_lbo = lbo; p.v_sbo = sbo; p.v_kstep = kstep; p.reverse = next_direction();
 #ifdef EDM_ATTN_TRACE
   p.trace = g_attn_trace;
 #endif
@@ -294,8 +310,10 @@ int launch_attention(const CUtensorMap& mqkv, int B, int N, int H, void* out, ui
   return 0;
 }
 
-int launch_ln(const LnParams& p, cudaStream_t st) {
-  if (p.rows <= 0) return 0;
+int launch_ln(const LnParams& p_in, cudaStream_t st) {
+  if (p_in.rows <= 0) return 0;
+  LnParams p = p_in;
+  p.reverse = next_direction();
   // algorithmic bytes: one read of the row + each requested output
   ProfScope prof(PK_LN, static_cast<double>(p.rows) * kD * ((p.in_is_bf16 ? 2 : 4) + (p.y_out ? 4 : 0)) +
                             (p.z_out ? static_cast<double>(p.rows) * (p.z_skip > 0 ? static_cast<double>(p.seq_len - p.z_skip) / p.seq_len : 1.0) * kD * 2 : 0.0), st);
@@ -341,6 +359,7 @@ int launch_conv(const ConvModParams& p, bool glu_input, cudaStream_t st) {
     ConvStreamParams q;
     q.in = p.in; q.out = p.out; q.dw_w = p.dw_w; q.dw_b = p.dw_b; q.cln_w = p.cln_w; q.B = p.B; q.N = p.N;
     q.run_len = best_len;
+    q.reverse = next_direction();
     q.runs_per_seq = (p.N + q.run_len - 1) / q.run_len;
     const long long units = static_cast<long long>(p.B) * q.runs_per_seq;
     conv_stream_kernel<<<static_cast<unsigned>(units < sms ? units : sms), kCsThreads, kCsSmemBytes, st>>>(q);

@@ -34,6 +34,7 @@ struct AttnParams {
   float scale_log2e;      // softmax scale * log2(e)
   // MN-major V descriptor knobs (bytes); defaults 1024 / 1024 / 2048, exposed so a bring-up run can sweep them.
   uint32_t v_lbo, v_sbo, v_kstep;
+  int reverse;            // 1: work items are walked from the last to the first
 #ifdef EDM_ATTN_TRACE
   unsigned long long* trace;  // bring-up build only (tools/gpu_attn_trace.sh): clock64 stamps of CTA 0, [kv iteration][16 events]
 #endif
@@ -128,7 +129,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
     if (warp == 8) {
       if (lane == 0) {
         for (int i = 0; i < my_items; ++i) {
-          const int it = blockIdx.x + i * gridDim.x;
+          const int it = p.reverse ? total_items - 1 - (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) : blockIdx.x + i * gridDim.x;
           const int qt2 = it % n_q2, h = (it / n_q2) % p.H, b = it / (n_q2 * p.H);
           const int qs = i & 1;
           mbar_wait(&q_empty[qs], ((i >> 1) & 1) ^ 1);
@@ -222,7 +223,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
 
     if (w == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");  // warpgroup 0 takes the first softmax phase
     for (int i = 0; i < my_items; ++i) {
-      const int it = blockIdx.x + i * gridDim.x;
+      const int it = p.reverse ? total_items - 1 - (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) : blockIdx.x + i * gridDim.x;
       const int qt2 = it % n_q2, h = (it / n_q2) % p.H, b = it / (n_q2 * p.H);
       const int q_row = qt2 * 256 + w * 128 + row_in_tile;
       float m_ref = -INFINITY;  // reference max in scaled log2 units

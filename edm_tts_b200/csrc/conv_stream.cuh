@@ -35,6 +35,7 @@ struct ConvStreamParams {
   int B, N;
   int run_len;          // tokens per run
   int runs_per_seq;
+  int reverse;          // 1: the runs are walked from the last to the first
 };
 
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
@@ -94,6 +95,7 @@ struct CsRun {
 };
 __device__ __forceinline__ CsRun cs_run(const ConvStreamParams& p, int unit) {
   CsRun r;
+  if (p.reverse) unit = p.B * p.runs_per_seq - 1 - unit;
   r.b = unit / p.runs_per_seq;
   r.t_begin = (unit % p.runs_per_seq) * p.run_len;
   r.t_end = min(p.N, r.t_begin + p.run_len);

@@ -106,12 +106,13 @@ struct LnParams {
   __nv_bfloat16* z_out;   // nullable
   int seq_len, z_skip;    // z row for input row (b*seq_len + n) is b*(seq_len - z_skip) + (n - z_skip); rows n < z_skip dropped
   float eps;
+  int reverse;            // 1: rows are walked from the last to the first (L2 reuse of the producer's most recent output)
 };
 
 // 3 CTAs / SM (80 registers): 24 warps x 4 KB of row data in flight per SM measured best (5.7 TB/s)
 __global__ void __launch_bounds__(256, 3) layernorm_kernel(const LnParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + warp;
+  const int row = (p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 8 + warp;
   if (row >= p.rows) return;
   float v[32];
   if (p.in_is_bf16)

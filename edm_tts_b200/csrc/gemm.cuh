@@ -41,6 +41,8 @@ struct GemmParams {
   float scale;
   const float* rope_cos;  // [max_pos, 32] fp32
   const float* rope_sin;
+  int reverse;    // 1: walk the output tiles from the last to the first (see edm_s2a_ctx::flip: each kernel of the decoder starts
+                  // where its producer finished, so the most recently written ~100 MB of its input are still in L2)
   int seq_len;    // rotary position = row % seq_len
   int rope_cols;  // columns [0, rope_cols) get rotary (q and k parts of the fused QKV projection)
 };
@@ -409,7 +411,8 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       int stage = 0;
       uint32_t phase = 0;
       for (int t = pair; t < num_tiles; t += num_pairs) {
-        const int m_blk = t / num_n, n_blk = t % num_n;
+        const int tt = p.reverse ? num_tiles - 1 - t : t;
+        const int m_blk = tt / num_n, n_blk = tt % num_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kPairStageBytes;
@@ -460,7 +463,8 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
-      const int m_blk = t / num_n, n_blk = t % num_n;
+      const int tt = p.reverse ? num_tiles - 1 - t : t;
+      const int m_blk = tt / num_n, n_blk = tt % num_n;
       const int row = m_blk * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM + quad * 32 + lane;
       const int col0 = n_blk * kGemmBN + sub * 64;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kGemmBN + sub * 64;
