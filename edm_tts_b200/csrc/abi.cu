@@ -238,6 +238,8 @@ int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
       EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI_SWISH_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     if (EPI == EPI_QKV_ROPE)
       EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI_ROPE_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    if (EPI == EPI_F32)
+      EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI_F32_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     attr_set = true;
   }
   ProfScope prof(PK_GEMM, 2.0 * p.M * p.N * p.K, st);
@@ -250,6 +252,10 @@ int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
       CUtensorMap mc;
       if (int rc = make_tmap_f32_2d(&mc, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
       gemm_bf16_tn_pair_kernel<EPI_RESID_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
+    } else if (EPI == EPI_F32 && gemm_out_tma() && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 4) % 16 == 0) {
+      CUtensorMap mc;  // fp32 logits leave as 32 x 32 TMA store boxes
+      if (int rc = make_tmap_f32_2d(&mc, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+      gemm_bf16_tn_pair_kernel<EPI_F32_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
     } else if ((EPI == EPI_SWISH_BF16 || EPI == EPI_QKV_ROPE) && gemm_out_tma() && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 2) % 16 == 0) {
       // bf16 tiles leave as TMA store boxes (whole 128-byte lines) instead of 16-byte stores from registers
       CUtensorMap mc;

@@ -25,6 +25,7 @@ enum EpiKind : int {
   EPI_F32 = 4,         // out_f32 = acc + bias                                                   (logits heads)
   EPI_GLU_BF16 = 5,    // per 64 columns: first 32 = value, last 32 = gate (weights interleaved at pack time);
                        // out_bf16[., N/2] = bf16(bf16(value) * bf16(sigmoid(bf16(gate))))       (conv module pointwise-1 + GLU)
+  EPI_F32_TMA = 9,     // EPI_F32 with TMA store boxes (logits heads)
   EPI_ROPE_TMA = 8,    // EPI_QKV_ROPE with TMA store boxes
   EPI_SWISH_TMA = 7,   // EPI_SWISH_BF16 with the tile leaving as TMA store boxes (pair kernel only; launcher's choice)
   EPI_RESID_TMA = 6,   // EPI_RESID_F32 with the add carried out as TMA reduce-add boxes (pair kernel only; chosen by the
@@ -359,7 +360,7 @@ template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                          const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
-  constexpr bool kTmaOut = EPI == EPI_RESID_TMA || EPI == EPI_SWISH_TMA || EPI == EPI_ROPE_TMA;
+  constexpr bool kTmaOut = EPI == EPI_RESID_TMA || EPI == EPI_SWISH_TMA || EPI == EPI_ROPE_TMA || EPI == EPI_F32_TMA;
   constexpr bool kRope = EPI == EPI_QKV_ROPE || EPI == EPI_ROPE_TMA;
   constexpr int kSt = kTmaOut ? kPairStagesTma : kPairStages;
   static_assert(kPairStagesTma * kPairStageBytes + kGemmEpiWarps * kPairStagingBytes == kPairStages * kPairStageBytes, "smem budget");
@@ -550,8 +551,9 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         }
         continue;
       }
-      if constexpr (EPI == EPI_RESID_TMA) {
-        // x[rows, cols] += scale * bf16(acc + bias): the warp's 32 x 64 slice leaves as two 32 x 32 fp32 boxes through its
+      if constexpr (EPI == EPI_RESID_TMA || EPI == EPI_F32_TMA) {
+        // RESID: x[rows, cols] += scale * bf16(acc + bias) (TMA reduce-add); F32: out = acc + bias (TMA store).
+        // The warp's 32 x 64 slice leaves as two 32 x 32 fp32 boxes through its
         // 4 KB staging buffer (128B-swizzled rows); rows beyond M are clipped by the tensor map
         uint8_t* stg = smem + kSt * kPairStageBytes + (warp - 2) * kPairStagingBytes;
         const uint32_t stg_row = smem_u32(stg) + lane * 128;
@@ -566,14 +568,21 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           for (int i = 0; i < 8; ++i) {
             const float4 b = lds128(b4 + 16 * i);
             const uint32_t* r = h == 0 ? r0 : r1;
-            sts128(stg_row + ((i ^ sw) << 4),
-                   make_float4(p.scale * bf16_round(__uint_as_float(r[4 * i + 0]) + b.x), p.scale * bf16_round(__uint_as_float(r[4 * i + 1]) + b.y),
-                               p.scale * bf16_round(__uint_as_float(r[4 * i + 2]) + b.z), p.scale * bf16_round(__uint_as_float(r[4 * i + 3]) + b.w)));
+            if constexpr (EPI == EPI_RESID_TMA)
+              sts128(stg_row + ((i ^ sw) << 4),
+                     make_float4(p.scale * bf16_round(__uint_as_float(r[4 * i + 0]) + b.x), p.scale * bf16_round(__uint_as_float(r[4 * i + 1]) + b.y),
+                                 p.scale * bf16_round(__uint_as_float(r[4 * i + 2]) + b.z), p.scale * bf16_round(__uint_as_float(r[4 * i + 3]) + b.w)));
+            else
+              sts128(stg_row + ((i ^ sw) << 4), make_float4(__uint_as_float(r[4 * i + 0]) + b.x, __uint_as_float(r[4 * i + 1]) + b.y,
+                                                            __uint_as_float(r[4 * i + 2]) + b.z, __uint_as_float(r[4 * i + 3]) + b.w));
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_reduce_add_2d(&tma_c, stg, col0 + 32 * h, row0);
+            if constexpr (EPI == EPI_RESID_TMA)
+              tma_reduce_add_2d(&tma_c, stg, col0 + 32 * h, row0);
+            else
+              tma_store_2d(&tma_c, stg, col0 + 32 * h, row0);
             bulk_commit_group();
           }
         }

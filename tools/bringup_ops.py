@@ -104,11 +104,11 @@ def test_gemm():
         print(f"gemm ROPE  max_abs_err={err:.3e} (rope_cols={rope_cols})", flush=True)
     # timing at the bench shapes
     for (M, N, K, epi) in [(32000, 4096, 1024, L.EPI_GLU_BF16), (32000, 4096, 1024, L.EPI_SWISH_BF16), (32000, 1024, 4096, L.EPI_RESID_F32), (32000, 3072, 1024, L.EPI_BF16),
-                           (32000, 1024, 1024, L.EPI_RESID_F32), (32000, 1024, 2048, L.EPI_RESID_F32)]:
+                           (32000, 1024, 1024, L.EPI_RESID_F32), (32000, 1024, 2048, L.EPI_RESID_F32), (32000, 1024, 1024, L.EPI_F32)]:
         a = bf(torch.randn(M, K, device=dev))
         b = bf(torch.randn(N, K, device=dev) / math.sqrt(K))
         bias = torch.randn(N, device=dev)
-        out = torch.zeros(M, N // 2 if epi == L.EPI_GLU_BF16 else N, device=dev, dtype=torch.float32 if epi == L.EPI_RESID_F32 else torch.bfloat16)
+        out = torch.zeros(M, N // 2 if epi == L.EPI_GLU_BF16 else N, device=dev, dtype=torch.float32 if epi in (L.EPI_RESID_F32, L.EPI_F32) else torch.bfloat16)
         ms = timeit(lambda: gemm_call(a, b, epi, bias, out, scale=0.5))
         ms_ref = timeit(lambda: torch.matmul(a, b.T))
         print(f"gemm time M={M} N={N} K={K} epi={epi}: {ms:.3f} ms = {2 * M * N * K / ms / 1e9:.1f} TFLOP/s  (torch.matmul {ms_ref:.3f} ms = {2 * M * N * K / ms_ref / 1e9:.1f})", flush=True)
