@@ -3,18 +3,23 @@
 //
 // Same algebra as rvq.cuh (z is read once, the level loop runs on 8-d latents with the G cross tables), split in two kernels:
 //
-//   rvq_project_kernel : E[frame, 96] = z[b, :, t] . W_in^T + b_in for all 12 levels at once. z [B, 1024, T] is consumed as an
+//   rvq_project_kernel : E[frame, 96] = z[b, :, t] . W_in^T + b_in for all 12 levels at once (256-frame CTA tiles: two 128-row
+//                        accumulators share every weight chunk). z [B, 1024, T] is consumed as an
 //                        MN-major (frames contiguous) tf32 A operand straight from TMA boxes (128B swizzle with 32 B atoms), so the
 //                        channel-major layout of the reference needs no transpose. fp32-level accuracy comes from the 3xTF32
 //                        split: four "split" warps rewrite every staged z tile as hi = tf32(z) and lo = tf32(z - hi) in place
 //                        (elementwise, so they never need to know the swizzle), the weights are pre-split at pack time, and the
-//                        MMA thread accumulates hi*hi + lo*hi + hi*lo into one TMEM accumulator.
-//   rvq_search_kernel  : 128 frames per CTA, thread <-> frame. Per level: subtract the G rows of the codes chosen so far,
+//                        MMA warp accumulates hi*hi + lo*hi + hi*lo into one TMEM accumulator. bf16 z (the reference's autocast
+//                        case) lands as bf16 staging boxes and is expanded on chip; being tf32-exact it needs no lo part.
+//   rvq_search_kernel  : 128 frames per CTA, two scan warps per TMEM lane quadrant (each half of the columns), the first of them
+//                        also owning its frame's bookkeeping. Per level: subtract the G rows of the codes chosen so far,
 //                        L2-normalise, write the 3xTF32-split latent row as a K-major A operand (128B swizzle) to shared memory;
 //                        the MMA thread multiplies it with the packed codebook [c_hi | c_hi | c_lo | -|c|^2/2] streamed in
 //                        128-code chunks by TMA (K = 32 per code), scores land in TMEM (2 x 128 columns, double-buffered) and
-//                        each thread scans its own row with tcgen05.ld for the first maximum. Two CTAs per SM overlap one
-//                        tile's level-boundary latency with the other's scan.
+//                        each thread scans its own row with tcgen05.ld for the first maximum (groups of eight: FMNMX3 tree on the
+//                        ALU pipe, the remembered group's scores saved by predicated FMUL on the FMA pipe). Two CTAs per SM
+//                        overlap one tile's level-boundary latency with the other's scan. Both kernels issue their MMAs from
+//                        warp-uniform code with one elected lane (see ptx.cuh: umma_ss_warp).
 //
 //   score(code) = e^ . c^ - |c^|^2 / 2  = -(dist - |e^|^2) / 2   with dist = |e^|^2 - 2 e^ . c^ + |c^|^2 (the reference formula),
 //   so arg-max score (first maximum) = the reference's argmax(-dist).
