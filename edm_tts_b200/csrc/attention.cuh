@@ -36,11 +36,11 @@ struct AttnParams {
   uint32_t v_lbo, v_sbo, v_kstep;
   int reverse;            // 1: work items are walked from the last to the first
 #ifdef EDM_ATTN_TRACE
-  unsigned long long* trace;  // bring-up build only (tools/gpu_attn_trace.sh): clock64 stamps of CTA 0, [kv iteration][16 events]
+  unsigned long long* trace;  // bring-up build only (tools/gpu_attn_trace.sh): clock64 stamps of CTA 0, [kv iteration][32 events]
 #endif
 };
 #ifdef EDM_ATTN_TRACE
-#define ATTN_TRACE(g, k) do { if (blockIdx.x == 0 && p.trace != nullptr && (g) < 96) p.trace[(g) * 16 + (k)] = clock64(); } while (0)
+#define ATTN_TRACE(g, k) do { if (blockIdx.x == 0 && p.trace != nullptr && (g) < 96) p.trace[(g) * 32 + (k)] = clock64(); } while (0)
 #else
 #define ATTN_TRACE(g, k) do { } while (0)
 #endif
@@ -188,6 +188,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
             mbar_wait_spin(&kv_full[g1 % kAttnKvStages], (g1 / kAttnKvStages) & 1);
             mbar_wait_spin(&s_free[0], g & 1);
             tc_fence_after();
+            ATTN_TRACE(g1, 18);
             issue_s(0, g1);
             ATTN_TRACE(g1, 8);
             mbar_wait_spin(&s_free[1], g & 1);
@@ -199,10 +200,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
           // P_w(g) is in smem (and O_w rescaled if needed)
           mbar_wait_spin(&p_full[0], g & 1);
           tc_fence_after();
+          ATTN_TRACE(g, 16);
           issue_pv(0, g);
           ATTN_TRACE(g, 10);
           mbar_wait_spin(&p_full[1], g & 1);
           tc_fence_after();
+          ATTN_TRACE(g, 17);
           issue_pv(1, g);
           ATTN_TRACE(g, 11);
           umma_commit_warp(&kv_empty[g % kAttnKvStages]);  // K / V stage free once everything issued so far has completed
@@ -225,7 +228,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
     for (int i = 0; i < my_items; ++i) {
       const int it = p.reverse ? total_items - 1 - (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) : blockIdx.x + i * gridDim.x;
       const int qt2 = it % n_q2, h = (it / n_q2) % p.H, b = it / (n_q2 * p.H);
-      const int q_row = qt2 * 256 + w * 128 + row_in_tile;
       float m_ref = -INFINITY;  // reference max in scaled log2 units
       float l_run = 0.f;
 
@@ -327,30 +329,51 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
         fence_proxy_async_smem();
         mbar_arrive(&p_full[w]);
         if ((warp & 3) == 0 && lane == 0) ATTN_TRACE(g, 4 * w + 3);
+        if ((warp & 3) == 3 && lane == 0) ATTN_TRACE(g, 22 + w);
       }
       // item epilogue: O_w / l
       mbar_wait(&o_full[w], (i * n_kv + n_kv - 1) & 1);
       tc_fence_after();
+      if ((warp & 3) == 0 && lane == 0) ATTN_TRACE(i * n_kv + n_kv - 1, 12 + 2 * w);
       const float inv_l = 1.0f / l_run;
       uint32_t o0[32], o1[32];
       tmem_ld_32x32(tmem_O, o0);
       tmem_ld_32x32(tmem_O + 32, o1);
       tmem_ld_wait_dep(o0);
       tmem_ld_wait_dep(o1);
-      if (q_row < p.N) {
-        uint4* o = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * p.N + q_row) * p.ldo + h * 64);
+      if ((warp & 3) == 0 && lane == 0) ATTN_TRACE(i * n_kv + n_kv - 1, 20 + w);
+      // Each thread holds one 128 B output row. Storing it directly costs 32 L1 wavefronts per STG (32 rows 2 KB apart per warp
+      // instruction; measured 1.9 k cycles per item); instead the warp parks its 32 rows in its own slice of the (now idle) P_w
+      // buffer and writes them back four full rows per instruction. Only this warp touches these smem rows: __syncwarp suffices.
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          o[e] = make_uint4(pack_bf16x2(__uint_as_float(o0[8 * e + 0]) * inv_l, __uint_as_float(o0[8 * e + 1]) * inv_l),
-                            pack_bf16x2(__uint_as_float(o0[8 * e + 2]) * inv_l, __uint_as_float(o0[8 * e + 3]) * inv_l),
-                            pack_bf16x2(__uint_as_float(o0[8 * e + 4]) * inv_l, __uint_as_float(o0[8 * e + 5]) * inv_l),
-                            pack_bf16x2(__uint_as_float(o0[8 * e + 6]) * inv_l, __uint_as_float(o0[8 * e + 7]) * inv_l));
-          o[4 + e] = make_uint4(pack_bf16x2(__uint_as_float(o1[8 * e + 0]) * inv_l, __uint_as_float(o1[8 * e + 1]) * inv_l),
-                                pack_bf16x2(__uint_as_float(o1[8 * e + 2]) * inv_l, __uint_as_float(o1[8 * e + 3]) * inv_l),
-                                pack_bf16x2(__uint_as_float(o1[8 * e + 4]) * inv_l, __uint_as_float(o1[8 * e + 5]) * inv_l),
-                                pack_bf16x2(__uint_as_float(o1[8 * e + 6]) * inv_l, __uint_as_float(o1[8 * e + 7]) * inv_l));
+      for (int e = 0; e < 4; ++e) {
+        *reinterpret_cast<uint4*>(p_row + ((e ^ sw) * 16)) =
+            make_uint4(pack_bf16x2(__uint_as_float(o0[8 * e + 0]) * inv_l, __uint_as_float(o0[8 * e + 1]) * inv_l),
+                       pack_bf16x2(__uint_as_float(o0[8 * e + 2]) * inv_l, __uint_as_float(o0[8 * e + 3]) * inv_l),
+                       pack_bf16x2(__uint_as_float(o0[8 * e + 4]) * inv_l, __uint_as_float(o0[8 * e + 5]) * inv_l),
+                       pack_bf16x2(__uint_as_float(o0[8 * e + 6]) * inv_l, __uint_as_float(o0[8 * e + 7]) * inv_l));
+        *reinterpret_cast<uint4*>(p_row + (((4 + e) ^ sw) * 16)) =
+            make_uint4(pack_bf16x2(__uint_as_float(o1[8 * e + 0]) * inv_l, __uint_as_float(o1[8 * e + 1]) * inv_l),
+                       pack_bf16x2(__uint_as_float(o1[8 * e + 2]) * inv_l, __uint_as_float(o1[8 * e + 3]) * inv_l),
+                       pack_bf16x2(__uint_as_float(o1[8 * e + 4]) * inv_l, __uint_as_float(o1[8 * e + 5]) * inv_l),
+                       pack_bf16x2(__uint_as_float(o1[8 * e + 6]) * inv_l, __uint_as_float(o1[8 * e + 7]) * inv_l));
+      }
+      __syncwarp();
+      {
+        const int r_sub = lane >> 3, ch = lane & 7;
+        const int row0 = (warp & 3) * 32;                                    // this warp's first row in the tile
+        const uint8_t* src = sP + w * 2 * kAttnTile;
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.N) * p.ldo + h * 64 + ch * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int r = row0 + k * 4 + r_sub;
+          const int qr = qt2 * 256 + w * 128 + r;
+          const uint4 v = *reinterpret_cast<const uint4*>(src + r * 128 + ((ch ^ (r & 7)) * 16));
+          if (qr < p.N) *reinterpret_cast<uint4*>(dst + static_cast<long long>(qr) * p.ldo) = v;
         }
       }
+      __syncwarp();   // the rows are overwritten by the next item's first P
+      if ((warp & 3) == 0 && lane == 0) ATTN_TRACE(i * n_kv + n_kv - 1, 13 + 2 * w);
     }
   }
 

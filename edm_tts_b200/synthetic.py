@@ -115,6 +115,41 @@ def make_quantizer_state_dict(cfg: OracleConfig, seed: int = 0, prefix: str = ""
     return sd
 
 
+def make_encoder_state_dict(encoder_dim: int = 64, rates=(2, 4, 5, 8), seed: int = 0, prefix: str = "") -> dict:
+    """DAC Encoder parameters keyed as edm_tts/models/dac/encoder.py builds them (nn.Sequential indices): block.0 first conv,
+    block.{1..n} EncoderBlocks (three ResidualUnits, Snake, strided conv), then Snake and the last conv. Weight-normed convs keep
+    the original0 (g) / original1 (v) split. Gains are chosen so activations stay O(1) through the stack."""
+    sd = {}
+
+    def wnconv(key, c_out, c_in, k, gain):
+        v = _randn(key + ".v", seed, c_out, c_in, k)
+        sd[key + ".parametrizations.weight.original1"] = v
+        sd[key + ".parametrizations.weight.original0"] = (gain * (1.0 + 0.2 * torch.rand(c_out, 1, 1, generator=_gen(key + ".g", seed)))).float()
+        sd[key + ".bias"] = _randn(key + ".bias", seed, c_out, std=0.05)
+
+    def snake(key, c):
+        sd[key + ".alpha"] = (0.5 + 1.5 * torch.rand(1, c, 1, generator=_gen(key + ".alpha", seed))).float()
+
+    d = encoder_dim
+    wnconv(f"{prefix}block.0", d, 1, 7, 2.0)
+    n = 1
+    for stride in rates:
+        d *= 2
+        c = d // 2
+        for u in range(3):
+            ru = f"{prefix}block.{n}.block.{u}.block."
+            snake(ru + "0", c)
+            wnconv(ru + "1", c, c, 7, 0.6)
+            snake(ru + "2", c)
+            wnconv(ru + "3", c, c, 1, 0.3)
+        snake(f"{prefix}block.{n}.block.3", c)
+        wnconv(f"{prefix}block.{n}.block.4", d, c, 2 * stride, 0.5)
+        n += 1
+    snake(f"{prefix}block.{n}", d)
+    wnconv(f"{prefix}block.{n + 1}", d, d, 3, 0.7)
+    return sd
+
+
 def make_inputs(B: int, T: int, P: int, steps: int, cfg: OracleConfig, seed: int = 1234) -> dict:
     """Synthetic tokens + injected sampling noise, all from one CPU generator."""
     g = torch.Generator(device="cpu")

@@ -23,9 +23,11 @@ os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
 sys.dont_write_bytecode = True
 
 from oracle.weights import OracleConfig, make_inputs, make_quantizer_state_dict, make_state_dict  # noqa: E402
+from edm_tts_b200.synthetic import make_encoder_state_dict  # noqa: E402
 
 from edm_tts.models.dac import DAC  # noqa: E402
 from edm_tts.models.dac.configuration import DACConfig  # noqa: E402
+from edm_tts.models.dac.encoder import Encoder  # noqa: E402
 from edm_tts.models.dac.vector_quantizer import ResidualVectorQuantize  # noqa: E402
 from edm_tts.models.injection_conformer import modeling_injection_conformer as mic  # noqa: E402
 from edm_tts.models.injection_conformer.configuration import InjectionConformerConfig  # noqa: E402
@@ -167,6 +169,21 @@ def make_rvq(name, cfg_name, B, T, seed=0):
     print(f"rvq_{name}: codes {tuple(out['codes'].shape)} saved", flush=True)
 
 
+def make_dac_encoder(name, encoder_dim, B, L, seed=0):
+    """The reference Encoder (fp32, CPU) on synthetic audio: full z for small shapes, a slice + checksums otherwise."""
+    rates = (2, 4, 5, 8)
+    enc = Encoder(encoder_dim, list(rates)).eval()
+    enc.load_state_dict(make_encoder_state_dict(encoder_dim, rates, seed), strict=True)
+    audio = (torch.randn(B, 1, L, generator=torch.Generator().manual_seed(7 + L)) * 0.3).clamp(-1, 1)
+    with torch.inference_mode():
+        z = enc(audio)
+    gold = dict(encoder_dim=encoder_dim, B=B, L=L, weight_seed=seed, audio_seed=7 + L, z_shape=tuple(z.shape),
+                z=z.clone() if z.numel() <= 1 << 18 else None, z_head=z[:, :32, :16].clone(), z_tail=z[:, -32:, -16:].clone(),
+                z_sum=z.double().sum().item(), z_abs_sum=z.double().abs().sum().item())
+    torch.save(gold, os.path.join(OUT, f"dac_encoder_{name}.pt"))
+    print(f"dac_encoder_{name}: z {tuple(z.shape)} rms {z.pow(2).mean().sqrt().item():.3f} saved", flush=True)
+
+
 def make_train_forward(name, cfg_name, B, T, seed=0):
     """InjectionConformerModel.forward (eval mode: no dropout, ground-truth injections) with cosine_schedule_mask replaced by a
     fixed Bernoulli(0.6) mask: loss, arg-max codes and a few logit rows."""
@@ -200,6 +217,10 @@ def make_train_forward(name, cfg_name, B, T, seed=0):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "dac_encoder":      # only the encoder fixtures (added after the others)
+        make_dac_encoder("small", 8, 2, 3200 + 137)
+        make_dac_encoder("full", 64, 2, 6400 + 160)
+        sys.exit(0)
     with tempfile.TemporaryDirectory():
         make_rvq("small", "small", 2, 50)
         make_rvq("full", "full", 2, 75)
@@ -211,3 +232,5 @@ if __name__ == "__main__":
         make_s2a("full_s4_prompt", "full", 1, 100, 50, 4)
         make_train_forward("small", "small", 2, 40)
         make_train_forward("full", "full", 1, 60)
+        make_dac_encoder("small", 8, 2, 3200 + 137)
+        make_dac_encoder("full", 64, 2, 6400 + 160)

@@ -96,3 +96,23 @@ def test_training_forward_oracle_matches_reference(name, golden_dir):
     assert abs(out["loss"].item() - g["loss"]) < 1e-4, (out["loss"].item(), g["loss"])
     assert torch.equal(out["output_acoustic_codes"].to(torch.int16), g["output_codes"])
     torch.testing.assert_close(out["logits"][:, :, g["row_idx"]], g["logit_rows"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["small", "full"])
+def test_dac_encoder_oracle_matches_reference(golden_dir, name):
+    """oracle/dac_encoder.py against z of the unmodified reference Encoder (fp32 CPU): same conv algorithm -> 1e-5."""
+    from edm_tts_b200.synthetic import make_encoder_state_dict
+    from oracle.dac_encoder import encoder_forward
+
+    g = torch.load(os.path.join(golden_dir, f"dac_encoder_{name}.pt"))
+    sd = make_encoder_state_dict(g["encoder_dim"], (2, 4, 5, 8), g["weight_seed"])
+    audio = (torch.randn(g["B"], 1, g["L"], generator=torch.Generator().manual_seed(g["audio_seed"])) * 0.3).clamp(-1, 1)
+    with torch.inference_mode():
+        z, stages = encoder_forward(sd, audio, return_stages=True)
+    assert tuple(z.shape) == tuple(g["z_shape"])
+    print("stage rms:", [round(s.pow(2).mean().sqrt().item(), 3) for s in stages])
+    if g["z"] is not None:
+        torch.testing.assert_close(z, g["z"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(z[:, :32, :16], g["z_head"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(z[:, -32:, -16:], g["z_tail"], rtol=1e-5, atol=1e-5)
+    assert abs(z.double().sum().item() - g["z_sum"]) < 1e-3 * max(1.0, g["z_abs_sum"] * 1e-3)
