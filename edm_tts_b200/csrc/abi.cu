@@ -13,6 +13,7 @@
 #include "attention.cuh"
 #include "elementwise.cuh"
 #include "conv_stream.cuh"
+#include "dac_conv.cuh"
 #include "gemm.cuh"
 #include "kmeans.cuh"
 #include "rvq.cuh"
@@ -606,6 +607,83 @@ extern "C" int edm_kmeans_assign(const float* x, long long n_frames, int dim, co
   const int tiles = (p.n_frames + kKmFrames - 1) / kKmFrames;
   kmeans_assign_kernel<<<tiles < num_sms() ? tiles : num_sms(), kKmThreads, kKmSmemBytes, static_cast<cudaStream_t>(stream)>>>(mx, mh, ml, p);
   EDM_LAUNCH_CHECK("kmeans_assign");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- DAC encoder convolutions
+namespace {
+// bf16 operand [B][rows][cols] with an explicit batch stride (elements): box = 64 channels x 128 rows x 1 batch; rows outside
+// [0, rows) are zero-filled (the conv's zero padding)
+int make_tmap_conv_a(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t rows, uint64_t cols, uint64_t batch_stride) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (enc == nullptr) return fail(EDM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (cols * 2) % 16 != 0 || (batch_stride * 2) % 16 != 0)
+    return fail(EDM_ERR_INVALID, "conv operand must be 16-byte aligned");
+  cuuint64_t dims[3] = {cols, rows, B};
+  cuuint64_t strides[2] = {cols * 2, batch_stride * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EDM_ERR_CUDA, "cuTensorMapEncodeTiled(conv operand rows=%llu cols=%llu) failed: %d", (unsigned long long)rows, (unsigned long long)cols, (int)r);
+  return 0;
+}
+
+template <int NT>
+int launch_dac_conv(const CUtensorMap& ma, const CUtensorMap& mw, DacConvParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    EDM_CUDA(cudaFuncSetAttribute(dac_conv_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, dac_conv_smem_bytes<NT>()));
+    attr_set = true;
+  }
+  p.n_tiles_n = p.c_out / NT;
+  const long long tiles = static_cast<long long>(p.B) * p.tiles_per_batch * p.n_tiles_n;
+  if (tiles > 0x7fffffffLL) return fail(EDM_ERR_INVALID, "dac_conv: too many tiles");
+  const int grid = tiles < num_sms() ? static_cast<int>(tiles) : num_sms();
+  dac_conv_kernel<NT><<<grid, kDcThreads, dac_conv_smem_bytes<NT>(), st>>>(ma, mw, p);
+  EDM_LAUNCH_CHECK("dac_conv");
+  return 0;
+}
+}  // namespace
+
+extern "C" int edm_dac_conv(const void* a, long long a_rows, int a_cols, long long a_batch_stride, int B, const void* w, int c_out,
+                            int n_taps, int tap_step, int row_off, int rows_out, const float* bias, const float* alpha,
+                            const float* x_res, float* y, long long y_batch_stride, void* s_out, long long s_batch_stride,
+                            int s_row_off, int s_rows, void* zt_out, int zt_is_f32, void* stream) {
+  if (int rc = check_arch()) return rc;
+  if (B <= 0 || rows_out <= 0) return 0;
+  if (a_cols <= 0 || a_cols % 64 != 0 || c_out < 64 || c_out % 64 != 0 || c_out > kDcMaxCout || n_taps <= 0 || a_rows <= 0)
+    return fail(EDM_ERR_INVALID, "dac_conv shape cin=%d cout=%d taps=%d unsupported (channels %% 64, cout <= 1024)", a_cols, c_out, n_taps);
+  if (bias == nullptr) return fail(EDM_ERR_INVALID, "dac_conv: bias is required");
+  CUtensorMap ma, mw;
+  if (int rc = make_tmap_conv_a(&ma, a, B, static_cast<uint64_t>(a_rows), a_cols, static_cast<uint64_t>(a_batch_stride))) return rc;
+  const int nt = c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 64);
+  const uint64_t k_total = static_cast<uint64_t>(n_taps) * a_cols;
+  if (int rc = make_tmap_2d(&mw, w, c_out, k_total, k_total, nt)) return rc;
+  DacConvParams p;
+  p.B = B; p.rows_out = rows_out; p.tiles_per_batch = (rows_out + kDcBM - 1) / kDcBM; p.c_out = c_out; p.n_tiles_n = 0;
+  p.n_taps = n_taps; p.tap_step = tap_step; p.row_off = row_off; p.k_chunks = a_cols / 64;
+  p.bias = bias; p.alpha = alpha; p.x_res = x_res; p.y = y; p.y_batch_stride = y_batch_stride;
+  p.s_out = static_cast<__nv_bfloat16*>(s_out); p.s_batch_stride = s_batch_stride; p.s_row_off = s_row_off; p.s_rows = s_rows;
+  p.zt_out = zt_out; p.zt_is_f32 = zt_is_f32;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (nt == 256) return launch_dac_conv<256>(ma, mw, p, st);
+  if (nt == 128) return launch_dac_conv<128>(ma, mw, p, st);
+  return launch_dac_conv<64>(ma, mw, p, st);
+}
+
+extern "C" int edm_dac_conv_first(const float* audio, int B, int L, const float* w, const float* bias, const float* alpha, int c0,
+                                  float* y, void* s_out, void* stream) {
+  if (int rc = check_arch()) return rc;
+  if (B <= 0 || L <= 0) return 0;
+  if (c0 <= 0 || c0 % 16 != 0 || c0 > 256) return fail(EDM_ERR_INVALID, "dac_conv_first: channels %d unsupported (%% 16, <= 256)", c0);
+  DacConv0Params p;
+  p.audio = audio; p.w = w; p.bias = bias; p.alpha = alpha; p.y = y; p.s_out = static_cast<__nv_bfloat16*>(s_out); p.B = B; p.L = L; p.C0 = c0;
+  const long long total = static_cast<long long>(B) * L * (c0 / 16);
+  const long long blocks = (total + 255) / 256;
+  const int grid = static_cast<int>(blocks < 8LL * num_sms() ? blocks : 8LL * num_sms());
+  dac_conv0_kernel<<<grid, 256, c0 * 10 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(p);
+  EDM_LAUNCH_CHECK("dac_conv_first");
   return 0;
 }
 

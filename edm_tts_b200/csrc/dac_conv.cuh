@@ -1,0 +1,298 @@
+// DAC encoder convolutions as implicit GEMMs on tcgen05 (kind::f16, bf16 operands, fp32 accumulators in TMEM).
+// Reference: edm_tts/models/dac/encoder.py:11-58 (Encoder / EncoderBlock), edm_tts/models/dac/nn_layers.py:8-47 (WNConv1d,
+// Snake1d, ResidualUnit); the reference runs this stack under bf16 autocast (utility_scripts/dump_tokens/dump_tokens.py:213).
+//
+// Data layout. Activations are channel-last: [batch][time][channels]. Every conv reads a bf16 "operand" tensor that already holds
+// Snake(x) (each conv of the encoder except the first is preceded by a Snake), written by the epilogue of the producing kernel, and
+// the residual stream stays fp32. A conv with taps j = 0..n_taps-1 is then
+//     D[t, co] = sum_j sum_ci  A[t + row_off + j * tap_step, ci] * W[co, j * Cin + ci]
+// i.e. a GEMM whose K loop walks (tap, 64-channel chunk) and whose A tile of each K step is one TMA box of the operand tensor at a
+// shifted time coordinate. The tensor map is 3-D (channels, time, batch): rows before 0 or past the end of a sequence are
+// zero-filled by TMA, which is exactly the conv's zero padding (Snake(0) = 0), and batches never bleed into each other.
+//   * dilated k=7 conv of a ResidualUnit: n_taps 7, tap_step = dilation, row_off = -3 * dilation
+//   * 1x1 conv: n_taps 1
+//   * strided conv (kernel 2s, stride s, padding ceil(s/2)): the producer writes the operand into a buffer with `pad` zero rows in
+//     front, viewed as [time / s][s * C]: output t reads buffer rows t and t + 1 of that view -> n_taps 2, tap_step 1, Cin = s * C
+//   * last conv (k=3, pad 1): n_taps 3, tap_step 1, row_off -1
+// Weights are packed [Cout][n_taps * Cin] bf16 (K-major), weight-norm folded at load.
+//
+// Epilogue (thread <-> time row, fused, runtime-selected): v = acc + bias [+ x_res]; y = v (fp32 stream); s_out = bf16(Snake_alpha(v))
+// (operand of the next conv, possibly in the padded layout of a strided conv); zt_out = v transposed to [batch][channel][time]
+// (the latent z handed to the RVQ, reference layout).
+//
+//   warp 0     : TMA producer (A box 128 rows x 64 channels, W box NT rows x 64), 4-stage ring
+//   warp 1     : MMA issuer (whole warp, elected lane), accumulator double-buffered in TMEM (2 x NT columns)
+//   warps 2-9  : epilogue, two warps per TMEM lane quadrant, each owning half of the tile's columns
+#pragma once
+#include "ptx.cuh"
+
+namespace edm {
+
+constexpr int kDcThreads = 320;
+constexpr int kDcStages = 4;
+constexpr int kDcBM = 128;
+constexpr uint32_t kDcABytes = kDcBM * 64 * 2;  // 16 KB
+constexpr int kDcMaxCout = 1024;
+
+struct DacConvParams {
+  int B, rows_out, tiles_per_batch, c_out, n_tiles_n;
+  int n_taps, tap_step, row_off, k_chunks;  // k_chunks = Cin / 64
+  const float* bias;                        // [c_out]
+  const float* alpha;                       // [c_out] Snake of the NEXT layer, applied to what goes to s_out; nullptr: identity
+  const float* x_res;                       // fp32 [B][rows_out][c_out] residual input or nullptr (may alias y)
+  float* y;                                 // fp32 stream out or nullptr
+  long long y_batch_stride;                 // elements
+  __nv_bfloat16* s_out;                     // bf16 operand out or nullptr: row (t + s_row_off) of batch b, rows >= s_rows are dropped
+  long long s_batch_stride;
+  int s_row_off, s_rows;
+  void* zt_out;                             // [B][c_out][rows_out] (bf16 or fp32) or nullptr
+  int zt_is_f32;
+};
+
+template <int NT>
+constexpr uint32_t dac_conv_smem_bytes() {
+  return kDcStages * (kDcABytes + NT * 128) + 3 * kDcMaxCout * 4 + 1024 + 256;
+}
+
+__device__ __forceinline__ float snake_act(float v, float a, float inv_a) {
+  const float s = __sinf(a * v);
+  return fmaf(inv_a * s, s, v);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kDcThreads, 1)
+dac_conv_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, const DacConvParams p) {
+  constexpr uint32_t kBBytes = NT * 128;
+  constexpr uint32_t kStageBytes = kDcABytes + kBBytes;
+  constexpr int kTmemCols = 2 * NT < 32 ? 32 : 2 * NT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* s_bias = reinterpret_cast<float*>(smem + kDcStages * kStageBytes);
+  float* s_alpha = s_bias + kDcMaxCout;
+  float* s_inva = s_alpha + kDcMaxCout;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_inva + kDcMaxCout);
+  uint64_t* empty_bar = full_bar + kDcStages;
+  uint64_t* tfull_bar = empty_bar + kDcStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.B * p.tiles_per_batch * p.n_tiles_n;
+  const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int k_steps = p.n_taps * p.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_w);
+    for (int s = 0; s < kDcStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
+  for (int i = threadIdx.x; i < p.c_out; i += kDcThreads) {
+    s_bias[i] = __ldg(p.bias + i);
+    const float a = p.alpha != nullptr ? __ldg(p.alpha + i) : 1.0f;
+    s_alpha[i] = a;
+    s_inva[i] = 1.0f / (a + 1e-9f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (n tile fastest, then time tile, then batch): CTAs running side by side share the A rows in L2
+  auto decode = [&](int tile, int& b, int& t0, int& n0) {
+    n0 = (tile % p.n_tiles_n) * NT;
+    const int mt = tile / p.n_tiles_n;
+    t0 = (mt % p.tiles_per_batch) * kDcBM;
+    b = mt / p.tiles_per_batch;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        int b, t0, n0;
+        decode(blockIdx.x + tl * gridDim.x, b, t0, n0);
+        for (int j = 0; j < p.n_taps; ++j) {
+          const int row = t0 + p.row_off + j * p.tap_step;
+          for (int c = 0; c < p.k_chunks; ++c, ++it) {
+            const uint32_t s = it % kDcStages;
+            uint8_t* st = smem + s * kStageBytes;
+            mbar_wait(&empty_bar[s], ((it / kDcStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+            tma_load_3d(&tma_a, &full_bar[s], st, c * 64, row, b);
+            tma_load_2d(&tma_w, &full_bar[s], st + kDcABytes, (j * p.k_chunks + c) * 64, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(kDcBM, NT, 0, 0);
+    uint32_t it = 0;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const uint32_t buf = tl & 1;
+      mbar_wait(&tempty_bar[buf], ((tl >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * NT;
+      for (int ks = 0; ks < k_steps; ++ks, ++it) {
+        const uint32_t s = it % kDcStages;
+        mbar_wait_spin(&full_bar[s], (it / kDcStages) & 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * kStageBytes);
+        const uint64_t a_desc = umma_desc_sw128(st, 16, 1024), b_desc = umma_desc_sw128(st + kDcABytes, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss_warp(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+        umma_commit_warp(&empty_bar[s]);
+      }
+      umma_commit_warp(&tfull_bar[buf]);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r_in = quad * 32 + lane;
+    constexpr int kColsPerWarp = NT / 2;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      int b, t0, n0;
+      decode(blockIdx.x + tl * gridDim.x, b, t0, n0);
+      const uint32_t buf = tl & 1;
+      const int t = t0 + r_in;
+      const bool valid = t < p.rows_out;
+      const bool s_valid = valid && p.s_out != nullptr && (t + p.s_row_off) < p.s_rows;
+      mbar_wait(&tfull_bar[buf], (tl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * NT + half * kColsPerWarp;
+#pragma unroll 1
+      for (int cc = 0; cc < kColsPerWarp / 32; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + cc * 32, r);
+        tmem_ld_wait_dep(r);
+        if (cc == kColsPerWarp / 32 - 1) {
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[buf]);
+        }
+        const int col = n0 + half * kColsPerWarp + cc * 32;
+        float v[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + s_bias[col + e];
+        if (valid) {
+          const long long yo = static_cast<long long>(b) * p.y_batch_stride + static_cast<long long>(t) * p.c_out + col;
+          if (p.x_res != nullptr) {
+            const float4* xr = reinterpret_cast<const float4*>(p.x_res + yo);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 x4 = xr[i];
+              v[4 * i] += x4.x; v[4 * i + 1] += x4.y; v[4 * i + 2] += x4.z; v[4 * i + 3] += x4.w;
+            }
+          }
+          if (p.y != nullptr) {
+            float4* yw = reinterpret_cast<float4*>(p.y + yo);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) yw[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          if (p.zt_out != nullptr) {
+            const long long zo = (static_cast<long long>(b) * p.c_out + col) * p.rows_out + t;
+            if (p.zt_is_f32) {
+              float* z = static_cast<float*>(p.zt_out) + zo;
+#pragma unroll
+              for (int e = 0; e < 32; ++e) z[static_cast<long long>(e) * p.rows_out] = v[e];
+            } else {
+              __nv_bfloat16* z = static_cast<__nv_bfloat16*>(p.zt_out) + zo;
+#pragma unroll
+              for (int e = 0; e < 32; ++e) z[static_cast<long long>(e) * p.rows_out] = __float2bfloat16(v[e]);
+            }
+          }
+        }
+        if (s_valid) {
+          uint32_t w[16];
+          if (p.alpha != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              w[e] = pack_bf16x2(snake_act(v[2 * e], s_alpha[col + 2 * e], s_inva[col + 2 * e]),
+                                 snake_act(v[2 * e + 1], s_alpha[col + 2 * e + 1], s_inva[col + 2 * e + 1]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) w[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+          }
+          uint4* so = reinterpret_cast<uint4*>(p.s_out + static_cast<long long>(b) * p.s_batch_stride +
+                                               static_cast<long long>(t + p.s_row_off) * p.c_out + col);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) so[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+// First conv of the encoder: 1 -> C0 channels, k = 7, padding 3 (encoder.py:38), CUDA cores (7 MACs per output, bandwidth-bound:
+// 4 B in, 6 * C0 B out per sample). Thread <-> (time, 16 channels); writes the fp32 stream and the Snake'd bf16 operand.
+struct DacConv0Params {
+  const float* audio;   // [B][L]
+  const float* w;       // [C0][7]
+  const float* bias;    // [C0]
+  const float* alpha;   // [C0] Snake of the first ResidualUnit
+  float* y;             // [B][L][C0]
+  __nv_bfloat16* s_out; // [B][L][C0]
+  int B, L, C0;
+};
+
+__global__ void __launch_bounds__(256) dac_conv0_kernel(const DacConv0Params p) {
+  extern __shared__ float s_w0[];  // [C0][7] | bias | alpha | inv_alpha
+  float* s_b = s_w0 + p.C0 * 7;
+  float* s_a = s_b + p.C0;
+  float* s_ia = s_a + p.C0;
+  for (int i = threadIdx.x; i < p.C0 * 7; i += blockDim.x) s_w0[i] = __ldg(p.w + i);
+  for (int i = threadIdx.x; i < p.C0; i += blockDim.x) {
+    s_b[i] = __ldg(p.bias + i);
+    const float a = __ldg(p.alpha + i);
+    s_a[i] = a;
+    s_ia[i] = 1.0f / (a + 1e-9f);
+  }
+  __syncthreads();
+  const int groups = p.C0 / 16;
+  const long long total = static_cast<long long>(p.B) * p.L * groups;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    const long long bt = i / groups;
+    const int t = static_cast<int>(bt % p.L);
+    const float* a = p.audio + (bt - t);
+    float x[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int tt = t + j - 3;
+      x[j] = (tt >= 0 && tt < p.L) ? __ldg(a + tt) : 0.f;
+    }
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float* w = s_w0 + (g * 16 + c) * 7;
+      float acc = s_b[g * 16 + c];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) acc = fmaf(w[j], x[j], acc);
+      v[c] = acc;
+    }
+    float4* yo = reinterpret_cast<float4*>(p.y + bt * p.C0 + g * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) yo[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    uint32_t w2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      w2[e] = pack_bf16x2(snake_act(v[2 * e], s_a[g * 16 + 2 * e], s_ia[g * 16 + 2 * e]),
+                          snake_act(v[2 * e + 1], s_a[g * 16 + 2 * e + 1], s_ia[g * 16 + 2 * e + 1]));
+    uint4* so = reinterpret_cast<uint4*>(p.s_out + bt * p.C0 + g * 16);
+    so[0] = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+    so[1] = make_uint4(w2[4], w2[5], w2[6], w2[7]);
+  }
+}
+
+}  // namespace edm

@@ -1,0 +1,159 @@
+"""DAC convolutional encoder on the CUDA path, behind the reference's module API.
+
+Mirrors edm_tts/models/dac/encoder.py:11-58 (Encoder(d_model, strides): first conv, EncoderBlocks of three dilated ResidualUnits +
+Snake + strided conv, last Snake + conv) and its caller DAC.encode_to_codes (edm_tts/models/dac/modeling_dac.py:163-167:
+z = encoder(audio); codes = quantizer(z)["codes"]), which utility_scripts/dump_tokens/dump_tokens.py:213-215 runs under bf16
+autocast. Every conv is one launch of the implicit-GEMM kernel of csrc/dac_conv.cuh: activations are channel-last, the residual
+stream is fp32, the conv operands are bf16 tensors that already hold Snake(x) and are written by the producing conv's epilogue.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _lib as L
+
+
+def _fold(sd, key):
+    """weight_norm (dim 0): w = g * v / ||v||, the norm taken over (in, k) per output channel (nn_layers.py:8-9)."""
+    g = sd[key + ".parametrizations.weight.original0"].float()
+    v = sd[key + ".parametrizations.weight.original1"].float()
+    return v * (g / v.flatten(1).norm(dim=1).view(-1, 1, 1))
+
+
+class DACEncoder:
+    def __init__(self, state_dict: dict, d_model: int = 64, strides=(2, 4, 5, 8), prefix: str = "", device="cuda",
+                 max_chunk_samples: int = 1 << 23):
+        if not torch.cuda.is_available():
+            raise L.EdmError("edm_tts_b200 needs a CUDA device (sm_100); there is no CPU fallback")
+        if d_model % 64 != 0 or d_model * 2 ** len(strides) > 1024:
+            raise ValueError("the conv kernels need channel counts that are multiples of 64 and at most 1024")
+        self.device = torch.device(device)
+        self.d_model, self.strides = d_model, tuple(strides)
+        self.enc_dim = d_model * 2 ** len(strides)
+        self.hop_length = math.prod(strides)
+        self.max_chunk_samples = max_chunk_samples
+        sd = {k: v.detach().to("cpu") for k, v in state_dict.items() if k.startswith(prefix)}
+        dev = self.device
+
+        def conv(key):
+            w = _fold(sd, key)                                                   # [c_out, c_in, k]
+            packed = w.permute(0, 2, 1).reshape(w.shape[0], -1)                  # K index = tap * c_in + channel
+            return packed.to(dev, torch.bfloat16).contiguous(), sd[key + ".bias"].float().to(dev).contiguous()
+
+        def alpha(key):
+            return sd[key + ".alpha"].float().reshape(-1).to(dev).contiguous()
+
+        self.w0 = _fold(sd, f"{prefix}block.0")[:, 0, :].to(dev).contiguous()   # [d_model, 7] fp32
+        self.b0 = sd[f"{prefix}block.0.bias"].float().to(dev).contiguous()
+        self.blocks = []
+        n = 1
+        for stride in self.strides:
+            units = []
+            for u in range(3):
+                ru = f"{prefix}block.{n}.block.{u}.block."
+                w7, b7 = conv(ru + "1")
+                w1, b1 = conv(ru + "3")
+                units.append(dict(a_in=alpha(ru + "0"), w7=w7, b7=b7, a_mid=alpha(ru + "2"), w1=w1, b1=b1))
+            wd, bd = conv(f"{prefix}block.{n}.block.4")
+            self.blocks.append(dict(units=units, a_down=alpha(f"{prefix}block.{n}.block.3"), wd=wd, bd=bd, stride=stride))
+            n += 1
+        self.a_last = alpha(f"{prefix}block.{n}")
+        self.w_last, self.b_last = conv(f"{prefix}block.{n + 1}")
+        self._ws = {}
+
+    def eval(self):
+        return self
+
+    # ------------------------------------------------------------------ geometry / workspace
+    def lengths(self, L_in: int):
+        """Time lengths after the first conv and after each strided conv (kernel 2s, stride s, padding ceil(s/2))."""
+        out = [L_in]
+        for s in self.strides:
+            out.append((out[-1] + 2 * math.ceil(s / 2) - 2 * s) // s + 1)
+        return out
+
+    def _workspace(self, B: int, L_in: int):
+        key = (B, L_in)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        self._ws.clear()                       # one geometry at a time: the buffers are large
+        lens = self.lengths(L_in)
+        dev = self.device
+        ws = dict(lens=lens, y=[], sx=[], sh=[], sd=[])
+        c = self.d_model
+        for k, s in enumerate(self.strides):
+            Lk, Ln = lens[k], lens[k + 1]
+            ws["y"].append(torch.empty(B, Lk, c, device=dev, dtype=torch.float32))
+            ws["sx"].append(torch.empty(B, Lk, c, device=dev, dtype=torch.bfloat16))
+            ws["sh"].append(torch.empty(B, Lk, c, device=dev, dtype=torch.bfloat16))
+            # operand of the strided conv: `pad` zero rows in front, (Ln + 1) * s rows in all; never-written rows stay zero
+            ws["sd"].append(torch.zeros(B, (Ln + 1) * s, c, device=dev, dtype=torch.bfloat16))
+            c *= 2
+        ws["y"].append(None)
+        ws["sx"].append(torch.empty(B, lens[-1], c, device=dev, dtype=torch.bfloat16))
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def _conv(self, a, a_rows, a_cols, w, bias, taps, step, off, rows_out, B, alpha=None, x_res=None, y=None, s_out=None,
+              s_row_off=0, s_rows=0, zt=None):
+        c_out = w.shape[0]
+        L.check(L.lib().edm_dac_conv(L.ptr(a), a_rows, a_cols, a.stride(0), B, L.ptr(w), c_out, taps, step, off, rows_out, L.ptr(bias),
+                                     L.ptr(alpha), L.ptr(x_res), L.ptr(y), y.stride(0) if y is not None else 0, L.ptr(s_out),
+                                     s_out.stride(0) if s_out is not None else 0, s_row_off, s_rows, L.ptr(zt),
+                                     int(zt is not None and zt.dtype == torch.float32), L.stream_ptr()), "dac_conv")
+
+    @torch.no_grad()
+    def forward(self, audio: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:
+        """audio [B, 1, L] -> z [B, enc_dim, T] (bf16 as under the reference's autocast, or fp32)."""
+        if audio.dim() != 3 or audio.shape[1] != 1:
+            raise ValueError("audio must be [B, 1, L]")
+        if out_dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError("out_dtype must be bfloat16 or float32")
+        audio = audio.to(self.device, torch.float32).contiguous()
+        B, _, L_in = audio.shape
+        T = self.lengths(L_in)[-1]
+        if T <= 0:
+            raise ValueError(f"audio of {L_in} samples is shorter than one frame")
+        z = torch.empty(B, self.enc_dim, T, device=self.device, dtype=out_dtype)
+        per = max(1, self.max_chunk_samples // L_in)
+        for b0 in range(0, B, per):
+            self._forward_chunk(audio[b0:b0 + per], z[b0:b0 + per])
+        return z
+
+    __call__ = forward
+
+    def _forward_chunk(self, audio, z_out):
+        B, _, L_in = audio.shape
+        ws = self._workspace(B, L_in)
+        lens = ws["lens"]
+        c = self.d_model
+        first_alpha = self.blocks[0]["units"][0]["a_in"]
+        L.check(L.lib().edm_dac_conv_first(L.ptr(audio), B, L_in, L.ptr(self.w0), L.ptr(self.b0), L.ptr(first_alpha), c, L.ptr(ws["y"][0]),
+                                           L.ptr(ws["sx"][0]), L.stream_ptr()), "dac_conv_first")
+        for k, blk in enumerate(self.blocks):
+            s, Lk, Ln = blk["stride"], lens[k], lens[k + 1]
+            y, sx, sh, sd = ws["y"][k], ws["sx"][k], ws["sh"][k], ws["sd"][k]
+            for u, ru in enumerate(blk["units"]):
+                d = 3 ** u
+                # dilated k=7 conv of Snake(x); epilogue applies the unit's second Snake
+                self._conv(sx, Lk, c, ru["w7"], ru["b7"], 7, d, -3 * d, Lk, B, alpha=ru["a_mid"], s_out=sh, s_rows=Lk)
+                # 1x1 conv + residual add into the fp32 stream; epilogue applies the Snake in front of the next conv
+                if u < 2:
+                    self._conv(sh, Lk, c, ru["w1"], ru["b1"], 1, 1, 0, Lk, B, alpha=blk["units"][u + 1]["a_in"], x_res=y, y=y, s_out=sx, s_rows=Lk)
+                else:
+                    self._conv(sh, Lk, c, ru["w1"], ru["b1"], 1, 1, 0, Lk, B, alpha=blk["a_down"], x_res=y, y=y, s_out=sd,
+                               s_row_off=math.ceil(s / 2), s_rows=(Ln + 1) * s)
+            # strided conv on the padded operand viewed as [Ln + 1][s * c]
+            nxt_alpha = self.blocks[k + 1]["units"][0]["a_in"] if k + 1 < len(self.blocks) else self.a_last
+            sd_view = sd.view(B, Ln + 1, s * c)
+            last = k + 1 == len(self.blocks)      # nothing reads the fp32 stream after the last strided conv
+            self._conv(sd_view, Ln + 1, s * c, blk["wd"], blk["bd"], 2, 1, 0, Ln, B, alpha=nxt_alpha, y=None if last else ws["y"][k + 1],
+                       s_out=ws["sx"][k + 1], s_rows=Ln)
+            c *= 2
+        T = lens[-1]
+        self._conv(ws["sx"][-1], T, c, self.w_last, self.b_last, 3, 1, -1, T, B, zt=z_out)
+        return z_out

@@ -117,6 +117,28 @@ int edm_codes_to_features(const long long* codes, const float* proj, float* out,
 int edm_kmeans_assign(const float* x, long long n_frames, int dim, const float* c_hi, const float* c_lo,
                       const float* half_neg_norm, int n_centroids, long long* idx_out, float* score_out, void* stream);
 
+/* One convolution of the DAC encoder as an implicit GEMM on tcgen05 (bf16 operands, fp32 accumulate), channel-last activations.
+ * Replaces each WNConv1d (+ the Snake1d in front of the NEXT conv, + the ResidualUnit add) of edm_tts/models/dac/encoder.py:11-58 /
+ * nn_layers.py:8-47 (run under bf16 autocast by utility_scripts/dump_tokens/dump_tokens.py:213).
+ *   a        bf16 operand view [B][a_rows][a_cols] (batch stride a_batch_stride elements) that already holds Snake(x); rows outside
+ *            [0, a_rows) read as zero (the conv padding)
+ *   w        bf16 [c_out][n_taps * a_cols], weight-norm folded, K index = tap * a_cols + channel
+ *   out[t]   = bias + sum_j a[t + row_off + j * tap_step] . w[:, j]   for t in [0, rows_out)
+ *   x_res    nullable fp32 [B][rows_out][c_out] added to out (ResidualUnit skip; may alias y)
+ *   y        nullable fp32 stream out, batch stride y_batch_stride
+ *   s_out    nullable bf16 operand out = Snake_alpha(out) (alpha nullable = identity), row t + s_row_off, rows >= s_rows dropped
+ *   zt_out   nullable [B][c_out][rows_out] (fp32 if zt_is_f32 else bf16): the latent z in the reference's [B, D, T] layout
+ * a_cols % 64 == 0, c_out % 64 == 0 and <= 1024. */
+int edm_dac_conv(const void* a, long long a_rows, int a_cols, long long a_batch_stride, int B, const void* w, int c_out,
+                 int n_taps, int tap_step, int row_off, int rows_out, const float* bias, const float* alpha, const float* x_res,
+                 float* y, long long y_batch_stride, void* s_out, long long s_batch_stride, int s_row_off, int s_rows,
+                 void* zt_out, int zt_is_f32, void* stream);
+
+/* First conv of the encoder (1 -> c0 channels, k = 7, padding 3; encoder.py:38) on CUDA cores: audio fp32 [B][L] ->
+ * y fp32 [B][L][c0] and s_out bf16 = Snake_alpha(y). w fp32 [c0][7]; c0 % 16 == 0. */
+int edm_dac_conv_first(const float* audio, int B, int L, const float* w, const float* bias, const float* alpha, int c0, float* y,
+                       void* s_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * S2A decoder context: InjectionConformerModel.infer_special, modeling_injection_conformer.py:130-230, and
  * InjectionConformerWrapper.forward_first_level / forward, injection_conformer_wrapper.py:65-150.
