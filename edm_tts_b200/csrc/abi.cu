@@ -629,8 +629,27 @@ int make_tmap_conv_a(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t rows,
   return 0;
 }
 
+// output boxes of the conv epilogue: 32 columns x 32 rows x 1 batch of [B][rows][cols]; fp32 (128 B rows, swizzle 128B) or bf16
+// (64 B rows, swizzle 64B). Rows >= `rows` are clipped by TMA (ragged last tile, end of the padded operand).
+int make_tmap_conv_out(CUtensorMap* m, const void* ptr, bool f32, uint64_t B, uint64_t rows, uint64_t cols, uint64_t batch_stride) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (enc == nullptr) return fail(EDM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const uint64_t es = f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (cols * es) % 16 != 0 || (batch_stride * es) % 16 != 0)
+    return fail(EDM_ERR_INVALID, "conv output must be 16-byte aligned");
+  cuuint64_t dims[3] = {cols, rows, B};
+  cuuint64_t strides[2] = {cols * es, batch_stride * es};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EDM_ERR_CUDA, "cuTensorMapEncodeTiled(conv output rows=%llu cols=%llu) failed: %d", (unsigned long long)rows, (unsigned long long)cols, (int)r);
+  return 0;
+}
+
 template <int NT>
-int launch_dac_conv(const CUtensorMap& ma, const CUtensorMap& mw, DacConvParams& p, cudaStream_t st) {
+int launch_dac_conv(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& ms, DacConvParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     EDM_CUDA(cudaFuncSetAttribute(dac_conv_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, dac_conv_smem_bytes<NT>()));
@@ -640,7 +659,7 @@ int launch_dac_conv(const CUtensorMap& ma, const CUtensorMap& mw, DacConvParams&
   const long long tiles = static_cast<long long>(p.B) * p.tiles_per_batch * p.n_tiles_n;
   if (tiles > 0x7fffffffLL) return fail(EDM_ERR_INVALID, "dac_conv: too many tiles");
   const int grid = tiles < num_sms() ? static_cast<int>(tiles) : num_sms();
-  dac_conv_kernel<NT><<<grid, kDcThreads, dac_conv_smem_bytes<NT>(), st>>>(ma, mw, p);
+  dac_conv_kernel<NT><<<grid, kDcThreads, dac_conv_smem_bytes<NT>(), st>>>(ma, mw, my, ms, p);
   EDM_LAUNCH_CHECK("dac_conv");
   return 0;
 }
@@ -666,10 +685,20 @@ extern "C" int edm_dac_conv(const void* a, long long a_rows, int a_cols, long lo
   p.bias = bias; p.alpha = alpha; p.x_res = x_res; p.y = y; p.y_batch_stride = y_batch_stride;
   p.s_out = static_cast<__nv_bfloat16*>(s_out); p.s_batch_stride = s_batch_stride; p.s_row_off = s_row_off; p.s_rows = s_rows;
   p.zt_out = zt_out; p.zt_is_f32 = zt_is_f32;
+  if (x_res != nullptr && x_res != y) return fail(EDM_ERR_INVALID, "dac_conv: the residual input must be the stream that is updated (x_res == y)");
+  CUtensorMap my = ma, ms = ma;  // placeholders when the output is absent (never dereferenced by the kernel)
+  if (y != nullptr)
+    if (int rc = make_tmap_conv_out(&my, y, true, B, rows_out, c_out, static_cast<uint64_t>(y_batch_stride))) return rc;
+  if (s_out != nullptr) {
+    const long long lim = static_cast<long long>(rows_out) + s_row_off;
+    const long long s_eff = s_rows < lim ? s_rows : lim;
+    if (s_eff <= 0 || s_row_off < 0) return fail(EDM_ERR_INVALID, "dac_conv: operand output rows");
+    if (int rc = make_tmap_conv_out(&ms, s_out, false, B, static_cast<uint64_t>(s_eff), c_out, static_cast<uint64_t>(s_batch_stride))) return rc;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (nt == 256) return launch_dac_conv<256>(ma, mw, p, st);
-  if (nt == 128) return launch_dac_conv<128>(ma, mw, p, st);
-  return launch_dac_conv<64>(ma, mw, p, st);
+  if (nt == 256) return launch_dac_conv<256>(ma, mw, my, ms, p, st);
+  if (nt == 128) return launch_dac_conv<128>(ma, mw, my, ms, p, st);
+  return launch_dac_conv<64>(ma, mw, my, ms, p, st);
 }
 
 extern "C" int edm_dac_conv_first(const float* audio, int B, int L, const float* w, const float* bias, const float* alpha, int c0,

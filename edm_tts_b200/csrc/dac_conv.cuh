@@ -22,14 +22,19 @@
 //
 //   warp 0     : TMA producer (A box 128 rows x 64 channels, W box NT rows x 64), 4-stage ring
 //   warp 1     : MMA issuer (whole warp, elected lane), accumulator double-buffered in TMEM (2 x NT columns)
-//   warps 2-9  : epilogue, two warps per TMEM lane quadrant, each owning half of the tile's columns
+//   warps 2-9  : epilogue, two warps per TMEM lane quadrant, each owning half of the tile's columns. A thread owns a time row, so
+//                direct global accesses would touch 32 different lines per warp instruction; instead every warp has a staging
+//                box in shared memory: the residual x is fetched with fully coalesced loads (4 rows x 128 B per instruction, one
+//                chunk ahead) and transposed through the box, and y (fp32) / s_out (bf16) leave as swizzled 32-row TMA store
+//                boxes whose tensor maps clip the ragged last tile
 #pragma once
 #include "ptx.cuh"
 
 namespace edm {
 
 constexpr int kDcThreads = 320;
-constexpr int kDcStages = 4;
+template <int NT> struct DacConvStages { static constexpr int value = NT == 256 ? 3 : 4; };
+constexpr uint32_t kDcStagingBytes = 4096 + 2048;   // per epilogue warp: y box (32 rows x 128 B, swizzle 128B) + s box (32 rows x 64 B, swizzle 64B)
 constexpr int kDcBM = 128;
 constexpr uint32_t kDcABytes = kDcBM * 64 * 2;  // 16 KB
 constexpr int kDcMaxCout = 1024;
@@ -42,7 +47,7 @@ struct DacConvParams {
   const float* x_res;                       // fp32 [B][rows_out][c_out] residual input or nullptr (may alias y)
   float* y;                                 // fp32 stream out or nullptr
   long long y_batch_stride;                 // elements
-  __nv_bfloat16* s_out;                     // bf16 operand out or nullptr: row (t + s_row_off) of batch b, rows >= s_rows are dropped
+  __nv_bfloat16* s_out;                     // bf16 operand out or nullptr: row (t + s_row_off) of batch b; the tensor map drops rows >= s_rows
   long long s_batch_stride;
   int s_row_off, s_rows;
   void* zt_out;                             // [B][c_out][rows_out] (bf16 or fp32) or nullptr
@@ -51,7 +56,7 @@ struct DacConvParams {
 
 template <int NT>
 constexpr uint32_t dac_conv_smem_bytes() {
-  return kDcStages * (kDcABytes + NT * 128) + 3 * kDcMaxCout * 4 + 1024 + 256;
+  return DacConvStages<NT>::value * (kDcABytes + NT * 128) + 8 * kDcStagingBytes + 3 * kDcMaxCout * 4 + 1024 + 256;
 }
 
 __device__ __forceinline__ float snake_act(float v, float a, float inv_a) {
@@ -61,13 +66,16 @@ __device__ __forceinline__ float snake_act(float v, float a, float inv_a) {
 
 template <int NT>
 __global__ void __launch_bounds__(kDcThreads, 1)
-dac_conv_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, const DacConvParams p) {
+dac_conv_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w, const __grid_constant__ CUtensorMap tma_y,
+                const __grid_constant__ CUtensorMap tma_s, const DacConvParams p) {
+  constexpr int kDcStages = DacConvStages<NT>::value;
   constexpr uint32_t kBBytes = NT * 128;
   constexpr uint32_t kStageBytes = kDcABytes + kBBytes;
   constexpr int kTmemCols = 2 * NT < 32 ? 32 : 2 * NT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  float* s_bias = reinterpret_cast<float*>(smem + kDcStages * kStageBytes);
+  uint8_t* staging = smem + kDcStages * kStageBytes;
+  float* s_bias = reinterpret_cast<float*>(staging + 8 * kDcStagingBytes);
   float* s_alpha = s_bias + kDcMaxCout;
   float* s_inva = s_alpha + kDcMaxCout;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_inva + kDcMaxCout);
@@ -84,6 +92,8 @@ dac_conv_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_w);
+    if (p.y != nullptr) tma_prefetch_desc(&tma_y);
+    if (p.s_out != nullptr) tma_prefetch_desc(&tma_s);
     for (int s = 0; s < kDcStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -158,75 +168,118 @@ dac_conv_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     const int half = (warp - 2) >> 2;
     const int r_in = quad * 32 + lane;
     constexpr int kColsPerWarp = NT / 2;
+    constexpr int kChunks = kColsPerWarp / 32;
+    uint8_t* stg_y = staging + (warp - 2) * kDcStagingBytes;
+    uint8_t* stg_s = stg_y + 4096;
+    const uint32_t y_row = smem_u32(stg_y) + lane * 128;
+    const uint32_t s_row = smem_u32(stg_s) + lane * 64;
+    const int sw = lane & 7, sw64 = (lane >> 1) & 3;
+    const int xr_row = lane >> 3, xr_ch = lane & 7;      // coalesced pattern: instruction k covers rows 4k .. 4k+3 of the warp's 32
+    const bool has_res = p.x_res != nullptr;
+    const bool has_y = p.y != nullptr, has_s = p.s_out != nullptr, has_alpha = p.alpha != nullptr;
+    const int total_chunks = my_tiles * kChunks;
+
+    // residual rows of flat chunk q (tile q / kChunks, column chunk q % kChunks), fetched one chunk ahead
+    auto load_x = [&](int q, float4 (&xr)[8]) {
+      int b, t0, n0;
+      decode(blockIdx.x + (q / kChunks) * gridDim.x, b, t0, n0);
+      const int col = n0 + half * kColsPerWarp + (q % kChunks) * 32;
+      const float* base = p.x_res + static_cast<long long>(b) * p.y_batch_stride + col + xr_ch * 4;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int t = t0 + quad * 32 + k * 4 + xr_row;
+        xr[k] = t < p.rows_out ? __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(t) * p.c_out)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    float4 xr[8];
+    if (has_res && total_chunks > 0) load_x(0, xr);
+
     for (int tl = 0; tl < my_tiles; ++tl) {
       int b, t0, n0;
       decode(blockIdx.x + tl * gridDim.x, b, t0, n0);
       const uint32_t buf = tl & 1;
       const int t = t0 + r_in;
-      const bool valid = t < p.rows_out;
-      const bool s_valid = valid && p.s_out != nullptr && (t + p.s_row_off) < p.s_rows;
       mbar_wait(&tfull_bar[buf], (tl >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * NT + half * kColsPerWarp;
 #pragma unroll 1
-      for (int cc = 0; cc < kColsPerWarp / 32; ++cc) {
+      for (int cc = 0; cc < kChunks; ++cc) {
         uint32_t r[32];
         tmem_ld_32x32(taddr + cc * 32, r);
         tmem_ld_wait_dep(r);
-        if (cc == kColsPerWarp / 32 - 1) {
+        if (cc == kChunks - 1) {
           tc_fence_before();
           mbar_arrive(&tempty_bar[buf]);
         }
         const int col = n0 + half * kColsPerWarp + cc * 32;
         float v[32];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]) + s_bias[col + e];
-        if (valid) {
-          const long long yo = static_cast<long long>(b) * p.y_batch_stride + static_cast<long long>(t) * p.c_out + col;
-          if (p.x_res != nullptr) {
-            const float4* xr = reinterpret_cast<const float4*>(p.x_res + yo);
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = lds128(smem_u32(s_bias + col) + 16 * i);
+          v[4 * i] = __uint_as_float(r[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
+          v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
+        }
+        // the previous chunk's store boxes have been read out of the staging buffers
+        if (lane == 0) bulk_wait_group_read0();
+        __syncwarp();
+        if (has_res) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 x4 = xr[i];
-              v[4 * i] += x4.x; v[4 * i + 1] += x4.y; v[4 * i + 2] += x4.z; v[4 * i + 3] += x4.w;
-            }
-          }
-          if (p.y != nullptr) {
-            float4* yw = reinterpret_cast<float4*>(p.y + yo);
+          for (int k = 0; k < 8; ++k) sts128(smem_u32(stg_y) + (k * 4 + xr_row) * 128 + ((xr_ch ^ ((k * 4 + xr_row) & 7)) << 4), xr[k]);
+          __syncwarp();
+          const int q = tl * kChunks + cc + 1;
+          if (q < total_chunks) load_x(q, xr);     // next chunk's residual rows: in flight during this chunk's math and stores
 #pragma unroll
-            for (int i = 0; i < 8; ++i) yw[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-          if (p.zt_out != nullptr) {
-            const long long zo = (static_cast<long long>(b) * p.c_out + col) * p.rows_out + t;
-            if (p.zt_is_f32) {
-              float* z = static_cast<float*>(p.zt_out) + zo;
-#pragma unroll
-              for (int e = 0; e < 32; ++e) z[static_cast<long long>(e) * p.rows_out] = v[e];
-            } else {
-              __nv_bfloat16* z = static_cast<__nv_bfloat16*>(p.zt_out) + zo;
-#pragma unroll
-              for (int e = 0; e < 32; ++e) z[static_cast<long long>(e) * p.rows_out] = __float2bfloat16(v[e]);
-            }
+          for (int i = 0; i < 8; ++i) {
+            const float4 x4 = lds128(y_row + ((i ^ sw) << 4));
+            v[4 * i] += x4.x; v[4 * i + 1] += x4.y; v[4 * i + 2] += x4.z; v[4 * i + 3] += x4.w;
           }
         }
-        if (s_valid) {
-          uint32_t w[16];
-          if (p.alpha != nullptr) {
+        if (has_y) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              w[e] = pack_bf16x2(snake_act(v[2 * e], s_alpha[col + 2 * e], s_inva[col + 2 * e]),
-                                 snake_act(v[2 * e + 1], s_alpha[col + 2 * e + 1], s_inva[col + 2 * e + 1]));
+          for (int i = 0; i < 8; ++i) sts128(y_row + ((i ^ sw) << 4), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+        }
+        if (p.zt_out != nullptr && t < p.rows_out) {
+          const long long zo = (static_cast<long long>(b) * p.c_out + col) * p.rows_out + t;
+          if (p.zt_is_f32) {
+            float* z = static_cast<float*>(p.zt_out) + zo;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) z[static_cast<long long>(e) * p.rows_out] = v[e];
+          } else {
+            __nv_bfloat16* z = static_cast<__nv_bfloat16*>(p.zt_out) + zo;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) z[static_cast<long long>(e) * p.rows_out] = __float2bfloat16(v[e]);
+          }
+        }
+        if (has_s) {
+          uint32_t w[16];
+          if (has_alpha) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 a4 = lds128(smem_u32(s_alpha + col) + 16 * i), ia4 = lds128(smem_u32(s_inva + col) + 16 * i);
+              w[2 * i] = pack_bf16x2(snake_act(v[4 * i], a4.x, ia4.x), snake_act(v[4 * i + 1], a4.y, ia4.y));
+              w[2 * i + 1] = pack_bf16x2(snake_act(v[4 * i + 2], a4.z, ia4.z), snake_act(v[4 * i + 3], a4.w, ia4.w));
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e) w[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
           }
-          uint4* so = reinterpret_cast<uint4*>(p.s_out + static_cast<long long>(b) * p.s_batch_stride +
-                                               static_cast<long long>(t + p.s_row_off) * p.c_out + col);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) so[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+          for (int i = 0; i < 4; ++i)
+            sts128(s_row + ((i ^ sw64) << 4), make_float4(__uint_as_float(w[4 * i]), __uint_as_float(w[4 * i + 1]), __uint_as_float(w[4 * i + 2]),
+                                                          __uint_as_float(w[4 * i + 3])));
+        }
+        if (has_y || has_s) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (has_y) tma_store_3d(&tma_y, stg_y, col, t0 + quad * 32, b);
+            if (has_s) tma_store_3d(&tma_s, stg_s, col, t0 + quad * 32 + p.s_row_off, b);
+            bulk_commit_group();
+          }
         }
       }
     }
+    if (lane == 0) bulk_wait_group0();   // all stores have landed before the CTA exits
   }
 
   tc_fence_before();

@@ -507,8 +507,75 @@ def test_kmeans():
               f"torch cdist+argmax {ms_ref:.3f} ms; mismatches vs torch fp32 {(ids != ref).sum().item()}", flush=True)
 
 
+def test_dacenc():
+    """DAC conv encoder at the dump_tokens shape (60 s segments -> L = 960160, T = 3000): whole-encoder time, per-conv times and
+    the same stack in plain torch (bf16 autocast, channels-first F.conv1d) as the GPU incumbent."""
+    import math
+    import torch.nn.functional as F
+    from edm_tts_b200.dac_encoder import DACEncoder, _fold
+    from edm_tts_b200.synthetic import make_encoder_state_dict
+    B, Ls = int(os.environ.get("DAC_B", "8")), int(os.environ.get("DAC_L", "960160"))
+    sd = make_encoder_state_dict(64, (2, 4, 5, 8), 0)
+    enc = DACEncoder(sd, 64)
+    audio = (torch.randn(B, 1, Ls, device=dev) * 0.3).clamp(-1, 1)
+    z = enc(audio)
+    torch.cuda.synchronize()
+    ms = timeit(lambda: enc(audio), iters=3, warm=1)
+    flop = 2.0 * 767.0e3 * B * Ls
+    print(f"dac encoder B={B} L={Ls}: {ms:.2f} ms = {B * z.shape[-1] / ms / 1e3:.2f} Mframes/s, {flop / ms / 1e9:.0f} TFLOP/s algorithmic", flush=True)
+    # per-launch times
+    times = []
+    orig = enc._conv
+
+    def timed(a, a_rows, a_cols, w, bias, taps, step, off, rows_out, Bc, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(a, a_rows, a_cols, w, bias, taps, step, off, rows_out, Bc, **kw)
+        e1.record()
+        times.append((f"cin={a_cols} cout={w.shape[0]} taps={taps} step={step} rows={rows_out}", 2.0 * Bc * rows_out * w.shape[0] * w.shape[1], e0, e1))
+    enc._conv = timed
+    enc(audio)
+    torch.cuda.synchronize()
+    enc._conv = orig
+    tot = 0.0
+    for name, fl, e0, e1 in times:
+        t = e0.elapsed_time(e1)
+        tot += t
+        print(f"  {name:58s} {t:8.3f} ms  {fl / t / 1e9:7.0f} TFLOP/s", flush=True)
+    print(f"  sum of convs {tot:.2f} ms", flush=True)
+
+    # torch incumbent
+    def fold(key):
+        return _fold(sd, key).to(dev), sd[key + ".bias"].to(dev)
+
+    def snake(x, key):
+        a = sd[key + ".alpha"].to(dev)
+        return x + (a + 1e-9).reciprocal() * torch.sin(a * x).pow(2)
+    W = {k[: -len(".bias")]: fold(k[: -len(".bias")]) for k in sd if k.endswith(".bias")}
+
+    def torch_enc(x):
+        x = F.conv1d(x, *W["block.0"], padding=3)
+        n = 1
+        for s in (2, 4, 5, 8):
+            for u, d in enumerate((1, 3, 9)):
+                ru = f"block.{n}.block.{u}.block."
+                h = F.conv1d(snake(x, ru + "0"), *W[ru + "1"], dilation=d, padding=3 * d)
+                h = F.conv1d(snake(h, ru + "2"), *W[ru + "3"])
+                x = x + h
+            x = F.conv1d(snake(x, f"block.{n}.block.3"), *W[f"block.{n}.block.4"], stride=s, padding=math.ceil(s / 2))
+            n += 1
+        return F.conv1d(snake(x, f"block.{n}"), *W[f"block.{n + 1}"], padding=1)
+    Bt = min(B, 4)
+    with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+        zt = torch_enc(audio[:Bt])
+        torch.cuda.synchronize()
+        ms_t = timeit(lambda: torch_enc(audio[:Bt]), iters=2, warm=1)
+    rel = ((z[:Bt].float() - zt.float()).pow(2).sum().sqrt() / zt.float().pow(2).sum().sqrt()).item()
+    print(f"torch bf16-autocast encoder B={Bt}: {ms_t:.2f} ms = {Bt * z.shape[-1] / ms_t / 1e3:.3f} Mframes/s ({ms_t / Bt * B / ms:.1f}x ours per utterance); rel L2 ours vs torch-bf16 {rel:.2e}", flush=True)
+
+
 if __name__ == "__main__":
     t0 = time.time()
-    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvq": test_rvq, "rvqtc": test_rvqtc, "rvqtime": test_rvqtime, "gemmsus": test_gemmsus, "kmeans": test_kmeans}[sys.argv[1]]()
+    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvq": test_rvq, "rvqtc": test_rvqtc, "rvqtime": test_rvqtime, "gemmsus": test_gemmsus, "kmeans": test_kmeans, "dacenc": test_dacenc}[sys.argv[1]]()
     torch.cuda.synchronize()
     print(f"[{sys.argv[1]}] done in {time.time() - t0:.1f}s", flush=True)
