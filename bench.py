@@ -283,6 +283,23 @@ def main():
     zb = zb.to(torch.bfloat16)          # what the DAC encoder hands over under the reference's bf16 autocast (dump_tokens.py:213)
     rvq_ms = time_rvq(zb)
     del zb
+    # the same dump_tokens batch from audio: DAC conv encoder + RVQ, 32 x 60 s segments resident in HBM
+    from edm_tts_b200.dac import DAC
+    from edm_tts_b200.synthetic import make_dac_state_dict
+
+    dac = DAC(make_dac_state_dict(0), device=dev)
+    audio = (torch.randn(32, 1, 960160, device=dev) * 0.3).clamp_(-1, 1)
+    dac.encode_to_codes(audio)
+    torch.cuda.synchronize()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(3):
+        dac.encode_to_codes(audio)
+    r1.record()
+    torch.cuda.synchronize()
+    enc_ms = r0.elapsed_time(r1) / 3
+    del audio, dac
+    torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -312,6 +329,12 @@ def main():
                       "note": "tcgen05 kind::tf32: 3xTF32 projection GEMM (z read once through MN-major TMA boxes) + 12-level search with the "
                               "[128 frames x 1024 codes] score tiles in TMEM; the search is bound by TMEM traffic (score reads + accumulator writes share the port: "
                               "0.20 ms floor without any compare work) and the per-score compare work, the projection by the L2->SM fabric, not by HBM"},
+        "secondary_encode": {"metric": "dac_encode_to_codes_frames_per_s", "value": 32 * 3000 / (enc_ms * 1e-3), "unit": "frames/s", "ms": enc_ms,
+                             "workload": "DAC.encode_to_codes, audio [32, 1, 960160] fp32 (32 x 60 s at 16 kHz, dump_tokens batch) -> codes [32, 12, 3000], per GPU",
+                             "algorithmic_tflops": 2 * 767.0e3 * 32 * 960160 / (enc_ms * 1e-3) / 1e12,
+                             "frac_of_tensor_peak": 2 * 767.0e3 * 32 * 960160 / (enc_ms * 1e-3) / 1e12 / tf_peak,
+                             "note": "conv encoder = 29 implicit-GEMM launches per chunk of 8 utterances (csrc/dac_conv.cuh, bf16 operands, fp32 stream) + the RVQ kernels above; "
+                                     "767 kMAC per audio sample; the 64/128-channel stages are HBM / L2 bound, the 256..1024-channel stages run at 1.1-1.3 PFLOP/s"},
         "model_flops_utilisation": {"algorithmic_tflops": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12,
                                     "frac_of_peak": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12 / tf_peak},
     }

@@ -13,4 +13,10 @@ def __getattr__(name):
     if name == "ResidualVectorQuantize":
         from .dac_rvq import ResidualVectorQuantize
         return ResidualVectorQuantize
+    if name == "DAC":
+        from .dac import DAC
+        return DAC
+    if name == "DACEncoder":
+        from .dac_encoder import DACEncoder
+        return DACEncoder
     raise AttributeError(name)

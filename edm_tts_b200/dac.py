@@ -1,0 +1,59 @@
+"""The encode side of the reference's DAC module on the CUDA path: conv encoder + residual vector quantizer.
+
+Mirrors edm_tts/models/dac/modeling_dac.py: DAC.encode (:111-139, without the resampling of preprocess), encode_to_codes (:163-167),
+codes_to_features / codes_to_features_unreduced (:173-182). State-dict keys are the reference's (`encoder.block...`,
+`quantizer.quantizers...`). The conv decoder (decode / decode_from_codes) is not part of this path and raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from .config import DACConfig
+from .dac_encoder import DACEncoder
+from .dac_rvq import ResidualVectorQuantize
+
+
+class DAC:
+    def __init__(self, state_dict: dict, config=None, device="cuda"):
+        self.config = cfg = DACConfig.from_any(config)
+        self.device = torch.device(device)
+        self.sample_rate = cfg.sample_rate
+        self.n_codebooks, self.codebook_size, self.codebook_dim = cfg.n_codebooks, cfg.codebook_size, cfg.codebook_dim
+        self.encoder = DACEncoder(state_dict, cfg.encoder_dim, cfg.encoder_rates, prefix="encoder.", device=device)
+        self.latent_dim = self.encoder.enc_dim
+        self.hop_length = self.encoder.hop_length
+        self.quantizer = ResidualVectorQuantize(state_dict, n_codebooks=cfg.n_codebooks, codebook_size=cfg.codebook_size,
+                                                codebook_dim=cfg.codebook_dim, input_dim=self.latent_dim, prefix="quantizer.", device=device)
+
+    def eval(self):
+        return self
+
+    @torch.no_grad()
+    def encode_to_codes(self, audio: torch.Tensor, n_quantizers=None) -> torch.Tensor:
+        """audio [B, 1, L] -> codes int64 [B, n_codebooks, T] (modeling_dac.py:163-167). z stays bf16 between the encoder and the
+        quantizer, as under the reference's autocast (dump_tokens.py:213)."""
+        z = self.encoder(audio, out_dtype=torch.bfloat16)
+        return self.quantizer.encode(z, n_quantizers)
+
+    @torch.no_grad()
+    def encode(self, audio_data: torch.Tensor, sample_rate=None, n_quantizers=None) -> dict:
+        """modeling_dac.py:111-139 for audio already at the model's sample rate."""
+        if sample_rate is not None and sample_rate != self.sample_rate:
+            raise ValueError("resample the audio to the model's sample rate first (preprocess is not part of this path)")
+        length = audio_data.shape[-1]
+        z = self.encoder(audio_data, out_dtype=torch.float32)
+        out = {"length": length, "z": z}
+        q = self.quantizer(z, n_quantizers)
+        out.update(q)
+        return out
+
+    def codes_to_features(self, codes):
+        return self.quantizer.from_codes(codes)[0]
+
+    def codes_to_features_unreduced(self, codes):
+        return self.quantizer.from_codes_unreduced(codes)
+
+    def decode(self, *a, **k):
+        raise NotImplementedError("the DAC conv decoder is outside the accelerated path (SURVEY.md section 8f, rank 2)")
+
+    decode_from_codes = decode

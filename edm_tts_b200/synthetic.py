@@ -150,6 +150,13 @@ def make_encoder_state_dict(encoder_dim: int = 64, rates=(2, 4, 5, 8), seed: int
     return sd
 
 
+def make_dac_state_dict(seed: int = 0) -> dict:
+    """Encoder + quantizer parameters keyed as DAC.state_dict() (`encoder.`, `quantizer.`) at the base config."""
+    sd = make_encoder_state_dict(64, (2, 4, 5, 8), seed, prefix="encoder.")
+    sd.update(make_quantizer_state_dict(OracleConfig(), seed, prefix="quantizer."))
+    return sd
+
+
 def make_inputs(B: int, T: int, P: int, steps: int, cfg: OracleConfig, seed: int = 1234) -> dict:
     """Synthetic tokens + injected sampling noise, all from one CPU generator."""
     g = torch.Generator(device="cpu")
