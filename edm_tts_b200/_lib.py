@@ -48,6 +48,7 @@ _SIGNATURES = {
     "edm_rvq_tc_debug": (None, [_u, _u, _i, _i]),
     "edm_kmeans_assign": (_i, [_vp, _ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "edm_dac_conv": (_i, [_vp, _ll, _i, _ll, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _vp, _i, _vp]),
+    "edm_dac_resunit": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _i, _i, _vp]),
     "edm_dac_conv_first": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "edm_codes_to_features": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "edm_s2a_num_weights": (_i, [C.POINTER(S2AConfig)]),

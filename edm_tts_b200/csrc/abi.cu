@@ -701,6 +701,49 @@ extern "C" int edm_dac_conv(const void* a, long long a_rows, int a_cols, long lo
   return launch_dac_conv<64>(ma, mw, my, ms, p, st);
 }
 
+namespace {
+template <int C>
+int launch_dac_resunit(const CUtensorMap& ma, const CUtensorMap& m7, const CUtensorMap& m1, const CUtensorMap& my, const CUtensorMap& ms,
+                       const DacResUnitParams& p, int s_row_off, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    EDM_CUDA(cudaFuncSetAttribute(dac_resunit_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, dac_resunit_smem_bytes<C>()));
+    attr_set = true;
+  }
+  const long long tiles = static_cast<long long>(p.B) * p.tiles_per_batch;
+  if (tiles > 0x7fffffffLL) return fail(EDM_ERR_INVALID, "dac_resunit: too many tiles");
+  const int grid = tiles < num_sms() ? static_cast<int>(tiles) : num_sms();
+  dac_resunit_kernel<C><<<grid, kDcThreads, dac_resunit_smem_bytes<C>(), st>>>(ma, m7, m1, my, ms, p, s_row_off);
+  EDM_LAUNCH_CHECK("dac_resunit");
+  return 0;
+}
+}  // namespace
+
+extern "C" int edm_dac_resunit(const void* a, long long a_batch_stride, int B, int rows, int channels, int dilation, const void* w7,
+                               const void* w1, const float* b7, const float* a_mid, const float* b1, const float* a_next, float* y,
+                               long long y_batch_stride, void* s_out, long long s_batch_stride, int s_row_off, int s_rows, void* stream) {
+  if (int rc = check_arch()) return rc;
+  if (B <= 0 || rows <= 0) return 0;
+  if (channels != 64 && channels != 128) return fail(EDM_ERR_INVALID, "dac_resunit: fused kernel exists for 64 and 128 channels (got %d)", channels);
+  if (a == s_out) return fail(EDM_ERR_INVALID, "dac_resunit: s_out must not alias the input operand (neighbouring tiles still read its halo)");
+  if (!b7 || !a_mid || !b1 || !a_next || !y || !s_out || s_row_off < 0) return fail(EDM_ERR_INVALID, "dac_resunit: null argument");
+  CUtensorMap ma, m7, m1, my, ms;
+  if (int rc = make_tmap_conv_a(&ma, a, B, rows, channels, static_cast<uint64_t>(a_batch_stride))) return rc;
+  if (int rc = make_tmap_2d(&m7, w7, channels, 7ull * channels, 7ull * channels, channels)) return rc;
+  if (int rc = make_tmap_2d(&m1, w1, channels, channels, channels, channels)) return rc;
+  if (int rc = make_tmap_conv_out(&my, y, true, B, rows, channels, static_cast<uint64_t>(y_batch_stride))) return rc;
+  const long long lim = static_cast<long long>(rows) + s_row_off;
+  const long long s_eff = s_rows < lim ? s_rows : lim;
+  if (s_eff <= 0) return fail(EDM_ERR_INVALID, "dac_resunit: operand output rows");
+  if (int rc = make_tmap_conv_out(&ms, s_out, false, B, static_cast<uint64_t>(s_eff), channels, static_cast<uint64_t>(s_batch_stride))) return rc;
+  DacResUnitParams p;
+  p.B = B; p.rows = rows; p.tiles_per_batch = (rows + kDcBM - 1) / kDcBM; p.dilation = dilation;
+  p.b7 = b7; p.a_mid = a_mid; p.b1 = b1; p.a_next = a_next; p.y = y; p.y_batch_stride = y_batch_stride;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (channels == 64) return launch_dac_resunit<64>(ma, m7, m1, my, ms, p, s_row_off, st);
+  return launch_dac_resunit<128>(ma, m7, m1, my, ms, p, s_row_off, st);
+}
+
 extern "C" int edm_dac_conv_first(const float* audio, int B, int L, const float* w, const float* bias, const float* alpha, int c0,
                                   float* y, void* s_out, void* stream) {
   if (int rc = check_arch()) return rc;

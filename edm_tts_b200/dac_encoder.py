@@ -24,7 +24,7 @@ def _fold(sd, key):
 
 class DACEncoder:
     def __init__(self, state_dict: dict, d_model: int = 64, strides=(2, 4, 5, 8), prefix: str = "", device="cuda",
-                 max_chunk_samples: int = 1 << 23):
+                 max_chunk_samples: int = 1 << 23, fused: bool = True):
         if not torch.cuda.is_available():
             raise L.EdmError("edm_tts_b200 needs a CUDA device (sm_100); there is no CPU fallback")
         if d_model % 64 != 0 or d_model * 2 ** len(strides) > 1024:
@@ -34,6 +34,7 @@ class DACEncoder:
         self.enc_dim = d_model * 2 ** len(strides)
         self.hop_length = math.prod(strides)
         self.max_chunk_samples = max_chunk_samples
+        self.fused = fused          # False: every ResidualUnit as two conv launches (A/B timing and parity of the fused kernel)
         sd = {k: v.detach().to("cpu") for k, v in state_dict.items() if k.startswith(prefix)}
         dev = self.device
 
@@ -82,13 +83,15 @@ class DACEncoder:
         self._ws.clear()                       # one geometry at a time: the buffers are large
         lens = self.lengths(L_in)
         dev = self.device
-        ws = dict(lens=lens, y=[], sx=[], sh=[], sd=[])
+        ws = dict(lens=lens, y=[], sx=[], sh=[], sd=[], sm=[])
         c = self.d_model
         for k, s in enumerate(self.strides):
             Lk, Ln = lens[k], lens[k + 1]
             ws["y"].append(torch.empty(B, Lk, c, device=dev, dtype=torch.float32))
             ws["sx"].append(torch.empty(B, Lk, c, device=dev, dtype=torch.bfloat16))
-            ws["sh"].append(torch.empty(B, Lk, c, device=dev, dtype=torch.bfloat16))
+            ws["sh"].append(torch.empty(B, Lk, c, device=dev, dtype=torch.bfloat16))     # sx / sh alternate as unit input / output
+            # hidden activation between the two convs of a unit (two-launch form only)
+            ws["sm"].append(None if self.fused and c in (64, 128) else torch.empty(B, Lk, c, device=dev, dtype=torch.bfloat16))
             # operand of the strided conv: `pad` zero rows in front, (Ln + 1) * s rows in all; never-written rows stay zero
             ws["sd"].append(torch.zeros(B, (Ln + 1) * s, c, device=dev, dtype=torch.bfloat16))
             c *= 2
@@ -105,6 +108,11 @@ class DACEncoder:
                                      L.ptr(alpha), L.ptr(x_res), L.ptr(y), y.stride(0) if y is not None else 0, L.ptr(s_out),
                                      s_out.stride(0) if s_out is not None else 0, s_row_off, s_rows, L.ptr(zt),
                                      int(zt is not None and zt.dtype == torch.float32), L.stream_ptr()), "dac_conv")
+
+    def _resunit(self, src, B, rows, c, dilation, ru, a_next, y, dst, dst_off, dst_rows):
+        L.check(L.lib().edm_dac_resunit(L.ptr(src), src.stride(0), B, rows, c, dilation, L.ptr(ru["w7"]), L.ptr(ru["w1"]), L.ptr(ru["b7"]),
+                                        L.ptr(ru["a_mid"]), L.ptr(ru["b1"]), L.ptr(a_next), L.ptr(y), y.stride(0), L.ptr(dst),
+                                        dst.stride(0), dst_off, dst_rows, L.stream_ptr()), "dac_resunit")
 
     @torch.no_grad()
     def forward(self, audio: torch.Tensor, out_dtype=torch.bfloat16) -> torch.Tensor:
@@ -137,16 +145,22 @@ class DACEncoder:
         for k, blk in enumerate(self.blocks):
             s, Lk, Ln = blk["stride"], lens[k], lens[k + 1]
             y, sx, sh, sd = ws["y"][k], ws["sx"][k], ws["sh"][k], ws["sd"][k]
+            src = sx
             for u, ru in enumerate(blk["units"]):
                 d = 3 ** u
-                # dilated k=7 conv of Snake(x); epilogue applies the unit's second Snake
-                self._conv(sx, Lk, c, ru["w7"], ru["b7"], 7, d, -3 * d, Lk, B, alpha=ru["a_mid"], s_out=sh, s_rows=Lk)
-                # 1x1 conv + residual add into the fp32 stream; epilogue applies the Snake in front of the next conv
-                if u < 2:
-                    self._conv(sh, Lk, c, ru["w1"], ru["b1"], 1, 1, 0, Lk, B, alpha=blk["units"][u + 1]["a_in"], x_res=y, y=y, s_out=sx, s_rows=Lk)
+                a_next = blk["units"][u + 1]["a_in"] if u < 2 else blk["a_down"]
+                # the unit's output operand: the other 64/128-channel buffer, or the padded operand of the strided conv
+                dst, dst_off, dst_rows = (sh if src is sx else sx, 0, Lk) if u < 2 else (sd, math.ceil(s / 2), (Ln + 1) * s)
+                if self.fused and c in (64, 128):
+                    # both convs in one launch, the hidden activation stays in shared memory (csrc/dac_conv.cuh, dac_resunit_kernel)
+                    self._resunit(src, B, Lk, c, d, ru, a_next, y, dst, dst_off, dst_rows)
                 else:
-                    self._conv(sh, Lk, c, ru["w1"], ru["b1"], 1, 1, 0, Lk, B, alpha=blk["a_down"], x_res=y, y=y, s_out=sd,
-                               s_row_off=math.ceil(s / 2), s_rows=(Ln + 1) * s)
+                    # dilated k=7 conv of Snake(x); epilogue applies the unit's second Snake
+                    self._conv(src, Lk, c, ru["w7"], ru["b7"], 7, d, -3 * d, Lk, B, alpha=ru["a_mid"], s_out=ws["sm"][k], s_rows=Lk)
+                    # 1x1 conv + residual add into the fp32 stream; epilogue applies the Snake in front of the next conv
+                    self._conv(ws["sm"][k], Lk, c, ru["w1"], ru["b1"], 1, 1, 0, Lk, B, alpha=a_next, x_res=y, y=y, s_out=dst,
+                               s_row_off=dst_off, s_rows=dst_rows)
+                src = dst
             # strided conv on the padded operand viewed as [Ln + 1][s * c]
             nxt_alpha = self.blocks[k + 1]["units"][0]["a_in"] if k + 1 < len(self.blocks) else self.a_last
             sd_view = sd.view(B, Ln + 1, s * c)

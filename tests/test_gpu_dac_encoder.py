@@ -51,6 +51,8 @@ def test_encoder_vs_oracle(B, L):
     _check(z32, ref)
     zb = enc(audio)                                   # bf16 out = the same values rounded once
     assert zb.dtype == torch.bfloat16 and torch.equal(zb, z32.to(torch.bfloat16))
+    # the fused ResidualUnit kernel performs the same arithmetic in the same order as the two-launch form
+    assert torch.equal(DACEncoder(sd, 64, fused=False)(audio, out_dtype=torch.float32), z32)
     # sequences are independent and chunking the batch changes nothing
     if B > 1:
         enc2 = DACEncoder(sd, 64, max_chunk_samples=L)

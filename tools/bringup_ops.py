@@ -533,10 +533,18 @@ def test_dacenc():
         orig(a, a_rows, a_cols, w, bias, taps, step, off, rows_out, Bc, **kw)
         e1.record()
         times.append((f"cin={a_cols} cout={w.shape[0]} taps={taps} step={step} rows={rows_out}", 2.0 * Bc * rows_out * w.shape[0] * w.shape[1], e0, e1))
-    enc._conv = timed
+    orig_ru = enc._resunit
+
+    def timed_ru(src, Bc, rows, c, dilation, ru, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_ru(src, Bc, rows, c, dilation, ru, *a)
+        e1.record()
+        times.append((f"fused unit c={c} dilation={dilation} rows={rows}", 2.0 * Bc * rows * c * c * 8, e0, e1))
+    enc._conv, enc._resunit = timed, timed_ru
     enc(audio)
     torch.cuda.synchronize()
-    enc._conv = orig
+    enc._conv, enc._resunit = orig, orig_ru
     tot = 0.0
     for name, fl, e0, e1 in times:
         t = e0.elapsed_time(e1)
