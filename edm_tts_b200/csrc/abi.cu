@@ -614,14 +614,14 @@ extern "C" int edm_kmeans_assign(const float* x, long long n_frames, int dim, co
 namespace {
 // bf16 operand [B][rows][cols] with an explicit batch stride (elements): box = 64 channels x 128 rows x 1 batch; rows outside
 // [0, rows) are zero-filled (the conv's zero padding)
-int make_tmap_conv_a(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t rows, uint64_t cols, uint64_t batch_stride) {
+int make_tmap_conv_a(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t rows, uint64_t cols, uint64_t batch_stride, uint32_t box_rows = 128) {
   PFN_tmapEncodeTiled enc = get_encode();
   if (enc == nullptr) return fail(EDM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (cols * 2) % 16 != 0 || (batch_stride * 2) % 16 != 0)
     return fail(EDM_ERR_INVALID, "conv operand must be 16-byte aligned");
   cuuint64_t dims[3] = {cols, rows, B};
   cuuint64_t strides[2] = {cols * 2, batch_stride * 2};
-  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t box[3] = {64, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -740,6 +740,26 @@ extern "C" int edm_dac_resunit(const void* a, long long a_batch_stride, int B, i
   p.B = B; p.rows = rows; p.tiles_per_batch = (rows + kDcBM - 1) / kDcBM; p.dilation = dilation;
   p.b7 = b7; p.a_mid = a_mid; p.b1 = b1; p.a_next = a_next; p.y = y; p.y_batch_stride = y_batch_stride;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static int halo_mode = -2;   // bring-up switch EDM_DAC_HALO=0: seven shifted TMA boxes per tile (first form) for 64 channels too
+  if (halo_mode == -2) {
+    const char* e = getenv("EDM_DAC_HALO");
+    halo_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (channels == 64 && halo_mode == 1 && dilation >= 1 && 128 + 6 * dilation <= kRu64HaloRows) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      EDM_CUDA(cudaFuncSetAttribute(dac_resunit64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRu64SmemBytes));
+      attr_set = true;
+    }
+    CUtensorMap mh, m7b;
+    if (int rc = make_tmap_conv_a(&mh, a, B, rows, channels, static_cast<uint64_t>(a_batch_stride), 128 + 6 * dilation)) return rc;
+    if (int rc = make_tmap_2d(&m7b, w7, channels, 7ull * channels, 7ull * channels, 64)) return rc;
+    const long long tiles = static_cast<long long>(p.B) * p.tiles_per_batch;
+    const int grid = tiles < num_sms() ? static_cast<int>(tiles) : num_sms();
+    dac_resunit64_kernel<<<grid, kDcThreads, kRu64SmemBytes, st>>>(mh, m7b, m1, my, ms, p, s_row_off);
+    EDM_LAUNCH_CHECK("dac_resunit64");
+    return 0;
+  }
   if (channels == 64) return launch_dac_resunit<64>(ma, m7, m1, my, ms, p, s_row_off, st);
   return launch_dac_resunit<128>(ma, m7, m1, my, ms, p, s_row_off, st);
 }

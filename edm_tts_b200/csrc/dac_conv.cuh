@@ -540,6 +540,227 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   if (warp == 1) tmem_dealloc<2 * C>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// 64-channel ResidualUnit, second form: the L2 -> SM fabric bounds dac_resunit_kernel<64> (every 128-row tile pulls seven shifted
+// 16 KB copies of its input rows and 64 KB of weights). Here
+//   * W7 (56 KB) and W1 (8 KB) are loaded once per CTA and stay in shared memory;
+//   * the input rows are loaded once per tile with their halo ([128 + 6 d] rows x 64 channels, one TMA box), and tap j of the
+//     dilated conv is the same tile read through a UMMA descriptor whose start address is advanced by j * d rows (128 B each).
+//     The 128B-swizzle XOR is a function of the absolute shared-memory address bits (TMA writes and UMMA reads agree on it), so
+//     a start address that is not a multiple of the 1024 B swizzle atom works as is, with the descriptor's base-offset field
+//     left at zero (measured: bit-identical to the seven-box form; setting base offset = (addr >> 7) & 7 gives wrong results).
+// Everything else (h tile, second GEMM, epilogue phases) is as in dac_resunit_kernel.
+constexpr int kRu64HaloRows = 192;                                 // >= 128 + 6 * 9
+constexpr uint32_t kRu64HaloBytes = kRu64HaloRows * 128;           // 24 KB
+constexpr uint32_t kRu64SmemBytes = 7 * 8192 + 8192 + 2 * kRu64HaloBytes + kDcABytes + 8 * kDcStagingBytes + 6 * 64 * 4 + 1024 + 256;
+
+__global__ void __launch_bounds__(kDcThreads, 1)
+dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w7, const __grid_constant__ CUtensorMap tma_w1,
+                     const __grid_constant__ CUtensorMap tma_y, const __grid_constant__ CUtensorMap tma_s, const DacResUnitParams p, const int s_row_off) {
+  constexpr int C = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* s_w7 = smem;                              // 7 taps x [64 co x 64 ci] bf16, 128B-swizzled
+  uint8_t* s_w1 = s_w7 + 7 * 8192;
+  uint8_t* s_a = s_w1 + 8192;                        // 2 halo tiles
+  uint8_t* s_h = s_a + 2 * kRu64HaloBytes;           // [128 x 64] bf16
+  uint8_t* staging = s_h + kDcABytes;
+  float* s_b7 = reinterpret_cast<float*>(staging + 8 * kDcStagingBytes);
+  float* s_am = s_b7 + C;
+  float* s_iam = s_am + C;
+  float* s_b1 = s_iam + C;
+  float* s_an = s_b1 + C;
+  float* s_ian = s_an + C;
+  uint64_t* w_bar = reinterpret_cast<uint64_t*>(s_ian + C);
+  uint64_t* afull_bar = w_bar + 1;     // [2]
+  uint64_t* aempty_bar = afull_bar + 2;  // [2]
+  uint64_t* t1full_bar = aempty_bar + 2;
+  uint64_t* hfull_bar = t1full_bar + 1;
+  uint64_t* t2full_bar = hfull_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t2full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.B * p.tiles_per_batch;
+  const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const uint32_t halo_bytes = static_cast<uint32_t>(128 + 6 * p.dilation) * 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_w7);
+    tma_prefetch_desc(&tma_w1);
+    tma_prefetch_desc(&tma_y);
+    tma_prefetch_desc(&tma_s);
+    mbar_init(w_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&afull_bar[s], 1);
+      mbar_init(&aempty_bar[s], 1);
+    }
+    mbar_init(t1full_bar, 1);
+    mbar_init(hfull_bar, 256);
+    mbar_init(t2full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  for (int i = threadIdx.x; i < C; i += kDcThreads) {
+    s_b7[i] = __ldg(p.b7 + i);
+    s_b1[i] = __ldg(p.b1 + i);
+    const float am = __ldg(p.a_mid + i), an = __ldg(p.a_next + i);
+    s_am[i] = am; s_iam[i] = 1.0f / (am + 1e-9f);
+    s_an[i] = an; s_ian[i] = 1.0f / (an + 1e-9f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, 8 * 8192);
+      for (int j = 0; j < 7; ++j) tma_load_2d(&tma_w7, w_bar, s_w7 + j * 8192, j * 64, 0);
+      tma_load_2d(&tma_w1, w_bar, s_w1, 0, 0);
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        const int tile = blockIdx.x + tl * gridDim.x;
+        const int t0 = (tile % p.tiles_per_batch) * kDcBM, b = tile / p.tiles_per_batch;
+        const int s = tl & 1;
+        mbar_wait(&aempty_bar[s], ((tl >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&afull_bar[s], halo_bytes);
+        tma_load_3d(&tma_a, &afull_bar[s], s_a + s * kRu64HaloBytes, 0, t0 - 3 * p.dilation, b);
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(kDcBM, C, 0, 0);
+    mbar_wait_spin(w_bar, 0);
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int s = tl & 1;
+      mbar_wait_spin(&afull_bar[s], (tl >> 1) & 1);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(s_a + s * kRu64HaloBytes);
+      for (int j = 0; j < 7; ++j) {
+        const uint64_t a_desc = umma_desc_sw128(a_base + j * p.dilation * 128, 16, 1024);
+        const uint64_t b_desc = umma_desc_sw128(smem_u32(s_w7) + j * 8192, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss_warp(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (j | k) != 0 ? 1u : 0u);
+      }
+      umma_commit_warp(&aempty_bar[s]);
+      umma_commit_warp(t1full_bar);
+      mbar_wait_spin(hfull_bar, tl & 1);
+      tc_fence_after();
+      {
+        const uint64_t a_desc = umma_desc_sw128(smem_u32(s_h), 16, 1024), b_desc = umma_desc_sw128(smem_u32(s_w1), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss_warp(tmem_base + C, a_desc + 2 * k, b_desc + 2 * k, idesc, k != 0 ? 1u : 0u);
+      }
+      umma_commit_warp(t2full_bar);
+    }
+  } else {
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r_in = quad * 32 + lane;
+    uint8_t* stg_y = staging + (warp - 2) * kDcStagingBytes;
+    uint8_t* stg_s = stg_y + 4096;
+    const uint32_t y_row = smem_u32(stg_y) + lane * 128;
+    const uint32_t s_row = smem_u32(stg_s) + lane * 64;
+    const int sw = lane & 7, sw64 = (lane >> 1) & 3;
+    const int xr_row = lane >> 3, xr_ch = lane & 7;
+    const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + half * 32;
+    const int col = half * 32;
+
+    auto load_x = [&](int tl, float4 (&xr)[8]) {
+      const int tile = blockIdx.x + tl * gridDim.x;
+      const int t0 = (tile % p.tiles_per_batch) * kDcBM, b = tile / p.tiles_per_batch;
+      const float* base = p.y + static_cast<long long>(b) * p.y_batch_stride + col + xr_ch * 4;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int t = t0 + quad * 32 + k * 4 + xr_row;
+        xr[k] = t < p.rows ? __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(t) * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    float4 xr[8];
+    if (my_tiles > 0) load_x(0, xr);
+
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int tile = blockIdx.x + tl * gridDim.x;
+      const int t0 = (tile % p.tiles_per_batch) * kDcBM, b = tile / p.tiles_per_batch;
+      // ---- phase 1
+      mbar_wait(t1full_bar, tl & 1);
+      tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld_32x32(tq, r);
+        tmem_ld_wait_dep(r);
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = lds128(smem_u32(s_b7 + col) + 16 * i), a4 = lds128(smem_u32(s_am + col) + 16 * i), ia4 = lds128(smem_u32(s_iam + col) + 16 * i);
+          w[2 * i] = pack_bf16x2(snake_act(__uint_as_float(r[4 * i]) + b4.x, a4.x, ia4.x), snake_act(__uint_as_float(r[4 * i + 1]) + b4.y, a4.y, ia4.y));
+          w[2 * i + 1] = pack_bf16x2(snake_act(__uint_as_float(r[4 * i + 2]) + b4.z, a4.z, ia4.z), snake_act(__uint_as_float(r[4 * i + 3]) + b4.w, a4.w, ia4.w));
+        }
+        const uint32_t h_row = smem_u32(s_h) + r_in * 128;
+        const int c0 = col >> 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          sts128(h_row + (((c0 + i) ^ sw) << 4), make_float4(__uint_as_float(w[4 * i]), __uint_as_float(w[4 * i + 1]), __uint_as_float(w[4 * i + 2]),
+                                                           __uint_as_float(w[4 * i + 3])));
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(hfull_bar);
+      // ---- phase 2
+      mbar_wait(t2full_bar, tl & 1);
+      tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld_32x32(tq + C, r);
+        tmem_ld_wait_dep(r);
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = lds128(smem_u32(s_b1 + col) + 16 * i);
+          v[4 * i] = __uint_as_float(r[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
+          v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
+        }
+        if (lane == 0) bulk_wait_group_read0();
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sts128(smem_u32(stg_y) + (k * 4 + xr_row) * 128 + ((xr_ch ^ ((k * 4 + xr_row) & 7)) << 4), xr[k]);
+        __syncwarp();
+        if (tl + 1 < my_tiles) load_x(tl + 1, xr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 x4 = lds128(y_row + ((i ^ sw) << 4));
+          v[4 * i] += x4.x; v[4 * i + 1] += x4.y; v[4 * i + 2] += x4.z; v[4 * i + 3] += x4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sts128(y_row + ((i ^ sw) << 4), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 a4 = lds128(smem_u32(s_an + col) + 16 * i), ia4 = lds128(smem_u32(s_ian + col) + 16 * i);
+          w[2 * i] = pack_bf16x2(snake_act(v[4 * i], a4.x, ia4.x), snake_act(v[4 * i + 1], a4.y, ia4.y));
+          w[2 * i + 1] = pack_bf16x2(snake_act(v[4 * i + 2], a4.z, ia4.z), snake_act(v[4 * i + 3], a4.w, ia4.w));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          sts128(s_row + ((i ^ sw64) << 4), make_float4(__uint_as_float(w[4 * i]), __uint_as_float(w[4 * i + 1]), __uint_as_float(w[4 * i + 2]),
+                                                        __uint_as_float(w[4 * i + 3])));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tma_y, stg_y, col, t0 + quad * 32, b);
+          tma_store_3d(&tma_s, stg_s, col, t0 + quad * 32 + s_row_off, b);
+          bulk_commit_group();
+        }
+      }
+      tc_fence_before();
+    }
+    if (lane == 0) bulk_wait_group0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<128>(tmem_base);
+}
+
 // First conv of the encoder: 1 -> C0 channels, k = 7, padding 3 (encoder.py:38), CUDA cores (7 MACs per output, bandwidth-bound:
 // 4 B in, 6 * C0 B out per sample). Thread <-> (time, 16 channels); writes the fp32 stream and the Snake'd bf16 operand.
 struct DacConv0Params {
