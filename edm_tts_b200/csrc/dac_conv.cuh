@@ -549,10 +549,10 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 //     The 128B-swizzle XOR is a function of the absolute shared-memory address bits (TMA writes and UMMA reads agree on it), so
 //     a start address that is not a multiple of the 1024 B swizzle atom works as is, with the descriptor's base-offset field
 //     left at zero (measured: bit-identical to the seven-box form; setting base offset = (addr >> 7) & 7 gives wrong results).
-// Everything else (h tile, second GEMM, epilogue phases) is as in dac_resunit_kernel.
+// The h tile and both accumulators are double-buffered and the two sides are software-pipelined across tiles (see the MMA warp).
 constexpr int kRu64HaloRows = 192;                                 // >= 128 + 6 * 9
 constexpr uint32_t kRu64HaloBytes = kRu64HaloRows * 128;           // 24 KB
-constexpr uint32_t kRu64SmemBytes = 7 * 8192 + 8192 + 2 * kRu64HaloBytes + kDcABytes + 8 * kDcStagingBytes + 6 * 64 * 4 + 1024 + 256;
+constexpr uint32_t kRu64SmemBytes = 7 * 8192 + 8192 + 2 * kRu64HaloBytes + 2 * kDcABytes + 8 * kDcStagingBytes + 6 * 64 * 4 + 1024 + 256;
 
 __global__ void __launch_bounds__(kDcThreads, 1)
 dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w7, const __grid_constant__ CUtensorMap tma_w1,
@@ -563,8 +563,8 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   uint8_t* s_w7 = smem;                              // 7 taps x [64 co x 64 ci] bf16, 128B-swizzled
   uint8_t* s_w1 = s_w7 + 7 * 8192;
   uint8_t* s_a = s_w1 + 8192;                        // 2 halo tiles
-  uint8_t* s_h = s_a + 2 * kRu64HaloBytes;           // [128 x 64] bf16
-  uint8_t* staging = s_h + kDcABytes;
+  uint8_t* s_h = s_a + 2 * kRu64HaloBytes;           // 2 x [128 x 64] bf16
+  uint8_t* staging = s_h + 2 * kDcABytes;
   float* s_b7 = reinterpret_cast<float*>(staging + 8 * kDcStagingBytes);
   float* s_am = s_b7 + C;
   float* s_iam = s_am + C;
@@ -574,10 +574,10 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   uint64_t* w_bar = reinterpret_cast<uint64_t*>(s_ian + C);
   uint64_t* afull_bar = w_bar + 1;     // [2]
   uint64_t* aempty_bar = afull_bar + 2;  // [2]
-  uint64_t* t1full_bar = aempty_bar + 2;
-  uint64_t* hfull_bar = t1full_bar + 1;
-  uint64_t* t2full_bar = hfull_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t2full_bar + 1);
+  uint64_t* t1full_bar = aempty_bar + 2;  // [2]
+  uint64_t* hfull_bar = t1full_bar + 2;   // [2]
+  uint64_t* t2full_bar = hfull_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t2full_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.B * p.tiles_per_batch;
@@ -594,13 +594,13 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     for (int s = 0; s < 2; ++s) {
       mbar_init(&afull_bar[s], 1);
       mbar_init(&aempty_bar[s], 1);
+      mbar_init(&t1full_bar[s], 1);
+      mbar_init(&hfull_bar[s], 256);
+      mbar_init(&t2full_bar[s], 1);
     }
-    mbar_init(t1full_bar, 1);
-    mbar_init(hfull_bar, 256);
-    mbar_init(t2full_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<128>(tmem_slot);
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
   for (int i = threadIdx.x; i < C; i += kDcThreads) {
     s_b7[i] = __ldg(p.b7 + i);
     s_b1[i] = __ldg(p.b1 + i);
@@ -628,9 +628,12 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       }
     }
   } else if (warp == 1) {
+    // TMEM columns: acc1[0] [0,64) acc1[1] [64,128) acc2[0] [128,192) acc2[1] [192,256). Software pipeline: GEMM 1 of tile i+1 is
+    // issued before GEMM 2 of tile i, and the epilogue warps run phase 1 of tile i+1 before phase 2 of tile i, so neither side
+    // waits for a hand-off round trip. Buffer reuse is ordered by the barriers already there (see the epilogue loop).
     constexpr uint32_t idesc = umma_idesc_bf16(kDcBM, C, 0, 0);
     mbar_wait_spin(w_bar, 0);
-    for (int tl = 0; tl < my_tiles; ++tl) {
+    auto gemm1 = [&](int tl) {
       const int s = tl & 1;
       mbar_wait_spin(&afull_bar[s], (tl >> 1) & 1);
       tc_fence_after();
@@ -639,18 +642,21 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         const uint64_t a_desc = umma_desc_sw128(a_base + j * p.dilation * 128, 16, 1024);
         const uint64_t b_desc = umma_desc_sw128(smem_u32(s_w7) + j * 8192, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss_warp(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (j | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_ss_warp(tmem_base + s * C, a_desc + 2 * k, b_desc + 2 * k, idesc, (j | k) != 0 ? 1u : 0u);
       }
       umma_commit_warp(&aempty_bar[s]);
-      umma_commit_warp(t1full_bar);
-      mbar_wait_spin(hfull_bar, tl & 1);
+      umma_commit_warp(&t1full_bar[s]);
+    };
+    if (my_tiles > 0) gemm1(0);
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int s = tl & 1;
+      if (tl + 1 < my_tiles) gemm1(tl + 1);
+      mbar_wait_spin(&hfull_bar[s], (tl >> 1) & 1);
       tc_fence_after();
-      {
-        const uint64_t a_desc = umma_desc_sw128(smem_u32(s_h), 16, 1024), b_desc = umma_desc_sw128(smem_u32(s_w1), 16, 1024);
+      const uint64_t a_desc = umma_desc_sw128(smem_u32(s_h) + s * kDcABytes, 16, 1024), b_desc = umma_desc_sw128(smem_u32(s_w1), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss_warp(tmem_base + C, a_desc + 2 * k, b_desc + 2 * k, idesc, k != 0 ? 1u : 0u);
-      }
-      umma_commit_warp(t2full_bar);
+      for (int k = 0; k < 4; ++k) umma_ss_warp(tmem_base + 2 * C + s * C, a_desc + 2 * k, b_desc + 2 * k, idesc, k != 0 ? 1u : 0u);
+      umma_commit_warp(&t2full_bar[s]);
     }
   } else {
     const int quad = warp & 3;
@@ -678,15 +684,17 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     float4 xr[8];
     if (my_tiles > 0) load_x(0, xr);
 
-    for (int tl = 0; tl < my_tiles; ++tl) {
-      const int tile = blockIdx.x + tl * gridDim.x;
-      const int t0 = (tile % p.tiles_per_batch) * kDcBM, b = tile / p.tiles_per_batch;
+    // Epilogue order: phase 1 of tile i+1, then phase 2 of tile i. Reuse of the double buffers needs no extra barriers:
+    //   acc1[s] (GEMM 1 of tile i+2) <- the MMA warp has waited hfull of tile i, arrived after this thread's phase-1 reads of tile i;
+    //   h[s] (phase 1 of tile i+2)   <- this thread has waited t2full of tile i (GEMM 2 of tile i has read h[s]) in phase 2 of tile i;
+    //   acc2[s] (GEMM 2 of tile i+2) <- waits hfull of tile i+2, arrived after this thread's phase 2 of tile i.
+    auto phase1 = [&](int tl) {
       // ---- phase 1
-      mbar_wait(t1full_bar, tl & 1);
+      mbar_wait(&t1full_bar[tl & 1], (tl >> 1) & 1);
       tc_fence_after();
       {
         uint32_t r[32];
-        tmem_ld_32x32(tq, r);
+        tmem_ld_32x32(tq + (tl & 1) * C, r);
         tmem_ld_wait_dep(r);
         uint32_t w[16];
 #pragma unroll
@@ -695,7 +703,7 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           w[2 * i] = pack_bf16x2(snake_act(__uint_as_float(r[4 * i]) + b4.x, a4.x, ia4.x), snake_act(__uint_as_float(r[4 * i + 1]) + b4.y, a4.y, ia4.y));
           w[2 * i + 1] = pack_bf16x2(snake_act(__uint_as_float(r[4 * i + 2]) + b4.z, a4.z, ia4.z), snake_act(__uint_as_float(r[4 * i + 3]) + b4.w, a4.w, ia4.w));
         }
-        const uint32_t h_row = smem_u32(s_h) + r_in * 128;
+        const uint32_t h_row = smem_u32(s_h) + (tl & 1) * kDcABytes + r_in * 128;
         const int c0 = col >> 3;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -704,13 +712,17 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(hfull_bar);
+      mbar_arrive(&hfull_bar[tl & 1]);
+    };
+    auto phase2 = [&](int tl) {
+      const int tile = blockIdx.x + tl * gridDim.x;
+      const int t0 = (tile % p.tiles_per_batch) * kDcBM, b = tile / p.tiles_per_batch;
       // ---- phase 2
-      mbar_wait(t2full_bar, tl & 1);
+      mbar_wait(&t2full_bar[tl & 1], (tl >> 1) & 1);
       tc_fence_after();
       {
         uint32_t r[32];
-        tmem_ld_32x32(tq + C, r);
+        tmem_ld_32x32(tq + 2 * C + (tl & 1) * C, r);
         tmem_ld_wait_dep(r);
         float v[32];
 #pragma unroll
@@ -752,13 +764,18 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         }
       }
       tc_fence_before();
+    };
+    if (my_tiles > 0) phase1(0);
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      if (tl + 1 < my_tiles) phase1(tl + 1);
+      phase2(tl);
     }
     if (lane == 0) bulk_wait_group0();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<128>(tmem_base);
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
 // First conv of the encoder: 1 -> C0 channels, k = 7, padding 3 (encoder.py:38), CUDA cores (7 MACs per output, bandwidth-bound:
