@@ -768,13 +768,13 @@ extern "C" int edm_dac_conv_first(const float* audio, int B, int L, const float*
                                   float* y, void* s_out, void* stream) {
   if (int rc = check_arch()) return rc;
   if (B <= 0 || L <= 0) return 0;
-  if (c0 <= 0 || c0 % 16 != 0 || c0 > 256) return fail(EDM_ERR_INVALID, "dac_conv_first: channels %d unsupported (%% 16, <= 256)", c0);
+  if (c0 <= 0 || c0 % 64 != 0 || c0 > 512) return fail(EDM_ERR_INVALID, "dac_conv_first: channels %d unsupported (%% 64, <= 512)", c0);
   DacConv0Params p;
   p.audio = audio; p.w = w; p.bias = bias; p.alpha = alpha; p.y = y; p.s_out = static_cast<__nv_bfloat16*>(s_out); p.B = B; p.L = L; p.C0 = c0;
-  const long long total = static_cast<long long>(B) * L * (c0 / 16);
-  const long long blocks = (total + 255) / 256;
-  const int grid = static_cast<int>(blocks < 8LL * num_sms() ? blocks : 8LL * num_sms());
-  dac_conv0_kernel<<<grid, 256, c0 * 10 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(p);
+  const long long runs = static_cast<long long>(B) * ((L + kDc0Run - 1) / kDc0Run);
+  const long long blocks = (runs + 15) / 16;
+  dim3 grid(static_cast<unsigned>(blocks < 16LL * num_sms() ? blocks : 16LL * num_sms()), c0 / 64);
+  dac_conv0_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   EDM_LAUNCH_CHECK("dac_conv_first");
   return 0;
 }

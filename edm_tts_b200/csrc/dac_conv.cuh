@@ -779,7 +779,10 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 }
 
 // First conv of the encoder: 1 -> C0 channels, k = 7, padding 3 (encoder.py:38), CUDA cores (7 MACs per output, bandwidth-bound:
-// 4 B in, 6 * C0 B out per sample). Thread <-> (time, 16 channels); writes the fp32 stream and the Snake'd bf16 operand.
+// 4 B in, 6 * C0 B out per sample). A half-warp owns 64 channels (4 per lane: 28 weights, bias and Snake constants in registers)
+// and walks a run of consecutive samples with the 7-tap window in registers, so a sample costs one broadcast load, and the two
+// output rows of a warp instruction are whole 256 B (fp32 stream) / 128 B (bf16 operand) segments. (The first version read the
+// weights from shared memory per output: 1.9 TB/s; this one is bound by the stores.)
 struct DacConv0Params {
   const float* audio;   // [B][L]
   const float* w;       // [C0][7]
@@ -789,53 +792,51 @@ struct DacConv0Params {
   __nv_bfloat16* s_out; // [B][L][C0]
   int B, L, C0;
 };
+constexpr int kDc0Run = 64;   // consecutive samples per half-warp
 
 __global__ void __launch_bounds__(256) dac_conv0_kernel(const DacConv0Params p) {
-  extern __shared__ float s_w0[];  // [C0][7] | bias | alpha | inv_alpha
-  float* s_b = s_w0 + p.C0 * 7;
-  float* s_a = s_b + p.C0;
-  float* s_ia = s_a + p.C0;
-  for (int i = threadIdx.x; i < p.C0 * 7; i += blockDim.x) s_w0[i] = __ldg(p.w + i);
-  for (int i = threadIdx.x; i < p.C0; i += blockDim.x) {
-    s_b[i] = __ldg(p.bias + i);
-    const float a = __ldg(p.alpha + i);
-    s_a[i] = a;
-    s_ia[i] = 1.0f / (a + 1e-9f);
+  const int hw = threadIdx.x >> 4, cl = threadIdx.x & 15;
+  const int c = blockIdx.y * 64 + cl * 4;               // this lane's 4 channels
+  float w[4][7], bs[4], al[4], ia[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j) w[q][j] = __ldg(p.w + (c + q) * 7 + j);
+    bs[q] = __ldg(p.bias + c + q);
+    al[q] = __ldg(p.alpha + c + q);
+    ia[q] = 1.0f / (al[q] + 1e-9f);
   }
-  __syncthreads();
-  const int groups = p.C0 / 16;
-  const long long total = static_cast<long long>(p.B) * p.L * groups;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % groups);
-    const long long bt = i / groups;
-    const int t = static_cast<int>(bt % p.L);
-    const float* a = p.audio + (bt - t);
+  const int runs_per_b = (p.L + kDc0Run - 1) / kDc0Run;
+  const long long total = static_cast<long long>(p.B) * runs_per_b;
+  for (long long run = static_cast<long long>(blockIdx.x) * 16 + hw; run < total; run += static_cast<long long>(gridDim.x) * 16) {
+    const int b = static_cast<int>(run / runs_per_b);
+    const int t0 = static_cast<int>(run % runs_per_b) * kDc0Run;
+    const float* a = p.audio + static_cast<long long>(b) * p.L;
+    const int t1 = t0 + kDc0Run < p.L ? t0 + kDc0Run : p.L;
     float x[7];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) {
-      const int tt = t + j - 3;
+    for (int j = 0; j < 6; ++j) {
+      const int tt = t0 + j - 3;
       x[j] = (tt >= 0 && tt < p.L) ? __ldg(a + tt) : 0.f;
     }
-    float v[16];
+    float* yo = p.y + (static_cast<long long>(b) * p.L + t0) * p.C0 + c;
+    __nv_bfloat16* so = p.s_out + (static_cast<long long>(b) * p.L + t0) * p.C0 + c;
+    for (int t = t0; t < t1; ++t, yo += p.C0, so += p.C0) {
+      x[6] = t + 3 < p.L ? __ldg(a + t + 3) : 0.f;
+      float v[4];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const float* w = s_w0 + (g * 16 + c) * 7;
-      float acc = s_b[g * 16 + c];
+      for (int q = 0; q < 4; ++q) {
+        float acc = bs[q];
 #pragma unroll
-      for (int j = 0; j < 7; ++j) acc = fmaf(w[j], x[j], acc);
-      v[c] = acc;
+        for (int j = 0; j < 7; ++j) acc = fmaf(w[q][j], x[j], acc);
+        v[q] = acc;
+      }
+      *reinterpret_cast<float4*>(yo) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<uint2*>(so) = make_uint2(pack_bf16x2(snake_act(v[0], al[0], ia[0]), snake_act(v[1], al[1], ia[1])),
+                                                pack_bf16x2(snake_act(v[2], al[2], ia[2]), snake_act(v[3], al[3], ia[3])));
+#pragma unroll
+      for (int j = 0; j < 6; ++j) x[j] = x[j + 1];
     }
-    float4* yo = reinterpret_cast<float4*>(p.y + bt * p.C0 + g * 16);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) yo[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-    uint32_t w2[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e)
-      w2[e] = pack_bf16x2(snake_act(v[2 * e], s_a[g * 16 + 2 * e], s_ia[g * 16 + 2 * e]),
-                          snake_act(v[2 * e + 1], s_a[g * 16 + 2 * e + 1], s_ia[g * 16 + 2 * e + 1]));
-    uint4* so = reinterpret_cast<uint4*>(p.s_out + bt * p.C0 + g * 16);
-    so[0] = make_uint4(w2[0], w2[1], w2[2], w2[3]);
-    so[1] = make_uint4(w2[4], w2[5], w2[6], w2[7]);
   }
 }
 

@@ -143,7 +143,7 @@ int edm_dac_resunit(const void* a, long long a_batch_stride, int B, int rows, in
                     long long y_batch_stride, void* s_out, long long s_batch_stride, int s_row_off, int s_rows, void* stream);
 
 /* First conv of the encoder (1 -> c0 channels, k = 7, padding 3; encoder.py:38) on CUDA cores: audio fp32 [B][L] ->
- * y fp32 [B][L][c0] and s_out bf16 = Snake_alpha(y). w fp32 [c0][7]; c0 % 16 == 0. */
+ * y fp32 [B][L][c0] and s_out bf16 = Snake_alpha(y). w fp32 [c0][7]; c0 % 64 == 0. */
 int edm_dac_conv_first(const float* audio, int B, int L, const float* w, const float* bias, const float* alpha, int c0, float* y,
                        void* s_out, void* stream);
 
