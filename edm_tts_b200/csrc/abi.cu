@@ -702,18 +702,18 @@ extern "C" int edm_dac_conv(const void* a, long long a_rows, int a_cols, long lo
 }
 
 namespace {
-template <int C>
+template <int C, bool kHalo>
 int launch_dac_resunit(const CUtensorMap& ma, const CUtensorMap& m7, const CUtensorMap& m1, const CUtensorMap& my, const CUtensorMap& ms,
                        const DacResUnitParams& p, int s_row_off, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    EDM_CUDA(cudaFuncSetAttribute(dac_resunit_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, dac_resunit_smem_bytes<C>()));
+    EDM_CUDA((cudaFuncSetAttribute(dac_resunit_kernel<C, kHalo>, cudaFuncAttributeMaxDynamicSharedMemorySize, dac_resunit_smem_bytes<C, kHalo>())));
     attr_set = true;
   }
   const long long tiles = static_cast<long long>(p.B) * p.tiles_per_batch;
   if (tiles > 0x7fffffffLL) return fail(EDM_ERR_INVALID, "dac_resunit: too many tiles");
   const int grid = tiles < num_sms() ? static_cast<int>(tiles) : num_sms();
-  dac_resunit_kernel<C><<<grid, kDcThreads, dac_resunit_smem_bytes<C>(), st>>>(ma, m7, m1, my, ms, p, s_row_off);
+  dac_resunit_kernel<C, kHalo><<<grid, kDcThreads, dac_resunit_smem_bytes<C, kHalo>(), st>>>(ma, m7, m1, my, ms, p, s_row_off);
   EDM_LAUNCH_CHECK("dac_resunit");
   return 0;
 }
@@ -760,8 +760,13 @@ extern "C" int edm_dac_resunit(const void* a, long long a_batch_stride, int B, i
     EDM_LAUNCH_CHECK("dac_resunit64");
     return 0;
   }
-  if (channels == 64) return launch_dac_resunit<64>(ma, m7, m1, my, ms, p, s_row_off, st);
-  return launch_dac_resunit<128>(ma, m7, m1, my, ms, p, s_row_off, st);
+  if (channels == 64) return launch_dac_resunit<64, false>(ma, m7, m1, my, ms, p, s_row_off, st);
+  if (halo_mode == 1 && dilation >= 1 && 128 + 6 * dilation <= kRu64HaloRows) {
+    CUtensorMap mh;
+    if (int rc = make_tmap_conv_a(&mh, a, B, rows, channels, static_cast<uint64_t>(a_batch_stride), 128 + 6 * dilation)) return rc;
+    return launch_dac_resunit<128, true>(mh, m7, m1, my, ms, p, s_row_off, st);
+  }
+  return launch_dac_resunit<128, false>(ma, m7, m1, my, ms, p, s_row_off, st);
 }
 
 extern "C" int edm_dac_conv_first(const float* audio, int B, int L, const float* w, const float* bias, const float* alpha, int c0,
