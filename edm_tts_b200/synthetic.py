@@ -150,10 +150,49 @@ def make_encoder_state_dict(encoder_dim: int = 64, rates=(2, 4, 5, 8), seed: int
     return sd
 
 
+def make_decoder_state_dict(input_channel: int = 1024, channels: int = 1536, rates=(8, 5, 4, 2), seed: int = 0, prefix: str = "") -> dict:
+    """DAC Decoder parameters keyed as edm_tts/models/dac/decoder.py builds them: model.0 first conv, model.{1..n} DecoderBlocks
+    (block.0 Snake, block.1 weight-normed ConvTranspose1d [c_in, c_out, 2s], block.{2,3,4} ResidualUnits), then Snake, last conv."""
+    sd = {}
+
+    def wn(key, shape, gain):
+        v = _randn(key + ".v", seed, *shape)
+        sd[key + ".parametrizations.weight.original1"] = v
+        sd[key + ".parametrizations.weight.original0"] = (gain * (1.0 + 0.2 * torch.rand(shape[0], 1, 1, generator=_gen(key + ".g", seed)))).float()
+
+    def snake(key, c):
+        sd[key + ".alpha"] = (0.5 + 1.5 * torch.rand(1, c, 1, generator=_gen(key + ".alpha", seed))).float()
+
+    wn(f"{prefix}model.0", (channels, input_channel, 7), 2.0)
+    sd[f"{prefix}model.0.bias"] = _randn(f"{prefix}model.0.bias", seed, channels, std=0.05)
+    n = 1
+    for i, stride in enumerate(rates):
+        c_in, c_out = channels // 2 ** i, channels // 2 ** (i + 1)
+        blk = f"{prefix}model.{n}.block."
+        snake(blk + "0", c_in)
+        wn(blk + "1", (c_in, c_out, 2 * stride), 0.5)        # weight_norm dim 0 of a transposed conv = the INPUT channels
+        sd[blk + "1.bias"] = _randn(blk + "1.bias", seed, c_out, std=0.05)
+        for u in range(3):
+            ru = f"{blk}{2 + u}.block."
+            snake(ru + "0", c_out)
+            wn(ru + "1", (c_out, c_out, 7), 0.6)
+            sd[ru + "1.bias"] = _randn(ru + "1.bias", seed, c_out, std=0.05)
+            snake(ru + "2", c_out)
+            wn(ru + "3", (c_out, c_out, 1), 0.3)
+            sd[ru + "3.bias"] = _randn(ru + "3.bias", seed, c_out, std=0.05)
+        n += 1
+    c_last = channels // 2 ** len(rates)
+    snake(f"{prefix}model.{n}", c_last)
+    wn(f"{prefix}model.{n + 1}", (1, c_last, 7), 1.0)
+    sd[f"{prefix}model.{n + 1}.bias"] = _randn(f"{prefix}model.{n + 1}.bias", seed, 1, std=0.05)
+    return sd
+
+
 def make_dac_state_dict(seed: int = 0) -> dict:
-    """Encoder + quantizer parameters keyed as DAC.state_dict() (`encoder.`, `quantizer.`) at the base config."""
+    """Encoder, quantizer and decoder parameters keyed as DAC.state_dict() (`encoder.`, `quantizer.`, `decoder.`) at the base config."""
     sd = make_encoder_state_dict(64, (2, 4, 5, 8), seed, prefix="encoder.")
     sd.update(make_quantizer_state_dict(OracleConfig(), seed, prefix="quantizer."))
+    sd.update(make_decoder_state_dict(1024, 1536, (8, 5, 4, 2), seed, prefix="decoder."))
     return sd
 
 

@@ -23,10 +23,11 @@ os.environ.setdefault("PYTHONDONTWRITEBYTECODE", "1")
 sys.dont_write_bytecode = True
 
 from oracle.weights import OracleConfig, make_inputs, make_quantizer_state_dict, make_state_dict  # noqa: E402
-from edm_tts_b200.synthetic import make_encoder_state_dict  # noqa: E402
+from edm_tts_b200.synthetic import make_decoder_state_dict, make_encoder_state_dict  # noqa: E402
 
 from edm_tts.models.dac import DAC  # noqa: E402
 from edm_tts.models.dac.configuration import DACConfig  # noqa: E402
+from edm_tts.models.dac.decoder import Decoder  # noqa: E402
 from edm_tts.models.dac.encoder import Encoder  # noqa: E402
 from edm_tts.models.dac.vector_quantizer import ResidualVectorQuantize  # noqa: E402
 from edm_tts.models.injection_conformer import modeling_injection_conformer as mic  # noqa: E402
@@ -184,6 +185,21 @@ def make_dac_encoder(name, encoder_dim, B, L, seed=0):
     print(f"dac_encoder_{name}: z {tuple(z.shape)} rms {z.pow(2).mean().sqrt().item():.3f} saved", flush=True)
 
 
+def make_dac_decoder(name, input_channel, channels, B, T, seed=0):
+    """The reference Decoder (fp32, CPU) on a synthetic latent: audio head / tail / strided samples and checksums."""
+    rates = (8, 5, 4, 2)
+    dec = Decoder(input_channel, channels, list(rates)).eval()
+    dec.load_state_dict(make_decoder_state_dict(input_channel, channels, rates, seed), strict=True)
+    z = torch.randn(B, input_channel, T, generator=torch.Generator().manual_seed(11 + T)) * 0.5
+    with torch.inference_mode():
+        audio = dec(z)
+    gold = dict(input_channel=input_channel, channels=channels, B=B, T=T, weight_seed=seed, z_seed=11 + T, audio_shape=tuple(audio.shape),
+                audio=audio.clone() if audio.numel() <= 1 << 17 else None, audio_head=audio[:, :, :256].clone(), audio_tail=audio[:, :, -256:].clone(),
+                audio_strided=audio[:, :, ::37].clone(), audio_sum=audio.double().sum().item(), audio_abs_sum=audio.double().abs().sum().item())
+    torch.save(gold, os.path.join(OUT, f"dac_decoder_{name}.pt"))
+    print(f"dac_decoder_{name}: audio {tuple(audio.shape)} rms {audio.pow(2).mean().sqrt().item():.3f} saved", flush=True)
+
+
 def make_train_forward(name, cfg_name, B, T, seed=0):
     """InjectionConformerModel.forward (eval mode: no dropout, ground-truth injections) with cosine_schedule_mask replaced by a
     fixed Bernoulli(0.6) mask: loss, arg-max codes and a few logit rows."""
@@ -221,6 +237,10 @@ if __name__ == "__main__":
         make_dac_encoder("small", 8, 2, 3200 + 137)
         make_dac_encoder("full", 64, 2, 6400 + 160)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "dac_decoder":
+        make_dac_decoder("small", 64, 96, 2, 9)
+        make_dac_decoder("full", 1024, 1536, 2, 12)
+        sys.exit(0)
     with tempfile.TemporaryDirectory():
         make_rvq("small", "small", 2, 50)
         make_rvq("full", "full", 2, 75)
@@ -234,3 +254,5 @@ if __name__ == "__main__":
         make_train_forward("full", "full", 1, 60)
         make_dac_encoder("small", 8, 2, 3200 + 137)
         make_dac_encoder("full", 64, 2, 6400 + 160)
+        make_dac_decoder("small", 64, 96, 2, 9)
+        make_dac_decoder("full", 1024, 1536, 2, 12)

@@ -116,3 +116,23 @@ def test_dac_encoder_oracle_matches_reference(golden_dir, name):
     torch.testing.assert_close(z[:, :32, :16], g["z_head"], rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(z[:, -32:, -16:], g["z_tail"], rtol=1e-5, atol=1e-5)
     assert abs(z.double().sum().item() - g["z_sum"]) < 1e-3 * max(1.0, g["z_abs_sum"] * 1e-3)
+
+
+@pytest.mark.parametrize("name", ["small", "full"])
+def test_dac_decoder_oracle_matches_reference(golden_dir, name):
+    """oracle/dac_decoder.py against the audio of the unmodified reference Decoder (fp32 CPU)."""
+    from edm_tts_b200.synthetic import make_decoder_state_dict
+    from oracle.dac_decoder import decoder_forward
+
+    g = torch.load(os.path.join(golden_dir, f"dac_decoder_{name}.pt"))
+    sd = make_decoder_state_dict(g["input_channel"], g["channels"], (8, 5, 4, 2), g["weight_seed"])
+    z = torch.randn(g["B"], g["input_channel"], g["T"], generator=torch.Generator().manual_seed(g["z_seed"])) * 0.5
+    with torch.inference_mode():
+        audio, stages = decoder_forward(sd, z, return_stages=True)
+    assert tuple(audio.shape) == tuple(g["audio_shape"])
+    print("stage rms:", [round(s.pow(2).mean().sqrt().item(), 3) for s in stages])
+    if g["audio"] is not None:
+        torch.testing.assert_close(audio, g["audio"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(audio[:, :, :256], g["audio_head"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(audio[:, :, -256:], g["audio_tail"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(audio[:, :, ::37], g["audio_strided"], rtol=1e-5, atol=1e-5)
