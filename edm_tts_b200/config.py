@@ -18,6 +18,8 @@ class DACConfig:
     codebook_size: int = 1024
     codebook_dim: int = 8
     sample_rate: int = 16000
+    decoder_dim: int = 1536
+    decoder_rates: tuple = (8, 5, 4, 2)
 
     @property
     def latent_dim(self) -> int:
@@ -33,7 +35,8 @@ class DACConfig:
         get = (lambda k, d: obj.get(k, d)) if isinstance(obj, dict) else (lambda k, d: getattr(obj, k, d))
         return cls(encoder_dim=get("encoder_dim", 64), encoder_rates=tuple(get("encoder_rates", (2, 4, 5, 8))),
                    n_codebooks=get("n_codebooks", 12), codebook_size=get("codebook_size", 1024),
-                   codebook_dim=get("codebook_dim", 8), sample_rate=get("sample_rate", 16000))
+                   codebook_dim=get("codebook_dim", 8), sample_rate=get("sample_rate", 16000), decoder_dim=get("decoder_dim", 1536),
+                   decoder_rates=tuple(get("decoder_rates", (8, 5, 4, 2))))
 
 
 @dataclass

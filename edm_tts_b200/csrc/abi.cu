@@ -666,13 +666,15 @@ int launch_dac_conv(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensor
 }  // namespace
 
 extern "C" int edm_dac_conv(const void* a, long long a_rows, int a_cols, long long a_batch_stride, int B, const void* w, int c_out,
-                            int n_taps, int tap_step, int row_off, int rows_out, const float* bias, const float* alpha,
+                            int n_taps, int tap_step, int row_off, int rows_out, const float* bias, const float* alpha, int bias_period,
                             const float* x_res, float* y, long long y_batch_stride, void* s_out, long long s_batch_stride,
                             int s_row_off, int s_rows, void* zt_out, int zt_is_f32, void* stream) {
   if (int rc = check_arch()) return rc;
   if (B <= 0 || rows_out <= 0) return 0;
-  if (a_cols <= 0 || a_cols % 64 != 0 || c_out < 64 || c_out % 64 != 0 || c_out > kDcMaxCout || n_taps <= 0 || a_rows <= 0)
-    return fail(EDM_ERR_INVALID, "dac_conv shape cin=%d cout=%d taps=%d unsupported (channels %% 64, cout <= 1024)", a_cols, c_out, n_taps);
+  const int c_mod = bias_period > 0 ? bias_period : c_out;
+  if (a_cols <= 0 || a_cols % 64 != 0 || c_out < 64 || c_out % 64 != 0 || c_mod > kDcMaxCout || c_mod % 32 != 0 || c_out % c_mod != 0 || n_taps <= 0 || a_rows <= 0)
+    return fail(EDM_ERR_INVALID, "dac_conv shape cin=%d cout=%d period=%d taps=%d unsupported (channels %% 64, period <= 1536)", a_cols, c_out, c_mod, n_taps);
+  if (zt_out != nullptr && c_mod != c_out) return fail(EDM_ERR_INVALID, "dac_conv: the transposed output needs bias_period == c_out");
   if (bias == nullptr) return fail(EDM_ERR_INVALID, "dac_conv: bias is required");
   CUtensorMap ma, mw;
   if (int rc = make_tmap_conv_a(&ma, a, B, static_cast<uint64_t>(a_rows), a_cols, static_cast<uint64_t>(a_batch_stride))) return rc;
@@ -682,7 +684,7 @@ extern "C" int edm_dac_conv(const void* a, long long a_rows, int a_cols, long lo
   DacConvParams p;
   p.B = B; p.rows_out = rows_out; p.tiles_per_batch = (rows_out + kDcBM - 1) / kDcBM; p.c_out = c_out; p.n_tiles_n = 0;
   p.n_taps = n_taps; p.tap_step = tap_step; p.row_off = row_off; p.k_chunks = a_cols / 64;
-  p.bias = bias; p.alpha = alpha; p.x_res = x_res; p.y = y; p.y_batch_stride = y_batch_stride;
+  p.c_mod = c_mod; p.bias = bias; p.alpha = alpha; p.x_res = x_res; p.y = y; p.y_batch_stride = y_batch_stride;
   p.s_out = static_cast<__nv_bfloat16*>(s_out); p.s_batch_stride = s_batch_stride; p.s_row_off = s_row_off; p.s_rows = s_rows;
   p.zt_out = zt_out; p.zt_is_f32 = zt_is_f32;
   if (x_res != nullptr && x_res != y) return fail(EDM_ERR_INVALID, "dac_conv: the residual input must be the stream that is updated (x_res == y)");
@@ -767,6 +769,22 @@ extern "C" int edm_dac_resunit(const void* a, long long a_batch_stride, int B, i
     return launch_dac_resunit<128, true>(mh, m7, m1, my, ms, p, s_row_off, st);
   }
   return launch_dac_resunit<128, false>(ma, m7, m1, my, ms, p, s_row_off, st);
+}
+
+extern "C" int edm_dac_conv_last(const void* a, long long a_batch_stride, int B, int rows, int c_pad, const float* w, float bias, float* out,
+                                 int apply_tanh, void* stream) {
+  if (int rc = check_arch()) return rc;
+  if (B <= 0 || rows <= 0) return 0;
+  if (c_pad <= 0 || c_pad % 8 != 0 || c_pad > 256) return fail(EDM_ERR_INVALID, "dac_conv_last: padded channels %d unsupported (%% 8, <= 256)", c_pad);
+  DacConvLastParams p;
+  p.a = static_cast<const __nv_bfloat16*>(a); p.a_batch_stride = a_batch_stride; p.rows = rows; p.c_pad = c_pad; p.B = B; p.w = w; p.bias = bias;
+  p.out = out; p.apply_tanh = apply_tanh;
+  const long long runs = static_cast<long long>(B) * ((rows + 31) / 32);
+  const long long blocks = (runs + 7) / 8;
+  const int grid = static_cast<int>(blocks < 16LL * num_sms() ? blocks : 16LL * num_sms());
+  dac_conv_last_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  EDM_LAUNCH_CHECK("dac_conv_last");
+  return 0;
 }
 
 extern "C" int edm_dac_conv_first(const float* audio, int B, int L, const float* w, const float* bias, const float* alpha, int c0,

@@ -37,13 +37,15 @@ template <int NT> struct DacConvStages { static constexpr int value = NT == 256 
 constexpr uint32_t kDcStagingBytes = 4096 + 2048;   // per epilogue warp: y box (32 rows x 128 B, swizzle 128B) + s box (32 rows x 64 B, swizzle 64B)
 constexpr int kDcBM = 128;
 constexpr uint32_t kDcABytes = kDcBM * 64 * 2;  // 16 KB
-constexpr int kDcMaxCout = 1024;
+constexpr int kDcMaxCout = 1536;   // capacity of the per-channel constant staging (bias / Snake alpha period)
 
 struct DacConvParams {
   int B, rows_out, tiles_per_batch, c_out, n_tiles_n;
   int n_taps, tap_step, row_off, k_chunks;  // k_chunks = Cin / 64
-  const float* bias;                        // [c_out]
-  const float* alpha;                       // [c_out] Snake of the NEXT layer, applied to what goes to s_out; nullptr: identity
+  int c_mod;                                // period of bias / alpha along the output columns (c_out, or C for a transposed conv
+                                            // whose columns are s phases x C channels)
+  const float* bias;                        // [c_mod]
+  const float* alpha;                       // [c_mod] Snake of the NEXT layer, applied to what goes to s_out; nullptr: identity
   const float* x_res;                       // fp32 [B][rows_out][c_out] residual input or nullptr (may alias y)
   float* y;                                 // fp32 stream out or nullptr
   long long y_batch_stride;                 // elements
@@ -105,7 +107,7 @@ dac_conv_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
-  for (int i = threadIdx.x; i < p.c_out; i += kDcThreads) {
+  for (int i = threadIdx.x; i < p.c_mod; i += kDcThreads) {
     s_bias[i] = __ldg(p.bias + i);
     const float a = p.alpha != nullptr ? __ldg(p.alpha + i) : 1.0f;
     s_alpha[i] = a;
@@ -212,10 +214,11 @@ dac_conv_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           mbar_arrive(&tempty_bar[buf]);
         }
         const int col = n0 + half * kColsPerWarp + cc * 32;
+        const int ccol = col % p.c_mod;      // channel of the chunk's first column (chunks never straddle a period: c_mod % 32 == 0)
         float v[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 b4 = lds128(smem_u32(s_bias + col) + 16 * i);
+          const float4 b4 = lds128(smem_u32(s_bias + ccol) + 16 * i);
           v[4 * i] = __uint_as_float(r[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
           v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
         }
@@ -255,7 +258,7 @@ dac_conv_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           if (has_alpha) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 a4 = lds128(smem_u32(s_alpha + col) + 16 * i), ia4 = lds128(smem_u32(s_inva + col) + 16 * i);
+              const float4 a4 = lds128(smem_u32(s_alpha + ccol) + 16 * i), ia4 = lds128(smem_u32(s_inva + ccol) + 16 * i);
               w[2 * i] = pack_bf16x2(snake_act(v[4 * i], a4.x, ia4.x), snake_act(v[4 * i + 1], a4.y, ia4.y));
               w[2 * i + 1] = pack_bf16x2(snake_act(v[4 * i + 2], a4.z, ia4.z), snake_act(v[4 * i + 3], a4.w, ia4.w));
             }
@@ -858,6 +861,73 @@ __global__ void __launch_bounds__(256) dac_conv0_kernel(const DacConv0Params p) 
                                                 pack_bf16x2(snake_act(v[2], al[2], ia[2]), snake_act(v[3], al[3], ia[3])));
 #pragma unroll
       for (int j = 0; j < 6; ++j) x[j] = x[j + 1];
+    }
+  }
+}
+
+// Last conv of the decoder: C channels -> 1, k = 7, padding 3, then tanh (decoder.py:55-59), on CUDA cores. The input is the bf16
+// operand Snake(x) [B][rows][c_pad] (channel-last, zero-padded channels carry zero weights). A warp produces 32 consecutive
+// samples: lane <-> 8 channels (one 16 B load per row), each of the 38 rows of the window is read once and its 7 tap products go to
+// the 7 outputs it touches, reduced over the lanes by shuffles at the end.
+struct DacConvLastParams {
+  const __nv_bfloat16* a; long long a_batch_stride; int rows, c_pad, B;
+  const float* w;   // [7][c_pad] fp32 (zero for padded channels)
+  float bias;
+  float* out;       // [B][rows]
+  int apply_tanh;
+};
+
+__global__ void __launch_bounds__(256) dac_conv_last_kernel(const DacConvLastParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lanes_used = p.c_pad / 8;                       // <= 32
+  float w[7][8];
+#pragma unroll
+  for (int j = 0; j < 7; ++j)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[j][e] = lane < lanes_used ? __ldg(p.w + j * p.c_pad + lane * 8 + e) : 0.f;
+  const int runs_per_b = (p.rows + 31) / 32;
+  const long long total = static_cast<long long>(p.B) * runs_per_b;
+  for (long long run = static_cast<long long>(blockIdx.x) * 8 + warp; run < total; run += static_cast<long long>(gridDim.x) * 8) {
+    const int b = static_cast<int>(run / runs_per_b);
+    const int t0 = static_cast<int>(run % runs_per_b) * 32;
+    const __nv_bfloat16* a = p.a + static_cast<long long>(b) * p.a_batch_stride + lane * 8;
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 38; ++r) {                          // input row t0 - 3 + r contributes to outputs t0 + r - j, j = 0..6 ... (tap index = r - i)
+      const int t = t0 - 3 + r;
+      float x[8];
+      if (t >= 0 && t < p.rows && lane < lanes_used) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(a + static_cast<long long>(t) * p.c_pad));
+        x[0] = bf16lo(q.x); x[1] = bf16hi(q.x); x[2] = bf16lo(q.y); x[3] = bf16hi(q.y);
+        x[4] = bf16lo(q.z); x[5] = bf16hi(q.z); x[6] = bf16lo(q.w); x[7] = bf16hi(q.w);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int i = r - j;                                // output index inside the run: out[t0 + i] += w[j] . x[t0 + i + j - 3]
+        if (i >= 0 && i < 32) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[i] = fmaf(w[j][e], x[e], acc[i]);
+        }
+      }
+    }
+    // reduce over lanes: after the butterfly lane l keeps output l
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mine = lane == i ? acc[i] : mine;
+    const int t = t0 + lane;
+    if (t < p.rows) {
+      const float v = mine + p.bias;
+      p.out[static_cast<long long>(b) * p.rows + t] = p.apply_tanh ? tanhf(v) : v;
     }
   }
 }

@@ -1,14 +1,16 @@
-"""The encode side of the reference's DAC module on the CUDA path: conv encoder + residual vector quantizer.
+"""The reference's DAC module on the CUDA path: conv encoder, residual vector quantizer, conv decoder.
 
-Mirrors edm_tts/models/dac/modeling_dac.py: DAC.encode (:111-139, without the resampling of preprocess), encode_to_codes (:163-167),
-codes_to_features / codes_to_features_unreduced (:173-182). State-dict keys are the reference's (`encoder.block...`,
-`quantizer.quantizers...`). The conv decoder (decode / decode_from_codes) is not part of this path and raises.
+Mirrors edm_tts/models/dac/modeling_dac.py: DAC.encode (:111-139, without the resampling of preprocess), decode (:141-161),
+encode_to_codes (:163-167), decode_from_codes (:169-171), codes_to_features / codes_to_features_unreduced (:173-182). State-dict keys
+are the reference's (`encoder.block...`, `quantizer.quantizers...`, `decoder.model...`); the decoder is built only when its weights
+are present.
 """
 from __future__ import annotations
 
 import torch
 
 from .config import DACConfig
+from .dac_decoder import DACDecoder
 from .dac_encoder import DACEncoder
 from .dac_rvq import ResidualVectorQuantize
 
@@ -24,6 +26,9 @@ class DAC:
         self.hop_length = self.encoder.hop_length
         self.quantizer = ResidualVectorQuantize(state_dict, n_codebooks=cfg.n_codebooks, codebook_size=cfg.codebook_size,
                                                 codebook_dim=cfg.codebook_dim, input_dim=self.latent_dim, prefix="quantizer.", device=device)
+        self.decoder = None
+        if any(k.startswith("decoder.") for k in state_dict):
+            self.decoder = DACDecoder(state_dict, self.latent_dim, cfg.decoder_dim, cfg.decoder_rates, prefix="decoder.", device=device)
 
     def eval(self):
         return self
@@ -53,7 +58,14 @@ class DAC:
     def codes_to_features_unreduced(self, codes):
         return self.quantizer.from_codes_unreduced(codes)
 
-    def decode(self, *a, **k):
-        raise NotImplementedError("the DAC conv decoder is outside the accelerated path (SURVEY.md section 8f, rank 2)")
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor, length=None) -> dict:
+        """z [B, D, T] -> {"audio": [B, 1, length]} (modeling_dac.py:141-161)."""
+        if self.decoder is None:
+            raise RuntimeError("this DAC was built without decoder weights")
+        x = self.decoder(z)
+        return {"audio": x[..., :length]}
 
-    decode_from_codes = decode
+    def decode_from_codes(self, codes: torch.Tensor, length=None) -> torch.Tensor:
+        """codes [B, n, T] -> audio [B, 1, L] (modeling_dac.py:169-171; the step after the S2A decode in inference.py:49)."""
+        return self.decode(self.quantizer.from_codes(codes)[0], length)["audio"]

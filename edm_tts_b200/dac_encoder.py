@@ -105,7 +105,7 @@ class DACEncoder:
               s_row_off=0, s_rows=0, zt=None):
         c_out = w.shape[0]
         L.check(L.lib().edm_dac_conv(L.ptr(a), a_rows, a_cols, a.stride(0), B, L.ptr(w), c_out, taps, step, off, rows_out, L.ptr(bias),
-                                     L.ptr(alpha), L.ptr(x_res), L.ptr(y), y.stride(0) if y is not None else 0, L.ptr(s_out),
+                                     L.ptr(alpha), 0, L.ptr(x_res), L.ptr(y), y.stride(0) if y is not None else 0, L.ptr(s_out),
                                      s_out.stride(0) if s_out is not None else 0, s_row_off, s_rows, L.ptr(zt),
                                      int(zt is not None and zt.dtype == torch.float32), L.stream_ptr()), "dac_conv")
 

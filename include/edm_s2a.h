@@ -128,9 +128,12 @@ int edm_kmeans_assign(const float* x, long long n_frames, int dim, const float* 
  *   y        nullable fp32 stream out, batch stride y_batch_stride
  *   s_out    nullable bf16 operand out = Snake_alpha(out) (alpha nullable = identity), row t + s_row_off, rows >= s_rows dropped
  *   zt_out   nullable [B][c_out][rows_out] (fp32 if zt_is_f32 else bf16): the latent z in the reference's [B, D, T] layout
- * a_cols % 64 == 0, c_out % 64 == 0 and <= 1024. */
+ * bias_period: 0, or the period C of bias / alpha along the output columns when the columns are s phases x C channels -- a
+ * ConvTranspose1d(kernel 2s, stride s) of the decoder (decoder.py:15-23) is the 2-tap conv out_view[q, r * C + co] =
+ * sum_u a[q - u] . w[:, co, r + u s] whose output view [L_in + 1][s * C] is the channel-last output shifted by `padding` rows.
+ * a_cols % 64 == 0, c_out % 64 == 0, period % 32 == 0 and <= 1536. */
 int edm_dac_conv(const void* a, long long a_rows, int a_cols, long long a_batch_stride, int B, const void* w, int c_out,
-                 int n_taps, int tap_step, int row_off, int rows_out, const float* bias, const float* alpha, const float* x_res,
+                 int n_taps, int tap_step, int row_off, int rows_out, const float* bias, const float* alpha, int bias_period, const float* x_res,
                  float* y, long long y_batch_stride, void* s_out, long long s_batch_stride, int s_row_off, int s_rows,
                  void* zt_out, int zt_is_f32, void* stream);
 
@@ -141,6 +144,11 @@ int edm_dac_conv(const void* a, long long a_rows, int a_cols, long long a_batch_
 int edm_dac_resunit(const void* a, long long a_batch_stride, int B, int rows, int channels, int dilation, const void* w7,
                     const void* w1, const float* b7, const float* a_mid, const float* b1, const float* a_next, float* y,
                     long long y_batch_stride, void* s_out, long long s_batch_stride, int s_row_off, int s_rows, void* stream);
+
+/* Last conv of the decoder (C -> 1 channel, k = 7, padding 3) + tanh (decoder.py:55-59): a bf16 [B][rows][c_pad] = Snake(x) with
+ * zero-padded channels, w fp32 [7][c_pad], out fp32 [B][rows]. */
+int edm_dac_conv_last(const void* a, long long a_batch_stride, int B, int rows, int c_pad, const float* w, float bias, float* out,
+                      int apply_tanh, void* stream);
 
 /* First conv of the encoder (1 -> c0 channels, k = 7, padding 3; encoder.py:38) on CUDA cores: audio fp32 [B][L] ->
  * y fp32 [B][L][c0] and s_out bf16 = Snake_alpha(y). w fp32 [c0][7]; c0 % 64 == 0. */

@@ -104,8 +104,8 @@ def test_dac_encode_to_codes_vs_oracle():
     assert torch.equal(codes[clean], own["codes"][clean]) and mism[:, 0].float().mean().item() < 1e-2
     out = dac.encode(audio)
     assert set(out) >= {"z", "codes", "latents", "length"} and out["z"].shape == (2, 1024, 100)
-    with pytest.raises(NotImplementedError):
-        dac.decode_from_codes(codes)
+    audio_hat = dac.decode_from_codes(codes, length=32000)
+    assert audio_hat.shape == (2, 1, 32000) and torch.isfinite(audio_hat).all()
 
 
 def test_encoder_full_size_config4_properties():
