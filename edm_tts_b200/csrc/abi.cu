@@ -678,7 +678,7 @@ extern "C" int edm_dac_conv(const void* a, long long a_rows, int a_cols, long lo
   if (bias == nullptr) return fail(EDM_ERR_INVALID, "dac_conv: bias is required");
   CUtensorMap ma, mw;
   if (int rc = make_tmap_conv_a(&ma, a, B, static_cast<uint64_t>(a_rows), a_cols, static_cast<uint64_t>(a_batch_stride))) return rc;
-  const int nt = c_out % 256 == 0 ? 256 : (c_out % 128 == 0 ? 128 : 64);
+  const int nt = c_out % 256 == 0 ? 256 : (c_out % 192 == 0 ? 192 : (c_out % 128 == 0 ? 128 : 64));
   const uint64_t k_total = static_cast<uint64_t>(n_taps) * a_cols;
   if (int rc = make_tmap_2d(&mw, w, c_out, k_total, k_total, nt)) return rc;
   DacConvParams p;
@@ -699,6 +699,7 @@ extern "C" int edm_dac_conv(const void* a, long long a_rows, int a_cols, long lo
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (nt == 256) return launch_dac_conv<256>(ma, mw, my, ms, p, st);
+  if (nt == 192) return launch_dac_conv<192>(ma, mw, my, ms, p, st);
   if (nt == 128) return launch_dac_conv<128>(ma, mw, my, ms, p, st);
   return launch_dac_conv<64>(ma, mw, my, ms, p, st);
 }

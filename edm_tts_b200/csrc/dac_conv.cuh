@@ -20,7 +20,7 @@
 // (operand of the next conv, possibly in the padded layout of a strided conv); zt_out = v transposed to [batch][channel][time]
 // (the latent z handed to the RVQ, reference layout).
 //
-//   warp 0     : TMA producer (A box 128 rows x 64 channels, W box NT rows x 64), 4-stage ring
+//   warp 0     : TMA producer (A box 128 rows x 64 channels, W box NT rows x 64, NT in {64, 128, 192, 256}), 3-4 stage ring
 //   warp 1     : MMA issuer (whole warp, elected lane), accumulator double-buffered in TMEM (2 x NT columns)
 //   warps 2-9  : epilogue, two warps per TMEM lane quadrant, each owning half of the tile's columns. A thread owns a time row, so
 //                direct global accesses would touch 32 different lines per warp instruction; instead every warp has a staging
@@ -33,7 +33,7 @@
 namespace edm {
 
 constexpr int kDcThreads = 320;
-template <int NT> struct DacConvStages { static constexpr int value = NT == 256 ? 3 : 4; };
+template <int NT> struct DacConvStages { static constexpr int value = NT >= 192 ? 3 : 4; };
 constexpr uint32_t kDcStagingBytes = 4096 + 2048;   // per epilogue warp: y box (32 rows x 128 B, swizzle 128B) + s box (32 rows x 64 B, swizzle 64B)
 constexpr int kDcBM = 128;
 constexpr uint32_t kDcABytes = kDcBM * 64 * 2;  // 16 KB
@@ -73,7 +73,7 @@ dac_conv_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   constexpr int kDcStages = DacConvStages<NT>::value;
   constexpr uint32_t kBBytes = NT * 128;
   constexpr uint32_t kStageBytes = kDcABytes + kBBytes;
-  constexpr int kTmemCols = 2 * NT < 32 ? 32 : 2 * NT;
+  constexpr int kTmemCols = 2 * NT <= 128 ? 128 : (2 * NT <= 256 ? 256 : 512);   // power of two >= 2 * NT
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* staging = smem + kDcStages * kStageBytes;

@@ -582,8 +582,76 @@ def test_dacenc():
     print(f"torch bf16-autocast encoder B={Bt}: {ms_t:.2f} ms = {Bt * z.shape[-1] / ms_t / 1e3:.3f} Mframes/s ({ms_t / Bt * B / ms:.1f}x ours per utterance); rel L2 ours vs torch-bf16 {rel:.2e}", flush=True)
 
 
+def test_dacdec():
+    """DAC conv decoder at the S2A bench shape (utterances of 500 frames = 10 s): whole-decoder time, per-launch times and the same
+    stack in plain torch (bf16 autocast) as the GPU incumbent."""
+    import torch.nn.functional as F
+    from edm_tts_b200.dac_decoder import DACDecoder
+    from edm_tts_b200.dac_encoder import _fold
+    from edm_tts_b200.synthetic import make_decoder_state_dict
+    B, T = int(os.environ.get("DAC_B", "16")), int(os.environ.get("DAC_T", "500"))
+    sd = make_decoder_state_dict(1024, 1536, (8, 5, 4, 2), 0)
+    dec = DACDecoder(sd, max_chunk_samples=1 << 30)
+    z = torch.randn(B, 1024, T, device=dev) * 0.5
+    audio = dec(z)
+    torch.cuda.synchronize()
+    ms = timeit(lambda: dec(z), iters=3, warm=1)
+    Ls = audio.shape[-1]
+    flop = 2.0 * 1.74e6 * B * Ls
+    print(f"dac decoder B={B} T={T} (L={Ls}): {ms:.2f} ms = {B * T / ms / 1e3:.3f} Mframes/s, {flop / ms / 1e9:.0f} TFLOP/s algorithmic", flush=True)
+    times = []
+    oc, oru = dec._conv, dec._resunit
+
+    def tc(a_ptr, a_rows, a_cols, a_bs, w, bias, taps, step, off, rows_out, Bc, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); oc(a_ptr, a_rows, a_cols, a_bs, w, bias, taps, step, off, rows_out, Bc, **kw); e1.record()
+        times.append((f"cin={a_cols} cout={w.shape[0]} taps={taps} step={step} rows={rows_out}", 2.0 * Bc * rows_out * w.shape[0] * w.shape[1], e0, e1))
+
+    def tr(a_ptr, a_bs, Bc, rows, c, dilation, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); oru(a_ptr, a_bs, Bc, rows, c, dilation, *a); e1.record()
+        times.append((f"fused unit c={c} dilation={dilation} rows={rows}", 2.0 * Bc * rows * c * c * 8, e0, e1))
+    dec._conv, dec._resunit = tc, tr
+    dec(z)
+    torch.cuda.synchronize()
+    dec._conv, dec._resunit = oc, oru
+    tot = 0.0
+    for name, fl, e0, e1 in times:
+        t = e0.elapsed_time(e1)
+        tot += t
+        print(f"  {name:58s} {t:8.3f} ms  {fl / t / 1e9:7.0f} TFLOP/s", flush=True)
+    print(f"  sum of convs {tot:.2f} ms", flush=True)
+
+    W = {k[: -len(".bias")]: (_fold(sd, k[: -len(".bias")]).to(dev), sd[k].to(dev)) for k in sd if k.endswith(".bias")}
+
+    def snake(x, key):
+        a = sd[key + ".alpha"].to(dev)
+        return x + (a + 1e-9).reciprocal() * torch.sin(a * x).pow(2)
+
+    def torch_dec(x):
+        x = F.conv1d(x, *W["model.0"], padding=3)
+        n = 1
+        for s in (8, 5, 4, 2):
+            blk = f"model.{n}.block."
+            x = F.conv_transpose1d(snake(x, blk + "0"), *W[blk + "1"], stride=s, padding=s // 2, output_padding=s % 2)
+            for u, d in enumerate((1, 3, 9)):
+                ru = f"{blk}{2 + u}.block."
+                h = F.conv1d(snake(x, ru + "0"), *W[ru + "1"], dilation=d, padding=3 * d)
+                h = F.conv1d(snake(h, ru + "2"), *W[ru + "3"])
+                x = x + h
+            n += 1
+        return torch.tanh(F.conv1d(snake(x, f"model.{n}"), *W[f"model.{n + 1}"], padding=3))
+    Bt = min(B, 8)
+    with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+        at = torch_dec(z[:Bt])
+        torch.cuda.synchronize()
+        ms_t = timeit(lambda: torch_dec(z[:Bt]), iters=2, warm=1)
+    rel = ((audio[:Bt].float() - at.float()).pow(2).sum().sqrt() / at.float().pow(2).sum().sqrt()).item()
+    print(f"torch bf16-autocast decoder B={Bt}: {ms_t:.2f} ms ({ms_t / Bt * B / ms:.1f}x ours per utterance); rel L2 ours vs torch-bf16 {rel:.2e}", flush=True)
+
+
 if __name__ == "__main__":
     t0 = time.time()
-    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvq": test_rvq, "rvqtc": test_rvqtc, "rvqtime": test_rvqtime, "gemmsus": test_gemmsus, "kmeans": test_kmeans, "dacenc": test_dacenc}[sys.argv[1]]()
+    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvq": test_rvq, "rvqtc": test_rvqtc, "rvqtime": test_rvqtime, "gemmsus": test_gemmsus, "kmeans": test_kmeans, "dacenc": test_dacenc, "dacdec": test_dacdec}[sys.argv[1]]()
     torch.cuda.synchronize()
     print(f"[{sys.argv[1]}] done in {time.time() - t0:.1f}s", flush=True)
