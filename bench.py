@@ -298,7 +298,19 @@ def main():
     r1.record()
     torch.cuda.synchronize()
     enc_ms = r0.elapsed_time(r1) / 3
-    del audio, dac
+    # and the step after the S2A decode (inference.py:49): codes of the bench batch -> waveform through the DAC conv decoder
+    dcodes = torch.randint(0, 1024, (B, 12, T), device=dev)
+    dac.decode_from_codes(dcodes)
+    torch.cuda.synchronize()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(3):
+        wav = dac.decode_from_codes(dcodes)
+    r1.record()
+    torch.cuda.synchronize()
+    dec_ms = r0.elapsed_time(r1) / 3
+    dec_samples = wav.shape[-1]
+    del audio, dac, wav, dcodes
     torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
@@ -335,6 +347,11 @@ def main():
                              "frac_of_tensor_peak": 2 * 767.0e3 * 32 * 960160 / (enc_ms * 1e-3) / 1e12 / tf_peak,
                              "note": "conv encoder = 29 implicit-GEMM launches per chunk of 8 utterances (csrc/dac_conv.cuh, bf16 operands, fp32 stream) + the RVQ kernels above; "
                                      "767 kMAC per audio sample; the 64/128-channel stages are HBM / L2 bound, the 256..1024-channel stages run at 1.1-1.3 PFLOP/s"},
+        "secondary_decode": {"metric": "dac_decode_from_codes_frames_per_s", "value": B * T / (dec_ms * 1e-3), "unit": "frames/s", "ms": dec_ms,
+                             "workload": f"DAC.decode_from_codes, codes [{B}, 12, {T}] (the S2A bench batch) -> audio [{B}, 1, {dec_samples}] fp32, per GPU",
+                             "algorithmic_tflops": 2 * 1.74e6 * B * dec_samples / (dec_ms * 1e-3) / 1e12,
+                             "frac_of_tensor_peak": 2 * 1.74e6 * B * dec_samples / (dec_ms * 1e-3) / 1e12 / tf_peak,
+                             "note": "conv decoder on the encoder's implicit-GEMM kernels (transposed convs as 2-tap convs into a shifted output view); 1.74 MMAC per output sample"},
         "model_flops_utilisation": {"algorithmic_tflops": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12,
                                     "frac_of_peak": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12 / tf_peak},
     }
