@@ -26,6 +26,22 @@ def _pad64(c):
     return (c + 63) // 64 * 64
 
 
+def pack_conv_transpose(wt: torch.Tensor, stride: int, c_out_pad: int) -> torch.Tensor:
+    """ConvTranspose1d weight [c_in, c_out, 2 * stride] (weight-norm folded) -> [stride * c_out_pad, 2 * c_in] fp32 for the 2-tap conv
+    of the module docstring: row = phase r * c_out_pad + co, K = tap j * c_in + ci, tap 0 reads x[q - 1] (u = 1), tap 1 reads x[q]."""
+    c_in, c_out, k = wt.shape
+    assert k == 2 * stride
+    wp = torch.zeros(stride, c_out_pad, 2, c_in, dtype=torch.float32)
+    for j in range(2):
+        wp[:, :c_out, j, :] = wt[:, :, (1 - j) * stride:(2 - j) * stride].permute(2, 1, 0)
+    return wp.reshape(stride * c_out_pad, 2 * c_in)
+
+
+def conv_transpose_length(L_in: int, stride: int) -> int:
+    """Output length of ConvTranspose1d(kernel 2s, stride s, padding floor(s/2), output_padding s % 2) (decoder.py:15-23)."""
+    return (L_in - 1) * stride - 2 * (stride // 2) + 2 * stride + stride % 2
+
+
 class DACDecoder:
     def __init__(self, state_dict: dict, input_channel: int = 1024, channels: int = 1536, rates=(8, 5, 4, 2), prefix: str = "",
                  device="cuda", max_chunk_samples: int = 1 << 21):
@@ -62,17 +78,14 @@ class DACDecoder:
             cp = _pad64(c_out)
             blk = f"{prefix}model.{n}.block."
             wt = _fold(sd, blk + "1")                                            # [c_in, c_out, 2s], normalised per input channel
-            # rows (phase r, output channel), K = (tap j, input channel); tap j = 0 reads x[q - 1] (u = 1), j = 1 reads x[q] (u = 0)
-            wp = torch.zeros(s, cp, 2, c_in)
-            for j in range(2):
-                wp[:, :c_out, j, :] = wt[:, :, (1 - j) * s:(2 - j) * s].permute(2, 1, 0)
+            wp = pack_conv_transpose(wt, s, cp)
             units = []
             for u in range(3):
                 ru = f"{blk}{2 + u}.block."
                 w7, b7 = conv(ru + "1", cp, cp)
                 w1, b1 = conv(ru + "3", cp, cp)
                 units.append(dict(a_in=alpha(ru + "0", cp), w7=w7, b7=b7, a_mid=alpha(ru + "2", cp), w1=w1, b1=b1))
-            self.blocks.append(dict(stride=s, c_in=c_in, c=cp, a_up=alpha(blk + "0", c_in), wt=wp.reshape(s * cp, 2 * c_in).to(dev, torch.bfloat16).contiguous(),
+            self.blocks.append(dict(stride=s, c_in=c_in, c=cp, a_up=alpha(blk + "0", c_in), wt=wp.to(dev, torch.bfloat16).contiguous(),
                                     bt=padded(sd[blk + "1.bias"], cp), units=units))
             c_in = cp
             n += 1
@@ -93,7 +106,7 @@ class DACDecoder:
         """Time lengths after the first conv and after each transposed conv: (L - 1) s - 2 floor(s/2) + 2 s + s % 2."""
         out = [T]
         for s in self.rates:
-            out.append((out[-1] - 1) * s - 2 * (s // 2) + 2 * s + s % 2)
+            out.append(conv_transpose_length(out[-1], s))
         return out
 
     def _workspace(self, B: int, T: int):

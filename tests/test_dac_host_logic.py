@@ -1,0 +1,60 @@
+"""Host-side algebra of the DAC conv paths, checked on CPU against torch's own convs (no kernels involved):
+the transposed conv as a 2-tap conv into a shifted output view (edm_tts_b200/dac_decoder.py), and the strided conv as a 2-tap conv
+over the padded operand viewed as [time / s][s * C] (edm_tts_b200/dac_encoder.py)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+
+@pytest.mark.parametrize("stride", [8, 5, 4, 2])
+def test_conv_transpose_as_two_tap_conv(stride):
+    from edm_tts_b200.dac_decoder import conv_transpose_length, pack_conv_transpose
+
+    g = torch.Generator().manual_seed(stride)
+    c_in, c_out, cp, L_in, B = 12, 5, 8, 9, 2
+    wt = torch.randn(c_in, c_out, 2 * stride, generator=g)
+    bias = torch.randn(c_out, generator=g)
+    x = torch.randn(B, c_in, L_in, generator=g)
+    pad = stride // 2
+    ref = F.conv_transpose1d(x, wt, bias, stride=stride, padding=pad, output_padding=stride % 2)
+    L_out = conv_transpose_length(L_in, stride)
+    assert ref.shape[-1] == L_out
+    wp = pack_conv_transpose(wt, stride, cp)                                    # [stride * cp, 2 * c_in]
+    xl = x.transpose(1, 2)                                                      # channel-last [B, L_in, c_in]
+    xz = F.pad(xl, (0, 0, 1, 1))                                                # rows -1 and L_in read as zero
+    a = torch.cat([xz[:, :-1], xz[:, 1:]], dim=-1)                              # view row q: [x[q - 1] | x[q]], q = 0 .. L_in
+    view = a @ wp.t()                                                           # [B, L_in + 1, stride * cp]
+    flat = view.reshape(B, (L_in + 1) * stride, cp)                             # row q * stride + r  <->  output time q * stride + r - pad
+    out = flat[:, pad:pad + L_out, :c_out] + bias
+    torch.testing.assert_close(out.transpose(1, 2), ref, rtol=1e-5, atol=1e-5)
+    assert flat[:, :, c_out:].abs().max() == 0                                  # padded channels stay zero
+
+
+@pytest.mark.parametrize("stride", [2, 4, 5, 8])
+def test_strided_conv_as_two_tap_conv(stride):
+    g = torch.Generator().manual_seed(10 + stride)
+    c, c_out, L_in, B = 6, 7, 53, 2
+    w = torch.randn(c_out, c, 2 * stride, generator=g)
+    x = torch.randn(B, c, L_in, generator=g)
+    pad = math.ceil(stride / 2)
+    ref = F.conv1d(x, w, stride=stride, padding=pad)
+    L_out = (L_in + 2 * pad - 2 * stride) // stride + 1
+    assert ref.shape[-1] == L_out
+    buf = torch.zeros(B, (L_out + 1) * stride, c)                               # `pad` zero rows in front, never-written tail stays zero
+    n = min(L_in, (L_out + 1) * stride - pad)
+    buf[:, pad:pad + n] = x.transpose(1, 2)[:, :n]
+    view = buf.view(B, L_out + 1, stride * c)
+    wp = w.permute(0, 2, 1).reshape(c_out, 2 * stride * c)                      # K index = tap * c + channel (DACEncoder packing)
+    a = torch.cat([view[:, :-1], view[:, 1:]], dim=-1)                          # output t reads view rows t and t + 1
+    torch.testing.assert_close((a @ wp.t()).transpose(1, 2), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_lengths_match_torch():
+    from edm_tts_b200.dac_decoder import conv_transpose_length
+
+    for s in (8, 5, 4, 2):
+        for L_in in (1, 2, 17):
+            assert conv_transpose_length(L_in, s) == F.conv_transpose1d(torch.zeros(1, 1, L_in), torch.zeros(1, 1, 2 * s), stride=s, padding=s // 2,
+                                                                         output_padding=s % 2).shape[-1]
