@@ -314,14 +314,16 @@ constexpr uint32_t kRu64HaloBytes = kRu64HaloRows * 128;           // 24 KB per 
 // traffic of a 128-channel tile from 480 KB to 300 KB.
 template <int C, bool kHalo>
 constexpr uint32_t dac_resunit_smem_bytes() {
-  return 4 * ((kHalo ? 0 : kDcABytes) + C * 128) + (kHalo ? (C / 64) * kRu64HaloBytes : 0) + 128 * C * 2 + 8 * kDcStagingBytes + 6 * C * 4 + 1024 + 256;
+  return (kHalo ? 5 : 4) * ((kHalo ? 0 : kDcABytes) + C * 128) + (kHalo ? (C / 64) * kRu64HaloBytes : 0) + 128 * C * 2 + 8 * kDcStagingBytes + 6 * C * 4 + 1024 + 256;
 }
 
 template <int C, bool kHalo>
 __global__ void __launch_bounds__(kDcThreads, 1)
 dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w7, const __grid_constant__ CUtensorMap tma_w1,
                    const __grid_constant__ CUtensorMap tma_y, const __grid_constant__ CUtensorMap tma_s, const DacResUnitParams p, const int s_row_off) {
-  constexpr int kStages = 4;
+  // the mainloop is bound by TMA latency x bytes in flight, not by the tensor pipe: with the halo tile out of the ring the same
+  // shared memory holds five 16 KB weight stages (80 KB in flight) instead of four 32 KB (A + W) stages carrying 64 KB of weights
+  constexpr int kStages = kHalo ? 5 : 4;
   constexpr int kKc = C / 64;                       // 64-channel chunks
   constexpr uint32_t kBBytes = C * 128;
   constexpr uint32_t kAOff = kHalo ? 0 : kDcABytes;     // offset of the weight chunk inside a ring stage
