@@ -56,6 +56,25 @@ def main():
         ms = timed(lambda: rvq.encode(z), 10)
         out.append({"config": "C4_rvq", "B": B, "T": T, "ms": ms, "frames_per_s": B * T / (ms * 1e-3)})
         print(json.dumps(out[-1]), flush=True)
+    del rvq, model
+    torch.cuda.empty_cache()
+    # the callers either side of the S2A decode: audio -> codes (dump_tokens) and codes -> audio (inference.py:49)
+    from edm_tts_b200.dac import DAC
+    from edm_tts_b200.synthetic import make_dac_state_dict
+    dac = DAC(make_dac_state_dict(0))
+    for B, secs in [(32, 60), (8, 60), (1, 10)]:
+        n = 960160 if secs == 60 else 160000
+        audio = (torch.randn(B, 1, n, device="cuda") * 0.3).clamp_(-1, 1)
+        ms = timed(lambda: dac.encode_to_codes(audio), 3, warm=1)
+        T = dac.encoder.lengths(n)[-1]
+        out.append({"config": "C4_encode_to_codes", "B": B, "samples": n, "T": T, "ms": ms, "frames_per_s": B * T / (ms * 1e-3)})
+        print(json.dumps(out[-1]), flush=True)
+        del audio
+    for B, T in [(64, 500), (8, 1500), (1, 150)]:
+        codes = torch.randint(0, 1024, (B, 12, T), device="cuda")
+        ms = timed(lambda: dac.decode_from_codes(codes), 3, warm=1)
+        out.append({"config": "decode_from_codes", "B": B, "T": T, "ms": ms, "frames_per_s": B * T / (ms * 1e-3)})
+        print(json.dumps(out[-1]), flush=True)
 
 
 if __name__ == "__main__":
