@@ -705,23 +705,27 @@ extern "C" int edm_dac_conv(const void* a, long long a_rows, int a_cols, long lo
 }
 
 namespace {
-template <int C, bool kHalo>
+template <int C>
 int launch_dac_resunit(const CUtensorMap& ma, const CUtensorMap& m7, const CUtensorMap& m1, const CUtensorMap& my, const CUtensorMap& ms,
                        const DacResUnitParams& p, int s_row_off, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    EDM_CUDA((cudaFuncSetAttribute(dac_resunit_kernel<C, kHalo>, cudaFuncAttributeMaxDynamicSharedMemorySize, dac_resunit_smem_bytes<C, kHalo>())));
+    EDM_CUDA(cudaFuncSetAttribute(dac_resunit_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, DacResUnitCfg<C>::kSmemBytes));
     attr_set = true;
   }
   const long long tiles = static_cast<long long>(p.B) * p.tiles_per_batch;
   if (tiles > 0x7fffffffLL) return fail(EDM_ERR_INVALID, "dac_resunit: too many tiles");
   const int grid = tiles < num_sms() ? static_cast<int>(tiles) : num_sms();
-  dac_resunit_kernel<C, kHalo><<<grid, kDcThreads, dac_resunit_smem_bytes<C, kHalo>(), st>>>(ma, m7, m1, my, ms, p, s_row_off);
+  dac_resunit_kernel<C><<<grid, kRuThreads, DacResUnitCfg<C>::kSmemBytes, st>>>(ma, m7, m1, my, ms, p, s_row_off);
   EDM_LAUNCH_CHECK("dac_resunit");
   return 0;
 }
 }  // namespace
 
+#ifdef EDM_DAC_TRACE
+unsigned long long* g_dac_trace = nullptr;
+extern "C" void edm_dac_set_trace(unsigned long long* p) { g_dac_trace = p; }
+#endif
 extern "C" int edm_dac_resunit(const void* a, long long a_batch_stride, int B, int rows, int channels, int dilation, const void* w7,
                                const void* w1, const float* b7, const float* a_mid, const float* b1, const float* a_next, float* y,
                                long long y_batch_stride, void* s_out, long long s_batch_stride, int s_row_off, int s_rows, void* stream) {
@@ -742,6 +746,14 @@ extern "C" int edm_dac_resunit(const void* a, long long a_batch_stride, int B, i
   DacResUnitParams p;
   p.B = B; p.rows = rows; p.tiles_per_batch = (rows + kDcBM - 1) / kDcBM; p.dilation = dilation;
   p.b7 = b7; p.a_mid = a_mid; p.b1 = b1; p.a_next = a_next; p.y = y; p.y_batch_stride = y_batch_stride;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("EDM_DAC_DBG"); dbg = e != nullptr ? atoi(e) : 0; }
+    p.dbg = dbg;
+  }
+#ifdef EDM_DAC_TRACE
+  p.trace = g_dac_trace;
+#endif
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static int halo_mode = -2;   // bring-up switch EDM_DAC_HALO=0: seven shifted TMA boxes per tile (first form) for 64 channels too
   if (halo_mode == -2) {
@@ -763,13 +775,11 @@ extern "C" int edm_dac_resunit(const void* a, long long a_batch_stride, int B, i
     EDM_LAUNCH_CHECK("dac_resunit64");
     return 0;
   }
-  if (channels == 64) return launch_dac_resunit<64, false>(ma, m7, m1, my, ms, p, s_row_off, st);
-  if (halo_mode == 1 && dilation >= 1 && 128 + 6 * dilation <= kRu64HaloRows) {
-    CUtensorMap mh;
-    if (int rc = make_tmap_conv_a(&mh, a, B, rows, channels, static_cast<uint64_t>(a_batch_stride), 128 + 6 * dilation)) return rc;
-    return launch_dac_resunit<128, true>(mh, m7, m1, my, ms, p, s_row_off, st);
-  }
-  return launch_dac_resunit<128, false>(ma, m7, m1, my, ms, p, s_row_off, st);
+  if (dilation < 1 || 128 + 6 * dilation > kRu64HaloRows) return fail(EDM_ERR_INVALID, "dac_resunit: dilation %d unsupported (halo tile of at most 192 rows)", dilation);
+  CUtensorMap mh;
+  if (int rc = make_tmap_conv_a(&mh, a, B, rows, channels, static_cast<uint64_t>(a_batch_stride), 128 + 6 * dilation)) return rc;
+  if (channels == 64) return launch_dac_resunit<64>(mh, m7, m1, my, ms, p, s_row_off, st);
+  return launch_dac_resunit<128>(mh, m7, m1, my, ms, p, s_row_off, st);
 }
 
 extern "C" int edm_dac_conv_last(const void* a, long long a_batch_stride, int B, int rows, int c_pad, const float* w, float bias, float* out,

@@ -299,40 +299,58 @@ dac_conv_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 //   warp 0: TMA producer: 7 * C/64 stages of (A box, W7 chunk), then C/64 stages of W1 chunks
 //   warp 1: MMA issuer: GEMM 1 -> acc1 (TMEM columns [0, C)); after the epilogue warps have published h: GEMM 2 -> acc2 ([C, 2C))
 //   warps 2-9: phase 1 (acc1 -> bias, Snake, bf16 -> h tile, swizzled K-major) and phase 2 (the residual epilogue of dac_conv_kernel)
-// GEMM 1 of the next tile runs under phase 2 of the current one (acc1 is free once h is published).
 struct DacResUnitParams {
   int B, rows, tiles_per_batch, dilation;
   const float* b7; const float* a_mid; const float* b1; const float* a_next;   // [C] each
   float* y; long long y_batch_stride;                                          // fp32 stream, updated in place
+  int dbg;                                                                     // bring-up probes (EDM_DAC_DBG), 0 in production
+#ifdef EDM_DAC_TRACE
+  unsigned long long* trace;   // bring-up build only (tools/gpu_dac_trace.sh): clock64 stamps of CTA 0, [tile][16 events]
+#endif
 };
+#ifdef EDM_DAC_TRACE
+#define DAC_TRACE(tl, k) do { if (blockIdx.x == 0 && p.trace != nullptr && (tl) < 64 && lane == 0) p.trace[(tl) * 16 + (k)] = clock64(); } while (0)
+#else
+#define DAC_TRACE(tl, k) do { } while (0)
+#endif
 
 constexpr int kRu64HaloRows = 192;                                 // >= 128 + 6 * 9
 constexpr uint32_t kRu64HaloBytes = kRu64HaloRows * 128;           // 24 KB per 64-channel chunk
 
-// kHalo: the input rows are loaded once per tile with their halo (one box per 64-channel chunk) and the taps are row-shifted
-// descriptors into that tile (see dac_resunit64_kernel below); the ring then carries weight chunks only. Cuts the L2 -> SM
-// traffic of a 128-channel tile from 480 KB to 300 KB.
-template <int C, bool kHalo>
-constexpr uint32_t dac_resunit_smem_bytes() {
-  return (kHalo ? 5 : 4) * ((kHalo ? 0 : kDcABytes) + C * 128) + (kHalo ? (C / 64) * kRu64HaloBytes : 0) + 128 * C * 2 + 8 * kDcStagingBytes + 6 * C * 4 + 1024 + 256;
-}
+template <int C>
+struct DacResUnitCfg {
+  static constexpr int kStages = 5;                                   // weight chunks [C x 64] in flight
+  static constexpr uint32_t kStageBytes = C * 128;
+  static constexpr uint32_t kHaloBytes = (C / 64) * kRu64HaloBytes;   // input rows with their halo, one box per 64-channel chunk
+  static constexpr uint32_t kHBytes = 128 * C * 2;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kHaloBytes + kHBytes + 8 * kDcStagingBytes + 6 * C * 4 + 1024 + 256;
+};
+constexpr int kRuThreads = 512;
 
-template <int C, bool kHalo>
-__global__ void __launch_bounds__(kDcThreads, 1)
+// Warp roles (four warpgroups, registers redistributed with setmaxnreg): warp 0 TMA producer, warp 1 MMA issuer, warps 4-7 phase 1
+// (one per TMEM lane quadrant, all C columns), warps 8-15 phase 2 (two per quadrant, half of the columns each). The epilogue phases
+// are latency-bound chains (TMEM load -> math -> shared / global memory), and with both phases on the same eight warps they bounded
+// the kernel (7.7 us per 128-channel tile against 4.5 us of HBM time); on separate warps phase 1 of tile i+1 runs beside phase 2 of
+// tile i. Both accumulators are double-buffered (TMEM columns: acc1[0] [0,C) acc1[1] [C,2C) acc2[0] [2C,3C) acc2[1] [3C,4C)); the
+// MMA warp issues GEMM 1 of tile i+1 before GEMM 2 of tile i and the producer feeds the ring in that order.
+// With the phases off its back the kernel is bound by TMA latency x bytes in flight (clock64 timeline, tools/gpu_dac_trace.sh: 600
+// cycles per K step with three 32 KB (A + W) stages), so the input rows are loaded once per tile with their halo (one box per
+// 64-channel chunk, taps = row-shifted descriptors, see dac_resunit64_kernel) and the ring carries five 16 KB weight chunks.
+// Buffer reuse: acc1[s] (GEMM 1 of tile i+2) <- the MMA warp has waited hfull of tile i; the halo tile (tile i+1) <- aempty, committed
+// after GEMM 1 of tile i; h (phase 1 of tile i+1) <- the phase-1 warps wait t2full of tile i (GEMM 2 has read h); acc2[s] (GEMM 2 of
+// tile i+2) <- the MMA warp waits t2empty[s] of tile i.
+template <int C>
+__global__ void __launch_bounds__(kRuThreads, 1)
 dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w7, const __grid_constant__ CUtensorMap tma_w1,
                    const __grid_constant__ CUtensorMap tma_y, const __grid_constant__ CUtensorMap tma_s, const DacResUnitParams p, const int s_row_off) {
-  // the mainloop is bound by TMA latency x bytes in flight, not by the tensor pipe: with the halo tile out of the ring the same
-  // shared memory holds five 16 KB weight stages (80 KB in flight) instead of four 32 KB (A + W) stages carrying 64 KB of weights
-  constexpr int kStages = kHalo ? 5 : 4;
+  constexpr int kStages = DacResUnitCfg<C>::kStages;
   constexpr int kKc = C / 64;                       // 64-channel chunks
-  constexpr uint32_t kBBytes = C * 128;
-  constexpr uint32_t kAOff = kHalo ? 0 : kDcABytes;     // offset of the weight chunk inside a ring stage
-  constexpr uint32_t kStageBytes = kAOff + kBBytes;
-  constexpr uint32_t kHBytes = 128 * C * 2;
+  constexpr uint32_t kStageBytes = DacResUnitCfg<C>::kStageBytes;
+  constexpr uint32_t kHBytes = DacResUnitCfg<C>::kHBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* s_a = smem + kStages * kStageBytes;      // kHalo: kKc halo tiles of [<= 192 rows x 64 channels]
-  uint8_t* s_h = s_a + (kHalo ? kKc * kRu64HaloBytes : 0);   // kKc sub-tiles of [128 rows x 64 channels] bf16, 128B-swizzled
+  uint8_t* s_a = smem + kStages * kStageBytes;      // kKc halo tiles of [<= 192 rows x 64 channels]
+  uint8_t* s_h = s_a + DacResUnitCfg<C>::kHaloBytes;   // kKc sub-tiles of [128 rows x 64 channels] bf16, 128B-swizzled
   uint8_t* staging = s_h + kHBytes;
   float* s_b7 = reinterpret_cast<float*>(staging + 8 * kDcStagingBytes);
   float* s_am = s_b7 + C;
@@ -342,10 +360,11 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   float* s_ian = s_an + C;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_ian + C);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* t1full_bar = empty_bar + kStages;
-  uint64_t* hfull_bar = t1full_bar + 1;
-  uint64_t* t2full_bar = hfull_bar + 1;
-  uint64_t* afull_bar = t2full_bar + 1;
+  uint64_t* t1full_bar = empty_bar + kStages;  // [2]
+  uint64_t* hfull_bar = t1full_bar + 2;        // [2]
+  uint64_t* t2full_bar = hfull_bar + 2;        // [2]
+  uint64_t* t2empty_bar = t2full_bar + 2;      // [2]
+  uint64_t* afull_bar = t2empty_bar + 2;
   uint64_t* aempty_bar = afull_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 1);
   const uint32_t halo_bytes = static_cast<uint32_t>(128 + 6 * p.dilation) * 128;
@@ -364,15 +383,18 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(t1full_bar, 1);
-    mbar_init(hfull_bar, 256);
-    mbar_init(t2full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&t1full_bar[s], 1);
+      mbar_init(&hfull_bar[s], 128);
+      mbar_init(&t2full_bar[s], 1);
+      mbar_init(&t2empty_bar[s], 256);
+    }
     mbar_init(afull_bar, 1);
     mbar_init(aempty_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<2 * C>(tmem_slot);
-  for (int i = threadIdx.x; i < C; i += kDcThreads) {
+  if (warp == 1) tmem_alloc<4 * C>(tmem_slot);
+  for (int i = threadIdx.x; i < C; i += kRuThreads) {
     s_b7[i] = __ldg(p.b7 + i);
     s_b1[i] = __ldg(p.b1 + i);
     const float am = __ldg(p.a_mid + i), an = __ldg(p.a_next + i);
@@ -384,88 +406,138 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tl = 0; tl < my_tiles; ++tl) {
-        const int tile = blockIdx.x + tl * gridDim.x;
-        const int t0 = (tile % p.tiles_per_batch) * kDcBM, b = tile / p.tiles_per_batch;
-        if constexpr (kHalo) {
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (warp == 0) {
+      if (lane == 0) {
+        uint32_t it = 0;
+        auto feed1 = [&](int tl) {      // the halo tile, then 7 * kKc W7 chunks
+          const int tile = blockIdx.x + tl * gridDim.x;
+          const int t0 = (tile % p.tiles_per_batch) * kDcBM, b = tile / p.tiles_per_batch;
           mbar_wait(aempty_bar, (tl & 1) ^ 1);   // GEMM 1 of the previous tile has read the halo tiles
           mbar_arrive_expect_tx(afull_bar, kKc * halo_bytes);
           for (int c = 0; c < kKc; ++c) tma_load_3d(&tma_a, afull_bar, s_a + c * kRu64HaloBytes, c * 64, t0 - 3 * p.dilation, b);
-        }
-        for (int j = 0; j < 7; ++j) {
-          const int row = t0 + (j - 3) * p.dilation;
+          for (int j = 0; j < 7; ++j) {
+            for (int c = 0; c < kKc; ++c, ++it) {
+              const uint32_t s = it % kStages;
+              mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+              mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+              tma_load_2d(&tma_w7, &full_bar[s], smem + s * kStageBytes, (j * kKc + c) * 64, 0);
+            }
+          }
+        };
+        auto feed2 = [&]() {            // kKc stages: W1 chunks
           for (int c = 0; c < kKc; ++c, ++it) {
             const uint32_t s = it % kStages;
-            uint8_t* st = smem + s * kStageBytes;
             mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
             mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-            if constexpr (!kHalo) tma_load_3d(&tma_a, &full_bar[s], st, c * 64, row, b);
-            tma_load_2d(&tma_w7, &full_bar[s], st + kAOff, (j * kKc + c) * 64, 0);
+            tma_load_2d(&tma_w1, &full_bar[s], smem + s * kStageBytes, c * 64, 0);
           }
-        }
-        for (int c = 0; c < kKc; ++c, ++it) {
-          const uint32_t s = it % kStages;
-          uint8_t* st = smem + s * kStageBytes;
-          mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], kBBytes);
-          tma_load_2d(&tma_w1, &full_bar[s], st + kAOff, c * 64, 0);
+        };
+        if (my_tiles > 0) feed1(0);
+        for (int tl = 0; tl < my_tiles; ++tl) {
+          if (tl + 1 < my_tiles) feed1(tl + 1);
+          feed2();
         }
       }
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc = umma_idesc_bf16(kDcBM, C, 0, 0);
-    uint32_t it = 0;
-    for (int tl = 0; tl < my_tiles; ++tl) {
-      // GEMM 1: acc1 is free (the previous tile's phase 1 finished before its hfull, which this warp has already waited on)
-      if constexpr (kHalo) {
+    } else if (warp == 1) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kDcBM, C, 0, 0);
+      uint32_t it = 0;
+      auto gemm1 = [&](int tl) {
+        DAC_TRACE(tl, 0);
+        const uint32_t d_tmem = tmem_base + (tl & 1) * C;
         mbar_wait_spin(afull_bar, tl & 1);
         tc_fence_after();
-      }
-      for (int ks = 0; ks < 7 * kKc; ++ks, ++it) {
-        const uint32_t s = it % kStages;
-        mbar_wait_spin(&full_bar[s], (it / kStages) & 1);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * kStageBytes);
-        const uint32_t a_addr = kHalo ? smem_u32(s_a) + (ks % kKc) * kRu64HaloBytes + (ks / kKc) * p.dilation * 128 : st;
-        const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024), b_desc = umma_desc_sw128(st + kAOff, 16, 1024);
+        for (int ks = 0; ks < 7 * kKc; ++ks, ++it) {
+          const uint32_t s = it % kStages;
+          mbar_wait_spin(&full_bar[s], (it / kStages) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(s_a) + (ks % kKc) * kRu64HaloBytes + (ks / kKc) * p.dilation * 128;   // tap = row shift
+          const uint64_t a_desc = umma_desc_sw128(a_addr, 16, 1024), b_desc = umma_desc_sw128(smem_u32(smem + s * kStageBytes), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss_warp(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
-        umma_commit_warp(&empty_bar[s]);
+          for (int k = 0; k < 4; ++k) umma_ss_warp(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+          umma_commit_warp(&empty_bar[s]);
+        }
+        umma_commit_warp(aempty_bar);
+        umma_commit_warp(&t1full_bar[tl & 1]);
+        DAC_TRACE(tl, 1);
+      };
+      if (my_tiles > 0) gemm1(0);
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        if (tl + 1 < my_tiles) gemm1(tl + 1);
+        mbar_wait_spin(&hfull_bar[tl & 1], (tl >> 1) & 1);
+        DAC_TRACE(tl, 2);
+        mbar_wait_spin(&t2empty_bar[tl & 1], ((tl >> 1) & 1) ^ 1);   // phase 2 of tile tl - 2 has drained acc2[tl & 1]
+        tc_fence_after();
+        DAC_TRACE(tl, 3);
+        for (int c = 0; c < kKc; ++c, ++it) {
+          const uint32_t s = it % kStages;
+          mbar_wait_spin(&full_bar[s], (it / kStages) & 1);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_sw128(smem_u32(s_h) + c * kDcABytes, 16, 1024);
+          const uint64_t b_desc = umma_desc_sw128(smem_u32(smem + s * kStageBytes), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss_warp(tmem_base + 2 * C + (tl & 1) * C, a_desc + 2 * k, b_desc + 2 * k, idesc, (c | k) != 0 ? 1u : 0u);
+          umma_commit_warp(&empty_bar[s]);
+        }
+        umma_commit_warp(&t2full_bar[tl & 1]);
+        DAC_TRACE(tl, 4);
       }
-      if constexpr (kHalo) umma_commit_warp(aempty_bar);
-      umma_commit_warp(t1full_bar);
-      // GEMM 2 once h is in shared memory (which also means acc2 of the previous tile has been drained)
-      mbar_wait_spin(hfull_bar, tl & 1);
+    }
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    // ---- phase 1: h = Snake_mid(acc1 + b7) -> bf16, this thread's row of the h tile
+    const int quad = warp & 3;
+    const int r_in = quad * 32 + lane;
+    const int sw = lane & 7;
+    const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int s = tl & 1;
+      if (tl >= 1) mbar_wait(&t2full_bar[s ^ 1], ((tl - 1) >> 1) & 1);   // GEMM 2 of tile tl - 1 has read h
+      if (warp == 4) DAC_TRACE(tl, 5);
+      mbar_wait(&t1full_bar[s], (tl >> 1) & 1);
       tc_fence_after();
-      for (int c = 0; c < kKc; ++c, ++it) {
-        const uint32_t s = it % kStages;
-        mbar_wait_spin(&full_bar[s], (it / kStages) & 1);
-        tc_fence_after();
-        const uint64_t a_desc = umma_desc_sw128(smem_u32(s_h) + c * kDcABytes, 16, 1024);
-        const uint64_t b_desc = umma_desc_sw128(smem_u32(smem + s * kStageBytes) + kAOff, 16, 1024);
+      if (warp == 4) DAC_TRACE(tl, 6);
+#pragma unroll 1
+      for (int cc = 0; cc < C / 32; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32(tq + s * C + cc * 32, r);
+        tmem_ld_wait_dep(r);
+        const int col = cc * 32;
+        uint32_t w[16];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss_warp(tmem_base + C, a_desc + 2 * k, b_desc + 2 * k, idesc, (c | k) != 0 ? 1u : 0u);
-        umma_commit_warp(&empty_bar[s]);
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = lds128(smem_u32(s_b7 + col) + 16 * i), a4 = lds128(smem_u32(s_am + col) + 16 * i), ia4 = lds128(smem_u32(s_iam + col) + 16 * i);
+          w[2 * i] = pack_bf16x2(snake_act(__uint_as_float(r[4 * i]) + b4.x, a4.x, ia4.x), snake_act(__uint_as_float(r[4 * i + 1]) + b4.y, a4.y, ia4.y));
+          w[2 * i + 1] = pack_bf16x2(snake_act(__uint_as_float(r[4 * i + 2]) + b4.z, a4.z, ia4.z), snake_act(__uint_as_float(r[4 * i + 3]) + b4.w, a4.w, ia4.w));
+        }
+        const uint32_t h_row = smem_u32(s_h) + (col >> 6) * kDcABytes + r_in * 128;
+        const int c0 = (col & 63) >> 3;   // first 16-byte chunk of these 32 channels inside the 128-byte row
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          sts128(h_row + (((c0 + i) ^ sw) << 4), make_float4(__uint_as_float(w[4 * i]), __uint_as_float(w[4 * i + 1]), __uint_as_float(w[4 * i + 2]),
+                                                           __uint_as_float(w[4 * i + 3])));
       }
-      umma_commit_warp(t2full_bar);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&hfull_bar[s]);
+      if (warp == 4) DAC_TRACE(tl, 7);
     }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    // ---- phase 2: y = x + acc2 + b1, s_out = Snake_next(y)
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int r_in = quad * 32 + lane;
+    const int half = (warp - 8) >> 2;
     constexpr int kColsPerWarp = C / 2;
     constexpr int kChunks = kColsPerWarp / 32;
-    uint8_t* stg_y = staging + (warp - 2) * kDcStagingBytes;
+    uint8_t* stg_y = staging + (warp - 8) * kDcStagingBytes;
     uint8_t* stg_s = stg_y + 4096;
     const uint32_t y_row = smem_u32(stg_y) + lane * 128;
     const uint32_t s_row = smem_u32(stg_s) + lane * 64;
     const int sw = lane & 7, sw64 = (lane >> 1) & 3;
     const int xr_row = lane >> 3, xr_ch = lane & 7;
     const int total_chunks = my_tiles * kChunks;
-    const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + half * kColsPerWarp;
+    const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + 2 * C + half * kColsPerWarp;
 
     auto load_x = [&](int q, float4 (&xr)[8]) {
       const int tile = blockIdx.x + (q / kChunks) * gridDim.x;
@@ -484,40 +556,20 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     for (int tl = 0; tl < my_tiles; ++tl) {
       const int tile = blockIdx.x + tl * gridDim.x;
       const int t0 = (tile % p.tiles_per_batch) * kDcBM, b = tile / p.tiles_per_batch;
-      // ---- phase 1: h = Snake_mid(acc1 + b7) -> bf16, this thread's row of the h tile
-      mbar_wait(t1full_bar, tl & 1);
+      if (warp == 8) DAC_TRACE(tl, 8);
+      mbar_wait(&t2full_bar[tl & 1], (tl >> 1) & 1);
       tc_fence_after();
+      if (warp == 8) DAC_TRACE(tl, 9);
 #pragma unroll 1
       for (int cc = 0; cc < kChunks; ++cc) {
         uint32_t r[32];
-        tmem_ld_32x32(tq + cc * 32, r);
+        tmem_ld_32x32(tq + (tl & 1) * C + cc * 32, r);
         tmem_ld_wait_dep(r);
-        const int col = half * kColsPerWarp + cc * 32;
-        uint32_t w[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b4 = lds128(smem_u32(s_b7 + col) + 16 * i), a4 = lds128(smem_u32(s_am + col) + 16 * i), ia4 = lds128(smem_u32(s_iam + col) + 16 * i);
-          w[2 * i] = pack_bf16x2(snake_act(__uint_as_float(r[4 * i]) + b4.x, a4.x, ia4.x), snake_act(__uint_as_float(r[4 * i + 1]) + b4.y, a4.y, ia4.y));
-          w[2 * i + 1] = pack_bf16x2(snake_act(__uint_as_float(r[4 * i + 2]) + b4.z, a4.z, ia4.z), snake_act(__uint_as_float(r[4 * i + 3]) + b4.w, a4.w, ia4.w));
+        if (warp == 8) DAC_TRACE(tl, 10 + 3 * cc);
+        if (cc == kChunks - 1) {
+          tc_fence_before();
+          mbar_arrive(&t2empty_bar[tl & 1]);
         }
-        const uint32_t h_row = smem_u32(s_h) + (col >> 6) * kDcABytes + r_in * 128;
-        const int c0 = (col & 63) >> 3;   // first 16-byte chunk of these 32 channels inside the 128-byte row
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          sts128(h_row + (((c0 + i) ^ sw) << 4), make_float4(__uint_as_float(w[4 * i]), __uint_as_float(w[4 * i + 1]), __uint_as_float(w[4 * i + 2]),
-                                                           __uint_as_float(w[4 * i + 3])));
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(hfull_bar);
-      // ---- phase 2: y = x + acc2 + b1, s_out = Snake_next(y)
-      mbar_wait(t2full_bar, tl & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int cc = 0; cc < kChunks; ++cc) {
-        uint32_t r[32];
-        tmem_ld_32x32(tq + C + cc * 32, r);
-        tmem_ld_wait_dep(r);
         const int col = half * kColsPerWarp + cc * 32;
         float v[32];
 #pragma unroll
@@ -526,11 +578,12 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           v[4 * i] = __uint_as_float(r[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
           v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
         }
-        if (lane == 0) bulk_wait_group_read0();
+        if (lane == 0 && !(p.dbg & 1)) bulk_wait_group_read0();
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 8; ++k) sts128(smem_u32(stg_y) + (k * 4 + xr_row) * 128 + ((xr_ch ^ ((k * 4 + xr_row) & 7)) << 4), xr[k]);
         __syncwarp();
+        if (warp == 8) DAC_TRACE(tl, 11 + 3 * cc);
         const int q = tl * kChunks + cc + 1;
         if (q < total_chunks) load_x(q, xr);
 #pragma unroll
@@ -558,15 +611,15 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           tma_store_3d(&tma_s, stg_s, col, t0 + quad * 32 + s_row_off, b);
           bulk_commit_group();
         }
+        if (warp == 8) DAC_TRACE(tl, 12 + 3 * cc);
       }
-      tc_fence_before();   // acc2 reads are ordered before the hfull arrive of the next tile, which releases GEMM 2
     }
     if (lane == 0) bulk_wait_group0();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<2 * C>(tmem_base);
+  if (warp == 1) tmem_dealloc<4 * C>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
@@ -758,7 +811,7 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           v[4 * i] = __uint_as_float(r[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
           v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
         }
-        if (lane == 0) bulk_wait_group_read0();
+        if (lane == 0 && !(p.dbg & 1)) bulk_wait_group_read0();
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 8; ++k) sts128(smem_u32(stg_y) + (k * 4 + xr_row) * 128 + ((xr_ch ^ ((k * 4 + xr_row) & 7)) << 4), xr[k]);
