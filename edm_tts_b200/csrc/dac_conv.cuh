@@ -565,7 +565,7 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         uint32_t r[32];
         tmem_ld_32x32(tq + (tl & 1) * C + cc * 32, r);
         tmem_ld_wait_dep(r);
-        if (warp == 8) DAC_TRACE(tl, 10 + 3 * cc);
+        if (warp == 8 && cc == 0) DAC_TRACE(tl, 10);
         if (cc == kChunks - 1) {
           tc_fence_before();
           mbar_arrive(&t2empty_bar[tl & 1]);
@@ -583,7 +583,7 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 #pragma unroll
         for (int k = 0; k < 8; ++k) sts128(smem_u32(stg_y) + (k * 4 + xr_row) * 128 + ((xr_ch ^ ((k * 4 + xr_row) & 7)) << 4), xr[k]);
         __syncwarp();
-        if (warp == 8) DAC_TRACE(tl, 11 + 3 * cc);
+        if (warp == 8 && cc == 0) DAC_TRACE(tl, 11);
         const int q = tl * kChunks + cc + 1;
         if (q < total_chunks) load_x(q, xr);
 #pragma unroll
@@ -593,6 +593,7 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) sts128(y_row + ((i ^ sw) << 4), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+        if (warp == 8 && cc == 0) DAC_TRACE(tl, 13);
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -604,14 +605,16 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         for (int i = 0; i < 4; ++i)
           sts128(s_row + ((i ^ sw64) << 4), make_float4(__uint_as_float(w[4 * i]), __uint_as_float(w[4 * i + 1]), __uint_as_float(w[4 * i + 2]),
                                                         __uint_as_float(w[4 * i + 3])));
+        if (warp == 8 && cc == 0) DAC_TRACE(tl, 14);
         fence_proxy_async_smem();
         __syncwarp();
+        if (warp == 8 && cc == 0) DAC_TRACE(tl, 15);
         if (lane == 0) {
           tma_store_3d(&tma_y, stg_y, col, t0 + quad * 32, b);
           tma_store_3d(&tma_s, stg_s, col, t0 + quad * 32 + s_row_off, b);
           bulk_commit_group();
         }
-        if (warp == 8) DAC_TRACE(tl, 12 + 3 * cc);
+        if (warp == 8 && cc == 0) DAC_TRACE(tl, 12);
       }
     }
     if (lane == 0) bulk_wait_group0();

@@ -33,7 +33,7 @@ for it in range(3):
 torch.cuda.synchronize()
 t = tr.view(64, 16).cpu()
 names = ["g1 start", "g1 issued", "hfull seen", "t2empty ok", "g2 issued", "p1 hfree", "p1 t1full", "p1 done", "p2 wait", "p2 t2full", "c0 tmem", "c0 x in", "c0 stored",
-         "c1 tmem", "c1 x in", "c1 stored"]
+         "c0 y sts", "c0 s sts", "c0 fenced"]
 base = int(t[t > 0].min())
 print("tile " + " ".join(f"{n:>10s}" for n in names))
 for tl in range(20, 30):
