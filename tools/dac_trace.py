@@ -7,12 +7,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import edm_tts_b200._lib as L  # noqa: E402
-
 lib = C.CDLL(os.path.join(ROOT, "gpurun_out", "libedm_trace.so"))
-L._LIB = lib  # noqa
-for name, (res, args) in L._SIGS.items() if hasattr(L, "_SIGS") else []:
-    pass
 c, B, rows = 128, 2, 480080
 dev = "cuda"
 a = torch.randn(B, rows, c, device=dev).to(torch.bfloat16)
