@@ -7,6 +7,9 @@ are present.
 """
 from __future__ import annotations
 
+import json
+import os
+
 import torch
 
 from .config import DACConfig
@@ -29,6 +32,20 @@ class DAC:
         self.decoder = None
         if any(k.startswith("decoder.") for k in state_dict):
             self.decoder = DACDecoder(state_dict, self.latent_dim, cfg.decoder_dim, cfg.decoder_rates, prefix="decoder.", device=device)
+
+    @staticmethod
+    def load_checkpoint(path: str):
+        """HF directory written by the reference's DAC.save_pretrained (config.json + model.safetensors) -> (state_dict, DACConfig)."""
+        from safetensors.torch import load_file
+
+        with open(os.path.join(path, "config.json")) as f:
+            cfg = DACConfig.from_any(json.load(f))
+        return load_file(os.path.join(path, "model.safetensors")), cfg
+
+    @classmethod
+    def from_pretrained(cls, path: str, device="cuda"):
+        sd, cfg = cls.load_checkpoint(path)
+        return cls(sd, cfg, device=device)
 
     def eval(self):
         return self

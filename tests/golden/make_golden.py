@@ -200,6 +200,16 @@ def make_dac_decoder(name, input_channel, channels, B, T, seed=0):
     print(f"dac_decoder_{name}: audio {tuple(audio.shape)} rms {audio.pow(2).mean().sqrt().item():.3f} saved", flush=True)
 
 
+def make_dac_key_layout():
+    """Key names and shapes of the unmodified reference DAC(DACConfig()).state_dict(): the checkpoint layout the CUDA-side DAC reads."""
+    import json
+
+    ref = DAC(DACConfig()).state_dict()
+    with open(os.path.join(OUT, "dac_state_dict_keys.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in ref.items()}, f, indent=0, sort_keys=True)
+    print(f"dac_state_dict_keys: {len(ref)} entries saved", flush=True)
+
+
 def make_train_forward(name, cfg_name, B, T, seed=0):
     """InjectionConformerModel.forward (eval mode: no dropout, ground-truth injections) with cosine_schedule_mask replaced by a
     fixed Bernoulli(0.6) mask: loss, arg-max codes and a few logit rows."""
@@ -240,6 +250,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "dac_decoder":
         make_dac_decoder("small", 64, 96, 2, 9)
         make_dac_decoder("full", 1024, 1536, 2, 12)
+        make_dac_key_layout()
         sys.exit(0)
     with tempfile.TemporaryDirectory():
         make_rvq("small", "small", 2, 50)
@@ -256,3 +267,4 @@ if __name__ == "__main__":
         make_dac_encoder("full", 64, 2, 6400 + 160)
         make_dac_decoder("small", 64, 96, 2, 9)
         make_dac_decoder("full", 1024, 1536, 2, 12)
+        make_dac_key_layout()

@@ -58,3 +58,37 @@ def test_lengths_match_torch():
         for L_in in (1, 2, 17):
             assert conv_transpose_length(L_in, s) == F.conv_transpose1d(torch.zeros(1, 1, L_in), torch.zeros(1, 1, 2 * s), stride=s, padding=s // 2,
                                                                          output_padding=s % 2).shape[-1]
+
+
+def test_dac_checkpoint_loader_reads_reference_layout(tmp_path):
+    """DAC.load_checkpoint on an HF directory (config.json + model.safetensors) with the reference's key names."""
+    import json
+
+    from safetensors.torch import save_file
+
+    from edm_tts_b200.dac import DAC
+    from edm_tts_b200.synthetic import make_dac_state_dict
+
+    sd = make_dac_state_dict(1)
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(tmp_path / "model.safetensors"))
+    (tmp_path / "config.json").write_text(json.dumps({"encoder_dim": 64, "encoder_rates": [2, 4, 5, 8], "decoder_dim": 1536, "decoder_rates": [8, 5, 4, 2],
+                                                      "n_codebooks": 12, "codebook_size": 1024, "codebook_dim": 8, "sample_rate": 16000, "model_type": "dac"}))
+    got, cfg = DAC.load_checkpoint(str(tmp_path))
+    assert set(got) == set(sd) and cfg.latent_dim == 1024 and cfg.decoder_rates == (8, 5, 4, 2)
+    k = "decoder.model.1.block.1.parametrizations.weight.original1"
+    assert torch.equal(got[k], sd[k]) and got[k].shape == (1536, 768, 16)
+
+
+def test_synthetic_dac_weights_follow_the_reference_key_layout(golden_dir):
+    """The key names / shapes the CUDA-side DAC reads are those of the unmodified reference DAC(DACConfig()).state_dict()
+    (tests/golden/dac_state_dict_keys.json, written by tests/golden/make_golden.py from /root/reference)."""
+    import json
+    import os
+
+    from edm_tts_b200.synthetic import make_dac_state_dict
+
+    with open(os.path.join(golden_dir, "dac_state_dict_keys.json")) as f:
+        ref = json.load(f)
+    ours = make_dac_state_dict(0)
+    assert set(ours) == set(ref)
+    assert all(list(ours[k].shape) == ref[k] for k in ref)
