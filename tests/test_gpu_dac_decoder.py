@@ -68,3 +68,26 @@ def test_decode_from_codes_and_errors():
     assert dac.decode_from_codes(codes.cuda(), length=1000).shape == (2, 1, 1000)
     with pytest.raises(ValueError):
         dac.decoder(torch.zeros(1, 512, 4))
+
+
+def test_decoder_full_size_properties():
+    """The S2A bench shape (utterances of 500 frames -> 160 016 samples): determinism, batch independence, bounded output and
+    time-locality (the receptive field of the stack is finite: editing one latent frame changes only nearby samples)."""
+    from edm_tts_b200.dac_decoder import DACDecoder
+    from edm_tts_b200.synthetic import make_decoder_state_dict
+
+    dec = DACDecoder(make_decoder_state_dict(1024, 1536, (8, 5, 4, 2), 0))
+    z = torch.randn(16, 1024, 500, device="cuda", generator=torch.Generator(device="cuda").manual_seed(6)) * 0.5
+    audio = dec(z)
+    assert audio.shape == (16, 1, 160016) and torch.isfinite(audio).all() and audio.abs().max() <= 1.0
+    assert torch.equal(audio, dec(z))
+    assert torch.equal(audio[5:7], dec(z[5:7].contiguous()))
+    z2 = z.clone()
+    z2[:, :, 250] = 0.0
+    a2 = dec(z2)
+    centre = 250 * 320
+    assert not torch.equal(a2[:, :, centre - 200:centre + 200], audio[:, :, centre - 200:centre + 200])
+    assert torch.equal(a2[:, :, :centre - 16000], audio[:, :, :centre - 16000]) and torch.equal(a2[:, :, centre + 16000:], audio[:, :, centre + 16000:])
+    # a prefix of the latent gives the prefix of the waveform away from the cut
+    ap = dec(z[:, :, :200].contiguous())
+    assert torch.equal(ap[:, :, :200 * 320 - 16000], audio[:, :, :200 * 320 - 16000])
