@@ -746,11 +746,6 @@ extern "C" int edm_dac_resunit(const void* a, long long a_batch_stride, int B, i
   DacResUnitParams p;
   p.B = B; p.rows = rows; p.tiles_per_batch = (rows + kDcBM - 1) / kDcBM; p.dilation = dilation;
   p.b7 = b7; p.a_mid = a_mid; p.b1 = b1; p.a_next = a_next; p.y = y; p.y_batch_stride = y_batch_stride;
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("EDM_DAC_DBG"); dbg = e != nullptr ? atoi(e) : 0; }
-    p.dbg = dbg;
-  }
 #ifdef EDM_DAC_TRACE
   p.trace = g_dac_trace;
 #endif

@@ -303,7 +303,6 @@ struct DacResUnitParams {
   int B, rows, tiles_per_batch, dilation;
   const float* b7; const float* a_mid; const float* b1; const float* a_next;   // [C] each
   float* y; long long y_batch_stride;                                          // fp32 stream, updated in place
-  int dbg;                                                                     // bring-up probes (EDM_DAC_DBG), 0 in production
 #ifdef EDM_DAC_TRACE
   unsigned long long* trace;   // bring-up build only (tools/gpu_dac_trace.sh): clock64 stamps of CTA 0, [tile][16 events]
 #endif
@@ -578,7 +577,7 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
           v[4 * i] = __uint_as_float(r[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
           v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
         }
-        if (lane == 0 && !(p.dbg & 1)) bulk_wait_group_read0();
+        if (lane == 0) bulk_wait_group_read0();
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 8; ++k) sts128(smem_u32(stg_y) + (k * 4 + xr_row) * 128 + ((xr_ch ^ ((k * 4 + xr_row) & 7)) << 4), xr[k]);
@@ -814,7 +813,7 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           v[4 * i] = __uint_as_float(r[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
           v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
         }
-        if (lane == 0 && !(p.dbg & 1)) bulk_wait_group_read0();
+        if (lane == 0) bulk_wait_group_read0();
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < 8; ++k) sts128(smem_u32(stg_y) + (k * 4 + xr_row) * 128 + ((xr_ch ^ ((k * 4 + xr_row) & 7)) << 4), xr[k]);
