@@ -345,12 +345,15 @@ def main():
                              "workload": "DAC.encode_to_codes, audio [32, 1, 960160] fp32 (32 x 60 s at 16 kHz, dump_tokens batch) -> codes [32, 12, 3000], per GPU",
                              "algorithmic_tflops": 2 * 767.0e3 * 32 * 960160 / (enc_ms * 1e-3) / 1e12,
                              "frac_of_tensor_peak": 2 * 767.0e3 * 32 * 960160 / (enc_ms * 1e-3) / 1e12 / tf_peak,
+                             # activation bytes each launch must move at least once: 8164 B per audio sample
+                             "algorithmic_gbs": 8164.0 * 32 * 960160 / (enc_ms * 1e-3) / 1e9, "frac_hbm": 8164.0 * 32 * 960160 / (enc_ms * 1e-3) / 1e9 / hbm_peak,
                              "note": "conv encoder = 29 implicit-GEMM launches per chunk of 8 utterances (csrc/dac_conv.cuh, bf16 operands, fp32 stream) + the RVQ kernels above; "
                                      "767 kMAC per audio sample; the 64/128-channel stages are HBM / L2 bound, the 256..1024-channel stages run at 1.1-1.3 PFLOP/s"},
         "secondary_decode": {"metric": "dac_decode_from_codes_frames_per_s", "value": B * T / (dec_ms * 1e-3), "unit": "frames/s", "ms": dec_ms,
                              "workload": f"DAC.decode_from_codes, codes [{B}, 12, {T}] (the S2A bench batch) -> audio [{B}, 1, {dec_samples}] fp32, per GPU",
                              "algorithmic_tflops": 2 * 1.74e6 * B * dec_samples / (dec_ms * 1e-3) / 1e12,
                              "frac_of_tensor_peak": 2 * 1.74e6 * B * dec_samples / (dec_ms * 1e-3) / 1e12 / tf_peak,
+                             "algorithmic_gbs": 14800.0 * B * dec_samples / (dec_ms * 1e-3) / 1e9, "frac_hbm": 14800.0 * B * dec_samples / (dec_ms * 1e-3) / 1e9 / hbm_peak,
                              "note": "conv decoder on the encoder's implicit-GEMM kernels (transposed convs as 2-tap convs into a shifted output view); 1.74 MMAC per output sample"},
         "model_flops_utilisation": {"algorithmic_tflops": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12,
                                     "frac_of_peak": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12 / tf_peak},
