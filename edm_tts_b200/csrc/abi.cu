@@ -196,6 +196,23 @@ bool gemm_use_pairs() {
 
 // rows of a B-operand TMA box: a CTA of a pair loads half of the 256-row weight tile
 uint32_t gemm_b_box_rows() { return gemm_use_pairs() ? kGemmBN / 2 : kGemmBN; }
+// Weight operand of a GEMM: the tensor map of the large-M kernels (128- or 256-row boxes) and the 64-row-box map of the small-M kernel
+struct WMap {
+  CUtensorMap big, small;
+};
+int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+int make_wmap(WMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
+  if (int rc = make_tmap_2d(&m->big, ptr, rows, cols, ld, gemm_b_box_rows())) return rc;
+  return make_tmap_2d(&m->small, ptr, rows, cols, ld, kSmBN);
+}
+bool gemm_small_m() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("EDM_GEMM_SMALL");  // bring-up switch: 0 = always the large-M kernels
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 bool gemm_resid_tma() {
   static int v = -1;
@@ -226,13 +243,15 @@ bool gemm_out_tma() {
 }
 
 template <int EPI>
-int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p_in, cudaStream_t st) {
+int launch_gemm_t(const CUtensorMap& ma, const WMap& wm, const GemmParams& p_in, cudaStream_t st) {
+  const CUtensorMap& mb = wm.big;
   GemmParams p = p_in;
   p.reverse = next_direction();
   static bool attr_set = false;
   if (!attr_set) {
     EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
     EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_small_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmSmemBytes));
     if (EPI == EPI_RESID_F32)
       EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI_RESID_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     if (EPI == EPI_SWISH_BF16)
@@ -244,6 +263,17 @@ int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
     attr_set = true;
   }
   ProfScope prof(PK_GEMM, 2.0 * p.M * p.N * p.K, st);
+  {
+    // small M: the large tiles would leave most SMs without work while a few stream the weights (see gemm.cuh, small-M variant)
+    const int pair_tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (p.N / kGemmBN);
+    if (gemm_small_m() && pair_tiles * 4 <= num_sms()) {
+      p.reverse = 0;
+      const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / kSmBN);
+      gemm_bf16_tn_small_kernel<EPI><<<tiles < num_sms() ? tiles : num_sms(), kSmThreads, kSmSmemBytes, st>>>(ma, wm.small, p);
+      EDM_LAUNCH_CHECK("gemm_bf16_tn_small");
+      return 0;
+    }
+  }
   if (gemm_use_pairs()) {
     const int tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (p.N / kGemmBN);
     const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
@@ -277,7 +307,7 @@ int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
   EDM_LAUNCH_CHECK("gemm_bf16_tn");
   return 0;
 }
-int launch_gemm(int epi, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+int launch_gemm(int epi, const CUtensorMap& ma, const WMap& mb, const GemmParams& p, cudaStream_t st) {
   if (p.M <= 0 || p.N % kGemmBN != 0 || p.N > kGemmMaxN || p.K % kGemmBK != 0 || p.K <= 0) return fail(EDM_ERR_INVALID, "gemm shape M=%d N=%d K=%d unsupported (N %% 256, N <= 8192, K %% 64)", p.M, p.N, p.K);
   switch (epi) {
     case EPI_BF16: return launch_gemm_t<EPI_BF16>(ma, mb, p, st);
@@ -434,9 +464,10 @@ extern "C" int edm_gemm_bf16(const void* a, long long lda, const void* b, long l
                              const float* bias, void* out, long long ldo, float scale, const float* rope_cos,
                              const float* rope_sin, int seq_len, int rope_cols, void* stream) {
   if (int rc = check_arch()) return rc;
-  CUtensorMap ma, mb;
+  CUtensorMap ma;
+  WMap mb;
   if (int rc = make_tmap_2d(&ma, a, M, K, lda, kGemmBM)) return rc;
-  if (int rc = make_tmap_2d(&mb, b, N, K, ldb, gemm_b_box_rows())) return rc;
+  if (int rc = make_wmap(&mb, b, N, K, ldb)) return rc;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.a_k_offset = 0; p.b_row_offset = 0;
   p.bias = bias; p.out = out; p.ldo = ldo; p.scale = scale;
@@ -834,7 +865,7 @@ enum GlobalField {
 };
 
 struct BlockMaps {
-  CUtensorMap ff1_w1, ff1_w2, wqkv, wo, pw1, pw2, ff2_w1, ff2_w2;
+  WMap ff1_w1, ff1_w2, wqkv, wo, pw1, pw2, ff2_w1, ff2_w2;
 };
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -845,7 +876,7 @@ struct edm_s2a_ctx {
   edm_s2a_config cfg;
   std::vector<const void*> w;  // depth * F_BLOCK_COUNT + G_COUNT
   std::vector<BlockMaps> bmaps;
-  CUtensorMap head_map, fine_map;
+  WMap head_map, fine_map;
   int n_fine;
 
   // bound shapes
@@ -988,17 +1019,17 @@ extern "C" edm_s2a_ctx* edm_s2a_create(const edm_s2a_config* cfg, const void* co
   int rc = 0;
   for (int l = 0; l < cfg->depth && rc == 0; ++l) {
     BlockMaps& m = c->bmaps[l];
-    rc = rc ? rc : make_tmap_2d(&m.ff1_w1, c->bw(l, F_FF1_W1), 4096, 1024, 1024, gemm_b_box_rows());
-    rc = rc ? rc : make_tmap_2d(&m.ff1_w2, c->bw(l, F_FF1_W2), 1024, 4096, 4096, gemm_b_box_rows());
-    rc = rc ? rc : make_tmap_2d(&m.wqkv, c->bw(l, F_WQKV), 3072, 1024, 1024, gemm_b_box_rows());
-    rc = rc ? rc : make_tmap_2d(&m.wo, c->bw(l, F_WO), 1024, 1024, 1024, gemm_b_box_rows());
-    rc = rc ? rc : make_tmap_2d(&m.pw1, c->bw(l, F_PW1_W), 4096, 1024, 1024, gemm_b_box_rows());
-    rc = rc ? rc : make_tmap_2d(&m.pw2, c->bw(l, F_PW2_W), 1024, 2048, 2048, gemm_b_box_rows());
-    rc = rc ? rc : make_tmap_2d(&m.ff2_w1, c->bw(l, F_FF2_W1), 4096, 1024, 1024, gemm_b_box_rows());
-    rc = rc ? rc : make_tmap_2d(&m.ff2_w2, c->bw(l, F_FF2_W2), 1024, 4096, 4096, gemm_b_box_rows());
+    rc = rc ? rc : make_wmap(&m.ff1_w1, c->bw(l, F_FF1_W1), 4096, 1024, 1024);
+    rc = rc ? rc : make_wmap(&m.ff1_w2, c->bw(l, F_FF1_W2), 1024, 4096, 4096);
+    rc = rc ? rc : make_wmap(&m.wqkv, c->bw(l, F_WQKV), 3072, 1024, 1024);
+    rc = rc ? rc : make_wmap(&m.wo, c->bw(l, F_WO), 1024, 1024, 1024);
+    rc = rc ? rc : make_wmap(&m.pw1, c->bw(l, F_PW1_W), 4096, 1024, 1024);
+    rc = rc ? rc : make_wmap(&m.pw2, c->bw(l, F_PW2_W), 1024, 2048, 2048);
+    rc = rc ? rc : make_wmap(&m.ff2_w1, c->bw(l, F_FF2_W1), 4096, 1024, 1024);
+    rc = rc ? rc : make_wmap(&m.ff2_w2, c->bw(l, F_FF2_W2), 1024, 4096, 4096);
   }
-  rc = rc ? rc : make_tmap_2d(&c->head_map, c->gw(G_HEAD_W), static_cast<uint64_t>(cfg->num_quantizers) * 1024, 1024, 1024, gemm_b_box_rows());
-  rc = rc ? rc : make_tmap_2d(&c->fine_map, c->gw(G_FINE_W), static_cast<uint64_t>(c->n_fine) * 1024, 1024, 1024, gemm_b_box_rows());
+  rc = rc ? rc : make_wmap(&c->head_map, c->gw(G_HEAD_W), static_cast<uint64_t>(cfg->num_quantizers) * 1024, 1024, 1024);
+  rc = rc ? rc : make_wmap(&c->fine_map, c->gw(G_FINE_W), static_cast<uint64_t>(c->n_fine) * 1024, 1024, 1024);
   if (rc) {
     delete c;
     return nullptr;
