@@ -14,7 +14,7 @@ import torch
 
 from .config import DACConfig
 from .dac_decoder import DACDecoder
-from .dac_encoder import DACEncoder
+from .dac_encoder import DACEncoder, code_lengths
 from .dac_rvq import ResidualVectorQuantize
 
 
@@ -68,6 +68,10 @@ class DAC:
         q = self.quantizer(z, n_quantizers)
         out.update(q)
         return out
+
+    def get_code_lengths(self, input_lengths: torch.Tensor) -> torch.Tensor:
+        """Frames per utterance for padded batches (AudioTokenizer.get_code_lengths, audio_tokenizer.py:84-93)."""
+        return code_lengths(input_lengths.long(), self.config.encoder_rates).int()
 
     def codes_to_features(self, codes):
         return self.quantizer.from_codes(codes)[0]

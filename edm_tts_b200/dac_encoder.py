@@ -22,6 +22,21 @@ def _fold(sd, key):
     return v * (g / v.flatten(1).norm(dim=1).view(-1, 1, 1))
 
 
+def strided_conv_length(L_in, stride: int):
+    """Output length of Conv1d(kernel 2s, stride s, padding ceil(s/2)) (encoder.py:19-25); works on ints and integer tensors. The
+    other convs of the encoder (k=7 pad 3, dilated k=7 pad 3d, k=1, k=3 pad 1) keep the length."""
+    return (L_in + 2 * math.ceil(stride / 2) - 2 * stride) // stride + 1
+
+
+def code_lengths(input_lengths, strides=(2, 4, 5, 8)):
+    """Frames produced for audio of `input_lengths` samples: what AudioTokenizer.get_code_lengths computes by walking the encoder's
+    Conv1d modules (edm_tts/models/audio_tokenizer/audio_tokenizer.py:84-93)."""
+    out = input_lengths
+    for s in strides:
+        out = strided_conv_length(out, s)
+    return out
+
+
 class DACEncoder:
     def __init__(self, state_dict: dict, d_model: int = 64, strides=(2, 4, 5, 8), prefix: str = "", device="cuda",
                  max_chunk_samples: int = 1 << 23, fused: bool = True):
@@ -72,7 +87,7 @@ class DACEncoder:
         """Time lengths after the first conv and after each strided conv (kernel 2s, stride s, padding ceil(s/2))."""
         out = [L_in]
         for s in self.strides:
-            out.append((out[-1] + 2 * math.ceil(s / 2) - 2 * s) // s + 1)
+            out.append(strided_conv_length(out[-1], s))
         return out
 
     def _workspace(self, B: int, L_in: int):

@@ -92,3 +92,21 @@ def test_synthetic_dac_weights_follow_the_reference_key_layout(golden_dir):
     ours = make_dac_state_dict(0)
     assert set(ours) == set(ref)
     assert all(list(ours[k].shape) == ref[k] for k in ref)
+
+
+def test_code_lengths_match_a_conv_stack():
+    """code_lengths == the length arithmetic of the reference encoder's Conv1d chain (what AudioTokenizer.get_code_lengths walks)."""
+    from edm_tts_b200.dac_encoder import code_lengths
+
+    convs = [torch.nn.Conv1d(1, 1, 7, padding=3)]
+    for s in (2, 4, 5, 8):
+        for d in (1, 3, 9):
+            convs += [torch.nn.Conv1d(1, 1, 7, dilation=d, padding=3 * d), torch.nn.Conv1d(1, 1, 1)]
+        convs.append(torch.nn.Conv1d(1, 1, 2 * s, stride=s, padding=math.ceil(s / 2)))
+    convs.append(torch.nn.Conv1d(1, 1, 3, padding=1))
+    net = torch.nn.Sequential(*convs)
+    for n in (320, 321, 4000, 16000, 16077, 960160):
+        with torch.inference_mode():
+            assert net(torch.zeros(1, 1, n)).shape[-1] == code_lengths(n)
+    lens = torch.tensor([320, 16077, 960160])
+    assert code_lengths(lens).tolist() == [code_lengths(int(v)) for v in lens]
