@@ -180,3 +180,34 @@ def test_full_size_config2_properties():
     out = model.infer_special(twin[:2], None, None, steps=8, seed=5)
     assert not torch.equal(out[0], out[1])          # same tokens, different Philox rows
     assert torch.equal(out[0], full[0])             # row 0 unchanged by what sits next to it
+
+
+def test_decode_is_cuda_graph_capturable():
+    """infer_special issues no host synchronisation and no allocation outside torch's pool, so the whole decode (854 launches at the
+    base config) can be captured with torch.cuda.graph and replayed; the replay reproduces the stream launch bit for bit."""
+    from tests.parity_utils import full_model
+
+    cfg, sd, model = full_model()
+    from oracle.weights import make_inputs
+
+    inp = make_inputs(1, 60, 20, 3, cfg, seed=77)
+    sem, ap, sp = inp["semantic_tokens"].cuda(), inp["acoustic_prompt_tokens"].cuda(), inp["semantic_prompt_tokens"].cuda()
+    ref = model.infer_special(sem, ap, sp, steps=3, seed=5)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        model.infer_special(sem, ap, sp, steps=3, seed=5)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        out = model.infer_special(sem, ap, sp, steps=3, seed=5)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    # new tokens through the captured graph: copy into the static input, replay
+    inp2 = make_inputs(1, 60, 20, 3, cfg, seed=78)
+    ref2 = model.infer_special(inp2["semantic_tokens"].cuda(), ap, sp, steps=3, seed=5)
+    sem.copy_(inp2["semantic_tokens"].cuda())
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref2)

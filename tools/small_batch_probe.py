@@ -41,3 +41,30 @@ for B, T in [(1, 150), (1, 500), (4, 500)]:
     names = ["gemm", "attention", "layernorm", "conv_module"]
     per = ", ".join(f"{n} {pc[i]} x {pm[i] / max(pc[i], 1) * 1e3:.1f} us = {pm[i]:.2f} ms" for i, n in enumerate(names))
     print(f"B={B} T={T}: device {e0.elapsed_time(e1):.2f} ms, host launch loop {(t1 - t0) * 1e3:.2f} ms, wall {(t2 - t0) * 1e3:.2f} ms, {launches} launches; {per}", flush=True)
+
+# What a captured graph of the same call would give (fixed seed: measurement only)
+for B, T in [(1, 150), (1, 500)]:
+    sem = make_inputs(B, T, 0, 1, cfg, seed=1)["semantic_tokens"].cuda()
+    try:
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                model.infer_special(sem, None, None, steps=8, seed=0)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            out = model.infer_special(sem, None, None, steps=8, seed=0)
+        torch.cuda.synchronize()
+        ref = model.infer_special(sem, None, None, steps=8, seed=0)
+        g.replay()
+        torch.cuda.synchronize()
+        same = bool(torch.equal(out, ref))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"B={B} T={T}: graph replay {e0.elapsed_time(e1) / 5:.2f} ms per decode (codes equal to the stream launch: {same})", flush=True)
+    except Exception as ex:  # noqa: BLE001
+        print(f"B={B} T={T}: graph capture failed: {type(ex).__name__}: {str(ex)[:200]}", flush=True)
