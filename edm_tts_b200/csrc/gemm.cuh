@@ -353,15 +353,14 @@ constexpr int kSmStages = 8;
 constexpr int kSmThreads = 64 + 32 * 4;
 constexpr uint32_t kSmBBytes = kSmBN * kGemmBK * 2;
 constexpr uint32_t kSmStageBytes = kGemmABytes + kSmBBytes;
-constexpr uint32_t kSmSmemBytes = kSmStages * kSmStageBytes + kGemmMaxN * 4 + 1024 + 256;
+constexpr uint32_t kSmSmemBytes = kSmStages * kSmStageBytes + 1024 + 256;
 
 template <int EPI>
 __global__ void __launch_bounds__(kSmThreads, 1)
 gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  float* s_bias = reinterpret_cast<float*>(smem + kSmStages * kSmStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSmStages * kSmStageBytes + kGemmMaxN * 4);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSmStages * kSmStageBytes);
   uint64_t* empty_bar = full_bar + kSmStages;
   uint64_t* tmem_full_bar = empty_bar + kSmStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -388,11 +387,6 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<128>(tmem_base_slot);
-  if (p.bias != nullptr) {
-    for (int i = threadIdx.x; i < p.N; i += kSmThreads) s_bias[i] = __ldg(p.bias + i);
-  } else {
-    for (int i = threadIdx.x; i < p.N; i += kSmThreads) s_bias[i] = 0.f;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -462,11 +456,13 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
       if constexpr (EPI == EPI_QKV_ROPE) {
         gemm_epilogue_rope64(p, row, col0, r0, r1);
       } else {
-        const uint32_t b4 = smem_u32(s_bias + col0);
+        // a CTA sees one or two tiles here: the 64 bias values come straight from L2 instead of staging all N in the prologue
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias != nullptr ? p.bias + col0 : nullptr);
+        auto bias4 = [&](int i) { return b4 != nullptr ? __ldg(b4 + i) : make_float4(0.f, 0.f, 0.f, 0.f); };
         float v[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 b = lds128(b4 + 16 * i);
+          const float4 b = bias4(i);
           v[4 * i + 0] = __uint_as_float(r0[4 * i + 0]) + b.x;
           v[4 * i + 1] = __uint_as_float(r0[4 * i + 1]) + b.y;
           v[4 * i + 2] = __uint_as_float(r0[4 * i + 2]) + b.z;
@@ -476,7 +472,7 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
           float g[32];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 b = lds128(b4 + 16 * (8 + i));
+            const float4 b = bias4(8 + i);
             g[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
             g[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
             g[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
@@ -487,7 +483,7 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
           gemm_store_32<EPI>(p, row, col0, v);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 b = lds128(b4 + 16 * (8 + i));
+            const float4 b = bias4(8 + i);
             v[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
             v[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
             v[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
