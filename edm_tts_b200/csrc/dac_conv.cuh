@@ -296,9 +296,11 @@ dac_conv_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 //     h = Snake_mid(conv7_dilated(sx) + b7)  ->  bf16 tile in shared memory (the A operand of the second GEMM)
 //     y = x + conv1x1(h) + b1 ;  s_out = bf16(Snake_next(y))
 // HBM traffic per row: sx (2C) + x (4C) in, y (4C) + s_out (2C) out = 12 C bytes instead of 16 C for the two-launch form.
-//   warp 0: TMA producer: 7 * C/64 stages of (A box, W7 chunk), then C/64 stages of W1 chunks
-//   warp 1: MMA issuer: GEMM 1 -> acc1 (TMEM columns [0, C)); after the epilogue warps have published h: GEMM 2 -> acc2 ([C, 2C))
-//   warps 2-9: phase 1 (acc1 -> bias, Snake, bf16 -> h tile, swizzled K-major) and phase 2 (the residual epilogue of dac_conv_kernel)
+// Two kernels: dac_resunit_kernel<C> (general, used at 128 channels: weights streamed through a ring, phases on separate
+// warpgroups) and dac_resunit64_kernel (64 channels: weights resident in shared memory). Both read the input rows once per tile with
+// their halo and address the seven taps through row-shifted UMMA descriptors.
+//   phase 1: acc1 -> + b7 -> Snake_mid -> bf16 -> h tile (swizzled K-major, the A operand of GEMM 2)
+//   phase 2: acc2 -> + b1 + x -> y (fp32 stream) and Snake_next -> s_out (the residual epilogue of dac_conv_kernel)
 struct DacResUnitParams {
   int B, rows, tiles_per_batch, dilation;
   const float* b7; const float* a_mid; const float* b1; const float* a_next;   // [C] each
