@@ -211,3 +211,28 @@ def test_decode_is_cuda_graph_capturable():
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, ref2)
+
+
+def test_graphed_decode_matches_infer_special():
+    """edm_tts_b200.serving.GraphedDecode: replays reproduce infer_special on the same tokens and the same (per-request) noise."""
+    from edm_tts_b200.serving import GraphedDecode
+    from oracle.weights import make_inputs
+    from tests.parity_utils import full_model
+
+    cfg, sd, model = full_model()
+    gd = GraphedDecode(model, 2, 40, prompt_frames=10, steps=3, seed=9)
+    prev = None
+    for s in (1, 2):
+        inp = make_inputs(2, 40, 10, 3, cfg, seed=100 + s)
+        got = gd(inp["semantic_tokens"], inp["acoustic_prompt_tokens"], inp["semantic_prompt_tokens"])
+        want = model.infer_special(inp["semantic_tokens"], inp["acoustic_prompt_tokens"], inp["semantic_prompt_tokens"], steps=3,
+                                   cat_gumbel=gd.cat.clone(), remask_gumbel=gd.rem.clone())
+        assert torch.equal(got, want) and got.shape == (2, 12, 40)
+        assert prev is None or not torch.equal(prev, gd.cat)        # fresh noise per request
+        prev = gd.cat.clone()
+    with pytest.raises(ValueError):
+        gd(torch.zeros(2, 41, dtype=torch.long))
+    # Philox mode (no injected noise): equals infer_special with the captured seed
+    gp = GraphedDecode(model, 1, 30, steps=2, seed=4, fresh_noise=False)
+    tok = make_inputs(1, 30, 0, 2, cfg, seed=5)["semantic_tokens"]
+    assert torch.equal(gp(tok), model.infer_special(tok, None, None, steps=2, seed=4))
