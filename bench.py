@@ -364,6 +364,28 @@ def main():
         out["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                                "sample": f"oracle (fp32 torch CPU restatement of the reference) on 1 utterance x 150 frames x {DECODE_STEPS} steps "
                                          f"(BASELINE config 1), best of 3 after 1 warm-up; runs {[round(t, 2) for t in times]} s"}
+        # the same port for the DAC conv stacks on a bounded sample (10 s of audio / 500 frames of latent), best of 2
+        from edm_tts_b200.synthetic import make_decoder_state_dict, make_encoder_state_dict
+        from oracle.dac_decoder import decoder_forward
+        from oracle.dac_encoder import encoder_forward
+
+        def best_of(fn, n=2):
+            ts = []
+            for _ in range(n + 1):
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            return min(ts[1:])
+        esd, dsd = make_encoder_state_dict(64, (2, 4, 5, 8), 0), make_decoder_state_dict(1024, 1536, (8, 5, 4, 2), 0)
+        a10 = torch.randn(1, 1, 160000) * 0.3
+        z10 = torch.randn(1, 1024, 500) * 0.5
+        with torch.inference_mode():
+            t_enc = best_of(lambda: encoder_forward(esd, a10))
+            t_dec = best_of(lambda: decoder_forward(dsd, z10))
+        out["secondary_encode"]["cpu_baseline"] = {"value": 500 / t_enc, "unit": "frames/s", "cores": threads, "kind": "port",
+                                                   "sample": "oracle conv encoder (fp32 torch CPU) on 1 x 10 s of audio, best of 2 (RVQ not included)"}
+        out["secondary_decode"]["cpu_baseline"] = {"value": 500 / t_dec, "unit": "frames/s", "cores": threads, "kind": "port",
+                                                   "sample": "oracle conv decoder (fp32 torch CPU) on 1 x 500 frames of latent, best of 2"}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
