@@ -797,7 +797,7 @@ extern "C" int edm_dac_resunit(const void* a, long long a_batch_stride, int B, i
     if (int rc = make_tmap_2d(&m7b, w7, channels, 7ull * channels, 7ull * channels, 64)) return rc;
     const long long tiles = static_cast<long long>(p.B) * p.tiles_per_batch;
     const int grid = tiles < num_sms() ? static_cast<int>(tiles) : num_sms();
-    dac_resunit64_kernel<<<grid, kDcThreads, kRu64SmemBytes, st>>>(mh, m7b, m1, my, ms, p, s_row_off);
+    dac_resunit64_kernel<<<grid, kRuThreads, kRu64SmemBytes, st>>>(mh, m7b, m1, my, ms, p, s_row_off);
     EDM_LAUNCH_CHECK("dac_resunit64");
     return 0;
   }

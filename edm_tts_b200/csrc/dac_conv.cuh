@@ -635,10 +635,11 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
 //     The 128B-swizzle XOR is a function of the absolute shared-memory address bits (TMA writes and UMMA reads agree on it), so
 //     a start address that is not a multiple of the 1024 B swizzle atom works as is, with the descriptor's base-offset field
 //     left at zero (measured: bit-identical to the seven-box form; setting base offset = (addr >> 7) & 7 gives wrong results).
-// The h tile and both accumulators are double-buffered and the two sides are software-pipelined across tiles (see the MMA warp).
+// The h tile and both accumulators are double-buffered, the MMA warp issues GEMM 1 of tile i+1 before GEMM 2 of tile i, and the two
+// epilogue phases run on separate warpgroups (as in dac_resunit_kernel), so phase 1 of tile i+1 runs beside phase 2 of tile i.
 constexpr uint32_t kRu64SmemBytes = 7 * 8192 + 8192 + 2 * kRu64HaloBytes + 2 * kDcABytes + 8 * kDcStagingBytes + 6 * 64 * 4 + 1024 + 256;
 
-__global__ void __launch_bounds__(kDcThreads, 1)
+__global__ void __launch_bounds__(kRuThreads, 1)
 dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w7, const __grid_constant__ CUtensorMap tma_w1,
                      const __grid_constant__ CUtensorMap tma_y, const __grid_constant__ CUtensorMap tma_s, const DacResUnitParams p, const int s_row_off) {
   constexpr int C = 64;
@@ -661,7 +662,8 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   uint64_t* t1full_bar = aempty_bar + 2;  // [2]
   uint64_t* hfull_bar = t1full_bar + 2;   // [2]
   uint64_t* t2full_bar = hfull_bar + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t2full_bar + 2);
+  uint64_t* t2empty_bar = t2full_bar + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t2empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.B * p.tiles_per_batch;
@@ -679,13 +681,14 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       mbar_init(&afull_bar[s], 1);
       mbar_init(&aempty_bar[s], 1);
       mbar_init(&t1full_bar[s], 1);
-      mbar_init(&hfull_bar[s], 256);
+      mbar_init(&hfull_bar[s], 128);
       mbar_init(&t2full_bar[s], 1);
+      mbar_init(&t2empty_bar[s], 256);
     }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<256>(tmem_slot);
-  for (int i = threadIdx.x; i < C; i += kDcThreads) {
+  for (int i = threadIdx.x; i < C; i += kRuThreads) {
     s_b7[i] = __ldg(p.b7 + i);
     s_b1[i] = __ldg(p.b1 + i);
     const float am = __ldg(p.a_mid + i), an = __ldg(p.a_next + i);
@@ -697,6 +700,9 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // warp roles as in dac_resunit_kernel: warps 0 / 1 producer / MMA, warps 4-7 phase 1, warps 8-15 phase 2 (setmaxnreg)
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(w_bar, 8 * 8192);
@@ -736,17 +742,54 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       const int s = tl & 1;
       if (tl + 1 < my_tiles) gemm1(tl + 1);
       mbar_wait_spin(&hfull_bar[s], (tl >> 1) & 1);
+      mbar_wait_spin(&t2empty_bar[s], ((tl >> 1) & 1) ^ 1);   // phase 2 of tile tl - 2 has drained acc2[s]
       tc_fence_after();
       const uint64_t a_desc = umma_desc_sw128(smem_u32(s_h) + s * kDcABytes, 16, 1024), b_desc = umma_desc_sw128(smem_u32(s_w1), 16, 1024);
 #pragma unroll
       for (int k = 0; k < 4; ++k) umma_ss_warp(tmem_base + 2 * C + s * C, a_desc + 2 * k, b_desc + 2 * k, idesc, k != 0 ? 1u : 0u);
       umma_commit_warp(&t2full_bar[s]);
     }
-  } else {
+  }
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    // ---- phase 1 (four warps, one per TMEM lane quadrant, both 32-column halves): h = Snake_mid(acc1 + b7) -> bf16
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
     const int r_in = quad * 32 + lane;
-    uint8_t* stg_y = staging + (warp - 2) * kDcStagingBytes;
+    const int sw = lane & 7;
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      if (tl >= 2) mbar_wait(&t2full_bar[tl & 1], ((tl >> 1) & 1) ^ 1);   // GEMM 2 of tile tl - 2 has read h[tl & 1]
+      mbar_wait(&t1full_bar[tl & 1], (tl >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int col = half * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (tl & 1) * C + col, r);
+        tmem_ld_wait_dep(r);
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = lds128(smem_u32(s_b7 + col) + 16 * i), a4 = lds128(smem_u32(s_am + col) + 16 * i), ia4 = lds128(smem_u32(s_iam + col) + 16 * i);
+          w[2 * i] = pack_bf16x2(snake_act(__uint_as_float(r[4 * i]) + b4.x, a4.x, ia4.x), snake_act(__uint_as_float(r[4 * i + 1]) + b4.y, a4.y, ia4.y));
+          w[2 * i + 1] = pack_bf16x2(snake_act(__uint_as_float(r[4 * i + 2]) + b4.z, a4.z, ia4.z), snake_act(__uint_as_float(r[4 * i + 3]) + b4.w, a4.w, ia4.w));
+        }
+        const uint32_t h_row = smem_u32(s_h) + (tl & 1) * kDcABytes + r_in * 128;
+        const int c0 = col >> 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          sts128(h_row + (((c0 + i) ^ sw) << 4), make_float4(__uint_as_float(w[4 * i]), __uint_as_float(w[4 * i + 1]), __uint_as_float(w[4 * i + 2]),
+                                                           __uint_as_float(w[4 * i + 3])));
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&hfull_bar[tl & 1]);
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+    // ---- phase 2 (eight warps, two per quadrant, 32 columns each): y = x + acc2 + b1, s_out = Snake_next(y)
+    const int quad = warp & 3;
+    const int half = (warp - 8) >> 2;
+    uint8_t* stg_y = staging + (warp - 8) * kDcStagingBytes;
     uint8_t* stg_s = stg_y + 4096;
     const uint32_t y_row = smem_u32(stg_y) + lane * 128;
     const uint32_t s_row = smem_u32(stg_s) + lane * 64;
@@ -767,37 +810,6 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
     };
     float4 xr[8];
     if (my_tiles > 0) load_x(0, xr);
-
-    // Epilogue order: phase 1 of tile i+1, then phase 2 of tile i. Reuse of the double buffers needs no extra barriers:
-    //   acc1[s] (GEMM 1 of tile i+2) <- the MMA warp has waited hfull of tile i, arrived after this thread's phase-1 reads of tile i;
-    //   h[s] (phase 1 of tile i+2)   <- this thread has waited t2full of tile i (GEMM 2 of tile i has read h[s]) in phase 2 of tile i;
-    //   acc2[s] (GEMM 2 of tile i+2) <- waits hfull of tile i+2, arrived after this thread's phase 2 of tile i.
-    auto phase1 = [&](int tl) {
-      // ---- phase 1
-      mbar_wait(&t1full_bar[tl & 1], (tl >> 1) & 1);
-      tc_fence_after();
-      {
-        uint32_t r[32];
-        tmem_ld_32x32(tq + (tl & 1) * C, r);
-        tmem_ld_wait_dep(r);
-        uint32_t w[16];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b4 = lds128(smem_u32(s_b7 + col) + 16 * i), a4 = lds128(smem_u32(s_am + col) + 16 * i), ia4 = lds128(smem_u32(s_iam + col) + 16 * i);
-          w[2 * i] = pack_bf16x2(snake_act(__uint_as_float(r[4 * i]) + b4.x, a4.x, ia4.x), snake_act(__uint_as_float(r[4 * i + 1]) + b4.y, a4.y, ia4.y));
-          w[2 * i + 1] = pack_bf16x2(snake_act(__uint_as_float(r[4 * i + 2]) + b4.z, a4.z, ia4.z), snake_act(__uint_as_float(r[4 * i + 3]) + b4.w, a4.w, ia4.w));
-        }
-        const uint32_t h_row = smem_u32(s_h) + (tl & 1) * kDcABytes + r_in * 128;
-        const int c0 = col >> 3;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          sts128(h_row + (((c0 + i) ^ sw) << 4), make_float4(__uint_as_float(w[4 * i]), __uint_as_float(w[4 * i + 1]), __uint_as_float(w[4 * i + 2]),
-                                                           __uint_as_float(w[4 * i + 3])));
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(&hfull_bar[tl & 1]);
-    };
     auto phase2 = [&](int tl) {
       const int tile = blockIdx.x + tl * gridDim.x;
       const int t0 = (tile % p.tiles_per_batch) * kDcBM, b = tile / p.tiles_per_batch;
@@ -808,6 +820,8 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         uint32_t r[32];
         tmem_ld_32x32(tq + 2 * C + (tl & 1) * C, r);
         tmem_ld_wait_dep(r);
+        tc_fence_before();
+        mbar_arrive(&t2empty_bar[tl & 1]);
         float v[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -849,11 +863,7 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       }
       tc_fence_before();
     };
-    if (my_tiles > 0) phase1(0);
-    for (int tl = 0; tl < my_tiles; ++tl) {
-      if (tl + 1 < my_tiles) phase1(tl + 1);
-      phase2(tl);
-    }
+    for (int tl = 0; tl < my_tiles; ++tl) phase2(tl);
     if (lane == 0) bulk_wait_group0();
   }
 
