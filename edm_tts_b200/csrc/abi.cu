@@ -762,7 +762,7 @@ extern "C" int edm_dac_resunit(const void* a, long long a_batch_stride, int B, i
                                long long y_batch_stride, void* s_out, long long s_batch_stride, int s_row_off, int s_rows, void* stream) {
   if (int rc = check_arch()) return rc;
   if (B <= 0 || rows <= 0) return 0;
-  if (channels != 64 && channels != 128) return fail(EDM_ERR_INVALID, "dac_resunit: fused kernel exists for 64 and 128 channels (got %d)", channels);
+  if (channels != 64 && channels != 128 && channels != 192) return fail(EDM_ERR_INVALID, "dac_resunit: fused kernel exists for 64, 128 and 192 channels (got %d)", channels);
   if (a == s_out) return fail(EDM_ERR_INVALID, "dac_resunit: s_out must not alias the input operand (neighbouring tiles still read its halo)");
   if (!b7 || !a_mid || !b1 || !a_next || !y || !s_out || s_row_off < 0) return fail(EDM_ERR_INVALID, "dac_resunit: null argument");
   CUtensorMap ma, m7, m1, my, ms;
@@ -781,6 +781,18 @@ extern "C" int edm_dac_resunit(const void* a, long long a_batch_stride, int B, i
   p.trace = g_dac_trace;
 #endif
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (channels == 192) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      EDM_CUDA(cudaFuncSetAttribute(dac_resunit_wide_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, DacResUnitWideCfg<192>::kSmemBytes));
+      attr_set = true;
+    }
+    const long long tiles = static_cast<long long>(p.B) * p.tiles_per_batch;
+    const int grid = tiles < num_sms() ? static_cast<int>(tiles) : num_sms();
+    dac_resunit_wide_kernel<192><<<grid, kRuThreads, DacResUnitWideCfg<192>::kSmemBytes, st>>>(ma, m7, m1, my, ms, p, s_row_off);
+    EDM_LAUNCH_CHECK("dac_resunit_wide");
+    return 0;
+  }
   static int halo_mode = -2;   // bring-up switch EDM_DAC_HALO=0: seven shifted TMA boxes per tile (first form) for 64 channels too
   if (halo_mode == -2) {
     const char* e = getenv("EDM_DAC_HALO");

@@ -626,6 +626,267 @@ dac_resunit_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
   if (warp == 1) tmem_dealloc<4 * C>(tmem_base);
 }
 
+template <int C>
+struct DacResUnitWideCfg {
+  static constexpr int kStages = 3;                                   // (shifted A box, weight chunk [C x 64]) pairs in flight
+  static constexpr uint32_t kStageBytes = kDcABytes + C * 128;
+  static constexpr uint32_t kHBytes = 128 * C * 2;
+  static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kHBytes + 8 * kDcStagingBytes + 6 * C * 4 + 1024 + 256;
+};
+
+// Wider channel counts (192: decoder stage 3; at 256 only two ring stages fit and the two-launch form is as fast), where 4 C accumulator columns and a halo tile no longer fit: one acc1 / acc2 / h
+// buffer each, the ring carries (shifted A box, W chunk) pairs as in dac_conv_kernel, same warp roles as dac_resunit_kernel. Order of
+// the MMA warp: GEMM 1 (i), GEMM 2 (i), GEMM 1 (i+1) ...: GEMM 1 of the next tile runs under phase 2 of the current one.
+// Buffer reuse: acc1 <- hfull of the previous tile (waited by the MMA warp before its GEMM 2); h <- the phase-1 warps wait t2full of
+// the previous tile; acc2 <- t2empty (phase 2 has drained it).
+template <int C>
+__global__ void __launch_bounds__(kRuThreads, 1)
+dac_resunit_wide_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w7, const __grid_constant__ CUtensorMap tma_w1,
+                   const __grid_constant__ CUtensorMap tma_y, const __grid_constant__ CUtensorMap tma_s, const DacResUnitParams p, const int s_row_off) {
+  constexpr int kStages = DacResUnitWideCfg<C>::kStages;
+  constexpr int kKc = C / 64;                       // 64-channel chunks
+  constexpr uint32_t kStageBytes = DacResUnitWideCfg<C>::kStageBytes;
+  constexpr uint32_t kHBytes = DacResUnitWideCfg<C>::kHBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* s_h = smem + kStages * kStageBytes;      // kKc sub-tiles of [128 rows x 64 channels] bf16, 128B-swizzled
+  uint8_t* staging = s_h + kHBytes;
+  float* s_b7 = reinterpret_cast<float*>(staging + 8 * kDcStagingBytes);
+  float* s_am = s_b7 + C;
+  float* s_iam = s_am + C;
+  float* s_b1 = s_iam + C;
+  float* s_an = s_b1 + C;
+  float* s_ian = s_an + C;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_ian + C);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* t1full_bar = empty_bar + kStages;
+  uint64_t* hfull_bar = t1full_bar + 1;
+  uint64_t* t2full_bar = hfull_bar + 1;
+  uint64_t* t2empty_bar = t2full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t2empty_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.B * p.tiles_per_batch;
+  const int my_tiles = (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_w7);
+    tma_prefetch_desc(&tma_w1);
+    tma_prefetch_desc(&tma_y);
+    tma_prefetch_desc(&tma_s);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(t1full_bar, 1);
+    mbar_init(hfull_bar, 128);
+    mbar_init(t2full_bar, 1);
+    mbar_init(t2empty_bar, 256);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  for (int i = threadIdx.x; i < C; i += kRuThreads) {
+    s_b7[i] = __ldg(p.b7 + i);
+    s_b1[i] = __ldg(p.b1 + i);
+    const float am = __ldg(p.a_mid + i), an = __ldg(p.a_next + i);
+    s_am[i] = am; s_iam[i] = 1.0f / (am + 1e-9f);
+    s_an[i] = an; s_ian[i] = 1.0f / (an + 1e-9f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (warp == 0) {
+      if (lane == 0) {
+        uint32_t it = 0;
+        for (int tl = 0; tl < my_tiles; ++tl) {
+          const int tile = blockIdx.x + tl * gridDim.x;
+          const int t0 = (tile % p.tiles_per_batch) * kDcBM, b = tile / p.tiles_per_batch;
+          for (int j = 0; j < 7; ++j) {
+            const int row = t0 + (j - 3) * p.dilation;
+            for (int c = 0; c < kKc; ++c, ++it) {
+              const uint32_t s = it % kStages;
+              uint8_t* st = smem + s * kStageBytes;
+              mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+              mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+              tma_load_3d(&tma_a, &full_bar[s], st, c * 64, row, b);
+              tma_load_2d(&tma_w7, &full_bar[s], st + kDcABytes, (j * kKc + c) * 64, 0);
+            }
+          }
+          for (int c = 0; c < kKc; ++c, ++it) {
+            const uint32_t s = it % kStages;
+            uint8_t* st = smem + s * kStageBytes;
+            mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(&full_bar[s], kStageBytes - kDcABytes);
+            tma_load_2d(&tma_w1, &full_bar[s], st + kDcABytes, c * 64, 0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kDcBM, C, 0, 0);
+      uint32_t it = 0;
+      for (int tl = 0; tl < my_tiles; ++tl) {
+        // GEMM 1 -> acc1 (free: hfull of the previous tile was waited below)
+        for (int ks = 0; ks < 7 * kKc; ++ks, ++it) {
+          const uint32_t s = it % kStages;
+          mbar_wait_spin(&full_bar[s], (it / kStages) & 1);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * kStageBytes);
+          const uint64_t a_desc = umma_desc_sw128(st, 16, 1024), b_desc = umma_desc_sw128(st + kDcABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss_warp(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (ks | k) != 0 ? 1u : 0u);
+          umma_commit_warp(&empty_bar[s]);
+        }
+        umma_commit_warp(t1full_bar);
+        mbar_wait_spin(hfull_bar, tl & 1);
+        mbar_wait_spin(t2empty_bar, (tl & 1) ^ 1);   // phase 2 of the previous tile has drained acc2
+        tc_fence_after();
+        for (int c = 0; c < kKc; ++c, ++it) {
+          const uint32_t s = it % kStages;
+          mbar_wait_spin(&full_bar[s], (it / kStages) & 1);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_sw128(smem_u32(s_h) + c * kDcABytes, 16, 1024);
+          const uint64_t b_desc = umma_desc_sw128(smem_u32(smem + s * kStageBytes) + kDcABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss_warp(tmem_base + C, a_desc + 2 * k, b_desc + 2 * k, idesc, (c | k) != 0 ? 1u : 0u);
+          umma_commit_warp(&empty_bar[s]);
+        }
+        umma_commit_warp(t2full_bar);
+      }
+    }
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    // ---- phase 1: h = Snake_mid(acc1 + b7) -> bf16, this thread's row of the h tile
+    const int quad = warp & 3;
+    const int r_in = quad * 32 + lane;
+    const int sw = lane & 7;
+    const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      if (tl >= 1) mbar_wait(t2full_bar, (tl - 1) & 1);   // GEMM 2 of the previous tile has read h
+      mbar_wait(t1full_bar, tl & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < C / 32; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32(tq + cc * 32, r);
+        tmem_ld_wait_dep(r);
+        const int col = cc * 32;
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = lds128(smem_u32(s_b7 + col) + 16 * i), a4 = lds128(smem_u32(s_am + col) + 16 * i), ia4 = lds128(smem_u32(s_iam + col) + 16 * i);
+          w[2 * i] = pack_bf16x2(snake_act(__uint_as_float(r[4 * i]) + b4.x, a4.x, ia4.x), snake_act(__uint_as_float(r[4 * i + 1]) + b4.y, a4.y, ia4.y));
+          w[2 * i + 1] = pack_bf16x2(snake_act(__uint_as_float(r[4 * i + 2]) + b4.z, a4.z, ia4.z), snake_act(__uint_as_float(r[4 * i + 3]) + b4.w, a4.w, ia4.w));
+        }
+        const uint32_t h_row = smem_u32(s_h) + (col >> 6) * kDcABytes + r_in * 128;
+        const int c0 = (col & 63) >> 3;   // first 16-byte chunk of these 32 channels inside the 128-byte row
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          sts128(h_row + (((c0 + i) ^ sw) << 4), make_float4(__uint_as_float(w[4 * i]), __uint_as_float(w[4 * i + 1]), __uint_as_float(w[4 * i + 2]),
+                                                           __uint_as_float(w[4 * i + 3])));
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(hfull_bar);
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    // ---- phase 2: y = x + acc2 + b1, s_out = Snake_next(y)
+    const int quad = warp & 3;
+    const int half = (warp - 8) >> 2;
+    constexpr int kColsPerWarp = C / 2;
+    constexpr int kChunks = kColsPerWarp / 32;
+    uint8_t* stg_y = staging + (warp - 8) * kDcStagingBytes;
+    uint8_t* stg_s = stg_y + 4096;
+    const uint32_t y_row = smem_u32(stg_y) + lane * 128;
+    const uint32_t s_row = smem_u32(stg_s) + lane * 64;
+    const int sw = lane & 7, sw64 = (lane >> 1) & 3;
+    const int xr_row = lane >> 3, xr_ch = lane & 7;
+    const int total_chunks = my_tiles * kChunks;
+    const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + C + half * kColsPerWarp;
+
+    auto load_x = [&](int q, float4 (&xr)[8]) {
+      const int tile = blockIdx.x + (q / kChunks) * gridDim.x;
+      const int t0 = (tile % p.tiles_per_batch) * kDcBM, b = tile / p.tiles_per_batch;
+      const int col = half * kColsPerWarp + (q % kChunks) * 32;
+      const float* base = p.y + static_cast<long long>(b) * p.y_batch_stride + col + xr_ch * 4;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int t = t0 + quad * 32 + k * 4 + xr_row;
+        xr[k] = t < p.rows ? __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(t) * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    float4 xr[8];
+    if (total_chunks > 0) load_x(0, xr);
+
+    for (int tl = 0; tl < my_tiles; ++tl) {
+      const int tile = blockIdx.x + tl * gridDim.x;
+      const int t0 = (tile % p.tiles_per_batch) * kDcBM, b = tile / p.tiles_per_batch;
+      mbar_wait(t2full_bar, tl & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < kChunks; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32(tq + cc * 32, r);
+        tmem_ld_wait_dep(r);
+        if (cc == kChunks - 1) {
+          tc_fence_before();
+          mbar_arrive(t2empty_bar);
+        }
+        const int col = half * kColsPerWarp + cc * 32;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = lds128(smem_u32(s_b1 + col) + 16 * i);
+          v[4 * i] = __uint_as_float(r[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
+          v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
+        }
+        if (lane == 0) bulk_wait_group_read0();
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sts128(smem_u32(stg_y) + (k * 4 + xr_row) * 128 + ((xr_ch ^ ((k * 4 + xr_row) & 7)) << 4), xr[k]);
+        __syncwarp();
+        const int q = tl * kChunks + cc + 1;
+        if (q < total_chunks) load_x(q, xr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 x4 = lds128(y_row + ((i ^ sw) << 4));
+          v[4 * i] += x4.x; v[4 * i + 1] += x4.y; v[4 * i + 2] += x4.z; v[4 * i + 3] += x4.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sts128(y_row + ((i ^ sw) << 4), make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 a4 = lds128(smem_u32(s_an + col) + 16 * i), ia4 = lds128(smem_u32(s_ian + col) + 16 * i);
+          w[2 * i] = pack_bf16x2(snake_act(v[4 * i], a4.x, ia4.x), snake_act(v[4 * i + 1], a4.y, ia4.y));
+          w[2 * i + 1] = pack_bf16x2(snake_act(v[4 * i + 2], a4.z, ia4.z), snake_act(v[4 * i + 3], a4.w, ia4.w));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          sts128(s_row + ((i ^ sw64) << 4), make_float4(__uint_as_float(w[4 * i]), __uint_as_float(w[4 * i + 1]), __uint_as_float(w[4 * i + 2]),
+                                                        __uint_as_float(w[4 * i + 3])));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tma_y, stg_y, col, t0 + quad * 32, b);
+          tma_store_3d(&tma_s, stg_s, col, t0 + quad * 32 + s_row_off, b);
+          bulk_commit_group();
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_group0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 // ------------------------------------------------------------------------------------------------------------------------------
 // 64-channel ResidualUnit, second form: the L2 -> SM fabric bounds dac_resunit_kernel<64> (every 128-row tile pulls seven shifted
 // 16 KB copies of its input rows and 64 KB of weights). Here

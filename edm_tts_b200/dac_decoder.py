@@ -20,6 +20,7 @@ from . import _lib as L
 from .dac_encoder import _fold
 
 _G = 8          # guard rows in front of every stage buffer (>= the largest transposed-conv padding)
+_FUSED = (128, 192)   # (padded) channel counts whose ResidualUnits run as one launch (edm_dac_resunit)
 
 
 def _pad64(c):
@@ -126,7 +127,7 @@ class DACDecoder:
             ws["y"].append(torch.empty(B, rows, c, device=dev, dtype=torch.float32))
             ws["sa"].append(torch.empty(B, rows, c, device=dev, dtype=torch.bfloat16))
             ws["sb"].append(torch.empty(B, rows, c, device=dev, dtype=torch.bfloat16))
-            ws["sm"].append(None if c == 128 else torch.empty(B, Lk, c, device=dev, dtype=torch.bfloat16))
+            ws["sm"].append(None if c in _FUSED else torch.empty(B, Lk, c, device=dev, dtype=torch.bfloat16))
         ws["audio"] = torch.empty(B, lens[-1], device=dev, dtype=torch.float32)
         self._ws[key] = ws
         return ws
@@ -187,7 +188,7 @@ class DACDecoder:
                 else:
                     a_next = self.blocks[k + 1]["a_up"] if k + 1 < len(self.blocks) else self.a_last
                 cur_ptr, oth_ptr = cur.data_ptr() + _G * c * 2, oth.data_ptr() + _G * c * 2
-                if c == 128:
+                if c in _FUSED:
                     self._resunit(cur_ptr, bs, B, Lk, c, d, ru, a_next, y_ptr, bs, oth_ptr, bs)
                 else:
                     sm = ws["sm"][k]

@@ -15,6 +15,9 @@ import torch
 from . import _lib as L
 
 
+_FUSED = (64, 128)   # channel counts whose ResidualUnits run as one launch (edm_dac_resunit); at 256 the two-launch form is as fast
+
+
 def _fold(sd, key):
     """weight_norm (dim 0): w = g * v / ||v||, the norm taken over (in, k) per output channel (nn_layers.py:8-9)."""
     g = sd[key + ".parametrizations.weight.original0"].float()
@@ -106,7 +109,7 @@ class DACEncoder:
             ws["sx"].append(torch.empty(B, Lk, c, device=dev, dtype=torch.bfloat16))
             ws["sh"].append(torch.empty(B, Lk, c, device=dev, dtype=torch.bfloat16))     # sx / sh alternate as unit input / output
             # hidden activation between the two convs of a unit (two-launch form only)
-            ws["sm"].append(None if self.fused and c in (64, 128) else torch.empty(B, Lk, c, device=dev, dtype=torch.bfloat16))
+            ws["sm"].append(None if self.fused and c in _FUSED else torch.empty(B, Lk, c, device=dev, dtype=torch.bfloat16))
             # operand of the strided conv: `pad` zero rows in front, (Ln + 1) * s rows in all; never-written rows stay zero
             ws["sd"].append(torch.zeros(B, (Ln + 1) * s, c, device=dev, dtype=torch.bfloat16))
             c *= 2
@@ -166,7 +169,7 @@ class DACEncoder:
                 a_next = blk["units"][u + 1]["a_in"] if u < 2 else blk["a_down"]
                 # the unit's output operand: the other 64/128-channel buffer, or the padded operand of the strided conv
                 dst, dst_off, dst_rows = (sh if src is sx else sx, 0, Lk) if u < 2 else (sd, math.ceil(s / 2), (Ln + 1) * s)
-                if self.fused and c in (64, 128):
+                if self.fused and c in _FUSED:
                     # both convs in one launch, the hidden activation stays in shared memory (csrc/dac_conv.cuh, dac_resunit_kernel)
                     self._resunit(src, B, Lk, c, d, ru, a_next, y, dst, dst_off, dst_rows)
                 else:

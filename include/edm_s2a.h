@@ -137,10 +137,10 @@ int edm_dac_conv(const void* a, long long a_rows, int a_cols, long long a_batch_
                  float* y, long long y_batch_stride, void* s_out, long long s_batch_stride, int s_row_off, int s_rows,
                  void* zt_out, int zt_is_f32, void* stream);
 
-/* One whole ResidualUnit (nn_layers.py:33-47) of the 64- / 128-channel stages in one launch:
+/* One whole ResidualUnit (nn_layers.py:33-47) of the 64- / 128- / 192-channel stages in one launch:
  *   h = Snake_mid(conv7_dilated(a) + b7) (kept in shared memory);  y += conv1x1(h) + b1 (in place);  s_out = bf16(Snake_next(y)).
  * a: bf16 [B][rows][channels] = Snake_in(x) (batch stride a_batch_stride); w7 bf16 [channels][7 * channels], w1 bf16
- * [channels][channels]; s_out as in edm_dac_conv and must not alias a. channels in {64, 128}. */
+ * [channels][channels]; s_out as in edm_dac_conv and must not alias a. channels in {64, 128, 192}. */
 int edm_dac_resunit(const void* a, long long a_batch_stride, int B, int rows, int channels, int dilation, const void* w7,
                     const void* w1, const float* b7, const float* a_mid, const float* b1, const float* a_next, float* y,
                     long long y_batch_stride, void* s_out, long long s_batch_stride, int s_row_off, int s_rows, void* stream);
