@@ -353,7 +353,7 @@ def main():
                              "workload": f"DAC.decode_from_codes, codes [{B}, 12, {T}] (the S2A bench batch) -> audio [{B}, 1, {dec_samples}] fp32, per GPU",
                              "algorithmic_tflops": 2 * 1.74e6 * B * dec_samples / (dec_ms * 1e-3) / 1e12,
                              "frac_of_tensor_peak": 2 * 1.74e6 * B * dec_samples / (dec_ms * 1e-3) / 1e12 / tf_peak,
-                             "algorithmic_gbs": 14800.0 * B * dec_samples / (dec_ms * 1e-3) / 1e9, "frac_hbm": 14800.0 * B * dec_samples / (dec_ms * 1e-3) / 1e9 / hbm_peak,
+                             "algorithmic_gbs": 13650.0 * B * dec_samples / (dec_ms * 1e-3) / 1e9, "frac_hbm": 13650.0 * B * dec_samples / (dec_ms * 1e-3) / 1e9 / hbm_peak,
                              "note": "conv decoder on the encoder's implicit-GEMM kernels (transposed convs as 2-tap convs into a shifted output view); 1.74 MMAC per output sample"},
         "model_flops_utilisation": {"algorithmic_tflops": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12,
                                     "frac_of_peak": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12 / tf_peak},
