@@ -91,3 +91,30 @@ def test_decoder_full_size_properties():
     # a prefix of the latent gives the prefix of the waveform away from the cut
     ap = dec(z[:, :, :200].contiguous())
     assert torch.equal(ap[:, :, :200 * 320 - 16000], audio[:, :, :200 * 320 - 16000])
+
+
+def test_pipeline_semantic_tokens_to_waveform():
+    """inference.py:43-49 on the CUDA path: S2A infer_special -> DAC.decode_from_codes, against the oracle decoder fed with the same
+    codes (the S2A stage itself is graded in tests/test_gpu_s2a.py)."""
+    from edm_tts_b200.dac import DAC
+    from edm_tts_b200.synthetic import make_dac_state_dict
+    from oracle.dac_decoder import decoder_forward
+    from oracle.weights import make_inputs
+    from tests.parity_utils import full_model
+
+    cfg, sd, model = full_model()
+    dsd = make_dac_state_dict(0)
+    # the vocoder must use the quantizer the S2A model was built with: same synthetic quantizer weights (seed 0) on both sides
+    for k in list(dsd):
+        if k.startswith("quantizer."):
+            dsd[k] = sd["acoustic_model." + k].cpu()
+    dac = DAC(dsd)
+    inp = make_inputs(2, 50, 10, 4, cfg, seed=21)
+    codes = model.infer_special(inp["semantic_tokens"], inp["acoustic_prompt_tokens"], inp["semantic_prompt_tokens"], steps=4, seed=3)
+    wav = dac.decode_from_codes(codes)
+    assert wav.shape == (2, 1, 50 * 320 + 16) and torch.isfinite(wav).all()
+    feats = dac.codes_to_features(codes).cpu()
+    assert torch.allclose(feats, model.acoustic_model.codes_to_features(codes).cpu(), rtol=1e-5, atol=1e-5)
+    with torch.inference_mode():
+        ref = decoder_forward(dsd, feats, prefix="decoder.")
+    _check(wav, ref)
