@@ -159,17 +159,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
           for (int k = 0; k < 4; ++k) umma_ss_warp(tmem_base + w * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
           umma_commit_warp(&s_full[w]);
         };
+        // descriptor fields that do not change (layout, LBO / SBO) are built once; per tile only the 14-bit start address moves
+        const uint64_t vdesc_fixed = umma_desc_sw128(0, p.v_lbo, p.v_sbo);
+        const uint32_t v_kstep16 = p.v_kstep >> 4;
         auto issue_pv = [&](int w, int g) {
           const uint32_t p_addr = smem_u32(sP + w * 2 * kAttnTile);
           const uint64_t pdesc0 = umma_desc_sw128(p_addr, 16, 1024);
-          const uint64_t pdesc1 = umma_desc_sw128(p_addr + kAttnTile, 16, 1024);
-          const uint32_t v_addr = smem_u32(sV + (g % kAttnKvStages) * kAttnTile);
+          const uint64_t pdesc1 = pdesc0 + (kAttnTile >> 4);
+          const uint64_t vdesc = vdesc_fixed + (smem_u32(sV + (g % kAttnKvStages) * kAttnTile) >> 4);
           const bool first = (g % n_kv) == 0;  // first kv tile of an item overwrites O
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const uint64_t adesc = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
-            const uint64_t bdesc = umma_desc_sw128(v_addr + k * p.v_kstep, p.v_lbo, p.v_sbo);
-            umma_ss_warp(tmem_base + 256 + w * 64, adesc, bdesc, idesc_o, (!first || k != 0) ? 1u : 0u);
+            umma_ss_warp(tmem_base + 256 + w * 64, adesc, vdesc + k * v_kstep16, idesc_o, (!first || k != 0) ? 1u : 0u);
           }
           umma_commit_warp(&o_full[w]);
         };
