@@ -296,15 +296,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
           tmem_st_wait();
         }
         l_run *= alpha;
-        float ls0 = 0.f, ls1 = 0.f;
+        // packed f32x2 arithmetic around the exp2: the scale / subtract and the row sums take one issue slot per column pair
+        // (same roundings as the scalar fma / add: the two halves are independent)
+        uint64_t ls2 = f2_pack(0.f, 0.f);
+        const uint64_t sl2_2 = f2_pack(sl2, sl2), nm2 = f2_pack(-m_ref, -m_ref);
         auto emit = [&](uint32_t (&s)[32], int c) {
           uint32_t wv[16];
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * e]), sl2, -m_ref));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * e + 1]), sl2, -m_ref));
-            ls0 += p0;
-            ls1 += p1;
+            float x0, x1;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(s[2 * e]), __uint_as_float(s[2 * e + 1])), sl2_2, nm2), x0, x1);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            ls2 = f2_add(ls2, f2_pack(p0, p1));
             wv[e] = pack_bf16x2(p0, p1);
           }
           // 32 kv columns = 64 B = four 16 B chunks of this row; 128B swizzle: chunk index ^= (row & 7)
@@ -326,6 +329,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
         emit(s2, 2);
         emit(s3, 3);
         if (w == 0) asm volatile("bar.arrive 3, 256;" ::: "memory"); else asm volatile("bar.arrive 2, 256;" ::: "memory");
+        float ls0, ls1;
+        f2_unpack(ls2, ls0, ls1);
         l_run += ls0 + ls1;
         tc_fence_before();
         fence_proxy_async_smem();
