@@ -1069,9 +1069,12 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
         xr[k] = t < p.rows ? __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(t) * C)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    float4 xr[8];
-    if (my_tiles > 0) load_x(0, xr);
-    auto phase2 = [&](int tl) {
+    // residual rows are fetched two tiles ahead (two register sets, the tile loop is unrolled by two): one tile of look-ahead left
+    // the loads on the critical path of the phase
+    float4 xr0[8], xr1[8];
+    if (my_tiles > 0) load_x(0, xr0);
+    if (my_tiles > 1) load_x(1, xr1);
+    auto phase2 = [&](int tl, float4 (&xr)[8]) {
       const int tile = blockIdx.x + tl * gridDim.x;
       const int t0 = (tile % p.tiles_per_batch) * kDcBM, b = tile / p.tiles_per_batch;
       // ---- phase 2
@@ -1095,7 +1098,7 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
 #pragma unroll
         for (int k = 0; k < 8; ++k) sts128(smem_u32(stg_y) + (k * 4 + xr_row) * 128 + ((xr_ch ^ ((k * 4 + xr_row) & 7)) << 4), xr[k]);
         __syncwarp();
-        if (tl + 1 < my_tiles) load_x(tl + 1, xr);
+        if (tl + 2 < my_tiles) load_x(tl + 2, xr);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 x4 = lds128(y_row + ((i ^ sw) << 4));
@@ -1124,7 +1127,10 @@ dac_resunit64_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       }
       tc_fence_before();
     };
-    for (int tl = 0; tl < my_tiles; ++tl) phase2(tl);
+    for (int tl = 0; tl < my_tiles; tl += 2) {
+      phase2(tl, xr0);
+      if (tl + 1 < my_tiles) phase2(tl + 1, xr1);
+    }
     if (lane == 0) bulk_wait_group0();
   }
 
