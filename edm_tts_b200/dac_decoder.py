@@ -115,7 +115,10 @@ class DACDecoder:
         ws = self._ws.get(key)
         if ws is not None:
             return ws
-        self._ws.clear()
+        # keep two geometries (a batch that does not divide into equal chunks alternates between two chunk sizes; re-allocating
+        # per chunk costs more than the kernels), drop the oldest beyond that: the buffers are large
+        while len(self._ws) >= 2:
+            self._ws.pop(next(iter(self._ws)))
         lens = self.lengths(T)
         dev = self.device
         ws = dict(lens=lens, zin=torch.empty(B, T, self.input_channel, device=dev, dtype=torch.bfloat16),

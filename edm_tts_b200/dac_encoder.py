@@ -98,7 +98,10 @@ class DACEncoder:
         ws = self._ws.get(key)
         if ws is not None:
             return ws
-        self._ws.clear()                       # one geometry at a time: the buffers are large
+        # keep two geometries (a batch that does not divide into equal chunks alternates between two chunk sizes; re-allocating
+        # per chunk costs more than the kernels), drop the oldest beyond that: the buffers are large
+        while len(self._ws) >= 2:
+            self._ws.pop(next(iter(self._ws)))
         lens = self.lengths(L_in)
         dev = self.device
         ws = dict(lens=lens, y=[], sx=[], sh=[], sd=[], sm=[])
