@@ -71,26 +71,34 @@ __device__ __forceinline__ void row_store_bf16(__nv_bfloat16* row, int lane, con
 
 // nn.LayerNorm over 1024 channels, eps 1e-5, fp32 statistics (two-pass, in registers).
 __device__ __forceinline__ void row_layernorm(float (&v)[32], const float* w, const float* b, int lane, float eps) {
-  float s = 0.f;
+  // packed f32x2 arithmetic (two channels per issue slot); the operations and their roundings are those of the scalar form, only
+  // the partial sums are kept per even / odd channel
+  uint64_t s2 = f2_pack(0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) s += v[i];
-  const float mean = warp_sum(s) * (1.0f / kD);
-  float q = 0.f;
+  for (int i = 0; i < 16; ++i) s2 = f2_add(s2, f2_pack(v[2 * i], v[2 * i + 1]));
+  float s0, s1;
+  f2_unpack(s2, s0, s1);
+  const float mean = warp_sum(s0 + s1) * (1.0f / kD);
+  const uint64_t nmean2 = f2_pack(-mean, -mean);
+  uint64_t q2 = f2_pack(0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float d = v[i] - mean;
-    q += d * d;
+  for (int i = 0; i < 16; ++i) {
+    const uint64_t d2 = f2_add(f2_pack(v[2 * i], v[2 * i + 1]), nmean2);
+    q2 = f2_fma(d2, d2, q2);
   }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / kD) + eps);
+  float q0, q1;
+  f2_unpack(q2, q0, q1);
+  const float rstd = rsqrtf(warp_sum(q0 + q1) * (1.0f / kD) + eps);
+  const uint64_t rstd2 = f2_pack(rstd, rstd);
   const float4* w4 = reinterpret_cast<const float4*>(w);
   const float4* b4 = reinterpret_cast<const float4*>(b);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float4 ww = __ldg(w4 + i * 32 + lane), bb = __ldg(b4 + i * 32 + lane);
-    v[4 * i + 0] = (v[4 * i + 0] - mean) * rstd * ww.x + bb.x;
-    v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * ww.y + bb.y;
-    v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * ww.z + bb.z;
-    v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * ww.w + bb.w;
+    const uint64_t lo = f2_fma(f2_mul(f2_add(f2_pack(v[4 * i + 0], v[4 * i + 1]), nmean2), rstd2), f2_pack(ww.x, ww.y), f2_pack(bb.x, bb.y));
+    const uint64_t hi = f2_fma(f2_mul(f2_add(f2_pack(v[4 * i + 2], v[4 * i + 3]), nmean2), rstd2), f2_pack(ww.z, ww.w), f2_pack(bb.z, bb.w));
+    f2_unpack(lo, v[4 * i + 0], v[4 * i + 1]);
+    f2_unpack(hi, v[4 * i + 2], v[4 * i + 3]);
   }
 }
 
