@@ -1,6 +1,8 @@
 """S2A decode throughput on B200: decoded codec frames/s for BASELINE.json's config 2 (B=64 x 10 s = 500 frames, full
-8-step first-level schedule + full pass, bf16 tensor cores) per GPU, weak-scaled over N GPUs (one process per GPU, no
-collective on the decode path; the codes are all-gathered once per step over NCCL).
+8-step first-level schedule + full pass, bf16 tensor cores) per GPU, weak-scaled over N GPUs (one process per GPU, batch-sharded
+through edm_tts_b200.runner.ShardedDecoder: no collective on the decode path, the int16 codes are all-gathered once per step over
+NCCL). Also in the line: the same global batch 512 split over the N GPUs (BASELINE config 3, `fixed_global_batch`), the eager-torch
+bf16-autocast incumbent on the same GPU (`gpu_incumbent`), single-utterance latency, and the secondary kernels.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
@@ -107,6 +109,35 @@ def cpu_oracle_fps(B, T, steps, repeats, threads):
     return B * T / best, times
 
 
+def gpu_incumbent_fps(dev, B, T, steps):
+    """What a user gets on this GPU without this repo: the reference's algorithm as eager torch ops under autocast(bf16), fp32
+    parameters (inference.py:33 runs the reference exactly so). The oracle restates that op sequence with torch library kernels
+    (F.linear, F.layer_norm, SDPA, conv1d), so it serves as the incumbent here; one warm-up + one timed decode of the bench batch."""
+    import torch
+
+    from oracle import s2a as os2a
+    from oracle.weights import OracleConfig, make_state_dict
+
+    cfg = OracleConfig()
+    sd = {k: v.to(dev) for k, v in make_state_dict(cfg, 0).items()}
+    g = torch.Generator(device=dev).manual_seed(5)
+    sem = torch.randint(0, cfg.num_semantic, (B, T), device=dev, generator=g)
+    cat = -torch.log(torch.empty(steps - 1, B * T, cfg.codebook_size, device=dev).exponential_(generator=g))
+    rem = -torch.log(-torch.log(torch.rand(steps - 1, B, T, device=dev, generator=g).clamp_(1e-7, 1 - 1e-7)))
+    times = []
+    with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+        for _ in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            os2a.infer_special(sd, cfg, sem, None, None, steps=steps, cat_gumbel=cat, remask_gumbel=rem, mode="fp32")
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+    del sd, cat, rem
+    torch.cuda.empty_cache()
+    return B * T / (times[-1] * 1e-3), times
+
+
 def run_reference(args):
     """--impl reference: the reference's algorithm on the host CPU (oracle port; the Python reference itself cannot
     travel to the GPU box), all host threads, one bounded sample per step: 1 utterance x 500 frames x 8 steps."""
@@ -181,23 +212,26 @@ def main():
     model = InjectionConformerModel(InjectionConformerConfig(), sd, device=dev)
     del sd
     B, T = B_PER_GPU, T_FRAMES
-    g = torch.Generator().manual_seed(1234 + rank)
-    sem_host = torch.randint(0, cfg.num_semantic, (B, T), generator=g).pin_memory()
-    codes_host = torch.empty(B, cfg.n_codebooks, T, dtype=torch.int64).pin_memory()
+    from edm_tts_b200.runner import ShardedDecoder, shard_bounds
+
+    # the global batch (64 utterances per GPU) is known to every rank; ShardedDecoder decodes this rank's contiguous shard with the
+    # Philox counters of the global rows and all-gathers the int16 codes, so every rank ends with the codes of all world * 64 rows
+    GB = world * B
+    sem_host = torch.randint(0, cfg.num_semantic, (GB, T), generator=torch.Generator().manual_seed(1234)).pin_memory()
+    codes_host = torch.empty(GB, cfg.n_codebooks, T, dtype=torch.int16).pin_memory()
     sem_dev = sem_host.to(dev)
-    gathered = [torch.empty(B, cfg.n_codebooks, T, device=dev, dtype=torch.int64) for _ in range(world)] if world > 1 else None
+    SEED = 7
+    sharded = ShardedDecoder(model.infer_special, keep_gather_dtype=True)
+    lo, hi = shard_bounds(GB, rank, world)
 
     def step_resident():
-        codes = model.infer_special(sem_dev, None, None, steps=DECODE_STEPS, temperature=1.0, seed=rank)
-        if world > 1:
-            dist.all_gather(gathered, codes)
-        return codes
+        return sharded(sem_dev, None, None, steps=DECODE_STEPS, temperature=1.0, seed=SEED)
 
     def step_e2e():
-        sd_ = sem_host.to(dev, non_blocking=True)
-        codes = model.infer_special(sd_, None, None, steps=DECODE_STEPS, temperature=1.0, seed=rank)
-        if world > 1:
-            dist.all_gather(gathered, codes)
+        # this rank's shard of the tokens host -> device, decode, gather, all codes device -> host (pinned buffers on both sides)
+        sd_ = torch.empty(GB, T, dtype=torch.int64, device=dev)
+        sd_[lo:hi].copy_(sem_host[lo:hi], non_blocking=True)
+        codes = sharded(sd_, None, None, steps=DECODE_STEPS, temperature=1.0, seed=SEED)
         codes_host.copy_(codes, non_blocking=True)
         return codes
 
@@ -225,8 +259,19 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item(), launches
 
+    first = None
     for _ in range(args.warmup):
-        step_resident()
+        first = step_resident()
+    # N-GPU == 1-GPU: rank 0 decodes the whole global batch alone and compares with what the sharded run gathered
+    sharded_ok = None
+    if world > 1:
+        if rank == 0:
+            alone = model.infer_special(sem_dev, None, None, steps=DECODE_STEPS, temperature=1.0, seed=SEED)
+            sharded_ok = bool(torch.equal(alone.to(torch.int16), first))
+            assert sharded_ok, "sharded decode differs from the single-GPU decode of the same rows"
+            del alone
+        sync_all()
+    del first
     sampler = ClockSampler(local)
     sampler.start()
     ms_total, launches = timed(step_resident, args.steps)          # the headline: no per-kernel instrumentation inside
@@ -245,6 +290,35 @@ def main():
     frames = world * B * T * args.steps
     value = frames / (ms_total * 1e-3)
     e2e = frames / (ms_e2e * 1e-3)
+
+    # BASELINE config 3: a fixed global batch of 512 x 10 s split over the N GPUs (strong scaling), same sharded path
+    FG = 512
+    sem512 = torch.randint(0, cfg.num_semantic, (FG, T), generator=torch.Generator().manual_seed(4321)).to(dev)
+    fixed_steps = 2
+
+    def step_fixed():
+        return sharded(sem512, None, None, steps=DECODE_STEPS, temperature=1.0, seed=SEED)
+
+    step_fixed()
+    ms_fixed, _ = timed(step_fixed, fixed_steps)
+    del sem512
+
+    # single-utterance latency (the reference's own call site, inference.py:43-48): B = 1, 150 frames, 8 steps, device time per decode
+    lat_ms = None
+    if rank == 0:
+        tok1 = sem_dev[:1, :150].contiguous()
+        for _ in range(3):
+            model.infer_special(tok1, None, None, steps=DECODE_STEPS, seed=SEED)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.edm_launch_count()
+        r0.record()
+        for _ in range(10):
+            model.infer_special(tok1, None, None, steps=DECODE_STEPS, seed=SEED)
+        r1.record()
+        torch.cuda.synchronize()
+        lat_ms = r0.elapsed_time(r1) / 10
+        lat_launches = (lib.edm_launch_count() - l0) // 10
     tf_peak, hbm_peak, peak_kind = peaks()
     traffic, traffic_src = ncu_traffic()
     # algorithmic bytes of the 8 GEMMs of one conformer block at M = B*T rows (operands read once, outputs written once,
@@ -323,11 +397,17 @@ def main():
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "frames": T, "prompt_frames": P_PROMPT, "decode_steps": DECODE_STEPS,
                    "weights": "random-init, reference architecture (configs/injection_conformer/base_config)",
                    "sampling_noise": "in-kernel Philox", "l2": "working set 3.5 GB per step >> 126 MB L2 (no flush needed)",
-                   "parallelism": f"batch-sharded x{world}, all_gather of codes per step" if world > 1 else "single GPU"},
+                   "parallelism": f"batch-sharded x{world} (runner.ShardedDecoder), one all_gather of the int16 codes per step" if world > 1 else "single GPU"},
         "clocks": sampler.result(),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": sem_host.numel() * 8 * world, "d2h_bytes_per_step": codes_host.numel() * 8 * world,
-                "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": sem_host.numel() * 8, "d2h_bytes_per_step": codes_host.numel() * 2 * world,
+                "ms_per_step": ms_e2e / args.steps,
+                "note": "whole job: every rank copies its shard of the int64 tokens in and the gathered int16 codes of all rows out"},
         "gpu_launches": int(launches) * world,
+        "sharded_equals_single_gpu": sharded_ok,
+        "fixed_global_batch": {"global_batch": FG, "per_gpu": FG // world, "frames": T, "decode_steps": DECODE_STEPS, "steps_timed": fixed_steps,
+                               "ms_per_step": ms_fixed / fixed_steps, "value": FG * T * fixed_steps / (ms_fixed * 1e-3), "unit": UNIT, "scaling": "strong",
+                               "workload": "BASELINE config 3: S2A decode of 512 x 10 s utterances batch-sharded over the GPUs of the run"},
+        "latency_b1_t150_s8_ms": lat_ms, "latency_b1_launches": lat_launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_pair_kernel (tcgen05 cta_group::2; all conformer / head GEMMs of the timed region)",
                      "achieved": gemm_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tf_peak, "traffic": traffic,
                      "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean of the 8 GEMMs of one block)",
@@ -359,6 +439,12 @@ def main():
                                     "frac_of_peak": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12 / tf_peak},
     }
     if not args.no_cpu_baseline:
+        del model
+        torch.cuda.empty_cache()
+        inc_fps, inc_ms = gpu_incumbent_fps(dev, B, T, DECODE_STEPS)
+        out["gpu_incumbent"] = {"value": inc_fps, "unit": UNIT, "ms_per_step": inc_ms[-1], "runs_ms": [round(t, 1) for t in inc_ms],
+                                "what": "the same decode (B=64 x 500 frames x 8 steps + full pass) as eager torch library kernels under autocast(bf16) on "
+                                        "this GPU: the reference's op sequence (oracle restatement), second of two runs, CUDA events"}
         threads = os.cpu_count() or 1
         fps, times = cpu_oracle_fps(1, 150, DECODE_STEPS, repeats=3, threads=threads)
         out["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",

@@ -16,7 +16,6 @@
 #include "dac_conv.cuh"
 #include "gemm.cuh"
 #include "kmeans.cuh"
-#include "rvq.cuh"
 #include "rvq_tc.cuh"
 
 using namespace edm;
@@ -55,9 +54,10 @@ struct ProfEntry {
   int kind;
   double work;
 };
-bool g_prof_on = false;
-std::vector<ProfEntry> g_prof;
-std::vector<cudaEvent_t> g_event_pool;
+// thread-local: the launching thread owns its timing state (a context is driven by one thread at a time)
+thread_local bool g_prof_on = false;
+thread_local std::vector<ProfEntry> g_prof;
+thread_local std::vector<cudaEvent_t> g_event_pool;
 
 cudaEvent_t prof_event() {
   if (!g_event_pool.empty()) {
@@ -90,26 +90,63 @@ struct ProfScope {
   }
 };
 
-int check_arch() {
-  static int cached = 1;  // 1 = unknown
-  if (cached != 1) return cached;
+// Everything cached about "the device" is keyed by the current device: one process may drive several GPUs (a context per device),
+// and cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting.
+constexpr int kMaxDevices = 64;
+int cur_device() {
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return cached = fail(EDM_ERR_CUDA, "no CUDA device");
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return cached = fail(EDM_ERR_CUDA, "cudaGetDeviceProperties failed");
-  if (prop.major != 10) return cached = fail(EDM_ERR_ARCH, "device sm_%d%d is not sm_100: this library has no fallback path", prop.major, prop.minor);
-  return cached = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+
+int check_arch() {
+  static std::atomic<int> cached[kMaxDevices];  // 0 = unknown, 1 = sm_100, 2 = something else
+  const int dev = cur_device();
+  int st = cached[dev].load(std::memory_order_relaxed);
+  if (st == 0) {
+    int major = 0, minor = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess)
+      return fail(EDM_ERR_CUDA, "no CUDA device");
+    st = major == 10 ? 1 : 2;
+    cached[dev].store(st, std::memory_order_relaxed);
+    if (st == 2) return fail(EDM_ERR_ARCH, "device sm_%d%d is not sm_100: this library has no fallback path", major, minor);
+  }
+  return st == 1 ? 0 : fail(EDM_ERR_ARCH, "device is not sm_100: this library has no fallback path");
 }
 
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = cur_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
 }
+
+// "has this call site configured its kernels on the current device yet?"
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool needed() const { return (mask.load(std::memory_order_acquire) >> cur_device() & 1ull) == 0; }
+  void done() { mask.fetch_or(1ull << cur_device(), std::memory_order_release); }
+};
+
+// Bring-up switches (environment variables) exist only in a -DEDM_BRINGUP build (tools/); the product library has none.
+#ifdef EDM_BRINGUP
+bool env_switch(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  return e == nullptr ? dflt : e[0] != '0';
+}
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e == nullptr ? dflt : atoi(e);
+}
+#else
+constexpr bool env_switch(const char*, bool dflt) { return dflt; }
+constexpr int env_int(const char*, int dflt) { return dflt; }
+#endif
 
 // ---------------------------------------------------------------------------------------------- TMA descriptors
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -174,82 +211,38 @@ int make_tmap_f32_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
 // Boustrophedon traversal: consecutive launches walk their rows / tiles in opposite directions, so a kernel starts with the part
 // of its input that its producer wrote last and that is still in the 126 MB L2 (the hand-offs of the decoder are 66-262 MB).
 int next_direction() {
-  static int enabled = -1;
-  static int dir = 0;
-  if (enabled < 0) {
-    const char* e = getenv("EDM_FLIP");  // bring-up switch: 0 = every kernel walks forward
-    enabled = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
+  static const bool enabled = env_switch("EDM_FLIP", true);
+  thread_local int dir = 0;
   if (!enabled) return 0;
   dir ^= 1;
   return dir;
 }
 
-bool gemm_use_pairs() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("EDM_GEMM_PAIR");  // bring-up switch: 0 = single-CTA 128x256 tiles, 1 = CTA-pair 256x256 tiles
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-// rows of a B-operand TMA box: a CTA of a pair loads half of the 256-row weight tile
-uint32_t gemm_b_box_rows() { return gemm_use_pairs() ? kGemmBN / 2 : kGemmBN; }
-// Weight operand of a GEMM: the tensor map of the large-M kernels (128- or 256-row boxes) and the 64-row-box map of the small-M kernel
+// Weight operand of a GEMM: the tensor map of the CTA-pair kernel (each CTA of a pair loads half of the 256-row weight tile) and the
+// 64-row-box map of the small-M kernel
 struct WMap {
   CUtensorMap big, small;
 };
-int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 int make_wmap(WMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld) {
-  if (int rc = make_tmap_2d(&m->big, ptr, rows, cols, ld, gemm_b_box_rows())) return rc;
+  if (rows % kGemmBN == 0) {
+    if (int rc = make_tmap_2d(&m->big, ptr, rows, cols, ld, kGemmBN / 2)) return rc;
+  } else {
+    memset(&m->big, 0, sizeof(m->big));  // N is not a multiple of 256: only the small-M kernel can take this weight
+  }
   return make_tmap_2d(&m->small, ptr, rows, cols, ld, kSmBN);
 }
-bool gemm_small_m() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("EDM_GEMM_SMALL");  // bring-up switch: 0 = always the large-M kernels
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-bool gemm_resid_tma() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("EDM_RESID_TMA");  // bring-up switch: 0 = residual add as red.global.add.v4.f32 from registers
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-
-int resid_tma_max_k() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("EDM_RESID_TMA_MAXK");  // bring-up knob: largest K whose residual epilogue goes through TMA reduce
-    v = e != nullptr ? atoi(e) : 2048;
-  }
-  return v;
-}
-
-bool gemm_out_tma() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("EDM_OUT_TMA");  // bring-up switch: 0 = bf16 epilogues store from registers
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  return v == 1;
-}
+bool gemm_small_m() { static const bool v = env_switch("EDM_GEMM_SMALL", true); return v; }
+bool gemm_resid_tma() { static const bool v = env_switch("EDM_RESID_TMA", true); return v; }
+int resid_tma_max_k() { static const int v = env_int("EDM_RESID_TMA_MAXK", 2048); return v; }
+bool gemm_out_tma() { static const bool v = env_switch("EDM_OUT_TMA", true); return v; }
 
 template <int EPI>
 int launch_gemm_t(const CUtensorMap& ma, const WMap& wm, const GemmParams& p_in, cudaStream_t st) {
   const CUtensorMap& mb = wm.big;
   GemmParams p = p_in;
   p.reverse = next_direction();
-  static bool attr_set = false;
-  if (!attr_set) {
-    EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_small_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmSmemBytes));
     if (EPI == EPI_RESID_F32)
@@ -260,55 +253,50 @@ int launch_gemm_t(const CUtensorMap& ma, const WMap& wm, const GemmParams& p_in,
       EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI_ROPE_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
     if (EPI == EPI_F32)
       EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_pair_kernel<EPI_F32_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
-    attr_set = true;
+    attr_once.done();
   }
   ProfScope prof(PK_GEMM, 2.0 * p.M * p.N * p.K, st);
+  const int sms = num_sms();
   {
-    // small M: the large tiles would leave most SMs without work while a few stream the weights (see gemm.cuh, small-M variant)
-    const int pair_tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (p.N / kGemmBN);
-    if (gemm_small_m() && pair_tiles * 4 <= num_sms()) {
+    // small M: the large tiles would leave most SMs without work while a few stream the weights (see gemm.cuh, small-M variant);
+    // N not a multiple of 256 (hidden sizes 384 / 512 of the text-to-semantic model): only the 64-column tiles fit
+    const int pair_tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((p.N + kGemmBN - 1) / kGemmBN);
+    if (p.N % kGemmBN != 0 || (gemm_small_m() && pair_tiles * 4 <= sms)) {
       p.reverse = 0;
       const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / kSmBN);
-      gemm_bf16_tn_small_kernel<EPI><<<tiles < num_sms() ? tiles : num_sms(), kSmThreads, kSmSmemBytes, st>>>(ma, wm.small, p);
+      gemm_bf16_tn_small_kernel<EPI><<<tiles < sms ? tiles : sms, kSmThreads, kSmSmemBytes, st>>>(ma, wm.small, p);
       EDM_LAUNCH_CHECK("gemm_bf16_tn_small");
       return 0;
     }
   }
-  if (gemm_use_pairs()) {
-    const int tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (p.N / kGemmBN);
-    const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-    // short-K residual GEMMs are epilogue-bound: their add leaves as TMA reduce boxes (0.113 -> 0.081 ms at K = 1024); at
-    // K = 4096 the mainloop hides the register-issued reductions and the 6-stage ring is worth more (0.202 vs 0.208 ms)
-    if (EPI == EPI_RESID_F32 && gemm_resid_tma() && p.K <= resid_tma_max_k() && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 4) % 16 == 0) {
-      CUtensorMap mc;
-      if (int rc = make_tmap_f32_2d(&mc, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-      gemm_bf16_tn_pair_kernel<EPI_RESID_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
-    } else if (EPI == EPI_F32 && gemm_out_tma() && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 4) % 16 == 0) {
-      CUtensorMap mc;  // fp32 logits leave as 32 x 32 TMA store boxes
-      if (int rc = make_tmap_f32_2d(&mc, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-      gemm_bf16_tn_pair_kernel<EPI_F32_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
-    } else if ((EPI == EPI_SWISH_BF16 || EPI == EPI_QKV_ROPE) && gemm_out_tma() && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 2) % 16 == 0) {
-      // bf16 tiles leave as TMA store boxes (whole 128-byte lines) instead of 16-byte stores from registers
-      CUtensorMap mc;
-      if (int rc = make_tmap_2d(&mc, p.out, p.M, p.N, p.ldo, 32)) return rc;
-      if (EPI == EPI_SWISH_BF16)
-        gemm_bf16_tn_pair_kernel<EPI_SWISH_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
-      else
-        gemm_bf16_tn_pair_kernel<EPI_ROPE_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
-    } else {
-      gemm_bf16_tn_pair_kernel<EPI><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, ma, p);
-    }
-    EDM_LAUNCH_CHECK("gemm_bf16_tn_pair");
-    return 0;
+  const int tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (p.N / kGemmBN);
+  const int pairs = tiles < sms / 2 ? tiles : sms / 2;
+  // short-K residual GEMMs are epilogue-bound: their add leaves as TMA reduce boxes (0.113 -> 0.081 ms at K = 1024); at
+  // K = 4096 the mainloop hides the register-issued reductions and the 6-stage ring is worth more (0.202 vs 0.208 ms)
+  if (EPI == EPI_RESID_F32 && gemm_resid_tma() && p.K <= resid_tma_max_k() && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 4) % 16 == 0) {
+    CUtensorMap mc;
+    if (int rc = make_tmap_f32_2d(&mc, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    gemm_bf16_tn_pair_kernel<EPI_RESID_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
+  } else if (EPI == EPI_F32 && gemm_out_tma() && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 4) % 16 == 0) {
+    CUtensorMap mc;  // fp32 logits leave as 32 x 32 TMA store boxes
+    if (int rc = make_tmap_f32_2d(&mc, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    gemm_bf16_tn_pair_kernel<EPI_F32_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
+  } else if ((EPI == EPI_SWISH_BF16 || EPI == EPI_QKV_ROPE) && gemm_out_tma() && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 2) % 16 == 0) {
+    // bf16 tiles leave as TMA store boxes (whole 128-byte lines) instead of 16-byte stores from registers
+    CUtensorMap mc;
+    if (int rc = make_tmap_2d(&mc, p.out, p.M, p.N, p.ldo, 32)) return rc;
+    if (EPI == EPI_SWISH_BF16)
+      gemm_bf16_tn_pair_kernel<EPI_SWISH_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
+    else
+      gemm_bf16_tn_pair_kernel<EPI_ROPE_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
+  } else {
+    gemm_bf16_tn_pair_kernel<EPI><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, ma, p);
   }
-  const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / kGemmBN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_tn_kernel<EPI><<<grid, kGemmThreads, kGemmSmemBytes, st>>>(ma, mb, p);
-  EDM_LAUNCH_CHECK("gemm_bf16_tn");
+  EDM_LAUNCH_CHECK("gemm_bf16_tn_pair");
   return 0;
 }
 int launch_gemm(int epi, const CUtensorMap& ma, const WMap& mb, const GemmParams& p, cudaStream_t st) {
-  if (p.M <= 0 || p.N % kGemmBN != 0 || p.N > kGemmMaxN || p.K % kGemmBK != 0 || p.K <= 0) return fail(EDM_ERR_INVALID, "gemm shape M=%d N=%d K=%d unsupported (N %% 256, N <= 8192, K %% 64)", p.M, p.N, p.K);
+  if (p.M <= 0 || p.N <= 0 || p.N % kSmBN != 0 || p.N > kGemmMaxN || p.K % kGemmBK != 0 || p.K <= 0) return fail(EDM_ERR_INVALID, "gemm shape M=%d N=%d K=%d unsupported (N %% 64, N <= 8192, K %% 64)", p.M, p.N, p.K);
   switch (epi) {
     case EPI_BF16: return launch_gemm_t<EPI_BF16>(ma, mb, p, st);
     case EPI_SWISH_BF16: return launch_gemm_t<EPI_SWISH_BF16>(ma, mb, p, st);
@@ -324,10 +312,10 @@ int launch_gemm(int epi, const CUtensorMap& ma, const WMap& mb, const GemmParams
 unsigned long long* g_attn_trace = nullptr;
 #endif
 int launch_attention(const CUtensorMap& mqkv, int B, int N, int H, void* out, uint32_t lbo, uint32_t sbo, uint32_t kstep, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     EDM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
-    attr_set = true;
+    attr_once.done();
   }
   AttnParams p;
   p.B = B; p.N = N; p.H = H;
@@ -362,16 +350,16 @@ int launch_ln(const LnParams& p_in, cudaStream_t st) {
 // glu_input: the kernel reads [B*N, 4096] and applies the GLU itself; otherwise the input is the already gated [B*N, 2048]
 // (the decoder's path: the GLU runs in the pointwise-conv GEMM epilogue) and the streaming kernel of conv_stream.cuh is used.
 int launch_conv(const ConvModParams& p, bool glu_input, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     EDM_CUDA(cudaFuncSetAttribute(conv_module_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
     EDM_CUDA(cudaFuncSetAttribute(conv_module_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kConvSmemBytes));
     EDM_CUDA(cudaFuncSetAttribute(conv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCsSmemBytes));
-    attr_set = true;
+    attr_once.done();
   }
   if (p.B <= 0 || p.N <= 0) return 0;
   ProfScope prof(PK_CONV, static_cast<double>(p.B) * p.N * (glu_input ? 12288.0 : 8192.0), st);
-  static const bool legacy = getenv("EDM_CONV_LEGACY") != nullptr;  // bring-up switch: tiled kernel on the gated input as well
+  static const bool legacy = env_switch("EDM_CONV_LEGACY", false);  // bring-up switch: tiled kernel on the gated input as well
   if (glu_input || legacy) {
     dim3 grid((p.N + kConvTT - 1) / kConvTT, p.B);
     if (glu_input)
@@ -479,16 +467,24 @@ extern "C" int edm_gemm_bf16(const void* a, long long lda, const void* b, long l
 #ifdef EDM_ATTN_TRACE
 extern "C" void edm_attn_set_trace(unsigned long long* p) { g_attn_trace = p; }
 #endif
-extern "C" int edm_attention_dbg(const void* qkv, int B, int N, int H, void* out, unsigned v_lbo, unsigned v_sbo,
-                                 unsigned v_kstep, void* stream) {
+namespace {
+int attention_entry(const void* qkv, int B, int N, int H, void* out, unsigned v_lbo, unsigned v_sbo, unsigned v_kstep, void* stream) {
   if (int rc = check_arch()) return rc;
   if (B <= 0 || N <= 0 || H <= 0) return fail(EDM_ERR_INVALID, "attention shape");
   CUtensorMap m;
   if (int rc = make_tmap_3d(&m, qkv, B, N, 3ull * H * 64)) return rc;
   return launch_attention(m, B, N, H, out, v_lbo, v_sbo, v_kstep, static_cast<cudaStream_t>(stream));
 }
+}  // namespace
+#ifdef EDM_BRINGUP
+// bring-up build only: the MN-major V descriptor fields (bytes) as arguments
+extern "C" int edm_attention_dbg(const void* qkv, int B, int N, int H, void* out, unsigned v_lbo, unsigned v_sbo,
+                                 unsigned v_kstep, void* stream) {
+  return attention_entry(qkv, B, N, H, out, v_lbo, v_sbo, v_kstep, stream);
+}
+#endif
 extern "C" int edm_attention(const void* qkv, int B, int N, int H, void* out, void* stream) {
-  return edm_attention_dbg(qkv, B, N, H, out, 1024, 1024, 2048, stream);
+  return attention_entry(qkv, B, N, H, out, 1024, 1024, 2048, stream);
 }
 
 extern "C" int edm_layernorm(const void* in, int in_is_bf16, int rows, const float* w1, const float* b1, const float* w2,
@@ -512,7 +508,7 @@ extern "C" int edm_sample(const float* logits, long long ld, int rows, const flo
                           unsigned step, const int* forced_ids, int* ids, float* logp, int T, int Q, int out_q_stride, int out_q0, void* stream) {
   if (int rc = check_arch()) return rc;
   SampleParams p;
-  p.logits = logits; p.ld = ld; p.rows = rows; p.noise = noise; p.use_philox = use_philox; p.seed = seed; p.step = step; p.row0 = 0;
+  p.logits = logits; p.ld = ld; p.rows = rows; p.noise = noise; p.use_philox = use_philox; p.seed = seed; p.seed_dev = nullptr; p.step = step; p.row0 = 0;
   p.forced_ids = forced_ids; p.ids = ids; p.ids_raw = nullptr; p.logp = logp; p.T = T; p.Q = Q; p.out_q_stride = out_q_stride; p.out_q0 = out_q0;
   return launch_sample(p, static_cast<cudaStream_t>(stream));
 }
@@ -522,42 +518,28 @@ extern "C" int edm_remask(const float* logp, const float* gumbel, const uint8_t*
   if (int rc = check_arch()) return rc;
   if (T > kRemaskMaxT) return fail(EDM_ERR_INVALID, "remask supports T <= %d", kRemaskMaxT);
   RemaskParams p;
-  p.logp = logp; p.gumbel = gumbel; p.mask_old = mask_old; p.mask_new = mask_new; p.forced_mask = forced_mask;
-  p.T = T; p.ratio = ratio; p.temp_ratio = temp_ratio; p.seed = seed; p.step = step; p.row0 = 0;
+  p.logp = logp; p.gumbel = gumbel; p.mask_old = mask_old; p.mask_new = mask_new; p.mask_raw = nullptr; p.forced_mask = forced_mask;
+  p.T = T; p.ratio = ratio; p.temp_ratio = temp_ratio; p.seed = seed; p.seed_dev = nullptr; p.step = step; p.row0 = 0;
   remask_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   EDM_LAUNCH_CHECK("remask");
   return 0;
 }
 
-extern "C" int edm_rvq_encode(const void* z, int z_is_bf16, int B, int T, int n_levels, const float* w_in_t, const float* b_in,
-                              const float* cb_norm, const float* cb_n2, const float* g, long long* codes, const long long* forced,
-                              float* latents, void* stream) {
-  if (int rc = check_arch()) return rc;
-  if (n_levels < 1 || n_levels > kRvqLevels || B <= 0 || T <= 0) return fail(EDM_ERR_INVALID, "rvq shape B=%d T=%d levels=%d", B, T, n_levels);
-  static bool attr_set = false;
-  if (!attr_set) {
-    EDM_CUDA(cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRvqSmemBytes));
-    attr_set = true;
-  }
-  RvqParams p;
-  p.z = z; p.z_is_bf16 = z_is_bf16; p.B = B; p.T = T; p.n_levels = n_levels; p.w_in_t = w_in_t; p.b_in = b_in;
-  p.cb_norm = cb_norm; p.cb_n2 = cb_n2; p.g = g; p.codes = codes; p.forced = forced; p.latents = latents;
-  dim3 grid((T + kRvqFrames - 1) / kRvqFrames, B);
-  rvq_encode_kernel<<<grid, 256, kRvqSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
-  EDM_LAUNCH_CHECK("rvq_encode");
-  return 0;
-}
-
-// bring-up knob (tools/bringup_ops.py rvqtc): descriptor strides of the MN-major tf32 A operand
+// descriptor strides (bytes) of the projection's MN-major tf32 A operand
+#ifdef EDM_BRINGUP
+// bring-up build only (tools/bringup_ops.py rvqtc): stride sweep, search kernel alone on given latents, scan without compare work
 unsigned g_rvq_a_lbo = 4096, g_rvq_a_sbo = 512;
-int g_rvq_skip_project = 0;  // 1: e_ws is taken as given (tests the search kernel alone)
-int g_rvq_scan_probe = 0;    // 1: search kernel without the compare work (timing floor of TMA + MMA + TMEM reads)
+int g_rvq_skip_project = 0, g_rvq_scan_probe = 0;
 extern "C" void edm_rvq_tc_debug(unsigned lbo, unsigned sbo, int skip_project, int scan_probe) {
   g_rvq_a_lbo = lbo;
   g_rvq_a_sbo = sbo;
   g_rvq_skip_project = skip_project;
   g_rvq_scan_probe = scan_probe;
 }
+#else
+constexpr unsigned g_rvq_a_lbo = 4096, g_rvq_a_sbo = 512;
+constexpr int g_rvq_skip_project = 0, g_rvq_scan_probe = 0;
+#endif
 
 extern "C" int edm_rvq_encode_tc(const void* z, int z_is_bf16, int B, int T, int n_levels, const float* w_hi, const float* w_lo, const float* b_in,
                                  const float* cb_packed, const float* g, float* e_ws, long long* codes, const long long* forced,
@@ -566,13 +548,13 @@ extern "C" int edm_rvq_encode_tc(const void* z, int z_is_bf16, int B, int T, int
   if (n_levels < 1 || n_levels > kRvqLevels || B <= 0 || T <= 0) return fail(EDM_ERR_INVALID, "rvq shape B=%d T=%d levels=%d", B, T, n_levels);
   if (T % (z_is_bf16 ? 8 : 4) != 0)
     return fail(EDM_ERR_INVALID, "rvq_encode_tc needs 16-byte rows for TMA (T %% %d == 0), got T=%d: pad the time axis", z_is_bf16 ? 8 : 4, T);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     EDM_CUDA(cudaFuncSetAttribute(rvq_project_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmemBytes));
     EDM_CUDA(cudaFuncSetAttribute(rvq_project_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmemBytes));
     EDM_CUDA(cudaFuncSetAttribute(rvq_search_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemBytes));
     EDM_CUDA(cudaFuncSetAttribute(rvq_search_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemBytes));
-    attr_set = true;
+    attr_once.done();
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CUtensorMap mz, mwh, mwl, mcb;
@@ -624,10 +606,10 @@ extern "C" int edm_kmeans_assign(const float* x, long long n_frames, int dim, co
   if (n_frames <= 0) return 0;
   if (dim <= 0 || dim % kKmKc != 0 || n_centroids <= 0 || n_centroids % kKmCodes != 0 || n_centroids > kKmMaxCentroids || n_frames > 0x7fffffffLL)
     return fail(EDM_ERR_INVALID, "kmeans_assign shape frames=%lld dim=%d centroids=%d unsupported (dim %% 32, centroids %% 256, <= 4096)", n_frames, dim, n_centroids);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     EDM_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKmSmemBytes));
-    attr_set = true;
+    attr_once.done();
   }
   CUtensorMap mx, mh, ml;
   if (int rc = make_tmap_f32_2d(&mx, x, static_cast<uint64_t>(n_frames), dim, dim, kKmFrames)) return rc;
@@ -681,10 +663,10 @@ int make_tmap_conv_out(CUtensorMap* m, const void* ptr, bool f32, uint64_t B, ui
 
 template <int NT>
 int launch_dac_conv(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& ms, DacConvParams& p, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     EDM_CUDA(cudaFuncSetAttribute(dac_conv_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, dac_conv_smem_bytes<NT>()));
-    attr_set = true;
+    attr_once.done();
   }
   p.n_tiles_n = p.c_out / NT;
   const long long tiles = static_cast<long long>(p.B) * p.tiles_per_batch * p.n_tiles_n;
@@ -739,10 +721,10 @@ namespace {
 template <int C>
 int launch_dac_resunit(const CUtensorMap& ma, const CUtensorMap& m7, const CUtensorMap& m1, const CUtensorMap& my, const CUtensorMap& ms,
                        const DacResUnitParams& p, int s_row_off, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
     EDM_CUDA(cudaFuncSetAttribute(dac_resunit_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, DacResUnitCfg<C>::kSmemBytes));
-    attr_set = true;
+    attr_once.done();
   }
   const long long tiles = static_cast<long long>(p.B) * p.tiles_per_batch;
   if (tiles > 0x7fffffffLL) return fail(EDM_ERR_INVALID, "dac_resunit: too many tiles");
@@ -782,10 +764,10 @@ extern "C" int edm_dac_resunit(const void* a, long long a_batch_stride, int B, i
 #endif
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (channels == 192) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (attr_once.needed()) {
       EDM_CUDA(cudaFuncSetAttribute(dac_resunit_wide_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, DacResUnitWideCfg<192>::kSmemBytes));
-      attr_set = true;
+      attr_once.done();
     }
     const long long tiles = static_cast<long long>(p.B) * p.tiles_per_batch;
     const int grid = tiles < num_sms() ? static_cast<int>(tiles) : num_sms();
@@ -793,16 +775,12 @@ extern "C" int edm_dac_resunit(const void* a, long long a_batch_stride, int B, i
     EDM_LAUNCH_CHECK("dac_resunit_wide");
     return 0;
   }
-  static int halo_mode = -2;   // bring-up switch EDM_DAC_HALO=0: seven shifted TMA boxes per tile (first form) for 64 channels too
-  if (halo_mode == -2) {
-    const char* e = getenv("EDM_DAC_HALO");
-    halo_mode = (e != nullptr && e[0] == '0') ? 0 : 1;
-  }
-  if (channels == 64 && halo_mode == 1 && dilation >= 1 && 128 + 6 * dilation <= kRu64HaloRows) {
-    static bool attr_set = false;
-    if (!attr_set) {
+  static const bool halo_mode = env_switch("EDM_DAC_HALO", true);  // bring-up switch, 0: seven shifted TMA boxes per tile (first form) for 64 channels too
+  if (channels == 64 && halo_mode && dilation >= 1 && 128 + 6 * dilation <= kRu64HaloRows) {
+    static DeviceOnce attr_once;
+    if (attr_once.needed()) {
       EDM_CUDA(cudaFuncSetAttribute(dac_resunit64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRu64SmemBytes));
-      attr_set = true;
+      attr_once.done();
     }
     CUtensorMap mh, m7b;
     if (int rc = make_tmap_conv_a(&mh, a, B, rows, channels, static_cast<uint64_t>(a_batch_stride), 128 + 6 * dilation)) return rc;
@@ -900,7 +878,9 @@ struct edm_s2a_ctx {
   float *x_in, *x, *coarse_out[4], *logits, *coarse_logits, *fine_logits, *logp;
   __nv_bfloat16 *z, *h, *qkv, *g, *zt, *fine_h, *fine_z;
   int *ids, *ids_raw, *pred_codes, *pred_raw, *fine_codes, *sem_tokens, *sem_prompt, *ac_prompt;
-  uint8_t *mask_a, *mask_b;
+  uint8_t *mask_a, *mask_b, *mask_raw;
+  const float* prompt_proj = nullptr;            // optional caller-projected prompt injections [n_inj, B*P, 1024] (edm_s2a_set_prompt_injections)
+  const unsigned long long* seed_dev = nullptr;  // optional device-resident seed offset (edm_s2a_set_seed_buffer)
   int ac_levels = 0;
   long long batch_offset = 0;  // global index of this context's first sequence (Philox counters)
   bool mask_in_a = true;  // which buffer holds the current mask
@@ -1093,13 +1073,14 @@ size_t carve(edm_s2a_ctx* c, uint8_t* base, int B, int T, int P, bool assign) {
   int* ac_prompt = k.take<int>(static_cast<size_t>(B) * 12 * (P > 0 ? P : 1));
   uint8_t* mask_a = k.take<uint8_t>(Mt);
   uint8_t* mask_b = k.take<uint8_t>(Mt);
+  uint8_t* mask_raw = k.take<uint8_t>(Mt);
   if (assign) {
     c->x_in = x_in; c->x = x;
     for (int i = 0; i < 4; ++i) c->coarse_out[i] = co[i];
     c->z = z; c->h = h; c->qkv = qkv; c->g = g; c->zt = zt; c->logits = logits; c->coarse_logits = coarse_logits;
     c->fine_h = fine_h; c->fine_z = fine_z; c->fine_logits = fine_logits; c->logp = logp; c->ids = ids; c->ids_raw = ids_raw;
     c->pred_codes = pred; c->pred_raw = pred_raw; c->fine_codes = fine_codes; c->sem_tokens = sem_tokens; c->sem_prompt = sem_prompt;
-    c->ac_prompt = ac_prompt; c->mask_a = mask_a; c->mask_b = mask_b;
+    c->ac_prompt = ac_prompt; c->mask_a = mask_a; c->mask_b = mask_b; c->mask_raw = mask_raw;
   }
   return align_up(k.off, 1024);
 }
@@ -1120,6 +1101,7 @@ extern "C" int edm_s2a_bind(edm_s2a_ctx* c, void* workspace, size_t bytes, int B
   carve(c, static_cast<uint8_t*>(workspace), B, T, P, true);
   c->ws = static_cast<uint8_t*>(workspace); c->ws_bytes = bytes;
   c->B = B; c->T = T; c->P = P; c->N = P + T; c->M = B * (P + T); c->Mt = B * T;
+  c->prompt_proj = nullptr;
   int rc = 0;
   rc = rc ? rc : make_tmap_2d(&c->m_z, c->z, c->M, 1024, 1024, kGemmBM);
   rc = rc ? rc : make_tmap_2d(&c->m_h, c->h, c->M, 4096, 4096, kGemmBM);
@@ -1143,7 +1125,7 @@ extern "C" void* edm_s2a_buffer(edm_s2a_ctx* c, const char* name, size_t* bytes)
       {"logits", c->logits, Mt * 1024 * 4}, {"coarse_logits", c->coarse_logits, 4 * Mt * 1024 * 4},
       {"fine_logits", c->fine_logits, Mt * c->n_fine * 1024 * 4}, {"logp", c->logp, Mt * 4}, {"ids", c->ids, Mt * 4},
       {"ids_raw", c->ids_raw, Mt * 4}, {"pred_codes", c->pred_codes, Mt * 16}, {"pred_raw", c->pred_raw, Mt * 16},
-      {"fine_codes", c->fine_codes, Mt * c->n_fine * 4}, {"mask", c->mask_cur(), Mt}};
+      {"fine_codes", c->fine_codes, Mt * c->n_fine * 4}, {"mask", c->mask_cur(), Mt}, {"mask_raw", c->mask_raw, Mt}};
   for (auto& e : tab)
     if (strcmp(e.n, name) == 0) {
       if (bytes) *bytes = e.b;
@@ -1168,6 +1150,7 @@ extern "C" int edm_s2a_build_input(edm_s2a_ctx* c, const int* sem_tokens, const 
   p.x = c->x_in; p.sem_tokens = c->sem_tokens; p.sem_prompt = c->P > 0 ? c->sem_prompt : nullptr; p.ac_prompt = c->P > 0 ? c->ac_prompt : nullptr;
   p.ac_prompt_levels = ac_levels; p.sem_emb = c->gwf(G_SEM_EMB); p.mask_token = c->gwf(G_MASK_TOKEN); p.feat_table = c->gwf(G_FEAT_TABLE);
   p.feat_const = c->gwf(G_FEAT_CONST); p.fp_ln_w = c->gwf(G_FP_LN_W); p.fp_ln_b = c->gwf(G_FP_LN_B); p.B = c->B; p.T = c->T; p.P = c->P; p.eps = 1e-5f;
+  p.num_semantic = c->cfg.num_semantic;
   build_input_kernel<<<(c->M + 7) / 8, 256, 0, st>>>(p);
   EDM_LAUNCH_CHECK("build_input");
   c->mask_in_a = true;
@@ -1198,6 +1181,18 @@ extern "C" int edm_s2a_first_level(edm_s2a_ctx* c, const float* x_in, void* stre
   return launch_gemm(EPI_F32, c->m_zt, c->head_map, p, st);
 }
 
+extern "C" int edm_s2a_set_prompt_injections(edm_s2a_ctx* c, const float* proj) {
+  if (c == nullptr) return fail(EDM_ERR_INVALID, "null context");
+  c->prompt_proj = proj;
+  return 0;
+}
+
+extern "C" int edm_s2a_set_seed_buffer(edm_s2a_ctx* c, const unsigned long long* seed_dev) {
+  if (c == nullptr) return fail(EDM_ERR_INVALID, "null context");
+  c->seed_dev = seed_dev;
+  return 0;
+}
+
 extern "C" int edm_s2a_set_batch_offset(edm_s2a_ctx* c, long long batch_offset) {
   if (c == nullptr || batch_offset < 0) return fail(EDM_ERR_INVALID, "batch offset");
   c->batch_offset = batch_offset;
@@ -1208,10 +1203,12 @@ extern "C" int edm_s2a_step(edm_s2a_ctx* c, int step, int steps, float temperatu
                             const float* remask_noise, const int* forced_ids, const uint8_t* forced_mask, void* stream) {
   if (c == nullptr || !c->bound) return fail(EDM_ERR_STATE, "context not bound");
   if (steps < 2 || step < 0 || step >= steps) return fail(EDM_ERR_INVALID, "step %d of %d", step, steps);
+  // the reference's take_along_dim(sorted_confidence, mask_len >= 1) is out of range for a single frame (utils/utils.py:56)
+  if (c->T < 2 && step < steps - 1 && forced_mask == nullptr) return fail(EDM_ERR_INVALID, "re-masking needs T >= 2 frames (T=%d, steps=%d)", c->T, steps);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool last = step == steps - 1;
   SampleParams sp;
-  sp.logits = c->logits; sp.ld = 1024; sp.rows = c->Mt; sp.noise = last ? nullptr : cat_noise; sp.use_philox = last ? 0 : 1; sp.seed = seed;
+  sp.logits = c->logits; sp.ld = 1024; sp.rows = c->Mt; sp.noise = last ? nullptr : cat_noise; sp.use_philox = last ? 0 : 1; sp.seed = seed; sp.seed_dev = c->seed_dev;
   sp.step = static_cast<unsigned>(step); sp.row0 = c->batch_offset * c->T; sp.forced_ids = forced_ids; sp.ids = c->ids; sp.ids_raw = c->ids_raw; sp.logp = last ? nullptr : c->logp;
   sp.T = c->T; sp.Q = 1; sp.out_q_stride = 1; sp.out_q0 = 0;
   if (int rc = launch_sample(sp, st)) return rc;
@@ -1221,9 +1218,9 @@ extern "C" int edm_s2a_step(edm_s2a_ctx* c, int step, int steps, float temperatu
     // python: mask_ratio is a double; torch multiplies float32 tensors by float32(ratio)
     const double ratio_d = std::cos(M_PI / 2.0 * (static_cast<double>(step + 1) / static_cast<double>(steps)));
     RemaskParams rp;
-    rp.logp = c->logp; rp.gumbel = remask_noise; rp.mask_old = m_old; rp.mask_new = c->mask_next(); rp.forced_mask = forced_mask;
+    rp.logp = c->logp; rp.gumbel = remask_noise; rp.mask_old = m_old; rp.mask_new = c->mask_next(); rp.mask_raw = c->mask_raw; rp.forced_mask = forced_mask;
     rp.T = c->T; rp.ratio = static_cast<float>(ratio_d); rp.temp_ratio = static_cast<float>(static_cast<double>(temperature) * ratio_d);
-    rp.seed = seed; rp.step = static_cast<unsigned>(step); rp.row0 = c->batch_offset * c->T;
+    rp.seed = seed; rp.seed_dev = c->seed_dev; rp.step = static_cast<unsigned>(step); rp.row0 = c->batch_offset * c->T;
     remask_kernel<<<c->B, 256, 0, st>>>(rp);
     EDM_LAUNCH_CHECK("remask");
     m_new = c->mask_next();
@@ -1231,7 +1228,7 @@ extern "C" int edm_s2a_step(edm_s2a_ctx* c, int step, int steps, float temperatu
   UpdateInputParams up;
   up.x = c->x_in; up.sem_tokens = c->sem_tokens; up.ids = c->ids; up.mask_old = m_old; up.mask_new = m_new; up.sem_emb = c->gwf(G_SEM_EMB);
   up.mask_token = c->gwf(G_MASK_TOKEN); up.feat_table = c->gwf(G_FEAT_TABLE); up.feat_const = c->gwf(G_FEAT_CONST);
-  up.fp_ln_w = c->gwf(G_FP_LN_W); up.fp_ln_b = c->gwf(G_FP_LN_B); up.B = c->B; up.T = c->T; up.P = c->P; up.eps = 1e-5f;
+  up.fp_ln_w = c->gwf(G_FP_LN_W); up.fp_ln_b = c->gwf(G_FP_LN_B); up.B = c->B; up.T = c->T; up.P = c->P; up.eps = 1e-5f; up.num_semantic = c->cfg.num_semantic;
   update_input_kernel<<<(c->Mt + 7) / 8, 256, 0, st>>>(up);
   EDM_LAUNCH_CHECK("update_input");
   if (!last) c->mask_in_a = !c->mask_in_a;
@@ -1268,12 +1265,13 @@ extern "C" int edm_s2a_full_pass(edm_s2a_ctx* c, const float* x_in, const int* f
       if (int rc = launch_gemm(EPI_F32, c->m_zt, c->head_map, p, st)) return rc;
     }
     SampleParams sp;
-    sp.logits = lk; sp.ld = 1024; sp.rows = c->Mt; sp.noise = nullptr; sp.use_philox = 0; sp.seed = 0; sp.step = 0; sp.row0 = 0; sp.forced_ids = forced_coarse;
+    sp.logits = lk; sp.ld = 1024; sp.rows = c->Mt; sp.noise = nullptr; sp.use_philox = 0; sp.seed = 0; sp.seed_dev = nullptr; sp.step = 0; sp.row0 = 0; sp.forced_ids = forced_coarse;
     sp.ids = c->pred_codes; sp.ids_raw = c->pred_raw; sp.logp = nullptr; sp.T = c->T; sp.Q = 1; sp.out_q_stride = 4; sp.out_q0 = k;
     if (int rc = launch_sample(sp, st)) return rc;
     InjectParams ip;
     ip.x = c->x; ip.cur_out = c->coarse_out[k]; ip.prev_out = (k > 0 && cfg.residual) ? c->coarse_out[k - 1] : nullptr;
     ip.pred_codes = c->pred_codes; ip.ac_prompt = c->P > 0 ? c->ac_prompt : nullptr; ip.ac_prompt_levels = c->ac_levels;
+    ip.prompt_proj = (c->P > 0 && c->prompt_proj != nullptr) ? c->prompt_proj + static_cast<size_t>(k) * c->B * c->P * 1024 : nullptr;
     for (int i = 0; i < 4; ++i) ip.tables[i] = c->gwf(G_INJ_TABLE) + (static_cast<size_t>(k) * 4 + i) * 1024 * 1024;
     ip.inj_const = c->gwf(G_INJ_CONST) + k * 1024; ip.ln_w = c->gwf(G_INJ_LN_W) + k * 1024; ip.ln_b = c->gwf(G_INJ_LN_B) + k * 1024;
     ip.level = k; ip.B = c->B; ip.T = c->T; ip.P = c->P; ip.eps = 1e-5f;
@@ -1305,7 +1303,7 @@ extern "C" int edm_s2a_full_pass(edm_s2a_ctx* c, const float* x_in, const int* f
   }
   {
     SampleParams sp;
-    sp.logits = c->fine_logits; sp.ld = 1024; sp.rows = c->Mt * nf; sp.noise = nullptr; sp.use_philox = 0; sp.seed = 0; sp.step = 0; sp.row0 = 0; sp.forced_ids = nullptr;
+    sp.logits = c->fine_logits; sp.ld = 1024; sp.rows = c->Mt * nf; sp.noise = nullptr; sp.use_philox = 0; sp.seed = 0; sp.seed_dev = nullptr; sp.step = 0; sp.row0 = 0; sp.forced_ids = nullptr;
     sp.ids = c->fine_codes; sp.ids_raw = nullptr; sp.logp = nullptr; sp.T = c->T; sp.Q = nf; sp.out_q_stride = nf; sp.out_q0 = 0;
     if (int rc = launch_sample(sp, st)) return rc;
   }

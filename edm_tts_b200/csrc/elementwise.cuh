@@ -11,6 +11,10 @@ constexpr int kD = 1024;        // hidden size
 constexpr int kConvC = 2048;    // conv-module inner channels
 constexpr int kV = 1024;        // codebook size (logit width)
 
+// Token / code indices come from the caller: the kernels keep them inside their tables (memory safety); range *validation* with an
+// IndexError, as F.embedding raises in the reference, is done by the host mirror before the launch (the C ABI never synchronises).
+__device__ __forceinline__ int clamp_index(int i, int n) { return min(max(i, 0), n - 1); }
+
 // lane l of a warp owns columns {i*128 + 4*l .. +3 : i = 0..7}
 __device__ __forceinline__ void row_load_f32(const float* row, int lane, float (&v)[32]) {
   const float4* r4 = reinterpret_cast<const float4*>(row);
@@ -312,6 +316,7 @@ struct BuildInputParams {
   const float* feat_const;         // [1024]
   const float *fp_ln_w, *fp_ln_b;  // acoustic_feat_proj.1
   int B, T, P;
+  int num_semantic;                // rows of sem_emb
   float eps;
 };
 
@@ -323,13 +328,13 @@ __global__ void __launch_bounds__(256) build_input_kernel(const BuildInputParams
   const int b = static_cast<int>(row / N), n = static_cast<int>(row % N);
   float v[32];
   if (n < p.P) {
-    const int code = p.ac_prompt[(static_cast<long long>(b) * p.ac_prompt_levels + 0) * p.P + n];
+    const int code = clamp_index(p.ac_prompt[(static_cast<long long>(b) * p.ac_prompt_levels + 0) * p.P + n], kV);
     row_load_f32_ldg(p.feat_table + static_cast<long long>(code) * kD, lane, v);
     row_add_f32_ldg(p.feat_const, lane, v);
     row_layernorm(v, p.fp_ln_w, p.fp_ln_b, lane, p.eps);
-    row_add_f32_ldg(p.sem_emb + static_cast<long long>(p.sem_prompt[static_cast<long long>(b) * p.P + n]) * kD, lane, v);
+    row_add_f32_ldg(p.sem_emb + static_cast<long long>(clamp_index(p.sem_prompt[static_cast<long long>(b) * p.P + n], p.num_semantic)) * kD, lane, v);
   } else {
-    row_load_f32_ldg(p.sem_emb + static_cast<long long>(p.sem_tokens[static_cast<long long>(b) * p.T + (n - p.P)]) * kD, lane, v);
+    row_load_f32_ldg(p.sem_emb + static_cast<long long>(clamp_index(p.sem_tokens[static_cast<long long>(b) * p.T + (n - p.P)], p.num_semantic)) * kD, lane, v);
     row_add_f32_ldg(p.mask_token, lane, v);
   }
   row_store_f32(p.x + row * kD, lane, v);
@@ -350,6 +355,7 @@ struct UpdateInputParams {
   const float* feat_const;
   const float *fp_ln_w, *fp_ln_b;
   int B, T, P;
+  int num_semantic;
   float eps;
 };
 
@@ -365,11 +371,11 @@ __global__ void __launch_bounds__(256) update_input_kernel(const UpdateInputPara
   if (now) {
     row_load_f32_ldg(p.mask_token, lane, v);
   } else {
-    row_load_f32_ldg(p.feat_table + static_cast<long long>(p.ids[r]) * kD, lane, v);
+    row_load_f32_ldg(p.feat_table + static_cast<long long>(clamp_index(p.ids[r], kV)) * kD, lane, v);
     row_add_f32_ldg(p.feat_const, lane, v);
     row_layernorm(v, p.fp_ln_w, p.fp_ln_b, lane, p.eps);
   }
-  row_add_f32_ldg(p.sem_emb + static_cast<long long>(p.sem_tokens[r]) * kD, lane, v);
+  row_add_f32_ldg(p.sem_emb + static_cast<long long>(clamp_index(p.sem_tokens[r], p.num_semantic)) * kD, lane, v);
   row_store_f32(p.x + (static_cast<long long>(b) * (p.P + p.T) + p.P + t) * kD, lane, v);
 }
 
@@ -385,6 +391,7 @@ struct InjectParams {
   const int* pred_codes;    // [B, 4, T]
   const int* ac_prompt;     // [B, Qp, P] or nullptr
   int ac_prompt_levels;
+  const float* prompt_proj; // [B, P, 1024] or nullptr: Linear_k(prompt feature) given by the caller (feature-valued injections)
   const float* tables[4];   // inj_table[k][i] : [1024 codes, 1024]
   const float* inj_const;   // [1024]
   const float *ln_w, *ln_b; // project_injection[k].1
@@ -400,14 +407,18 @@ __global__ void __launch_bounds__(256) inject_kernel(const InjectParams p) {
   if (row >= static_cast<long long>(p.B) * N) return;
   const int b = static_cast<int>(row / N), n = static_cast<int>(row % N);
   float v[32];
-  row_load_f32_ldg(p.inj_const, lane, v);
-  for (int i = 0; i <= p.level; ++i) {
-    int code;
-    if (n < p.P)
-      code = p.ac_prompt[(static_cast<long long>(b) * p.ac_prompt_levels + i) * p.P + n];
-    else
-      code = p.pred_codes[(static_cast<long long>(b) * 4 + i) * p.T + (n - p.P)];
-    row_add_f32_ldg(p.tables[i] + static_cast<long long>(code) * kD, lane, v);
+  if (n < p.P && p.prompt_proj != nullptr) {
+    row_load_f32_ldg(p.prompt_proj + (static_cast<long long>(b) * p.P + n) * kD, lane, v);
+  } else {
+    row_load_f32_ldg(p.inj_const, lane, v);
+    for (int i = 0; i <= p.level; ++i) {
+      int code;
+      if (n < p.P)
+        code = p.ac_prompt[(static_cast<long long>(b) * p.ac_prompt_levels + i) * p.P + n];
+      else
+        code = p.pred_codes[(static_cast<long long>(b) * 4 + i) * p.T + (n - p.P)];
+      row_add_f32_ldg(p.tables[i] + static_cast<long long>(clamp_index(code, kV)) * kD, lane, v);
+    }
   }
   row_layernorm(v, p.ln_w, p.ln_b, lane, p.eps);
   float o[32];
@@ -450,6 +461,7 @@ struct SampleParams {
   const float* noise;       // [rows, 1024] Gumbel noise (parity runs) or nullptr
   int use_philox;           // noise == nullptr && use_philox: in-kernel Gumbel noise
   unsigned long long seed;
+  const unsigned long long* seed_dev;  // when set, *seed_dev is added to seed (a captured CUDA graph draws fresh noise per replay)
   unsigned int step;
   long long row0;           // global index of row 0 (keeps the Philox stream independent of batch chunking / sharding)
   const int* forced_ids;    // teacher forcing (parity runs) or nullptr
@@ -490,11 +502,12 @@ __global__ void __launch_bounds__(256) sample_kernel(const SampleParams p) {
       }
     }
   } else if (p.use_philox) {
+    const unsigned long long seed = p.seed + (p.seed_dev != nullptr ? *p.seed_dev : 0ull);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const uint4 bits = philox4x32_10(make_uint4(static_cast<uint32_t>(p.row0 + row), static_cast<uint32_t>(i * 32 + lane), p.step,
                                                   static_cast<uint32_t>((p.row0 + row) >> 32)),
-                                       make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32)));
+                                       make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
       const uint32_t bb[4] = {bits.x, bits.y, bits.z, bits.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -526,12 +539,15 @@ __global__ void __launch_bounds__(256) sample_kernel(const SampleParams p) {
       best_idx = oi;
     }
   }
+  // a row without any finite maximum (all NaN / all -inf) never updates best_idx: id 0, as torch.argmax gives for all -inf; ids index
+  // the feature tables downstream, so they must stay inside [0, 1024)
+  if (best_idx >= kV) best_idx = 0;
   const long long bt = row / p.Q;
   const int q = static_cast<int>(row % p.Q);
   const int b = static_cast<int>(bt / p.T), t = static_cast<int>(bt % p.T);
   const long long oidx = (static_cast<long long>(b) * p.out_q_stride + p.out_q0 + q) * p.T + t;
   int id = best_idx;
-  if (p.forced_ids != nullptr) id = p.forced_ids[oidx];
+  if (p.forced_ids != nullptr) id = min(max(p.forced_ids[oidx], 0), kV - 1);
   if (lane == 0) {
     p.ids[oidx] = id;
     if (p.ids_raw != nullptr) p.ids_raw[oidx] = best_idx;
@@ -560,11 +576,13 @@ struct RemaskParams {
   const float* gumbel;      // [B, T] or nullptr (then Philox)
   const uint8_t* mask_old;  // [B, T]
   uint8_t* mask_new;        // [B, T]
+  uint8_t* mask_raw;        // [B, T] or nullptr: the kernel's own mask (before teacher forcing), for parity runs
   const uint8_t* forced_mask;  // teacher forcing: copied to mask_new when given
   int T;
   float ratio;       // float32(cos(pi/2 (t+1)/S))
   float temp_ratio;  // float32(temperature * ratio)
   unsigned long long seed;
+  const unsigned long long* seed_dev;  // see SampleParams
   unsigned int step;
   long long row0;    // global index of element (0, 0)
 };
@@ -576,8 +594,12 @@ __global__ void __launch_bounds__(256) remask_kernel(const RemaskParams p) {
   __shared__ float s_cut;
   const int b = blockIdx.x, tid = threadIdx.x;
   const long long base = static_cast<long long>(b) * p.T;
-  if (tid == 0) s_count = 0;
+  if (tid == 0) {
+    s_count = 0;
+    s_cut = INFINITY;  // stays when mask_len >= T (the reference's take_along_dim raises there; the host rejects T < 2 with steps > 1)
+  }
   __syncthreads();
+  const unsigned long long seed = p.seed + (p.seed_dev != nullptr ? *p.seed_dev : 0ull);
   int local = 0;
   for (int t = tid; t < p.T; t += 256) {
     const bool m = p.mask_old[base + t] != 0;
@@ -588,7 +610,7 @@ __global__ void __launch_bounds__(256) remask_kernel(const RemaskParams p) {
         g = p.gumbel[base + t];
       } else {
         const uint4 bits = philox4x32_10(make_uint4(static_cast<uint32_t>(p.row0 + base + t), 0x52454d41u, p.step, static_cast<uint32_t>((p.row0 + base + t) >> 32)),
-                                         make_uint2(static_cast<uint32_t>(p.seed), static_cast<uint32_t>(p.seed >> 32)));
+                                         make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
         g = gumbel_from_bits(bits.x);
       }
       c = __fadd_rn(p.logp[base + t], __fmul_rn(p.temp_ratio, g));
@@ -598,7 +620,7 @@ __global__ void __launch_bounds__(256) remask_kernel(const RemaskParams p) {
   }
   atomicAdd(&s_count, local);
   __syncthreads();
-  if (p.forced_mask != nullptr) {
+  if (p.forced_mask != nullptr && p.mask_raw == nullptr) {
     for (int t = tid; t < p.T; t += 256) p.mask_new[base + t] = p.forced_mask[base + t];
     return;
   }
@@ -617,7 +639,11 @@ __global__ void __launch_bounds__(256) remask_kernel(const RemaskParams p) {
   }
   __syncthreads();
   const float cut = s_cut;
-  for (int t = tid; t < p.T; t += 256) p.mask_new[base + t] = conf[t] < cut ? 1 : 0;
+  for (int t = tid; t < p.T; t += 256) {
+    const uint8_t own = conf[t] < cut ? 1 : 0;
+    if (p.mask_raw != nullptr) p.mask_raw[base + t] = own;
+    p.mask_new[base + t] = p.forced_mask != nullptr ? p.forced_mask[base + t] : own;
+  }
 }
 
 }  // namespace edm

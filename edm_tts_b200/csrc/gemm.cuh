@@ -1,8 +1,9 @@
-// Persistent warp-specialised bf16 GEMM for sm_100a: C[M,N] = A[M,K] * B[N,K]^T (both operands K-major, which is
-// how activations [tokens, channels] and nn.Linear weights [out, in] already sit in HBM).
+// Persistent warp-specialised bf16 GEMMs for sm_100a: C[M,N] = A[M,K] * B[N,K]^T (both operands K-major, which is
+// how activations [tokens, channels] and nn.Linear weights [out, in] already sit in HBM). Two kernels: CTA pairs on 256 x 256 tiles
+// (tcgen05.mma.cta_group::2) for large M, 128 x 64 tiles for small M / N that is not a multiple of 256. Roles in both:
 //
-//   warp 0       : TMA producer  (cp.async.bulk.tensor, 128B swizzle, kStages-deep mbarrier ring)
-//   warp 1       : TMEM allocator + single-thread tcgen05.mma issuer (128 x 256 x 16 per instruction, fp32 accum in TMEM)
+//   warp 0       : TMA producer  (cp.async.bulk.tensor, 128B swizzle, mbarrier ring)
+//   warp 1       : TMEM allocator + tcgen05.mma issue (whole warp runs the descriptor arithmetic, one elected lane issues; fp32 accum in TMEM)
 //   warps 2..17  : epilogue. Warp w owns TMEM lane quadrant w % 4 and 64 of the tile's 256 columns: it pulls its
 //                  128 x 64 slice into registers with two tcgen05.ld, releases the accumulator buffer at once
 //                  (so the MMA warp never waits for epilogue arithmetic), then applies the fused op and stores.
@@ -51,14 +52,10 @@ struct GemmParams {
 constexpr int kGemmBM = 128;
 constexpr int kGemmBN = 256;
 constexpr int kGemmBK = 64;
-constexpr int kGemmStages = 4;
 constexpr int kGemmEpiWarps = 16;  // four per TMEM lane quadrant, each owning 64 of the tile's 256 columns
 constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;
 constexpr int kGemmMaxN = 8192;    // bias staging capacity
 constexpr uint32_t kGemmABytes = kGemmBM * kGemmBK * 2;
-constexpr uint32_t kGemmBBytes = kGemmBN * kGemmBK * 2;
-constexpr uint32_t kGemmStageBytes = kGemmABytes + kGemmBBytes;
-constexpr uint32_t kGemmSmemBytes = kGemmStages * kGemmStageBytes + kGemmMaxN * 4 /*bias*/ + 1024 /*align slack*/ + 256 /*barriers*/;
 
 // 32 consecutive columns of one row. v: accumulators (+ bias already added by the caller).
 template <int EPI>
@@ -176,177 +173,11 @@ __device__ __forceinline__ void gemm_epilogue_rope64(const GemmParams& p, int ro
   }
 }
 
-template <int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  float* s_bias = reinterpret_cast<float*>(smem + kGemmStages * kGemmStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes + kGemmMaxN * 4);
-  uint64_t* empty_bar = full_bar + kGemmStages;
-  uint64_t* tmem_full_bar = empty_bar + kGemmStages;
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  const int num_m = (p.M + kGemmBM - 1) / kGemmBM;
-  const int num_n = p.N / kGemmBN;
-  const int num_tiles = num_m * num_n;
-  const int num_kb = p.K / kGemmBK;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_a);
-    tma_prefetch_desc(&tma_b);
-    for (int s = 0; s < kGemmStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], kGemmEpiWarps);  // one elected lane per epilogue warp
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_base_slot);
-  if (p.bias != nullptr) {
-    for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = __ldg(p.bias + i);
-  } else {
-    for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = 0.f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_blk = t / num_n, n_blk = t % num_n;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * kGemmStageBytes;
-          uint8_t* sb = sa + kGemmABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], kGemmStageBytes);
-          tma_load_2d(&tma_a, &full_bar[stage], sa, p.a_k_offset + kb * kGemmBK, m_blk * kGemmBM);
-          tma_load_2d(&tma_b, &full_bar[stage], sb, kb * kGemmBK, p.b_row_offset + n_blk * kGemmBN);
-          if (++stage == kGemmStages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, kGemmBN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kGemmBN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kGemmStageBytes);
-          const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
-          const uint64_t bdesc = umma_desc_sw128(sa + kGemmABytes, 16, 1024);
-#pragma unroll
-          for (int k = 0; k < kGemmBK / 16; ++k) {
-            // +32 B per 16-element K step inside the 128 B swizzle atom (start-address field is in 16 B units)
-            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
-          if (++stage == kGemmStages) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
-  } else {
-    const int quad = warp & 3;         // TMEM lane quadrant this warp may read
-    const int sub = (warp - 2) >> 2;   // which 64 of the tile's 256 columns
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m_blk = t / num_n, n_blk = t % num_n;
-      const int row = m_blk * kGemmBM + quad * 32 + lane;
-      const int col0 = n_blk * kGemmBN + sub * 64;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kGemmBN + sub * 64;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32(taddr, r0);
-      tmem_ld_32x32(taddr + 32, r1);
-      tmem_ld_wait_dep(r0);
-      tmem_ld_wait_dep(r1);
-      // the slice is in registers: hand the accumulator buffer back before doing any arithmetic
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-      if (row >= p.M) continue;
-      if constexpr (EPI == EPI_QKV_ROPE) {
-        gemm_epilogue_rope64(p, row, col0, r0, r1);
-      } else {
-        const uint32_t b4 = smem_u32(s_bias + col0);
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 b = lds128(b4 + 16 * i);
-          v[4 * i + 0] = __uint_as_float(r0[4 * i + 0]) + b.x;
-          v[4 * i + 1] = __uint_as_float(r0[4 * i + 1]) + b.y;
-          v[4 * i + 2] = __uint_as_float(r0[4 * i + 2]) + b.z;
-          v[4 * i + 3] = __uint_as_float(r0[4 * i + 3]) + b.w;
-        }
-        if constexpr (EPI == EPI_GLU_BF16) {
-          float g[32];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b = lds128(b4 + 16 * (8 + i));
-            g[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
-            g[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
-            g[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
-            g[4 * i + 3] = __uint_as_float(r1[4 * i + 3]) + b.w;
-          }
-          gemm_store_glu(p, row, col0 >> 1, v, g);
-        } else {
-          gemm_store_32<EPI>(p, row, col0, v);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b = lds128(b4 + 16 * (8 + i));
-            v[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
-            v[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
-            v[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
-            v[4 * i + 3] = __uint_as_float(r1[4 * i + 3]) + b.w;
-          }
-          gemm_store_32<EPI>(p, row, col0 + 32, v);
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
-}
-
 // ------------------------------------------------------------------------------------------------ small-M variant
 // At M <= a few hundred rows (single-utterance decodes) the 256 x 256 CTA-pair tiles leave 4-32 CTAs, each streaming 128 weight rows
 // x K from HBM, while the other SMs idle: the GEMM is a weight-streaming problem, not a tensor-pipe one. This variant uses
 // 128 x 64 tiles (N / 64 CTAs per 128 rows: 16-128 CTAs pull the weights concurrently) and an 8-stage ring of 24 KB stages so each
-// CTA keeps 190 KB of loads in flight. Same epilogues as the single-CTA kernel (register stores; a 64-column tile is one epilogue
+// CTA keeps 190 KB of loads in flight. Epilogues store from registers ( a 64-column tile is one epilogue
 // sub-tile: GLU pairs and rotary heads never straddle it). The weight tensor map has 64-row boxes (WMap::small in abi.cu).
 constexpr int kSmBN = 64;
 constexpr int kSmStages = 8;

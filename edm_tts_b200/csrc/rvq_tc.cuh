@@ -31,6 +31,8 @@ namespace edm {
 constexpr int kRtFrames = 128;  // frames per tile = UMMA M
 constexpr int kRtE = 96;        // 12 levels x 8 dims
 constexpr int kRtLatent = 1024;
+constexpr int kRtCodes = 1024;   // codes per codebook
+constexpr int kRvqLevels = 12;   // codebooks
 
 // ------------------------------------------------------------------------------------------------ projection
 // Two rings: one for the raw z tiles (the only HBM stream: 3 x 32 KB in flight per SM keeps the memory system busy
@@ -573,6 +575,66 @@ rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchPar
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ codes -> features
+// Reference: vector_quantizer.py:212-252 (from_codes / from_codes_unreduced): z_q = sum_i W_out_i c_i[code_i] + b_out_i,
+// output channel-major [B, 1024, T] (or [B, L, 1024, T] unreduced). proj[i][code] = W_out_i c_i[code] + b_out_i is
+// precomputed ([12, 1024, 1024] fp32), so this is a gather-sum plus a transpose through shared memory.
+struct CodesToFeatParams {
+  const long long* codes;  // [B, L, T]
+  const float* proj;       // [12, 1024 codes, 1024 ch]
+  float* out;              // [B, 1024, T] or [B, L, 1024, T]
+  int B, L, T;
+  int unreduced;
+};
+
+__global__ void __launch_bounds__(256) codes_to_features_kernel(const CodesToFeatParams p) {
+  __shared__ float tile[32][kRtLatent / 4 + 1];  // 32 frames x 256 channels (one quarter of the channels per pass)
+  const int b = blockIdx.y, t0 = blockIdx.x * 32;
+  const int tid = threadIdx.x;
+  const int n_out = p.unreduced ? p.L : 1;
+  for (int o = 0; o < n_out; ++o) {
+    const int l_lo = p.unreduced ? o : 0, l_hi = p.unreduced ? o + 1 : p.L;
+    for (int cq = 0; cq < 4; ++cq) {
+      // gather: thread (f = tid / 8, 8 threads x 32 channels each)
+      {
+        const int f = tid >> 3, part = tid & 7;
+        const int t = t0 + f;
+        float acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+        if (t < p.T) {
+          for (int l = l_lo; l < l_hi; ++l) {
+            long long code = p.codes[(static_cast<long long>(b) * p.L + l) * p.T + t];
+            code = code < 0 ? 0 : (code >= kRtCodes ? kRtCodes - 1 : code);  // memory safety; the host mirror validates the range
+            const float4* src = reinterpret_cast<const float4*>(p.proj + (static_cast<long long>(l) * kRtCodes + code) * kRtLatent + cq * 256 + part * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 v = __ldg(src + i);
+              acc[4 * i] += v.x;
+              acc[4 * i + 1] += v.y;
+              acc[4 * i + 2] += v.z;
+              acc[4 * i + 3] += v.w;
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tile[f][part * 32 + i] = acc[i];
+      }
+      __syncthreads();
+      // scatter: channel-major, coalesced along t
+      for (int e = tid; e < 256 * 32; e += 256) {
+        const int c = e >> 5, f = e & 31;
+        const int t = t0 + f;
+        if (t < p.T) {
+          const long long plane = p.unreduced ? (static_cast<long long>(b) * p.L + o) : b;
+          p.out[(plane * kRtLatent + cq * 256 + c) * p.T + t] = tile[f][c];
+        }
+      }
+      __syncthreads();
+    }
+  }
 }
 
 }  // namespace edm

@@ -1,6 +1,6 @@
 """The reference's DAC module on the CUDA path: conv encoder, residual vector quantizer, conv decoder.
 
-Mirrors edm_tts/models/dac/modeling_dac.py: DAC.encode (:111-139, without the resampling of preprocess), decode (:141-161),
+Mirrors edm_tts/models/dac/modeling_dac.py: DAC.preprocess (:75-93) + encode (:111-139), decode (:141-161),
 encode_to_codes (:163-167), decode_from_codes (:169-171), codes_to_features / codes_to_features_unreduced (:173-182). State-dict keys
 are the reference's (`encoder.block...`, `quantizer.quantizers...`, `decoder.model...`); the decoder is built only when its weights
 are present.
@@ -8,6 +8,7 @@ are present.
 from __future__ import annotations
 
 import json
+import math
 import os
 
 import torch
@@ -57,12 +58,22 @@ class DAC:
         z = self.encoder(audio, out_dtype=torch.bfloat16)
         return self.quantizer.encode(z, n_quantizers)
 
+    def preprocess(self, audio_data: torch.Tensor, sample_rate=None):
+        """modeling_dac.py:75-93: resample to the model's rate when another one is given (torchaudio, as the reference), then right-pad
+        with zeros to a multiple of the hop length. -> (padded audio, un-padded length)."""
+        if sample_rate is not None and sample_rate != self.sample_rate:
+            import torchaudio
+
+            audio_data = torchaudio.functional.resample(audio_data, sample_rate, self.sample_rate)
+        length = audio_data.shape[-1]
+        right_pad = math.ceil(length / self.hop_length) * self.hop_length - length
+        return torch.nn.functional.pad(audio_data, (0, int(right_pad))), length
+
     @torch.no_grad()
     def encode(self, audio_data: torch.Tensor, sample_rate=None, n_quantizers=None) -> dict:
-        """modeling_dac.py:111-139 for audio already at the model's sample rate."""
-        if sample_rate is not None and sample_rate != self.sample_rate:
-            raise ValueError("resample the audio to the model's sample rate first (preprocess is not part of this path)")
-        length = audio_data.shape[-1]
+        """modeling_dac.py:111-139: preprocess (resample + right-pad to a hop multiple), conv encoder, quantizer. encode_to_codes
+        does not pad, in the reference either (:163-167)."""
+        audio_data, length = self.preprocess(audio_data, sample_rate)
         z = self.encoder(audio_data, out_dtype=torch.float32)
         out = {"length": length, "z": z}
         q = self.quantizer(z, n_quantizers)

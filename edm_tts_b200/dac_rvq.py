@@ -28,13 +28,10 @@ class ResidualVectorQuantize:
         return self
 
     @torch.no_grad()
-    def encode(self, z: torch.Tensor, n_quantizers=None, forced_codes=None, return_latents=False, impl="tcgen05"):
-        """z [B, 1024, T] (fp32 or bf16) -> codes int64 [B, n_codebooks, T]. impl="mma_sync" selects the first-generation kernel
-        (csrc/rvq.cuh, kept for A/B timing in tools/bringup_ops.py)."""
+    def encode(self, z: torch.Tensor, n_quantizers=None, forced_codes=None, return_latents=False):
+        """z [B, 1024, T] (fp32 or bf16) -> codes int64 [B, n_codebooks, T] (csrc/rvq_tc.cuh)."""
         if z.dim() != 3 or z.shape[1] != self.input_dim:
             raise ValueError(f"z must be [B, {self.input_dim}, T]")
-        if impl == "mma_sync":
-            return self._encode_mma_sync(z, forced_codes, return_latents)
         # the tcgen05 path reads z through TMA boxes: rows (the time axis) must be 16-byte multiples
         if z.dtype not in (torch.float32, torch.bfloat16):
             z = z.float()
@@ -57,20 +54,6 @@ class ResidualVectorQuantize:
         if Tp != T:
             codes = codes[:, :, :T].contiguous()
             lat = lat[:, :, :T].contiguous() if lat is not None else None
-        return (codes, lat[:, : self.n_codebooks * self.codebook_dim]) if return_latents else codes
-
-    def _encode_mma_sync(self, z, forced_codes, return_latents):
-        if z.dtype not in (torch.float32, torch.bfloat16):
-            z = z.float()
-        z = z.to(self.device).contiguous()
-        B, _, T = z.shape
-        t = self._t
-        codes = torch.empty(B, self.n_codebooks, T, device=self.device, dtype=torch.int64)
-        lat = torch.empty(B, 96, T, device=self.device, dtype=torch.float32) if return_latents else None
-        fc = None if forced_codes is None else forced_codes.to(self.device, torch.int64).contiguous()
-        L.check(L.lib().edm_rvq_encode(L.ptr(z), int(z.dtype == torch.bfloat16), B, T, self.n_codebooks, L.ptr(t["w_in_t"]), L.ptr(t["b_in"]),
-                                       L.ptr(t["cb_norm"]), L.ptr(t["cb_n2"]), L.ptr(t["g"]), L.ptr(codes), L.ptr(fc), L.ptr(lat),
-                                       L.stream_ptr()), "rvq_encode")
         return (codes, lat[:, : self.n_codebooks * self.codebook_dim]) if return_latents else codes
 
     def forward(self, z: torch.Tensor, n_quantizers=None) -> dict:

@@ -29,9 +29,10 @@ class ShardedDecoder:
     """decode_fn(semantic_tokens, acoustic_prompt_tokens, semantic_prompt_tokens, steps=, temperature=, batch_offset=, **kw)
     -> LongTensor [b, Q, T] for the rows it is given (normally InjectionConformerModel.infer_special)."""
 
-    def __init__(self, decode_fn, group=None, gather_dtype=torch.int16):
+    def __init__(self, decode_fn, group=None, gather_dtype=torch.int16, keep_gather_dtype=False):
         self.decode_fn = decode_fn
         self.group = group
+        self.keep_gather_dtype = keep_gather_dtype  # return the gathered int16 codes as they are (the on-disk dtype) instead of int64
         self.gather_dtype = gather_dtype  # codes are < 1024; int16 is also the reference's on-disk format (codes_dataset.py:41-42)
 
     def __call__(self, semantic_tokens, acoustic_prompt_tokens=None, semantic_prompt_tokens=None, steps=1, temperature=1.0, *,
@@ -51,14 +52,16 @@ class ShardedDecoder:
         sp = None if semantic_prompt_tokens is None else semantic_prompt_tokens[sl]
         local = self.decode_fn(semantic_tokens[sl], ap, sp, **kw) if hi > lo else None
         if world == 1:
-            return local
+            return local.to(self.gather_dtype) if self.keep_gather_dtype else local
         # shards differ by at most one row: pad to the largest, gather, trim
         per = max(shard_bounds(B, r, world)[1] - shard_bounds(B, r, world)[0] for r in range(world))
         ref = local if local is not None else semantic_tokens
-        Q = local.shape[1] if local is not None else 0
-        q_t = torch.tensor([Q], device=ref.device)
-        dist.all_reduce(q_t, op=dist.ReduceOp.MAX, group=self.group)
-        Q = int(q_t.item())
+        if B >= world:
+            Q = local.shape[1]       # every rank has rows: no extra collective, no host synchronisation on the decode path
+        else:                        # some ranks are empty and do not know the number of codebooks
+            q_t = torch.tensor([local.shape[1] if local is not None else 0], device=ref.device)
+            dist.all_reduce(q_t, op=dist.ReduceOp.MAX, group=self.group)
+            Q = int(q_t.item())
         buf = torch.zeros(per, Q, T, device=ref.device, dtype=self.gather_dtype)
         if local is not None:
             buf[: hi - lo] = local.to(self.gather_dtype)
@@ -71,4 +74,5 @@ class ShardedDecoder:
         for r, part in enumerate(parts):
             a, b = shard_bounds(B, r, world)
             out.append(part[: b - a])
-        return torch.cat(out, dim=0).to(torch.int64)
+        out = torch.cat(out, dim=0)
+        return out if self.keep_gather_dtype else out.to(torch.int64)

@@ -8,6 +8,7 @@ malformed prompts). Python only moves pointers; all arithmetic runs in the CUDA 
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 
 import torch
@@ -27,6 +28,64 @@ class InjectionConformerOutput(dict):
 MAX_CHUNK = 64  # sequences decoded per bound workspace (larger batches are processed in chunks; utterances are independent)
 
 
+def _on_device(fn):
+    """Run a public entry point with the model's device current: L.stream_ptr() and every allocation of the call then belong to the
+    device that holds the weights and the workspace, whichever device the caller had selected."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        model = getattr(self, "_m", self)
+        with torch.cuda.device(model.device):
+            return fn(self, *a, **k)
+    return wrapped
+
+
+def _check_range(t, n, what):
+    """F.embedding raises IndexError for an out-of-range index; the kernels only clamp (memory safety), so the range is checked here.
+    Host tensors cost nothing; a device tensor costs one small reduction + sync, skipped while a CUDA graph is being captured."""
+    if t is None or t.numel() == 0:
+        return
+    if t.is_cuda and torch.cuda.is_current_stream_capturing():
+        return
+    lo, hi = torch.aminmax(t)
+    if int(lo) < 0 or int(hi) >= n:
+        raise IndexError(f"{what}: index out of range [0, {n}) (min {int(lo)}, max {int(hi)})")
+
+
+class _Embedding:
+    """Callable embedding table (the reference's nn.Embedding attribute): table[tokens]; `.weight` is the fp32 table."""
+
+    def __init__(self, weight):
+        self.weight = weight
+        self.num_embeddings, self.embedding_dim = weight.shape
+
+    def __call__(self, tokens):
+        _check_range(tokens, self.num_embeddings, "embedding")
+        return torch.nn.functional.embedding(tokens.to(self.weight.device), self.weight)
+
+
+class _LinearLayerNorm:
+    """nn.Sequential(nn.Linear(d, d), nn.LayerNorm(d)) on the C ABI (acoustic_feat_proj / project_injection[k],
+    modeling_injection_conformer.py:44-47, injection_conformer_wrapper.py:26-32): bf16 tensor-core GEMM with fp32 accumulation and
+    an fp32 LayerNorm. x [..., 1024] -> fp32 [..., 1024]."""
+
+    def __init__(self, model, w_bf16, bias, ln_w, ln_b):
+        self._m, self._w, self._b, self._ln_w, self._ln_b = model, w_bf16, bias, ln_w, ln_b
+
+    @_on_device
+    def __call__(self, x):
+        d = self._w.shape[1]
+        lead = x.shape[:-1]
+        a = x.to(self._m.device).reshape(-1, d).to(torch.bfloat16).contiguous()
+        rows = a.shape[0]
+        h = torch.empty(rows, d, device=a.device, dtype=torch.float32)
+        L.check(L.lib().edm_gemm_bf16(L.ptr(a), d, L.ptr(self._w), d, rows, self._w.shape[0], d, L.EPI_F32, L.ptr(self._b), L.ptr(h), d, 1.0,
+                                      None, None, 1, 0, L.stream_ptr()), "gemm")
+        y = torch.empty_like(h)
+        L.check(L.lib().edm_layernorm(L.ptr(h), 0, rows, L.ptr(self._ln_w), L.ptr(self._ln_b), None, None, L.ptr(y), None, 1, 0, 1e-5,
+                                      L.stream_ptr()), "layernorm")
+        return y.view(*lead, d)
+
+
 class _Encoder:
     """InjectionConformerWrapper mirror: forward_first_level / forward / apply_single_to_logits."""
 
@@ -44,35 +103,68 @@ class _Encoder:
             raise ValueError("mask_time_indices must select a common suffix [:, P:] of every sequence (as infer_special builds it)")
         return int(first)
 
+    @_on_device
     def forward_first_level(self, x, mask=None, mask_time_indices=None):
         """injection_conformer_wrapper.py:65-90 -> logits [b, 1, t, codes] (fp32)."""
         assert mask is None, "the S2A decode path never passes a padding mask"
         m = self._m
+        x = x.to(m.device)
         B, N, _ = x.shape
+        if B > MAX_CHUNK:
+            return torch.cat([self.forward_first_level(x[i:i + MAX_CHUNK], None, None if mask_time_indices is None else mask_time_indices[i:i + MAX_CHUNK])
+                              for i in range(0, B, MAX_CHUNK)])
         P = self._prompt_len(x, mask_time_indices)
         m._bind(B, N - P, P)
         xf = x.float().contiguous()
         L.check(L.lib().edm_s2a_first_level(m._ctx, L.ptr(xf), L.stream_ptr()), "first_level")
         return m._view("logits", (B, 1, N - P, m.num_codevectors), torch.float32).clone()
 
+    @_on_device
     def forward(self, x, mask=None, injections=None, acoustic_model=None, mask_time_indices=None, *, prompt_codes=None,
                 forced_coarse=None):
         """injection_conformer_wrapper.py:92-150 in eval mode -> logits [b, q, t, codes] (fp32).
-        Prompt injections are taken as the acoustic prompt *codes* (prompt_codes [b, >=4, P]); the feature tensors the
-        reference passes in `injections` are a function of those codes and are rebuilt from the folded tables."""
+        Prompt rows are injected either from `injections` -- the reference's argument: one feature tensor [b, n, 1024] per injection
+        layer (cumulative DAC features of the prompt, zeros on the target rows), projected here with project_injection[k].0 on the
+        tensor cores -- or from the acoustic prompt *codes* (prompt_codes [b, >=4, P]) through the folded tables, which is what
+        infer_special does. `acoustic_model` is accepted for signature compatibility (the model's own folded tables are used)."""
         assert mask is None, "the S2A decode path never passes a padding mask"
         m = self._m
+        x = x.to(m.device)
         B, N, _ = x.shape
+        if B > MAX_CHUNK:
+            raise ValueError(f"encoder.forward takes at most {MAX_CHUNK} sequences per call (infer_special chunks larger batches itself)")
         P = self._prompt_len(x, mask_time_indices)
-        if P > 0 and prompt_codes is None:
-            raise ValueError("with a prompt prefix pass prompt_codes=<acoustic prompt tokens>; feature-valued injections are not accepted")
+        n_inj = len(m.injection_layers)
+        if P > 0 and prompt_codes is None and injections is None:
+            raise ValueError("a prompt prefix needs its injections: pass injections=[features per injection layer] or prompt_codes=<acoustic prompt tokens>")
         m._bind(B, N - P, P)
-        if P > 0:
+        L.check(L.lib().edm_s2a_set_prompt_injections(m._ctx, None), "set_prompt_injections")
+        keep = None
+        if P > 0 and prompt_codes is not None:
             m._load_prompt_codes(prompt_codes)
+        elif P > 0:
+            if len(injections) < n_inj:
+                raise IndexError("one injection tensor per injection layer is required")   # reference: list index out of range
+            m._load_prompt_codes(torch.zeros(B, n_inj, P, dtype=torch.int64))
+            # project_injection[k].0 on the prompt rows (bf16 operands as under autocast, fp32 accumulate + bias), LayerNorm in the kernel
+            w = m._w
+            keep = torch.empty(n_inj, B * P, 1024, device=m.device, dtype=torch.float32)
+            for k in range(n_inj):
+                inj = injections[k].to(m.device)
+                if tuple(inj.shape) != (B, N, 1024):
+                    raise ValueError(f"injections[{k}] must be [b, n, 1024], got {tuple(inj.shape)}")
+                a = inj[:, :P].reshape(B * P, 1024).to(torch.bfloat16).contiguous()
+                L.check(L.lib().edm_gemm_bf16(L.ptr(a), 1024, L.ptr(w["inj_w"][k]), 1024, B * P, 1024, 1024, L.EPI_F32, L.ptr(w["inj_b"][k]),
+                                              L.ptr(keep[k]), 1024, 1.0, None, None, 1, 0, L.stream_ptr()), "gemm")
+                del a
+            L.check(L.lib().edm_s2a_set_prompt_injections(m._ctx, L.ptr(keep)), "set_prompt_injections")
         codes = torch.empty(B, m.num_quantizers, N - P, device=x.device, dtype=torch.int64)
-        fc = None if forced_coarse is None else forced_coarse.to(torch.int32).contiguous()
+        fc = None if forced_coarse is None else forced_coarse.to(m.device, torch.int32).contiguous()
         xf = x.float().contiguous()
-        L.check(L.lib().edm_s2a_full_pass(m._ctx, L.ptr(xf), L.ptr(fc), L.ptr(codes), L.stream_ptr()), "full_pass")
+        try:
+            L.check(L.lib().edm_s2a_full_pass(m._ctx, L.ptr(xf), L.ptr(fc), L.ptr(codes), L.stream_ptr()), "full_pass")
+        finally:
+            L.check(L.lib().edm_s2a_set_prompt_injections(m._ctx, None), "set_prompt_injections")
         n_inj = len(m.injection_layers)
         coarse = m._view("coarse_logits", (4, B, N - P, m.num_codevectors), torch.float32)[:n_inj].permute(1, 0, 2, 3)
         fine = m._view("fine_logits", (B, N - P, m.num_quantizers - n_inj, m.num_codevectors), torch.float32).permute(0, 2, 1, 3)
@@ -80,9 +172,13 @@ class _Encoder:
 
     __call__ = forward
 
+    @_on_device
     def apply_single_to_logits(self, inp, idx):
         """injection_conformer_wrapper.py:56-63: LayerNorm + per-codebook head idx -> [b, 1, n, codes]."""
         m = self._m
+        if not 0 <= int(idx) < m.num_quantizers:
+            raise IndexError(f"head index {idx} out of range")
+        inp = inp.to(m.device)
         B, n, d = inp.shape
         z = torch.empty(B * n, d, device=inp.device, dtype=torch.bfloat16)
         w = m._w
@@ -100,12 +196,15 @@ class _Encoder:
 class _AcousticModel:
     """The slice of the DAC API the S2A path touches (dac/modeling_dac.py:173-182): code -> feature lookups."""
 
-    def __init__(self, rvq_tables, latent_dim, n_codebooks, codebook_size):
+    def __init__(self, rvq_tables, latent_dim, n_codebooks, codebook_size, device):
         self._t = rvq_tables
+        self.device = device
         self.latent_dim, self.n_codebooks, self.codebook_size = latent_dim, n_codebooks, codebook_size
 
+    @_on_device
     def _c2f(self, codes, unreduced):
-        codes = codes.to(torch.int64).contiguous()
+        _check_range(codes, self.codebook_size, "codes_to_features")
+        codes = codes.to(self.device, torch.int64).contiguous()
         B, Lv, T = codes.shape
         if Lv > self._t["n_levels"]:
             raise ValueError(f"codes have {Lv} levels, quantizer has {self._t['n_levels']}")
@@ -161,8 +260,12 @@ class InjectionConformerModel:
         self._bound = None
         self._ws = None
         self.encoder = _Encoder(self)
-        self.acoustic_model = _AcousticModel(self._rvq, self.acoustic_size, self.num_quantizers, self.num_codevectors)
-        self.semantic_embedding = self._w["sem_emb"]
+        self.acoustic_model = _AcousticModel(self._rvq, self.acoustic_size, self.num_quantizers, self.num_codevectors, self.device)
+        self.semantic_embedding = _Embedding(self._w["sem_emb"])
+        w = self._w
+        self.acoustic_feat_proj = _LinearLayerNorm(self, w["fp_w"], w["fp_b"], w["fp_ln_w"], w["fp_ln_b"])
+        self.encoder.project_injection = [_LinearLayerNorm(self, w["inj_w"][k], w["inj_b"][k], w["inj_ln_w"][k], w["inj_ln_b"][k])
+                                          for k in range(len(self.injection_layers))]
         self.mask_token = self._w["mask_token"].view(1, 1, -1)
         self.training = False
 
@@ -175,11 +278,41 @@ class InjectionConformerModel:
         cfg = InjectionConformerConfig.from_pretrained(path)
         return cls(cfg, load_file(os.path.join(path, "model.safetensors")), device=device, **kw)
 
+    # nn.Module-like surface of an inference-only model: eval() is the only mode, the weights live (packed) on the device given
+    # at construction
     def eval(self):
         return self
 
-    def to(self, *a, **k):
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("edm_tts_b200.InjectionConformerModel is inference-only (no dropout, no autograd); train with the reference")
         return self
+
+    def requires_grad_(self, requires_grad: bool = False):
+        if requires_grad:
+            raise NotImplementedError("inference-only model")
+        return self
+
+    def parameters(self):
+        return iter(())
+
+    def to(self, *args, **kwargs):
+        """Accepts the device the model already lives on (and any dtype argument: precision is fixed by the kernels); moving the
+        packed weights to another device is refused -- build a second model with device=... instead."""
+        dev = kwargs.get("device", next((a for a in args if isinstance(a, (str, torch.device, int))), None))
+        if dev is not None:
+            dev = torch.device("cuda", dev) if isinstance(dev, int) else torch.device(dev)
+            cur = self.device if self.device.index is not None else torch.device("cuda", torch.cuda.current_device())
+            if dev.type != "cuda" or (dev.index is not None and dev.index != cur.index):
+                raise ValueError(f"model lives on {cur}; construct it with device={dev!s} instead of moving it (there is no CPU path)")
+        return self
+
+    def cuda(self, device=None):
+        return self.to(device if device is not None else self.device)
+
+    def state_dict(self):
+        raise NotImplementedError("the packed bf16 weights / folded tables are not the reference's parameters; keep the HF directory "
+                                  "(from_pretrained) as the interchange format")
 
     def __del__(self):
         try:
@@ -226,6 +359,7 @@ class InjectionConformerModel:
 
     # ------------------------------------------------------------------ the decode API
     @torch.no_grad()
+    @_on_device
     def infer_special(self, semantic_tokens, acoustic_prompt_tokens=None, semantic_prompt_tokens=None, steps=1, temperature=1.0, *,
                       seed=0, batch_offset=0, cat_gumbel=None, remask_gumbel=None, forced_ids=None, forced_masks=None, forced_coarse=None):
         """modeling_injection_conformer.py:130-230. Returns LongTensor [b, num_quantizers, t].
@@ -233,11 +367,18 @@ class InjectionConformerModel:
         batch decoded in chunks or shards gives the same tokens as in one piece. Other keyword-only extras are for parity runs: injected Gumbel noise (cat_gumbel [S-1, b*t, codes], remask_gumbel
         [S-1, b, t]) and teacher forcing (forced_ids [S, b, t], forced_masks [S-1, b, t], forced_coarse [b, 4, t])."""
         dev = self.device
+        _check_range(semantic_tokens, self.config.num_semantic_tokens, "semantic_tokens")
         st = semantic_tokens.to(dev)
         B, T = st.shape
+        if steps > 1 and T < 2:
+            raise IndexError("re-masking needs at least 2 frames (the reference's take_along_dim is out of range for T = 1 with steps > 1)")
+        _check_range(forced_ids, self.num_codevectors, "forced_ids")
+        _check_range(forced_coarse, self.num_codevectors, "forced_coarse")
         has_prompt = acoustic_prompt_tokens is not None and semantic_prompt_tokens is not None
         P = 0
         if has_prompt:
+            _check_range(acoustic_prompt_tokens, self.num_codevectors, "acoustic_prompt_tokens")
+            _check_range(semantic_prompt_tokens, self.config.num_semantic_tokens, "semantic_prompt_tokens")
             ap, sp = acoustic_prompt_tokens.to(dev), semantic_prompt_tokens.to(dev)
             if ap.dim() != 3 or sp.dim() != 2 or ap.shape[0] != B or sp.shape[0] != B or ap.shape[-1] != sp.shape[-1]:
                 raise ValueError("prompt tokens must be acoustic [b, q, p] and semantic [b, p] with matching b and p")
@@ -270,6 +411,7 @@ class InjectionConformerModel:
     generate = infer_special
 
     @torch.no_grad()
+    @_on_device
     def decode_trace(self, semantic_tokens, acoustic_prompt_tokens=None, semantic_prompt_tokens=None, steps=1, temperature=1.0, *,
                      seed=0, cat_gumbel=None, remask_gumbel=None, forced_ids=None, forced_masks=None, forced_coarse=None):
         """infer_special run stage by stage through the same C entry points edm_s2a_decode composes, returning every
@@ -285,7 +427,7 @@ class InjectionConformerModel:
         self._bind(B, T, P)
         s_ = L.stream_ptr()
         L.check(lib.edm_s2a_build_input(self._ctx, L.ptr(st), L.ptr(sp), L.ptr(ap), ap.shape[1] if has_prompt else 0, s_), "build_input")
-        tr = dict(step_logits=[], step_ids=[], step_masks=[], x0=self._view("x_in", (B, P + T, self.config.hidden_size), torch.float32).clone())
+        tr = dict(step_logits=[], step_ids=[], step_masks=[], step_masks_raw=[], step_logp=[], x0=self._view("x_in", (B, P + T, self.config.hidden_size), torch.float32).clone())
         V = self.num_codevectors
         if steps > 1:
             for s in range(steps):
@@ -300,6 +442,8 @@ class InjectionConformerModel:
                 tr["step_ids"].append(self._view("ids_raw", (B, T), torch.int32).clone().long())
                 if not last:
                     tr["step_masks"].append(self._view("mask", (B, T), torch.uint8).clone().bool())
+                    tr["step_masks_raw"].append(self._view("mask_raw", (B, T), torch.uint8).clone().bool())
+                    tr["step_logp"].append(self._view("logp", (B, T), torch.float32).clone())
         tr["x_final"] = self._view("x_in", (B, P + T, self.config.hidden_size), torch.float32).clone()
         codes = torch.empty(B, self.num_quantizers, T, device=dev, dtype=torch.int64)
         fc = None if forced_coarse is None else forced_coarse.to(dev).to(torch.int32).contiguous()
@@ -320,6 +464,7 @@ class InjectionConformerModel:
         return torch.bernoulli(p).bool()
 
     @torch.no_grad()
+    @_on_device
     def forward(self, acoustic_tokens, semantic_tokens, *, mask_time_indices=None):
         """InjectionConformerModel.forward (modeling_injection_conformer.py:76-128) in eval mode: masked encoder input,
         ground-truth coarse injections, 12-level logits, mean cross-entropy over the masked positions (all positions with
@@ -327,6 +472,8 @@ class InjectionConformerModel:
         composed from the decoder's own kernels; `mask_time_indices` replaces the cosine_schedule_mask draw (parity tests)."""
         assert acoustic_tokens.shape[-1] == semantic_tokens.shape[-1], "Acoustic and semantic tokens must have same length"
         dev, lib = self.device, L.lib()
+        _check_range(acoustic_tokens, self.num_codevectors, "acoustic_tokens")
+        _check_range(semantic_tokens, self.config.num_semantic_tokens, "semantic_tokens")
         ac = acoustic_tokens.to(dev)
         st = semantic_tokens.to(dev)
         B, Q, T = ac.shape
@@ -373,6 +520,9 @@ class InjectionConformerModel:
         sel = torch.ones_like(mask) if self.loss_all else mask
         sel3 = sel[:, None, :].expand(B, Q, T)
         loss = -(logp.masked_select(sel3).mean())
-        return InjectionConformerOutput(loss=loss, output_acoustic_codes=out_codes.masked_select(sel3), target_acoustic_codes=ac.clone())
+        # the reference flattens only on the masked branch (modeling_injection_conformer.py:114-120): with loss_all the arg-max codes
+        # keep their [b, q, t] shape
+        out_sel = out_codes if self.loss_all else out_codes.masked_select(sel3)
+        return InjectionConformerOutput(loss=loss, output_acoustic_codes=out_sel, target_acoustic_codes=ac.clone())
 
     __call__ = forward

@@ -6,7 +6,8 @@ the device), so its ~850 launches can be captured as they are; a replay removes 
 sampling noise of the reference (Categorical.sample and the Gumbel of random_topk_mask, modeling_injection_conformer.py:192,
 edm_tts/utils/utils.py:49-60) is drawn per request with torch's device RNG into static tensors the captured kernels read (the
 injected-noise inputs of the decode), so requests do not share noise; for shapes where those tensors would be large the in-kernel
-Philox stream with the captured seed is used instead.
+Philox stream is used instead, keyed by the captured seed plus a device-resident request counter (edm_s2a_set_seed_buffer) that is
+bumped before every replay: scalar kernel arguments are baked into a captured graph, a word in device memory is not.
 """
 from __future__ import annotations
 
@@ -32,6 +33,10 @@ class GraphedDecode:
             self._gen = torch.Generator(device=dev)
             self._gen.manual_seed(self.seed)
             self._refresh_noise()
+        # Philox mode: the kernels add this device word to the captured seed; __call__ bumps it per request
+        self.seed_word = None
+        if self.cat is None and self.steps > 1:
+            self.seed_word = torch.zeros(1, dtype=torch.int64, device=dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -44,8 +49,17 @@ class GraphedDecode:
             self.codes = self._run()
 
     def _run(self):
-        return self.model.infer_special(self.sem, self.ap, self.sp, steps=self.steps, temperature=self.temperature, seed=self.seed,
-                                        cat_gumbel=self.cat, remask_gumbel=self.rem)
+        from . import _lib as L
+
+        m = self.model
+        if self.seed_word is not None:
+            L.check(L.lib().edm_s2a_set_seed_buffer(m._ctx, self.seed_word.data_ptr()), "set_seed_buffer")
+        try:
+            return m.infer_special(self.sem, self.ap, self.sp, steps=self.steps, temperature=self.temperature, seed=self.seed,
+                                   cat_gumbel=self.cat, remask_gumbel=self.rem)
+        finally:
+            if self.seed_word is not None:
+                L.check(L.lib().edm_s2a_set_seed_buffer(m._ctx, None), "set_seed_buffer")
 
     def _refresh_noise(self):
         # Categorical(logits).sample() == argmax(log p + g) with g = -log E, E ~ Exp(1); Gumbel(0, 1) = -log(-log U)
@@ -54,8 +68,9 @@ class GraphedDecode:
         self.rem.uniform_(tiny, 1.0, generator=self._gen).clamp_(max=1.0 - torch.finfo(torch.float32).eps).log_().neg_().log_().neg_()
 
     @torch.no_grad()
-    def __call__(self, semantic_tokens, acoustic_prompt_tokens=None, semantic_prompt_tokens=None, clone: bool = True):
-        """Same arguments and result as infer_special for the captured shape; `clone=False` returns the graph's static output tensor."""
+    def __call__(self, semantic_tokens, acoustic_prompt_tokens=None, semantic_prompt_tokens=None, clone: bool = True, request_id=None):
+        """Same arguments and result as infer_special for the captured shape; `clone=False` returns the graph's static output tensor.
+        Philox mode: request n (counted from 0, or `request_id`) decodes as infer_special(..., seed=seed + n)."""
         if tuple(semantic_tokens.shape) != tuple(self.sem.shape):
             raise ValueError(f"captured for semantic tokens of shape {tuple(self.sem.shape)}")
         if (self.ap is None) != (acoustic_prompt_tokens is None) or (self.sp is None) != (semantic_prompt_tokens is None):
@@ -68,5 +83,13 @@ class GraphedDecode:
             self.sp.copy_(semantic_prompt_tokens)
         if self.cat is not None:
             self._refresh_noise()
+        if self.seed_word is not None:
+            if request_id is not None:
+                self.seed_word.fill_(int(request_id))
+            self.graph.replay()
+            out = self.codes.clone() if clone else self.codes
+            if request_id is None:
+                self.seed_word.add_(1)
+            return out
         self.graph.replay()
         return self.codes.clone() if clone else self.codes

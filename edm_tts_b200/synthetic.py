@@ -48,6 +48,105 @@ def _randn(key, seed, *shape, std=1.0):
     return torch.randn(*shape, generator=_gen(key, seed), dtype=torch.float32) * std
 
 
+def _conformer_layer(sd: dict, p: str, d: int, ff_mult: int, conv_expansion: int, conv_kernel: int, seed: int) -> None:
+    """Parameters of one ConformerBlock (edm_tts/models/conformer/conformer.py:184-235) under prefix p."""
+    def linear(prefix, out_f, in_f, bias=True):
+        sd[prefix + ".weight"] = _randn(prefix + ".weight", seed, out_f, in_f, std=1.0 / math.sqrt(in_f))
+        if bias:
+            sd[prefix + ".bias"] = _randn(prefix + ".bias", seed, out_f, std=0.05)
+
+    def lnorm(prefix, n):
+        sd[prefix + ".weight"] = 1.0 + _randn(prefix + ".weight", seed, n, std=0.1)
+        sd[prefix + ".bias"] = _randn(prefix + ".bias", seed, n, std=0.05)
+
+    inner = d * conv_expansion
+    for ff in ("ff1", "ff2"):
+        linear(p + ff + ".fn.fn.net.0", d * ff_mult, d)
+        linear(p + ff + ".fn.fn.net.3", d, d * ff_mult)
+        lnorm(p + ff + ".fn.norm", d)
+    linear(p + "attn.fn.to_q", d, d, bias=False)
+    linear(p + "attn.fn.to_kv", 2 * d, d, bias=False)
+    linear(p + "attn.fn.to_out", d, d)
+    lnorm(p + "attn.norm", d)
+    lnorm(p + "conv.net.0", d)
+    sd[p + "conv.net.2.weight"] = _randn(p + "conv.net.2.weight", seed, inner * 2, d, 1, std=1 / math.sqrt(d))
+    sd[p + "conv.net.2.bias"] = _randn(p + "conv.net.2.bias", seed, inner * 2, std=0.05)
+    sd[p + "conv.net.4.conv.weight"] = _randn(p + "conv.net.4.conv.weight", seed, inner, 1, conv_kernel, std=0.5)
+    sd[p + "conv.net.4.conv.bias"] = _randn(p + "conv.net.4.conv.bias", seed, inner, std=0.05)
+    sd[p + "conv.net.6.weight"] = 1.0 + _randn(p + "conv.net.6.weight", seed, 1, inner, 1, std=0.1)
+    sd[p + "conv.net.7.weight"] = _randn(p + "conv.net.7.weight", seed, d, inner, 1, std=1 / math.sqrt(inner))
+    sd[p + "conv.net.7.bias"] = _randn(p + "conv.net.7.bias", seed, d, std=0.05)
+    lnorm(p + "post_norm", d)
+
+
+@dataclass
+class T2SConfig:
+    """Dims of TextToSemanticWLen (edm_tts/models/text_to_semantic/configuration.py:4-86). Defaults = its base config (hidden 512,
+    16 heads of 32); configs/text_to_semantic_w_length/train_config.yaml trains hidden 384, 8 heads of 48, depth 12."""
+    hidden: int = 512
+    text_vocab: int = 256
+    semantic_vocab: int = 1024
+    heads: int = 16
+    depth: int = 8
+    lp_heads: int = 16
+    lp_depth: int = 4
+    ff_mult: int = 4
+    conv_expansion: int = 2
+    conv_kernel: int = 5
+    num_special: int = 5          # pad 0, text 1, speech 2, sep 3, mask 4
+    target_length: float = 60.0   # synthetic length head: exp(bias) frames
+
+    @property
+    def dim_head(self) -> int:
+        return self.hidden // self.heads
+
+    @property
+    def lp_dim_head(self) -> int:
+        return self.hidden // self.lp_heads
+
+    @property
+    def total_tokens(self) -> int:
+        return self.text_vocab + self.semantic_vocab + self.num_special
+
+    @property
+    def codebook_size(self) -> int:   # logit width, for the shared parity helpers
+        return self.semantic_vocab
+
+
+def make_t2s_state_dict(cfg: T2SConfig, seed: int = 0) -> dict:
+    """TextToSemanticWLen.state_dict() keys (modeling_text_to_semantic.py:30-60) with deterministic values. The length head is
+    centred on cfg.target_length frames so that exp(length_pred_head(.)) is a usable sequence length at random init."""
+    d, sd = cfg.hidden, {}
+    sd["input_embedding.weight"] = _randn("input_embedding.weight", seed, cfg.total_tokens, d)
+    sd["input_embedding.weight"][0].zero_()                      # padding_idx row, as nn.Embedding initialises it
+    for i in range(cfg.depth):
+        _conformer_layer(sd, f"conformer.layers.{i}.", d, cfg.ff_mult, cfg.conv_expansion, cfg.conv_kernel, seed)
+    sd["length_token"] = _randn("length_token", seed, 1, 1, d)
+    for i in range(cfg.lp_depth):
+        _conformer_layer(sd, f"length_predictor.layers.{i}.", d, cfg.ff_mult, cfg.conv_expansion, cfg.conv_kernel, seed)
+    sd["pred_transform.0.weight"] = _randn("pred_transform.0.weight", seed, d, d, std=1.0 / math.sqrt(d))
+    sd["pred_transform.0.bias"] = _randn("pred_transform.0.bias", seed, d, std=0.05)
+    sd["pred_transform.2.weight"] = 1.0 + _randn("pred_transform.2.weight", seed, d, std=0.1)
+    sd["pred_transform.2.bias"] = _randn("pred_transform.2.bias", seed, d, std=0.05)
+    sd["pred_head.weight"] = _randn("pred_head.weight", seed, cfg.semantic_vocab, d, std=1.0 / math.sqrt(d))
+    sd["pred_head.bias"] = _randn("pred_head.bias", seed, cfg.semantic_vocab, std=0.05)
+    sd["length_pred_head.weight"] = _randn("length_pred_head.weight", seed, 1, d, std=0.2 / math.sqrt(d))
+    sd["length_pred_head.bias"] = torch.tensor([math.log(cfg.target_length)], dtype=torch.float32)
+    return sd
+
+
+def make_t2s_noise(n_positions: int, pred_iters: int, cfg: T2SConfig, seed: int = 1234) -> dict:
+    """Injected sampling noise of TextToSemanticWLen.infer: cat_gumbel [iters-1, L, V] (Categorical.sample == argmax(logits + g)) and
+    remask_gumbel [iters-1, 1, L] (the Gumbel draw of random_topk_mask), L = sequence length incl. text and special tokens."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    n = max(pred_iters - 1, 0)
+    u = torch.rand(n, n_positions, cfg.semantic_vocab, generator=g).clamp_(1e-10, 1 - 1e-7)
+    cat = -torch.log(-torch.log(u))
+    u = torch.rand(n, 1, n_positions, generator=g).clamp_(1e-10, 1 - 1e-7)
+    return {"cat_gumbel": cat, "remask_gumbel": -torch.log(-torch.log(u))}
+
+
 def make_state_dict(cfg: OracleConfig, seed: int = 0) -> dict:
     """All parameters the hot path touches, keyed as in InjectionConformerModel.state_dict()."""
     d, sd = cfg.hidden, {}
@@ -65,26 +164,8 @@ def make_state_dict(cfg: OracleConfig, seed: int = 0) -> dict:
     sd["semantic_embedding.weight"] = _randn("semantic_embedding.weight", seed, cfg.num_semantic, d)
     linear("acoustic_feat_proj.0", d, cfg.latent_dim)
     lnorm("acoustic_feat_proj.1", d)
-    inner = d * cfg.conv_expansion
     for i in range(cfg.depth):
-        p = f"encoder.layers.{i}."
-        for ff in ("ff1", "ff2"):
-            linear(p + ff + ".fn.fn.net.0", d * cfg.ff_mult, d)
-            linear(p + ff + ".fn.fn.net.3", d, d * cfg.ff_mult)
-            lnorm(p + ff + ".fn.norm", d)
-        linear(p + "attn.fn.to_q", d, d, bias=False)
-        linear(p + "attn.fn.to_kv", 2 * d, d, bias=False)
-        linear(p + "attn.fn.to_out", d, d)
-        lnorm(p + "attn.norm", d)
-        lnorm(p + "conv.net.0", d)
-        sd[p + "conv.net.2.weight"] = _randn(p + "conv.net.2.weight", seed, inner * 2, d, 1, std=1 / math.sqrt(d))
-        sd[p + "conv.net.2.bias"] = _randn(p + "conv.net.2.bias", seed, inner * 2, std=0.05)
-        sd[p + "conv.net.4.conv.weight"] = _randn(p + "conv.net.4.conv.weight", seed, inner, 1, cfg.conv_kernel, std=0.5)
-        sd[p + "conv.net.4.conv.bias"] = _randn(p + "conv.net.4.conv.bias", seed, inner, std=0.05)
-        sd[p + "conv.net.6.weight"] = 1.0 + _randn(p + "conv.net.6.weight", seed, 1, inner, 1, std=0.1)
-        sd[p + "conv.net.7.weight"] = _randn(p + "conv.net.7.weight", seed, d, inner, 1, std=1 / math.sqrt(inner))
-        sd[p + "conv.net.7.bias"] = _randn(p + "conv.net.7.bias", seed, d, std=0.05)
-        lnorm(p + "post_norm", d)
+        _conformer_layer(sd, f"encoder.layers.{i}.", d, cfg.ff_mult, cfg.conv_expansion, cfg.conv_kernel, seed)
     for k in range(len(cfg.injection_layers)):
         linear(f"encoder.project_injection.{k}.0", d, cfg.latent_dim)
         lnorm(f"encoder.project_injection.{k}.1", d)

@@ -95,6 +95,11 @@ def pack_s2a_weights(sd: dict, cfg: InjectionConformerConfig, device, max_positi
     out["mask_token"] = f32(sd["mask_token"].reshape(-1))
     out["feat_table"] = f32(proj[0] @ w_fp.t())
     out["feat_const"] = f32(w_fp @ b_out[0] + sd["acoustic_feat_proj.0.bias"].to(device, f64))
+    # the un-folded projections, for callers that hand in DAC *features* (model.acoustic_feat_proj(x), encoder.forward(injections=...))
+    out["fp_w"] = bf16(sd["acoustic_feat_proj.0.weight"])
+    out["fp_b"] = f32(sd["acoustic_feat_proj.0.bias"])
+    out["inj_w"] = torch.stack([bf16(sd[f"encoder.project_injection.{k}.0.weight"]) for k in range(n_inj)])
+    out["inj_b"] = torch.stack([f32(sd[f"encoder.project_injection.{k}.0.bias"]) for k in range(n_inj)])
     out["fp_ln_w"] = f32(sd["acoustic_feat_proj.1.weight"])
     out["fp_ln_b"] = f32(sd["acoustic_feat_proj.1.bias"])
     codes = cb.shape[1]
@@ -128,7 +133,7 @@ def tf32_round(t: torch.Tensor) -> torch.Tensor:
 
 
 def pack_rvq_weights(sd: dict, n_codebooks: int, prefix: str, device) -> dict:
-    """Tables of the fused RVQ search (csrc/rvq.cuh): stacked in_proj, normalised codebooks, G[i][j] cross tables, and the
+    """Tables of the fused RVQ search (csrc/rvq_tc.cuh): stacked in_proj, normalised codebooks, G[i][j] cross tables, and the
     projected codebooks (incl. bias) for codes -> features."""
     w_in, b_in, w_out, b_out, cb = quantizer_tensors(sd, n_codebooks, prefix, device)
     L, cbd, latent = w_in.shape
@@ -155,7 +160,6 @@ def pack_rvq_weights(sd: dict, n_codebooks: int, prefix: str, device) -> dict:
     cb_packed[..., 24], cb_packed[..., 25] = x_hi, x_lo
     return {
         "w_hi": w_hi.contiguous(), "w_lo": w_lo.contiguous(), "cb_packed": cb_packed.contiguous(),
-        "w_in_t": padl(w_in.float()).reshape(12 * cbd, latent).t().contiguous(),   # [latent, 96]: rows are contiguous per channel
         "b_in": padl(b_in.float()).reshape(-1).contiguous(),
         "cb_norm": padl(cbn).contiguous(),
         "cb_n2": padl(cbn.pow(2).sum(-1)).contiguous(),

@@ -46,7 +46,8 @@ const char* edm_last_error(void);
  * ------------------------------------------------------------------------------------------------------------- */
 
 /* out[M,N] = epilogue(A[M,K] (bf16, row pitch lda) x B[N,K]^T (bf16, row pitch ldb)), tcgen05 + TMA.
- * Replaces nn.Linear / 1x1 nn.Conv1d calls: conformer.py:124-126,152-154,170,175; wrapper :38-63. N % 256 == 0, K % 64 == 0. */
+ * Replaces nn.Linear / 1x1 nn.Conv1d calls: conformer.py:124-126,152-154,170,175; wrapper :38-63. N % 64 == 0
+ * (N % 256 == 0 for the CTA-pair kernel that large M selects), K % 64 == 0. */
 int edm_gemm_bf16(const void* a, long long lda, const void* b, long long ldb, int M, int N, int K, int epilogue,
                   const float* bias, void* out, long long ldo, float scale, const float* rope_cos,
                   const float* rope_sin, int seq_len, int rope_cols, void* stream);
@@ -54,9 +55,6 @@ int edm_gemm_bf16(const void* a, long long lda, const void* b, long long ldb, in
 /* softmax(q k^T / 8) v for H heads of 64; qkv is the fused projection [B*N, 3*H*64] (q | k | v), out [B*N, H*64] bf16.
  * Replaces Attend.flash_attn, attend.py:63-115 (non-causal, no mask, dropout 0). */
 int edm_attention(const void* qkv, int B, int N, int H, void* out, void* stream);
-/* bring-up variant exposing the MN-major V descriptor fields (bytes) */
-int edm_attention_dbg(const void* qkv, int B, int N, int H, void* out, unsigned v_lbo, unsigned v_sbo, unsigned v_kstep,
-                      void* stream);
 
 /* y = LN(in; w1,b1) [optional fp32 store], z = LN(y; w2,b2) or y [optional bf16 store, rows n < z_skip of every
  * seq_len-long sequence dropped]. 1024 channels. Replaces nn.LayerNorm at conformer.py:106,168,216 and wrapper :44. */
@@ -82,27 +80,14 @@ int edm_remask(const float* logp, const float* gumbel, const uint8_t* mask_old, 
                const uint8_t* forced_mask, int B, int T, float ratio, float temp_ratio, unsigned long long seed,
                unsigned step, void* stream);
 
-/* DAC residual VQ: z [B,1024,T] (fp32 or bf16) -> codes int64 [B,n_levels,T]. Replaces
- * ResidualVectorQuantize.forward, dac/vector_quantizer.py:146-210 (codes only; eval mode). Tables are built by the
- * host side (edm_tts_b200/weights.py:pack_rvq_weights) from the reference state dict: w_in_t [1024,96] stacked folded
- * in_proj weights (transposed), b_in [96], cb_norm [12,1024,8], cb_n2 [12,1024], g [12,12,1024,8]. */
-int edm_rvq_encode(const void* z, int z_is_bf16, int B, int T, int n_levels, const float* w_in_t, const float* b_in,
-                   const float* cb_norm, const float* cb_n2, const float* g, long long* codes,
-                   const long long* forced, float* latents, void* stream);
-
-/* Same search on the tcgen05 tensor cores (csrc/rvq_tc.cuh): a 3xTF32 projection GEMM z -> e_ws [B*T,96] followed by the
- * 12-level search with TMEM-resident score tiles. z [B,1024,T] fp32 with T % 4 == 0 or bf16 with T % 8 == 0 (TMA needs
+/* DAC residual VQ on the tcgen05 tensor cores (csrc/rvq_tc.cuh): z [B,1024,T] -> codes int64 [B,n_levels,T] (codes only; eval mode).
+ * A 3xTF32 projection GEMM z -> e_ws [B*T,96] followed by the 12-level search with TMEM-resident score tiles. z [B,1024,T] fp32 with T % 4 == 0 or bf16 with T % 8 == 0 (TMA needs
  * 16-byte rows; the host side pads other lengths). bf16 z is expanded to tf32-exact fp32 tiles on chip (half the HBM bytes). Tables (pack_rvq_weights): w_hi / w_lo [96,1024] tf32-split stacked in_proj weights,
  * b_in [96], cb_packed [12,1024,32] = [c^_hi | c^_hi | c^_lo | -|c^|^2/2 hi, lo, 0...], g [12,12,1024,8]. e_ws is caller
  * scratch of B*T*96 floats. Replaces ResidualVectorQuantize.forward, dac/vector_quantizer.py:146-210. */
 int edm_rvq_encode_tc(const void* z, int z_is_bf16, int B, int T, int n_levels, const float* w_hi, const float* w_lo, const float* b_in,
                       const float* cb_packed, const float* g, float* e_ws, long long* codes, const long long* forced,
                       float* latents, void* stream);
-
-/* Bring-up only: override the shared-memory descriptor strides of the projection's MN-major A operand; skip_project = 1
- * makes edm_rvq_encode_tc search the latents already in e_ws; scan_probe = 1 runs the search without its compare work
- * (timing floor; the codes are meaningless). */
-void edm_rvq_tc_debug(unsigned lbo, unsigned sbo, int skip_project, int scan_probe);
 
 /* codes int64 [B,L,T] -> features fp32 [B,1024,T] (or [B,L,1024,T] when unreduced); proj = [12,1024,1024] projected
  * codebooks incl. bias. Replaces from_codes / from_codes_unreduced, dac/vector_quantizer.py:212-252. */
@@ -193,6 +178,18 @@ void* edm_s2a_buffer(edm_s2a_ctx* ctx, const char* name, size_t* bytes);
 /* Global index of this context's first sequence inside the caller's whole batch. The in-kernel Philox counters are
  * offset by it so the sampled tokens do not depend on how the batch is chunked or sharded over GPUs. */
 int edm_s2a_set_batch_offset(edm_s2a_ctx* ctx, long long batch_offset);
+
+/* Feature-valued prompt injections (the `injections` argument of InjectionConformerWrapper.forward, injection_conformer_wrapper.py:92-131):
+ * proj = fp32 [n_injection, B*P, 1024], row (k, b, n) = project_injection[k].0 applied to the caller's cumulative DAC feature of
+ * prompt frame n (Linear only; the LayerNorm runs in the kernel). While set, edm_s2a_full_pass injects these on the prompt rows
+ * instead of the rows looked up from the acoustic prompt codes. NULL (the default, and after every edm_s2a_bind) restores the codes. */
+int edm_s2a_set_prompt_injections(edm_s2a_ctx* ctx, const float* proj);
+
+/* Optional device-resident seed offset: when set (non-NULL), the sampling / re-masking kernels add *seed_dev to the seed argument
+ * of edm_s2a_step / edm_s2a_decode at run time. A decode captured in a CUDA graph bakes its scalar arguments into the capture; the
+ * caller bumps this word before each replay so that every replay draws fresh noise, as Categorical.sample() /
+ * Gumbel.sample() do per call in the reference (modeling_injection_conformer.py:192, utils/utils.py:52). NULL detaches. */
+int edm_s2a_set_seed_buffer(edm_s2a_ctx* ctx, const unsigned long long* seed_dev);
 
 /* modeling_injection_conformer.py:139-168: build encoder input + mask state (all target rows masked). */
 int edm_s2a_build_input(edm_s2a_ctx* ctx, const int* sem_tokens, const int* sem_prompt, const int* ac_prompt,

@@ -127,9 +127,9 @@ def conv_module(sd, p, x, cfg, mode):
     return _linear(h, sd[p + "net.7.weight"][:, :, 0], sd[p + "net.7.bias"], mode)
 
 
-def conformer_block(sd, i, x, cfg, freqs, mode):
+def conformer_block(sd, i, x, cfg, freqs, mode, prefix="encoder.layers."):
     """ConformerBlock.forward, conformer/conformer.py:219-235."""
-    p = f"encoder.layers.{i}."
+    p = f"{prefix}{i}."
     x = feed_forward(sd, p + "ff1.", x, mode) + x
     x = attention(sd, p + "attn.", x, cfg, freqs, mode) + x
     x = conv_module(sd, p + "conv.", x, cfg, mode) + x
@@ -208,11 +208,14 @@ def forward_full(sd, cfg, x, prompt_injections=None, prompt_len=0, mode="fp32", 
 
 
 # ---------------------------------------------------------------------------------------------- decode loop
-def random_topk_mask(mask_len, probs, gumbel, temperature):
-    """edm_tts/utils/utils.py:49-60 with the Gumbel draw injected."""
+def random_topk_mask(mask_len, probs, gumbel, temperature, trace=None):
+    """edm_tts/utils/utils.py:49-60 with the Gumbel draw injected. trace (dict of lists) receives the confidences and the cut-off."""
     confidence = torch.log(probs) + temperature * gumbel
     sorted_confidence, _ = torch.sort(confidence, dim=-1)
     cut_off = torch.take_along_dim(sorted_confidence, mask_len.long().unsqueeze(-1), dim=-1)
+    if trace is not None:
+        trace["step_conf"].append(confidence)
+        trace["step_cut"].append(cut_off)
     return confidence < cut_off
 
 
@@ -259,7 +262,7 @@ def infer_special(sd, cfg: OracleConfig, semantic_tokens, acoustic_prompt_tokens
     B, T = semantic_tokens.shape
     mask_token = sd["mask_token"].expand(B, T, -1)
     if trace is not None:
-        trace.update(step_logits=[], step_ids=[], step_masks=[], x0=x.clone())
+        trace.update(step_logits=[], step_ids=[], step_masks=[], step_conf=[], step_cut=[], x0=x.clone())
     if steps > 1:
         ratios = [math.cos(math.pi / 2.0 * ((t + 1) / steps)) for t in range(steps)]
         mask = torch.ones(B, T, dtype=torch.bool, device=x.device)
@@ -283,7 +286,7 @@ def infer_special(sd, cfg: OracleConfig, semantic_tokens, acoustic_prompt_tokens
                 probs = F.softmax(logits, dim=-1)
                 sel = torch.take_along_dim(probs, ids.unsqueeze(-1), -1).squeeze(-1)
                 sel = torch.where(mask, sel, torch.inf)
-                next_mask = random_topk_mask(mask_len, sel, remask_gumbel[i].to(sel.device), temperature * ratio)
+                next_mask = random_topk_mask(mask_len, sel, remask_gumbel[i].to(sel.device), temperature * ratio, trace)
                 if trace is not None:
                     trace["step_masks"].append(next_mask)
                 if forced_masks is not None:
@@ -302,7 +305,7 @@ def training_forward(sd, cfg: OracleConfig, acoustic_tokens, semantic_tokens, ma
     """InjectionConformerModel.forward in eval mode, modeling_injection_conformer.py:76-128, with the cosine_schedule_mask draw
     (:62-74) injected. Eval mode of the wrapper (injection_conformer_wrapper.py:113-131): the coarse logits are predicted, but
     the features injected at every row are the ground-truth ones (`injections[injection_idx]`).
-    Returns loss, output codes (flat over the selected (b, q, t) positions, as the reference returns them) and all logits."""
+    Returns loss, output codes (flat over the masked (b, q, t) positions, or [b, q, t] with loss_all, as the reference returns them) and all logits."""
     assert acoustic_tokens.shape[-1] == semantic_tokens.shape[-1], "Acoustic and semantic tokens must have same length"
     sem = F.embedding(semantic_tokens, sd["semantic_embedding.weight"])
     B, T, _ = sem.shape
@@ -315,6 +318,6 @@ def training_forward(sd, cfg: OracleConfig, acoustic_tokens, semantic_tokens, ma
         sel = logits.masked_select(m[:, None, :, None]).view(-1, V)                          # :114-116
         tgt = acoustic_tokens.masked_select(m[:, None, :]).view(-1)
     else:
-        sel, tgt = logits.reshape(-1, V), acoustic_tokens.reshape(-1)
-    loss = F.cross_entropy(sel.float(), tgt, reduction="mean")                               # :122
+        sel, tgt = logits, acoustic_tokens.reshape(-1)                                       # :117-118: logits keep [b, q, t, V]
+    loss = F.cross_entropy(sel.reshape(-1, V).float(), tgt, reduction="mean")                # :120-122
     return dict(loss=loss, output_acoustic_codes=sel.argmax(dim=-1), target_acoustic_codes=acoustic_tokens, logits=logits)

@@ -8,7 +8,7 @@ The reference is imported from /root/reference (never copied). Harness-side patc
   * torch.multinomial and Gumbel.sample read pre-generated noise so the run is bit-deterministic;
   * random_topk_mask / forward_first_level / encoder.forward are wrapped to record their outputs.
 Weights are the deterministic ones of oracle/weights.py loaded into the reference modules, inputs oracle.weights.make_inputs.
-Outputs: tests/golden/s2a_*.pt, tests/golden/rvq_*.pt (small tensors only).
+Outputs: tests/golden/s2a_*.pt, rvq_*.pt, train_fwd_*.pt, dac_*.pt, t2s_*.pt (small tensors only).
 """
 import os
 import sys
@@ -210,12 +210,13 @@ def make_dac_key_layout():
     print(f"dac_state_dict_keys: {len(ref)} entries saved", flush=True)
 
 
-def make_train_forward(name, cfg_name, B, T, seed=0):
+def make_train_forward(name, cfg_name, B, T, seed=0, loss_all=False):
     """InjectionConformerModel.forward (eval mode: no dropout, ground-truth injections) with cosine_schedule_mask replaced by a
     fixed Bernoulli(0.6) mask: loss, arg-max codes and a few logit rows."""
     cfg, dac_kwargs = CONFIGS[cfg_name]
     torch.manual_seed(0)
     model, _ = build_reference(cfg, dac_kwargs, seed)
+    model.loss_all = loss_all                    # config.loss_all (modeling_injection_conformer.py:60)
     g = torch.Generator().manual_seed(4321 + T)
     sem = torch.randint(0, cfg.num_semantic, (B, T), generator=g)
     ac = torch.randint(0, cfg.codebook_size, (B, cfg.n_codebooks, T), generator=g)
@@ -237,15 +238,107 @@ def make_train_forward(name, cfg_name, B, T, seed=0):
     top2 = al.topk(2, dim=-1)[0]
     gold = dict(cfg_name=cfg_name, B=B, T=T, weight_seed=seed, semantic_tokens=sem.to(torch.int16), acoustic_tokens=ac.to(torch.int16), mask=mask,
                 loss=out.loss.item(), output_codes=out.output_acoustic_codes.to(torch.int16), logit_rows=al[:, :, idx].clone(), row_idx=idx,
-                margin=(top2[..., 0] - top2[..., 1]).to(torch.float16))
+                margin=(top2[..., 0] - top2[..., 1]).to(torch.float16), loss_all=loss_all)
     torch.save(gold, os.path.join(OUT, f"train_fwd_{name}.pt"))
     print(f"train_fwd_{name}: loss {out.loss.item():.6f} codes {tuple(out.output_acoustic_codes.shape)} saved", flush=True)
 
 
+from tests.golden.make_golden_cfg import T2S_CONFIGS  # noqa: E402
+
+
+def make_t2s(name, cfg_name, text, pred_iters, gt_length=None, seed=0):
+    """TextToSemanticWLen.infer of the unmodified reference with injected sampling noise: predicted length, per-iteration own ids /
+    masks, the final tokens, and logit rows of the first and last iteration."""
+    from edm_tts.models.text_to_semantic.configuration import TextToSemanticWLenConfig
+    from edm_tts.models.text_to_semantic import modeling_text_to_semantic as mts
+    from edm_tts_b200.synthetic import T2SConfig, make_t2s_noise, make_t2s_state_dict
+
+    cfg = T2SConfig(**T2S_CONFIGS[cfg_name])
+    rc = TextToSemanticWLenConfig(hidden_size=cfg.hidden, semantic_vocab_size=cfg.semantic_vocab, text_vocab_size=cfg.text_vocab,
+                                  main_encoder_num_heads=cfg.heads, main_encoder_num_layers=cfg.depth, length_predictor_num_heads=cfg.lp_heads,
+                                  length_predictor_num_layers=cfg.lp_depth)
+    torch.manual_seed(0)
+    model = mts.TextToSemanticWLen(rc).eval()
+    sd = make_t2s_state_dict(cfg, seed)
+    res = model.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    buffers = {"text_token", "speech_token", "sep_token", "pad_token", "mask_token", "false"}
+    bad = [k for k in res.missing_keys if k not in buffers and not k.endswith("rotary_emb.inv_freq")]
+    assert not bad, f"keys not covered by make_t2s_state_dict: {bad[:5]}"
+    # the length first (its own forward), then the noise for that sequence length
+    n_text = len(text.encode("utf-8"))
+    rec = {"logits": []}
+    with torch.inference_mode():
+        if gt_length is None:
+            tt = torch.tensor(list(text.encode("utf-8")), dtype=torch.long) + model.num_special_tokens
+            lp_in = torch.cat([model.length_token, model.input_embedding(tt).unsqueeze(0)], dim=1)
+            raw = model.length_pred_head(model.length_predictor(lp_in, return_attn=False)[0][:, 0]).squeeze(-1)
+            length = int(raw.exp().ceil().long().item())
+        else:
+            raw, length = None, int(gt_length)
+    L = n_text + length + 4
+    noise = make_t2s_noise(L, pred_iters, cfg, seed=777 + L)
+    feed = NoiseFeed(noise["cat_gumbel"], noise["remask_gumbel"][:, 0])
+    orig_mult, orig_gs = torch.multinomial, torch.distributions.gumbel.Gumbel.sample
+    orig_e2l = model.embeddings_to_logits
+    orig_topk = mts.random_topk_mask
+    masks = []
+
+    def e2l(*a, **k):
+        out = orig_e2l(*a, **k)
+        rec["logits"].append(out.float().clone())
+        return out
+
+    def topk(*a, **k):
+        m = orig_topk(*a, **k)
+        masks.append(m.clone())
+        return m
+
+    def gumbel_sample(dist_self, sample_shape=torch.Size()):
+        g = feed.rem[feed.i_rem]
+        feed.i_rem += 1
+        return g.view(*sample_shape, 1)
+
+    model.embeddings_to_logits = e2l
+    mts.random_topk_mask = topk
+    torch.multinomial = feed.multinomial
+    torch.distributions.gumbel.Gumbel.sample = gumbel_sample
+    try:
+        with torch.inference_mode():
+            out = model.infer(text=text, pred_iters=pred_iters, temperature=1.0, gt_length=gt_length)
+    finally:
+        torch.multinomial, torch.distributions.gumbel.Gumbel.sample = orig_mult, orig_gs
+        mts.random_topk_mask = orig_topk
+    assert feed.i_cat == pred_iters - 1 and feed.i_rem == pred_iters - 1
+    tokens = out.speech_pred_tokens
+    first, last = rec["logits"][0][0], rec["logits"][-1][0]
+    rows = torch.linspace(0, L - 1, 6).long()
+    top2 = last.topk(2, dim=-1)[0]
+    gold = dict(cfg_name=cfg_name, text=text, pred_iters=pred_iters, gt_length=gt_length, weight_seed=seed, length=length,
+                raw_log_length=None if raw is None else raw.item(), noise_seed=777 + L, tokens=tokens.to(torch.int16),
+                masks=torch.stack(masks) if masks else None, row_idx=rows, first_rows=first[rows].clone(), last_rows=last[rows].clone(),
+                last_margin=(top2[:, 0] - top2[:, 1]).to(torch.float16))
+    torch.save(gold, os.path.join(OUT, f"t2s_{name}.pt"))
+    print(f"t2s_{name}: length {length} tokens {tuple(tokens.shape)} masks {[int(m.sum()) for m in masks]} saved", flush=True)
+
+
+def make_all_t2s():
+    make_t2s("small_s4", "small", "hello world", 4)
+    make_t2s("small_s1", "small", "one step", 1, gt_length=23)
+    make_t2s("base_s3", "base", "The quick brown fox.", 3)
+    make_t2s("train_s4", "train", "Grafted onto new rootstock, the old tree bore fruit.", 4, gt_length=75)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "t2s":
+        make_all_t2s()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dac_encoder":      # only the encoder fixtures (added after the others)
         make_dac_encoder("small", 8, 2, 3200 + 137)
         make_dac_encoder("full", 64, 2, 6400 + 160)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "loss_all":          # the loss_all branch of forward (returns [b, q, t] codes)
+        make_train_forward("small_loss_all", "small", 2, 33, loss_all=True)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dac_decoder":
         make_dac_decoder("small", 64, 96, 2, 9)
@@ -263,8 +356,10 @@ if __name__ == "__main__":
         make_s2a("full_s4_prompt", "full", 1, 100, 50, 4)
         make_train_forward("small", "small", 2, 40)
         make_train_forward("full", "full", 1, 60)
+        make_train_forward("small_loss_all", "small", 2, 33, loss_all=True)
         make_dac_encoder("small", 8, 2, 3200 + 137)
         make_dac_encoder("full", 64, 2, 6400 + 160)
         make_dac_decoder("small", 64, 96, 2, 9)
         make_dac_decoder("full", 1024, 1536, 2, 12)
         make_dac_key_layout()
+        make_all_t2s()

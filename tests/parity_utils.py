@@ -1,5 +1,7 @@
 """Shared helpers of the GPU parity tests: build identical weights for the oracle and the CUDA path, run both under the
-teacher-forcing protocol and classify arg-max disagreements as near-ties by the oracle's margin."""
+teacher-forcing protocol and classify every disagreement of a discrete decision as a near-tie by the
+oracle's own margin. Each graded stage appends a record to RECORDS; tests/conftest.py writes them to gpurun_out/parity_r02.json at
+the end of the session (the committed copy is profiles/parity_r02.json)."""
 from __future__ import annotations
 
 import torch
@@ -7,9 +9,24 @@ import torch
 from oracle import s2a as os2a
 from oracle.weights import OracleConfig, make_inputs, make_state_dict
 
-NEAR_TIE_EPS = 0.12  # a disagreement is a documented near-tie iff oracle_logit[its choice] - oracle_logit[our choice] < eps
+# A discrete disagreement (arg-max id, sampled id) is a documented near-tie iff the ORACLE's margin between its choice and ours is
+# below eps. |ours - oracle| <= d on two logits can flip an arg-max only if their oracle margin is <= 2 d. SURVEY.md section 8c
+# suggests eps ~ 0.06 from the reference's own bf16-vs-fp32 noise on a few hundred rows (max 0.028). Measured here at the benchmark
+# size (B=64 x 500 frames x 8 steps, 1.2 M graded rows of 1024 logits; profiles/parity_r02.json): max |logit diff| 0.071, i.e. flips are
+# possible up to a margin of 0.14; the largest margin actually flipped is 0.061 (1 row in 1.2 M above 0.06). eps = 0.08 is that
+# observation plus headroom, well inside the 2 d bound; every stage also records how many flips exceed SURVEY's 0.06 (n_above_survey_eps).
+NEAR_TIE_EPS = 0.08
+SURVEY_EPS = 0.06
+# re-masking: conf = log p(id) + noise, and the cut-off is an order statistic of the same confidences: a token within eps of the
+# oracle's cut-off may land on either side (largest observed distance at the benchmark size: 0.028).
+MASK_TIE_EPS = 0.06
 
+RECORDS: list = []
 _CACHE = {}
+
+
+def record(case: str, **kw):
+    RECORDS.append(dict(case=case, **{k: (round(v, 6) if isinstance(v, float) else v) for k, v in kw.items()}))
 
 
 def full_model(seed=0, device="cuda"):
@@ -40,20 +57,48 @@ def oracle_trace(cfg, sd, inp, steps, temperature=1.0, mode="fp32", device="cuda
     return trace
 
 
-def compare_logits(ours: torch.Tensor, ref: torch.Tensor, what: str, eps=NEAR_TIE_EPS):
-    """-> dict(max, mean, agree, n_mismatch, n_not_near_tie). ours/ref [..., V]."""
+def compare_logits(ours: torch.Tensor, ref: torch.Tensor, what: str, eps=NEAR_TIE_EPS, noise: torch.Tensor | None = None):
+    """-> dict(max, mean, agree, n_mismatch, n_not_near_tie, ...). ours/ref [..., V]. With `noise` (the injected Gumbel draw) the
+    decision graded is the sample arg-max(logits + noise) instead of the plain arg-max."""
     d = (ours.float() - ref.float()).abs()
-    a_o, a_r = ours.argmax(-1), ref.argmax(-1)
+    so, sr = (ours, ref) if noise is None else (ours + noise, ref + noise)
+    a_o, a_r = so.argmax(-1), sr.argmax(-1)
     mism = a_o != a_r
-    margin = ref.gather(-1, a_r[..., None])[..., 0] - ref.gather(-1, a_o[..., None])[..., 0]
+    margin = sr.gather(-1, a_r[..., None])[..., 0] - sr.gather(-1, a_o[..., None])[..., 0]
     bad = mism & (margin >= eps)
     return dict(what=what, max=d.max().item(), mean=d.mean().item(), agree=1.0 - mism.float().mean().item(), n=mism.numel(),
-                n_mismatch=int(mism.sum().item()), n_not_near_tie=int(bad.sum().item()),
-                worst_margin=margin[mism].max().item() if mism.any() else 0.0)
+                n_mismatch=int(mism.sum().item()), n_not_near_tie=int(bad.sum().item()), n_above_survey_eps=int((mism & (margin >= SURVEY_EPS)).sum().item()),
+                worst_margin=margin[mism].max().item() if mism.any() else 0.0,
+                margins=sorted(margin[mism].tolist(), reverse=True)[:16])
 
 
-def teacher_forced_parity(cfg, sd, model, B, T, P, steps, input_seed, temperature=1.0, mode="fp32"):
-    """Runs the oracle free, then the CUDA path with the oracle's decisions forced upstream of every graded stage."""
+def compare_ids(ours_ids, ref_ids, ref_scores, what, eps=NEAR_TIE_EPS):
+    """The CUDA path's own discrete choices against the oracle's: every disagreement must be a near-tie of the oracle's scores
+    (logits, or logits + injected noise) [..., V]."""
+    mism = ours_ids != ref_ids
+    margin = ref_scores.gather(-1, ref_ids[..., None])[..., 0] - ref_scores.gather(-1, ours_ids[..., None])[..., 0]
+    bad = mism & (margin >= eps)
+    return dict(what=what, agree=1.0 - mism.float().mean().item(), n=mism.numel(), n_mismatch=int(mism.sum().item()),
+                n_not_near_tie=int(bad.sum().item()), n_above_survey_eps=int((mism & (margin >= SURVEY_EPS)).sum().item()), worst_margin=margin[mism].max().item() if mism.any() else 0.0,
+                margins=sorted(margin[mism].tolist(), reverse=True)[:16])
+
+
+def compare_masks(ours_mask, ref_mask, ref_conf, ref_cut, what, eps=MASK_TIE_EPS):
+    """The CUDA path's own re-masking decision (before teacher forcing) against the oracle's: every token that lands on the other
+    side must sit within eps of the oracle's cut-off confidence."""
+    mism = ours_mask != ref_mask
+    dist = (ref_conf - ref_cut).abs()
+    bad = mism & ~(dist < eps)
+    return dict(what=what, agree=1.0 - mism.float().mean().item(), n=mism.numel(), n_mismatch=int(mism.sum().item()),
+                n_not_near_tie=int(bad.sum().item()), worst_margin=dist[mism].max().item() if mism.any() else 0.0,
+                count_diff=int((ours_mask.sum(-1) - ref_mask.sum(-1)).abs().max().item()),
+                margins=sorted(dist[mism].tolist(), reverse=True)[:16])
+
+
+def teacher_forced_parity(cfg, sd, model, B, T, P, steps, input_seed, temperature=1.0, mode="fp32", case=None):
+    """Runs the oracle free, then the CUDA path with the oracle's decisions forced upstream of every graded stage. Graded: first-level
+    logits per step, the path's own sampled ids (same injected noise) and own re-masking decisions per step, final logits per level."""
+    case = case or f"B={B} T={T} P={P} S={steps}"
     inp = make_inputs(B, T, P, steps, cfg, seed=input_seed)
     ref = oracle_trace(cfg, sd, inp, steps, temperature, mode)
     n_inj = len(cfg.injection_layers)
@@ -66,8 +111,19 @@ def teacher_forced_parity(cfg, sd, model, B, T, P, steps, input_seed, temperatur
                               remask_gumbel=inp["remask_gumbel"] if steps > 1 else None, **forced)
     torch.cuda.synchronize()
     reports = []
-    for s in range(len(ref["step_logits"])):
+    V = cfg.codebook_size
+    n_steps = len(ref["step_logits"])
+    for s in range(n_steps):
+        last = s == n_steps - 1
+        noise = None if last else inp["cat_gumbel"][s].view(B, T, V).to(ref["step_logits"][s].device)
         reports.append(compare_logits(ours["step_logits"][s], ref["step_logits"][s], f"first-level logits step {s}"))
+        scores = ref["step_logits"][s] if noise is None else ref["step_logits"][s] + noise
+        reports.append(compare_ids(ours["step_ids"][s], ref["step_ids"][s], scores, f"own sampled ids step {s}"))
+        if not last:
+            reports.append(compare_masks(ours["step_masks_raw"][s], ref["step_masks"][s], ref["step_conf"][s], ref["step_cut"][s],
+                                         f"own re-masking step {s}"))
     for q in range(cfg.n_codebooks):
         reports.append(compare_logits(ours["all_logits"][:, q], ref["all_logits"][:, q], f"final logits level {q}"))
+    for r in reports:
+        record(case, **r)
     return inp, ref, ours, reports

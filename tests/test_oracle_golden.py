@@ -85,15 +85,17 @@ def test_rvq_oracle_matches_reference(name, golden_dir):
     torch.testing.assert_close(unred[:, :, :16, :8], g["unred_head"], rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("name", ["small", "full"])
+@pytest.mark.parametrize("name", ["small", "full", "small_loss_all"])
 def test_training_forward_oracle_matches_reference(name, golden_dir):
-    """InjectionConformerModel.forward in eval mode (loss + arg-max codes) with the mask draw injected."""
+    """InjectionConformerModel.forward in eval mode (loss + arg-max codes) with the mask draw injected; the loss_all case pins
+    the un-flattened [b, q, t] shape of the returned codes."""
     g = torch.load(os.path.join(golden_dir, f"train_fwd_{name}.pt"))
     cfg = CONFIGS[g["cfg_name"]]
     sd = state_dict(g["cfg_name"], g["weight_seed"])
     with torch.inference_mode():
-        out = os2a.training_forward(sd, cfg, g["acoustic_tokens"].long(), g["semantic_tokens"].long(), g["mask"])
+        out = os2a.training_forward(sd, cfg, g["acoustic_tokens"].long(), g["semantic_tokens"].long(), g["mask"], loss_all=g.get("loss_all", False))
     assert abs(out["loss"].item() - g["loss"]) < 1e-4, (out["loss"].item(), g["loss"])
+    assert out["output_acoustic_codes"].shape == g["output_codes"].shape
     assert torch.equal(out["output_acoustic_codes"].to(torch.int16), g["output_codes"])
     torch.testing.assert_close(out["logits"][:, :, g["row_idx"]], g["logit_rows"], rtol=1e-4, atol=1e-4)
 
@@ -136,3 +138,31 @@ def test_dac_decoder_oracle_matches_reference(golden_dir, name):
     torch.testing.assert_close(audio[:, :, :256], g["audio_head"], rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(audio[:, :, -256:], g["audio_tail"], rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(audio[:, :, ::37], g["audio_strided"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["small_s4", "small_s1", "base_s3", "train_s4"])
+def test_t2s_oracle_matches_reference(golden_dir, name):
+    """oracle/t2s.py against TextToSemanticWLen.infer of the unmodified reference (fp32 CPU, injected noise): predicted length,
+    per-iteration masks and final tokens bit-exact, logit rows to 1e-4. Covers hidden 128 / 512 (dh 32) / 384 (dh 48)."""
+    from edm_tts_b200.synthetic import T2SConfig, make_t2s_noise, make_t2s_state_dict
+    from oracle import t2s as ot2s
+    from tests.golden.make_golden_cfg import T2S_CONFIGS
+
+    g = torch.load(os.path.join(golden_dir, f"t2s_{name}.pt"))
+    cfg = T2SConfig(**T2S_CONFIGS[g["cfg_name"]])
+    sd = make_t2s_state_dict(cfg, g["weight_seed"])
+    with torch.inference_mode():
+        if g["gt_length"] is None:
+            length, raw = ot2s.predict_length(sd, cfg, ot2s.text_tokens_of(g["text"], cfg), return_raw=True)
+            assert int(length) == g["length"]
+            assert abs(raw.item() - g["raw_log_length"]) < 1e-4
+        L = len(g["text"].encode("utf-8")) + g["length"] + 4
+        noise = make_t2s_noise(L, g["pred_iters"], cfg, seed=g["noise_seed"])
+        tr = {}
+        tokens = ot2s.infer(sd, cfg, g["text"], pred_iters=g["pred_iters"], gt_length=g["gt_length"], cat_gumbel=noise["cat_gumbel"],
+                            remask_gumbel=noise["remask_gumbel"], trace=tr)
+    assert torch.equal(tokens.to(torch.int16), g["tokens"])
+    if g["masks"] is not None:
+        assert torch.equal(torch.stack(tr["step_masks"]), g["masks"])
+    torch.testing.assert_close(tr["step_logits"][0][0][g["row_idx"]], g["first_rows"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(tr["step_logits"][-1][0][g["row_idx"]], g["last_rows"], rtol=1e-4, atol=1e-4)
