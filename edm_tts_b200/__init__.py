@@ -2,7 +2,7 @@
 
 (The directory is named edm_tts_b200 because "edm-tts_b200" is not an importable Python identifier.)
 """
-from .config import DACConfig, InjectionConformerConfig  # noqa: F401
+from .config import DACConfig, InjectionConformerConfig, TextToSemanticWLenConfig  # noqa: F401
 
 
 def __getattr__(name):
@@ -10,6 +10,9 @@ def __getattr__(name):
     if name == "InjectionConformerModel":
         from .s2a import InjectionConformerModel
         return InjectionConformerModel
+    if name == "TextToSemanticWLen":
+        from .t2s import TextToSemanticWLen
+        return TextToSemanticWLen
     if name == "ResidualVectorQuantize":
         from .dac_rvq import ResidualVectorQuantize
         return ResidualVectorQuantize

@@ -22,6 +22,13 @@ class S2AConfig(C.Structure):
     ]
 
 
+class T2SConfig(C.Structure):
+    _fields_ = [
+        ("hidden", C.c_int), ("heads", C.c_int), ("depth", C.c_int), ("lp_heads", C.c_int), ("lp_depth", C.c_int), ("ff_mult", C.c_int),
+        ("conv_kernel", C.c_int), ("text_vocab", C.c_int), ("semantic_vocab", C.c_int), ("num_special", C.c_int), ("max_positions", C.c_int),
+    ]
+
+
 class EdmError(RuntimeError):
     pass
 
@@ -64,6 +71,19 @@ _SIGNATURES = {
     "edm_s2a_step": (_i, [_vp, _i, _i, _f, _ull, _vp, _vp, _vp, _vp, _vp]),
     "edm_s2a_full_pass": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "edm_s2a_decode": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _ull, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "edm_t2s_num_weights": (_i, [C.POINTER(T2SConfig)]),
+    "edm_t2s_weight_name": (C.c_char_p, [C.POINTER(T2SConfig), _i]),
+    "edm_t2s_create": (_vp, [C.POINTER(T2SConfig), C.POINTER(_vp), _i]),
+    "edm_t2s_destroy": (None, [_vp]),
+    "edm_t2s_workspace_bytes": (_sz, [_vp, _i]),
+    "edm_t2s_bind": (_i, [_vp, _vp, _sz, _i]),
+    "edm_t2s_buffer": (_vp, [_vp, C.c_char_p, C.POINTER(_sz)]),
+    "edm_t2s_predict_length": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "edm_t2s_begin": (_i, [_vp, _vp, _i, _i, _vp]),
+    "edm_t2s_logits": (_i, [_vp, _vp, _vp]),
+    "edm_t2s_step": (_i, [_vp, _i, _i, _f, _ull, _vp, _vp, _vp, _vp, _vp]),
+    "edm_t2s_result": (_i, [_vp, _vp, _vp]),
+    "edm_t2s_decode": (_i, [_vp, _vp, _i, _i, _i, _f, _ull, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

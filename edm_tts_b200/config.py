@@ -1,4 +1,4 @@
-"""Configuration mirror of the reference's InjectionConformerConfig / DACConfig.
+"""Configuration mirror of the reference's InjectionConformerConfig / DACConfig / TextToSemanticWLenConfig.
 
 Reads the same HF-style config.json (edm_tts/models/injection_conformer/configuration.py:4-65,
 edm_tts/models/dac/configuration.py:6-20) and also accepts the reference's own config objects (duck-typed).
@@ -88,3 +88,38 @@ class InjectionConformerConfig:
             with open(dac_path) as f:
                 dac = json.load(f)
         return cls.from_any(raw, dac)
+
+
+@dataclass
+class TextToSemanticWLenConfig:
+    """edm_tts/models/text_to_semantic/configuration.py:4-86 (the fields the decode path reads)."""
+    hidden_size: int = 512
+    semantic_vocab_size: int = 1024
+    text_vocab_size: int = 256
+    main_encoder_args: dict = field(default_factory=lambda: dict(depth=8, heads=16, ff_mult=4, conv_kernel_size=5))
+    length_predictor_args: dict = field(default_factory=lambda: dict(depth=4, heads=16, ff_mult=4, conv_kernel_size=5))
+    special_tokens: dict = field(default_factory=lambda: dict(pad=0, text=1, speech=2, sep=3, mask=4))
+
+    @classmethod
+    def from_any(cls, obj) -> "TextToSemanticWLenConfig":
+        if isinstance(obj, cls):
+            return obj
+        if obj is None:
+            return cls()
+        get = (lambda k, d: obj.get(k, d)) if isinstance(obj, dict) else (lambda k, d: getattr(obj, k, d))
+        base = cls()
+        main = dict(base.main_encoder_args, **(get("main_encoder_args", None) or {}))
+        lp = dict(base.length_predictor_args, **(get("length_predictor_args", None) or {}))
+        if isinstance(obj, dict):                      # constructor-style keys of configuration.py (main_encoder_num_heads, ...)
+            for short, key in (("heads", "num_heads"), ("depth", "num_layers"), ("ff_mult", "ff_mult"), ("conv_kernel_size", "conv_kernel_size")):
+                if f"main_encoder_{key}" in obj and "main_encoder_args" not in obj:
+                    main[short] = obj[f"main_encoder_{key}"]
+                if f"length_predictor_{key}" in obj and "length_predictor_args" not in obj:
+                    lp[short] = obj[f"length_predictor_{key}"]
+        return cls(hidden_size=get("hidden_size", 512), semantic_vocab_size=get("semantic_vocab_size", 1024), text_vocab_size=get("text_vocab_size", 256),
+                   main_encoder_args=main, length_predictor_args=lp, special_tokens=dict(get("special_tokens", base.special_tokens)))
+
+    @classmethod
+    def from_pretrained(cls, path: str) -> "TextToSemanticWLenConfig":
+        with open(os.path.join(path, "config.json")) as f:
+            return cls.from_any(json.load(f))

@@ -311,7 +311,7 @@ int launch_gemm(int epi, const CUtensorMap& ma, const WMap& mb, const GemmParams
 #ifdef EDM_ATTN_TRACE
 unsigned long long* g_attn_trace = nullptr;
 #endif
-int launch_attention(const CUtensorMap& mqkv, int B, int N, int H, void* out, uint32_t lbo, uint32_t sbo, uint32_t kstep, cudaStream_t st) {
+int launch_attention(const CUtensorMap& mqkv, int B, int N, int H, void* out, uint32_t lbo, uint32_t sbo, uint32_t kstep, cudaStream_t st, float scale = 0.125f) {
   static DeviceOnce attr_once;
   if (attr_once.needed()) {
     EDM_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
@@ -322,7 +322,7 @@ int launch_attention(const CUtensorMap& mqkv, int B, int N, int H, void* out, ui
   p.q_col0 = 0; p.k_col0 = H * 64; p.v_col0 = 2 * H * 64;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.ldo = static_cast<long long>(H) * 64;
-  p.scale_log2e = 0.125f * 1.4426950408889634f;
+  p.scale_log2e = scale * 1.4426950408889634f;  // softmax scale = dim_head^-1/2 (0.125 for the 64-wide heads of the S2A model)
   p.v_lbo = lbo; p.v_sbo = sbo; p.v_kstep = kstep; p.reverse = next_direction();
 #ifdef EDM_ATTN_TRACE
   p.trace = g_attn_trace;
@@ -519,7 +519,7 @@ extern "C" int edm_remask(const float* logp, const float* gumbel, const uint8_t*
   if (T > kRemaskMaxT) return fail(EDM_ERR_INVALID, "remask supports T <= %d", kRemaskMaxT);
   RemaskParams p;
   p.logp = logp; p.gumbel = gumbel; p.mask_old = mask_old; p.mask_new = mask_new; p.mask_raw = nullptr; p.forced_mask = forced_mask;
-  p.T = T; p.ratio = ratio; p.temp_ratio = temp_ratio; p.seed = seed; p.seed_dev = nullptr; p.step = step; p.row0 = 0;
+  p.T = T; p.init_count = 0; p.ratio = ratio; p.temp_ratio = temp_ratio; p.seed = seed; p.seed_dev = nullptr; p.step = step; p.row0 = 0;
   remask_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
   EDM_LAUNCH_CHECK("remask");
   return 0;
@@ -1219,7 +1219,7 @@ extern "C" int edm_s2a_step(edm_s2a_ctx* c, int step, int steps, float temperatu
     const double ratio_d = std::cos(M_PI / 2.0 * (static_cast<double>(step + 1) / static_cast<double>(steps)));
     RemaskParams rp;
     rp.logp = c->logp; rp.gumbel = remask_noise; rp.mask_old = m_old; rp.mask_new = c->mask_next(); rp.mask_raw = c->mask_raw; rp.forced_mask = forced_mask;
-    rp.T = c->T; rp.ratio = static_cast<float>(ratio_d); rp.temp_ratio = static_cast<float>(static_cast<double>(temperature) * ratio_d);
+    rp.T = c->T; rp.init_count = 0; rp.ratio = static_cast<float>(ratio_d); rp.temp_ratio = static_cast<float>(static_cast<double>(temperature) * ratio_d);
     rp.seed = seed; rp.seed_dev = c->seed_dev; rp.step = static_cast<unsigned>(step); rp.row0 = c->batch_offset * c->T;
     remask_kernel<<<c->B, 256, 0, st>>>(rp);
     EDM_LAUNCH_CHECK("remask");
@@ -1333,4 +1333,436 @@ extern "C" int edm_s2a_decode(edm_s2a_ctx* c, const int* sem_tokens, const int* 
     }
   }
   return edm_s2a_full_pass(c, nullptr, forced_coarse, codes_out, stream);
+}
+
+// ================================================================================================ text-to-semantic context
+// TextToSemanticWLen.infer (edm_tts/models/text_to_semantic/modeling_text_to_semantic.py:184-267): length predictor + `pred_iters`
+// iterations of (embed -> conformer -> pred_transform -> pred_head -> sample -> re-mask) on ONE sequence (the reference's infer is
+// batch-1). Hidden sizes 128..1024 in steps of 128, heads of <= 64 dims: the fused QKV projection is packed with every head
+// zero-padded to 64 columns (first half of the rotary pair in columns [0, dh/2), second half in [32, 32 + dh/2)), so the GEMM's
+// rotary epilogue and the tcgen05 attention kernel of the S2A path run unchanged; only the softmax scale dh^-1/2 differs.
+#include "t2s.cuh"
+
+namespace {
+const char* const kT2sGlobalFields[] = {"emb", "length_token", "pt_w", "pt_b", "pt_ln_w", "pt_ln_b", "head_w", "head_b",
+                                        "len_w", "len_b", "rope_cos", "rope_sin", "lp_rope_cos", "lp_rope_sin"};
+enum T2sGlobal { TG_EMB, TG_LENGTH_TOKEN, TG_PT_W, TG_PT_B, TG_PT_LN_W, TG_PT_LN_B, TG_HEAD_W, TG_HEAD_B,
+                 TG_LEN_W, TG_LEN_B, TG_ROPE_COS, TG_ROPE_SIN, TG_LP_ROPE_COS, TG_LP_ROPE_SIN, TG_COUNT };
+}  // namespace
+
+struct edm_t2s_ctx {
+  edm_t2s_config cfg;
+  std::vector<const void*> w;      // (depth + lp_depth) * F_BLOCK_COUNT + TG_COUNT; main blocks first, then the length predictor's
+  std::vector<BlockMaps> bmaps;
+  WMap pt_map, head_map;
+  int d = 0, ff = 0, C = 0, hp = 0, lp_hp = 0, hp_max = 0, total_tokens = 0;
+  // bound workspace
+  bool bound = false;
+  int max_len = 0;
+  float *x, *y, *logits, *logp, *raw_len;
+  __nv_bfloat16 *z, *h, *qkv, *att, *g, *zt;
+  int *ids, *ids_raw, *tokens, *input_ids, *text;
+  uint8_t *full_mask, *mask_a, *mask_b, *mask_raw;
+  // current request
+  bool begun = false, mask_in_a = true;
+  int L = 0, n_text = 0, length = 0;
+  CUtensorMap m_z, m_h, m_att, m_g, m_zt, m_qkv;
+
+  const void* bw(int blk, int f) const { return w[static_cast<size_t>(blk) * F_BLOCK_COUNT + f]; }
+  const float* bwf(int blk, int f) const { return static_cast<const float*>(bw(blk, f)); }
+  const void* gw(int f) const { return w[static_cast<size_t>(cfg.depth + cfg.lp_depth) * F_BLOCK_COUNT + f]; }
+  const float* gwf(int f) const { return static_cast<const float*>(gw(f)); }
+  uint8_t* mask_cur() { return mask_in_a ? mask_a : mask_b; }
+  uint8_t* mask_next() { return mask_in_a ? mask_b : mask_a; }
+};
+
+namespace {
+
+int t2s_validate(const edm_t2s_config* c) {
+  if (c == nullptr) return fail(EDM_ERR_INVALID, "null config");
+  const int d = c->hidden;
+  if (d != 128 && d != 256 && d != 384 && d != 512 && d != 1024)
+    return fail(EDM_ERR_INVALID, "text-to-semantic kernels are built for hidden 128 / 256 / 384 / 512 / 1024 (got %d)", d);
+  if (c->ff_mult != 4 || c->conv_kernel != 5) return fail(EDM_ERR_INVALID, "kernels are specialised for ff_mult=4 conv_kernel=5 (got %d %d)", c->ff_mult, c->conv_kernel);
+  for (int heads : {c->heads, c->lp_heads}) {
+    if (heads < 1 || d % heads != 0) return fail(EDM_ERR_INVALID, "hidden %d is not divisible by %d heads", d, heads);
+    const int dh = d / heads;
+    if (dh > 64 || dh % 8 != 0) return fail(EDM_ERR_INVALID, "head dim %d unsupported (multiple of 8, <= 64)", dh);
+  }
+  if (c->depth < 1 || c->depth > 64 || c->lp_depth < 1 || c->lp_depth > 64) return fail(EDM_ERR_INVALID, "unsupported depth");
+  if (c->semantic_vocab != 1024) return fail(EDM_ERR_INVALID, "the sampling kernel is built for 1024 semantic tokens (got %d)", c->semantic_vocab);
+  if (c->text_vocab < 1 || c->num_special != 5) return fail(EDM_ERR_INVALID, "unsupported vocabulary (text %d, special %d)", c->text_vocab, c->num_special);
+  if (c->max_positions < 8 || c->max_positions > kRemaskMaxT) return fail(EDM_ERR_INVALID, "max_positions must be in [8, %d]", kRemaskMaxT);
+  return 0;
+}
+
+int launch_ln_g(int d, const LnGParams& p, cudaStream_t st) {
+  if (p.rows <= 0) return 0;
+  const int grid = (p.rows + 7) / 8;
+  switch (d) {
+    case 128: layernorm_g_kernel<1><<<grid, 256, 0, st>>>(p); break;
+    case 256: layernorm_g_kernel<2><<<grid, 256, 0, st>>>(p); break;
+    case 384: layernorm_g_kernel<3><<<grid, 256, 0, st>>>(p); break;
+    case 512: layernorm_g_kernel<4><<<grid, 256, 0, st>>>(p); break;
+    case 1024: layernorm_g_kernel<8><<<grid, 256, 0, st>>>(p); break;
+    default: return fail(EDM_ERR_INVALID, "layernorm: hidden %d", d);
+  }
+  EDM_LAUNCH_CHECK("layernorm_g");
+  return 0;
+}
+
+template <int kC>
+int launch_conv_tiled_t(const ConvModParams& p, cudaStream_t st) {
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
+    EDM_CUDA((cudaFuncSetAttribute(conv_module_kernel<false, kC>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv_smem_bytes(kC))));
+    attr_once.done();
+  }
+  dim3 grid((p.N + kConvTT - 1) / kConvTT, p.B);
+  conv_module_kernel<false, kC><<<grid, kC / 4, conv_smem_bytes(kC), st>>>(p);
+  EDM_LAUNCH_CHECK("conv_module");
+  return 0;
+}
+// gated input [B*N, C] -> depthwise conv, Swish, ChanLayerNorm for C inner channels (tiled kernel; sequences here are a few hundred tokens)
+int launch_conv_tiled(int C, const ConvModParams& p, cudaStream_t st) {
+  switch (C) {
+    case 256: return launch_conv_tiled_t<256>(p, st);
+    case 512: return launch_conv_tiled_t<512>(p, st);
+    case 768: return launch_conv_tiled_t<768>(p, st);
+    case 1024: return launch_conv_tiled_t<1024>(p, st);
+    case 2048: return launch_conv_tiled_t<2048>(p, st);
+  }
+  return fail(EDM_ERR_INVALID, "conv module: %d inner channels", C);
+}
+
+LnGParams lng(const void* in, int rows, const float* w1, const float* b1, const float* w2, const float* b2, float* y, __nv_bfloat16* z) {
+  LnGParams p;
+  p.in = in; p.in_is_bf16 = 0; p.gather = nullptr; p.gather_rows = 0; p.row0_override = nullptr; p.rows = rows;
+  p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.y_out = y; p.z_out = z; p.eps = 1e-5f; p.pre_gelu = 0;
+  return p;
+}
+
+// tensor maps of the activation buffers for a pass over M rows with padded head width hp
+int t2s_maps(edm_t2s_ctx* c, int M, int hp) {
+  int rc = 0;
+  rc = rc ? rc : make_tmap_2d(&c->m_z, c->z, M, c->d, c->d, kGemmBM);
+  rc = rc ? rc : make_tmap_2d(&c->m_h, c->h, M, c->ff, c->ff, kGemmBM);
+  rc = rc ? rc : make_tmap_2d(&c->m_att, c->att, M, hp, hp, kGemmBM);
+  rc = rc ? rc : make_tmap_2d(&c->m_g, c->g, M, c->C, c->C, kGemmBM);
+  rc = rc ? rc : make_tmap_2d(&c->m_zt, c->zt, M, c->d, c->d, kGemmBM);
+  rc = rc ? rc : make_tmap_3d(&c->m_qkv, c->qkv, 1, M, 3ull * hp);
+  return rc;
+}
+
+// One ConformerBlock (conformer/conformer.py:219-235) on M rows of one sequence. In: x (fp32 stream), z = LN_ff1(x). Out: x = pre-post_norm sum.
+int t2s_block_body(edm_t2s_ctx* c, int blk, int M, int H, int hp, const float* rope_cos, const float* rope_sin, cudaStream_t st) {
+  const int d = c->d, ff = c->ff, C = c->C;
+  const BlockMaps& bm = c->bmaps[blk];
+  if (int rc = launch_gemm(EPI_SWISH_BF16, c->m_z, bm.ff1_w1, gp(M, ff, d, c->bwf(blk, F_FF1_B1), c->h, ff), st)) return rc;
+  if (int rc = launch_gemm(EPI_RESID_F32, c->m_h, bm.ff1_w2, gp(M, d, ff, c->bwf(blk, F_FF1_B2), c->x, d, 0.5f), st)) return rc;
+  if (int rc = launch_ln_g(d, lng(c->x, M, c->bwf(blk, F_ATTN_LN_W), c->bwf(blk, F_ATTN_LN_B), nullptr, nullptr, nullptr, c->z), st)) return rc;
+  {
+    GemmParams p = gp(M, 3 * hp, d, nullptr, c->qkv, 3 * hp);
+    p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.seq_len = M; p.rope_cols = 2 * hp;
+    if (int rc = launch_gemm(EPI_QKV_ROPE, c->m_z, bm.wqkv, p, st)) return rc;
+  }
+  const float scale = 1.0f / sqrtf(static_cast<float>(d / H));
+  if (int rc = launch_attention(c->m_qkv, 1, M, H, c->att, 1024, 1024, 2048, st, scale)) return rc;
+  if (int rc = launch_gemm(EPI_RESID_F32, c->m_att, bm.wo, gp(M, d, hp, c->bwf(blk, F_BO), c->x, d, 1.0f), st)) return rc;
+  if (int rc = launch_ln_g(d, lng(c->x, M, c->bwf(blk, F_CONV_LN_W), c->bwf(blk, F_CONV_LN_B), nullptr, nullptr, nullptr, c->z), st)) return rc;
+  if (int rc = launch_gemm(EPI_GLU_BF16, c->m_z, bm.pw1, gp(M, 2 * C, d, c->bwf(blk, F_PW1_B), c->h, C), st)) return rc;
+  {
+    ConvModParams p;
+    p.in = c->h; p.out = c->g; p.dw_w = c->bwf(blk, F_DW_W); p.dw_b = c->bwf(blk, F_DW_B); p.cln_w = c->bwf(blk, F_CLN_W); p.B = 1; p.N = M;
+    if (int rc = launch_conv_tiled(C, p, st)) return rc;
+  }
+  if (int rc = launch_gemm(EPI_RESID_F32, c->m_g, bm.pw2, gp(M, d, C, c->bwf(blk, F_PW2_B), c->x, d, 1.0f), st)) return rc;
+  if (int rc = launch_ln_g(d, lng(c->x, M, c->bwf(blk, F_FF2_LN_W), c->bwf(blk, F_FF2_LN_B), nullptr, nullptr, nullptr, c->z), st)) return rc;
+  if (int rc = launch_gemm(EPI_SWISH_BF16, c->m_z, bm.ff2_w1, gp(M, ff, d, c->bwf(blk, F_FF2_B1), c->h, ff), st)) return rc;
+  if (int rc = launch_gemm(EPI_RESID_F32, c->m_h, bm.ff2_w2, gp(M, d, ff, c->bwf(blk, F_FF2_B2), c->x, d, 0.5f), st)) return rc;
+  return 0;
+}
+
+// blocks [blk0, blk0 + n) on M rows; x / z prepared by the caller; after the last block x holds the pre-post_norm sum
+int t2s_stack(edm_t2s_ctx* c, int blk0, int n, int M, int H, int hp, const float* rope_cos, const float* rope_sin, cudaStream_t st) {
+  for (int i = 0; i < n; ++i) {
+    const int blk = blk0 + i;
+    if (int rc = t2s_block_body(c, blk, M, H, hp, rope_cos, rope_sin, st)) return rc;
+    if (i + 1 < n) {
+      // post_norm of this block fused with the first pre-norm of the next one
+      if (int rc = launch_ln_g(c->d, lng(c->x, M, c->bwf(blk, F_POST_LN_W), c->bwf(blk, F_POST_LN_B), c->bwf(blk + 1, F_FF1_LN_W), c->bwf(blk + 1, F_FF1_LN_B), c->x, c->z), st)) return rc;
+    }
+  }
+  return 0;
+}
+
+size_t t2s_carve(edm_t2s_ctx* c, uint8_t* base, int max_len, bool assign) {
+  const size_t M = static_cast<size_t>(max_len);
+  Carver k{base};
+  float* x = k.take<float>(M * c->d);
+  float* y = k.take<float>(M * c->d);
+  __nv_bfloat16* z = k.take<__nv_bfloat16>(M * c->d);
+  __nv_bfloat16* h = k.take<__nv_bfloat16>(M * c->ff);
+  __nv_bfloat16* qkv = k.take<__nv_bfloat16>(M * 3 * c->hp_max);
+  __nv_bfloat16* att = k.take<__nv_bfloat16>(M * c->hp_max);
+  __nv_bfloat16* g = k.take<__nv_bfloat16>(M * c->C);
+  __nv_bfloat16* zt = k.take<__nv_bfloat16>(M * c->d);
+  float* logits = k.take<float>(M * 1024);
+  float* logp = k.take<float>(M);
+  float* raw_len = k.take<float>(4);
+  int* ids = k.take<int>(M);
+  int* ids_raw = k.take<int>(M);
+  int* tokens = k.take<int>(M);
+  int* input_ids = k.take<int>(M);
+  int* text = k.take<int>(M);
+  uint8_t* full_mask = k.take<uint8_t>(M);
+  uint8_t* mask_a = k.take<uint8_t>(M);
+  uint8_t* mask_b = k.take<uint8_t>(M);
+  uint8_t* mask_raw = k.take<uint8_t>(M);
+  if (assign) {
+    c->x = x; c->y = y; c->z = z; c->h = h; c->qkv = qkv; c->att = att; c->g = g; c->zt = zt; c->logits = logits; c->logp = logp; c->raw_len = raw_len;
+    c->ids = ids; c->ids_raw = ids_raw; c->tokens = tokens; c->input_ids = input_ids; c->text = text;
+    c->full_mask = full_mask; c->mask_a = mask_a; c->mask_b = mask_b; c->mask_raw = mask_raw;
+  }
+  return align_up(k.off, 1024);
+}
+
+}  // namespace
+
+extern "C" int edm_t2s_num_weights(const edm_t2s_config* cfg) {
+  if (t2s_validate(cfg)) return EDM_ERR_INVALID;
+  return (cfg->depth + cfg->lp_depth) * F_BLOCK_COUNT + TG_COUNT;
+}
+
+extern "C" const char* edm_t2s_weight_name(const edm_t2s_config* cfg, int index) {
+  thread_local char buf[64];
+  if (t2s_validate(cfg)) return nullptr;
+  const int nb = (cfg->depth + cfg->lp_depth) * F_BLOCK_COUNT;
+  if (index < 0 || index >= nb + TG_COUNT) return nullptr;
+  if (index < nb) {
+    const int blk = index / F_BLOCK_COUNT;
+    if (blk < cfg->depth)
+      snprintf(buf, sizeof(buf), "blocks.%d.%s", blk, kBlockFields[index % F_BLOCK_COUNT]);
+    else
+      snprintf(buf, sizeof(buf), "lp_blocks.%d.%s", blk - cfg->depth, kBlockFields[index % F_BLOCK_COUNT]);
+  } else {
+    snprintf(buf, sizeof(buf), "%s", kT2sGlobalFields[index - nb]);
+  }
+  return buf;
+}
+
+extern "C" edm_t2s_ctx* edm_t2s_create(const edm_t2s_config* cfg, const void* const* weights, int n_weights) {
+  if (check_arch()) return nullptr;
+  if (t2s_validate(cfg)) return nullptr;
+  const int expect = (cfg->depth + cfg->lp_depth) * F_BLOCK_COUNT + TG_COUNT;
+  if (weights == nullptr || n_weights != expect) {
+    fail(EDM_ERR_INVALID, "expected %d weight pointers, got %d", expect, n_weights);
+    return nullptr;
+  }
+  for (int i = 0; i < expect; ++i)
+    if (weights[i] == nullptr) {
+      fail(EDM_ERR_INVALID, "weight %s is null", edm_t2s_weight_name(cfg, i));
+      return nullptr;
+    }
+  edm_t2s_ctx* c = new edm_t2s_ctx();
+  c->cfg = *cfg;
+  c->w.assign(weights, weights + expect);
+  c->d = cfg->hidden; c->ff = cfg->hidden * cfg->ff_mult; c->C = cfg->hidden * 2;
+  c->hp = cfg->heads * 64; c->lp_hp = cfg->lp_heads * 64; c->hp_max = c->hp > c->lp_hp ? c->hp : c->lp_hp;
+  c->total_tokens = cfg->text_vocab + cfg->semantic_vocab + cfg->num_special;
+  const int nblk = cfg->depth + cfg->lp_depth;
+  c->bmaps.resize(nblk);
+  int rc = 0;
+  for (int b = 0; b < nblk && rc == 0; ++b) {
+    BlockMaps& m = c->bmaps[b];
+    const int hp = b < cfg->depth ? c->hp : c->lp_hp;
+    rc = rc ? rc : make_wmap(&m.ff1_w1, c->bw(b, F_FF1_W1), c->ff, c->d, c->d);
+    rc = rc ? rc : make_wmap(&m.ff1_w2, c->bw(b, F_FF1_W2), c->d, c->ff, c->ff);
+    rc = rc ? rc : make_wmap(&m.wqkv, c->bw(b, F_WQKV), 3ull * hp, c->d, c->d);
+    rc = rc ? rc : make_wmap(&m.wo, c->bw(b, F_WO), c->d, hp, hp);
+    rc = rc ? rc : make_wmap(&m.pw1, c->bw(b, F_PW1_W), 2ull * c->C, c->d, c->d);
+    rc = rc ? rc : make_wmap(&m.pw2, c->bw(b, F_PW2_W), c->d, c->C, c->C);
+    rc = rc ? rc : make_wmap(&m.ff2_w1, c->bw(b, F_FF2_W1), c->ff, c->d, c->d);
+    rc = rc ? rc : make_wmap(&m.ff2_w2, c->bw(b, F_FF2_W2), c->d, c->ff, c->ff);
+  }
+  rc = rc ? rc : make_wmap(&c->pt_map, c->gw(TG_PT_W), c->d, c->d, c->d);
+  rc = rc ? rc : make_wmap(&c->head_map, c->gw(TG_HEAD_W), 1024, c->d, c->d);
+  if (rc) {
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+extern "C" void edm_t2s_destroy(edm_t2s_ctx* ctx) { delete ctx; }
+
+extern "C" size_t edm_t2s_workspace_bytes(const edm_t2s_ctx* ctx, int max_len) {
+  if (ctx == nullptr || max_len <= 0) return 0;
+  return t2s_carve(const_cast<edm_t2s_ctx*>(ctx), nullptr, max_len, false);
+}
+
+extern "C" int edm_t2s_bind(edm_t2s_ctx* c, void* workspace, size_t bytes, int max_len) {
+  if (c == nullptr || workspace == nullptr || max_len <= 0) return fail(EDM_ERR_INVALID, "bind arguments");
+  if (max_len > c->cfg.max_positions) return fail(EDM_ERR_INVALID, "max_len=%d exceeds the rotary tables (%d)", max_len, c->cfg.max_positions);
+  if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0) return fail(EDM_ERR_INVALID, "workspace must be 1024-byte aligned");
+  const size_t need = t2s_carve(c, nullptr, max_len, false);
+  if (bytes < need) return fail(EDM_ERR_INVALID, "workspace too small: %zu < %zu", bytes, need);
+  t2s_carve(c, static_cast<uint8_t*>(workspace), max_len, true);
+  c->max_len = max_len;
+  c->bound = true;
+  c->begun = false;
+  return 0;
+}
+
+extern "C" void* edm_t2s_buffer(edm_t2s_ctx* c, const char* name, size_t* bytes) {
+  if (c == nullptr || !c->bound || name == nullptr) return nullptr;
+  const size_t M = c->max_len;
+  struct { const char* n; void* p; size_t b; } tab[] = {
+      {"x", c->x, M * c->d * 4}, {"logits", c->logits, M * 1024 * 4}, {"logp", c->logp, M * 4}, {"raw_len", c->raw_len, 4},
+      {"ids", c->ids, M * 4}, {"ids_raw", c->ids_raw, M * 4}, {"tokens", c->tokens, M * 4}, {"input_ids", c->input_ids, M * 4},
+      {"full_mask", c->full_mask, M}, {"mask", c->mask_cur(), M}, {"mask_raw", c->mask_raw, M}};
+  for (auto& e : tab)
+    if (strcmp(e.n, name) == 0) {
+      if (bytes) *bytes = e.b;
+      return e.p;
+    }
+  return nullptr;
+}
+
+// :198-203: length predictor on [length_token, text embeddings]; raw_out[0] (device) = log of the predicted length. The caller reads it
+// back (the sequence length decides every later shape), applies exp / ceil as the reference does, and passes `length` to edm_t2s_begin.
+extern "C" int edm_t2s_predict_length(edm_t2s_ctx* c, const int* text_tokens, int n_text, float* raw_out, void* stream) {
+  if (c == nullptr || !c->bound) return fail(EDM_ERR_STATE, "context not bound");
+  if (n_text < 0 || n_text + 1 > c->max_len) return fail(EDM_ERR_INVALID, "text of %d tokens does not fit the bound workspace (%d rows)", n_text, c->max_len);
+  if (n_text > 0 && text_tokens == nullptr) return fail(EDM_ERR_INVALID, "text tokens required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int M = n_text + 1;
+  const edm_t2s_config& cfg = c->cfg;
+  // gather indices: row 0 is the length token (row0_override), rows 1.. the text embeddings
+  EDM_CUDA(cudaMemsetAsync(c->text, 0, sizeof(int), st));
+  if (n_text > 0) EDM_CUDA(cudaMemcpyAsync(c->text + 1, text_tokens, sizeof(int) * n_text, cudaMemcpyDeviceToDevice, st));
+  if (int rc = t2s_maps(c, M, c->lp_hp)) return rc;
+  const int b0 = cfg.depth;
+  LnGParams p = lng(c->gw(TG_EMB), M, nullptr, nullptr, c->bwf(b0, F_FF1_LN_W), c->bwf(b0, F_FF1_LN_B), c->x, c->z);
+  p.gather = c->text; p.gather_rows = c->total_tokens; p.row0_override = c->gwf(TG_LENGTH_TOKEN);
+  if (int rc = launch_ln_g(c->d, p, st)) return rc;
+  if (int rc = t2s_stack(c, b0, cfg.lp_depth, M, cfg.lp_heads, c->lp_hp, c->gwf(TG_LP_ROPE_COS), c->gwf(TG_LP_ROPE_SIN), st)) return rc;
+  const int last = b0 + cfg.lp_depth - 1;
+  float* out = raw_out != nullptr ? raw_out : c->raw_len;
+  switch (c->d) {
+    case 128: t2s_length_head_kernel<1><<<1, 32, 0, st>>>(c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
+    case 256: t2s_length_head_kernel<2><<<1, 32, 0, st>>>(c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
+    case 384: t2s_length_head_kernel<3><<<1, 32, 0, st>>>(c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
+    case 512: t2s_length_head_kernel<4><<<1, 32, 0, st>>>(c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
+    default: t2s_length_head_kernel<8><<<1, 32, 0, st>>>(c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
+  }
+  EDM_LAUNCH_CHECK("t2s_length_head");
+  c->begun = false;  // the activation buffers were reused
+  return 0;
+}
+
+// :205-222: the token sequence of one request and its mask state
+extern "C" int edm_t2s_begin(edm_t2s_ctx* c, const int* text_tokens, int n_text, int length, void* stream) {
+  if (c == nullptr || !c->bound) return fail(EDM_ERR_STATE, "context not bound");
+  if (n_text < 0 || length < 1) return fail(EDM_ERR_INVALID, "n_text=%d length=%d", n_text, length);
+  const long long L = static_cast<long long>(n_text) + length + 4;
+  if (L > c->max_len) return fail(EDM_ERR_INVALID, "sequence of %lld tokens exceeds the bound workspace (%d rows)", L, c->max_len);
+  if (n_text > 0 && text_tokens == nullptr) return fail(EDM_ERR_INVALID, "text tokens required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n_text > 0) EDM_CUDA(cudaMemcpyAsync(c->text, text_tokens, sizeof(int) * n_text, cudaMemcpyDeviceToDevice, st));
+  c->L = static_cast<int>(L); c->n_text = n_text; c->length = length; c->mask_in_a = true;
+  T2sBeginParams p;
+  p.text_tokens = c->text; p.n_text = n_text; p.length = length; p.tok_text = 1; p.tok_sep = 3; p.tok_speech = 2; p.tok_mask = 4;
+  p.input_ids = c->input_ids; p.tokens = c->tokens; p.full_mask = c->full_mask; p.mask = c->mask_a;
+  t2s_begin_kernel<<<(c->L + 255) / 256, 256, 0, st>>>(p);
+  EDM_LAUNCH_CHECK("t2s_begin");
+  if (int rc = t2s_maps(c, c->L, c->hp)) return rc;
+  c->begun = true;
+  return 0;
+}
+
+// embeddings_to_logits (:135-152, mask = None) -> buffer "logits" [L, 1024] fp32. x_in: fp32 [L, hidden] embeddings, or NULL to embed
+// the context's running tokens (input_embedding lookup fused into the first LayerNorm pass).
+extern "C" int edm_t2s_logits(edm_t2s_ctx* c, const float* x_in, void* stream) {
+  if (c == nullptr || !c->bound || !c->begun) return fail(EDM_ERR_STATE, "no sequence: call edm_t2s_begin first");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const edm_t2s_config& cfg = c->cfg;
+  const int M = c->L, d = c->d;
+  LnGParams p = lng(x_in != nullptr ? static_cast<const void*>(x_in) : c->gw(TG_EMB), M, nullptr, nullptr, c->bwf(0, F_FF1_LN_W), c->bwf(0, F_FF1_LN_B), c->x, c->z);
+  if (x_in == nullptr) {
+    p.gather = c->tokens;
+    p.gather_rows = c->total_tokens;
+  }
+  if (int rc = launch_ln_g(d, p, st)) return rc;
+  if (int rc = t2s_stack(c, 0, cfg.depth, M, cfg.heads, c->hp, c->gwf(TG_ROPE_COS), c->gwf(TG_ROPE_SIN), st)) return rc;
+  const int last = cfg.depth - 1;
+  // post_norm -> bf16 operand of pred_transform.0; Linear -> fp32; GELU + LayerNorm -> bf16 operand of pred_head -> fp32 logits
+  if (int rc = launch_ln_g(d, lng(c->x, M, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), nullptr, nullptr, nullptr, c->zt), st)) return rc;
+  if (int rc = launch_gemm(EPI_F32, c->m_zt, c->pt_map, gp(M, d, d, c->gwf(TG_PT_B), c->y, d), st)) return rc;
+  {
+    LnGParams q = lng(c->y, M, c->gwf(TG_PT_LN_W), c->gwf(TG_PT_LN_B), nullptr, nullptr, nullptr, c->zt);
+    q.pre_gelu = 1;
+    if (int rc = launch_ln_g(d, q, st)) return rc;
+  }
+  return launch_gemm(EPI_F32, c->m_zt, c->head_map, gp(M, 1024, d, c->gwf(TG_HEAD_B), c->logits, 1024), st);
+}
+
+// one iteration's decisions (:229-260) on the logits of edm_t2s_logits: sample / arg-max, confidence re-masking over the speech
+// positions, token update. Noise / forcing arrays are those of this iteration ([L, 1024], [L], [L], [L]) or NULL.
+extern "C" int edm_t2s_step(edm_t2s_ctx* c, int iter, int iters, float temperature, unsigned long long seed, const float* cat_noise,
+                            const float* remask_noise, const int* forced_ids, const uint8_t* forced_mask, void* stream) {
+  if (c == nullptr || !c->bound || !c->begun) return fail(EDM_ERR_STATE, "no sequence: call edm_t2s_begin first");
+  if (iters < 1 || iter < 0 || iter >= iters) return fail(EDM_ERR_INVALID, "iteration %d of %d", iter, iters);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool last = iter == iters - 1;
+  const int L = c->L;
+  SampleParams sp;
+  sp.logits = c->logits; sp.ld = 1024; sp.rows = L; sp.noise = last ? nullptr : cat_noise; sp.use_philox = last ? 0 : 1; sp.seed = seed; sp.seed_dev = nullptr;
+  sp.step = static_cast<unsigned>(iter); sp.row0 = 0; sp.forced_ids = forced_ids; sp.ids = c->ids; sp.ids_raw = c->ids_raw; sp.logp = last ? nullptr : c->logp;
+  sp.T = L; sp.Q = 1; sp.out_q_stride = 1; sp.out_q0 = 0;
+  if (int rc = launch_sample(sp, st)) return rc;
+  T2sUpdateParams up;
+  up.ids = c->ids; up.next_mask = nullptr; up.full_mask = c->full_mask; up.input_ids = c->input_ids; up.tokens = c->tokens; up.L = L;
+  up.offset = c->cfg.num_special + c->cfg.text_vocab; up.tok_mask = 4;
+  if (!last) {
+    const double ratio_d = std::cos(M_PI / 2.0 * (static_cast<double>(iter + 1) / static_cast<double>(iters)));
+    RemaskParams rp;
+    rp.logp = c->logp; rp.gumbel = remask_noise; rp.mask_old = c->mask_cur(); rp.mask_new = c->mask_next(); rp.mask_raw = c->mask_raw; rp.forced_mask = forced_mask;
+    rp.T = L; rp.init_count = c->length; rp.ratio = static_cast<float>(ratio_d); rp.temp_ratio = static_cast<float>(static_cast<double>(temperature) * ratio_d);
+    rp.seed = seed; rp.seed_dev = nullptr; rp.step = static_cast<unsigned>(iter); rp.row0 = 0;
+    remask_kernel<<<1, 256, 0, st>>>(rp);
+    EDM_LAUNCH_CHECK("remask");
+    up.next_mask = c->mask_next();
+  }
+  t2s_update_kernel<<<(L + 255) / 256, 256, 0, st>>>(up);
+  EDM_LAUNCH_CHECK("t2s_update");
+  if (!last) c->mask_in_a = !c->mask_in_a;
+  return 0;
+}
+
+// speech_pred_tokens (:267): int64 [length], semantic vocabulary
+extern "C" int edm_t2s_result(edm_t2s_ctx* c, long long* tokens_out, void* stream) {
+  if (c == nullptr || !c->bound || !c->begun) return fail(EDM_ERR_STATE, "no sequence: call edm_t2s_begin first");
+  if (tokens_out == nullptr) return fail(EDM_ERR_INVALID, "output required");
+  t2s_gather_out_kernel<<<(c->length + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(c->tokens, c->n_text + 3, c->length, tokens_out);
+  EDM_LAUNCH_CHECK("t2s_gather_out");
+  return 0;
+}
+
+// whole infer loop for a known length. Noise / forcing arrays are laid out [iteration][...] over L = n_text + length + 4 positions.
+extern "C" int edm_t2s_decode(edm_t2s_ctx* c, const int* text_tokens, int n_text, int length, int pred_iters, float temperature,
+                              unsigned long long seed, const float* cat_noise, const float* remask_noise, const int* forced_ids,
+                              const uint8_t* forced_masks, long long* tokens_out, void* stream) {
+  if (pred_iters < 1) return fail(EDM_ERR_INVALID, "pred_iters must be >= 1");
+  if (int rc = edm_t2s_begin(c, text_tokens, n_text, length, stream)) return rc;
+  const size_t L = c->L;
+  for (int i = 0; i < pred_iters; ++i) {
+    const bool last = i == pred_iters - 1;
+    if (int rc = edm_t2s_logits(c, nullptr, stream)) return rc;
+    if (int rc = edm_t2s_step(c, i, pred_iters, temperature, seed, (cat_noise && !last) ? cat_noise + i * L * 1024 : nullptr,
+                              (remask_noise && !last) ? remask_noise + i * L : nullptr, forced_ids ? forced_ids + i * L : nullptr,
+                              (forced_masks && !last) ? forced_masks + i * L : nullptr, stream))
+      return rc;
+  }
+  return edm_t2s_result(c, tokens_out, stream);
 }

@@ -161,17 +161,22 @@ struct ConvModParams {
   int B, N;
 };
 constexpr int kConvTT = 20;        // output tokens per CTA (4 halo rows are re-read: 20 % more loads, served by L2); 25 measured slower (wave quantisation)
-constexpr int kConvThreads = 512;  // 4 channels per thread
+constexpr int kConvThreads = 512;  // 4 channels per thread at the S2A model's 2048 inner channels
 constexpr uint32_t kConvSmemBytes = kConvTT * kConvThreads * 8;  // Swish outputs of the tile (bf16 x 4 per thread and token)
+constexpr uint32_t conv_smem_bytes(int channels) { return kConvTT * (channels / 4) * 8; }
 
 // kGlu = true : in is [B*N, 4096] (value | gate), the GLU runs here.
 // kGlu = false: in is [B*N, 2048], already gated by the pointwise-conv GEMM epilogue (EPI_GLU_BF16).
 // Three phases per CTA (20 tokens x 2048 channels): (1) every thread streams its 4 channels through the 5-tap window and
 // parks the Swish outputs in shared memory, (2) one warp per token reduces mean / variance over the 2048 channels,
 // (3) every thread normalises its channels. 16 warps per CTA, two CTAs per SM.
-template <bool kGlu>
-__global__ void __launch_bounds__(kConvThreads, 2) conv_module_kernel(const ConvModParams p) {
-  extern __shared__ uint2 s_keep[];  // [kConvTT][512]
+// kC = inner channels (2048 for the S2A conformer; 1024 / 768 for the text-to-semantic model's hidden 512 / 384), kC / 4 threads.
+template <bool kGlu, int kC = kConvC>
+__global__ void __launch_bounds__(kC / 4, 2) conv_module_kernel(const ConvModParams p) {
+  constexpr int kConvThreads = kC / 4;
+  constexpr int kConvC = kC;
+  static_assert(kC % 256 == 0, "one warp reduces a token's channels in 256-channel steps");
+  extern __shared__ uint2 s_keep[];  // [kConvTT][kC / 4]
   __shared__ uint32_t s_mean2[kConvTT];
   __shared__ uint32_t s_rstd2[kConvTT];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_module_kernel(const Conv
     const uint4* row = reinterpret_cast<const uint4*>(s_keep + o * kConvThreads);
     float s = 0.f, q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kC / 256; ++i) {
       const uint4 v = row[i * 32 + lane];
       const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -579,6 +584,9 @@ struct RemaskParams {
   uint8_t* mask_raw;        // [B, T] or nullptr: the kernel's own mask (before teacher forcing), for parity runs
   const uint8_t* forced_mask;  // teacher forcing: copied to mask_new when given
   int T;
+  int init_count;    // 0: the S2A rule mask_len = max(1, min(#masked - 1, floor(T * ratio))) (modeling_injection_conformer.py:199-202);
+                     // > 0: the text-to-semantic rule max(1, min(floor(init_count * ratio), init_count)) with init_count = number of
+                     // speech positions (modeling_text_to_semantic.py:237-242)
   float ratio;       // float32(cos(pi/2 (t+1)/S))
   float temp_ratio;  // float32(temperature * ratio)
   unsigned long long seed;
@@ -624,8 +632,13 @@ __global__ void __launch_bounds__(256) remask_kernel(const RemaskParams p) {
     for (int t = tid; t < p.T; t += 256) p.mask_new[base + t] = p.forced_mask[base + t];
     return;
   }
-  float ml = floorf(__fmul_rn(static_cast<float>(p.T), p.ratio));
-  ml = fmaxf(1.0f, fminf(static_cast<float>(s_count - 1), ml));
+  float ml;
+  if (p.init_count > 0) {
+    ml = fmaxf(1.0f, fminf(floorf(__fmul_rn(static_cast<float>(p.init_count), p.ratio)), static_cast<float>(p.init_count)));
+  } else {
+    ml = floorf(__fmul_rn(static_cast<float>(p.T), p.ratio));
+    ml = fmaxf(1.0f, fminf(static_cast<float>(s_count - 1), ml));
+  }
   const int k = static_cast<int>(ml);
   for (int t = tid; t < p.T; t += 256) {
     const float c = conf[t];

@@ -30,12 +30,25 @@ MAX_CHUNK = 64  # sequences decoded per bound workspace (larger batches are proc
 
 def _on_device(fn):
     """Run a public entry point with the model's device current: L.stream_ptr() and every allocation of the call then belong to the
-    device that holds the weights and the workspace, whichever device the caller had selected."""
+    device that holds the weights and the workspace, whichever device the caller had selected. The context's workspace is shared by
+    all calls, so a call issued on another stream than the previous one first waits for that one's recorded end (calls on one stream
+    are ordered anyway); while a CUDA graph is being captured the caller owns the ordering."""
     @functools.wraps(fn)
     def wrapped(self, *a, **k):
         model = getattr(self, "_m", self)
         with torch.cuda.device(model.device):
-            return fn(self, *a, **k)
+            cur = torch.cuda.current_stream()
+            capturing = torch.cuda.is_current_stream_capturing()
+            last = getattr(model, "_last_use", None)
+            if last is not None and not capturing and last[0] != cur.cuda_stream:
+                cur.wait_event(last[1])
+            try:
+                return fn(self, *a, **k)
+            finally:
+                if not capturing:
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    model._last_use = (cur.cuda_stream, ev)
     return wrapped
 
 

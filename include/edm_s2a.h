@@ -212,6 +212,55 @@ int edm_s2a_decode(edm_s2a_ctx* ctx, const int* sem_tokens, const int* sem_promp
                    int ac_prompt_levels, int steps, float temperature, unsigned long long seed, const float* cat_noise,
                    const float* remask_noise, const int* forced_ids, const uint8_t* forced_masks,
                    const int* forced_coarse, long long* codes_out, void* stream);
+/* ---------------------------------------------------------------------------------------------------------------
+ * Text-to-semantic decoder context: TextToSemanticWLen.infer, edm_tts/models/text_to_semantic/modeling_text_to_semantic.py:184-267
+ * (one sequence per call, as in the reference). Same conventions as the S2A context: weights by name, caller-owned workspace,
+ * stream-ordered, no host synchronisation inside the library.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct edm_t2s_ctx edm_t2s_ctx;
+
+typedef struct edm_t2s_config {
+  int hidden;          /* 128 / 256 / 384 / 512 / 1024 (configuration.py:16; train_config.yaml:15 uses 384) */
+  int heads;           /* main encoder heads, head dim = hidden / heads <= 64 */
+  int depth;           /* main encoder blocks */
+  int lp_heads;        /* length predictor heads */
+  int lp_depth;        /* length predictor blocks */
+  int ff_mult;         /* 4 */
+  int conv_kernel;     /* 5 */
+  int text_vocab;      /* 256 byte tokens */
+  int semantic_vocab;  /* 1024 */
+  int num_special;     /* 5: pad, text, speech, sep, mask (configuration.py:45-51) */
+  int max_positions;   /* rows of the rotary tables = longest sequence (text + speech + 4), <= 4096 */
+} edm_t2s_config;
+
+/* Weight names: "blocks.{i}.<field>" / "lp_blocks.{i}.<field>" with the S2A block fields (wqkv / wo packed with 64-column padded
+ * heads, see edm_tts_b200/t2s.py), then emb, length_token, pt_w, pt_b, pt_ln_w, pt_ln_b, head_w, head_b, len_w, len_b,
+ * rope_cos, rope_sin, lp_rope_cos, lp_rope_sin. */
+int edm_t2s_num_weights(const edm_t2s_config* cfg);
+const char* edm_t2s_weight_name(const edm_t2s_config* cfg, int index);
+edm_t2s_ctx* edm_t2s_create(const edm_t2s_config* cfg, const void* const* weights, int n_weights);
+void edm_t2s_destroy(edm_t2s_ctx* ctx);
+size_t edm_t2s_workspace_bytes(const edm_t2s_ctx* ctx, int max_len);
+int edm_t2s_bind(edm_t2s_ctx* ctx, void* workspace, size_t bytes, int max_len);
+void* edm_t2s_buffer(edm_t2s_ctx* ctx, const char* name, size_t* bytes);
+
+/* :198-203 length predictor; text_tokens int32 [n_text] on the device (bytes + num_special). raw_out[0] (device, or the buffer
+ * "raw_len" when NULL) = log(length); the caller applies exp / ceil (the sequence length fixes every later shape). */
+int edm_t2s_predict_length(edm_t2s_ctx* ctx, const int* text_tokens, int n_text, float* raw_out, void* stream);
+/* :205-222 sequence [text] bytes [sep] [speech] [mask]*length [sep] + mask state. */
+int edm_t2s_begin(edm_t2s_ctx* ctx, const int* text_tokens, int n_text, int length, void* stream);
+/* embeddings_to_logits :135-152 on the running tokens (x_in == NULL) or on given embeddings fp32 [L, hidden] -> buffer "logits". */
+int edm_t2s_logits(edm_t2s_ctx* ctx, const float* x_in, void* stream);
+/* :229-260 decisions of iteration `iter` of `iters`: sample (arg-max on the last), confidence re-masking, token update. */
+int edm_t2s_step(edm_t2s_ctx* ctx, int iter, int iters, float temperature, unsigned long long seed, const float* cat_noise,
+                 const float* remask_noise, const int* forced_ids, const uint8_t* forced_mask, void* stream);
+/* :267 speech_pred_tokens int64 [length]. */
+int edm_t2s_result(edm_t2s_ctx* ctx, long long* tokens_out, void* stream);
+/* begin + pred_iters x (logits, step) + result. */
+int edm_t2s_decode(edm_t2s_ctx* ctx, const int* text_tokens, int n_text, int length, int pred_iters, float temperature,
+                   unsigned long long seed, const float* cat_noise, const float* remask_noise, const int* forced_ids,
+                   const uint8_t* forced_masks, long long* tokens_out, void* stream);
+
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 unsigned long long edm_launch_count(void);
 /* Measurement hooks (bench.py): while enabled, every GEMM / attention / LayerNorm / conv-module launch is bracketed by

@@ -363,9 +363,10 @@ def test_decode_is_cuda_graph_capturable():
     sem, ap, sp = inp["semantic_tokens"].cuda(), inp["acoustic_prompt_tokens"].cuda(), inp["semantic_prompt_tokens"].cuda()
     ref = model.infer_special(sem, ap, sp, steps=3, seed=5)
     s = torch.cuda.Stream()
-    with torch.cuda.stream(s):
-        model.infer_special(sem, ap, sp, steps=3, seed=5)
+    with torch.cuda.stream(s):          # the mirror orders this call after `ref` (one workspace per context), although the stream differs
+        warm = model.infer_special(sem, ap, sp, steps=3, seed=5)
     torch.cuda.synchronize()
+    assert torch.equal(warm, ref)
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g, stream=s):
         out = model.infer_special(sem, ap, sp, steps=3, seed=5)
