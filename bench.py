@@ -386,6 +386,38 @@ def main():
     dec_samples = wav.shape[-1]
     del audio, dac, wav, dcodes
     torch.cuda.empty_cache()
+    # the step before the S2A decode (inference.py:38-41): text -> semantic tokens, TextToSemanticWLen.infer with the trained
+    # configuration (train_config.yaml: hidden 384, 8 heads of 48, depth 12) and the script's pred_iters = 16, one utterance of 10 s
+    from edm_tts_b200 import TextToSemanticWLen
+    from edm_tts_b200.config import TextToSemanticWLenConfig
+    from edm_tts_b200.synthetic import T2SConfig, make_t2s_state_dict
+
+    t2s_dims = T2SConfig(hidden=384, heads=8, depth=12, lp_heads=8, lp_depth=4)
+    t2s = TextToSemanticWLen(TextToSemanticWLenConfig(hidden_size=384, main_encoder_args=dict(depth=12, heads=8), length_predictor_args=dict(depth=4, heads=8)),
+                             make_t2s_state_dict(t2s_dims, 0), device=dev, max_positions=1024)
+    t2s_text = "The quick brown fox jumps over the lazy dog, and the dog, for once, does not mind at all."
+    for _ in range(2):
+        t2s.infer(t2s_text, pred_iters=16, gt_length=T, seed=1)
+    torch.cuda.synchronize()
+    l0 = lib.edm_launch_count()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(5):
+        t2s.infer(t2s_text, pred_iters=16, gt_length=T, seed=1)
+    r1.record()
+    torch.cuda.synchronize()
+    t2s_ms = r0.elapsed_time(r1) / 5
+    t2s_launches = (lib.edm_launch_count() - l0) // 5
+    t2s.predict_length(t2s_text)
+    torch.cuda.synchronize()
+    r0.record()
+    for _ in range(5):
+        t2s.predict_length(t2s_text)
+    r1.record()
+    torch.cuda.synchronize()
+    t2s_len_ms = r0.elapsed_time(r1) / 5
+    del t2s
+    torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -435,6 +467,11 @@ def main():
                              "frac_of_tensor_peak": 2 * 1.74e6 * B * dec_samples / (dec_ms * 1e-3) / 1e12 / tf_peak,
                              "algorithmic_gbs": 13650.0 * B * dec_samples / (dec_ms * 1e-3) / 1e9, "frac_hbm": 13650.0 * B * dec_samples / (dec_ms * 1e-3) / 1e9 / hbm_peak,
                              "note": "conv decoder on the encoder's implicit-GEMM kernels (transposed convs as 2-tap convs into a shifted output view); 1.74 MMAC per output sample"},
+        "secondary_t2s": {"metric": "t2s_semantic_tokens_per_s", "value": T / (t2s_ms * 1e-3), "unit": "tokens/s", "ms_per_utterance": t2s_ms,
+                          "length_predictor_ms": t2s_len_ms, "launches_per_utterance": int(t2s_launches),
+                          "workload": f"TextToSemanticWLen.infer, hidden 384 / 8 heads of 48 / depth 12 (train_config.yaml), pred_iters 16 (inference.py:38), "
+                                      f"{len(t2s_text)} text bytes -> {T} semantic tokens, batch 1 (the reference's infer is batch-1), in-kernel Philox noise",
+                          "note": "latency-bound: ~180 dependent launches per iteration on a 600-row sequence; device time per utterance, tokens resident"},
         "model_flops_utilisation": {"algorithmic_tflops": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12,
                                     "frac_of_peak": flops_per_frame(DECODE_STEPS, T) * B * T / (ms_total / args.steps * 1e-3) / 1e12 / tf_peak},
     }
