@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libedm_s2a.so")
 
 EPI_BF16, EPI_SWISH_BF16, EPI_QKV_ROPE, EPI_RESID_F32, EPI_F32, EPI_GLU_BF16 = range(6)
+EPI_ARGMAX = 10
 
 
 class S2AConfig(C.Structure):
@@ -65,6 +66,7 @@ _SIGNATURES = {
     "edm_s2a_buffer": (_vp, [_vp, C.c_char_p, C.POINTER(_sz)]),
     "edm_s2a_set_batch_offset": (_i, [_vp, _ll]),
     "edm_s2a_set_seed_buffer": (_i, [_vp, _vp]),
+    "edm_s2a_set_keep_logits": (_i, [_vp, _i]),
     "edm_s2a_set_prompt_injections": (_i, [_vp, _vp]),
     "edm_s2a_build_input": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "edm_s2a_first_level": (_i, [_vp, _vp, _vp]),

@@ -304,6 +304,7 @@ int launch_gemm(int epi, const CUtensorMap& ma, const WMap& mb, const GemmParams
     case EPI_RESID_F32: return launch_gemm_t<EPI_RESID_F32>(ma, mb, p, st);
     case EPI_F32: return launch_gemm_t<EPI_F32>(ma, mb, p, st);
     case EPI_GLU_BF16: return launch_gemm_t<EPI_GLU_BF16>(ma, mb, p, st);
+    case EPI_ARGMAX: return launch_gemm_t<EPI_ARGMAX>(ma, mb, p, st);
   }
   return fail(EDM_ERR_INVALID, "unknown epilogue %d", epi);
 }
@@ -876,6 +877,8 @@ struct edm_s2a_ctx {
   size_t ws_bytes = 0;
   // workspace views
   float *x_in, *x, *coarse_out[4], *logits, *coarse_logits, *fine_logits, *logp;
+  float2* arg_part;          // [Mt, n_fine, 16] partial arg-max of the fused heads (keep_logits == false)
+  bool keep_logits = false;  // true: coarse / fine logits are materialised (parity runs, the eval-mode loss); false: arg-max in the GEMM epilogue
   __nv_bfloat16 *z, *h, *qkv, *g, *zt, *fine_h, *fine_z;
   int *ids, *ids_raw, *pred_codes, *pred_raw, *fine_codes, *sem_tokens, *sem_prompt, *ac_prompt;
   uint8_t *mask_a, *mask_b, *mask_raw;
@@ -1058,10 +1061,12 @@ size_t carve(edm_s2a_ctx* c, uint8_t* base, int B, int T, int P, bool assign) {
   __nv_bfloat16* g = k.take<__nv_bfloat16>(M * 2048);
   __nv_bfloat16* zt = k.take<__nv_bfloat16>(Mt * 1024);
   float* logits = k.take<float>(Mt * 1024);
-  float* coarse_logits = k.take<float>(4 * Mt * 1024);
+  // the [B, 12, T, 1024] logits exist only when a caller asks for them (1.5 GB at the bench shape); the decode keeps 64-column partial arg-maxes
+  float* coarse_logits = c->keep_logits ? k.take<float>(4 * Mt * 1024) : nullptr;
   __nv_bfloat16* fine_h = k.take<__nv_bfloat16>(Mt * nf * 1024);
   __nv_bfloat16* fine_z = k.take<__nv_bfloat16>(Mt * nf * 1024);
-  float* fine_logits = k.take<float>(Mt * nf * 1024);
+  float* fine_logits = c->keep_logits ? k.take<float>(Mt * nf * 1024) : nullptr;
+  float2* arg_part = k.take<float2>(Mt * nf * 16);
   float* logp = k.take<float>(Mt);
   int* ids = k.take<int>(Mt);
   int* ids_raw = k.take<int>(Mt);
@@ -1078,7 +1083,7 @@ size_t carve(edm_s2a_ctx* c, uint8_t* base, int B, int T, int P, bool assign) {
     c->x_in = x_in; c->x = x;
     for (int i = 0; i < 4; ++i) c->coarse_out[i] = co[i];
     c->z = z; c->h = h; c->qkv = qkv; c->g = g; c->zt = zt; c->logits = logits; c->coarse_logits = coarse_logits;
-    c->fine_h = fine_h; c->fine_z = fine_z; c->fine_logits = fine_logits; c->logp = logp; c->ids = ids; c->ids_raw = ids_raw;
+    c->fine_h = fine_h; c->fine_z = fine_z; c->fine_logits = fine_logits; c->arg_part = arg_part; c->logp = logp; c->ids = ids; c->ids_raw = ids_raw;
     c->pred_codes = pred; c->pred_raw = pred_raw; c->fine_codes = fine_codes; c->sem_tokens = sem_tokens; c->sem_prompt = sem_prompt;
     c->ac_prompt = ac_prompt; c->mask_a = mask_a; c->mask_b = mask_b; c->mask_raw = mask_raw;
   }
@@ -1122,8 +1127,8 @@ extern "C" void* edm_s2a_buffer(edm_s2a_ctx* c, const char* name, size_t* bytes)
       {"qkv", c->qkv, M * 3072 * 2}, {"g", c->g, M * 2048 * 2}, {"zt", c->zt, Mt * 1024 * 2},
       {"coarse_out0", c->coarse_out[0], M * 1024 * 4}, {"coarse_out1", c->coarse_out[1], M * 1024 * 4},
       {"coarse_out2", c->coarse_out[2], M * 1024 * 4}, {"coarse_out3", c->coarse_out[3], M * 1024 * 4},
-      {"logits", c->logits, Mt * 1024 * 4}, {"coarse_logits", c->coarse_logits, 4 * Mt * 1024 * 4},
-      {"fine_logits", c->fine_logits, Mt * c->n_fine * 1024 * 4}, {"logp", c->logp, Mt * 4}, {"ids", c->ids, Mt * 4},
+      {"logits", c->logits, Mt * 1024 * 4}, {"coarse_logits", c->coarse_logits, c->keep_logits ? 4 * Mt * 1024 * 4 : 0},
+      {"fine_logits", c->fine_logits, c->keep_logits ? Mt * c->n_fine * 1024 * 4 : 0}, {"logp", c->logp, Mt * 4}, {"ids", c->ids, Mt * 4},
       {"ids_raw", c->ids_raw, Mt * 4}, {"pred_codes", c->pred_codes, Mt * 16}, {"pred_raw", c->pred_raw, Mt * 16},
       {"fine_codes", c->fine_codes, Mt * c->n_fine * 4}, {"mask", c->mask_cur(), Mt}, {"mask_raw", c->mask_raw, Mt}};
   for (auto& e : tab)
@@ -1179,6 +1184,13 @@ extern "C" int edm_s2a_first_level(edm_s2a_ctx* c, const float* x_in, void* stre
   }
   GemmParams p = gp(c->Mt, 1024, 1024, c->gwf(G_HEAD_B), c->logits, 1024);
   return launch_gemm(EPI_F32, c->m_zt, c->head_map, p, st);
+}
+
+extern "C" int edm_s2a_set_keep_logits(edm_s2a_ctx* c, int keep) {
+  if (c == nullptr) return fail(EDM_ERR_INVALID, "null context");
+  if ((keep != 0) != c->keep_logits) c->bound = false;  // the workspace layout changes: bind again
+  c->keep_logits = keep != 0;
+  return 0;
 }
 
 extern "C" int edm_s2a_set_prompt_injections(edm_s2a_ctx* c, const float* proj) {
@@ -1258,16 +1270,26 @@ extern "C" int edm_s2a_full_pass(edm_s2a_ctx* c, const float* x_in, const int* f
     // injection layer k: keep the block output, predict level k on the target rows, inject
     ln.w2 = c->gwf(G_TL_LN_W); ln.b2 = c->gwf(G_TL_LN_B); ln.y_out = c->coarse_out[k]; ln.z_out = c->zt; ln.seq_len = c->N; ln.z_skip = c->P;
     if (int rc = launch_ln(ln, st)) return rc;
-    float* lk = c->coarse_logits + static_cast<size_t>(k) * c->Mt * 1024;
-    {
+    if (c->keep_logits) {
+      float* lk = c->coarse_logits + static_cast<size_t>(k) * c->Mt * 1024;
       GemmParams p = gp(c->Mt, 1024, 1024, c->gwf(G_HEAD_B) + k * 1024, lk, 1024);
       p.b_row_offset = k * 1024;
       if (int rc = launch_gemm(EPI_F32, c->m_zt, c->head_map, p, st)) return rc;
+      SampleParams sp;
+      sp.logits = lk; sp.ld = 1024; sp.rows = c->Mt; sp.noise = nullptr; sp.use_philox = 0; sp.seed = 0; sp.seed_dev = nullptr; sp.step = 0; sp.row0 = 0; sp.forced_ids = forced_coarse;
+      sp.ids = c->pred_codes; sp.ids_raw = c->pred_raw; sp.logp = nullptr; sp.T = c->T; sp.Q = 1; sp.out_q_stride = 4; sp.out_q0 = k;
+      if (int rc = launch_sample(sp, st)) return rc;
+    } else {
+      // head k with the arg-max in the GEMM epilogue: 16 (max, index) partials per row instead of 1024 fp32 logits
+      GemmParams p = gp(c->Mt, 1024, 1024, c->gwf(G_HEAD_B) + k * 1024, c->arg_part, 16);
+      p.b_row_offset = k * 1024;
+      if (int rc = launch_gemm(EPI_ARGMAX, c->m_zt, c->head_map, p, st)) return rc;
+      ArgmaxCombineParams ap;
+      ap.part = c->arg_part; ap.rows = c->Mt; ap.parts = 16; ap.forced_ids = forced_coarse; ap.ids = c->pred_codes; ap.ids_raw = c->pred_raw;
+      ap.T = c->T; ap.Q = 1; ap.out_q_stride = 4; ap.out_q0 = k;
+      argmax_combine_kernel<<<(c->Mt + 255) / 256, 256, 0, st>>>(ap);
+      EDM_LAUNCH_CHECK("argmax_combine");
     }
-    SampleParams sp;
-    sp.logits = lk; sp.ld = 1024; sp.rows = c->Mt; sp.noise = nullptr; sp.use_philox = 0; sp.seed = 0; sp.seed_dev = nullptr; sp.step = 0; sp.row0 = 0; sp.forced_ids = forced_coarse;
-    sp.ids = c->pred_codes; sp.ids_raw = c->pred_raw; sp.logp = nullptr; sp.T = c->T; sp.Q = 1; sp.out_q_stride = 4; sp.out_q0 = k;
-    if (int rc = launch_sample(sp, st)) return rc;
     InjectParams ip;
     ip.x = c->x; ip.cur_out = c->coarse_out[k]; ip.prev_out = (k > 0 && cfg.residual) ? c->coarse_out[k - 1] : nullptr;
     ip.pred_codes = c->pred_codes; ip.ac_prompt = c->P > 0 ? c->ac_prompt : nullptr; ip.ac_prompt_levels = c->ac_levels;
@@ -1297,15 +1319,28 @@ extern "C" int edm_s2a_full_pass(edm_s2a_ctx* c, const float* x_in, const int* f
   }
   for (int q = 0; q < nf; ++q) {
     const int lvl = cfg.n_injection + q;
-    GemmParams p = gp(c->Mt, 1024, 1024, c->gwf(G_HEAD_B) + lvl * 1024, c->fine_logits + q * 1024, static_cast<long long>(nf) * 1024);
-    p.a_k_offset = q * 1024; p.b_row_offset = lvl * 1024;
-    if (int rc = launch_gemm(EPI_F32, c->m_fine_z, c->head_map, p, st)) return rc;
+    if (c->keep_logits) {
+      GemmParams p = gp(c->Mt, 1024, 1024, c->gwf(G_HEAD_B) + lvl * 1024, c->fine_logits + q * 1024, static_cast<long long>(nf) * 1024);
+      p.a_k_offset = q * 1024; p.b_row_offset = lvl * 1024;
+      if (int rc = launch_gemm(EPI_F32, c->m_fine_z, c->head_map, p, st)) return rc;
+    } else {
+      // partials of (token, level q) at arg_part[(token * nf + q) * 16 ..]: row pitch nf * 16, level offset q * 16
+      GemmParams p = gp(c->Mt, 1024, 1024, c->gwf(G_HEAD_B) + lvl * 1024, c->arg_part + q * 16, static_cast<long long>(nf) * 16);
+      p.a_k_offset = q * 1024; p.b_row_offset = lvl * 1024;
+      if (int rc = launch_gemm(EPI_ARGMAX, c->m_fine_z, c->head_map, p, st)) return rc;
+    }
   }
-  {
+  if (c->keep_logits) {
     SampleParams sp;
     sp.logits = c->fine_logits; sp.ld = 1024; sp.rows = c->Mt * nf; sp.noise = nullptr; sp.use_philox = 0; sp.seed = 0; sp.seed_dev = nullptr; sp.step = 0; sp.row0 = 0; sp.forced_ids = nullptr;
     sp.ids = c->fine_codes; sp.ids_raw = nullptr; sp.logp = nullptr; sp.T = c->T; sp.Q = nf; sp.out_q_stride = nf; sp.out_q0 = 0;
     if (int rc = launch_sample(sp, st)) return rc;
+  } else {
+    ArgmaxCombineParams ap;
+    ap.part = c->arg_part; ap.rows = c->Mt * nf; ap.parts = 16; ap.forced_ids = nullptr; ap.ids = c->fine_codes; ap.ids_raw = nullptr;
+    ap.T = c->T; ap.Q = nf; ap.out_q_stride = nf; ap.out_q0 = 0;
+    argmax_combine_kernel<<<(c->Mt * nf + 255) / 256, 256, 0, st>>>(ap);
+    EDM_LAUNCH_CHECK("argmax_combine");
   }
   if (codes_out != nullptr) {
     const long long total = static_cast<long long>(c->B) * cfg.num_quantizers * c->T;

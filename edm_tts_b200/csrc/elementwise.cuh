@@ -570,6 +570,40 @@ __global__ void __launch_bounds__(256) sample_kernel(const SampleParams p) {
   }
 }
 
+// Finishes the arg-max of the fused logits heads (gemm.cuh EPI_ARGMAX): part[row, j] = (max, first arg-max) of columns [64 j, 64 j + 64).
+// Same output mapping / teacher forcing as sample_kernel with no noise; ascending j with strict '>' keeps the first maximum.
+struct ArgmaxCombineParams {
+  const float2* part;       // [rows, parts]
+  int rows, parts;
+  const int* forced_ids;
+  int* ids;
+  int* ids_raw;             // nullable
+  int T, Q, out_q_stride, out_q0;
+};
+__global__ void __launch_bounds__(256) argmax_combine_kernel(const ArgmaxCombineParams p) {
+  const long long row = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (row >= p.rows) return;
+  const float2* r = p.part + row * p.parts;
+  float2 first = r[0];
+  float best = first.x;
+  int idx = __float_as_int(first.y);
+  for (int j = 1; j < p.parts; ++j) {
+    const float2 v = r[j];
+    if (v.x > best) {
+      best = v.x;
+      idx = __float_as_int(v.y);
+    }
+  }
+  if (!(best == best)) idx = 0;      // NaN logits: no defined maximum; stay inside the tables
+  idx = clamp_index(idx, kV);
+  const long long bt = row / p.Q;
+  const int q = static_cast<int>(row % p.Q);
+  const int b = static_cast<int>(bt / p.T), t = static_cast<int>(bt % p.T);
+  const long long oidx = (static_cast<long long>(b) * p.out_q_stride + p.out_q0 + q) * p.T + t;
+  p.ids[oidx] = p.forced_ids != nullptr ? clamp_index(p.forced_ids[oidx], kV) : idx;
+  if (p.ids_raw != nullptr) p.ids_raw[oidx] = idx;
+}
+
 // ------------------------------------------------------------------------------------------------ re-masking
 // Reference: modeling_injection_conformer.py:199-219 + edm_tts/utils/utils.py:49-60.
 //   mask_len = max(1, min(#masked - 1, floor(float32(T) * float32(ratio))))

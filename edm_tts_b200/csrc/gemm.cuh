@@ -26,6 +26,9 @@ enum EpiKind : int {
   EPI_F32 = 4,         // out_f32 = acc + bias                                                   (logits heads)
   EPI_GLU_BF16 = 5,    // per 64 columns: first 32 = value, last 32 = gate (weights interleaved at pack time);
                        // out_bf16[., N/2] = bf16(bf16(value) * bf16(sigmoid(bf16(gate))))       (conv module pointwise-1 + GLU)
+  EPI_ARGMAX = 10,     // logits heads whose only consumer is an arg-max (injection_conformer_wrapper.py:119-121, modeling :228): the
+                       // logits acc + bias never leave the SM; every epilogue thread writes (max, first arg-max) of its 64 columns
+                       // of one row to out_part[row * ldo + col / 64] (float2: value, index bits); argmax_combine_kernel finishes the row
   EPI_F32_TMA = 9,     // EPI_F32 with TMA store boxes (logits heads)
   EPI_ROPE_TMA = 8,    // EPI_QKV_ROPE with TMA store boxes
   EPI_SWISH_TMA = 7,   // EPI_SWISH_BF16 with the tile leaving as TMA store boxes (pair kernel only; launcher's choice)
@@ -92,6 +95,27 @@ __device__ __forceinline__ void gemm_store_32(const GemmParams& p, int row, int 
 #pragma unroll
     for (int i = 0; i < 4; ++i) o[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
   }
+}
+
+// EPI_ARGMAX: v = the 64 logits (acc + bias) of columns [col, col + 64) of one row, as two 32-column halves. Strict '>' in ascending
+// column order keeps the first maximum, as torch.argmax does; a row of NaNs keeps index col (the combine step clamps).
+__device__ __forceinline__ void gemm_store_argmax(const GemmParams& p, int row, int col, const float (&a)[32], const float (&b)[32]) {
+  float best = a[0];
+  int idx = 0;
+#pragma unroll
+  for (int i = 1; i < 32; ++i)
+    if (a[i] > best) {
+      best = a[i];
+      idx = i;
+    }
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (b[i] > best) {
+      best = b[i];
+      idx = 32 + i;
+    }
+  float2* o = reinterpret_cast<float2*>(p.out) + static_cast<long long>(row) * p.ldo + (col >> 6);
+  *o = make_float2(best, __int_as_float(col + idx));
 }
 
 // One 64-wide head: lo = columns [col, col+32), hi = [col+32, col+64). Reference: conformer.py:45-51 (rotate_half),
@@ -299,7 +323,7 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
           v[4 * i + 2] = __uint_as_float(r0[4 * i + 2]) + b.z;
           v[4 * i + 3] = __uint_as_float(r0[4 * i + 3]) + b.w;
         }
-        if constexpr (EPI == EPI_GLU_BF16) {
+        if constexpr (EPI == EPI_GLU_BF16 || EPI == EPI_ARGMAX) {
           float g[32];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -309,7 +333,10 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
             g[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
             g[4 * i + 3] = __uint_as_float(r1[4 * i + 3]) + b.w;
           }
-          gemm_store_glu(p, row, col0 >> 1, v, g);
+          if constexpr (EPI == EPI_GLU_BF16)
+            gemm_store_glu(p, row, col0 >> 1, v, g);
+          else
+            gemm_store_argmax(p, row, col0, v, g);
         } else {
           gemm_store_32<EPI>(p, row, col0, v);
 #pragma unroll
@@ -592,7 +619,7 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           v[4 * i + 2] = __uint_as_float(r0[4 * i + 2]) + b.z;
           v[4 * i + 3] = __uint_as_float(r0[4 * i + 3]) + b.w;
         }
-        if constexpr (EPI == EPI_GLU_BF16) {
+        if constexpr (EPI == EPI_GLU_BF16 || EPI == EPI_ARGMAX) {
           float g[32];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -602,7 +629,10 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
             g[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
             g[4 * i + 3] = __uint_as_float(r1[4 * i + 3]) + b.w;
           }
-          gemm_store_glu(p, row, col0 >> 1, v, g);
+          if constexpr (EPI == EPI_GLU_BF16)
+            gemm_store_glu(p, row, col0 >> 1, v, g);
+          else
+            gemm_store_argmax(p, row, col0, v, g);
         } else {
           gemm_store_32<EPI>(p, row, col0, v);
 #pragma unroll

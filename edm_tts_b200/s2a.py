@@ -150,7 +150,7 @@ class _Encoder:
         n_inj = len(m.injection_layers)
         if P > 0 and prompt_codes is None and injections is None:
             raise ValueError("a prompt prefix needs its injections: pass injections=[features per injection layer] or prompt_codes=<acoustic prompt tokens>")
-        m._bind(B, N - P, P)
+        m._bind(B, N - P, P, keep_logits=True)
         L.check(L.lib().edm_s2a_set_prompt_injections(m._ctx, None), "set_prompt_injections")
         keep = None
         if P > 0 and prompt_codes is not None:
@@ -336,11 +336,14 @@ class InjectionConformerModel:
             pass
 
     # ------------------------------------------------------------------ workspace plumbing
-    def _bind(self, B, T, P):
-        key = (B, T, P)
+    def _bind(self, B, T, P, keep_logits=False):
+        """keep_logits: the per-level logits of the full pass are materialised (parity runs, encoder.forward, the eval-mode loss);
+        infer_special leaves it off and the [b, 12, t, 1024] logits never exist (arg-max in the head GEMM's epilogue)."""
+        key = (B, T, P, bool(keep_logits))
         if self._bound == key:
             return
         lib = L.lib()
+        L.check(lib.edm_s2a_set_keep_logits(self._ctx, int(bool(keep_logits))), "set_keep_logits")
         need = lib.edm_s2a_workspace_bytes(self._ctx, B, T, P)
         if need == 0:
             raise ValueError(f"invalid decode shape B={B} T={T} P={P}")
@@ -364,7 +367,7 @@ class InjectionConformerModel:
         return self._ws[off:off + numel * esz].view(dtype).view(*shape)
 
     def _load_prompt_codes(self, prompt_codes):
-        B, T, P = self._bound
+        B, T, P = self._bound[:3]
         pc = prompt_codes.to(self.device, torch.int32).contiguous()
         dummy_sem = torch.zeros(B, T, device=self.device, dtype=torch.int32)
         dummy_sp = torch.zeros(B, P, device=self.device, dtype=torch.int32)
@@ -437,8 +440,9 @@ class InjectionConformerModel:
         ap = acoustic_prompt_tokens.to(dev).to(torch.int32).contiguous() if has_prompt else None
         sp = semantic_prompt_tokens.to(dev).to(torch.int32).contiguous() if has_prompt else None
         P = ap.shape[-1] if has_prompt else 0
-        self._bind(B, T, P)
+        self._bind(B, T, P, keep_logits=True)
         s_ = L.stream_ptr()
+        L.check(lib.edm_s2a_set_batch_offset(self._ctx, 0), "set_batch_offset")
         L.check(lib.edm_s2a_build_input(self._ctx, L.ptr(st), L.ptr(sp), L.ptr(ap), ap.shape[1] if has_prompt else 0, s_), "build_input")
         tr = dict(step_logits=[], step_ids=[], step_masks=[], step_masks_raw=[], step_logp=[], x0=self._view("x_in", (B, P + T, self.config.hidden_size), torch.float32).clone())
         V = self.num_codevectors
@@ -500,7 +504,7 @@ class InjectionConformerModel:
         for b0 in range(0, B, MAX_CHUNK):
             b1 = min(B, b0 + MAX_CHUNK)
             nb, sl = b1 - b0, slice(b0, b1)
-            self._bind(nb, T, 0)
+            self._bind(nb, T, 0, keep_logits=True)
             sem = st[sl].to(torch.int32).contiguous()
             tgt = ac[sl].to(torch.int32).contiguous()
             L.check(lib.edm_s2a_build_input(self._ctx, L.ptr(sem), None, None, 0, s_), "build_input")

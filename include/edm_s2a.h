@@ -35,7 +35,9 @@ enum edm_epilogue {
   EDM_EPI_QKV_ROPE = 2,    /* conformer.py:132-138       to_q/to_kv + rotary embedding on q,k */
   EDM_EPI_RESID_F32 = 3,   /* conformer.py:222-233       x += scale * (Linear(...)) on the fp32 residual stream */
   EDM_EPI_F32 = 4,         /* injection_conformer_wrapper.py:56-63   logits head */
-  EDM_EPI_GLU_BF16 = 5     /* conformer.py:59-66,170-171  pointwise conv + GLU; weight rows interleaved 32 value | 32 gate */
+  EDM_EPI_GLU_BF16 = 5,    /* conformer.py:59-66,170-171  pointwise conv + GLU; weight rows interleaved 32 value | 32 gate */
+  EDM_EPI_ARGMAX = 10      /* logits head followed by argmax(-1) (wrapper :119-121, modeling :228): out = float2 [M, ldo] partials,
+                              out[r, c / 64] = (max, first arg-max as int bits) of logits[r, c .. c + 64); N % 64 == 0 */
 };
 
 int edm_abi_version(void);
@@ -179,6 +181,13 @@ void* edm_s2a_buffer(edm_s2a_ctx* ctx, const char* name, size_t* bytes);
  * offset by it so the sampled tokens do not depend on how the batch is chunked or sharded over GPUs. */
 int edm_s2a_set_batch_offset(edm_s2a_ctx* ctx, long long batch_offset);
 
+/* keep != 0: edm_s2a_full_pass materialises the per-level logits (buffers "coarse_logits" [4,B*T,1024] and "fine_logits"
+ * [B*T,n_fine,1024], fp32) as InjectionConformerWrapper.forward returns them (injection_conformer_wrapper.py:143-150). keep == 0 (the
+ * default, what infer_special needs: it only takes the arg-max, modeling_injection_conformer.py:228): the head GEMMs reduce their logits
+ * to (max, arg-max) partials in the epilogue and the [B,12,T,1024] tensor never exists. Changes the workspace layout: query
+ * edm_s2a_workspace_bytes and bind again after switching. */
+int edm_s2a_set_keep_logits(edm_s2a_ctx* ctx, int keep);
+
 /* Feature-valued prompt injections (the `injections` argument of InjectionConformerWrapper.forward, injection_conformer_wrapper.py:92-131):
  * proj = fp32 [n_injection, B*P, 1024], row (k, b, n) = project_injection[k].0 applied to the caller's cumulative DAC feature of
  * prompt frame n (Linear only; the LayerNorm runs in the kernel). While set, edm_s2a_full_pass injects these on the prompt rows
@@ -202,8 +211,8 @@ int edm_s2a_step(edm_s2a_ctx* ctx, int step, int steps, float temperature, unsig
                  const float* cat_noise, const float* remask_noise, const int* forced_ids, const uint8_t* forced_mask,
                  void* stream);
 /* wrapper :92-150 + modeling :228: full pass -> codes int64 [B,12,T]. forced_coarse int32 [B,4,T] teacher-forces the
- * tokens injected at the coarse levels (the emitted codes are still the model's own arg-max). keep_logits != 0 keeps
- * per-level logits in buffers "coarse_logits" / "fine_logits". x_in as above. */
+ * tokens injected at the coarse levels (the emitted codes are still the model's own arg-max). Per-level logits are kept in the
+ * buffers "coarse_logits" / "fine_logits" only after edm_s2a_set_keep_logits(ctx, 1). x_in as above. */
 int edm_s2a_full_pass(edm_s2a_ctx* ctx, const float* x_in, const int* forced_coarse, long long* codes_out,
                       void* stream);
 /* whole infer_special: build_input, `steps` first-level passes (skipped when steps == 1), full pass. Noise / forcing

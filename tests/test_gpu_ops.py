@@ -78,6 +78,30 @@ def test_gemm_epilogues(L, M, N, K):
     assert_bf16_close(outb, rb(ref), mag, ulps=3)
 
 
+@pytest.mark.parametrize("M,N,K", [(77, 1024, 1024), (2500, 1024, 1024), (300, 512, 384)])
+def test_gemm_argmax_epilogue(L, M, N, K):
+    """EPI_ARGMAX: the 64-column (max, first arg-max) partials equal those of the fp32 logits the EPI_F32 epilogue writes, bit for bit
+    (small-M and CTA-pair kernels), including ties."""
+    torch.manual_seed(M)
+    a = bf(torch.randn(M, K, device=dev))
+    b = bf(torch.randn(N, K, device=dev) / math.sqrt(K))
+    b[N // 2 + 3] = b[5]                                    # two identical logit columns: the first index must win
+    bias = torch.randn(N, device=dev)
+    bias[N // 2 + 3] = bias[5]
+    logits = torch.empty(M, N, device=dev)
+    gemm(L, a, b, L.EPI_F32, bias, logits)
+    part = torch.full((M, N // 64, 2), float("nan"), device=dev)
+    L.check(L.lib().edm_gemm_bf16(L.ptr(a), K, L.ptr(b), K, M, N, K, L.EPI_ARGMAX, L.ptr(bias), L.ptr(part), N // 64, 1.0, None, None, 1, 0, L.stream_ptr()), "gemm")
+    seg = logits.view(M, N // 64, 64)
+    want_max, want_idx = seg.max(-1)
+    assert torch.equal(part[..., 0], want_max)
+    got_idx = part[..., 1].contiguous().view(torch.int32)
+    assert torch.equal(got_idx.long(), want_idx + 64 * torch.arange(N // 64, device=dev))
+    # whole-row arg-max from the partials == torch.argmax of the logits (first maximum)
+    j = part[..., 0].argmax(-1)
+    assert torch.equal(got_idx.gather(1, j[:, None])[:, 0].long(), logits.argmax(-1))
+
+
 def test_gemm_rejects_bad_shapes(L):
     a = bf(torch.randn(8, 64, device=dev))
     b = bf(torch.randn(100, 64, device=dev))

@@ -262,6 +262,26 @@ def test_batch_chunking_and_determinism(monkeypatch):
     assert torch.equal(chunked, all_codes)
 
 
+def test_fused_argmax_heads_equal_materialised_logits():
+    """infer_special never materialises the [b, 12, t, 1024] logits (arg-max in the head GEMM epilogues, 16 partials per row); the
+    codes must equal, bit for bit, those of the staged run that writes fp32 logits and arg-maxes them with sample_kernel. Checked on
+    the small-M GEMM kernel (B=2) and on the CTA-pair kernel (B=16 x 200 frames), with a prompt and teacher-forced coarse tokens."""
+    from oracle.weights import make_inputs
+    from tests.parity_utils import full_model
+
+    cfg, sd, model = full_model()
+    for B, T, P, steps in ((2, 70, 10, 3), (16, 200, 0, 2)):
+        inp = make_inputs(B, T, P, steps, cfg, seed=B + T)
+        args = (inp["semantic_tokens"], inp["acoustic_prompt_tokens"], inp["semantic_prompt_tokens"])
+        tr = model.decode_trace(*args, steps=steps, seed=3)
+        assert torch.equal(tr["codes"], tr["all_logits"].argmax(-1))
+        fused = model.infer_special(*args, steps=steps, seed=3)
+        assert torch.equal(fused, tr["codes"])
+        fc = torch.randint(0, 1024, (B, 4, T))
+        tr2 = model.decode_trace(*args, steps=steps, seed=3, forced_coarse=fc)
+        assert torch.equal(model.infer_special(*args, steps=steps, seed=3, forced_coarse=fc), tr2["codes"])
+
+
 def test_philox_path_runs_and_is_seeded():
     from oracle.weights import make_inputs
     from tests.parity_utils import full_model
