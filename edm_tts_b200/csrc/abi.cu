@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/edm_s2a.h"
@@ -148,6 +149,43 @@ constexpr bool env_switch(const char*, bool dflt) { return dflt; }
 constexpr int env_int(const char*, int dflt) { return dflt; }
 #endif
 
+// ---------------------------------------------------------------------------------------------- launches
+// Every kernel of the decode paths is launched with programmatic stream serialisation (PDL): its CTAs may be scheduled while the
+// previous kernel of the stream is still draining, run their prologue (barrier init, TMEM allocation, descriptor prefetch, bias /
+// table staging from constant weights) and then block in griddepcontrol.wait until the previous kernel has completed and flushed its
+// memory. Each such kernel executes griddepcontrol.wait in every CTA before it touches anything another kernel wrote (pdl_wait() in
+// ptx.cuh), so completion stays transitive along the chain; a launch after a non-PDL kernel (torch's, a memcpy) simply serialises.
+// Measured on the decode (tools/gpu_ab.sh, 854 launches): a constant ~1.7 ms less per decode up to 8 000 rows (B=1 x 150 frames: 8.4 ->
+// 6.6 ms, B=16 x 500: 31.9 -> 30.5 ms), neutral at 16 000 rows and 0.5-1 % *slower* at the 32 000 rows of the bench step, where the
+// kernels run for 100+ us and the early-resident CTAs of the next kernel only compete with the draining one. The decoder contexts
+// therefore switch it off above kPdlMaxRows rows (PdlScope); the stateless operators keep it on.
+constexpr int kPdlMaxRows = 16384;
+thread_local bool t_pdl_allow = true;
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool allow) : prev(t_pdl_allow) { t_pdl_allow = allow; }
+  ~PdlScope() { t_pdl_allow = prev; }
+};
+bool pdl_enabled() {
+  static const int mode = env_int("EDM_PDL", -1);  // bring-up switch: 0 = never, 1 = always, default = by size
+  return mode < 0 ? t_pdl_allow : mode != 0;
+}
+
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);  // the error is picked up by EDM_LAUNCH_CHECK (cudaGetLastError)
+}
+
 // ---------------------------------------------------------------------------------------------- TMA descriptors
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -264,7 +302,7 @@ int launch_gemm_t(const CUtensorMap& ma, const WMap& wm, const GemmParams& p_in,
     if (p.N % kGemmBN != 0 || (gemm_small_m() && pair_tiles * 4 <= sms)) {
       p.reverse = 0;
       const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / kSmBN);
-      gemm_bf16_tn_small_kernel<EPI><<<tiles < sms ? tiles : sms, kSmThreads, kSmSmemBytes, st>>>(ma, wm.small, p);
+      launch_pdl(gemm_bf16_tn_small_kernel<EPI>, dim3(tiles < sms ? tiles : sms), dim3(kSmThreads), kSmSmemBytes, st, ma, wm.small, p);
       EDM_LAUNCH_CHECK("gemm_bf16_tn_small");
       return 0;
     }
@@ -276,21 +314,21 @@ int launch_gemm_t(const CUtensorMap& ma, const WMap& wm, const GemmParams& p_in,
   if (EPI == EPI_RESID_F32 && gemm_resid_tma() && p.K <= resid_tma_max_k() && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 4) % 16 == 0) {
     CUtensorMap mc;
     if (int rc = make_tmap_f32_2d(&mc, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    gemm_bf16_tn_pair_kernel<EPI_RESID_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
+    launch_pdl(gemm_bf16_tn_pair_kernel<EPI_RESID_TMA>, dim3(2 * pairs), dim3(kGemmThreads), kPairSmemBytes, st, ma, mb, mc, p);
   } else if (EPI == EPI_F32 && gemm_out_tma() && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 4) % 16 == 0) {
     CUtensorMap mc;  // fp32 logits leave as 32 x 32 TMA store boxes
     if (int rc = make_tmap_f32_2d(&mc, p.out, p.M, p.N, p.ldo, 32, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
-    gemm_bf16_tn_pair_kernel<EPI_F32_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
+    launch_pdl(gemm_bf16_tn_pair_kernel<EPI_F32_TMA>, dim3(2 * pairs), dim3(kGemmThreads), kPairSmemBytes, st, ma, mb, mc, p);
   } else if ((EPI == EPI_SWISH_BF16 || EPI == EPI_QKV_ROPE) && gemm_out_tma() && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo * 2) % 16 == 0) {
     // bf16 tiles leave as TMA store boxes (whole 128-byte lines) instead of 16-byte stores from registers
     CUtensorMap mc;
     if (int rc = make_tmap_2d(&mc, p.out, p.M, p.N, p.ldo, 32)) return rc;
     if (EPI == EPI_SWISH_BF16)
-      gemm_bf16_tn_pair_kernel<EPI_SWISH_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
+      launch_pdl(gemm_bf16_tn_pair_kernel<EPI_SWISH_TMA>, dim3(2 * pairs), dim3(kGemmThreads), kPairSmemBytes, st, ma, mb, mc, p);
     else
-      gemm_bf16_tn_pair_kernel<EPI_ROPE_TMA><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, mc, p);
+      launch_pdl(gemm_bf16_tn_pair_kernel<EPI_ROPE_TMA>, dim3(2 * pairs), dim3(kGemmThreads), kPairSmemBytes, st, ma, mb, mc, p);
   } else {
-    gemm_bf16_tn_pair_kernel<EPI><<<2 * pairs, kGemmThreads, kPairSmemBytes, st>>>(ma, mb, ma, p);
+    launch_pdl(gemm_bf16_tn_pair_kernel<EPI>, dim3(2 * pairs), dim3(kGemmThreads), kPairSmemBytes, st, ma, mb, ma, p);
   }
   EDM_LAUNCH_CHECK("gemm_bf16_tn_pair");
   return 0;
@@ -331,7 +369,7 @@ int launch_attention(const CUtensorMap& mqkv, int B, int N, int H, void* out, ui
   const int items = ((N + 255) / 256) * H * B;
   dim3 grid(items < num_sms() ? items : num_sms());
   ProfScope prof(PK_ATTN, 4.0 * B * H * static_cast<double>(N) * N * 64, st);
-  attention_fwd_kernel<<<grid, kAttnThreads, kAttnSmemBytes, st>>>(mqkv, p);
+  launch_pdl(attention_fwd_kernel, dim3(grid), dim3(kAttnThreads), kAttnSmemBytes, st, mqkv, p);
   EDM_LAUNCH_CHECK("attention_fwd");
   return 0;
 }
@@ -343,7 +381,7 @@ int launch_ln(const LnParams& p_in, cudaStream_t st) {
   // algorithmic bytes: one read of the row + each requested output
   ProfScope prof(PK_LN, static_cast<double>(p.rows) * kD * ((p.in_is_bf16 ? 2 : 4) + (p.y_out ? 4 : 0)) +
                             (p.z_out ? static_cast<double>(p.rows) * (p.z_skip > 0 ? static_cast<double>(p.seq_len - p.z_skip) / p.seq_len : 1.0) * kD * 2 : 0.0), st);
-  layernorm_kernel<<<(p.rows + 7) / 8, 256, 0, st>>>(p);
+  launch_pdl(layernorm_kernel, dim3((p.rows + 7) / 8), dim3(256), 0, st, p);
   EDM_LAUNCH_CHECK("layernorm");
   return 0;
 }
@@ -364,9 +402,9 @@ int launch_conv(const ConvModParams& p, bool glu_input, cudaStream_t st) {
   if (glu_input || legacy) {
     dim3 grid((p.N + kConvTT - 1) / kConvTT, p.B);
     if (glu_input)
-      conv_module_kernel<true><<<grid, kConvThreads, kConvSmemBytes, st>>>(p);
+      launch_pdl(conv_module_kernel<true>, dim3(grid), dim3(kConvThreads), kConvSmemBytes, st, p);
     else
-      conv_module_kernel<false><<<grid, kConvThreads, kConvSmemBytes, st>>>(p);
+      launch_pdl(conv_module_kernel<false>, dim3(grid), dim3(kConvThreads), kConvSmemBytes, st, p);
   } else {
     // split every sequence into runs so that the persistent CTAs are evenly loaded and few halo rows are re-read
     // (run lengths are multiples of the 16-token statistics group, so only a sequence's last run has a partial group)
@@ -388,7 +426,7 @@ int launch_conv(const ConvModParams& p, bool glu_input, cudaStream_t st) {
     q.reverse = next_direction();
     q.runs_per_seq = (p.N + q.run_len - 1) / q.run_len;
     const long long units = static_cast<long long>(p.B) * q.runs_per_seq;
-    conv_stream_kernel<<<static_cast<unsigned>(units < sms ? units : sms), kCsThreads, kCsSmemBytes, st>>>(q);
+    launch_pdl(conv_stream_kernel, dim3(static_cast<unsigned>(units < sms ? units : sms)), dim3(kCsThreads), kCsSmemBytes, st, q);
   }
   EDM_LAUNCH_CHECK("conv_module");
   return 0;
@@ -396,16 +434,18 @@ int launch_conv(const ConvModParams& p, bool glu_input, cudaStream_t st) {
 
 int launch_sample(const SampleParams& p, cudaStream_t st) {
   if (p.rows <= 0) return 0;
-  sample_kernel<<<(p.rows + 7) / 8, 256, 0, st>>>(p);
+  launch_pdl(sample_kernel, dim3((p.rows + 7) / 8), dim3(256), 0, st, p);
   EDM_LAUNCH_CHECK("sample");
   return 0;
 }
 
 __global__ void fill_u8_kernel(uint8_t* p, long long n, uint8_t v) {
+  pdl_sync();
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
 __global__ void assemble_codes_kernel(const int* coarse, int n_coarse, const int* fine, int n_fine, long long* out, int B, int T) {
+  pdl_sync();
   const int Q = n_coarse + n_fine;
   long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<long long>(B) * Q * T) return;
@@ -521,7 +561,7 @@ extern "C" int edm_remask(const float* logp, const float* gumbel, const uint8_t*
   RemaskParams p;
   p.logp = logp; p.gumbel = gumbel; p.mask_old = mask_old; p.mask_new = mask_new; p.mask_raw = nullptr; p.forced_mask = forced_mask;
   p.T = T; p.init_count = 0; p.ratio = ratio; p.temp_ratio = temp_ratio; p.seed = seed; p.seed_dev = nullptr; p.step = step; p.row0 = 0;
-  remask_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(remask_kernel, dim3(B), dim3(256), 0, static_cast<cudaStream_t>(stream), p);
   EDM_LAUNCH_CHECK("remask");
   return 0;
 }
@@ -1141,6 +1181,7 @@ extern "C" void* edm_s2a_buffer(edm_s2a_ctx* c, const char* name, size_t* bytes)
 
 extern "C" int edm_s2a_build_input(edm_s2a_ctx* c, const int* sem_tokens, const int* sem_prompt, const int* ac_prompt, int ac_levels, void* stream) {
   if (c == nullptr || !c->bound) return fail(EDM_ERR_STATE, "context not bound");
+  PdlScope pdl(c->M <= kPdlMaxRows);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (sem_tokens == nullptr) return fail(EDM_ERR_INVALID, "semantic tokens required");
   if (c->P > 0) {
@@ -1156,16 +1197,17 @@ extern "C" int edm_s2a_build_input(edm_s2a_ctx* c, const int* sem_tokens, const 
   p.ac_prompt_levels = ac_levels; p.sem_emb = c->gwf(G_SEM_EMB); p.mask_token = c->gwf(G_MASK_TOKEN); p.feat_table = c->gwf(G_FEAT_TABLE);
   p.feat_const = c->gwf(G_FEAT_CONST); p.fp_ln_w = c->gwf(G_FP_LN_W); p.fp_ln_b = c->gwf(G_FP_LN_B); p.B = c->B; p.T = c->T; p.P = c->P; p.eps = 1e-5f;
   p.num_semantic = c->cfg.num_semantic;
-  build_input_kernel<<<(c->M + 7) / 8, 256, 0, st>>>(p);
+  launch_pdl(build_input_kernel, dim3((c->M + 7) / 8), dim3(256), 0, st, p);
   EDM_LAUNCH_CHECK("build_input");
   c->mask_in_a = true;
-  fill_u8_kernel<<<(c->Mt + 255) / 256, 256, 0, st>>>(c->mask_a, c->Mt, 1);
+  launch_pdl(fill_u8_kernel, dim3((c->Mt + 255) / 256), dim3(256), 0, st, c->mask_a, c->Mt, 1);
   EDM_LAUNCH_CHECK("fill_mask");
   return 0;
 }
 
 extern "C" int edm_s2a_first_level(edm_s2a_ctx* c, const float* x_in, void* stream) {
   if (c == nullptr || !c->bound) return fail(EDM_ERR_STATE, "context not bound");
+  PdlScope pdl(c->M <= kPdlMaxRows);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int rc = pass_prologue(c, x_in ? x_in : c->x_in, st)) return rc;
   const int last = c->cfg.injection_layers[0];
@@ -1215,6 +1257,7 @@ extern "C" int edm_s2a_step(edm_s2a_ctx* c, int step, int steps, float temperatu
                             const float* remask_noise, const int* forced_ids, const uint8_t* forced_mask, void* stream) {
   if (c == nullptr || !c->bound) return fail(EDM_ERR_STATE, "context not bound");
   if (steps < 2 || step < 0 || step >= steps) return fail(EDM_ERR_INVALID, "step %d of %d", step, steps);
+  PdlScope pdl(c->M <= kPdlMaxRows);
   // the reference's take_along_dim(sorted_confidence, mask_len >= 1) is out of range for a single frame (utils/utils.py:56)
   if (c->T < 2 && step < steps - 1 && forced_mask == nullptr) return fail(EDM_ERR_INVALID, "re-masking needs T >= 2 frames (T=%d, steps=%d)", c->T, steps);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1233,7 +1276,7 @@ extern "C" int edm_s2a_step(edm_s2a_ctx* c, int step, int steps, float temperatu
     rp.logp = c->logp; rp.gumbel = remask_noise; rp.mask_old = m_old; rp.mask_new = c->mask_next(); rp.mask_raw = c->mask_raw; rp.forced_mask = forced_mask;
     rp.T = c->T; rp.init_count = 0; rp.ratio = static_cast<float>(ratio_d); rp.temp_ratio = static_cast<float>(static_cast<double>(temperature) * ratio_d);
     rp.seed = seed; rp.seed_dev = c->seed_dev; rp.step = static_cast<unsigned>(step); rp.row0 = c->batch_offset * c->T;
-    remask_kernel<<<c->B, 256, 0, st>>>(rp);
+    launch_pdl(remask_kernel, dim3(c->B), dim3(256), 0, st, rp);
     EDM_LAUNCH_CHECK("remask");
     m_new = c->mask_next();
   }
@@ -1241,7 +1284,7 @@ extern "C" int edm_s2a_step(edm_s2a_ctx* c, int step, int steps, float temperatu
   up.x = c->x_in; up.sem_tokens = c->sem_tokens; up.ids = c->ids; up.mask_old = m_old; up.mask_new = m_new; up.sem_emb = c->gwf(G_SEM_EMB);
   up.mask_token = c->gwf(G_MASK_TOKEN); up.feat_table = c->gwf(G_FEAT_TABLE); up.feat_const = c->gwf(G_FEAT_CONST);
   up.fp_ln_w = c->gwf(G_FP_LN_W); up.fp_ln_b = c->gwf(G_FP_LN_B); up.B = c->B; up.T = c->T; up.P = c->P; up.eps = 1e-5f; up.num_semantic = c->cfg.num_semantic;
-  update_input_kernel<<<(c->Mt + 7) / 8, 256, 0, st>>>(up);
+  launch_pdl(update_input_kernel, dim3((c->Mt + 7) / 8), dim3(256), 0, st, up);
   EDM_LAUNCH_CHECK("update_input");
   if (!last) c->mask_in_a = !c->mask_in_a;
   return 0;
@@ -1249,6 +1292,7 @@ extern "C" int edm_s2a_step(edm_s2a_ctx* c, int step, int steps, float temperatu
 
 extern "C" int edm_s2a_full_pass(edm_s2a_ctx* c, const float* x_in, const int* forced_coarse, long long* codes_out, void* stream) {
   if (c == nullptr || !c->bound) return fail(EDM_ERR_STATE, "context not bound");
+  PdlScope pdl(c->M <= kPdlMaxRows);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const edm_s2a_config& cfg = c->cfg;
   if (int rc = pass_prologue(c, x_in ? x_in : c->x_in, st)) return rc;
@@ -1287,7 +1331,7 @@ extern "C" int edm_s2a_full_pass(edm_s2a_ctx* c, const float* x_in, const int* f
       ArgmaxCombineParams ap;
       ap.part = c->arg_part; ap.rows = c->Mt; ap.parts = 16; ap.forced_ids = forced_coarse; ap.ids = c->pred_codes; ap.ids_raw = c->pred_raw;
       ap.T = c->T; ap.Q = 1; ap.out_q_stride = 4; ap.out_q0 = k;
-      argmax_combine_kernel<<<(c->Mt + 255) / 256, 256, 0, st>>>(ap);
+      launch_pdl(argmax_combine_kernel, dim3((c->Mt + 255) / 256), dim3(256), 0, st, ap);
       EDM_LAUNCH_CHECK("argmax_combine");
     }
     InjectParams ip;
@@ -1297,7 +1341,7 @@ extern "C" int edm_s2a_full_pass(edm_s2a_ctx* c, const float* x_in, const int* f
     for (int i = 0; i < 4; ++i) ip.tables[i] = c->gwf(G_INJ_TABLE) + (static_cast<size_t>(k) * 4 + i) * 1024 * 1024;
     ip.inj_const = c->gwf(G_INJ_CONST) + k * 1024; ip.ln_w = c->gwf(G_INJ_LN_W) + k * 1024; ip.ln_b = c->gwf(G_INJ_LN_B) + k * 1024;
     ip.level = k; ip.B = c->B; ip.T = c->T; ip.P = c->P; ip.eps = 1e-5f;
-    inject_kernel<<<(c->M + 7) / 8, 256, 0, st>>>(ip);
+    launch_pdl(inject_kernel, dim3((c->M + 7) / 8), dim3(256), 0, st, ip);
     EDM_LAUNCH_CHECK("inject");
     LnParams nx;
     nx.in = c->x; nx.in_is_bf16 = 0; nx.rows = c->M; nx.w1 = nullptr; nx.b1 = nullptr; nx.eps = 1e-5f; nx.y_out = nullptr;
@@ -1339,12 +1383,12 @@ extern "C" int edm_s2a_full_pass(edm_s2a_ctx* c, const float* x_in, const int* f
     ArgmaxCombineParams ap;
     ap.part = c->arg_part; ap.rows = c->Mt * nf; ap.parts = 16; ap.forced_ids = nullptr; ap.ids = c->fine_codes; ap.ids_raw = nullptr;
     ap.T = c->T; ap.Q = nf; ap.out_q_stride = nf; ap.out_q0 = 0;
-    argmax_combine_kernel<<<(c->Mt * nf + 255) / 256, 256, 0, st>>>(ap);
+    launch_pdl(argmax_combine_kernel, dim3((c->Mt * nf + 255) / 256), dim3(256), 0, st, ap);
     EDM_LAUNCH_CHECK("argmax_combine");
   }
   if (codes_out != nullptr) {
     const long long total = static_cast<long long>(c->B) * cfg.num_quantizers * c->T;
-    assemble_codes_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(c->pred_raw, cfg.n_injection, c->fine_codes, nf, codes_out, c->B, c->T);
+    launch_pdl(assemble_codes_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, st, c->pred_raw, cfg.n_injection, c->fine_codes, nf, codes_out, c->B, c->T);
     EDM_LAUNCH_CHECK("assemble_codes");
   }
   return 0;
@@ -1435,11 +1479,11 @@ int launch_ln_g(int d, const LnGParams& p, cudaStream_t st) {
   if (p.rows <= 0) return 0;
   const int grid = (p.rows + 7) / 8;
   switch (d) {
-    case 128: layernorm_g_kernel<1><<<grid, 256, 0, st>>>(p); break;
-    case 256: layernorm_g_kernel<2><<<grid, 256, 0, st>>>(p); break;
-    case 384: layernorm_g_kernel<3><<<grid, 256, 0, st>>>(p); break;
-    case 512: layernorm_g_kernel<4><<<grid, 256, 0, st>>>(p); break;
-    case 1024: layernorm_g_kernel<8><<<grid, 256, 0, st>>>(p); break;
+    case 128: launch_pdl(layernorm_g_kernel<1>, dim3(grid), dim3(256), 0, st, p); break;
+    case 256: launch_pdl(layernorm_g_kernel<2>, dim3(grid), dim3(256), 0, st, p); break;
+    case 384: launch_pdl(layernorm_g_kernel<3>, dim3(grid), dim3(256), 0, st, p); break;
+    case 512: launch_pdl(layernorm_g_kernel<4>, dim3(grid), dim3(256), 0, st, p); break;
+    case 1024: launch_pdl(layernorm_g_kernel<8>, dim3(grid), dim3(256), 0, st, p); break;
     default: return fail(EDM_ERR_INVALID, "layernorm: hidden %d", d);
   }
   EDM_LAUNCH_CHECK("layernorm_g");
@@ -1454,7 +1498,7 @@ int launch_conv_tiled_t(const ConvModParams& p, cudaStream_t st) {
     attr_once.done();
   }
   dim3 grid((p.N + kConvTT - 1) / kConvTT, p.B);
-  conv_module_kernel<false, kC><<<grid, kC / 4, conv_smem_bytes(kC), st>>>(p);
+  launch_pdl(conv_module_kernel<false, kC>, dim3(grid), dim3(kC / 4), conv_smem_bytes(kC), st, p);
   EDM_LAUNCH_CHECK("conv_module");
   return 0;
 }
@@ -1685,11 +1729,11 @@ extern "C" int edm_t2s_predict_length(edm_t2s_ctx* c, const int* text_tokens, in
   const int last = b0 + cfg.lp_depth - 1;
   float* out = raw_out != nullptr ? raw_out : c->raw_len;
   switch (c->d) {
-    case 128: t2s_length_head_kernel<1><<<1, 32, 0, st>>>(c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
-    case 256: t2s_length_head_kernel<2><<<1, 32, 0, st>>>(c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
-    case 384: t2s_length_head_kernel<3><<<1, 32, 0, st>>>(c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
-    case 512: t2s_length_head_kernel<4><<<1, 32, 0, st>>>(c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
-    default: t2s_length_head_kernel<8><<<1, 32, 0, st>>>(c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
+    case 128: launch_pdl(t2s_length_head_kernel<1>, dim3(1), dim3(32), 0, st, c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
+    case 256: launch_pdl(t2s_length_head_kernel<2>, dim3(1), dim3(32), 0, st, c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
+    case 384: launch_pdl(t2s_length_head_kernel<3>, dim3(1), dim3(32), 0, st, c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
+    case 512: launch_pdl(t2s_length_head_kernel<4>, dim3(1), dim3(32), 0, st, c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
+    default: launch_pdl(t2s_length_head_kernel<8>, dim3(1), dim3(32), 0, st, c->x, c->bwf(last, F_POST_LN_W), c->bwf(last, F_POST_LN_B), c->gwf(TG_LEN_W), c->gwf(TG_LEN_B), 1e-5f, out); break;
   }
   EDM_LAUNCH_CHECK("t2s_length_head");
   c->begun = false;  // the activation buffers were reused
@@ -1709,7 +1753,7 @@ extern "C" int edm_t2s_begin(edm_t2s_ctx* c, const int* text_tokens, int n_text,
   T2sBeginParams p;
   p.text_tokens = c->text; p.n_text = n_text; p.length = length; p.tok_text = 1; p.tok_sep = 3; p.tok_speech = 2; p.tok_mask = 4;
   p.input_ids = c->input_ids; p.tokens = c->tokens; p.full_mask = c->full_mask; p.mask = c->mask_a;
-  t2s_begin_kernel<<<(c->L + 255) / 256, 256, 0, st>>>(p);
+  launch_pdl(t2s_begin_kernel, dim3((c->L + 255) / 256), dim3(256), 0, st, p);
   EDM_LAUNCH_CHECK("t2s_begin");
   if (int rc = t2s_maps(c, c->L, c->hp)) return rc;
   c->begun = true;
@@ -1765,11 +1809,11 @@ extern "C" int edm_t2s_step(edm_t2s_ctx* c, int iter, int iters, float temperatu
     rp.logp = c->logp; rp.gumbel = remask_noise; rp.mask_old = c->mask_cur(); rp.mask_new = c->mask_next(); rp.mask_raw = c->mask_raw; rp.forced_mask = forced_mask;
     rp.T = L; rp.init_count = c->length; rp.ratio = static_cast<float>(ratio_d); rp.temp_ratio = static_cast<float>(static_cast<double>(temperature) * ratio_d);
     rp.seed = seed; rp.seed_dev = nullptr; rp.step = static_cast<unsigned>(iter); rp.row0 = 0;
-    remask_kernel<<<1, 256, 0, st>>>(rp);
+    launch_pdl(remask_kernel, dim3(1), dim3(256), 0, st, rp);
     EDM_LAUNCH_CHECK("remask");
     up.next_mask = c->mask_next();
   }
-  t2s_update_kernel<<<(L + 255) / 256, 256, 0, st>>>(up);
+  launch_pdl(t2s_update_kernel, dim3((L + 255) / 256), dim3(256), 0, st, up);
   EDM_LAUNCH_CHECK("t2s_update");
   if (!last) c->mask_in_a = !c->mask_in_a;
   return 0;
@@ -1779,7 +1823,7 @@ extern "C" int edm_t2s_step(edm_t2s_ctx* c, int iter, int iters, float temperatu
 extern "C" int edm_t2s_result(edm_t2s_ctx* c, long long* tokens_out, void* stream) {
   if (c == nullptr || !c->bound || !c->begun) return fail(EDM_ERR_STATE, "no sequence: call edm_t2s_begin first");
   if (tokens_out == nullptr) return fail(EDM_ERR_INVALID, "output required");
-  t2s_gather_out_kernel<<<(c->length + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(c->tokens, c->n_text + 3, c->length, tokens_out);
+  launch_pdl(t2s_gather_out_kernel, dim3((c->length + 255) / 256), dim3(256), 0, static_cast<cudaStream_t>(stream), c->tokens, c->n_text + 3, c->length, tokens_out);
   EDM_LAUNCH_CHECK("t2s_gather_out");
   return 0;
 }

@@ -19,6 +19,11 @@
 //                       (One issuer per query tile, warp 10 taking tile 1, was measured slower: 0.171 vs 0.154 ms at B=64,
 //                       N=500. The single in-order issuer keeps the two warpgroups half a tile apart, so one is in its MUFU
 //                       phase while the other's MMAs run.)
+//   Tried and dropped (round 2, tools/gpu_attn_variants.sh): taking 25 / 50 % of the exp2 from the FMA pipe (Cody-Waite split + degree-3
+//   minimax polynomial in packed f32x2, exponent merged with one integer multiply-add), as FlashAttention-4 does. 122.8 us -> 124.7 /
+//   137.0 us at B=64, N=500: with the ping-pong hand-over only one warp per SM sub-partition is in its exp2 phase at a time, and that
+//   phase is bound by its own instruction stream (scale, exp2, sum, bf16 pack, swizzled store: ~6 issue slots per column pair), not by
+//   MUFU throughput; every polynomial pair adds ~10 slots to it.
 //   warps 10..11      : idle; they exist so the producer/MMA warpgroup can hand its registers to the softmax warpgroups
 //                       (setmaxnreg 88 / 208): a 128-wide fp32 score row per thread does not fit in 168 registers.
 #pragma once
@@ -123,6 +128,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
 
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stream_kernel(const ConvSt
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_sync();
 
   // producer state (thread 0 only): next row to request, as (unit, row inside the unit's [t_lo, t_hi))
   int pu = blockIdx.x, pr = 0;

@@ -123,6 +123,7 @@ struct LnParams {
 
 // 3 CTAs / SM (80 registers): 24 warps x 4 KB of row data in flight per SM measured best (5.7 TB/s)
 __global__ void __launch_bounds__(256, 3) layernorm_kernel(const LnParams p) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = (p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 8 + warp;
   if (row >= p.rows) return;
@@ -199,6 +200,8 @@ __global__ void __launch_bounds__(kC / 4, 2) conv_module_kernel(const ConvModPar
   for (int j = 0; j < 5; ++j)
 #pragma unroll
     for (int c = 0; c < 4; ++c) win[j][c] = 0.f;
+
+  pdl_sync();  // the depthwise weights above are constants; the rows below come from the previous kernel
 
   // two rows of loads in flight ahead of the arithmetic
   uint2 pa[2], pg[2] = {make_uint2(0, 0), make_uint2(0, 0)};
@@ -326,6 +329,7 @@ struct BuildInputParams {
 };
 
 __global__ void __launch_bounds__(256) build_input_kernel(const BuildInputParams p) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.P + p.T;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
@@ -365,6 +369,7 @@ struct UpdateInputParams {
 };
 
 __global__ void __launch_bounds__(256) update_input_kernel(const UpdateInputParams p) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long r = static_cast<long long>(blockIdx.x) * 8 + warp;
   if (r >= static_cast<long long>(p.B) * p.T) return;
@@ -406,6 +411,7 @@ struct InjectParams {
 };
 
 __global__ void __launch_bounds__(256) inject_kernel(const InjectParams p) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = p.P + p.T;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
@@ -478,6 +484,7 @@ struct SampleParams {
 };
 
 __global__ void __launch_bounds__(256) sample_kernel(const SampleParams p) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + warp;
   if (row >= p.rows) return;
@@ -581,6 +588,7 @@ struct ArgmaxCombineParams {
   int T, Q, out_q_stride, out_q0;
 };
 __global__ void __launch_bounds__(256) argmax_combine_kernel(const ArgmaxCombineParams p) {
+  pdl_sync();
   const long long row = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
   if (row >= p.rows) return;
   const float2* r = p.part + row * p.parts;
@@ -631,6 +639,7 @@ struct RemaskParams {
 constexpr int kRemaskMaxT = 4096;
 
 __global__ void __launch_bounds__(256) remask_kernel(const RemaskParams p) {
+  pdl_sync();
   __shared__ float conf[kRemaskMaxT];
   __shared__ int s_count;
   __shared__ float s_cut;

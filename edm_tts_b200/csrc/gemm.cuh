@@ -246,6 +246,7 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_sync();  // prologue done (barriers, TMEM): from here on the activations written by the previous kernel are read
 
   if (warp == 0) {
     if (lane == 0) {
@@ -422,6 +423,7 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
   cluster_sync_all();  // both CTAs' barriers initialised and TMEM allocated before any cross-CTA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_sync();  // prologue done (barriers, TMEM, bias staged from the weights): the previous kernel's activations are read from here on
 
   if (warp == 0) {
     if (lane == 0) {

@@ -32,6 +32,17 @@ __device__ __forceinline__ uint32_t elect_one() {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+// Programmatic dependent launch (see launch_pdl in abi.cu). pdl_trigger: this CTA no longer objects to the next kernel of the stream
+// being scheduled (its CTAs start their prologue as SM resources free up). pdl_wait: block until the previous kernel of the stream has
+// completed and its memory is visible; must precede the first access to anything another kernel wrote. Both are no-ops for a kernel
+// launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() {
+  pdl_trigger();
+  pdl_wait();
+}
+
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

@@ -80,6 +80,7 @@ struct LnGParams {
 
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_g_kernel(const LnGParams p) {
+  pdl_sync();
   constexpr int D = 128 * NV;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(256) layernorm_g_kernel(const LnGParams p) {
 template <int NV>
 __global__ void __launch_bounds__(32) t2s_length_head_kernel(const float* x0, const float* ln_w, const float* ln_b, const float* w, const float* b,
                                                              float eps, float* raw_out) {
+  pdl_sync();
   const int lane = threadIdx.x;
   float v[4 * NV], ww[4 * NV];
   rowg_load_f32<NV>(x0, lane, v);
@@ -136,6 +138,7 @@ struct T2sBeginParams {
   uint8_t* mask;           // [L] current mask = full_mask
 };
 __global__ void t2s_begin_kernel(const T2sBeginParams p) {
+  pdl_sync();
   const int L = p.n_text + p.length + 4;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L) return;
@@ -165,6 +168,7 @@ struct T2sUpdateParams {
   int L, offset, tok_mask;
 };
 __global__ void t2s_update_kernel(const T2sUpdateParams p) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.L) return;
   int tok = p.input_ids[i];
@@ -177,6 +181,7 @@ __global__ void t2s_update_kernel(const T2sUpdateParams p) {
 
 // speech_pred_tokens = sampled_tokens[full_mask] (:267): the speech positions are the contiguous range [start, start + length)
 __global__ void t2s_gather_out_kernel(const int* tokens, int start, int length, long long* out) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < length) out[i] = tokens[start + i];
 }
