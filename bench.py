@@ -26,6 +26,14 @@ WORKLOAD = "S2A decode: batch 64 x 10 s (500 frames) per GPU, 8 first-level step
 METRIC, UNIT = "s2a_decoded_codec_frames_per_s", "frames/s"
 
 
+def bench_config(world):
+    """The workload both arms are quoted on (BASELINE config 2). The reference arm times a bounded sample of it (cpu_baseline.sample)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": B_PER_GPU, "frames": T_FRAMES, "prompt_frames": P_PROMPT, "decode_steps": DECODE_STEPS,
+            "weights": "random-init, reference architecture (configs/injection_conformer/base_config)",
+            "sampling_noise": "synthetic Gumbel noise: in-kernel Philox in the GPU arm, pre-generated tensors in the reference arm", "l2": "working set 3.5 GB per step >> 126 MB L2 (no flush needed)",
+            "parallelism": f"batch-sharded x{world} (runner.ShardedDecoder), one all_gather of the int16 codes per step" if world > 1 else "single GPU"}
+
+
 def flops_per_frame(S, T):
     """algorithmic FLOPs per target frame with no prompt."""
     return (S * (276.82e6 + 20480.0 * T) if S > 1 else 0.0) + 922.75e6 + 65536.0 * T
@@ -167,11 +175,12 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     fps = args.steps * T_FRAMES / dt
-    sample = f"1 utterance x {T_FRAMES} frames x {DECODE_STEPS} steps per step (1/64 of the GPU arm's batch), fp32, torch CPU"
+    sample = (f"bounded sample of the workload: 1 utterance x {T_FRAMES} frames x {DECODE_STEPS} steps per timed step (1/64 of the 64-utterance batch the "
+              f"GPU arm decodes per step; the full batch takes ~70 s per step on these cores), oracle port of the reference in fp32 torch, {threads} threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "data": "synthetic", "config": bench_config(args.gpus), "sample": sample,
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -426,10 +435,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "frames": T, "prompt_frames": P_PROMPT, "decode_steps": DECODE_STEPS,
-                   "weights": "random-init, reference architecture (configs/injection_conformer/base_config)",
-                   "sampling_noise": "in-kernel Philox", "l2": "working set 3.5 GB per step >> 126 MB L2 (no flush needed)",
-                   "parallelism": f"batch-sharded x{world} (runner.ShardedDecoder), one all_gather of the int16 codes per step" if world > 1 else "single GPU"},
+        "config": bench_config(world),
         "clocks": sampler.result(),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": sem_host.numel() * 8, "d2h_bytes_per_step": codes_host.numel() * 2 * world,
                 "ms_per_step": ms_e2e / args.steps,
