@@ -85,14 +85,14 @@ def peaks():
 
 def ncu_traffic():
     """DRAM bytes per GEMM launch from the committed ncu --set full capture of this same command (tools/gpu_ncu_bench.sh ->
-    tools/ncu_traffic.py -> profiles/ncu_traffic_r01.json); None when the file is missing."""
-    path = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
-    if not os.path.exists(path):
+    tools/ncu_traffic.py -> profiles/ncu_traffic_r02.json); None when the file is missing."""
+    path = next((q for q in (os.path.join(ROOT, "profiles", f"ncu_traffic_r0{r}.json") for r in (2, 1)) if os.path.exists(q)), None)
+    if path is None:
         return None, None
     with open(path) as f:
         t = json.load(f)
     e = t.get("gemm_bf16_tn_pair_kernel (all captured epilogues)")
-    return (e["traffic_bytes_per_launch"], "profiles/ncu_traffic_r01.json") if e else (None, None)
+    return (e["traffic_bytes_per_launch"], os.path.relpath(path, ROOT)) if e else (None, None)
 
 
 def cpu_oracle_fps(B, T, steps, repeats, threads):
