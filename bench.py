@@ -328,6 +328,20 @@ def main():
         torch.cuda.synchronize()
         lat_ms = r0.elapsed_time(r1) / 10
         lat_launches = (lib.edm_launch_count() - l0) // 10
+        # the same decode replayed from a CUDA graph (edm_tts_b200.serving.GraphedDecode, Philox noise with a per-request seed word)
+        from edm_tts_b200.serving import GraphedDecode
+
+        gd = GraphedDecode(model, 1, 150, steps=DECODE_STEPS, seed=SEED, fresh_noise=False)
+        for _ in range(3):
+            gd(tok1, clone=False)
+        torch.cuda.synchronize()
+        r0.record()
+        for _ in range(10):
+            gd(tok1, clone=False)
+        r1.record()
+        torch.cuda.synchronize()
+        lat_graph_ms = r0.elapsed_time(r1) / 10
+        del gd
     tf_peak, hbm_peak, peak_kind = peaks()
     traffic, traffic_src = ncu_traffic()
     # algorithmic bytes of the 8 GEMMs of one conformer block at M = B*T rows (operands read once, outputs written once,
@@ -427,6 +441,26 @@ def main():
     t2s_len_ms = r0.elapsed_time(r1) / 5
     del t2s
     torch.cuda.empty_cache()
+    t2s_inc_ms = None
+    if rank == 0 and not args.no_cpu_baseline:
+        # the incumbent for this step: the reference's op sequence as eager torch kernels under autocast(bf16) on the same GPU
+        from oracle import t2s as ot2s
+        from edm_tts_b200.synthetic import make_t2s_noise
+
+        tsd = {k: v.to(dev) for k, v in make_t2s_state_dict(t2s_dims, 0).items()}
+        tt = ot2s.text_tokens_of(t2s_text, t2s_dims, dev)
+        tn = make_t2s_noise(len(t2s_text) + T + 4, 16, t2s_dims, seed=3)
+        tcat, trem = tn["cat_gumbel"].to(dev), tn["remask_gumbel"].to(dev)
+        ts = []
+        with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+            for _ in range(2):
+                r0.record()
+                ot2s.infer(tsd, t2s_dims, tt, pred_iters=16, gt_length=T, cat_gumbel=tcat, remask_gumbel=trem)
+                r1.record()
+                torch.cuda.synchronize()
+                ts.append(r0.elapsed_time(r1))
+        t2s_inc_ms = ts[-1]
+        del tsd, tcat, trem
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -445,7 +479,7 @@ def main():
         "fixed_global_batch": {"global_batch": FG, "per_gpu": FG // world, "frames": T, "decode_steps": DECODE_STEPS, "steps_timed": fixed_steps,
                                "ms_per_step": ms_fixed / fixed_steps, "value": FG * T * fixed_steps / (ms_fixed * 1e-3), "unit": UNIT, "scaling": "strong",
                                "workload": "BASELINE config 3: S2A decode of 512 x 10 s utterances batch-sharded over the GPUs of the run"},
-        "latency_b1_t150_s8_ms": lat_ms, "latency_b1_launches": lat_launches,
+        "latency_b1_t150_s8_ms": lat_ms, "latency_b1_launches": lat_launches, "latency_b1_t150_s8_graph_replay_ms": lat_graph_ms,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_pair_kernel (tcgen05 cta_group::2; all conformer / head GEMMs of the timed region)",
                      "achieved": gemm_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tf_peak, "traffic": traffic,
                      "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean of the 8 GEMMs of one block)",
@@ -475,6 +509,7 @@ def main():
                              "note": "conv decoder on the encoder's implicit-GEMM kernels (transposed convs as 2-tap convs into a shifted output view); 1.74 MMAC per output sample"},
         "secondary_t2s": {"metric": "t2s_semantic_tokens_per_s", "value": T / (t2s_ms * 1e-3), "unit": "tokens/s", "ms_per_utterance": t2s_ms,
                           "length_predictor_ms": t2s_len_ms, "launches_per_utterance": int(t2s_launches),
+                          "gpu_incumbent_ms_per_utterance": t2s_inc_ms,
                           "workload": f"TextToSemanticWLen.infer, hidden 384 / 8 heads of 48 / depth 12 (train_config.yaml), pred_iters 16 (inference.py:38), "
                                       f"{len(t2s_text)} text bytes -> {T} semantic tokens, batch 1 (the reference's infer is batch-1), in-kernel Philox noise",
                           "note": "latency-bound: ~180 dependent launches per iteration on a 600-row sequence; device time per utterance, tokens resident"},
