@@ -616,6 +616,6 @@ def test_dacdec():
 
 if __name__ == "__main__":
     t0 = time.time()
-    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvq": test_rvq, "rvqtc": test_rvqtc, "rvqtime": test_rvqtime, "gemmsus": test_gemmsus, "kmeans": test_kmeans, "dacenc": test_dacenc, "dacdec": test_dacdec}[sys.argv[1]]()
+    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvqtc": test_rvqtc, "rvqtime": test_rvqtime, "gemmsus": test_gemmsus, "kmeans": test_kmeans, "dacenc": test_dacenc, "dacdec": test_dacdec}[sys.argv[1]]()
     torch.cuda.synchronize()
     print(f"[{sys.argv[1]}] done in {time.time() - t0:.1f}s", flush=True)
