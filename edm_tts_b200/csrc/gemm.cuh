@@ -365,13 +365,16 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
 // less L2->SM operand traffic per FLOP than 128 x 256 tiles), CTA 0's MMA thread issues M = 256 instructions that read
 // both CTAs' shared memory and write each CTA's own TMEM half, completion is multicast to both CTAs' barriers.
 // 32 KB per stage instead of 48 KB -> a 6-deep ring in the same shared memory.
-constexpr int kPairStages = 6;
+// Shared memory of one CTA: a ring of 32 KB stages, then (TMA-output epilogues) a 4 KB staging box per epilogue warp, then (rotary
+// epilogues) the 32 KB cos|sin table of the tile's rows, barriers at a fixed offset. The bias is read through the read-only path by
+// the epilogue threads (64 floats each, L1-resident), not staged: that leaves room for 7 / 5 ring stages instead of 6 / 4.
 constexpr uint32_t kPairStageBytes = 2 * kGemmABytes;  // A (128 x 64) + half of B (128 x 64)
-constexpr uint32_t kPairSmemBytes = kPairStages * kPairStageBytes + kGemmMaxN * 4 + 1024 + 256;
-
-// EPI_RESID_TMA trades two of the six ring stages for a 4 KB staging box per epilogue warp (same shared-memory total).
-constexpr int kPairStagesTma = 4;
-constexpr uint32_t kPairStagingBytes = 32 * 32 * 4;  // 32 rows x 32 fp32 columns
+constexpr uint32_t kPairStagingBytes = 32 * 32 * 4;    // 32 rows x 32 fp32 columns (or 32 rows x 64 bf16)
+constexpr uint32_t kPairRopeTabBytes = 128 * 16 * 16;  // 128 rows x (8 cos + 8 sin float4 chunks)
+constexpr uint32_t kPairBarOffset = 7 * kPairStageBytes;
+constexpr uint32_t kPairSmemBytes = kPairBarOffset + 256 + 1024;
+__host__ __device__ constexpr int pair_stages(bool tma_out, bool rope) { return rope ? (tma_out ? 4 : 6) : (tma_out ? 5 : 7); }
+constexpr int kPairMaxStages = 7;
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
@@ -379,14 +382,16 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
                          const __grid_constant__ CUtensorMap tma_c, const GemmParams p) {
   constexpr bool kTmaOut = EPI == EPI_RESID_TMA || EPI == EPI_SWISH_TMA || EPI == EPI_ROPE_TMA || EPI == EPI_F32_TMA;
   constexpr bool kRope = EPI == EPI_QKV_ROPE || EPI == EPI_ROPE_TMA;
-  constexpr int kSt = kTmaOut ? kPairStagesTma : kPairStages;
-  static_assert(kPairStagesTma * kPairStageBytes + kGemmEpiWarps * kPairStagingBytes == kPairStages * kPairStageBytes, "smem budget");
+  constexpr int kSt = pair_stages(kTmaOut, kRope);
+  constexpr uint32_t kStagingOffset = kSt * kPairStageBytes;
+  constexpr uint32_t kRopeTabOffset = kStagingOffset + (kTmaOut ? kGemmEpiWarps * kPairStagingBytes : 0);
+  static_assert(kRopeTabOffset + (kRope ? kPairRopeTabBytes : 0) <= kPairBarOffset, "smem budget");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  float* s_bias = reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes + kGemmMaxN * 4);
-  uint64_t* empty_bar = full_bar + kPairStages;
-  uint64_t* tmem_full_bar = empty_bar + kPairStages;
+  float* s_rope = reinterpret_cast<float*>(smem + kRopeTabOffset);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kPairBarOffset);
+  uint64_t* empty_bar = full_bar + kPairMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kPairMaxStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
@@ -414,16 +419,11 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_pair<512>(tmem_base_slot);
-  if (p.bias != nullptr) {
-    for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = __ldg(p.bias + i);
-  } else {
-    for (int i = threadIdx.x; i < p.N; i += kGemmThreads) s_bias[i] = 0.f;
-  }
   tc_fence_before();
   cluster_sync_all();  // both CTAs' barriers initialised and TMEM allocated before any cross-CTA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
-  pdl_sync();  // prologue done (barriers, TMEM, bias staged from the weights): the previous kernel's activations are read from here on
+  pdl_sync();  // prologue done (barriers, TMEM): the previous kernel's activations are read from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -487,14 +487,17 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       const int row = m_blk * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM + quad * 32 + lane;
       const int col0 = n_blk * kGemmBN + sub * 64;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kGemmBN + sub * 64;
+      // this thread's 64 bias values as 16 float4 chunks: the same addresses in every lane (one broadcast transaction each), L1-resident
+      const float4* bias_g = reinterpret_cast<const float4*>(p.bias != nullptr ? p.bias + col0 : nullptr);
+      auto bias4 = [&](int k) { return bias_g != nullptr ? __ldg(bias_g + k) : make_float4(0.f, 0.f, 0.f, 0.f); };
       bool rope_tile = false;
       if constexpr (kRope) {
-        // The rotary cos|sin rows of this CTA's 128 token rows go to shared memory (the bias area is free: no bias here)
+        // The rotary cos|sin rows of this CTA's 128 token rows go to shared memory
         // while the tile's mainloop is still running: one coalesced 32 KB read per tile instead of 4 x 128 rows x 256 B
         // of dependent 16-byte loads. Chunk index is XOR-swizzled with (row & 7) so row-per-lane reads are conflict-free.
         rope_tile = n_blk * kGemmBN < p.rope_cols;
         if (rope_tile) {
-          float4* tab = reinterpret_cast<float4*>(s_bias);
+          float4* tab = reinterpret_cast<float4*>(s_rope);
           const int et = threadIdx.x - 64;
           asm volatile("bar.sync 1, 512;" ::: "memory");  // previous tile's readers are done
 #pragma unroll
@@ -521,11 +524,11 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
       if constexpr (EPI == EPI_ROPE_TMA) {
-        uint8_t* stg = smem + kSt * kPairStageBytes + (warp - 2) * kPairStagingBytes;
+        uint8_t* stg = smem + kStagingOffset + (warp - 2) * kPairStagingBytes;
         const int tr = quad * 32 + lane;
         if (lane == 0) bulk_wait_group_read0();
         __syncwarp();
-        gemm_epilogue_rope64(p, row, col0, r0, r1, rope_tile ? smem_u32(s_bias) + tr * 256 : 0u, tr & 7, smem_u32(stg) + lane * 128);
+        gemm_epilogue_rope64(p, row, col0, r0, r1, rope_tile ? smem_u32(s_rope) + tr * 256 : 0u, tr & 7, smem_u32(stg) + lane * 128);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -537,18 +540,17 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       if constexpr (EPI == EPI_SWISH_TMA) {
         // bf16 output: the warp's 32 x 64 slice is one 32-row x 128-byte box in its staging buffer (128B-swizzled rows), stored
         // by TMA as whole lines instead of 32 x 8 scattered 16-byte stores; rows beyond M are clipped by the tensor map
-        uint8_t* stg = smem + kSt * kPairStageBytes + (warp - 2) * kPairStagingBytes;
+        uint8_t* stg = smem + kStagingOffset + (warp - 2) * kPairStagingBytes;
         const uint32_t stg_row = smem_u32(stg) + lane * 128;
         const int sw = lane & 7;
         const int row0 = m_blk * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM + quad * 32;
-        const uint32_t b4 = smem_u32(s_bias + col0);
         uint32_t w[32];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const uint32_t* r = h == 0 ? r0 : r1;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 b = lds128(b4 + 16 * (8 * h + i));
+            const float4 b = bias4(8 * h + i);
             const uint32_t h01 = pack_bf16x2(__uint_as_float(r[4 * i + 0]) + b.x, __uint_as_float(r[4 * i + 1]) + b.y);
             const uint32_t h23 = pack_bf16x2(__uint_as_float(r[4 * i + 2]) + b.z, __uint_as_float(r[4 * i + 3]) + b.w);
             w[16 * h + 2 * i] = bf16x2_mul(h01, pack_bf16x2(sigmoid_tanh(bf16lo(h01)), sigmoid_tanh(bf16hi(h01))));
@@ -573,18 +575,17 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
         // RESID: x[rows, cols] += scale * bf16(acc + bias) (TMA reduce-add); F32: out = acc + bias (TMA store).
         // The warp's 32 x 64 slice leaves as two 32 x 32 fp32 boxes through its
         // 4 KB staging buffer (128B-swizzled rows); rows beyond M are clipped by the tensor map
-        uint8_t* stg = smem + kSt * kPairStageBytes + (warp - 2) * kPairStagingBytes;
+        uint8_t* stg = smem + kStagingOffset + (warp - 2) * kPairStagingBytes;
         const uint32_t stg_row = smem_u32(stg) + lane * 128;
         const int sw = lane & 7;
         const int row0 = m_blk * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM + quad * 32;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const uint32_t b4 = smem_u32(s_bias + col0 + 32 * h);
           if (lane == 0) bulk_wait_group_read0();  // the previous box has been read out of the staging buffer
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 b = lds128(b4 + 16 * i);
+            const float4 b = bias4(8 * h + i);
             const uint32_t* r = h == 0 ? r0 : r1;
             if constexpr (EPI == EPI_RESID_TMA)
               sts128(stg_row + ((i ^ sw) << 4),
@@ -609,13 +610,12 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
       if (row >= p.M) continue;
       if constexpr (EPI == EPI_QKV_ROPE) {
         const int tr = quad * 32 + lane;
-        gemm_epilogue_rope64(p, row, col0, r0, r1, rope_tile ? smem_u32(s_bias) + tr * 256 : 0u, tr & 7);
+        gemm_epilogue_rope64(p, row, col0, r0, r1, rope_tile ? smem_u32(s_rope) + tr * 256 : 0u, tr & 7);
       } else {
-        const uint32_t b4 = smem_u32(s_bias + col0);
         float v[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 b = lds128(b4 + 16 * i);
+          const float4 b = bias4(i);
           v[4 * i + 0] = __uint_as_float(r0[4 * i + 0]) + b.x;
           v[4 * i + 1] = __uint_as_float(r0[4 * i + 1]) + b.y;
           v[4 * i + 2] = __uint_as_float(r0[4 * i + 2]) + b.z;
@@ -625,7 +625,7 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           float g[32];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 b = lds128(b4 + 16 * (8 + i));
+            const float4 b = bias4(8 + i);
             g[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
             g[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
             g[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
@@ -639,7 +639,7 @@ gemm_bf16_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid
           gemm_store_32<EPI>(p, row, col0, v);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 b = lds128(b4 + 16 * (8 + i));
+            const float4 b = bias4(8 + i);
             v[4 * i + 0] = __uint_as_float(r1[4 * i + 0]) + b.x;
             v[4 * i + 1] = __uint_as_float(r1[4 * i + 1]) + b.y;
             v[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;

@@ -1,6 +1,6 @@
 """A/B timing of the bench step (B=64 x 500 frames x 8 steps) and of the single-utterance decode under the bring-up library
 (gpurun_out/libedm_bringup.so, built with -DEDM_BRINGUP so that the EDM_* environment switches exist).
-    EDM_PDL=0 python tools/ab_step.py [steps]"""
+    EDM_PDL=0 python tools/ab_step.py [steps]          EDM_AB_LIB=path/to/other.so python tools/ab_step.py   (another build of the library)"""
 import os
 import sys
 
@@ -10,9 +10,9 @@ import torch  # noqa: E402
 
 import edm_tts_b200._lib as L  # noqa: E402
 
-alt = os.path.join(ROOT, "gpurun_out", "libedm_bringup.so")
+alt = os.environ.get("EDM_AB_LIB") or os.path.join(ROOT, "gpurun_out", "libedm_bringup.so")
 if os.path.exists(alt):
-    L.LIB_PATH = alt
+    L.LIB_PATH = os.path.abspath(alt)
 from edm_tts_b200 import InjectionConformerModel  # noqa: E402
 from edm_tts_b200.config import InjectionConformerConfig  # noqa: E402
 from edm_tts_b200.synthetic import OracleConfig, make_state_dict  # noqa: E402
