@@ -123,8 +123,17 @@ struct LnParams {
 
 // 3 CTAs / SM (80 registers): 24 warps x 4 KB of row data in flight per SM measured best (5.7 TB/s)
 __global__ void __launch_bounds__(256, 3) layernorm_kernel(const LnParams p) {
-  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+  // Few rows (single-utterance decodes): the kernel is a chain of L2 round trips (row -> statistics -> weights), so the weight lines
+  // (constants) are pulled into L1 while the previous kernel is still running. With many rows L1 holds them after the first warp anyway.
+  if (p.rows <= 4096) {
+    const float* wb[4] = {p.w1, p.b1, p.w2, p.b2};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (wb[j] != nullptr) prefetch_l1(wb[j] + (warp * 32 + lane) * 4);  // 8 warps x 512 B = the 4 KB vector, one 16 B touch per lane
+  }
+  pdl_wait();
   const int row = (p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 8 + warp;
   if (row >= p.rows) return;
   float v[32];

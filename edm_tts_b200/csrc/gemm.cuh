@@ -246,24 +246,36 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
-  pdl_sync();  // prologue done (barriers, TMEM): from here on the activations written by the previous kernel are read
-
+  // Prologue done (barriers, TMEM). Everything the previous kernel of the stream wrote (the activations: A operand, residual stream)
+  // may be touched only after pdl_wait; the weights are constants, so the producer requests the first ring-full of weight tiles
+  // before it waits: their DRAM latency (the whole cost of a single-utterance GEMM) overlaps the previous kernel's tail.
+  pdl_trigger();
   if (warp == 0) {
     if (lane == 0) {
+      const int t0 = blockIdx.x;
+      const int pre = t0 < num_tiles ? (num_kb < kSmStages ? num_kb : kSmStages) : 0;
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_arrive_expect_tx(&full_bar[kb], kSmStageBytes);
+        tma_load_2d(&tma_b, &full_bar[kb], smem + kb * kSmStageBytes + kGemmABytes, kb * kGemmBK, p.b_row_offset + (t0 % num_n) * kSmBN);
+      }
+      pdl_wait();
       uint32_t it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m_blk = t / num_n, n_blk = t % num_n;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t stage = it % kSmStages;
-          mbar_wait(&empty_bar[stage], ((it / kSmStages) & 1) ^ 1);
           uint8_t* sa = smem + stage * kSmStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], kSmStageBytes);
+          if (it >= static_cast<uint32_t>(pre)) {
+            mbar_wait(&empty_bar[stage], ((it / kSmStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], kSmStageBytes);
+            tma_load_2d(&tma_b, &full_bar[stage], sa + kGemmABytes, kb * kGemmBK, p.b_row_offset + n_blk * kSmBN);
+          }
           tma_load_2d(&tma_a, &full_bar[stage], sa, p.a_k_offset + kb * kGemmBK, m_blk * kGemmBM);
-          tma_load_2d(&tma_b, &full_bar[stage], sa + kGemmABytes, kb * kGemmBK, p.b_row_offset + n_blk * kSmBN);
         }
       }
     }
   } else if (warp == 1) {
+    pdl_wait();
     constexpr uint32_t idesc = umma_idesc_bf16(kGemmBM, kSmBN, 0, 0);
     uint32_t it = 0;
     int acc = 0;
@@ -288,6 +300,7 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
+    pdl_wait();
     const int quad = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -296,6 +309,19 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
       const int row = m_blk * kGemmBM + quad * 32 + lane;
       const int col0 = n_blk * kSmBN;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kSmBN;
+      // the tile's 64 bias values are requested before the wait for the accumulator: an L2 round trip off the critical path
+      float4 bias_v[16];
+      if constexpr (EPI == EPI_QKV_ROPE) {
+        if (col0 < p.rope_cols && row < p.M) {  // this row's cos | sin lines (constants): in L1 by the time the accumulator is ready
+          prefetch_l1(p.rope_cos + static_cast<long long>(row % p.seq_len) * 32);
+          prefetch_l1(p.rope_sin + static_cast<long long>(row % p.seq_len) * 32);
+        }
+      }
+      if constexpr (EPI != EPI_QKV_ROPE) {
+        const float4* bg = reinterpret_cast<const float4*>(p.bias != nullptr ? p.bias + col0 : nullptr);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bias_v[i] = bg != nullptr ? __ldg(bg + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       uint32_t r0[32], r1[32];
@@ -312,9 +338,7 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
       if constexpr (EPI == EPI_QKV_ROPE) {
         gemm_epilogue_rope64(p, row, col0, r0, r1);
       } else {
-        // a CTA sees one or two tiles here: the 64 bias values come straight from L2 instead of staging all N in the prologue
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias != nullptr ? p.bias + col0 : nullptr);
-        auto bias4 = [&](int i) { return b4 != nullptr ? __ldg(b4 + i) : make_float4(0.f, 0.f, 0.f, 0.f); };
+        auto bias4 = [&](int i) { return bias_v[i]; };
         float v[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

@@ -299,6 +299,7 @@ struct RvqSearchParams {
   float* latents;           // out [B, 96, T] residual-corrected latents before normalisation, or nullptr
   float one;                // 1.0f and 1, passed at run time so the saves of rvq_scan32 stay FMUL / IMAD (FMA pipe)
   int onei;
+  int n_mma;                // MMAs per codebook chunk: 4 (K = 32: the 3xTF32 products and the norm term); fewer = bring-up timing probe only
 };
 
 // Running first maximum of one frame's scores. The scan is ALU-pipe bound (FSETP / FMNMX / SEL all issue there at half
@@ -412,7 +413,8 @@ rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchPar
             tc_fence_after();
             const uint64_t bdesc = umma_desc_sw128(smem_u32(sRing + s * kRsTileBytes), 16, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss_tf32_warp(tmem_base + buf * kRsChunk, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              if (k < p.n_mma) umma_ss_tf32_warp(tmem_base + buf * kRsChunk, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0 ? 1u : 0u);
             umma_commit_warp(&ring_empty[s]);
             umma_commit_warp(&tfull_bar[buf]);
           }

@@ -409,6 +409,21 @@ def test_rvqtime():
     print(f"rvq mma.sync kernel B=32 T=3000: {ms_old:.3f} ms", flush=True)
 
 
+def test_rvqmma():
+    """Search kernel alone at config 4 with 4 / 2 / 1 MMAs per codebook chunk, with and without the compare work (timing only: fewer
+    than 4 MMAs give wrong codes). Separates the tensor-pipe / TMEM-accumulate cost of the K = 32 packing from the scan."""
+    from edm_tts_b200 import ResidualVectorQuantize
+    from edm_tts_b200.synthetic import OracleConfig, make_quantizer_state_dict
+    q = ResidualVectorQuantize(make_quantizer_state_dict(OracleConfig(), 0))
+    z = torch.randn(32, 1024, 3000, device=dev)
+    for n_mma in (4, 2, 1):
+        for probe in (0, 1):
+            L.lib().edm_rvq_tc_debug(4096, 512, 1, probe | (n_mma << 4))
+            ms = timeit(lambda: q.encode(z), iters=10, warm=3)
+            print(f"rvq search alone, {n_mma} MMAs per chunk, {'loads only' if probe else 'full scan'}: {ms:.3f} ms", flush=True)
+    L.lib().edm_rvq_tc_debug(4096, 512, 0, 0)
+
+
 def test_gemmsus():
     """Sustained (power-capped) throughput of single GEMM shapes run back to back for ~2 s each, ours vs torch.matmul (cuBLAS),
     with the SM clock sampled through NVML: separates 'kernel efficiency per clock' from 'energy per FLOP at the 1 kW cap'."""
@@ -616,6 +631,6 @@ def test_dacdec():
 
 if __name__ == "__main__":
     t0 = time.time()
-    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvqtc": test_rvqtc, "rvqtime": test_rvqtime, "gemmsus": test_gemmsus, "kmeans": test_kmeans, "dacenc": test_dacenc, "dacdec": test_dacdec}[sys.argv[1]]()
+    {"gemm": test_gemm, "attn": test_attn, "ln": test_ln, "conv": test_conv, "sample": test_sample, "remask": test_remask, "rvqtc": test_rvqtc, "rvqtime": test_rvqtime, "rvqmma": test_rvqmma, "gemmsus": test_gemmsus, "kmeans": test_kmeans, "dacenc": test_dacenc, "dacdec": test_dacdec}[sys.argv[1]]()
     torch.cuda.synchronize()
     print(f"[{sys.argv[1]}] done in {time.time() - t0:.1f}s", flush=True)
