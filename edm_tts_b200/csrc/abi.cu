@@ -489,6 +489,20 @@ extern "C" int edm_prof_collect(double* ms, double* work, int* count) {
   return 0;
 }
 
+#ifdef EDM_KTRACE
+// bring-up build only: copies the kernel timeline (8 x uint64 per traced launch) to the host and resets it; returns the launch count
+extern "C" int edm_ktrace_dump(unsigned long long* host, int max_slots) {
+  unsigned n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_ktrace_n, sizeof(n));
+  const int m = static_cast<int>(n) < max_slots ? static_cast<int>(n) : max_slots;
+  if (host != nullptr && m > 0) cudaMemcpyFromSymbol(host, g_ktrace, sizeof(unsigned long long) * 8 * (m < 4096 ? m : 4096));
+  const unsigned zero = 0;
+  cudaMemcpyToSymbol(g_ktrace_n, &zero, sizeof(zero));
+  return static_cast<int>(n);
+}
+#endif
+
 extern "C" int edm_gemm_bf16(const void* a, long long lda, const void* b, long long ldb, int M, int N, int K, int epilogue,
                              const float* bias, void* out, long long ldo, float scale, const float* rope_cos,
                              const float* rope_sin, int seq_len, int rope_cols, void* stream) {

@@ -128,7 +128,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  KTRACE_ENTRY(kt_entry);
   pdl_sync();
+#ifdef EDM_KTRACE
+  if (threadIdx.x == 0) { KTRACE_PUT(1, kt_entry); KTRACE_PUT(2, ktrace_now()); }
+#endif
 
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
@@ -392,6 +396,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tma_qkv, const AttnPara
 
   tc_fence_before();
   __syncthreads();
+#ifdef EDM_KTRACE
+  if (threadIdx.x == 0) KTRACE_END(2);
+#endif
   if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 

@@ -92,7 +92,11 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stream_kernel(const ConvSt
     fence_mbar_init();
   }
   __syncthreads();
+  KTRACE_ENTRY(kt_entry);
   pdl_sync();
+#ifdef EDM_KTRACE
+  if (tid == 0) { KTRACE_PUT(1, kt_entry); KTRACE_PUT(2, ktrace_now()); }
+#endif
 
   // producer state (thread 0 only): next row to request, as (unit, row inside the unit's [t_lo, t_hi))
   int pu = blockIdx.x, pr = 0;
@@ -257,6 +261,10 @@ __global__ void __launch_bounds__(kCsThreads, 1) conv_stream_kernel(const ConvSt
     }
     // rows t_end+2.. never requested: the run's last window rows were pulled by the loop above (t + 2 <= t_end + 1)
   }
+#ifdef EDM_KTRACE
+  __syncthreads();
+  if (tid == 0) KTRACE_END(3);
+#endif
 }
 
 }  // namespace edm

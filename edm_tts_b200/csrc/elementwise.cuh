@@ -124,6 +124,7 @@ struct LnParams {
 // 3 CTAs / SM (80 registers): 24 warps x 4 KB of row data in flight per SM measured best (5.7 TB/s)
 __global__ void __launch_bounds__(256, 3) layernorm_kernel(const LnParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  KTRACE_ENTRY(kt_entry);
   pdl_trigger();
   // Few rows (single-utterance decodes): the kernel is a chain of L2 round trips (row -> statistics -> weights), so the weight lines
   // (constants) are pulled into L1 while the previous kernel is still running. With many rows L1 holds them after the first warp anyway.
@@ -134,6 +135,9 @@ __global__ void __launch_bounds__(256, 3) layernorm_kernel(const LnParams p) {
       if (wb[j] != nullptr) prefetch_l1(wb[j] + (warp * 32 + lane) * 4);  // 8 warps x 512 B = the 4 KB vector, one 16 B touch per lane
   }
   pdl_wait();
+#ifdef EDM_KTRACE
+  if (threadIdx.x == 0) { KTRACE_PUT(1, kt_entry); KTRACE_PUT(2, ktrace_now()); }
+#endif
   const int row = (p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 8 + warp;
   if (row >= p.rows) return;
   float v[32];
@@ -153,6 +157,9 @@ __global__ void __launch_bounds__(256, 3) layernorm_kernel(const LnParams p) {
     if (p.w2 != nullptr) row_layernorm(v, p.w2, p.b2, lane, p.eps);
     row_store_bf16(p.z_out + zrow * kD, lane, v);
   }
+#ifdef EDM_KTRACE
+  if (threadIdx.x == 0) KTRACE_END(1);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ conv module core

@@ -249,6 +249,7 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
   // Prologue done (barriers, TMEM). Everything the previous kernel of the stream wrote (the activations: A operand, residual stream)
   // may be touched only after pdl_wait; the weights are constants, so the producer requests the first ring-full of weight tiles
   // before it waits: their DRAM latency (the whole cost of a single-utterance GEMM) overlaps the previous kernel's tail.
+  KTRACE_ENTRY(kt_entry);
   pdl_trigger();
   if (warp == 0) {
     if (lane == 0) {
@@ -259,6 +260,8 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
         tma_load_2d(&tma_b, &full_bar[kb], smem + kb * kSmStageBytes + kGemmABytes, kb * kGemmBK, p.b_row_offset + (t0 % num_n) * kSmBN);
       }
       pdl_wait();
+      KTRACE_PUT(1, kt_entry);
+      KTRACE_PUT(2, ktrace_now());
       uint32_t it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m_blk = t / num_n, n_blk = t % num_n;
@@ -288,6 +291,9 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
         const uint32_t stage = it % kSmStages;
         mbar_wait_spin(&full_bar[stage], (it / kSmStages) & 1);
         tc_fence_after();
+#ifdef EDM_KTRACE
+        if (it == 0 && lane == 0) KTRACE_PUT(3, ktrace_now());
+#endif
         const uint32_t sa = smem_u32(smem + stage * kSmStageBytes);
         const uint64_t adesc = umma_desc_sw128(sa, 16, 1024);
         const uint64_t bdesc = umma_desc_sw128(sa + kGemmABytes, 16, 1024);
@@ -296,6 +302,9 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
         umma_commit_warp(&empty_bar[stage]);
       }
       umma_commit_warp(&tmem_full_bar[acc]);
+#ifdef EDM_KTRACE
+      if (lane == 0) KTRACE_PUT(4, ktrace_now());
+#endif
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -331,6 +340,9 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
       tmem_ld_wait_dep(r1);
       tc_fence_before();
       __syncwarp();
+#ifdef EDM_KTRACE
+      if (warp == 2 && lane == 0) KTRACE_PUT(5, ktrace_now());
+#endif
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -380,6 +392,9 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
 
   tc_fence_before();
   __syncthreads();
+#ifdef EDM_KTRACE
+  if (threadIdx.x == 64) KTRACE_END(100 + EPI);
+#endif
   if (warp == 1) tmem_dealloc<128>(tmem_base);
 }
 

@@ -28,6 +28,27 @@ __device__ __forceinline__ uint32_t elect_one() {
   return pred;
 }
 
+// ---------------------------------------------------------------- kernel timeline (bring-up builds with -DEDM_KTRACE only)
+// Block 0 of a traced kernel writes %globaltimer stamps into slot g_ktrace_n (read after the PDL wait, i.e. after the previous kernel
+// has bumped it): [0] kind, [1] entry, [2] PDL wait over, [3..5] kernel-specific, [6] end. tools/ktrace.py prints the timeline.
+#ifdef EDM_KTRACE
+__device__ unsigned long long g_ktrace[8 * 4096];
+__device__ unsigned int g_ktrace_n;
+__device__ __forceinline__ unsigned long long ktrace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned ktrace_slot() { return *reinterpret_cast<volatile unsigned*>(&g_ktrace_n) & 4095u; }
+#define KTRACE_ENTRY(var) const unsigned long long var = ktrace_now()
+#define KTRACE_PUT(idx, val) do { if (blockIdx.x == 0) g_ktrace[ktrace_slot() * 8 + (idx)] = (val); } while (0)
+#define KTRACE_END(kind) do { if (blockIdx.x == 0) { const unsigned s_ = ktrace_slot(); g_ktrace[s_ * 8] = (kind); g_ktrace[s_ * 8 + 6] = ktrace_now(); __threadfence(); atomicAdd(&g_ktrace_n, 1u); } } while (0)
+#else
+#define KTRACE_ENTRY(var) do { } while (0)
+#define KTRACE_PUT(idx, val) do { } while (0)
+#define KTRACE_END(kind) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
