@@ -316,18 +316,24 @@ def main():
     lat_ms = None
     if rank == 0:
         tok1 = sem_dev[:1, :150].contiguous()
-        for _ in range(3):
-            model.infer_special(tok1, None, None, steps=DECODE_STEPS, seed=SEED)
-        torch.cuda.synchronize()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = lib.edm_launch_count()
-        r0.record()
-        for _ in range(10):
-            model.infer_special(tok1, None, None, steps=DECODE_STEPS, seed=SEED)
-        r1.record()
-        torch.cuda.synchronize()
-        lat_ms = r0.elapsed_time(r1) / 10
-        lat_launches = (lib.edm_launch_count() - l0) // 10
+
+        def lat_once():
+            for _ in range(3):
+                model.infer_special(tok1, None, None, steps=DECODE_STEPS, seed=SEED)
+            torch.cuda.synchronize()
+            l0 = lib.edm_launch_count()
+            r0.record()
+            for _ in range(10):
+                model.infer_special(tok1, None, None, steps=DECODE_STEPS, seed=SEED)
+            r1.record()
+            torch.cuda.synchronize()
+            return r0.elapsed_time(r1) / 10, (lib.edm_launch_count() - l0) // 10
+
+        lat_default_ms, lat_launches = lat_once()   # default mode: a row's bits never depend on the batch it is decoded in
+        model.set_low_latency(True)                 # single-utterance serving mode (split-K residual GEMMs below 512 rows)
+        lat_ms, _ = lat_once()
+        model.set_low_latency(False)
         # the same decode replayed from a CUDA graph (edm_tts_b200.serving.GraphedDecode, Philox noise with a per-request seed word)
         from edm_tts_b200.serving import GraphedDecode
 
@@ -480,6 +486,8 @@ def main():
                                "ms_per_step": ms_fixed / fixed_steps, "value": FG * T * fixed_steps / (ms_fixed * 1e-3), "unit": UNIT, "scaling": "strong",
                                "workload": "BASELINE config 3: S2A decode of 512 x 10 s utterances batch-sharded over the GPUs of the run"},
         "latency_b1_t150_s8_ms": lat_ms, "latency_b1_launches": lat_launches, "latency_b1_t150_s8_graph_replay_ms": lat_graph_ms,
+        "latency_b1_t150_s8_default_mode_ms": lat_default_ms,
+        "latency_note": "B=1 x 150 frames x 8 steps + full pass, device time per decode; *_ms and the graph replay in the model's low-latency mode (set_low_latency: split-K residual GEMMs, the mode for the reference's single-utterance call), *_default_mode_ms in the batch-invariant default",
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tn_pair_kernel (tcgen05 cta_group::2; all conformer / head GEMMs of the timed region)",
                      "achieved": gemm_tflops, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tflops / tf_peak, "traffic": traffic,
                      "traffic_unit": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, mean of the 8 GEMMs of one block)",

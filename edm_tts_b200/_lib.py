@@ -47,6 +47,7 @@ _SIGNATURES = {
     "edm_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _f, _vp, _vp, _i, _i, _vp]),
     "edm_attention": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "edm_layernorm": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "edm_gemm_resid_layernorm": (_i, [_vp, _ll, _vp, _ll, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _i, _vp]),
     "edm_conv_module": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "edm_sample": (_i, [_vp, _ll, _i, _vp, _i, _ull, _u, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "edm_remask": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _ull, _u, _vp]),
@@ -67,6 +68,7 @@ _SIGNATURES = {
     "edm_s2a_set_batch_offset": (_i, [_vp, _ll]),
     "edm_s2a_set_seed_buffer": (_i, [_vp, _vp]),
     "edm_s2a_set_keep_logits": (_i, [_vp, _i]),
+    "edm_s2a_set_low_latency": (_i, [_vp, _i]),
     "edm_s2a_set_prompt_injections": (_i, [_vp, _vp]),
     "edm_s2a_build_input": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "edm_s2a_first_level": (_i, [_vp, _vp, _vp]),

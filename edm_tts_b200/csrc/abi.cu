@@ -386,6 +386,55 @@ int launch_ln(const LnParams& p_in, cudaStream_t st) {
   return 0;
 }
 
+// Residual GEMM x += scale * bf16(A W^T + b) followed by the LayerNorm of the updated rows (every residual branch of the conformer
+// block is followed by one: conformer.py:229-234 with PreNorm :102-110). splits > 1 (low-latency mode of a context, few rows): a long-K
+// GEMM on few tiles is bound by what one SM's TMA pulls in (~100 GB/s: 250 ns per 24 KB k-step, tools/ktrace.py) while most SMs idle,
+// so K is cut into `splits` ranges that run as separate work items writing raw partial sums to `part`, and the LayerNorm launch adds
+// them up (layernorm_splitk_kernel): no extra launch, deterministic (fixed order), the bf16 rounding point of the Linear output kept.
+// The fp32 summation order differs from the unsplit kernels, which is why this is an opt-in: by default a row's bits do not depend on
+// the batch it is decoded in. splits <= 1 or an unsuitable shape: the two plain launches.
+int gemm_splitk_min_k() { static const int v = env_int("EDM_SPLITK_MINK", 2048); return v; }  // bring-up switch
+int choose_splits(int M, int K) {
+  const int tiles = ((M + kGemmBM - 1) / kGemmBM) * (kD / kSmBN), num_kb = K / kGemmBK, sms = num_sms();
+  if (K < gemm_splitk_min_k()) return 1;
+  for (int s = 4; s >= 2; s >>= 1)
+    if (tiles * s <= sms && num_kb % s == 0 && num_kb / s >= 4) return s;
+  return 1;
+}
+int launch_gemm_resid_ln(const CUtensorMap& ma, const WMap& wm, const GemmParams& p, const LnParams& ln, float* part, int splits, cudaStream_t st) {
+  const int sms = num_sms();
+  const int pair_tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((p.N + kGemmBN - 1) / kGemmBN);
+  const bool small = p.N % kGemmBN != 0 || (gemm_small_m() && pair_tiles * 4 <= sms);
+  if (!small || part == nullptr || splits < 2 || splits > 4 || p.K % (kGemmBK * splits) != 0 || p.N != kD || p.ldo != kD || ln.in != p.out ||
+      ln.rows != p.M || p.a_k_offset != 0) {
+    if (int rc = launch_gemm(EPI_RESID_F32, ma, wm, p, st)) return rc;
+    return launch_ln(ln, st);
+  }
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
+    EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_small_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmSmemBytes));
+    attr_once.done();
+  }
+  {
+    GemmParams q = p;
+    q.bias = nullptr; q.out = part; q.ldo = kD; q.scale = 1.0f; q.reverse = 0;
+    q.splits = splits; q.split_stride = static_cast<long long>(p.M) * kD;
+    next_direction();
+    ProfScope prof(PK_GEMM, 2.0 * p.M * p.N * p.K, st);
+    const int work = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / kSmBN) * splits;
+    launch_pdl(gemm_bf16_tn_small_kernel<EPI_F32>, dim3(work < sms ? work : sms), dim3(kSmThreads), kSmSmemBytes, st, ma, wm.small, q);
+    EDM_LAUNCH_CHECK("gemm_bf16_tn_small (split-K)");
+  }
+  LnParams l = ln;
+  l.partials = part; l.n_partials = splits; l.partial_stride = static_cast<long long>(p.M) * kD; l.lin_bias = p.bias; l.lin_scale = p.scale;
+  l.x_io = static_cast<float*>(p.out); l.reverse = 0;
+  next_direction();
+  ProfScope prof(PK_LN, static_cast<double>(l.rows) * kD * (4.0 * (splits + 2) + (l.y_out ? 4 : 0) + (l.z_out ? 2 : 0)), st);
+  launch_pdl(layernorm_splitk_kernel, dim3((l.rows + 7) / 8), dim3(256), 0, st, l);
+  EDM_LAUNCH_CHECK("layernorm_splitk");
+  return 0;
+}
+
 // glu_input: the kernel reads [B*N, 4096] and applies the GLU itself; otherwise the input is the already gated [B*N, 2048]
 // (the decoder's path: the GLU runs in the pointwise-conv GEMM epilogue) and the streaming kernel of conv_stream.cuh is used.
 int launch_conv(const ConvModParams& p, bool glu_input, cudaStream_t st) {
@@ -514,9 +563,27 @@ extern "C" int edm_gemm_bf16(const void* a, long long lda, const void* b, long l
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.a_k_offset = 0; p.b_row_offset = 0;
   p.bias = bias; p.out = out; p.ldo = ldo; p.scale = scale;
-  p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.seq_len = seq_len > 0 ? seq_len : 1; p.rope_cols = rope_cols;
+  p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.seq_len = seq_len > 0 ? seq_len : 1; p.rope_cols = rope_cols; p.reverse = 0; p.splits = 1; p.split_stride = 0;
   if (epilogue == EPI_QKV_ROPE && (rope_cos == nullptr || rope_sin == nullptr)) return fail(EDM_ERR_INVALID, "rope tables required");
   return launch_gemm(epilogue, ma, mb, p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int edm_gemm_resid_layernorm(const void* a, long long lda, const void* b, long long ldb, int M, int K, const float* bias, float* x,
+                                        float scale, const float* w1, const float* b1, const float* w2, const float* b2, float* y_out, void* z_out,
+                                        int seq_len, int z_skip, float eps, float* scratch, int splits, void* stream) {
+  if (int rc = check_arch()) return rc;
+  if (M <= 0 || K <= 0 || K % kGemmBK != 0 || x == nullptr) return fail(EDM_ERR_INVALID, "gemm_resid_layernorm shape M=%d K=%d", M, K);
+  CUtensorMap ma;
+  WMap mb;
+  if (int rc = make_tmap_2d(&ma, a, M, K, lda, kGemmBM)) return rc;
+  if (int rc = make_wmap(&mb, b, kD, K, ldb)) return rc;
+  GemmParams p;
+  p.M = M; p.N = kD; p.K = K; p.a_k_offset = 0; p.b_row_offset = 0; p.bias = bias; p.out = x; p.ldo = kD; p.scale = scale;
+  p.rope_cos = nullptr; p.rope_sin = nullptr; p.seq_len = 1; p.rope_cols = 0; p.reverse = 0; p.splits = 1; p.split_stride = 0;
+  LnParams ln;
+  ln.in = x; ln.in_is_bf16 = 0; ln.rows = M; ln.w1 = w1; ln.b1 = b1; ln.w2 = w2; ln.b2 = b2; ln.y_out = y_out;
+  ln.z_out = static_cast<__nv_bfloat16*>(z_out); ln.seq_len = seq_len > 0 ? seq_len : 1; ln.z_skip = z_skip; ln.eps = eps; ln.reverse = 0;
+  return launch_gemm_resid_ln(ma, mb, p, ln, scratch, splits, static_cast<cudaStream_t>(stream));
 }
 
 #ifdef EDM_ATTN_TRACE
@@ -942,6 +1009,8 @@ struct edm_s2a_ctx {
   long long batch_offset = 0;  // global index of this context's first sequence (Philox counters)
   bool mask_in_a = true;  // which buffer holds the current mask
   CUtensorMap m_z, m_h, m_g, m_zt, m_fine_z, m_qkv;
+  float* part = nullptr;  // [4, M, 1024] partial sums of the split-K residual GEMMs (low-latency mode; carved only for M <= kSplitMaxRows)
+  bool low_latency = false;  // edm_s2a_set_low_latency
 
   const void* bw(int layer, int f) const { return w[static_cast<size_t>(layer) * F_BLOCK_COUNT + f]; }
   const float* bwf(int layer, int f) const { return static_cast<const float*>(bw(layer, f)); }
@@ -976,47 +1045,44 @@ int injection_index(const edm_s2a_config& c, int layer) {
 GemmParams gp(int M, int N, int K, const float* bias, void* out, long long ldo, float scale = 1.0f) {
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.a_k_offset = 0; p.b_row_offset = 0; p.bias = bias; p.out = out; p.ldo = ldo; p.scale = scale;
-  p.rope_cos = nullptr; p.rope_sin = nullptr; p.seq_len = 1; p.rope_cols = 0;
+  p.rope_cos = nullptr; p.rope_sin = nullptr; p.seq_len = 1; p.rope_cols = 0; p.reverse = 0; p.splits = 1; p.split_stride = 0;
   return p;
 }
 
-// One conformer block on the bound workspace. In: x (fp32 residual stream) and z = LN_ff1(x) (bf16). Out: x holds the
-// pre-post_norm sum; the caller applies post_norm (it differs per call site).
-int run_block_body(edm_s2a_ctx* c, int l, cudaStream_t st) {
+// One conformer block on the bound workspace. In: x (fp32 residual stream) and z = LN_ff1(x) (bf16). Out: `post` applied to the
+// block's sum (post_norm and whatever the call site chains after it: the next block's pre-norm, the heads' LayerNorm, row compaction).
+// Every residual GEMM goes out together with the LayerNorm that follows it (launch_gemm_resid_ln).
+int run_block_body(edm_s2a_ctx* c, int l, const LnParams& post, cudaStream_t st) {
   const int M = c->M;
   const float eps = 1e-5f;
-  // ff1: x += 0.5 * W2 swish(W1 z + b1) + b2
-  if (int rc = launch_gemm(EPI_SWISH_BF16, c->m_z, c->bmaps[l].ff1_w1, gp(M, 4096, 1024, c->bwf(l, F_FF1_B1), c->h, 4096), st)) return rc;
-  if (int rc = launch_gemm(EPI_RESID_F32, c->m_h, c->bmaps[l].ff1_w2, gp(M, 1024, 4096, c->bwf(l, F_FF1_B2), c->x, 1024, 0.5f), st)) return rc;
-  // attention
   LnParams ln;
-  ln.in = c->x; ln.in_is_bf16 = 0; ln.rows = M; ln.w1 = c->bwf(l, F_ATTN_LN_W); ln.b1 = c->bwf(l, F_ATTN_LN_B); ln.w2 = nullptr; ln.b2 = nullptr;
+  ln.in = c->x; ln.in_is_bf16 = 0; ln.rows = M; ln.w2 = nullptr; ln.b2 = nullptr;
   ln.y_out = nullptr; ln.z_out = c->z; ln.seq_len = 1; ln.z_skip = 0; ln.eps = eps;
-  if (int rc = launch_ln(ln, st)) return rc;
+  // ff1: x += 0.5 * W2 swish(W1 z + b1) + b2; then the attention pre-norm
+  if (int rc = launch_gemm(EPI_SWISH_BF16, c->m_z, c->bmaps[l].ff1_w1, gp(M, 4096, 1024, c->bwf(l, F_FF1_B1), c->h, 4096), st)) return rc;
+  ln.w1 = c->bwf(l, F_ATTN_LN_W); ln.b1 = c->bwf(l, F_ATTN_LN_B);
+  if (int rc = launch_gemm_resid_ln(c->m_h, c->bmaps[l].ff1_w2, gp(M, 1024, 4096, c->bwf(l, F_FF1_B2), c->x, 1024, 0.5f), ln, c->part, c->low_latency ? choose_splits(M, 4096) : 1, st)) return rc;
+  // attention
   {
     GemmParams p = gp(M, 3072, 1024, nullptr, c->qkv, 3072);
     p.rope_cos = c->gwf(G_ROPE_COS); p.rope_sin = c->gwf(G_ROPE_SIN); p.seq_len = c->N; p.rope_cols = 2048;
     if (int rc = launch_gemm(EPI_QKV_ROPE, c->m_z, c->bmaps[l].wqkv, p, st)) return rc;
   }
   if (int rc = launch_attention(c->m_qkv, c->B, c->N, 16, c->z, 1024, 1024, 2048, st)) return rc;
-  if (int rc = launch_gemm(EPI_RESID_F32, c->m_z, c->bmaps[l].wo, gp(M, 1024, 1024, c->bwf(l, F_BO), c->x, 1024, 1.0f), st)) return rc;
-  // conv module
   ln.w1 = c->bwf(l, F_CONV_LN_W); ln.b1 = c->bwf(l, F_CONV_LN_B);
-  if (int rc = launch_ln(ln, st)) return rc;
-  // pointwise conv 1 + GLU in one pass: the packed weight interleaves 32 value rows with their 32 gate rows
+  if (int rc = launch_gemm_resid_ln(c->m_z, c->bmaps[l].wo, gp(M, 1024, 1024, c->bwf(l, F_BO), c->x, 1024, 1.0f), ln, c->part, c->low_latency ? choose_splits(M, 1024) : 1, st)) return rc;
+  // conv module. pointwise conv 1 + GLU in one pass: the packed weight interleaves 32 value rows with their 32 gate rows
   if (int rc = launch_gemm(EPI_GLU_BF16, c->m_z, c->bmaps[l].pw1, gp(M, 4096, 1024, c->bwf(l, F_PW1_B), c->h, 2048), st)) return rc;
   {
     ConvModParams p;
     p.in = c->h; p.out = c->g; p.dw_w = c->bwf(l, F_DW_W); p.dw_b = c->bwf(l, F_DW_B); p.cln_w = c->bwf(l, F_CLN_W); p.B = c->B; p.N = c->N;
     if (int rc = launch_conv(p, false, st)) return rc;
   }
-  if (int rc = launch_gemm(EPI_RESID_F32, c->m_g, c->bmaps[l].pw2, gp(M, 1024, 2048, c->bwf(l, F_PW2_B), c->x, 1024, 1.0f), st)) return rc;
-  // ff2
   ln.w1 = c->bwf(l, F_FF2_LN_W); ln.b1 = c->bwf(l, F_FF2_LN_B);
-  if (int rc = launch_ln(ln, st)) return rc;
+  if (int rc = launch_gemm_resid_ln(c->m_g, c->bmaps[l].pw2, gp(M, 1024, 2048, c->bwf(l, F_PW2_B), c->x, 1024, 1.0f), ln, c->part, c->low_latency ? choose_splits(M, 2048) : 1, st)) return rc;
+  // ff2, then post_norm (+ what the caller chains after it)
   if (int rc = launch_gemm(EPI_SWISH_BF16, c->m_z, c->bmaps[l].ff2_w1, gp(M, 4096, 1024, c->bwf(l, F_FF2_B1), c->h, 4096), st)) return rc;
-  if (int rc = launch_gemm(EPI_RESID_F32, c->m_h, c->bmaps[l].ff2_w2, gp(M, 1024, 4096, c->bwf(l, F_FF2_B2), c->x, 1024, 0.5f), st)) return rc;
-  return 0;
+  return launch_gemm_resid_ln(c->m_h, c->bmaps[l].ff2_w2, gp(M, 1024, 4096, c->bwf(l, F_FF2_B2), c->x, 1024, 0.5f), post, c->part, c->low_latency ? choose_splits(M, 4096) : 1, st);
 }
 
 // pass prologue: x = copy of the encoder input, z = LN_ff1[0](x)
@@ -1101,6 +1167,7 @@ struct Carver {
   }
 };
 
+constexpr size_t kSplitMaxRows = 1024;  // choose_splits never splits beyond 4 row tiles (148 SMs / 16 column tiles / 2)
 size_t carve(edm_s2a_ctx* c, uint8_t* base, int B, int T, int P, bool assign) {
   const size_t N = static_cast<size_t>(P) + T, M = static_cast<size_t>(B) * N, Mt = static_cast<size_t>(B) * T;
   const int nf = c->n_fine;
@@ -1133,7 +1200,9 @@ size_t carve(edm_s2a_ctx* c, uint8_t* base, int B, int T, int P, bool assign) {
   uint8_t* mask_a = k.take<uint8_t>(Mt);
   uint8_t* mask_b = k.take<uint8_t>(Mt);
   uint8_t* mask_raw = k.take<uint8_t>(Mt);
+  float* part = M <= kSplitMaxRows ? k.take<float>(4 * M * 1024) : nullptr;
   if (assign) {
+    c->part = part;
     c->x_in = x_in; c->x = x;
     for (int i = 0; i < 4; ++i) c->coarse_out[i] = co[i];
     c->z = z; c->h = h; c->qkv = qkv; c->g = g; c->zt = zt; c->logits = logits; c->coarse_logits = coarse_logits;
@@ -1226,7 +1295,6 @@ extern "C" int edm_s2a_first_level(edm_s2a_ctx* c, const float* x_in, void* stre
   if (int rc = pass_prologue(c, x_in ? x_in : c->x_in, st)) return rc;
   const int last = c->cfg.injection_layers[0];
   for (int l = 0; l <= last; ++l) {
-    if (int rc = run_block_body(c, l, st)) return rc;
     LnParams ln;
     ln.in = c->x; ln.in_is_bf16 = 0; ln.rows = c->M; ln.w1 = c->bwf(l, F_POST_LN_W); ln.b1 = c->bwf(l, F_POST_LN_B); ln.eps = 1e-5f;
     if (l < last) {
@@ -1236,7 +1304,7 @@ extern "C" int edm_s2a_first_level(edm_s2a_ctx* c, const float* x_in, void* stre
       ln.w2 = c->gwf(G_TL_LN_W); ln.b2 = c->gwf(G_TL_LN_B);
       ln.y_out = nullptr; ln.z_out = c->zt; ln.seq_len = c->N; ln.z_skip = c->P;
     }
-    if (int rc = launch_ln(ln, st)) return rc;
+    if (int rc = run_block_body(c, l, ln, st)) return rc;
   }
   GemmParams p = gp(c->Mt, 1024, 1024, c->gwf(G_HEAD_B), c->logits, 1024);
   return launch_gemm(EPI_F32, c->m_zt, c->head_map, p, st);
@@ -1246,6 +1314,12 @@ extern "C" int edm_s2a_set_keep_logits(edm_s2a_ctx* c, int keep) {
   if (c == nullptr) return fail(EDM_ERR_INVALID, "null context");
   if ((keep != 0) != c->keep_logits) c->bound = false;  // the workspace layout changes: bind again
   c->keep_logits = keep != 0;
+  return 0;
+}
+
+extern "C" int edm_s2a_set_low_latency(edm_s2a_ctx* c, int on) {
+  if (c == nullptr) return fail(EDM_ERR_INVALID, "null context");
+  c->low_latency = on != 0;
   return 0;
 }
 
@@ -1311,7 +1385,6 @@ extern "C" int edm_s2a_full_pass(edm_s2a_ctx* c, const float* x_in, const int* f
   const edm_s2a_config& cfg = c->cfg;
   if (int rc = pass_prologue(c, x_in ? x_in : c->x_in, st)) return rc;
   for (int l = 0; l < cfg.depth; ++l) {
-    if (int rc = run_block_body(c, l, st)) return rc;
     const int k = injection_index(cfg, l);
     const bool is_last = l == cfg.depth - 1;
     LnParams ln;
@@ -1322,12 +1395,12 @@ extern "C" int edm_s2a_full_pass(edm_s2a_ctx* c, const float* x_in, const int* f
       } else {
         ln.w2 = nullptr; ln.b2 = nullptr; ln.y_out = nullptr; ln.z_out = c->zt; ln.seq_len = c->N; ln.z_skip = c->P;  // bf16 copy of the target rows
       }
-      if (int rc = launch_ln(ln, st)) return rc;
+      if (int rc = run_block_body(c, l, ln, st)) return rc;
       continue;
     }
     // injection layer k: keep the block output, predict level k on the target rows, inject
     ln.w2 = c->gwf(G_TL_LN_W); ln.b2 = c->gwf(G_TL_LN_B); ln.y_out = c->coarse_out[k]; ln.z_out = c->zt; ln.seq_len = c->N; ln.z_skip = c->P;
-    if (int rc = launch_ln(ln, st)) return rc;
+    if (int rc = run_block_body(c, l, ln, st)) return rc;
     if (c->keep_logits) {
       float* lk = c->coarse_logits + static_cast<size_t>(k) * c->Mt * 1024;
       GemmParams p = gp(c->Mt, 1024, 1024, c->gwf(G_HEAD_B) + k * 1024, lk, 1024);

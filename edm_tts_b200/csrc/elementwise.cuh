@@ -38,6 +38,17 @@ __device__ __forceinline__ void row_load_f32_ldg(const float* row, int lane, flo
     v[4 * i + 3] = t.w;
   }
 }
+__device__ __forceinline__ void row_add_f32(const float* row, int lane, float (&v)[32]) {
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 t = r4[i * 32 + lane];
+    v[4 * i + 0] += t.x;
+    v[4 * i + 1] += t.y;
+    v[4 * i + 2] += t.z;
+    v[4 * i + 3] += t.w;
+  }
+}
 __device__ __forceinline__ void row_add_f32_ldg(const float* row, int lane, float (&v)[32]) {
   const float4* r4 = reinterpret_cast<const float4*>(row);
 #pragma unroll
@@ -119,6 +130,14 @@ struct LnParams {
   int seq_len, z_skip;    // z row for input row (b*seq_len + n) is b*(seq_len - z_skip) + (n - z_skip); rows n < z_skip dropped
   float eps;
   int reverse;            // 1: rows are walked from the last to the first (L2 reuse of the producer's most recent output)
+  // layernorm_splitk_kernel only: the input row is the residual stream updated by a split-K GEMM whose K ranges left raw fp32 partial
+  // sums at partials + s * partial_stride (s < n_partials, [rows, 1024] each): x_io[row] += lin_scale * bf16(sum_s partial_s + lin_bias)
+  const float* partials;
+  int n_partials;
+  long long partial_stride;
+  const float* lin_bias;  // nullable
+  float lin_scale;
+  float* x_io;
 };
 
 // 3 CTAs / SM (80 registers): 24 warps x 4 KB of row data in flight per SM measured best (5.7 TB/s)
@@ -160,6 +179,45 @@ __global__ void __launch_bounds__(256, 3) layernorm_kernel(const LnParams p) {
 #ifdef EDM_KTRACE
   if (threadIdx.x == 0) KTRACE_END(1);
 #endif
+}
+
+// Residual update + LayerNorm for the small-M split-K GEMMs (gemm.cuh: GemmParams::splits): the K ranges' partial sums are added in
+// range order, then bias, rounding to bf16 (the Linear output of the reference under autocast), scale and the residual add - the same
+// single rounded fp32 add per element the unsplit epilogue performs with red.global.add - and the LayerNorm pass of layernorm_kernel
+// on the updated row. The updated row goes back to x_io unless the LayerNorm's fp32 output overwrites it anyway (post_norm in place).
+__global__ void __launch_bounds__(256) layernorm_splitk_kernel(const LnParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+  {
+    const float* wb[4] = {p.w1, p.b1, p.w2, p.b2};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (wb[j] != nullptr) prefetch_l1(wb[j] + (warp * 32 + lane) * 4);
+    if (p.lin_bias != nullptr) prefetch_l1(p.lin_bias + (warp * 32 + lane) * 4);
+  }
+  pdl_wait();
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= p.rows) return;
+  float v[32], a[32];
+  row_load_f32(p.partials + static_cast<long long>(row) * kD, lane, a);
+  for (int s = 1; s < p.n_partials; ++s) row_add_f32(p.partials + s * p.partial_stride + static_cast<long long>(row) * kD, lane, a);
+  row_load_f32(p.x_io + static_cast<long long>(row) * kD, lane, v);
+  if (p.lin_bias != nullptr) row_add_f32_ldg(p.lin_bias, lane, a);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], __fmul_rn(p.lin_scale, bf16_round(a[i])));
+  if (p.y_out != p.x_io) row_store_f32(p.x_io + static_cast<long long>(row) * kD, lane, v);
+  if (p.w1 != nullptr) row_layernorm(v, p.w1, p.b1, lane, p.eps);
+  if (p.y_out != nullptr) row_store_f32(p.y_out + static_cast<long long>(row) * kD, lane, v);
+  if (p.z_out != nullptr) {
+    long long zrow = row;
+    if (p.z_skip > 0) {
+      const int b = row / p.seq_len, n = row % p.seq_len;
+      if (n < p.z_skip) return;
+      zrow = static_cast<long long>(b) * (p.seq_len - p.z_skip) + (n - p.z_skip);
+    }
+    if (p.w2 != nullptr) row_layernorm(v, p.w2, p.b2, lane, p.eps);
+    row_store_bf16(p.z_out + zrow * kD, lane, v);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ conv module core

@@ -50,6 +50,10 @@ struct GemmParams {
                   // where its producer finished, so the most recently written ~100 MB of its input are still in L2)
   int seq_len;    // rotary position = row % seq_len
   int rope_cols;  // columns [0, rope_cols) get rotary (q and k parts of the fused QKV projection)
+  // small-M kernel, EPI_F32 only: K is cut into `splits` equal ranges, one work item per (tile, range); range s writes its raw fp32
+  // partial sums (no bias) to out + s * split_stride. The consumer adds them in range order (layernorm_kernel with LnParams::partials).
+  int splits;
+  long long split_stride;
 };
 
 constexpr int kGemmBM = 128;
@@ -225,8 +229,9 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
   const int lane = threadIdx.x & 31;
   const int num_m = (p.M + kGemmBM - 1) / kGemmBM;
   const int num_n = p.N / kSmBN;
-  const int num_tiles = num_m * num_n;
-  const int num_kb = p.K / kGemmBK;
+  const int splits = (EPI == EPI_F32 && p.splits > 1) ? p.splits : 1;
+  const int num_tiles = num_m * num_n * splits;  // work items: (tile, K range), the ranges of a tile adjacent
+  const int num_kb = p.K / kGemmBK / splits;      // k-blocks per work item
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -257,23 +262,26 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
       const int pre = t0 < num_tiles ? (num_kb < kSmStages ? num_kb : kSmStages) : 0;
       for (int kb = 0; kb < pre; ++kb) {
         mbar_arrive_expect_tx(&full_bar[kb], kSmStageBytes);
-        tma_load_2d(&tma_b, &full_bar[kb], smem + kb * kSmStageBytes + kGemmABytes, kb * kGemmBK, p.b_row_offset + (t0 % num_n) * kSmBN);
+        tma_load_2d(&tma_b, &full_bar[kb], smem + kb * kSmStageBytes + kGemmABytes, ((t0 % splits) * num_kb + kb) * kGemmBK,
+                    p.b_row_offset + ((t0 / splits) % num_n) * kSmBN);
       }
       pdl_wait();
       KTRACE_PUT(1, kt_entry);
       KTRACE_PUT(2, ktrace_now());
       uint32_t it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_blk = t / num_n, n_blk = t % num_n;
+        const int m_blk = (t / splits) / num_n, n_blk = (t / splits) % num_n, kb0 = (t % splits) * num_kb;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t stage = it % kSmStages;
           uint8_t* sa = smem + stage * kSmStageBytes;
           if (it >= static_cast<uint32_t>(pre)) {
-            mbar_wait(&empty_bar[stage], ((it / kSmStages) & 1) ^ 1);
+            // polling wait: the ring is latency-bound at small M (8 stages = 192 KB in flight per SM against a ~2 us load + hand-back
+            // round trip), and the hardware-suspended try_wait adds its 0.4-0.7 us wake-up to every round
+            mbar_wait_spin(&empty_bar[stage], ((it / kSmStages) & 1) ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], kSmStageBytes);
-            tma_load_2d(&tma_b, &full_bar[stage], sa + kGemmABytes, kb * kGemmBK, p.b_row_offset + n_blk * kSmBN);
+            tma_load_2d(&tma_b, &full_bar[stage], sa + kGemmABytes, (kb0 + kb) * kGemmBK, p.b_row_offset + n_blk * kSmBN);
           }
-          tma_load_2d(&tma_a, &full_bar[stage], sa, p.a_k_offset + kb * kGemmBK, m_blk * kGemmBM);
+          tma_load_2d(&tma_a, &full_bar[stage], sa, p.a_k_offset + (kb0 + kb) * kGemmBK, m_blk * kGemmBM);
         }
       }
     }
@@ -314,7 +322,7 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m_blk = t / num_n, n_blk = t % num_n;
+      const int m_blk = (t / splits) / num_n, n_blk = (t / splits) % num_n;
       const int row = m_blk * kGemmBM + quad * 32 + lane;
       const int col0 = n_blk * kSmBN;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * kSmBN;
@@ -375,7 +383,9 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
           else
             gemm_store_argmax(p, row, col0, v, g);
         } else {
-          gemm_store_32<EPI>(p, row, col0, v);
+          GemmParams q = p;
+          if constexpr (EPI == EPI_F32) q.out = static_cast<float*>(p.out) + (t % splits) * p.split_stride;  // this K range's partial sums
+          gemm_store_32<EPI>(q, row, col0, v);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 b = bias4(8 + i);
@@ -384,7 +394,7 @@ gemm_bf16_tn_small_kernel(const __grid_constant__ CUtensorMap tma_a, const __gri
             v[4 * i + 2] = __uint_as_float(r1[4 * i + 2]) + b.z;
             v[4 * i + 3] = __uint_as_float(r1[4 * i + 3]) + b.w;
           }
-          gemm_store_32<EPI>(p, row, col0 + 32, v);
+          gemm_store_32<EPI>(q, row, col0 + 32, v);
         }
       }
     }

@@ -272,6 +272,7 @@ class InjectionConformerModel:
             raise L.EdmError("edm_s2a_create failed: " + lib.edm_last_error().decode())
         self._bound = None
         self._ws = None
+        self.low_latency = False
         self.encoder = _Encoder(self)
         self.acoustic_model = _AcousticModel(self._rvq, self.acoustic_size, self.num_quantizers, self.num_codevectors, self.device)
         self.semantic_embedding = _Embedding(self._w["sem_emb"])
@@ -372,6 +373,14 @@ class InjectionConformerModel:
         dummy_sem = torch.zeros(B, T, device=self.device, dtype=torch.int32)
         dummy_sp = torch.zeros(B, P, device=self.device, dtype=torch.int32)
         L.check(L.lib().edm_s2a_build_input(self._ctx, L.ptr(dummy_sem), L.ptr(dummy_sp), L.ptr(pc), pc.shape[1], L.stream_ptr()), "build_input")
+
+    def set_low_latency(self, on=True):
+        """Single-utterance serving mode (the reference's own call, inference.py:43-48): decodes of <= 512 rows split their long-K
+        residual GEMMs over K (edm_s2a_set_low_latency). Faster for one short utterance; the rounding noise of a row then depends on
+        how many rows are decoded together, which the default mode guarantees it never does."""
+        L.check(L.lib().edm_s2a_set_low_latency(self._ctx, int(bool(on))), "set_low_latency")
+        self.low_latency = bool(on)
+        return self
 
     # ------------------------------------------------------------------ the decode API
     @torch.no_grad()

@@ -16,10 +16,15 @@ import torch
 
 class GraphedDecode:
     def __init__(self, model, batch: int, frames: int, prompt_frames: int = 0, steps: int = 8, temperature: float = 1.0, seed: int = 0,
-                 fresh_noise=None, max_noise_bytes: int = 256 << 20):
+                 fresh_noise=None, max_noise_bytes: int = 256 << 20, low_latency=None):
+        """low_latency: capture the decode in the model's single-utterance mode (InjectionConformerModel.set_low_latency); default: on
+        for shapes of at most 512 rows, where it applies."""
         self.model, self.steps, self.temperature, self.seed = model, int(steps), float(temperature), int(seed)
         dev = model.device
         B, T, P, V = batch, frames, prompt_frames, model.num_codevectors
+        self.low_latency = bool(B * (T + P) <= 512 if low_latency is None else low_latency)
+        prev_mode = getattr(model, "low_latency", False)
+        model.set_low_latency(self.low_latency)
         self.sem = torch.zeros(B, T, dtype=torch.long, device=dev)
         self.ap = torch.zeros(B, model.num_quantizers, P, dtype=torch.long, device=dev) if P else None
         self.sp = torch.zeros(B, P, dtype=torch.long, device=dev) if P else None
@@ -47,6 +52,7 @@ class GraphedDecode:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=side):
             self.codes = self._run()
+        model.set_low_latency(prev_mode)   # the mode is baked into the captured launches
 
     def _run(self):
         from . import _lib as L

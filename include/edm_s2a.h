@@ -63,6 +63,15 @@ int edm_attention(const void* qkv, int B, int N, int H, void* out, void* stream)
 int edm_layernorm(const void* in, int in_is_bf16, int rows, const float* w1, const float* b1, const float* w2,
                   const float* b2, float* y_out, void* z_out, int seq_len, int z_skip, float eps, void* stream);
 
+/* x[M,1024] += scale * bf16(A[M,K] x B[1024,K]^T + bias), then edm_layernorm(x, ...) on the updated rows: a residual branch of the
+ * conformer block and the pre-norm of the next one (conformer.py:229-234 with PreNorm :102-110). splits = 2 or 4 with few rows (the
+ * small-M kernel's regime, M <= 2304): the GEMM runs as that many K ranges whose raw partial sums go to `scratch`
+ * ([splits, M, 1024] fp32) and are added, in range order, by the LayerNorm launch (what a context in low-latency mode does for
+ * single utterances). splits <= 1, scratch NULL or a larger M: edm_gemm_bf16(EDM_EPI_RESID_F32) followed by edm_layernorm. */
+int edm_gemm_resid_layernorm(const void* a, long long lda, const void* b, long long ldb, int M, int K, const float* bias, float* x,
+                             float scale, const float* w1, const float* b1, const float* w2, const float* b2, float* y_out,
+                             void* z_out, int seq_len, int z_skip, float eps, float* scratch, int splits, void* stream);
+
 /* GLU -> depthwise conv (k=5, zero pad 2|2 per sequence) -> Swish -> ChanLayerNorm -> out [B*N,2048] bf16.
  * glu_input != 0: in is [B*N,4096] bf16 (value | gate) and the GLU runs here; glu_input == 0: in is [B*N,2048] bf16 already
  * gated by the pointwise-conv GEMM (EDM_EPI_GLU_BF16), which is what the decoder context uses.
@@ -187,6 +196,13 @@ int edm_s2a_set_batch_offset(edm_s2a_ctx* ctx, long long batch_offset);
  * to (max, arg-max) partials in the epilogue and the [B,12,T,1024] tensor never exists. Changes the workspace layout: query
  * edm_s2a_workspace_bytes and bind again after switching. */
 int edm_s2a_set_keep_logits(edm_s2a_ctx* ctx, int keep);
+
+/* on != 0: single-utterance serving mode. The reference's own call site decodes ONE utterance (inference.py:43-48); with a few hundred
+ * rows every kernel is latency-bound and the long-K residual GEMMs (FeedForward down-projection K = 4096, pointwise-conv-2 K = 2048)
+ * leave most SMs idle, so for <= 512 rows they are split over K (2 or 4 ranges, reduced in a fixed order inside the LayerNorm launch
+ * that follows: deterministic, same bf16 rounding points). The fp32 summation order then differs from the unsplit kernels, i.e. the
+ * rounding noise of a row depends on how many rows are decoded together; with on == 0 (the default) a row's bits never do. */
+int edm_s2a_set_low_latency(edm_s2a_ctx* ctx, int on);
 
 /* Feature-valued prompt injections (the `injections` argument of InjectionConformerWrapper.forward, injection_conformer_wrapper.py:92-131):
  * proj = fp32 [n_injection, B*P, 1024], row (k, b, n) = project_injection[k].0 applied to the caller's cumulative DAC feature of

@@ -206,3 +206,56 @@ def test_sample_and_remask(L):
         diff = mn.bool() != ref
         assert (((conf - cut).abs() < 1e-4) | ~diff).all()
         mask_old = ref
+
+
+@pytest.mark.parametrize("M,K,double_ln,skip,splits", [(150, 4096, False, 0, 4), (150, 2048, False, 0, 4), (600, 4096, True, 0, 2), (400, 4096, True, 50, 2),
+                                                       (1, 4096, False, 0, 4), (150, 1024, False, 0, 1), (3000, 4096, False, 0, 4)])
+def test_gemm_resid_layernorm_split_k(L, M, K, double_ln, skip, splits):
+    """edm_gemm_resid_layernorm with splits > 1: the residual GEMM runs as K ranges and the LayerNorm launch adds their partial sums
+    (conformer.py:229-234 with PreNorm :102-110; the low-latency mode of a context). Against edm_gemm_bf16(EPI_RESID_F32) +
+    edm_layernorm: the residual stream within one bf16 ulp of the GEMM term (the fp32 summation order differs), the LayerNorm output
+    within bf16 rounding, deterministic, rows independent of the other rows of the call. splits = 1 and M = 3000 (beyond the small-M
+    kernel) take the two-launch path inside the entry point and must then match it exactly."""
+    torch.manual_seed(M + K)
+    a = bf(torch.randn(M, K, device=dev))
+    b = bf(torch.randn(1024, K, device=dev) / math.sqrt(K))
+    bias = torch.randn(1024, device=dev)
+    x0 = torch.randn(M, 1024, device=dev) * 3
+    w1, b1, w2, b2 = (torch.randn(1024, device=dev) for _ in range(4))
+    seq = 200 if skip else 1
+    rows_out = M if not skip else (M // seq) * (seq - skip)
+
+    def ln_args(y, z):
+        return (L.ptr(w1), L.ptr(b1), L.ptr(w2) if double_ln else None, L.ptr(b2) if double_ln else None, L.ptr(y) if y is not None else None, L.ptr(z), seq, skip, 1e-5)
+
+    x_ref = x0.clone()
+    gemm(L, a, b, L.EPI_RESID_F32, bias, x_ref, scale=0.5)
+    y_ref = torch.empty_like(x_ref) if double_ln else None
+    z_ref = torch.zeros(rows_out, 1024, device=dev, dtype=torch.bfloat16)
+    L.check(L.lib().edm_layernorm(L.ptr(x_ref), 0, M, *ln_args(y_ref, z_ref), L.stream_ptr()), "layernorm")
+
+    def fused(a_, x_init, rows):
+        x = x_init.clone()
+        z = torch.zeros((rows if not skip else (rows // seq) * (seq - skip)), 1024, device=dev, dtype=torch.bfloat16)
+        scratch = torch.full((4, rows, 1024), float("nan"), device=dev)
+        L.check(L.lib().edm_gemm_resid_layernorm(L.ptr(a_), K, L.ptr(b), K, rows, K, L.ptr(bias), L.ptr(x), 0.5, *ln_args(x if double_ln else None, z),
+                                                 L.ptr(scratch), splits, L.stream_ptr()), "gemm_resid_layernorm")
+        torch.cuda.synchronize()
+        return x, z
+
+    x1, z1 = fused(a, x0, M)
+    x2, z2 = fused(a, x0, M)
+    assert torch.equal(x1, x2) and torch.equal(z1, z2)
+    if splits == 1 or M > 2304:
+        assert torch.equal(z1, z_ref) and torch.equal(x1, y_ref if double_ln else x_ref)
+        return
+    acc = a.float() @ b.float().T
+    if double_ln:
+        torch.testing.assert_close(x1, y_ref, rtol=0, atol=0.06)    # post_norm output (fp32, in place); a bf16 ulp of the GEMM term moves it by O(1e-2)
+    else:
+        assert_bf16_close(x1, x_ref, 0.5 * (acc + bias), ulps=1.0)
+    assert (z1.float() - z_ref.float()).abs().max().item() < 0.08
+    assert ((z1.float() - z_ref.float()).abs() > 0.02).float().mean().item() < 0.01
+    if M >= 256 and not skip:  # the first 128 rows decoded alone (same split) give the same bits
+        xs, zs = fused(a[:128].contiguous(), x0[:128], 128)
+        assert torch.equal(xs, x1[:128]) and torch.equal(zs, z1[:128])
