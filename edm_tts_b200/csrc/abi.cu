@@ -1525,7 +1525,7 @@ struct edm_t2s_ctx {
   // bound workspace
   bool bound = false;
   int max_len = 0;
-  float *x, *y, *logits, *logp, *raw_len;
+  float *x, *y, *logits, *logp, *raw_len, *part = nullptr;
   __nv_bfloat16 *z, *h, *qkv, *att, *g, *zt;
   int *ids, *ids_raw, *tokens, *input_ids, *text;
   uint8_t *full_mask, *mask_a, *mask_b, *mask_raw;
@@ -1577,6 +1577,54 @@ int launch_ln_g(int d, const LnGParams& p, cudaStream_t st) {
   return 0;
 }
 
+// Residual GEMM + the LayerNorm that follows it, text-to-semantic form (any hidden size 128 * NV): with `part` and a K that divides into
+// 2 / 4 ranges of >= 4 k-blocks on few enough tiles, split-K partial sums reduced by layernorm_g_splitk_kernel (see launch_gemm_resid_ln);
+// otherwise the two plain launches. One sequence per decode, so there is no batch-invariance to keep: the split is always taken.
+int launch_gemm_resid_ln_g(int d, const CUtensorMap& ma, const WMap& wm, const GemmParams& p, const LnGParams& ln, float* part, cudaStream_t st) {
+  const int sms = num_sms();
+  const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / kSmBN), num_kb = p.K / kGemmBK;
+  const int pair_tiles = ((p.M + 2 * kGemmBM - 1) / (2 * kGemmBM)) * ((p.N + kGemmBN - 1) / kGemmBN);
+  const bool small = p.N % kGemmBN != 0 || (gemm_small_m() && pair_tiles * 4 <= sms);
+  int splits = 1;
+  if (small && part != nullptr && p.K % kGemmBK == 0 && p.N == d && p.ldo == d && ln.in == p.out && ln.rows == p.M && p.a_k_offset == 0 &&
+      ln.gather == nullptr && ln.row0_override == nullptr && !ln.pre_gelu && p.K >= 768)
+    for (int s = 4; s >= 2 && splits == 1; s >>= 1)
+      if (tiles * s <= sms && num_kb % s == 0 && num_kb / s >= 3) splits = s;
+  if (splits == 1) {
+    if (int rc = launch_gemm(EPI_RESID_F32, ma, wm, p, st)) return rc;
+    return launch_ln_g(d, ln, st);
+  }
+  static DeviceOnce attr_once;
+  if (attr_once.needed()) {
+    EDM_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_small_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmSmemBytes));
+    attr_once.done();
+  }
+  {
+    GemmParams q = p;
+    q.bias = nullptr; q.out = part; q.ldo = d; q.scale = 1.0f; q.reverse = 0;
+    q.splits = splits; q.split_stride = static_cast<long long>(p.M) * d;
+    next_direction();
+    ProfScope prof(PK_GEMM, 2.0 * p.M * p.N * p.K, st);
+    const int work = tiles * splits;
+    launch_pdl(gemm_bf16_tn_small_kernel<EPI_F32>, dim3(work < sms ? work : sms), dim3(kSmThreads), kSmSmemBytes, st, ma, wm.small, q);
+    EDM_LAUNCH_CHECK("gemm_bf16_tn_small (split-K)");
+  }
+  LnGParams l = ln;
+  l.partials = part; l.n_partials = splits; l.partial_stride = static_cast<long long>(p.M) * d; l.lin_bias = p.bias; l.lin_scale = p.scale;
+  l.x_io = static_cast<float*>(p.out);
+  const int grid = (l.rows + 7) / 8;
+  switch (d) {
+    case 128: launch_pdl(layernorm_g_splitk_kernel<1>, dim3(grid), dim3(256), 0, st, l); break;
+    case 256: launch_pdl(layernorm_g_splitk_kernel<2>, dim3(grid), dim3(256), 0, st, l); break;
+    case 384: launch_pdl(layernorm_g_splitk_kernel<3>, dim3(grid), dim3(256), 0, st, l); break;
+    case 512: launch_pdl(layernorm_g_splitk_kernel<4>, dim3(grid), dim3(256), 0, st, l); break;
+    case 1024: launch_pdl(layernorm_g_splitk_kernel<8>, dim3(grid), dim3(256), 0, st, l); break;
+    default: return fail(EDM_ERR_INVALID, "layernorm: hidden %d", d);
+  }
+  EDM_LAUNCH_CHECK("layernorm_g_splitk");
+  return 0;
+}
+
 template <int kC>
 int launch_conv_tiled_t(const ConvModParams& p, cudaStream_t st) {
   static DeviceOnce attr_once;
@@ -1620,13 +1668,14 @@ int t2s_maps(edm_t2s_ctx* c, int M, int hp) {
   return rc;
 }
 
-// One ConformerBlock (conformer/conformer.py:219-235) on M rows of one sequence. In: x (fp32 stream), z = LN_ff1(x). Out: x = pre-post_norm sum.
-int t2s_block_body(edm_t2s_ctx* c, int blk, int M, int H, int hp, const float* rope_cos, const float* rope_sin, cudaStream_t st) {
+// One ConformerBlock (conformer/conformer.py:219-235) on M rows of one sequence. In: x (fp32 stream), z = LN_ff1(x). Out: `post` applied
+// to the block's sum (post_norm + the next block's pre-norm), or x = pre-post_norm sum when post == nullptr (the last block of a stack).
+int t2s_block_body(edm_t2s_ctx* c, int blk, int M, int H, int hp, const float* rope_cos, const float* rope_sin, const LnGParams* post, cudaStream_t st) {
   const int d = c->d, ff = c->ff, C = c->C;
   const BlockMaps& bm = c->bmaps[blk];
   if (int rc = launch_gemm(EPI_SWISH_BF16, c->m_z, bm.ff1_w1, gp(M, ff, d, c->bwf(blk, F_FF1_B1), c->h, ff), st)) return rc;
-  if (int rc = launch_gemm(EPI_RESID_F32, c->m_h, bm.ff1_w2, gp(M, d, ff, c->bwf(blk, F_FF1_B2), c->x, d, 0.5f), st)) return rc;
-  if (int rc = launch_ln_g(d, lng(c->x, M, c->bwf(blk, F_ATTN_LN_W), c->bwf(blk, F_ATTN_LN_B), nullptr, nullptr, nullptr, c->z), st)) return rc;
+  if (int rc = launch_gemm_resid_ln_g(d, c->m_h, bm.ff1_w2, gp(M, d, ff, c->bwf(blk, F_FF1_B2), c->x, d, 0.5f),
+                                      lng(c->x, M, c->bwf(blk, F_ATTN_LN_W), c->bwf(blk, F_ATTN_LN_B), nullptr, nullptr, nullptr, c->z), c->part, st)) return rc;
   {
     GemmParams p = gp(M, 3 * hp, d, nullptr, c->qkv, 3 * hp);
     p.rope_cos = rope_cos; p.rope_sin = rope_sin; p.seq_len = M; p.rope_cols = 2 * hp;
@@ -1634,29 +1683,31 @@ int t2s_block_body(edm_t2s_ctx* c, int blk, int M, int H, int hp, const float* r
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(d / H));
   if (int rc = launch_attention(c->m_qkv, 1, M, H, c->att, 1024, 1024, 2048, st, scale)) return rc;
-  if (int rc = launch_gemm(EPI_RESID_F32, c->m_att, bm.wo, gp(M, d, hp, c->bwf(blk, F_BO), c->x, d, 1.0f), st)) return rc;
-  if (int rc = launch_ln_g(d, lng(c->x, M, c->bwf(blk, F_CONV_LN_W), c->bwf(blk, F_CONV_LN_B), nullptr, nullptr, nullptr, c->z), st)) return rc;
+  if (int rc = launch_gemm_resid_ln_g(d, c->m_att, bm.wo, gp(M, d, hp, c->bwf(blk, F_BO), c->x, d, 1.0f),
+                                      lng(c->x, M, c->bwf(blk, F_CONV_LN_W), c->bwf(blk, F_CONV_LN_B), nullptr, nullptr, nullptr, c->z), c->part, st)) return rc;
   if (int rc = launch_gemm(EPI_GLU_BF16, c->m_z, bm.pw1, gp(M, 2 * C, d, c->bwf(blk, F_PW1_B), c->h, C), st)) return rc;
   {
     ConvModParams p;
     p.in = c->h; p.out = c->g; p.dw_w = c->bwf(blk, F_DW_W); p.dw_b = c->bwf(blk, F_DW_B); p.cln_w = c->bwf(blk, F_CLN_W); p.B = 1; p.N = M;
     if (int rc = launch_conv_tiled(C, p, st)) return rc;
   }
-  if (int rc = launch_gemm(EPI_RESID_F32, c->m_g, bm.pw2, gp(M, d, C, c->bwf(blk, F_PW2_B), c->x, d, 1.0f), st)) return rc;
-  if (int rc = launch_ln_g(d, lng(c->x, M, c->bwf(blk, F_FF2_LN_W), c->bwf(blk, F_FF2_LN_B), nullptr, nullptr, nullptr, c->z), st)) return rc;
+  if (int rc = launch_gemm_resid_ln_g(d, c->m_g, bm.pw2, gp(M, d, C, c->bwf(blk, F_PW2_B), c->x, d, 1.0f),
+                                      lng(c->x, M, c->bwf(blk, F_FF2_LN_W), c->bwf(blk, F_FF2_LN_B), nullptr, nullptr, nullptr, c->z), c->part, st)) return rc;
   if (int rc = launch_gemm(EPI_SWISH_BF16, c->m_z, bm.ff2_w1, gp(M, ff, d, c->bwf(blk, F_FF2_B1), c->h, ff), st)) return rc;
-  if (int rc = launch_gemm(EPI_RESID_F32, c->m_h, bm.ff2_w2, gp(M, d, ff, c->bwf(blk, F_FF2_B2), c->x, d, 0.5f), st)) return rc;
-  return 0;
+  if (post == nullptr) return launch_gemm(EPI_RESID_F32, c->m_h, bm.ff2_w2, gp(M, d, ff, c->bwf(blk, F_FF2_B2), c->x, d, 0.5f), st);
+  return launch_gemm_resid_ln_g(d, c->m_h, bm.ff2_w2, gp(M, d, ff, c->bwf(blk, F_FF2_B2), c->x, d, 0.5f), *post, c->part, st);
 }
 
 // blocks [blk0, blk0 + n) on M rows; x / z prepared by the caller; after the last block x holds the pre-post_norm sum
 int t2s_stack(edm_t2s_ctx* c, int blk0, int n, int M, int H, int hp, const float* rope_cos, const float* rope_sin, cudaStream_t st) {
   for (int i = 0; i < n; ++i) {
     const int blk = blk0 + i;
-    if (int rc = t2s_block_body(c, blk, M, H, hp, rope_cos, rope_sin, st)) return rc;
     if (i + 1 < n) {
       // post_norm of this block fused with the first pre-norm of the next one
-      if (int rc = launch_ln_g(c->d, lng(c->x, M, c->bwf(blk, F_POST_LN_W), c->bwf(blk, F_POST_LN_B), c->bwf(blk + 1, F_FF1_LN_W), c->bwf(blk + 1, F_FF1_LN_B), c->x, c->z), st)) return rc;
+      const LnGParams post = lng(c->x, M, c->bwf(blk, F_POST_LN_W), c->bwf(blk, F_POST_LN_B), c->bwf(blk + 1, F_FF1_LN_W), c->bwf(blk + 1, F_FF1_LN_B), c->x, c->z);
+      if (int rc = t2s_block_body(c, blk, M, H, hp, rope_cos, rope_sin, &post, st)) return rc;
+    } else {
+      if (int rc = t2s_block_body(c, blk, M, H, hp, rope_cos, rope_sin, nullptr, st)) return rc;
     }
   }
   return 0;
@@ -1685,7 +1736,9 @@ size_t t2s_carve(edm_t2s_ctx* c, uint8_t* base, int max_len, bool assign) {
   uint8_t* mask_a = k.take<uint8_t>(M);
   uint8_t* mask_b = k.take<uint8_t>(M);
   uint8_t* mask_raw = k.take<uint8_t>(M);
+  float* part = k.take<float>(4 * M * c->d);   // K-range partial sums of the split-K residual GEMMs
   if (assign) {
+    c->part = part;
     c->x = x; c->y = y; c->z = z; c->h = h; c->qkv = qkv; c->att = att; c->g = g; c->zt = zt; c->logits = logits; c->logp = logp; c->raw_len = raw_len;
     c->ids = ids; c->ids_raw = ids_raw; c->tokens = tokens; c->input_ids = input_ids; c->text = text;
     c->full_mask = full_mask; c->mask_a = mask_a; c->mask_b = mask_b; c->mask_raw = mask_raw;

@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(256, 3) layernorm_kernel(const LnParams p) {
 // on the updated row. The updated row goes back to x_io unless the LayerNorm's fp32 output overwrites it anyway (post_norm in place).
 __global__ void __launch_bounds__(256) layernorm_splitk_kernel(const LnParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  KTRACE_ENTRY(kt_entry);
   pdl_trigger();
   {
     const float* wb[4] = {p.w1, p.b1, p.w2, p.b2};
@@ -196,12 +197,33 @@ __global__ void __launch_bounds__(256) layernorm_splitk_kernel(const LnParams p)
     if (p.lin_bias != nullptr) prefetch_l1(p.lin_bias + (warp * 32 + lane) * 4);
   }
   pdl_wait();
+#ifdef EDM_KTRACE
+  if (threadIdx.x == 0) { KTRACE_PUT(1, kt_entry); KTRACE_PUT(2, ktrace_now()); }
+#endif
   const int row = blockIdx.x * 8 + warp;
   if (row >= p.rows) return;
+  // every load of the row is issued before the first add (one L2 round trip instead of one per K range): 2 or 4 ranges
   float v[32], a[32];
-  row_load_f32(p.partials + static_cast<long long>(row) * kD, lane, a);
-  for (int s = 1; s < p.n_partials; ++s) row_add_f32(p.partials + s * p.partial_stride + static_cast<long long>(row) * kD, lane, a);
-  row_load_f32(p.x_io + static_cast<long long>(row) * kD, lane, v);
+  const float* pr = p.partials + static_cast<long long>(row) * kD;
+  row_load_f32(pr, lane, a);
+  if (p.n_partials == 4) {
+    float b[32], c[32], d[32];
+    row_load_f32(pr + p.partial_stride, lane, b);
+    row_load_f32(pr + 2 * p.partial_stride, lane, c);
+    row_load_f32(pr + 3 * p.partial_stride, lane, d);
+    row_load_f32(p.x_io + static_cast<long long>(row) * kD, lane, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = __fadd_rn(__fadd_rn(__fadd_rn(a[i], b[i]), c[i]), d[i]);
+  } else {
+    float b[32];
+    if (p.n_partials >= 2) row_load_f32(pr + p.partial_stride, lane, b);
+    row_load_f32(p.x_io + static_cast<long long>(row) * kD, lane, v);
+    if (p.n_partials >= 2) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) a[i] = __fadd_rn(a[i], b[i]);
+    }
+    for (int s = 2; s < p.n_partials; ++s) row_add_f32(pr + s * p.partial_stride, lane, a);
+  }
   if (p.lin_bias != nullptr) row_add_f32_ldg(p.lin_bias, lane, a);
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], __fmul_rn(p.lin_scale, bf16_round(a[i])));
@@ -218,6 +240,9 @@ __global__ void __launch_bounds__(256) layernorm_splitk_kernel(const LnParams p)
     if (p.w2 != nullptr) row_layernorm(v, p.w2, p.b2, lane, p.eps);
     row_store_bf16(p.z_out + zrow * kD, lane, v);
   }
+#ifdef EDM_KTRACE
+  if (threadIdx.x == 0) KTRACE_END(4);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ conv module core

@@ -76,6 +76,14 @@ struct LnGParams {
   __nv_bfloat16* z_out;
   float eps;
   int pre_gelu;
+  // layernorm_g_splitk_kernel only (see LnParams in elementwise.cuh): the input row is x_io[row] += lin_scale * bf16(sum of the
+  // n_partials K-range partial sums + lin_bias), written back unless y_out overwrites it
+  const float* partials;
+  int n_partials;
+  long long partial_stride;
+  const float* lin_bias;
+  float lin_scale;
+  float* x_io;
 };
 
 template <int NV>
@@ -101,6 +109,53 @@ __global__ void __launch_bounds__(256) layernorm_g_kernel(const LnGParams p) {
       v[i] = 0.5f * x * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
     }
   }
+  if (p.w1 != nullptr) rowg_layernorm<NV>(v, p.w1, p.b1, lane, p.eps);
+  if (p.y_out != nullptr) rowg_store_f32<NV>(p.y_out + static_cast<long long>(row) * D, lane, v);
+  if (p.z_out != nullptr) {
+    if (p.w2 != nullptr) rowg_layernorm<NV>(v, p.w2, p.b2, lane, p.eps);
+    rowg_store_bf16<NV>(p.z_out + static_cast<long long>(row) * D, lane, v);
+  }
+}
+
+// Residual update + LayerNorm behind a split-K residual GEMM (gemm.cuh GemmParams::splits; the S2A form is layernorm_splitk_kernel):
+// the text-to-semantic model decodes one sequence of a few hundred rows, so its long-K GEMMs (FeedForward down-projection, pointwise
+// conv 2) always run as K ranges; this kernel adds their partial sums in range order, then bias, bf16 rounding, scale, residual add.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_g_splitk_kernel(const LnGParams p) {
+  pdl_sync();
+  constexpr int D = 128 * NV;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= p.rows) return;
+  float v[4 * NV], a[4 * NV];
+  const float* pr = p.partials + static_cast<long long>(row) * D;
+  rowg_load_f32<NV>(pr, lane, a);
+  if (p.n_partials == 4) {
+    float b[4 * NV], c[4 * NV], d[4 * NV];
+    rowg_load_f32<NV>(pr + p.partial_stride, lane, b);
+    rowg_load_f32<NV>(pr + 2 * p.partial_stride, lane, c);
+    rowg_load_f32<NV>(pr + 3 * p.partial_stride, lane, d);
+    rowg_load_f32<NV>(p.x_io + static_cast<long long>(row) * D, lane, v);
+#pragma unroll
+    for (int i = 0; i < 4 * NV; ++i) a[i] = __fadd_rn(__fadd_rn(__fadd_rn(a[i], b[i]), c[i]), d[i]);
+  } else {
+    rowg_load_f32<NV>(p.x_io + static_cast<long long>(row) * D, lane, v);
+    for (int s = 1; s < p.n_partials; ++s) {
+      float b[4 * NV];
+      rowg_load_f32<NV>(pr + s * p.partial_stride, lane, b);
+#pragma unroll
+      for (int i = 0; i < 4 * NV; ++i) a[i] = __fadd_rn(a[i], b[i]);
+    }
+  }
+  if (p.lin_bias != nullptr) {
+    float b[4 * NV];
+    rowg_load_f32<NV>(p.lin_bias, lane, b);
+#pragma unroll
+    for (int i = 0; i < 4 * NV; ++i) a[i] = __fadd_rn(a[i], b[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4 * NV; ++i) v[i] = __fadd_rn(v[i], __fmul_rn(p.lin_scale, bf16_round(a[i])));
+  if (p.y_out != p.x_io) rowg_store_f32<NV>(p.x_io + static_cast<long long>(row) * D, lane, v);
   if (p.w1 != nullptr) rowg_layernorm<NV>(v, p.w1, p.b1, lane, p.eps);
   if (p.y_out != nullptr) rowg_store_f32<NV>(p.y_out + static_cast<long long>(row) * D, lane, v);
   if (p.z_out != nullptr) {

@@ -17,9 +17,11 @@ from edm_tts_b200.config import InjectionConformerConfig  # noqa: E402
 from edm_tts_b200.synthetic import OracleConfig, make_inputs, make_state_dict  # noqa: E402
 
 B, T = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (1, 150)
+LOW_LATENCY = len(sys.argv) > 4 and sys.argv[4] == "low_latency"
 cfg = OracleConfig()
 model = InjectionConformerModel(InjectionConformerConfig(), make_state_dict(cfg, 0), device="cuda")
 sem = make_inputs(B, T, 0, 1, cfg, seed=1)["semantic_tokens"].cuda()
+model.set_low_latency(LOW_LATENCY)
 lib = L.lib()
 lib.edm_ktrace_dump.argtypes = [C.c_void_p, C.c_int]
 lib.edm_ktrace_dump.restype = C.c_int
@@ -30,7 +32,7 @@ model.infer_special(sem, None, None, steps=8, seed=0)
 buf = (C.c_ulonglong * (8 * 4096))()
 n = lib.edm_ktrace_dump(buf, 4096)
 rows = [[buf[8 * i + j] for j in range(8)] for i in range(min(n, 4096))]
-names = {1: "layernorm", 2: "attention", 3: "conv_stream"}
+names = {1: "layernorm", 2: "attention", 3: "conv_stream", 4: "layernorm_splitk"}
 name = lambda k: names.get(k, f"gemm<{k - 100}>")
 print(f"{n} traced launches; first conformer block (times in us relative to the first entry):")
 t0 = rows[1][1]
