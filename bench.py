@@ -499,8 +499,9 @@ def main():
                       "hbm_gbs": 32 * 3000 * (2048 + 96) / (rvq_ms * 1e-3) / 1e9, "frac_hbm": 32 * 3000 * (2048 + 96) / (rvq_ms * 1e-3) / 1e9 / hbm_peak,
                       "fp32_z_ms": rvq_ms_f32, "fp32_z_frames_per_s": 32 * 3000 / (rvq_ms_f32 * 1e-3),
                       "note": "tcgen05 kind::tf32: 3xTF32 projection GEMM (z read once through MN-major TMA boxes) + 12-level search with the "
-                              "[128 frames x 1024 codes] score tiles in TMEM; the search is bound by TMEM traffic (score reads + accumulator writes share the port: "
-                              "0.20 ms floor without any compare work) and the per-score compare work, the projection by the L2->SM fabric, not by HBM"},
+                              "[128 frames x 1024 codes] score tiles in TMEM; the search is bound by the latency of its level-serial pipeline (12 levels x score-tile round "
+                              "trips + level boundary: 0.14 of its 0.24 ms remain without compare work, TMEM reads and 3 of 4 MMAs; DESIGN 7b), then by the "
+                              "per-score compare work; the projection by the L2->SM fabric, not by HBM"},
         "secondary_encode": {"metric": "dac_encode_to_codes_frames_per_s", "value": 32 * 3000 / (enc_ms * 1e-3), "unit": "frames/s", "ms": enc_ms,
                              "workload": "DAC.encode_to_codes, audio [32, 1, 960160] fp32 (32 x 60 s at 16 kHz, dump_tokens batch) -> codes [32, 12, 3000], per GPU",
                              "algorithmic_tflops": 2 * 767.0e3 * 32 * 960160 / (enc_ms * 1e-3) / 1e12,

@@ -703,6 +703,16 @@ extern "C" int edm_rvq_encode_tc(const void* z, int z_is_bf16, int B, int T, int
   sp.B = B; sp.T = T; sp.n_levels = n_levels; sp.e = e_ws; sp.g = g; sp.codes = codes; sp.forced = forced; sp.latents = latents;
   sp.one = 1.0f; sp.onei = 1; sp.n_mma = (g_rvq_scan_probe >> 4) ? (g_rvq_scan_probe >> 4) : 4;
   const int sgrid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
+#ifdef EDM_BRINGUP
+  if ((g_rvq_scan_probe & 3) == 2) {
+    static DeviceOnce once2;
+    if (once2.needed()) {
+      EDM_CUDA(cudaFuncSetAttribute(rvq_search_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRsSmemBytes));
+      once2.done();
+    }
+    rvq_search_kernel<2><<<sgrid, kRsThreads, kRsSmemBytes, st>>>(mcb, sp);
+  } else
+#endif
   if (g_rvq_scan_probe & 1)
     rvq_search_kernel<1><<<sgrid, kRsThreads, kRsSmemBytes, st>>>(mcb, sp);
   else

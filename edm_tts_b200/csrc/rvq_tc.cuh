@@ -345,7 +345,7 @@ __device__ __forceinline__ void rvq_scan32_probe(const uint32_t (&r)[32], RvqBes
   st.best = fmaxf(st.best, __uint_as_float(r[0] ^ r[31]));
 }
 
-template <int kScan>  // 0 = full scan, 1 = bring-up probe (loads only)
+template <int kScan>  // 0 = full scan, 1 = bring-up probe (loads only), 2 = bring-up probe (no loads either)
 __global__ void __launch_bounds__(kRsThreads, 2)
 rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -445,10 +445,15 @@ rvq_search_kernel(const __grid_constant__ CUtensorMap tma_cb, const RvqSearchPar
         mbar_wait(&tfull_bar[buf], (g >> 1) & 1);
         tc_fence_after();
         uint32_t r0[32], r1[32];
-        tmem_ld_32x32(taddr, r0);
-        tmem_ld_32x32(taddr + 32, r1);
-        tmem_ld_wait_dep(r0);
-        tmem_ld_wait_dep(r1);
+        if constexpr (kScan != 2) {
+          tmem_ld_32x32(taddr, r0);
+          tmem_ld_32x32(taddr + 32, r1);
+          tmem_ld_wait_dep(r0);
+          tmem_ld_wait_dep(r1);
+        } else {  // bring-up probe: no TMEM reads at all (what the MMA / barrier pipeline alone costs)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r0[i] = r1[i] = taddr + i;
+        }
         tc_fence_before();
         mbar_arrive(&tempty_bar[buf]);  // the accumulator buffer may be overwritten by chunk g + 2
         if constexpr (kScan == 0) {

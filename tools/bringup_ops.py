@@ -417,10 +417,33 @@ def test_rvqmma():
     q = ResidualVectorQuantize(make_quantizer_state_dict(OracleConfig(), 0))
     z = torch.randn(32, 1024, 3000, device=dev)
     for n_mma in (4, 2, 1):
-        for probe in (0, 1):
+        for probe in (0, 1, 2):
             L.lib().edm_rvq_tc_debug(4096, 512, 1, probe | (n_mma << 4))
             ms = timeit(lambda: q.encode(z), iters=10, warm=3)
-            print(f"rvq search alone, {n_mma} MMAs per chunk, {'loads only' if probe else 'full scan'}: {ms:.3f} ms", flush=True)
+            print(f"rvq search alone, {n_mma} MMAs per chunk, {('full scan', 'TMEM loads only', 'no TMEM loads')[probe]}: {ms:.3f} ms", flush=True)
+    # host cost of one call (no synchronisation): if it is close to the numbers above, those are launch-bound, not device time
+    L.lib().edm_rvq_tc_debug(4096, 512, 1, 2 | (1 << 4))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        q.encode(z)
+    host_ms = (time.perf_counter() - t0) / 20 * 1e3
+    torch.cuda.synchronize()
+    # the same probe replayed from a CUDA graph of 10 calls: device time without any host in the loop
+    res = {}
+    for probe, n_mma in ((0, 4), (1, 4), (2, 4), (2, 1)):
+        L.lib().edm_rvq_tc_debug(4096, 512, 1, probe | (n_mma << 4))
+        s_ = torch.cuda.Stream()
+        with torch.cuda.stream(s_):
+            q.encode(z)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s_):
+            for _ in range(10):
+                q.encode(z)
+        res[(probe, n_mma)] = timeit(g.replay, iters=5, warm=2) / 10
+    print(f"host time per q.encode call {host_ms:.3f} ms; graph-replayed device time per call: full scan {res[(0, 4)]:.3f} ms, TMEM loads only "
+          f"{res[(1, 4)]:.3f}, no TMEM loads {res[(2, 4)]:.3f}, no loads + 1 MMA per chunk {res[(2, 1)]:.3f}", flush=True)
     L.lib().edm_rvq_tc_debug(4096, 512, 0, 0)
 
 
