@@ -207,6 +207,11 @@ __device__ __forceinline__ void gemm_epilogue_rope64(const GemmParams& p, int ro
 // 128 x 64 tiles (N / 64 CTAs per 128 rows: 16-128 CTAs pull the weights concurrently) and an 8-stage ring of 24 KB stages so each
 // CTA keeps 190 KB of loads in flight. Epilogues store from registers ( a 64-column tile is one epilogue
 // sub-tile: GLU pairs and rotary heads never straddle it). The weight tensor map has 64-row boxes (WMap::small in abi.cu).
+// Round 2 (tools/ktrace.py timeline: 2.2 us per kernel boundary, 0.75 us to the first A tile, 250 ns per k-step = the ring's ~2 us
+// round trip / 8 stages): (1) under programmatic dependent launch the producer requests the first ring-full of WEIGHT tiles before
+// griddepcontrol.wait - they are constants - and only the A tiles after it; (2) the epilogue loads its bias / touches its rotary rows
+// before it waits for the accumulator; (3) a work item may be one of `splits` K ranges of a tile (EPI_F32 raw partial sums, reduced in
+// range order by layernorm_splitk_kernel): the long-K residual GEMMs of single-utterance decodes then use 128 instead of 32 CTAs.
 constexpr int kSmBN = 64;
 constexpr int kSmStages = 8;
 constexpr int kSmThreads = 64 + 32 * 4;
