@@ -702,7 +702,8 @@ extern "C" int edm_rvq_encode_tc(const void* z, int z_is_bf16, int B, int T, int
   RvqSearchParams sp;
   sp.B = B; sp.T = T; sp.n_levels = n_levels; sp.e = e_ws; sp.g = g; sp.codes = codes; sp.forced = forced; sp.latents = latents;
   sp.one = 1.0f; sp.onei = 1; sp.n_mma = (g_rvq_scan_probe >> 4) ? (g_rvq_scan_probe >> 4) : 4;
-  const int sgrid = tiles < 2 * num_sms() ? tiles : 2 * num_sms();
+  const int s_ctas = (g_rvq_scan_probe & 8) ? num_sms() : 2 * num_sms();  // bring-up probe: one CTA per SM (how much the two co-resident tiles overlap)
+  const int sgrid = tiles < s_ctas ? tiles : s_ctas;
 #ifdef EDM_BRINGUP
   if ((g_rvq_scan_probe & 3) == 2) {
     static DeviceOnce once2;

@@ -431,7 +431,7 @@ def test_rvqmma():
     torch.cuda.synchronize()
     # the same probe replayed from a CUDA graph of 10 calls: device time without any host in the loop
     res = {}
-    for probe, n_mma in ((0, 4), (1, 4), (2, 4), (2, 1)):
+    for probe, n_mma in ((0, 4), (1, 4), (2, 4), (2, 1), (8, 4), (10, 1)):
         L.lib().edm_rvq_tc_debug(4096, 512, 1, probe | (n_mma << 4))
         s_ = torch.cuda.Stream()
         with torch.cuda.stream(s_):
@@ -443,7 +443,8 @@ def test_rvqmma():
                 q.encode(z)
         res[(probe, n_mma)] = timeit(g.replay, iters=5, warm=2) / 10
     print(f"host time per q.encode call {host_ms:.3f} ms; graph-replayed device time per call: full scan {res[(0, 4)]:.3f} ms, TMEM loads only "
-          f"{res[(1, 4)]:.3f}, no TMEM loads {res[(2, 4)]:.3f}, no loads + 1 MMA per chunk {res[(2, 1)]:.3f}", flush=True)
+          f"{res[(1, 4)]:.3f}, no TMEM loads {res[(2, 4)]:.3f}, no loads + 1 MMA per chunk {res[(2, 1)]:.3f}; one CTA per SM: full scan "
+          f"{res[(8, 4)]:.3f}, no loads + 1 MMA {res[(10, 1)]:.3f}", flush=True)
     L.lib().edm_rvq_tc_debug(4096, 512, 0, 0)
 
 
