@@ -9,6 +9,8 @@ import torch  # noqa: E402
 
 import edm_tts_b200._lib as L  # noqa: E402
 
+if os.environ.get("EDM_AB_LIB"):
+    L.LIB_PATH = os.path.abspath(os.environ["EDM_AB_LIB"])
 lib = L.lib()
 dev = "cuda"
 
@@ -43,4 +45,4 @@ for (N, K, epi) in ((4096, 1024, L.EPI_SWISH_BF16), (1024, 4096, L.EPI_RESID_F32
             for _ in range(20):
                 call()
         res.append(f"M={M}: {timeit(g.replay) / 20 * 1e3:.2f}")
-    print(f"N={N} K={K}: us per GEMM (20 back-to-back in a graph)  " + "  ".join(res), flush=True)
+    print({k: v for k, v in os.environ.items() if k.startswith("EDM_GEMM")}, f"N={N} K={K}: us per GEMM (20 back-to-back in a graph)  " + "  ".join(res), flush=True)
